@@ -1,0 +1,130 @@
+"""Pin the CPU oracle (oracle/) to fixtures produced by the reference's own Python (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import operators as oo
+from oracle import steps as osteps
+from tests import stubs
+from tests.conftest import rel_l2
+
+L1, LP = 16000, 4000
+TOL = 1e-6  # same library calls as the reference on the same CPU -> agreement to fp32 rounding
+
+
+def _loss_grad(op, wav, meas, space):
+    w = wav.clone().requires_grad_(True)
+    pred = op.forward(w)
+    diff = (meas - pred) if space == "wav_form" else (op.transform(meas) - op.transform(pred))
+    loss = torch.linalg.norm(diff)
+    return loss.detach(), torch.autograd.grad(loss, w)[0]
+
+
+def test_masks_bit_exact(golden_ops):
+    kw = dict(audio_length_in_s=10, sample_rate=16000, mask_percentage=0.3, interval_s=1, mask_duration_s=0.1)
+    cases = {
+        "mask_box_10s": dict(mask_type="box", start_inpainting_s=2, end_inpainting_s=3),
+        "mask_boxfrac_10s": dict(mask_type="box", start_inpainting_s=1.37, end_inpainting_s=2.913),
+        "mask_periodic_10s": dict(mask_type="periodic"),
+    }
+    for key, c in cases.items():
+        m = oo.inpaint_mask(**kw, **c)
+        assert np.array_equal(np.packbits(m[0].numpy().astype(np.uint8)), golden_ops[key]), key
+    torch.manual_seed(7)
+    m = oo.inpaint_mask(mask_type="random", **kw)
+    assert np.array_equal(np.packbits(m[0].numpy().astype(np.uint8)), golden_ops["mask_random_seed7_10s"])
+    box = np.unpackbits(golden_ops["mask_box_10s"])[:160000]
+    assert box.sum() == 160000 - 16000 and not box[32000:48000].any()  # SURVEY 8c known answer
+
+
+def test_transforms_and_forwards(golden_ops):
+    wav = stubs.synth_clips(2, L1)
+    mask = oo.inpaint_mask(1, 16000, "box", 0.25, 0.5)
+    assert rel_l2(oo.mel_db(wav), golden_ops["identity_transform"]) < TOL
+    assert rel_l2(oo.a_inpaint(wav, mask), golden_ops["inpaint_forward"]) == 0.0
+    assert rel_l2(oo.mel_db(oo.a_inpaint(wav, mask), clamp=False), golden_ops["inpaint_transform"]) < TOL
+    for s in (2, 10):
+        y = oo.a_superres(wav, 16000, s)
+        assert rel_l2(y, golden_ops[f"superres_forward_s{s}"]) < TOL
+        assert rel_l2(oo.mel_db(y), golden_ops[f"superres_transform_s{s}"]) < TOL
+    mag = oo.a_phase(wav[:, :LP])
+    assert rel_l2(mag, golden_ops["phase_forward"]) < TOL
+    assert rel_l2(oo.phase_mel(mag), golden_ops["phase_transform"]) < TOL
+    for K, decay in ((800, 0.85), (5000, 0.99), (801, 0.9)):
+        torch.manual_seed(100 + K)
+        ir = oo.draw_impulse_response(K, decay)
+        assert np.array_equal(ir.numpy(), golden_ops[f"dereverb_ir_K{K}"])
+        assert rel_l2(oo.a_dereverb(wav, ir), golden_ops[f"dereverb_forward_K{K}"]) < 1e-5
+    torch.manual_seed(5)
+    assert np.array_equal(oo.gaussian_noise(wav[:1, :256], 0.05).numpy(), golden_ops["gaussian_noise_s0.05_seed5"])
+
+
+@pytest.mark.parametrize("space", ["mel_spectrogram", "wav_form"])
+def test_loss_and_grad(golden_ops, space):
+    wav = stubs.synth_clips(1, L1)
+    ref = stubs.synth_clips(1, L1, first=50)
+    mask = oo.inpaint_mask(1, 16000, "box", 0.25, 0.5)
+    ops = {"inpaint": oo.OracleOperator("inpainting", mask=mask),
+           "superres_s2": oo.OracleOperator("super_resolution", scale=2),
+           "superres_s10": oo.OracleOperator("super_resolution", scale=10)}
+    for K in (800, 5000, 801):
+        ops[f"dereverb_K{K}"] = oo.OracleOperator("dereverberation",
+                                                  fixed_ir=torch.from_numpy(golden_ops[f"dereverb_ir_K{K}"]))
+    for name, op in ops.items():
+        l, g = _loss_grad(op, wav, op.forward(ref), space)
+        assert abs(float(l) - float(golden_ops[f"{name}_{space}_loss"])) <= 2e-5 * abs(float(l)), name
+        assert rel_l2(g, golden_ops[f"{name}_{space}_grad"]) < 2e-4, name
+    ph = oo.OracleOperator("phase_retrieval")
+    l, g = _loss_grad(ph, wav[:, :LP], ph.forward(ref[:, :LP]), space)
+    assert abs(float(l) - float(golden_ops[f"phase_{space}_loss"])) <= 2e-5 * abs(float(l))
+    assert rel_l2(g, golden_ops[f"phase_{space}_grad"]) < 2e-4
+
+
+def _step_cases(golden_steps):
+    seen = []
+    for k in golden_steps.files:
+        if k.endswith("|prev"):
+            seen.append(k[:-5])
+    return seen
+
+
+def test_scheduler_constants(golden_steps):
+    base = osteps.make_base(**stubs.MUSICLDM_SCHED)
+    base.set_timesteps(500)
+    assert np.array_equal(base.timesteps.numpy(), golden_steps["timesteps_500"])
+    assert base.timesteps[0] == 999 and base.timesteps[-1] == 1
+    assert np.array_equal(base.alphas_cumprod.numpy(), golden_steps["alphas_cumprod"])
+    assert abs(float(base.final_alpha_cumprod) - 0.99849999) < 1e-7      # SURVEY 8c known answers
+    assert abs(float(base.alphas_cumprod[999]) - 1.4230386e-4) < 1e-10
+
+
+def test_steps_match_reference(golden_steps):
+    vae, voc = stubs.StubVAE(), stubs.StubVocoder()
+    ref_wav = stubs.synth_clips(1, L1, first=50)
+    x, e = stubs.synth_latents(1, 25)
+    mask = oo.inpaint_mask(1, 16000, "box", 0.25, 0.5)
+    ops = {"inpainting": oo.OracleOperator("inpainting", mask=mask),
+           "super_resolution": oo.OracleOperator("super_resolution", scale=2),
+           "phase_retrieval": oo.OracleOperator("phase_retrieval"),
+           "dereverberation": oo.OracleOperator("dereverberation", ir_length=800, decay_factor=0.85),
+           "identity": oo.OracleOperator("identity")}
+    base = osteps.make_base(**stubs.MUSICLDM_SCHED)
+    base.set_timesteps(500)
+    cases = _step_cases(golden_steps)
+    assert len(cases) == 33
+    for key in cases:
+        sched, op_name, space, eta, t = key.split("|")
+        eta, t = float(eta[3:]), int(t[1:])
+        op = ops[op_name]
+        torch.manual_seed(321)
+        meas = op.forward(ref_wav)
+        rate = {"ddim": None, "dps": 5e-4, "mpgd": 0.005, "dsg": 0.08, "diffmusic": 0.08}[sched]
+        gen = torch.Generator().manual_seed(3000)
+        torch.manual_seed(654 + t)
+        o = osteps.reference_step(sched, base, op, e, t, x, eta=eta, ip_guidance_rate=rate, generator=gen,
+                                  measurement=meas, vae=vae, vocoder=voc, original_waveform_length=L1,
+                                  supervised_space=space)
+        assert rel_l2(o.prev_sample, golden_steps[key + "|prev"]) < 5e-6, key
+        assert rel_l2(o.pred_original_sample, golden_steps[key + "|x0"]) < 5e-6, key
+        gl = float(golden_steps[key + "|loss"].ravel()[0])
+        assert abs(float(o.loss.float().ravel()[0]) - gl) <= 1e-5 * max(1.0, abs(gl)), key
