@@ -1,0 +1,127 @@
+// Radix-8 Stockham FFT building blocks shared by the STFT guidance kernel (N = 512 complex, one 1024-point real
+// frame) and the overlap-save RIR convolution kernel (N = 4096 complex, one 8192-point real block).
+//
+// Everything here is `__host__ __device__` and written as *phases*: a phase is executed by every thread of an FFT
+// group with a barrier between phases.  On the GPU the barrier is `bar.sync`; tests/cpu_emul runs the very same
+// phase functions on the host, looping over thread ids, so the index arithmetic is validated without a GPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DM_HD __host__ __device__ __forceinline__
+#else
+#define DM_HD inline
+#endif
+
+namespace dm {
+
+struct cf {
+    float x, y;
+};
+
+DM_HD cf cmul(cf a, cf b) { return cf{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+DM_HD cf cadd(cf a, cf b) { return cf{a.x + b.x, a.y + b.y}; }
+DM_HD cf csub(cf a, cf b) { return cf{a.x - b.x, a.y - b.y}; }
+DM_HD cf cconj(cf a) { return cf{a.x, -a.y}; }
+// multiply by sign*i  (sign = +1: i*a, sign = -1: -i*a)
+template <int SIGN>
+DM_HD cf cmul_i(cf a) {
+    return SIGN > 0 ? cf{-a.y, a.x} : cf{a.y, -a.x};
+}
+
+// shared-memory index padding: one extra word every 8 keeps all Stockham passes (stride-8 / stride-64 scatters)
+// essentially bank-conflict free with split re/im float arrays.
+DM_HD int padi(int i) { return i + (i >> 3); }
+constexpr int padded_len(int n) { return n + (n >> 3) + 8; }
+
+// 8-point DFT in registers: out[q] = sum_r v[r] * exp(SIGN * 2*pi*i * r*q / 8)
+template <int SIGN>
+DM_HD void dft8(cf v[8]) {
+    const float h = 0.70710678118654752440f;
+    cf a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+    cf a1 = cadd(v[1], v[5]), a5 = csub(v[1], v[5]);
+    cf a2 = cadd(v[2], v[6]), a6 = csub(v[2], v[6]);
+    cf a3 = cadd(v[3], v[7]), a7 = csub(v[3], v[7]);
+    // odd branch twiddles w^1, w^2, w^3 with w = exp(SIGN*i*pi/4)
+    a5 = cf{h * (a5.x - SIGN * a5.y), h * (a5.y + SIGN * a5.x)};
+    a6 = cmul_i<SIGN>(a6);
+    a7 = cf{h * (-a7.x - SIGN * a7.y), h * (-a7.y + SIGN * a7.x)};
+    cf b0 = cadd(a0, a2), b2 = csub(a0, a2), b1 = cadd(a1, a3), b3 = cmul_i<SIGN>(csub(a1, a3));
+    cf b4 = cadd(a4, a6), b6 = csub(a4, a6), b5 = cadd(a5, a7), b7 = cmul_i<SIGN>(csub(a5, a7));
+    v[0] = cadd(b0, b1);
+    v[4] = csub(b0, b1);
+    v[2] = cadd(b2, b3);
+    v[6] = csub(b2, b3);
+    v[1] = cadd(b4, b5);
+    v[5] = csub(b4, b5);
+    v[3] = cadd(b6, b7);
+    v[7] = csub(b6, b7);
+}
+
+// One Stockham pass for thread j of N/8.  `load(i)` returns input element i (natural order of the previous pass),
+// `store(i, c)` writes output element i.  tw[m] = exp(-2*pi*i*m/N) (forward table; conjugated for SIGN=+1).
+template <int N, int NS, int SIGN, class Load, class Store>
+DM_HD void stockham_pass(int j, const cf* __restrict__ tw, Load load, Store store) {
+    constexpr int T = N / 8;
+    const int k = j % NS;
+    cf v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = load(j + r * T);
+    if (NS > 1) {
+        constexpr int TWS = N / (NS * 8);
+#pragma unroll
+        for (int r = 1; r < 8; ++r) {
+            cf w = tw[r * k * TWS];
+            if (SIGN > 0) w.y = -w.y;
+            v[r] = cmul(v[r], w);
+        }
+    }
+    dft8<SIGN>(v);
+    const int j0 = (j / NS) * NS * 8 + k;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) store(j0 + q * NS, v[q]);
+}
+
+// Split-array accessors with padding.
+struct PadLoad {
+    const float* re;
+    const float* im;
+    DM_HD cf operator()(int i) const {
+        int p = padi(i);
+        return cf{re[p], im[p]};
+    }
+};
+struct PadStore {
+    float* re;
+    float* im;
+    DM_HD void operator()(int i, cf c) const {
+        int p = padi(i);
+        re[p] = c.x;
+        im[p] = c.y;
+    }
+};
+
+// Real-FFT unpacking for a 2H-point real signal packed as H complex (z[n] = x[2n] + i x[2n+1]); Z = FFT_H(z).
+// For the pair (k, H-k), 1 <= k < H/2:  X[k] = E + T, X[H-k] = conj(E - T) with E = (Z[k]+conj(Z[H-k]))/2,
+// T = W^k * (-i/2) * (Z[k]-conj(Z[H-k])), W = exp(-2*pi*i/(2H)).
+DM_HD void rfft_unpack_pair(cf zk, cf zc, cf w, cf& xk, cf& xc) {
+    cf e = cf{0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y)};
+    cf d = cf{0.5f * (zk.x - zc.x), 0.5f * (zk.y + zc.y)};  // (Z[k] - conj(Z[H-k]))/2
+    cf o = cf{d.y, -d.x};                                    // -i * d
+    cf t = cmul(w, o);
+    xk = cadd(e, t);
+    xc = cconj(csub(e, t));
+}
+// Adjoint / inverse packing: given Y[k], Y[H-k] of a Hermitian half spectrum, Z[k] = A + S, Z[H-k] = conj(A - S)
+// with A = Y[k] + conj(Y[H-k]), S = i * conj(W^k) * (Y[k] - conj(Y[H-k])).  IFFT_H(Z) (unnormalised) then holds
+// x[2n] in re and x[2n+1] in im, where x[n] = Y0 + (-1)^n YH + 2 Re sum_{0<k<H} Y[k] e^{+2 pi i k n/(2H)}.
+DM_HD void irfft_pack_pair(cf yk, cf yc, cf w, cf& zk, cf& zc) {
+    cf a = cf{yk.x + yc.x, yk.y - yc.y};
+    cf b = cf{yk.x - yc.x, yk.y + yc.y};
+    cf vb = cmul(cconj(w), b);
+    cf s = cf{-vb.y, vb.x};  // i * vb
+    zk = cadd(a, s);
+    zc = cconj(csub(a, s));
+}
+
+}  // namespace dm

@@ -1,0 +1,200 @@
+// Per-frame STFT guidance pipeline (one 1024-sample frame handled by a group of 64 threads), as host/device phases.
+//
+//   forward : windowed frame -> 512-pt complex FFT -> X[0..512] -> |X|^2 (or |X|) -> sparse mel -> dB / clamp
+//   residual: d = ref - out ; sum d^2 ; Gbar = -d (the 1/loss factor is applied later, per clip)
+//   backward: melbar -> Pbar[k] (<= 2 mel bands per bin) -> Xbar -> Hermitian pack -> 512-pt inverse FFT
+//             -> frame gradient (still to be multiplied by the window and overlap-added by the caller)
+//
+// Arithmetic restated from torchaudio (functional.spectrogram / MelScale.forward / amplitude_to_DB) as used by
+// diffmusic/inverse_problem/operator.py:24-36,123-124,153-154,162-171 (reference); VJP edge rules follow
+// autograd: clamp passes gradient at equality, |0| has zero gradient.
+#pragma once
+#include <math.h>
+
+#include "fft_core.cuh"
+
+namespace dm {
+
+constexpr int kNfft = 1024;
+constexpr int kH = 512;     // complex FFT size
+constexpr int kBins = 513;  // one-sided bins
+constexpr int kMels = 64;
+constexpr int kGroupThreads = 64;
+
+enum StftMode { kModeMelDb = 0, kModePhaseMel = 1, kModePhaseWav = 2 };
+
+// Device/host constant tables (built on the host by diffmusic_b200/tables.py from torch / torchaudio tensors).
+struct StftTables {
+    const float* window;     // [1024] analysis window (hann periodic, or ones for phase retrieval)
+    const cf* tw512;         // [512]  exp(-2 pi i m / 512)
+    const cf* w1024;         // [257]  exp(-2 pi i k / 1024)
+    const int* mel_kstart;   // [64]   first bin with non-zero weight
+    const int* mel_klen;     // [64]   number of consecutive non-zero bins
+    const float* mel_w;      // [64 * mel_wstride] banded filterbank weights fb[kstart+i, m]
+    int mel_wstride;
+    const int* bin_m0;       // [513]  first mel band touching bin k
+    const float* bin_w0;     // [513]  fb[k, m0]
+    const float* bin_w1;     // [513]  fb[k, m0+1] (0 if none)
+};
+
+// Shared-memory working set of one frame group (all float).
+struct FrameSmem {
+    float* a_re;  // [padded_len(512)]
+    float* a_im;
+    float* b_re;
+    float* b_im;
+    float* x_re;  // [520] spectrum X[0..512]
+    float* x_im;
+    float* p;     // [520] |X|^2 or |X|, later reused for magbar in phase_wav mode
+    float* mel;   // [64]
+    float* melbar;  // [72] (index 64 must read as 0)
+};
+constexpr int kFrameSmemFloats = 4 * padded_len(kH) + 3 * 520 + 64 + 72;
+
+// ---- forward FFT: three Stockham passes. frame[] is the (already masked) signal tile in shared memory. ----
+DM_HD void fwd_pass1(int tid, const StftTables& t, const float* frame, const float* window, FrameSmem s) {
+    auto load = [&](int i) { return cf{frame[2 * i] * window[2 * i], frame[2 * i + 1] * window[2 * i + 1]}; };
+    stockham_pass<kH, 1, -1>(tid, t.tw512, load, PadStore{s.a_re, s.a_im});
+}
+DM_HD void fwd_pass2(int tid, const cf* tw, FrameSmem s) {
+    stockham_pass<kH, 8, -1>(tid, tw, PadLoad{s.a_re, s.a_im}, PadStore{s.b_re, s.b_im});
+}
+DM_HD void fwd_pass3(int tid, const cf* tw, FrameSmem s) {
+    stockham_pass<kH, 64, -1>(tid, tw, PadLoad{s.b_re, s.b_im}, PadStore{s.a_re, s.a_im});
+}
+
+// ---- unpack Z (in a_re/a_im, natural order) to the real-FFT spectrum X and the per-bin energy ----
+template <int MODE>
+DM_HD void fwd_unpack(int tid, const cf* w1024, FrameSmem s) {
+    PadLoad Z{s.a_re, s.a_im};
+    auto put = [&](int k, cf x) {
+        s.x_re[k] = x.x;
+        s.x_im[k] = x.y;
+        float e = x.x * x.x + x.y * x.y;
+        s.p[k] = (MODE == kModeMelDb) ? e : sqrtf(e);
+    };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int k = tid + 64 * i;  // 0..255
+        if (k == 0) {
+            cf z0 = Z(0);
+            put(0, cf{z0.x + z0.y, 0.f});
+            put(kH, cf{z0.x - z0.y, 0.f});
+            cf zq = Z(kH / 2);
+            put(kH / 2, cconj(zq));
+        } else {
+            cf xk, xc;
+            rfft_unpack_pair(Z(k), Z(kH - k), w1024[k], xk, xc);
+            put(k, xk);
+            put(kH - k, xc);
+        }
+    }
+}
+
+// ---- mel projection + dB + clamp + residual (threads 0..63, one mel band each). Returns d^2 (0 if no ref). ----
+// out_val receives the transformed value (what operator.transform returns); melbar gets dLoss_unscaled/dMel.
+template <int MODE>
+DM_HD float mel_residual(int m, const StftTables& t, FrameSmem s, bool clamp, bool has_ref, float ref_val,
+                         float* out_val) {
+    const int k0 = t.mel_kstart[m], n = t.mel_klen[m];
+    const float* w = t.mel_w + m * t.mel_wstride;
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc = fmaf(w[i], s.p[k0 + i], acc);
+    float val, dval_dmel;  // transformed value and its derivative w.r.t. the mel energy
+    if (MODE == kModeMelDb) {
+        float c = fmaxf(acc, 1e-10f);
+        float db = 10.0f * log10f(c);
+        dval_dmel = (acc >= 1e-10f) ? (4.342944819032518f / c) : 0.f;  // 10 / ln(10) / mel
+        val = db;
+        if (clamp) {
+            val = fminf(fmaxf(db, -80.f), 80.f);
+            if (!(db >= -80.f && db <= 80.f)) dval_dmel = 0.f;
+        }
+    } else {  // phase_mel: clamp(mel of magnitude, +-80), no log
+        val = acc;
+        dval_dmel = 1.f;
+        if (clamp) {
+            val = fminf(fmaxf(acc, -80.f), 80.f);
+            if (!(acc >= -80.f && acc <= 80.f)) dval_dmel = 0.f;
+        }
+    }
+    *out_val = val;
+    s.mel[m] = acc;
+    float d = 0.f;
+    if (has_ref) {
+        d = ref_val - val;
+        s.melbar[m] = -d * dval_dmel;
+    }
+    return d * d;
+}
+
+// ---- backward: spectrum cotangent -> Hermitian-packed Z for the inverse FFT (written to b_re/b_im) ----
+// For MODE == kModePhaseWav, s.p[] must already hold magbar[k] = -(ref - |X|) (written by the caller).
+template <int MODE>
+DM_HD cf xbar_of_bin(int k, const StftTables& t, const FrameSmem& s) {
+    cf x = cf{s.x_re[k], s.x_im[k]};
+    float g;
+    if (MODE == kModePhaseWav) {
+        g = s.p[k];
+    } else {
+        int m0 = t.bin_m0[k];
+        g = t.bin_w0[k] * s.melbar[m0] + t.bin_w1[k] * s.melbar[m0 + 1];
+    }
+    float scale;
+    if (MODE == kModeMelDb) {
+        scale = 2.f * g;  // d|X|^2 = 2 X
+    } else {
+        float mag = sqrtf(x.x * x.x + x.y * x.y);
+        scale = mag > 0.f ? g / mag : 0.f;  // d|X| = X/|X|, 0 at X = 0
+    }
+    return cf{scale * x.x, scale * x.y};
+}
+
+template <int MODE>
+DM_HD void bwd_pack(int tid, const StftTables& t, FrameSmem s) {
+    PadStore Zb{s.b_re, s.b_im};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int k = tid + 64 * i;  // 0..255
+        if (k == 0) {
+            float y0 = xbar_of_bin<MODE>(0, t, s).x;     // only the real part of the DC / Nyquist cotangent acts
+            float yh = xbar_of_bin<MODE>(kH, t, s).x;
+            Zb(0, cf{y0 + yh, y0 - yh});
+            cf yq = xbar_of_bin<MODE>(kH / 2, t, s);     // Y[256] = Xbar/2 ; Z[256] = 2 conj(Y)
+            Zb(kH / 2, cf{yq.x, -yq.y});
+        } else {
+            cf yk = xbar_of_bin<MODE>(k, t, s), yc = xbar_of_bin<MODE>(kH - k, t, s);
+            yk = cf{0.5f * yk.x, 0.5f * yk.y};
+            yc = cf{0.5f * yc.x, 0.5f * yc.y};
+            cf zk, zc;
+            irfft_pack_pair(yk, yc, t.w1024[k], zk, zc);
+            Zb(k, zk);
+            Zb(kH - k, zc);
+        }
+    }
+}
+
+// ---- inverse FFT: b -> a -> b -> a ; afterwards frame gradient n is a_re[pad(n/2)] (n even) / a_im (n odd) ----
+DM_HD void inv_pass1(int tid, const cf* tw, FrameSmem s) {
+    stockham_pass<kH, 1, +1>(tid, tw, PadLoad{s.b_re, s.b_im}, PadStore{s.a_re, s.a_im});
+}
+DM_HD void inv_pass2(int tid, const cf* tw, FrameSmem s) {
+    stockham_pass<kH, 8, +1>(tid, tw, PadLoad{s.a_re, s.a_im}, PadStore{s.b_re, s.b_im});
+}
+DM_HD void inv_pass3(int tid, const cf* tw, FrameSmem s) {
+    stockham_pass<kH, 64, +1>(tid, tw, PadLoad{s.b_re, s.b_im}, PadStore{s.a_re, s.a_im});
+}
+DM_HD float frame_grad_sample(const FrameSmem& s, int n) {
+    int p = padi(n >> 1);
+    return (n & 1) ? s.a_im[p] : s.a_re[p];
+}
+
+// reflect padding (center=True, pad_mode="reflect", pad = 512): padded index -> source index
+DM_HD long long reflect_src(long long i, long long len) {
+    long long j = i - 512;
+    if (j < 0) j = -j;
+    if (j >= len) j = 2 * (len - 1) - j;
+    return j;
+}
+
+}  // namespace dm

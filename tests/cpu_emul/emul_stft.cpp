@@ -1,0 +1,101 @@
+// Host emulation of the device phase functions in diffmusic_b200/csrc/{fft_core,stft_frame}.cuh.
+// TEST INFRASTRUCTURE: compiled with g++ by tests/test_cpu_emulation.py; never shipped, never on the product path.
+// Every phase is run for all 64 "threads" of a frame group before the next phase starts (= the GPU barrier).
+#include <cstring>
+#include <vector>
+
+#include "../../diffmusic_b200/csrc/stft_frame.cuh"
+
+using namespace dm;
+
+extern "C" {
+
+// complex FFT of size 512 / 4096 through the Stockham passes (in: interleaved re,im; out likewise)
+void emul_fft(int n, int inverse, const float* tw, const float* in, float* out) {
+    std::vector<float> are(padded_len(n)), aim(padded_len(n)), bre(padded_len(n)), bim(padded_len(n));
+    const cf* t = reinterpret_cast<const cf*>(tw);
+    for (int i = 0; i < n; ++i) { are[padi(i)] = in[2 * i]; aim[padi(i)] = in[2 * i + 1]; }
+    PadLoad la{are.data(), aim.data()}, lb{bre.data(), bim.data()};
+    PadStore sa{are.data(), aim.data()}, sb{bre.data(), bim.data()};
+    const float* rr; const float* ri;
+    if (n == 512) {
+        for (int j = 0; j < 64; ++j) inverse ? stockham_pass<512, 1, 1>(j, t, la, sb) : stockham_pass<512, 1, -1>(j, t, la, sb);
+        for (int j = 0; j < 64; ++j) inverse ? stockham_pass<512, 8, 1>(j, t, lb, sa) : stockham_pass<512, 8, -1>(j, t, lb, sa);
+        for (int j = 0; j < 64; ++j) inverse ? stockham_pass<512, 64, 1>(j, t, la, sb) : stockham_pass<512, 64, -1>(j, t, la, sb);
+        rr = bre.data(); ri = bim.data();
+    } else {
+        for (int j = 0; j < 512; ++j) inverse ? stockham_pass<4096, 1, 1>(j, t, la, sb) : stockham_pass<4096, 1, -1>(j, t, la, sb);
+        for (int j = 0; j < 512; ++j) inverse ? stockham_pass<4096, 8, 1>(j, t, lb, sa) : stockham_pass<4096, 8, -1>(j, t, lb, sa);
+        for (int j = 0; j < 512; ++j) inverse ? stockham_pass<4096, 64, 1>(j, t, la, sb) : stockham_pass<4096, 64, -1>(j, t, la, sb);
+        for (int j = 0; j < 512; ++j) inverse ? stockham_pass<4096, 512, 1>(j, t, lb, sa) : stockham_pass<4096, 512, -1>(j, t, lb, sa);
+        rr = are.data(); ri = aim.data();
+    }
+    for (int i = 0; i < n; ++i) { out[2 * i] = rr[padi(i)]; out[2 * i + 1] = ri[padi(i)]; }
+}
+
+}  // extern "C"
+
+struct EmulTables {
+    const float* window; const float* tw512; const float* w1024;
+    const int* mel_kstart; const int* mel_klen; const float* mel_w; int mel_wstride;
+    const int* bin_m0; const float* bin_w0; const float* bin_w1;
+};
+
+template <int MODE>
+static void run(const EmulTables& e, int clamp, const float* y, long long Ly, int hop, const float* mask,
+                const float* ref, float* out, float* ypbar, double* sumsq) {
+    StftTables t{e.window, reinterpret_cast<const cf*>(e.tw512), reinterpret_cast<const cf*>(e.w1024),
+                 e.mel_kstart, e.mel_klen, e.mel_w, e.mel_wstride, e.bin_m0, e.bin_w0, e.bin_w1};
+    const long long T = 1 + Ly / hop;
+    const int nrow = (MODE == kModePhaseWav) ? kBins : kMels;
+    std::vector<float> buf(kFrameSmemFloats, 0.f), frame(kNfft);
+    float* p = buf.data();
+    FrameSmem s;
+    s.a_re = p; p += padded_len(kH); s.a_im = p; p += padded_len(kH);
+    s.b_re = p; p += padded_len(kH); s.b_im = p; p += padded_len(kH);
+    s.x_re = p; p += 520; s.x_im = p; p += 520; s.p = p; p += 520; s.mel = p; p += 64; s.melbar = p;
+    if (ypbar) std::memset(ypbar, 0, sizeof(float) * (Ly + 1024));
+    double acc = 0.0;
+    for (long long f = 0; f < T; ++f) {
+        for (int n = 0; n < kNfft; ++n) {
+            long long j = reflect_src(f * hop + n, Ly);
+            frame[n] = y[j] * (mask ? mask[j] : 1.f);
+        }
+        for (int tid = 0; tid < 64; ++tid) fwd_pass1(tid, t, frame.data(), t.window, s);
+        for (int tid = 0; tid < 64; ++tid) fwd_pass2(tid, t.tw512, s);
+        for (int tid = 0; tid < 64; ++tid) fwd_pass3(tid, t.tw512, s);
+        for (int tid = 0; tid < 64; ++tid) fwd_unpack<MODE>(tid, t.w1024, s);
+        if (MODE == kModePhaseWav) {
+            for (int k = 0; k < kBins; ++k) {
+                float mag = s.p[k];
+                if (out) out[k * T + f] = mag;
+                if (ref) { float d = ref[k * T + f] - mag; acc += (double)d * d; s.p[k] = -d; }
+            }
+        } else {
+            for (int m = 0; m < 64; ++m) {
+                float v;
+                float d2 = mel_residual<MODE>(m, t, s, clamp != 0, ref != nullptr, ref ? ref[m * T + f] : 0.f, &v);
+                acc += d2;
+                if (out) out[m * T + f] = v;
+            }
+        }
+        if (!ypbar) continue;
+        for (int tid = 0; tid < 64; ++tid) bwd_pack<MODE>(tid, t, s);
+        for (int tid = 0; tid < 64; ++tid) inv_pass1(tid, t.tw512, s);
+        for (int tid = 0; tid < 64; ++tid) inv_pass2(tid, t.tw512, s);
+        for (int tid = 0; tid < 64; ++tid) inv_pass3(tid, t.tw512, s);
+        for (int n = 0; n < kNfft; ++n) ypbar[f * hop + n] += frame_grad_sample(s, n) * t.window[n];
+    }
+    (void)nrow;
+    *sumsq = acc;
+}
+
+extern "C" {
+// y: (Ly,), ref/out: (64 or 513, T) row-major, ypbar: (Ly + 1024,) unscaled padded gradient (d(sum d^2)/2 ... see test)
+void emul_stft_guidance(const EmulTables* e, int mode, int clamp, const float* y, long long Ly, int hop,
+                        const float* mask, const float* ref, float* out, float* ypbar, double* sumsq) {
+    if (mode == 0) run<kModeMelDb>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
+    else if (mode == 1) run<kModePhaseMel>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
+    else run<kModePhaseWav>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
+}
+}

@@ -1,0 +1,182 @@
+"""Run the device phase functions (diffmusic_b200/csrc/{fft_core,stft_frame}.cuh) on the HOST, thread by thread,
+and compare with the oracle.  This validates the FFT index math, real-FFT pack/unpack, sparse mel tables and the
+hand-derived VJP before any GPU time is spent; the CUDA kernels call exactly these functions."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from diffmusic_b200 import tables
+from oracle import operators as oo
+from tests import stubs
+from tests.conftest import rel_l2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class EmulTables(C.Structure):
+    _fields_ = [("window", C.c_void_p), ("tw512", C.c_void_p), ("w1024", C.c_void_p), ("mel_kstart", C.c_void_p),
+                ("mel_klen", C.c_void_p), ("mel_w", C.c_void_p), ("mel_wstride", C.c_int), ("bin_m0", C.c_void_p),
+                ("bin_w0", C.c_void_p), ("bin_w1", C.c_void_p)]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    d = tempfile.mkdtemp(prefix="dm_emul_")
+    so = os.path.join(d, "libdm_emul.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tests", "cpu_emul", "emul_stft.cpp")])
+    return C.CDLL(so)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _tables(window):
+    keep = {}
+    keep["window"] = window.numpy().copy()
+    keep["tw512"] = tables.twiddles(512).numpy().copy()
+    keep["w1024"] = tables.half_twiddles(1024).numpy().copy()
+    mt = tables.mel_tables(tables.mel_filterbank(16000))
+    for k, v in mt.items():
+        keep[k] = v.numpy().copy()
+    t = EmulTables(_ptr(keep["window"]), _ptr(keep["tw512"]), _ptr(keep["w1024"]), _ptr(keep["mel_kstart"]),
+                   _ptr(keep["mel_klen"]), _ptr(keep["mel_w"]), tables.MEL_WSTRIDE, _ptr(keep["bin_m0"]),
+                   _ptr(keep["bin_w0"]), _ptr(keep["bin_w1"]))
+    return t, keep
+
+
+def test_tables_match_reference_constants(golden_ops):
+    assert np.array_equal(tables.hann_window().numpy(), golden_ops["hann_window"])
+    fb = tables.mel_filterbank(16000)
+    ref = np.zeros(tuple(golden_ops["fb_shape"]), np.float32)
+    idx = golden_ops["fb_idx"]
+    ref[idx[:, 0], idx[:, 1]] = golden_ops["fb_val"]
+    assert np.array_equal(fb.numpy(), ref)
+    assert len(golden_ops["fb_val"]) == 1000  # SURVEY 8c known answer
+    mt = tables.mel_tables(fb)
+    assert int(mt["mel_klen"].max()) <= 41
+    # the sparse tables rebuild the dense matrix exactly
+    dense = np.zeros_like(ref)
+    for m in range(64):
+        k0, n = int(mt["mel_kstart"][m]), int(mt["mel_klen"][m])
+        dense[k0:k0 + n, m] = mt["mel_w"][m, :n].numpy()
+    assert np.array_equal(dense, ref)
+    dense2 = np.zeros_like(ref)
+    for k in range(513):
+        m0 = int(mt["bin_m0"][k])
+        dense2[k, m0] += float(mt["bin_w0"][k])
+        if float(mt["bin_w1"][k]) != 0:
+            dense2[k, m0 + 1] += float(mt["bin_w1"][k])
+    assert np.array_equal(dense2, ref)
+    for s in (2, 10):
+        k, width, orig, new = tables.sinc_resample_kernel(16000, 16000 // s)
+        assert np.array_equal(k.numpy(), golden_ops[f"resample_kernel_s{s}"][:, 0, :])
+        assert width == int(golden_ops[f"resample_width_s{s}"]) and (orig, new) == (s, 1)
+
+
+@pytest.mark.parametrize("n", [512, 4096])
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_stockham_fft(emul, n, inverse):
+    rng = np.random.default_rng(n + inverse)
+    z = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    tw = tables.twiddles(n).numpy().copy()
+    inp = np.stack([z.real, z.imag], 1).astype(np.float32).copy()
+    out = np.zeros_like(inp)
+    emul.emul_fft(n, inverse, _ptr(tw), _ptr(inp), _ptr(out))
+    got = out[:, 0] + 1j * out[:, 1]
+    want = np.fft.ifft(z.astype(np.complex128)) * n if inverse else np.fft.fft(z.astype(np.complex128))
+    assert rel_l2(np.stack([got.real, got.imag]), np.stack([want.real, want.imag])) < 5e-7
+
+
+def _run(emul, mode, clamp, y, hop, window, ref=None, mask=None, grad=True):
+    t, keep = _tables(window)
+    Ly = y.shape[0]
+    T = 1 + Ly // hop
+    rows = 513 if mode == 2 else 64
+    out = np.zeros((rows, T), np.float32)
+    ypbar = np.zeros(Ly + 1024, np.float32)
+    ss = C.c_double(0)
+    y = np.ascontiguousarray(y, np.float32)
+    refp = _ptr(np.ascontiguousarray(ref, np.float32)) if ref is not None else None
+    refk = np.ascontiguousarray(ref, np.float32) if ref is not None else None
+    maskk = np.ascontiguousarray(mask, np.float32) if mask is not None else None
+    emul.emul_stft_guidance(C.byref(t), mode, clamp, _ptr(y), C.c_longlong(Ly), hop,
+                            _ptr(maskk) if maskk is not None else None,
+                            _ptr(refk) if refk is not None else None, _ptr(out),
+                            _ptr(ypbar) if grad else None, C.byref(ss))
+    del refp
+    return out, ypbar, ss.value
+
+
+def _fold(ypbar, L):
+    g = np.zeros(L, np.float64)
+    idx = np.arange(L + 1024) - 512
+    idx = np.abs(idx)
+    idx = np.where(idx >= L, 2 * (L - 1) - idx, idx)
+    np.add.at(g, idx, ypbar.astype(np.float64))
+    return g
+
+
+def _torch_loss_grad(op, wav, meas, space):
+    w = wav.clone().requires_grad_(True)
+    pred = op.forward(w)
+    diff = (meas - pred) if space == "wav_form" else (op.transform(meas) - op.transform(pred))
+    loss = torch.linalg.norm(diff)
+    return float(loss), torch.autograd.grad(loss, w)[0][0].numpy()
+
+
+@pytest.mark.parametrize("L", [4000, 4173])
+def test_mel_db_guidance(emul, L):
+    wav = stubs.synth_clips(1, L)
+    ref_wav = stubs.synth_clips(1, L, first=50)
+    for clamp, kind in ((1, "identity"), (0, "inpainting")):
+        mask = oo.inpaint_mask(1, L, "box", 0.25, 0.5) if kind == "inpainting" else None
+        op = oo.OracleOperator(kind, mask=mask)
+        ref_mel = op.transform(op.forward(ref_wav))
+        out, ypbar, ss = _run(emul, 0, clamp, wav[0].numpy(), 160, tables.hann_window(),
+                              ref=ref_mel[0].numpy(), mask=None if mask is None else mask[0].numpy())
+        assert rel_l2(out, op.transform(op.forward(wav))[0]) < 2e-5
+        loss, g = _torch_loss_grad(op, wav, op.forward(ref_wav), "mel_spectrogram")
+        assert abs(np.sqrt(ss) - loss) < 1e-4 * loss
+        got = _fold(ypbar, L) / np.sqrt(ss)
+        if mask is not None:
+            got = got * mask[0].numpy()
+        assert rel_l2(got, g) < 1e-4
+
+
+def test_mel_db_quiet_signal_edges(emul):
+    """amin floor (1e-10) and the -80 dB clamp both active."""
+    L = 4000
+    wav = stubs.synth_clips(1, L) * 3e-5
+    ref_wav = stubs.synth_clips(1, L, first=50)
+    op = oo.OracleOperator("identity")
+    out, ypbar, ss = _run(emul, 0, 1, wav[0].numpy(), 160, tables.hann_window(), ref=op.transform(ref_wav)[0].numpy())
+    want = op.transform(wav)[0]
+    assert float((want == -80).float().mean()) > 0.2
+    assert np.abs(out - want.numpy()).max() < 2e-3
+    loss, g = _torch_loss_grad(op, wav, ref_wav, "mel_spectrogram")
+    assert rel_l2(_fold(ypbar, L) / np.sqrt(ss), g) < 2e-4
+
+
+@pytest.mark.parametrize("space", ["mel_spectrogram", "wav_form"])
+def test_phase_guidance(emul, space):
+    L = 4000
+    wav = stubs.synth_clips(1, L)
+    ref_wav = stubs.synth_clips(1, L, first=50)
+    op = oo.OracleOperator("phase_retrieval")
+    meas = op.forward(ref_wav)
+    if space == "mel_spectrogram":
+        out, ypbar, ss = _run(emul, 1, 1, wav[0].numpy(), 160, tables.rect_window(), ref=op.transform(meas)[0].numpy())
+        assert rel_l2(out, op.transform(op.forward(wav))[0]) < 2e-5
+    else:
+        out, ypbar, ss = _run(emul, 2, 0, wav[0].numpy(), 160, tables.rect_window(), ref=meas[0].numpy())
+        assert rel_l2(out, op.forward(wav)[0]) < 2e-5
+    loss, g = _torch_loss_grad(op, wav, meas, space)
+    assert abs(np.sqrt(ss) - loss) < 1e-4 * loss
+    assert rel_l2(_fold(ypbar, L) / np.sqrt(ss), g) < 1e-4
