@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- guided denoising steps/s on 10 s clips (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3|cfg4]
+
+A *step* is one pass of the guidance hot path over one batch of synthetic clips: `scheduler.step(...)` of the
+host-side mirror = x0 kernel -> (torch stand-ins for vae.decode / vocoder, which stay in PyTorch) -> fused operator +
+T_mel + loss + VJP kernels -> torch autograd back through the stand-ins -> fused scheduler-update kernel.
+Default workload = BASELINE.json configs[1]: super_resolution (scale 2) + DPS, batch 16 x 10 s @ 16 kHz on one B200.
+
+  value : clip-steps/s with inputs resident in HBM (CUDA events per step, L2 flushed between steps, max over ranks)
+  e2e   : the same through the public `.step` API with PINNED HOST latents in and prev_sample + loss out, the
+          host<->device copies inside the timed region
+  roofline     : dominant kernel (stft_guidance_kernel), algorithmic bytes / CUDA-event time, vs MEASURED_PEAKS hbm_gbs
+  cpu_baseline : the CPU oracle (torch restatement of the reference's scheduler.step) on this box's host cores, on a
+                 bounded sample of the same workload
+`--impl reference` times that CPU oracle alone, with every host thread, and prints the same line with impl=reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tests import stubs  # noqa: E402  (synthetic inputs + torch stand-ins for the networks that stay in PyTorch)
+
+L10 = 160000
+WORKLOADS = {
+    # name: (scheduler, operator, batch per GPU, eta, rate, description)
+    "cfg1": ("ddim", "inpainting", 1, 0.0, None, "music_inpainting box[2s,3s) + DDIM, 1 x 10 s clip"),
+    "cfg2": ("dps", "super_resolution", 16, 0.0, 5e-4, "super_resolution scale 2 + DPS, 16 x 10 s clips per GPU"),
+    "cfg3": ("dsg", "phase_retrieval", 8, 1.0, 0.08, "phase_retrieval |STFT| + DSG, 8 x 10 s clips per GPU"),
+    "cfg4": ("diffmusic", "dereverberation", 16, 1.0, 0.08, "dereverberation K=5000 + DiffMusic, 16 x 10 s per GPU"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle-reason samples while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_case(workload, device, first_clip=0, batch=None):
+    import diffmusic_b200 as dm
+    sched_name, op_name, B, eta, rate, _ = WORKLOADS[workload]
+    B = batch or B
+    noiser = dm.get_noiser("gaussian", 0.0)
+    if op_name == "inpainting":
+        op = dm.MusicInpaintingOperator(10, 16000, "box", 2, 3, 0.3, 0.1, 1, noiser=noiser)
+    elif op_name == "super_resolution":
+        op = dm.SuperResolutionOperator(16000, scale=2, noiser=noiser)
+    elif op_name == "phase_retrieval":
+        op = dm.PhaseRetrievalOperator(1024, 160, 1024, noiser=noiser)
+    else:
+        op = dm.MusicDereverberationOperator(ir_length=5000, decay_factor=0.99, noiser=noiser)
+    sched = dm.get_scheduler(sched_name)(operator=op, **stubs.MUSICLDM_SCHED)
+    sched.set_timesteps(500)
+    torch.manual_seed(0)
+    meas = op.forward(stubs.synth_clips(1, L10, first=50).to(device))
+    x, e = stubs.synth_latents(B, 250, first=first_clip)
+    vae, voc = stubs.StubVAE().to(device), stubs.StubVocoder().to(device)
+    kw = dict(eta=eta, measurement=meas, vae=vae, vocoder=voc, original_waveform_length=L10)
+    if rate is not None:
+        kw.update(ip_guidance_rate=rate, supervised_space="mel_spectrogram")
+    return sched, op, x, e, kw, B
+
+
+def cpu_oracle_rate(workload, clips, steps, warmup, threads):
+    """clip-steps/s of the CPU oracle (restated reference scheduler.step, torch CPU) on `clips` clips per step."""
+    from oracle import operators as oo
+    from oracle import steps as osteps
+    torch.set_num_threads(threads)
+    sched_name, op_name, _, eta, rate, _ = WORKLOADS[workload]
+    if op_name == "inpainting":
+        op = oo.OracleOperator("inpainting", mask=oo.inpaint_mask(10, 16000, "box", 2, 3))
+    elif op_name == "super_resolution":
+        op = oo.OracleOperator("super_resolution", scale=2)
+    elif op_name == "phase_retrieval":
+        op = oo.OracleOperator("phase_retrieval")
+    else:
+        op = oo.OracleOperator("dereverberation", ir_length=5000, decay_factor=0.99)
+    base = osteps.make_base(**stubs.MUSICLDM_SCHED)
+    base.set_timesteps(500)
+    torch.manual_seed(0)
+    meas = op.forward(stubs.synth_clips(1, L10, first=50))
+    x, e = stubs.synth_latents(clips, 250)
+    vae, voc = stubs.StubVAE(), stubs.StubVocoder()
+    ts = [999, 501, 1]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        osteps.per_clip_step(sched_name, base, op, e, ts[i % 3], x, generators=stubs.step_generators(clips),
+                             measurement=meas, eta=eta, ip_guidance_rate=rate, vae=vae, vocoder=voc,
+                             original_waveform_length=L10, supervised_space="mel_spectrogram")
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return clips / statistics.mean(times), statistics.mean(times)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    clips = 2 if WORKLOADS[args.workload][1] != "dereverberation" else 1
+    rate, sec = cpu_oracle_rate(args.workload, clips, args.steps, min(args.warmup, 1), threads)
+    sample = f"{clips} clip(s) per step of the same workload, {args.steps} steps, oracle per_clip_step on CPU"
+    line = {"impl": "reference", "metric": "guided denoising steps/s (10 s clips)", "value": rate,
+            "unit": "clip-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload][5], "name": args.workload},
+            "cpu_baseline": {"value": rate, "unit": "clip-steps/s", "cores": threads, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": rate, "unit": "clip-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from diffmusic_b200 import _lib
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    sched, op, x_h, e_h, kw, B = build_case(args.workload, device, first_clip=rank * 64)
+    x_d, e_d = x_h.to(device), e_h.to(device)
+    x_pin, e_pin = x_h.pin_memory(), e_h.pin_memory()
+    prev_pin = torch.empty_like(x_h).pin_memory()
+    loss_pin = torch.empty(B).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=device, dtype=torch.float32)  # 256 MB > 126 MB L2
+    ts = [int(t) for t in sched.timesteps[: args.steps + args.warmup]]
+    gens = stubs.step_generators(B, first=rank * 64, device=device) if kw["eta"] > 0 else None
+
+    # event pair around the dominant kernel (dm_stft_guidance), on the launching stream
+    dom_events = []
+    orig_call = _lib.call
+
+    def timed_call(name, *a):
+        if name == "dm_stft_guidance" and timed_call.on:
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            orig_call(name, *a)
+            t.record()
+            dom_events.append((s, t))
+        else:
+            orig_call(name, *a)
+
+    timed_call.on = False
+    _lib.call = timed_call
+    import diffmusic_b200.operators as _ops_mod
+    import diffmusic_b200.schedulers as _sch_mod
+    _ops_mod._lib.call = timed_call
+    _sch_mod._lib.call = timed_call
+
+    def one_step(i, host):
+        if host:
+            xs, es = x_pin.to(device, non_blocking=True), e_pin.to(device, non_blocking=True)
+        else:
+            xs, es = x_d, e_d
+        out = sched.step(es, ts[i % len(ts)], xs, generator=gens, **kw)
+        if host:
+            prev_pin.copy_(out.prev_sample, non_blocking=True)
+            loss_pin.copy_(out.loss_per_clip, non_blocking=True)
+        return out
+
+    def timed_region(host):
+        per_step = []
+        for i in range(args.warmup):
+            one_step(i, host)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        timed_call.on = not host
+        launches0 = _lib.launch_count()
+        for i in range(args.steps):
+            flush.fill_(float(i))  # evict L2 between timed iterations (not timed)
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            one_step(args.warmup + i, host)
+            t.record()
+            per_step.append((s, t))
+        torch.cuda.synchronize()
+        timed_call.on = False
+        launches = _lib.launch_count() - launches0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = sum(s.elapsed_time(t) for s, t in per_step)
+        tt = torch.tensor([total_ms], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), launches
+
+    with ClockSampler(local) as clk:
+        total_ms, launches = timed_region(host=False)
+        dom_ms = [s.elapsed_time(t) for s, t in dom_events]
+        e2e_ms, _ = timed_region(host=True)
+    clocks = clk.summary()
+
+    if rank == 0:
+        ms_step = total_ms / args.steps
+        value = world * B / (ms_step * 1e-3)
+        e2e_value = world * B / (e2e_ms / args.steps * 1e-3)
+        # algorithmic bytes of the dominant kernel per launch: signal in + reference mel in + padded
+        # cotangent out, per clip, times the clips of one launch
+        op_name = WORKLOADS[args.workload][1]
+        Ly = {"super_resolution": L10 // 2, "dereverberation": L10 + 1}.get(op_name, L10)
+        T = 1 + Ly // 160
+        rows = 64
+        bytes_launch = B * (4 * Ly + 4 * rows * T + 4 * (Ly + 1024))
+        peak, peak_src = peaks()
+        dom = statistics.mean(dom_ms) if dom_ms else None
+        achieved = bytes_launch / (dom * 1e-3) / 1e9 if dom else None
+        roofline = {"bound": "hbm", "kernel": "stft_guidance_kernel", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                    "bytes_per_launch": bytes_launch, "ms_per_launch": dom, "launches_timed": len(dom_ms),
+                    "peak_source": peak_src,
+                    "note": "compute/shared-memory bound FFT kernel: algorithmic HBM bytes are the floor, see DESIGN.md"}
+        line = {"metric": "guided denoising steps/s (10 s clips)", "value": value, "unit": "clip-steps/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOADS[args.workload][5], "name": args.workload, "clips_per_gpu": B,
+                           "l2": "flushed between timed steps (256 MB write)",
+                           "networks": "torch stand-ins for vae.decode / vocoder (stay in PyTorch, inside the step)"},
+                "e2e": {"value": e2e_value, "unit": "clip-steps/s", "h2d_bytes_per_step": 2 * x_h.numel() * 4,
+                        "d2h_bytes_per_step": x_h.numel() * 4 + B * 4, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            clips = 2 if op_name != "dereverberation" else 1
+            rate, sec = cpu_oracle_rate(args.workload, clips, 3, 1, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "clip-steps/s", "cores": threads, "kind": "port",
+                                    "sample": f"{clips} clip(s) x 3 steps of the same workload through the CPU oracle "
+                                              f"(oracle/steps.py per_clip_step), {sec:.2f} s per step"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,85 @@
+// Shared host-side helpers for the C ABI: error string, launch accounting, argument checks.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/dm_abi.h"
+
+namespace dm {
+
+extern thread_local char g_err[512];
+extern std::atomic<unsigned long long> g_launches;
+
+template <typename... A>
+inline int fail(int code, const char* fmt, A... a) {
+    snprintf(g_err, sizeof(g_err), fmt, a...);
+    return code;
+}
+
+#define DM_REQUIRE(cond)                                                                                   \
+    do {                                                                                                   \
+        if (!(cond)) return dm::fail(DM_ERR_INVALID, "%s: requirement failed: %s", __func__, #cond);       \
+    } while (0)
+
+// call after every kernel launch: counts it and turns a launch error into a return code
+#define DM_LAUNCHED()                                                                                      \
+    do {                                                                                                   \
+        dm::g_launches.fetch_add(1, std::memory_order_relaxed);                                            \
+        cudaError_t e__ = cudaGetLastError();                                                              \
+        if (e__ != cudaSuccess)                                                                            \
+            return dm::fail(DM_ERR_CUDA, "%s: kernel launch failed: %s", __func__, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define DM_CUDA(call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return dm::fail(DM_ERR_CUDA, "%s: %s failed: %s", __func__, #call, cudaGetErrorString(e__));   \
+    } while (0)
+
+inline cudaStream_t as_stream(dm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ---- device helpers ----
+#if defined(__CUDACC__)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Deterministic per-clip scale from the per-tile partial sums of squared residuals: every CTA of an adjoint kernel
+// recomputes it (<= a few hundred floats, L2 resident) in a fixed order.  loss = sqrt(sum); scale = 1/loss, 0 at 0
+// (torch.linalg.norm backward is masked at 0); NaN / Inf propagate.
+__device__ __forceinline__ float clip_loss(const float* __restrict__ partial, int ntiles, float* smem_scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        double acc = 0.0;
+        for (int i = lane; i < ntiles; i += 32) acc += (double)partial[i];
+        acc = warp_sum(acc);
+        if (lane == 0) smem_scratch[0] = sqrtf((float)acc);
+    }
+    __syncthreads();
+    return smem_scratch[0];
+}
+__device__ __forceinline__ float inv_loss(float loss) { return loss == 0.f ? 0.f : 1.0f / loss; }
+#endif
+
+}  // namespace dm

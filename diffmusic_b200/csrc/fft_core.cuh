@@ -9,8 +9,10 @@
 
 #if defined(__CUDACC__)
 #define DM_HD __host__ __device__ __forceinline__
+#define DM_HDC __host__ __device__ constexpr
 #else
 #define DM_HD inline
+#define DM_HDC constexpr
 #endif
 
 namespace dm {
@@ -32,7 +34,7 @@ DM_HD cf cmul_i(cf a) {
 // shared-memory index padding: one extra word every 8 keeps all Stockham passes (stride-8 / stride-64 scatters)
 // essentially bank-conflict free with split re/im float arrays.
 DM_HD int padi(int i) { return i + (i >> 3); }
-constexpr int padded_len(int n) { return n + (n >> 3) + 8; }
+DM_HDC int padded_len(int n) { return n + (n >> 3) + 8; }
 
 // 8-point DFT in registers: out[q] = sum_r v[r] * exp(SIGN * 2*pi*i * r*q / 8)
 template <int SIGN>

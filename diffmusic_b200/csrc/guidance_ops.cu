@@ -1,0 +1,213 @@
+// Bandwidth-bound pieces of the guidance path: wav-space residual, reflect-fold + mask adjoint, sinc resampling
+// forward / adjoint, noise add.  All coalesced, per-clip reductions through per-chunk partial slots (deterministic).
+#include "dm_common.cuh"
+
+namespace dm {
+
+constexpr int kEwThreads = 256;
+
+// cotangent of the un-padded signal at j from a reflect-padded cotangent (pad = 512 each side)
+__device__ __forceinline__ float fold_at(const float* __restrict__ yp, long long j, long long Ly) {
+    float v = yp[512 + j];
+    if (j >= 1 && j <= 512) v += yp[512 - j];
+    if (j >= Ly - 513 && j <= Ly - 2) v += yp[512 + 2 * (Ly - 1) - j];
+    return v;
+}
+__device__ __forceinline__ float ybar_at(const float* __restrict__ yb, int pad, long long j, long long Ly) {
+    return pad ? fold_at(yb, j, Ly) : yb[j];
+}
+
+// ---------------------------------------------------------------------------------------------------- residual
+__global__ void __launch_bounds__(kEwThreads) residual_wav_kernel(const float* __restrict__ y, long long y_bstride,
+                                                                  long long n, const float* __restrict__ mask,
+                                                                  const float* __restrict__ meas,
+                                                                  long long meas_bstride, float* __restrict__ ybar,
+                                                                  float* __restrict__ partial, int ntiles) {
+    __shared__ float red[kEwThreads / 32];
+    const int b = blockIdx.y;
+    const long long lo = (long long)blockIdx.x * DM_RESID_CHUNK;
+    const long long hi = min(n, lo + DM_RESID_CHUNK);
+    const float* yb = y + (long long)b * y_bstride;
+    const float* mb = meas + (long long)b * meas_bstride;
+    float* ob = ybar + (long long)b * n;
+    float s = 0.f;
+    for (long long i = lo + threadIdx.x; i < hi; i += kEwThreads) {
+        float v = yb[i];
+        if (mask) v *= __ldg(mask + i);
+        float d = mb[i] - v;
+        ob[i] = -d;
+        s = fmaf(d, d, s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < kEwThreads / 32; ++i) t += red[i];
+        partial[(long long)b * ntiles + blockIdx.x] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- fold adjoint
+__global__ void __launch_bounds__(kEwThreads) fold_adjoint_kernel(const float* __restrict__ ybar, int pad,
+                                                                  long long Ly, const float* __restrict__ mask,
+                                                                  const float* __restrict__ partial, int ntiles,
+                                                                  float* __restrict__ dwav, long long dwav_bstride,
+                                                                  float* __restrict__ loss) {
+    __shared__ float scratch[2];
+    const int b = blockIdx.y;
+    const float l = clip_loss(partial + (long long)b * ntiles, ntiles, scratch);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[b] = l;
+    if (dwav == nullptr) return;  // loss only
+    const float sc = inv_loss(l);
+    const float* yb = ybar + (long long)b * (Ly + 2 * pad);
+    float* ob = dwav + (long long)b * dwav_bstride;
+    const long long lo = (long long)blockIdx.x * (kEwThreads * 8);
+    const long long hi = min(Ly, lo + kEwThreads * 8);
+    for (long long j = lo + threadIdx.x; j < hi; j += kEwThreads) {
+        float v = ybar_at(yb, pad, j, Ly) * sc;
+        if (mask) v *= __ldg(mask + j);
+        ob[j] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- resampling
+__global__ void __launch_bounds__(kEwThreads) resample_fwd_kernel(const float* __restrict__ x, long long x_bstride,
+                                                                  long long L, const float* __restrict__ kernel,
+                                                                  int n_new, int taps, int orig, int width,
+                                                                  float* __restrict__ y, long long Ly) {
+    extern __shared__ float kw[];  // [n_new * taps]
+    for (int i = threadIdx.x; i < n_new * taps; i += kEwThreads) kw[i] = kernel[i];
+    __syncthreads();
+    const int b = blockIdx.y;
+    const float* xb = x + (long long)b * x_bstride;
+    const long long o = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+    if (o >= Ly) return;
+    const long long j = o / n_new;
+    const int ph = (int)(o - j * n_new);
+    const float* w = kw + ph * taps;
+    const long long i0 = (long long)orig * j - width;
+    float acc = 0.f;
+    for (int k = 0; k < taps; ++k) {
+        long long i = i0 + k;
+        if (i >= 0 && i < L) acc = fmaf(xb[i], w[k], acc);
+    }
+    y[(long long)b * Ly + o] = acc;
+}
+
+__global__ void __launch_bounds__(kEwThreads) resample_adjoint_kernel(
+    const float* __restrict__ ybar, int pad, long long Ly, const float* __restrict__ partial, int ntiles,
+    const float* __restrict__ kernel, int n_new, int taps, int orig, int width, float* __restrict__ dwav,
+    long long dwav_bstride, long long L, float* __restrict__ loss) {
+    extern __shared__ float kw[];
+    __shared__ float scratch[2];
+    for (int i = threadIdx.x; i < n_new * taps; i += kEwThreads) kw[i] = kernel[i];
+    const int b = blockIdx.y;
+    const float l = clip_loss(partial + (long long)b * ntiles, ntiles, scratch);  // contains __syncthreads
+    if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[b] = l;
+    const float sc = inv_loss(l);
+    const long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+    if (i >= L) return;
+    const float* yb = ybar + (long long)b * (Ly + 2 * pad);
+    // output blocks j with 0 <= i + width - orig*j < taps
+    const long long num = i + width - taps + 1;
+    const long long jlo = num <= 0 ? 0 : (num + orig - 1) / orig;
+    const long long jhi = (i + width) / orig;
+    float acc = 0.f;
+    for (long long j = jlo; j <= jhi; ++j) {
+        const int k = (int)(i + width - (long long)orig * j);
+        for (int ph = 0; ph < n_new; ++ph) {
+            const long long o = j * n_new + ph;
+            if (o < Ly) acc = fmaf(ybar_at(yb, pad, o, Ly), kw[ph * taps + k], acc);
+        }
+    }
+    dwav[(long long)b * dwav_bstride + i] = acc * sc;
+}
+
+__global__ void __launch_bounds__(kEwThreads) mask_apply_kernel(const float* __restrict__ x, long long x_bstride,
+                                                                long long L, const float* __restrict__ mask,
+                                                                float* __restrict__ y) {
+    const int b = blockIdx.y;
+    const long long stride = (long long)gridDim.x * kEwThreads;
+    for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < L; i += stride)
+        y[(long long)b * L + i] = x[(long long)b * x_bstride + i] * __ldg(mask + i);
+}
+
+__global__ void __launch_bounds__(kEwThreads) add_scaled_kernel(float* __restrict__ y,
+                                                                const float* __restrict__ noise, float sigma,
+                                                                long long n) {
+    const long long stride = (long long)gridDim.x * kEwThreads;
+    for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += stride)
+        y[i] = y[i] + noise[i] * sigma;
+}
+
+}  // namespace dm
+
+using namespace dm;
+
+extern "C" int dm_residual_wav(const float* y, long long y_bstride, long long n, int B, const float* mask,
+                               const float* meas, long long meas_bstride, float* ybar, float* partial,
+                               dm_stream_t stream) {
+    DM_REQUIRE(y && meas && ybar && partial && n > 0 && B > 0);
+    const int ntiles = (int)((n + DM_RESID_CHUNK - 1) / DM_RESID_CHUNK);
+    residual_wav_kernel<<<dim3(ntiles, B), kEwThreads, 0, as_stream(stream)>>>(y, y_bstride, n, mask, meas,
+                                                                               meas_bstride, ybar, partial, ntiles);
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_fold_adjoint(const float* ybar, int pad, long long Ly, int B, const float* mask,
+                               const float* partial, int ntiles, float* dwav, long long dwav_bstride, float* loss,
+                               dm_stream_t stream) {
+    DM_REQUIRE(partial && Ly > 0 && B > 0 && ntiles > 0);
+    DM_REQUIRE((dwav == nullptr && loss != nullptr) || ybar != nullptr);
+    DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 513));
+    const int nblk = dwav ? (int)((Ly + kEwThreads * 8 - 1) / (kEwThreads * 8)) : 1;
+    fold_adjoint_kernel<<<dim3(nblk, B), kEwThreads, 0, as_stream(stream)>>>(ybar, pad, Ly, mask, partial, ntiles,
+                                                                             dwav, dwav_bstride, loss);
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_resample_fwd(const float* x, long long x_bstride, long long L, int B, const float* kernel,
+                               int n_new, int taps, int orig, int width, float* y, long long Ly,
+                               dm_stream_t stream) {
+    DM_REQUIRE(x && kernel && y && L > 0 && B > 0 && Ly > 0);
+    DM_REQUIRE(n_new >= 1 && taps >= 1 && orig >= 1 && width >= 0);
+    DM_REQUIRE((size_t)n_new * taps * sizeof(float) <= 48 * 1024);
+    const int nblk = (int)((Ly + kEwThreads - 1) / kEwThreads);
+    resample_fwd_kernel<<<dim3(nblk, B), kEwThreads, (size_t)n_new * taps * sizeof(float), as_stream(stream)>>>(
+        x, x_bstride, L, kernel, n_new, taps, orig, width, y, Ly);
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
+                                   const float* kernel, int n_new, int taps, int orig, int width, float* dwav,
+                                   long long dwav_bstride, long long L, float* loss, dm_stream_t stream) {
+    DM_REQUIRE(ybar && partial && kernel && dwav && L > 0 && B > 0 && Ly > 0 && ntiles > 0);
+    DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 513));
+    DM_REQUIRE((size_t)n_new * taps * sizeof(float) <= 48 * 1024);
+    const int nblk = (int)((L + kEwThreads - 1) / kEwThreads);
+    resample_adjoint_kernel<<<dim3(nblk, B), kEwThreads, (size_t)n_new * taps * sizeof(float), as_stream(stream)>>>(
+        ybar, pad, Ly, partial, ntiles, kernel, n_new, taps, orig, width, dwav, dwav_bstride, L, loss);
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_mask_apply(const float* x, long long x_bstride, long long L, int B, const float* mask, float* y,
+                             dm_stream_t stream) {
+    DM_REQUIRE(x && mask && y && L > 0 && B > 0);
+    const int nblk = (int)min((long long)num_sms() * 4, (L + kEwThreads - 1) / kEwThreads);
+    mask_apply_kernel<<<dim3(nblk, B), kEwThreads, 0, as_stream(stream)>>>(x, x_bstride, L, mask, y);
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_add_scaled(float* y, const float* noise, float sigma, long long n, dm_stream_t stream) {
+    DM_REQUIRE(y && noise && n > 0);
+    const int nblk = (int)min((long long)num_sms() * 8, (n + kEwThreads - 1) / kEwThreads);
+    add_scaled_kernel<<<nblk, kEwThreads, 0, as_stream(stream)>>>(y, noise, sigma, n);
+    DM_LAUNCHED();
+    return DM_OK;
+}

@@ -1,0 +1,383 @@
+// Fused scheduler updates on the latent.
+//
+// DDIM / DPS / MPGD are pure elementwise passes: 128-bit vectorised, one read of each input, one write of each output.
+// DSG / DiffMusic need per-clip norms: one thread-block CLUSTER (8 CTAs) per clip, partial sums exchanged through
+// distributed shared memory, the data-dependent slerp branch resolved on the device (no host sync) and the second
+// sweep served from L2.  Multiplications / additions are kept un-fused (__fmul_rn/__fadd_rn) where the reference's
+// eager torch ops round after every step, so results track the reference to the last bit or two.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
+#include "dm_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace dm {
+
+constexpr int kThreads = 256;
+constexpr int kCluster = 8;
+
+template <int W>
+struct VecT;
+template <>
+struct VecT<4> {
+    using type = float4;
+};
+template <>
+struct VecT<1> {
+    using type = float;
+};
+
+template <int W>
+__device__ __forceinline__ void ldv(const float* __restrict__ p, long long v, float (&o)[W]) {
+    if (W == 4) {
+        float4 t = reinterpret_cast<const float4*>(p)[v];
+        o[0] = t.x;
+        o[1 % W] = t.y;
+        o[2 % W] = t.z;
+        o[3 % W] = t.w;
+    } else {
+        o[0] = p[v];
+    }
+}
+template <int W>
+__device__ __forceinline__ void stv(float* __restrict__ p, long long v, const float (&o)[W]) {
+    if (W == 4) {
+        reinterpret_cast<float4*>(p)[v] = make_float4(o[0], o[1 % W], o[2 % W], o[3 % W]);
+    } else {
+        p[v] = o[0];
+    }
+}
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float dvd(float a, float b) { return __fdiv_rn(a, b); }
+
+// ------------------------------------------------------------------------------------------------ elementwise
+struct EwParams {
+    const float* x;
+    const float* x0;
+    const float* eps;
+    const float* g0;
+    const float* z;
+    float* prev;
+    float* x0_out;
+    float sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate, clip_range;
+    int clip;
+};
+
+enum EwKind { kX0 = 0, kDdim = 1, kDps = 2, kMpgd = 3 };
+
+template <int KIND, int W>
+__global__ void __launch_bounds__(kThreads) ew_update_kernel(EwParams p, long long nvec) {
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += stride) {
+        float x[W], a[W], g[W], z[W], o[W], o2[W];
+        ldv<W>(p.x, v, x);
+        if (KIND == kX0) {
+            ldv<W>(p.eps, v, a);
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                float t = dvd(sub(x[i], mul(p.sqrt_b, a[i])), p.sqrt_a);
+                if (p.clip) t = fminf(fmaxf(t, -p.clip_range), p.clip_range);
+                o[i] = t;
+            }
+            stv<W>(p.x0_out, v, o);
+        } else {
+            ldv<W>(p.x0, v, a);
+            if (KIND != kDdim) ldv<W>(p.g0, v, g);
+            const bool has_z = (KIND != kDdim) && p.z != nullptr;
+            if (has_z) ldv<W>(p.z, v, z);
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                float x0 = a[i];
+                if (KIND == kMpgd) x0 = sub(x0, mul(p.rate, g[i]));                 // scheduling_mpgd.py:199-200
+                float e = dvd(sub(x[i], mul(p.sqrt_a, x0)), p.sqrt_b);              // noise_pred
+                float prev = add(mul(p.sqrt_p, x0), mul(p.dir_coef, e));
+                if (has_z) prev = add(prev, mul(p.std, z[i]));
+                if (KIND == kDps) prev = sub(prev, mul(p.rate, dvd(g[i], p.sqrt_a)));  // scheduling_dps.py:212-213
+                o[i] = prev;
+                o2[i] = x0;
+            }
+            stv<W>(p.prev, v, o);
+            if (KIND == kMpgd) stv<W>(p.x0_out, v, o2);
+        }
+    }
+}
+
+static bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int KIND>
+static int launch_ew(const EwParams& p, long long n, cudaStream_t st) {
+    const bool vec = (n % 4 == 0) && aligned16(p.x) && aligned16(p.x0) && aligned16(p.eps) && aligned16(p.g0) &&
+                     aligned16(p.z) && aligned16(p.prev) && aligned16(p.x0_out);
+    const long long nvec = vec ? n / 4 : n;
+    const int nblk = (int)std::max<long long>(1, std::min<long long>((nvec + kThreads - 1) / kThreads,
+                                                                      (long long)num_sms() * 8));
+    if (vec)
+        ew_update_kernel<KIND, 4><<<nblk, kThreads, 0, st>>>(p, nvec);
+    else
+        ew_update_kernel<KIND, 1><<<nblk, kThreads, 0, st>>>(p, nvec);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ per-clip norms
+struct NormParams {
+    const float* x0;
+    const float* eps;
+    const float* g0;
+    const float* z;
+    float* prev;
+    long long n_clip;
+    float sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, threshold;
+};
+
+// block-level sum of up to 3 doubles, result broadcast through smem slot `out[0..2]`
+__device__ __forceinline__ void block_sum3(double a, double b, double c, double* wred, double* out) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    c = warp_sum(c);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        wred[warp * 3 + 0] = a;
+        wred[warp * 3 + 1] = b;
+        wred[warp * 3 + 2] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) t += wred[w * 3 + threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+}
+
+// sum the per-CTA slots of every CTA in the cluster through DSMEM, in rank order (deterministic)
+__device__ __forceinline__ void cluster_sum3(cg::cluster_group& cluster, double* slot, double (&tot)[3]) {
+    cluster.sync();  // all slots written
+    tot[0] = tot[1] = tot[2] = 0.0;
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r) {
+        const double* remote = cluster.map_shared_rank(slot, r);
+        tot[0] += remote[0];
+        tot[1] += remote[1];
+        tot[2] += remote[2];
+    }
+}
+
+enum NormKind { kDsg = 0, kDiffMusic = 1 };
+
+template <int KIND, int W>
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) norm_update_kernel(NormParams p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double wred[(kThreads / 32) * 3];
+    __shared__ double slot1[3], slot2[3];
+    const unsigned rank = cluster.block_rank();
+    const long long clip = blockIdx.x / kCluster;
+    const long long nv_clip = p.n_clip / W;
+    const long long chunk = (nv_clip + kCluster - 1) / kCluster;
+    const long long lo = rank * chunk, hi = min(nv_clip, lo + chunk);
+    const long long off = clip * nv_clip;  // in vectors
+    const float kappa_num = p.grad_scale;  // g = (grad_scale * g0) / sqrt_a   (scheduling_dsg.py:210, autograd)
+
+    // ---- sweep 1: |g|^2 (+ |z|^2 and <z, g> for DiffMusic) ----
+    double s_gg = 0.0, s_zz = 0.0, s_gz = 0.0;
+    for (long long v = lo + threadIdx.x; v < hi; v += kThreads) {
+        float g[W], z[W];
+        ldv<W>(p.g0, off + v, g);
+        if (KIND == kDiffMusic) ldv<W>(p.z, off + v, z);
+        float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            float gi = dvd(mul(kappa_num, g[i]), p.sqrt_a);
+            a = fmaf(gi, gi, a);
+            if (KIND == kDiffMusic) {
+                b = fmaf(z[i], z[i], b);
+                c = fmaf(z[i], gi, c);
+            }
+        }
+        s_gg += a;
+        s_zz += b;
+        s_gz += c;
+    }
+    block_sum3(s_gg, s_zz, s_gz, wred, slot1);
+    double t1[3];
+    cluster_sum3(cluster, slot1, t1);
+    const float gn = sqrtf((float)t1[0]);
+
+    float w0 = 0.f, w1 = 0.f, mix_scale = 0.f, zn = 0.f;
+    bool lin = false;
+    if (KIND == kDsg) {
+        // ---- sweep 2: |mix|^2, mix = std z + rate (d* - std z), d* = -r g/(|g|+e)   (scheduling_dsg.py:214-223) ----
+        double s_mm = 0.0;
+        for (long long v = lo + threadIdx.x; v < hi; v += kThreads) {
+            float g[W], z[W];
+            ldv<W>(p.g0, off + v, g);
+            ldv<W>(p.z, off + v, z);
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                float gi = dvd(mul(kappa_num, g[i]), p.sqrt_a);
+                float dstar = dvd(mul(-p.r, gi), add(gn, p.e));
+                float ds = mul(p.std, z[i]);
+                float mix = add(ds, mul(p.rate, sub(dstar, ds)));
+                a = fmaf(mix, mix, a);
+            }
+            s_mm += a;
+        }
+        __syncthreads();  // wred reuse
+        block_sum3(s_mm, 0.0, 0.0, wred, slot2);
+        double t2[3];
+        cluster_sum3(cluster, slot2, t2);
+        mix_scale = add(sqrtf((float)t2[0]), p.e);
+    } else {
+        // ---- slerp weights (scheduling_diffmusic.py:59-68), per clip, on the device ----
+        zn = sqrtf((float)t1[1]);
+        // u = -g/(gn+e) * zn ; |u| = gn/(gn+e) * zn ; cos = <z,u>/(|z||u|) = -<z,g>/(gn zn)   (NaN when gn == 0, as ref)
+        const float c = (float)(-t1[2] / ((double)gn * (double)zn));
+        lin = fabsf(c) > p.threshold;  // data-dependent branch of slerp, resolved here instead of on the host
+        if (!lin) {
+            const float th = acosf(c);
+            const float sn = sinf(th);
+            w0 = dvd(sinf(mul(1.f - p.rate, th)), sn);
+            w1 = dvd(sinf(mul(p.rate, th)), sn);
+        }
+    }
+
+    // ---- final sweep: write prev ----
+    for (long long v = lo + threadIdx.x; v < hi; v += kThreads) {
+        float x0[W], ep[W], g[W], z[W], o[W];
+        ldv<W>(p.x0, off + v, x0);
+        ldv<W>(p.eps, off + v, ep);
+        ldv<W>(p.g0, off + v, g);
+        ldv<W>(p.z, off + v, z);
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            float mean = add(mul(p.sqrt_p, x0[i]), mul(p.dir_coef, ep[i]));
+            float gi = dvd(mul(kappa_num, g[i]), p.sqrt_a);
+            if (KIND == kDsg) {
+                float dstar = dvd(mul(-p.r, gi), add(gn, p.e));
+                float ds = mul(p.std, z[i]);
+                float mix = add(ds, mul(p.rate, sub(dstar, ds)));
+                o[i] = add(mean, dvd(mul(p.r, mix), mix_scale));
+            } else {
+                float u = -mul(dvd(gi, add(gn, p.e)), zn);
+                float m = lin ? add(z[i], mul(p.rate, sub(u, z[i]))) : add(mul(w0, z[i]), mul(w1, u));
+                o[i] = add(mean, mul(p.std, m));
+            }
+        }
+        stv<W>(p.prev, off + v, o);
+    }
+    cluster.sync();  // keep every CTA's shared memory alive until all remote reads are done
+}
+
+template <int KIND>
+static int launch_norm(const NormParams& p, int n_clips, cudaStream_t st) {
+    const bool vec = (p.n_clip % 4 == 0) && aligned16(p.x0) && aligned16(p.eps) && aligned16(p.g0) &&
+                     aligned16(p.z) && aligned16(p.prev);
+    if (vec)
+        norm_update_kernel<KIND, 4><<<n_clips * kCluster, kThreads, 0, st>>>(p);
+    else
+        norm_update_kernel<KIND, 1><<<n_clips * kCluster, kThreads, 0, st>>>(p);
+    return 0;
+}
+
+}  // namespace dm
+
+using namespace dm;
+
+extern "C" int dm_sched_x0(const float* x, const float* eps, float* x0, long long n, float sqrt_a, float sqrt_b,
+                           int clip, float clip_range, dm_stream_t stream) {
+    DM_REQUIRE(x && eps && x0 && n > 0);
+    EwParams p{};
+    p.x = x;
+    p.eps = eps;
+    p.x0_out = x0;
+    p.sqrt_a = sqrt_a;
+    p.sqrt_b = sqrt_b;
+    p.clip = clip;
+    p.clip_range = clip_range;
+    launch_ew<kX0>(p, n, as_stream(stream));
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_sched_ddim_update(const float* x, const float* x0, float* prev, long long n, float sqrt_a,
+                                    float sqrt_b, float sqrt_p, float sqrt_1mp, dm_stream_t stream) {
+    DM_REQUIRE(x && x0 && prev && n > 0);
+    EwParams p{};
+    p.x = x;
+    p.x0 = x0;
+    p.prev = prev;
+    p.sqrt_a = sqrt_a;
+    p.sqrt_b = sqrt_b;
+    p.sqrt_p = sqrt_p;
+    p.dir_coef = sqrt_1mp;
+    launch_ew<kDdim>(p, n, as_stream(stream));
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_sched_dps_update(const float* x, const float* x0, const float* g0, const float* z, float* prev,
+                                   long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std,
+                                   float rate, dm_stream_t stream) {
+    DM_REQUIRE(x && x0 && g0 && prev && n > 0);
+    EwParams p{};
+    p.x = x;
+    p.x0 = x0;
+    p.g0 = g0;
+    p.z = z;
+    p.prev = prev;
+    p.sqrt_a = sqrt_a;
+    p.sqrt_b = sqrt_b;
+    p.sqrt_p = sqrt_p;
+    p.dir_coef = dir_coef;
+    p.std = std;
+    p.rate = rate;
+    launch_ew<kDps>(p, n, as_stream(stream));
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_sched_mpgd_update(const float* x, const float* x0, const float* g0, const float* z, float* prev,
+                                    float* x0_out, long long n, float sqrt_a, float sqrt_b, float sqrt_p,
+                                    float dir_coef, float std, float rate, dm_stream_t stream) {
+    DM_REQUIRE(x && x0 && g0 && prev && x0_out && n > 0);
+    EwParams p{};
+    p.x = x;
+    p.x0 = x0;
+    p.g0 = g0;
+    p.z = z;
+    p.prev = prev;
+    p.x0_out = x0_out;
+    p.sqrt_a = sqrt_a;
+    p.sqrt_b = sqrt_b;
+    p.sqrt_p = sqrt_p;
+    p.dir_coef = dir_coef;
+    p.std = std;
+    p.rate = rate;
+    launch_ew<kMpgd>(p, n, as_stream(stream));
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_sched_dsg_update(const float* x0, const float* eps, const float* g0, const float* z, float* prev,
+                                   int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef,
+                                   float std, float rate, float r, float grad_scale, float e, dm_stream_t stream) {
+    DM_REQUIRE(x0 && eps && g0 && z && prev && n_clips > 0 && n_clip > 0);
+    NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, 0.f};
+    launch_norm<kDsg>(p, n_clips, as_stream(stream));
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_sched_diffmusic_update(const float* x0, const float* eps, const float* g0, const float* z,
+                                         float* prev, int n_clips, long long n_clip, float sqrt_a, float sqrt_p,
+                                         float dir_coef, float std, float rate, float grad_scale, float e,
+                                         float threshold, dm_stream_t stream) {
+    DM_REQUIRE(x0 && eps && g0 && z && prev && n_clips > 0 && n_clip > 0);
+    NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, 0.f, grad_scale, e, threshold};
+    launch_norm<kDiffMusic>(p, n_clips, as_stream(stream));
+    DM_LAUNCHED();
+    return DM_OK;
+}

@@ -1,0 +1,289 @@
+// Fused STFT / mel guidance kernel for sm_100a.
+//
+// One CTA (256 threads = 4 frame groups of 64) owns a tile of consecutive frames of one clip:
+//   * the signal span of the tile is staged once in shared memory (reflect padding, optional inpainting mask);
+//   * each group runs the per-frame pipeline of stft_frame.cuh entirely out of shared memory / registers:
+//     FFT -> |X|^2 -> sparse mel -> dB/clamp -> residual -> VJP -> inverse FFT;
+//   * frame gradients are windowed and overlap-added in shared memory by the whole CTA, in a fixed order;
+//   * the tile's padded-signal cotangent is added to HBM once (tiles overlap by < 1 frame, 2 commutative adds
+//     per address -> bit-reproducible), the tile's sum of squared residuals goes to a per-tile slot.
+// HBM traffic is the algorithmic minimum: signal in, reference mel in, cotangent out.  The spectrum (4.1 MB/clip in
+// the reference's autograd graph) never leaves the SM.
+#include "dm_common.cuh"
+#include "stft_frame.cuh"
+
+namespace dm {
+
+constexpr int kCtaThreads = 256;
+constexpr int kGroups = kCtaThreads / kGroupThreads;
+constexpr int kTileLd = kMels + 1;  // padded row of the ref/out tile
+__host__ __device__ constexpr int tile_floats(int nf) { return (nf * kTileLd + 3) & ~3; }
+
+struct StftParams {
+    StftTables tab;
+    int clamp, hop, B, nf, ntiles;
+    long long Ly, T, y_bstride, ref_bstride;
+    const float* y;
+    const float* mask;
+    const float* ref;
+    const float* noise;
+    float sigma;
+    float* out;
+    float* ypbar;
+    float* partial;
+};
+
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kGroupThreads)); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kCtaThreads) stft_guidance_kernel(const StftParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, g = tid / kGroupThreads, gt = tid % kGroupThreads;
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const long long f0 = (long long)tile * p.nf;
+    const int nfr = (int)min((long long)p.nf, p.T - f0);
+    const int span = (nfr - 1) * p.hop + kNfft;
+    const int span_alloc = (p.nf - 1) * p.hop + kNfft;
+    const long long base = f0 * p.hop;  // first padded-signal index of the tile
+    const bool has_ref = p.ref != nullptr, want_grad = p.ypbar != nullptr;
+
+    // ---- shared memory carve-up ----
+    float* sig = smem;
+    float* acc = sig + span_alloc;
+    float* tilebuf = acc + span_alloc;                    // [nf][kTileLd] ref (guidance) or out (transform)
+    float* win = tilebuf + tile_floats(p.nf);                // [1024]
+    cf* tw = reinterpret_cast<cf*>(win + kNfft);          // [512]
+    cf* w1024 = tw + kH;                                  // [257] (+3 pad)
+    float* grp = reinterpret_cast<float*>(w1024 + 260);
+    float* red = grp + kGroups * kFrameSmemFloats;        // [8]
+    FrameSmem s;
+    {
+        float* q = grp + g * kFrameSmemFloats;
+        s.a_re = q; q += padded_len(kH);
+        s.a_im = q; q += padded_len(kH);
+        s.b_re = q; q += padded_len(kH);
+        s.b_im = q; q += padded_len(kH);
+        s.x_re = q; q += 520;
+        s.x_im = q; q += 520;
+        s.p = q; q += 520;
+        s.mel = q; q += 64;
+        s.melbar = q;
+    }
+    StftTables tab = p.tab;
+    tab.window = win;
+    tab.tw512 = tw;
+    tab.w1024 = w1024;
+
+    // ---- stage the signal span, tables and the reference tile ----
+    const float* yb = p.y + (long long)b * p.y_bstride;
+    for (int i = tid; i < span; i += kCtaThreads) {
+        long long j = reflect_src(base + i, p.Ly);
+        float v = __ldg(yb + j);
+        if (p.mask) v *= __ldg(p.mask + j);
+        sig[i] = v;
+        acc[i] = 0.f;
+    }
+    for (int i = tid; i < kNfft; i += kCtaThreads) win[i] = __ldg(p.tab.window + i);
+    for (int i = tid; i < kH; i += kCtaThreads) tw[i] = p.tab.tw512[i];
+    for (int i = tid; i < 257; i += kCtaThreads) w1024[i] = p.tab.w1024[i];
+    if (gt < 8) s.melbar[64 + gt] = 0.f;
+    if (MODE != kModePhaseWav && has_ref) {
+        const float* rb = p.ref + (long long)b * p.ref_bstride;
+        for (int i = tid; i < kMels * nfr; i += kCtaThreads) {
+            int m = i / nfr, f = i - m * nfr;
+            tilebuf[f * kTileLd + m] = __ldg(rb + (long long)m * p.T + f0 + f);
+        }
+    }
+    __syncthreads();
+
+    float lsum = 0.f;
+    const int rounds = (nfr + kGroups - 1) / kGroups;
+    for (int r = 0; r < rounds; ++r) {
+        const int f = r * kGroups + g;
+        const bool active = f < nfr;
+        if (active) {
+            const float* frame = sig + f * p.hop;
+            fwd_pass1(gt, tab, frame, win, s);
+            group_sync(g);
+            fwd_pass2(gt, tw, s);
+            group_sync(g);
+            fwd_pass3(gt, tw, s);
+            group_sync(g);
+            fwd_unpack<MODE>(gt, w1024, s);
+            group_sync(g);
+            if (MODE != kModeMelDb && p.noise != nullptr) {  // GaussianNoise on the magnitude (operator.py:171)
+                const long long t = f0 + f;
+                for (int k = gt; k < kBins; k += kGroupThreads)
+                    s.p[k] += p.sigma * __ldg(p.noise + ((long long)b * kBins + k) * p.T + t);
+                group_sync(g);
+            }
+            if (MODE == kModePhaseWav) {
+                const long long t = f0 + f;
+                for (int k = gt; k < kBins; k += kGroupThreads) {
+                    float mag = s.p[k];
+                    if (p.out) p.out[((long long)b * kBins + k) * p.T + t] = mag;
+                    if (has_ref) {
+                        float d = __ldg(p.ref + (long long)b * p.ref_bstride + (long long)k * p.T + t) - mag;
+                        lsum = fmaf(d, d, lsum);
+                        s.p[k] = -d;
+                    }
+                }
+            } else {
+                float v;
+                lsum += mel_residual<MODE>(gt, tab, s, p.clamp != 0, has_ref, has_ref ? tilebuf[f * kTileLd + gt] : 0.f,
+                                           &v);
+                if (p.out) tilebuf[f * kTileLd + gt] = v;
+            }
+            if (want_grad) {
+                group_sync(g);
+                bwd_pack<MODE>(gt, tab, s);
+                group_sync(g);
+                inv_pass1(gt, tw, s);
+                group_sync(g);
+                inv_pass2(gt, tw, s);
+                group_sync(g);
+                inv_pass3(gt, tw, s);
+            }
+        }
+        if (want_grad) {
+            __syncthreads();
+            // overlap-add the (up to) 4 frame gradients of this round, fixed order -> deterministic
+            const int fr0 = r * kGroups;
+            const int nact = min(kGroups, nfr - fr0);
+            const int lo = fr0 * p.hop, hi = (fr0 + nact - 1) * p.hop + kNfft;
+            for (int i = lo + tid; i < hi; i += kCtaThreads) {
+                float a = acc[i];
+                for (int q = 0; q < nact; ++q) {
+                    int off = i - (fr0 + q) * p.hop;
+                    if (off >= 0 && off < kNfft) {
+                        const float* gq = grp + q * kFrameSmemFloats;
+                        int pp = padi(off >> 1);
+                        float v = (off & 1) ? gq[padded_len(kH) + pp] : gq[pp];
+                        a = fmaf(v, win[off], a);
+                    }
+                }
+                acc[i] = a;
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- tile epilogue ----
+    if (want_grad) {
+        float* gb = p.ypbar + (long long)b * (p.Ly + kNfft) + base;
+        for (int i = tid; i < span; i += kCtaThreads) atomicAdd(gb + i, acc[i]);
+    }
+    if (p.out && MODE != kModePhaseWav) {
+        __syncthreads();
+        float* ob = p.out + (long long)b * kMels * p.T;
+        for (int i = tid; i < kMels * nfr; i += kCtaThreads) {
+            int m = i / nfr, f = i - m * nfr;
+            ob[(long long)m * p.T + f0 + f] = tilebuf[f * kTileLd + m];
+        }
+    }
+    if (p.partial) {
+        lsum = warp_sum(lsum);
+        if ((tid & 31) == 0) red[tid >> 5] = lsum;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int i = 0; i < kCtaThreads / 32; ++i) t += red[i];
+            p.partial[(long long)b * p.ntiles + tile] = t;
+        }
+    }
+}
+
+// mel projection of an already materialised magnitude (PhaseRetrievalOperator.transform, operator.py:153-154):
+// out[b, m, t] = clamp(sum_k fb[k, m] * mag[b, k, t], +-80) with the banded filterbank; coalesced along t.
+__global__ void __launch_bounds__(128) mel_project_kernel(const float* __restrict__ mag, long long T, StftTables tab,
+                                                          int clamp, float* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+    const int m = blockIdx.y, b = blockIdx.z;
+    if (t >= T) return;
+    const int k0 = tab.mel_kstart[m], n = tab.mel_klen[m];
+    const float* w = tab.mel_w + m * tab.mel_wstride;
+    const float* src = mag + ((long long)b * kBins + k0) * T + t;
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc = fmaf(__ldg(w + i), src[(long long)i * T], acc);
+    if (clamp) acc = fminf(fmaxf(acc, -80.f), 80.f);
+    out[((long long)b * kMels + m) * T + t] = acc;
+}
+
+static size_t stft_smem_bytes(int nf, int hop) {
+    size_t span = (size_t)(nf - 1) * hop + kNfft;
+    size_t fl = 2 * span + (size_t)tile_floats(nf) + kNfft + 2 * kH + 2 * 260 + (size_t)kGroups * kFrameSmemFloats + 8;
+    return fl * sizeof(float);
+}
+
+}  // namespace dm
+
+using namespace dm;
+
+extern "C" int dm_stft_num_tiles(long long Ly, int hop, int frames_per_tile) {
+    if (Ly <= 0 || hop <= 0 || frames_per_tile <= 0) return DM_ERR_INVALID;
+    long long T = 1 + Ly / hop;
+    return (int)((T + frames_per_tile - 1) / frames_per_tile);
+}
+
+extern "C" int dm_stft_guidance(const dm_stft_tables* tab, int mode, int clamp, int hop, const float* y,
+                                long long y_bstride, long long Ly, const float* mask, int B, const float* ref,
+                                long long ref_bstride, const float* noise, float sigma, float* out, float* ypbar,
+                                float* partial, int frames_per_tile, dm_stream_t stream) {
+    DM_REQUIRE(tab != nullptr && y != nullptr);
+    DM_REQUIRE(mode >= 0 && mode <= 2);
+    DM_REQUIRE(B > 0 && Ly > kNfft / 2);  // reflect padding needs pad < length (torch.stft raises otherwise)
+    DM_REQUIRE(hop > 0 && hop <= kNfft);
+    DM_REQUIRE(frames_per_tile >= 1 && frames_per_tile <= 64);
+    DM_REQUIRE((ref != nullptr) != (out != nullptr));  // guidance mode xor transform mode
+    DM_REQUIRE(ypbar == nullptr || ref != nullptr);
+    DM_REQUIRE(ref == nullptr || partial != nullptr);
+    DM_REQUIRE(noise == nullptr || mode != DM_STFT_MEL_DB);
+    StftParams p;
+    p.tab = StftTables{tab->window, reinterpret_cast<const cf*>(tab->tw512), reinterpret_cast<const cf*>(tab->w1024),
+                       tab->mel_kstart, tab->mel_klen, tab->mel_w, tab->mel_wstride, tab->bin_m0, tab->bin_w0,
+                       tab->bin_w1};
+    p.clamp = clamp;
+    p.hop = hop;
+    p.B = B;
+    p.nf = frames_per_tile;
+    p.Ly = Ly;
+    p.T = 1 + Ly / hop;
+    p.ntiles = (int)((p.T + p.nf - 1) / p.nf);
+    p.y_bstride = y_bstride;
+    p.ref_bstride = ref_bstride;
+    p.y = y;
+    p.mask = mask;
+    p.ref = ref;
+    p.noise = noise;
+    p.sigma = sigma;
+    p.out = out;
+    p.ypbar = ypbar;
+    p.partial = partial;
+    size_t smem = stft_smem_bytes(p.nf, hop);
+    if (smem > 227 * 1024) return fail(DM_ERR_UNSUPPORTED, "%s: tile needs %zu B of shared memory", __func__, smem);
+    dim3 grid(p.ntiles, B), block(kCtaThreads);
+    cudaStream_t st = as_stream(stream);
+#define DM_LAUNCH_STFT(M)                                                                                     \
+    do {                                                                                                      \
+        DM_CUDA(cudaFuncSetAttribute(stft_guidance_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                     (int)smem));                                                             \
+        stft_guidance_kernel<M><<<grid, block, smem, st>>>(p);                                                \
+    } while (0)
+    if (mode == DM_STFT_MEL_DB) DM_LAUNCH_STFT(kModeMelDb);
+    else if (mode == DM_STFT_PHASE_MEL) DM_LAUNCH_STFT(kModePhaseMel);
+    else DM_LAUNCH_STFT(kModePhaseWav);
+#undef DM_LAUNCH_STFT
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_mel_project(const dm_stft_tables* tab, const float* mag, int B, long long T, int clamp, float* out,
+                              dm_stream_t stream) {
+    DM_REQUIRE(tab && mag && out && B > 0 && T > 0);
+    StftTables t{tab->window, reinterpret_cast<const cf*>(tab->tw512), reinterpret_cast<const cf*>(tab->w1024),
+                 tab->mel_kstart, tab->mel_klen, tab->mel_w, tab->mel_wstride, tab->bin_m0, tab->bin_w0, tab->bin_w1};
+    mel_project_kernel<<<dim3((unsigned)((T + 127) / 128), kMels, B), 128, 0, as_stream(stream)>>>(mag, T, t, clamp,
+                                                                                                 out);
+    DM_LAUNCHED();
+    return DM_OK;
+}

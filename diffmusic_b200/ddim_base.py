@@ -1,0 +1,156 @@
+"""Base scheduler plumbing: diffusers' DDIMScheduler when it is installed, else a dependency-free restatement.
+
+The guided schedulers only need from the base: the beta / alphas_cumprod tables, final_alpha_cumprod,
+set_timesteps, timesteps, _get_variance, init_noise_sigma, scale_model_input, order and `.config`.  The arithmetic of
+`step` itself lives in csrc/sched_update.cu.  The restatement follows diffusers==0.31.0 (requirements.txt:6 of the
+reference); diffusers is not vendored by the reference and no reference test pins this boundary (parity unpinned).
+"""
+from __future__ import annotations
+
+import functools
+import inspect
+import math
+from dataclasses import fields
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+try:  # the deployment the reference pipelines run in
+    from diffusers.configuration_utils import register_to_config  # type: ignore
+    from diffusers.schedulers import DDIMScheduler as DDIMBase  # type: ignore
+    from diffusers.utils import BaseOutput  # type: ignore
+    HAVE_DIFFUSERS = True
+except Exception:  # diffusers absent (this build container): stand-alone base
+    HAVE_DIFFUSERS = False
+
+    def register_to_config(init):
+        """Record the constructor arguments on `self.config` (what diffusers' decorator of the same name does)."""
+        sig = inspect.signature(init)
+
+        @functools.wraps(init)
+        def wrapper(self, *args, **kwargs):
+            init(self, *args, **kwargs)
+            bound = sig.bind_partial(self, *args, **kwargs)
+            cfg = getattr(self, "config", None) or SimpleNamespace()
+            for name, p in sig.parameters.items():
+                if name == "self" or p.kind in (p.VAR_POSITIONAL, p.VAR_KEYWORD):
+                    continue
+                setattr(cfg, name, bound.arguments.get(name, p.default))
+            self.config = cfg
+
+        return wrapper
+
+    class BaseOutput:
+        """dataclass with dict-style access, like diffusers.utils.BaseOutput."""
+
+        def __getitem__(self, key):
+            if isinstance(key, str):
+                return getattr(self, key)
+            return self.to_tuple()[key]
+
+        def keys(self):
+            return [f.name for f in fields(self) if getattr(self, f.name) is not None]
+
+        def to_tuple(self):
+            return tuple(getattr(self, k) for k in self.keys())
+
+    def _cosine_betas(n, max_beta=0.999):
+        bar = lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2  # noqa: E731
+        return torch.tensor([min(1 - bar((i + 1) / n) / bar(i / n), max_beta) for i in range(n)],
+                            dtype=torch.float32)
+
+    def _zero_terminal_snr(betas):
+        s = torch.cumprod(1.0 - betas, dim=0).sqrt()
+        first, last = s[0].clone(), s[-1].clone()
+        s = (s - last) * (first / (first - last))
+        bar = s ** 2
+        return 1 - torch.cat([bar[0:1], bar[1:] / bar[:-1]])
+
+    class DDIMBase:
+        """Tables and timestep bookkeeping of diffusers 0.31.0 DDIMScheduler (no `step`)."""
+
+        order = 1
+
+        def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                     trained_betas=None, clip_sample=True, set_alpha_to_one=True, steps_offset=0,
+                     prediction_type="epsilon", thresholding=False, dynamic_thresholding_ratio=0.995,
+                     clip_sample_range=1.0, sample_max_value=1.0, timestep_spacing="leading",
+                     rescale_betas_zero_snr=False):
+            self.config = SimpleNamespace(
+                num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+                beta_schedule=beta_schedule, trained_betas=trained_betas, clip_sample=clip_sample,
+                set_alpha_to_one=set_alpha_to_one, steps_offset=steps_offset, prediction_type=prediction_type,
+                thresholding=thresholding, dynamic_thresholding_ratio=dynamic_thresholding_ratio,
+                clip_sample_range=clip_sample_range, sample_max_value=sample_max_value,
+                timestep_spacing=timestep_spacing, rescale_betas_zero_snr=rescale_betas_zero_snr)
+            f32 = torch.float32
+            if trained_betas is not None:
+                betas = torch.tensor(trained_betas, dtype=f32)
+            elif beta_schedule == "linear":
+                betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=f32)
+            elif beta_schedule == "scaled_linear":
+                betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=f32) ** 2
+            elif beta_schedule == "squaredcos_cap_v2":
+                betas = _cosine_betas(num_train_timesteps)
+            else:
+                raise NotImplementedError(f"{beta_schedule} is not implemented for {self.__class__}")
+            if rescale_betas_zero_snr:
+                betas = _zero_terminal_snr(betas)
+            self.betas = betas
+            self.alphas = 1.0 - betas
+            self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+            self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+            self.init_noise_sigma = 1.0
+            self.num_inference_steps = None
+            self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
+
+        def scale_model_input(self, sample, timestep=None):
+            return sample
+
+        def _get_variance(self, timestep, prev_timestep):
+            a_t = self.alphas_cumprod[timestep]
+            a_p = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+            return ((1 - a_p) / (1 - a_t)) * (1 - a_t / a_p)
+
+        def set_timesteps(self, num_inference_steps, device=None):
+            n_train = self.config.num_train_timesteps
+            if num_inference_steps > n_train:
+                raise ValueError(f"`num_inference_steps`: {num_inference_steps} cannot be larger than "
+                                 f"`self.config.train_timesteps`: {n_train}")
+            self.num_inference_steps = num_inference_steps
+            mode = self.config.timestep_spacing
+            if mode == "linspace":
+                ts = np.linspace(0, n_train - 1, num_inference_steps).round()[::-1].copy().astype(np.int64)
+            elif mode == "leading":
+                ts = (np.arange(0, num_inference_steps) * (n_train // num_inference_steps)).round()[::-1]
+                ts = ts.copy().astype(np.int64) + self.config.steps_offset
+            elif mode == "trailing":
+                ts = np.round(np.arange(n_train, 0, -n_train / num_inference_steps)).astype(np.int64) - 1
+            else:
+                raise ValueError(f"{mode} is not supported. Choose one of 'leading', 'trailing' or 'linspace'.")
+            self.timesteps = torch.from_numpy(ts).to(device)
+
+
+def randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
+    """Noise draw with the reference's generator semantics (diffmusic/torch_utils.py:31-76): a single generator draws
+    the whole batch, a list draws one (1, ...) tensor per clip; CPU generators draw on the CPU and the result is moved.
+    Kept in torch so RNG streams are bit-identical to the reference (kernels never generate randomness)."""
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    layout = layout or torch.strided
+    where = device
+    if generator is not None:
+        first = generator[0] if isinstance(generator, (list, tuple)) else generator
+        kind = first.device.type
+        if kind != device.type and kind == "cpu":
+            where = torch.device("cpu")
+        elif kind != device.type and kind == "cuda":
+            raise ValueError(f"Cannot generate a {device} tensor from a generator of type {kind}.")
+    if isinstance(generator, (list, tuple)) and len(generator) == 1:
+        generator = generator[0]
+    if isinstance(generator, (list, tuple)):
+        per = (1,) + tuple(shape[1:])
+        out = torch.cat([torch.randn(per, generator=generator[i], device=where, dtype=dtype, layout=layout)
+                         for i in range(shape[0])], dim=0)
+        return out.to(device)
+    return torch.randn(tuple(shape), generator=generator, device=where, dtype=dtype, layout=layout).to(device)

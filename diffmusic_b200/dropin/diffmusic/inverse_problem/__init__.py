@@ -1,0 +1,2 @@
+"""Drop-in for the reference's `diffmusic.inverse_problem` (diffmusic/inverse_problem/__init__.py:1-11)."""
+from diffmusic_b200.noise import GaussianNoise, PoissonNoise, get_noiser  # noqa: F401

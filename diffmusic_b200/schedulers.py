@@ -1,0 +1,306 @@
+"""Guided schedulers -- host-side mirror of diffmusic/schedulers/scheduling_{ddim,dps,mpgd,dsg,diffmusic}.py with the
+same class names, constructor and `.step` signatures, running the latent algebra on the sm_100a kernels of
+csrc/sched_update.cu and the measurement path on the fused guidance kernels (operators.py).
+
+Batched semantics are per clip: a batch of B clips behaves like B independent batch-1 reference
+trajectories (per-clip loss, per-clip gradient norms, per-clip slerp).  For B = 1 this is the reference.
+
+The base class is diffusers' DDIMScheduler when diffusers is importable (so the reference pipelines accept the
+object), otherwise the dependency-free restatement in ddim_base.py.  `super().step` is never called: x0 comes from
+dm_sched_x0; the base's only other effect -- one discarded randn draw when eta > 0 -- is reproduced so generator
+streams stay aligned with the reference.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .ddim_base import BaseOutput, DDIMBase, randn_tensor, register_to_config
+from .operators import BaseOperator, generic_guidance_loss
+
+
+@dataclass
+class InverseProblemSchedulerOutput(BaseOutput):
+    """diffmusic/schedulers/utils.py:8-16 (+ loss_per_clip for batched use)."""
+    sample: Optional[torch.Tensor] = None
+    prev_sample: torch.Tensor = None
+    pred_original_sample: Optional[torch.Tensor] = None
+    loss: Optional[torch.Tensor] = None
+    encoder_hidden_states: Optional[torch.Tensor] = None
+    encoder_hidden_states_1: Optional[torch.Tensor] = None
+    init_latents: Optional[torch.Tensor] = None
+    loss_per_clip: Optional[torch.Tensor] = None
+
+
+def _f(t):
+    """exact Python float of a 0-d fp32 tensor / number (so the kernel sees the reference's fp32 scalar)."""
+    return float(t.item()) if isinstance(t, torch.Tensor) else float(t)
+
+
+class _GuidedBase(DDIMBase):
+    """Shared constructor (scheduling_dps.py:22-61, identical in all five files) and helpers."""
+
+    @register_to_config
+    def __init__(self, operator: BaseOperator = None, num_train_timesteps: int = 1000, beta_start: float = 0.0001,
+                 beta_end: float = 0.02, beta_schedule: str = "linear", trained_betas=None, clip_sample: bool = True,
+                 set_alpha_to_one: bool = True, steps_offset: int = 0, prediction_type: str = "epsilon",
+                 thresholding: bool = False, dynamic_thresholding_ratio: float = 0.995,
+                 clip_sample_range: float = 1.0, sample_max_value: float = 1.0, timestep_spacing: str = "leading",
+                 rescale_betas_zero_snr: bool = False, *args, **kwargs):
+        super().__init__(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+                         beta_schedule=beta_schedule, trained_betas=trained_betas, clip_sample=clip_sample,
+                         set_alpha_to_one=set_alpha_to_one, steps_offset=steps_offset,
+                         prediction_type=prediction_type, thresholding=thresholding,
+                         dynamic_thresholding_ratio=dynamic_thresholding_ratio, clip_sample_range=clip_sample_range,
+                         sample_max_value=sample_max_value, timestep_spacing=timestep_spacing,
+                         rescale_betas_zero_snr=rescale_betas_zero_snr)
+        self.operator = operator
+
+    # ---- coefficient prep (scheduling_dps.py:157-162): 0-d fp32 CPU tensors, exactly the reference's arithmetic ----
+    def _coeffs(self, timestep, eta):
+        t = int(timestep)
+        t_prev = t - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        b_t = 1 - a_t
+        a_prev = self.alphas_cumprod[t_prev] if t_prev >= 0 else self.final_alpha_cumprod
+        var = self._get_variance(t, t_prev)
+        std = eta * var ** 0.5
+        return dict(sqrt_a=_f(a_t ** 0.5), sqrt_b=_f(b_t ** 0.5), sqrt_p=_f(a_prev ** 0.5),
+                    sqrt_1mp=_f((1 - a_prev) ** 0.5), dir_coef=_f((1 - a_prev - std ** 2) ** 0.5), std=_f(std))
+
+    def _check_supported(self):
+        if self.config.prediction_type != "epsilon" or self.config.thresholding:
+            raise NotImplementedError("the fused x0 kernel covers prediction_type='epsilon' without dynamic "
+                                      "thresholding (every shipped config, configs/model/*.yaml)")
+
+    @staticmethod
+    def _prep(t):
+        _lib.require_cuda(t)
+        return t.detach().float().contiguous()
+
+    def _x0(self, x, eps, c):
+        """dm_sched_x0: pred_original_sample of the diffusers base step."""
+        self._check_supported()
+        x0 = torch.empty_like(x)
+        _lib.call("dm_sched_x0", x.data_ptr(), eps.data_ptr(), x0.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"],
+                  int(bool(self.config.clip_sample)), float(self.config.clip_sample_range), _lib.stream())
+        return x0
+
+    @staticmethod
+    def _base_rng_side_effect(eta, generator, variance_noise, model_output):
+        """diffusers DDIMScheduler.step draws (and the reference discards) one noise tensor when eta > 0."""
+        if eta > 0:
+            if variance_noise is not None and generator is not None:
+                raise ValueError("Cannot pass both generator and variance_noise. Please make sure that either "
+                                 "`generator` or `variance_noise` stays `None`.")
+            if variance_noise is None:
+                randn_tensor(model_output.shape, generator=generator, device=model_output.device,
+                             dtype=model_output.dtype)
+
+    @staticmethod
+    def _own_noise(eta, generator, variance_noise, model_output):
+        """scheduling_dps.py:180-191: the step's own z (None when eta == 0)."""
+        if not eta > 0:
+            return None
+        if variance_noise is not None and generator is not None:
+            raise ValueError("Cannot pass both generator and variance_noise. Please make sure that either "
+                             "`generator` or `variance_noise` stays `None`.")
+        if variance_noise is None:
+            variance_noise = randn_tensor(model_output.shape, generator=generator, device=model_output.device,
+                                          dtype=model_output.dtype)
+        return variance_noise.detach().float().contiguous()
+
+    def _guidance(self, x0, measurement, vae, vocoder, L, supervised_space, model_dtype):
+        """loss (per clip) and G0 = dLoss/dx0 through vae.decode + vocoder (torch autograd) and the fused operator
+        kernels (scheduling_dps.py:195-212).  x0 is re-leafed: the UNet is never differentiated."""
+        if supervised_space not in ("wav_form", "mel_spectrogram"):
+            raise ValueError("supervised_space should be either 'wav_form' or 'mel_spectrogram")
+        op = self.operator
+        with torch.enable_grad():
+            leaf = x0.detach().requires_grad_(True)
+            mel = vae.decode(1 / vae.config.scaling_factor * leaf.to(model_dtype)).sample
+            wav = op.inverse_transform(mel, vocoder)
+            wav = wav[:, :L]
+            if hasattr(op, "guidance_loss"):
+                losses = op.guidance_loss(wav, measurement, supervised_space)
+            else:
+                losses = generic_guidance_loss(op, wav, measurement, supervised_space)
+            (g0,) = torch.autograd.grad(losses.sum(), leaf)
+        return losses.detach(), g0.float().contiguous()
+
+    @staticmethod
+    def _loss_out(losses):
+        """0-d loss like the reference's torch.linalg.norm over the whole batch (= the per-clip norm for B = 1)."""
+        if losses.numel() == 1:
+            return losses.reshape(())
+        return torch.linalg.norm(losses)
+
+    def optim_prompt(self, model_output, timestep, sample, encoder_hidden_states=None, encoder_hidden_states_1=None,
+                     eta=0.0, use_clipped_model_output=False, generator=None, variance_noise=None, return_dict=True,
+                     measurement=None, vae=None, vocoder=None, original_waveform_length=0,
+                     optim_prompt_learning_rate=1e-4, supervised_space="mel_spectrogram", *args, **kwargs):
+        """scheduling_dps.py:63-135.  Disabled in every shipped config (configs/*.yaml: optim_prompt: false) and, as
+        written in the reference, a no-op on the embeddings (the SGD steps act on discarded clones, :94-96): it returns
+        the embeddings detached.  Kept for API compatibility; the guided loss is still evaluated so errors surface."""
+        c = self._coeffs(timestep, eta)
+        x, eps = self._prep(sample), self._prep(model_output)
+        x0 = self._x0(x, eps, c)
+        self._guidance(x0, measurement, vae, vocoder, original_waveform_length, supervised_space, sample.dtype)
+        return InverseProblemSchedulerOutput(
+            encoder_hidden_states=None if encoder_hidden_states is None else encoder_hidden_states.detach(),
+            encoder_hidden_states_1=None if encoder_hidden_states_1 is None else encoder_hidden_states_1.detach())
+
+
+class DDIMScheduler(_GuidedBase):
+    """scheduling_ddim.py:58-104.  Unlike the reference (which raises when the pipelines call it without
+    encoder_hidden_states) None is accepted for the two passthrough tensors."""
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output: bool = False,
+             generator=None, variance_noise=None, return_dict: bool = True, measurement=None, vae=None, vocoder=None,
+             original_waveform_length: int = 0, encoder_hidden_states=None, encoder_hidden_states_1=None, *args,
+             **kwargs):
+        c = self._coeffs(timestep, eta)
+        x, eps = self._prep(sample), self._prep(model_output)
+        x0 = self._x0(x, eps, c)
+        self._base_rng_side_effect(eta, generator, variance_noise, model_output)
+        prev = torch.empty_like(x)
+        _lib.call("dm_sched_ddim_update", x.data_ptr(), x0.data_ptr(), prev.data_ptr(), x.numel(), c["sqrt_a"],
+                  c["sqrt_b"], c["sqrt_p"], c["sqrt_1mp"], _lib.stream())
+        return InverseProblemSchedulerOutput(
+            prev_sample=prev.to(sample.dtype), pred_original_sample=x0.to(sample.dtype),
+            loss=torch.tensor([int(timestep)]),
+            encoder_hidden_states=None if encoder_hidden_states is None else encoder_hidden_states.detach(),
+            encoder_hidden_states_1=None if encoder_hidden_states_1 is None else encoder_hidden_states_1.detach())
+
+
+class DPSScheduler(_GuidedBase):
+    """Diffusion Posterior Sampling, scheduling_dps.py:137-219."""
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output: bool = False,
+             generator=None, variance_noise=None, return_dict: bool = True, measurement=None,
+             ip_guidance_rate: float = 5e-4, vae=None, vocoder=None, original_waveform_length: int = 0,
+             supervised_space: str = "mel_spectrogram", *args, **kwargs):
+        c = self._coeffs(timestep, eta)
+        x, eps = self._prep(sample), self._prep(model_output)
+        x0 = self._x0(x, eps, c)
+        self._base_rng_side_effect(eta, generator, variance_noise, model_output)
+        z = self._own_noise(eta, generator, variance_noise, model_output)
+        losses, g0 = self._guidance(x0, measurement, vae, vocoder, original_waveform_length, supervised_space,
+                                    sample.dtype)
+        prev = torch.empty_like(x)
+        _lib.call("dm_sched_dps_update", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), _lib.ptr(z), prev.data_ptr(),
+                  x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"], float(ip_guidance_rate),
+                  _lib.stream())
+        return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
+                                             pred_original_sample=x0.to(sample.dtype), loss=self._loss_out(losses),
+                                             loss_per_clip=losses)
+
+
+class MPGDScheduler(_GuidedBase):
+    """Manifold Preserving Guided Diffusion, scheduling_mpgd.py:137-224."""
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output: bool = False,
+             generator=None, variance_noise=None, return_dict: bool = True, measurement=None,
+             ip_guidance_rate: float = 1.0, vae=None, vocoder=None, original_waveform_length: int = 0,
+             supervised_space: str = "mel_spectrogram", *args, **kwargs):
+        c = self._coeffs(timestep, eta)
+        x, eps = self._prep(sample), self._prep(model_output)
+        x0 = self._x0(x, eps, c)
+        self._base_rng_side_effect(eta, generator, variance_noise, model_output)
+        losses, g0 = self._guidance(x0, measurement, vae, vocoder, original_waveform_length, supervised_space,
+                                    sample.dtype)
+        z = self._own_noise(eta, generator, variance_noise, model_output)
+        prev, x0_new = torch.empty_like(x), torch.empty_like(x)
+        _lib.call("dm_sched_mpgd_update", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), _lib.ptr(z), prev.data_ptr(),
+                  x0_new.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"],
+                  float(ip_guidance_rate), _lib.stream())
+        return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
+                                             pred_original_sample=x0_new.to(sample.dtype),
+                                             loss=self._loss_out(losses), loss_per_clip=losses)
+
+
+class _SphericalBase(_GuidedBase):
+    """DSG and DiffMusic share everything up to the per-clip mixing rule."""
+
+    def _spherical_step(self, kernel, model_output, timestep, sample, eta, generator, variance_noise, measurement,
+                        vae, vocoder, L, ip_guidance_rate, eps, supervised_space):
+        c = self._coeffs(timestep, eta)
+        x, e = self._prep(sample), self._prep(model_output)
+        x0 = self._x0(x, e, c)  # base step called without eta (scheduling_dsg.py:178-186): no RNG side effect
+        losses, g0 = self._guidance(x0, measurement, vae, vocoder, L, supervised_space, sample.dtype)
+        # one draw per step, AFTER the gradient (scheduling_dsg.py:215-220); variance_noise is not consulted there
+        z = randn_tensor(model_output.shape, generator=generator, device=model_output.device,
+                         dtype=model_output.dtype).float().contiguous()
+        B = x.shape[0]
+        n_clip = x.numel() // B
+        prev = torch.empty_like(x)
+        if kernel == "dsg":
+            # r = sqrt(c*h*w) * std as fp32 (scheduling_dsg.py:212-213)
+            r = _f(torch.sqrt(torch.tensor(n_clip)) * c["std"])
+            _lib.call("dm_sched_dsg_update", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), z.data_ptr(),
+                      prev.data_ptr(), B, n_clip, c["sqrt_a"], c["sqrt_p"], c["dir_coef"], c["std"],
+                      float(ip_guidance_rate), r, 1.0 / 1000.0, float(eps), _lib.stream())
+        else:
+            _lib.call("dm_sched_diffmusic_update", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), z.data_ptr(),
+                      prev.data_ptr(), B, n_clip, c["sqrt_a"], c["sqrt_p"], c["dir_coef"], c["std"],
+                      float(ip_guidance_rate), 1.0 / 1000.0, float(eps), 0.9995, _lib.stream())
+        return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
+                                             pred_original_sample=x0.to(sample.dtype), loss=self._loss_out(losses),
+                                             loss_per_clip=losses)
+
+
+class DSGScheduler(_SphericalBase):
+    """Diffusion with Spherical Gaussian constraint, scheduling_dsg.py:148-230.  eta defaults to 1."""
+
+    def step(self, model_output, timestep, sample, eta: float = 1.0, use_clipped_model_output: bool = False,
+             generator=None, variance_noise=None, return_dict: bool = True, measurement=None, vae=None, vocoder=None,
+             original_waveform_length: int = 0, ip_guidance_rate: float = 0.08, eps: float = 1e-8,
+             supervised_space: str = "mel_spectrogram", *args, **kwargs):
+        return self._spherical_step("dsg", model_output, timestep, sample, eta, generator, variance_noise,
+                                    measurement, vae, vocoder, original_waveform_length, ip_guidance_rate, eps,
+                                    supervised_space)
+
+
+class DiffMusicScheduler(_SphericalBase):
+    """scheduling_diffmusic.py:148-229 + slerp :59-68; the |cos| > 0.9995 branch is taken on the
+    device per clip, so `.step` never synchronises with the host."""
+
+    @staticmethod
+    def slerp(x0, x1, gamma=0.008, threshold=0.9995):
+        """scheduling_diffmusic.py:59-68 (public static helper of the reference class; torch, for API parity)."""
+        cos_theta = ((x0 / torch.norm(x0)) * (x1 / torch.norm(x1))).sum()
+        if cos_theta.abs() > threshold:
+            return x0 + gamma * (x1 - x0)
+        theta = torch.acos(cos_theta)
+        sin_theta = torch.sin(theta)
+        return torch.sin((1 - gamma) * theta) / sin_theta * x0 + torch.sin(gamma * theta) / sin_theta * x1
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output: bool = False,
+             generator=None, variance_noise=None, return_dict: bool = True, measurement=None, vae=None, vocoder=None,
+             original_waveform_length: int = 0, ip_guidance_rate: float = 0.08, eps: float = 1e-8,
+             supervised_space: str = "mel_spectrogram", *args, **kwargs):
+        return self._spherical_step("diffmusic", model_output, timestep, sample, eta, generator, variance_noise,
+                                    measurement, vae, vocoder, original_waveform_length, ip_guidance_rate, eps,
+                                    supervised_space)
+
+
+def get_scheduler(scheduler_name):
+    """diffmusic/schedulers/__init__.py:9-24."""
+    table = {"ddim": DDIMScheduler, "dps": DPSScheduler, "mpgd": MPGDScheduler, "dsg": DSGScheduler,
+             "diffmusic": DiffMusicScheduler}
+    if scheduler_name in table:
+        return table[scheduler_name]
+    if scheduler_name == "ditto":
+        # DITTO back-propagates through the whole sampling chain including the UNet (scheduling_ditto.py:187-208):
+        # out of the hot-path scope, so the reference class is re-exported when the reference is importable.
+        try:
+            import importlib
+            return importlib.import_module("diffmusic.schedulers.scheduling_ditto").DITTOScheduler
+        except Exception as exc:  # pragma: no cover - depends on the deployment
+            raise ImportError("DITTOScheduler is not part of diffmusic_b200; put the reference's "
+                              "diffmusic/schedulers/scheduling_ditto.py on sys.path to use it") from exc
+    raise ValueError(f"Unknown scheduler: {scheduler_name}")

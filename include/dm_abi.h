@@ -1,0 +1,177 @@
+/* diffmusic-b200 C ABI  --  the drop-in boundary of the guidance hot path.
+ *
+ * The reference (jwliao1209/DiffMusic) is pure Python and has no FFI of its own; every entry point below replaces a
+ * chain of torch / torchaudio library calls made by the reference file:line cited next to it (paths relative to
+ * /root/reference).  Callers are the Python classes in diffmusic_b200/ that mirror diffmusic/inverse_problem and
+ * diffmusic/schedulers (see INTEGRATION.md for the ctypes binding).
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, explicit sizes and strides (in elements), fp32 scalars by value, a CUDA stream;
+ *   - every function returns 0 on success, <0 on error (DM_ERR_*); dm_last_error() gives the thread-local message;
+ *   - nothing allocates, nothing synchronises; work is enqueued on `stream`; workspaces are caller-owned;
+ *   - batched semantics are per clip: every norm / loss is taken over one clip.
+ */
+#ifndef DM_ABI_H_
+#define DM_ABI_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_OK 0
+#define DM_ERR_INVALID (-1)
+#define DM_ERR_CUDA (-2)
+#define DM_ERR_UNSUPPORTED (-3)
+
+typedef void* dm_stream_t; /* cudaStream_t */
+
+int dm_version(void);
+const char* dm_last_error(void);
+/* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+unsigned long long dm_launch_count(void);
+void dm_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Scheduler algebra on the latent  (SURVEY.md Appendix B).  n = total elements, n_clip = C*H*W of one clip.
+ * Scalars are the fp32 values the reference computes on the host (scheduling_dps.py:157-162):
+ *   sqrt_a = alpha_prod_t ** 0.5, sqrt_b = (1 - alpha_prod_t) ** 0.5, sqrt_p = alpha_prod_t_prev ** 0.5,
+ *   dir_coef = (1 - alpha_prod_t_prev - std_dev_t ** 2) ** 0.5, std = eta * variance ** 0.5.
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* x0 = (x - sqrt_b * eps) / sqrt_a, optionally clamped to +-clip_range.
+ * Replaces diffusers DDIMScheduler.step(...).pred_original_sample as called at scheduling_ddim.py:84-93,
+ * scheduling_dps.py:166-175, scheduling_mpgd.py:164-173, scheduling_dsg.py:178-186, scheduling_diffmusic.py:180-188. */
+int dm_sched_x0(const float* x, const float* eps, float* x0, long long n, float sqrt_a, float sqrt_b, int clip,
+                float clip_range, dm_stream_t stream);
+
+/* scheduling_ddim.py:95-96: e = (x - sqrt_a x0)/sqrt_b ; prev = sqrt_p x0 + sqrt_1mp e */
+int dm_sched_ddim_update(const float* x, const float* x0, float* prev, long long n, float sqrt_a, float sqrt_b,
+                         float sqrt_p, float sqrt_1mp, dm_stream_t stream);
+
+/* scheduling_dps.py:177-213: prev = sqrt_p x0 + dir_coef (x - sqrt_a x0)/sqrt_b (+ std z) - rate * g0 / sqrt_a.
+ * g0 = dLoss/dx0 (from torch autograd through vocoder + VAE); z may be NULL when eta == 0. */
+int dm_sched_dps_update(const float* x, const float* x0, const float* g0, const float* z, float* prev, long long n,
+                        float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std, float rate,
+                        dm_stream_t stream);
+
+/* scheduling_mpgd.py:199-218: x0' = x0 - rate g0 ; prev = sqrt_p x0' + dir_coef (x - sqrt_a x0')/sqrt_b (+ std z) */
+int dm_sched_mpgd_update(const float* x, const float* x0, const float* g0, const float* z, float* prev,
+                         float* x0_out, long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef,
+                         float std, float rate, dm_stream_t stream);
+
+/* scheduling_dsg.py:189-224 with per-clip norms: g = grad_scale * g0 / sqrt_a ; mean = sqrt_p x0 + dir_coef eps ;
+ * d* = -r g/(|g|+e) ; mix = std z + rate (d* - std z) ; prev = mean + r mix/(|mix|+e).  r = sqrt(n_clip) * std. */
+int dm_sched_dsg_update(const float* x0, const float* eps, const float* g0, const float* z, float* prev, int n_clips,
+                        long long n_clip, float sqrt_a, float sqrt_p, float dir_coef, float std, float rate, float r,
+                        float grad_scale, float e, dm_stream_t stream);
+
+/* scheduling_diffmusic.py:191-223 + slerp (59-68), branch resolved on the device: g as above ;
+ * u = -g/(|g|+e) |z| ; c = <z/|z|, u/|u|> ; m = |c| > thr ? z + rate (u - z) : slerp ; prev = mean + std m. */
+int dm_sched_diffmusic_update(const float* x0, const float* eps, const float* g0, const float* z, float* prev,
+                              int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef, float std,
+                              float rate, float grad_scale, float e, float threshold, dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * STFT / mel guidance  (operator.py:24-36,123-124 T_mel ; 153-154 phase mel ; 162-171 |STFT|)
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct dm_stft_tables {
+    const float* window;   /* [1024] hann (periodic) or ones (phase retrieval, operator.py:163-169 window=None) */
+    const float* tw512;    /* [512][2] exp(-2 pi i m/512)  */
+    const float* w1024;    /* [257][2] exp(-2 pi i k/1024) */
+    const int* mel_kstart; /* [64] */
+    const int* mel_klen;   /* [64] */
+    const float* mel_w;    /* [64][mel_wstride] banded filterbank */
+    int mel_wstride;
+    const int* bin_m0;     /* [513] */
+    const float* bin_w0;   /* [513] */
+    const float* bin_w1;   /* [513] */
+} dm_stft_tables;
+
+#define DM_STFT_MEL_DB 0    /* |X|^2 -> mel -> 10 log10(max(.,1e-10)) [-> clamp +-80]   (n_fft = win = 1024) */
+#define DM_STFT_PHASE_MEL 1 /* |X|   -> mel [-> clamp +-80]                                                    */
+#define DM_STFT_PHASE_WAV 2 /* |X|                                                                             */
+
+/* number of frame tiles per clip for a signal of Ly samples: ceil((1 + Ly/hop) / frames_per_tile) */
+int dm_stft_num_tiles(long long Ly, int hop, int frames_per_tile);
+
+/* One launch over B clips.  y: (B, Ly) with row stride y_bstride, optionally multiplied by mask[Ly] on load
+ * (inpainting A(x) = x * mask, operator.py:132-133, fused into the frame load).
+ *   transform mode : out != NULL, ref == NULL   -> out (B, R, T) = transform value, R = 64 (mel) or 513 (PHASE_WAV)
+ *   guidance mode  : ref != NULL (row stride ref_bstride, 0 = shared by all clips), out == NULL
+ *        partial[b * ntiles + tile] = sum over the tile of (ref - value)^2
+ *        ypbar (B, Ly + 1024), may be NULL for loss only: accumulates (+=, caller zeroes) the UNSCALED cotangent of
+ *        the reflect-padded signal, i.e. d(loss)/d(ypad) * loss ; the adjoint kernels below fold the padding
+ *        and apply 1/loss per clip.
+ *   noise (B, 513, T) / sigma: phase modes only, magnitude += sigma * noise (GaussianNoise on |STFT|,
+ *        operator.py:171); NULL otherwise.
+ * Replaces torch.stft + abs/pow + MelScale matmul + AmplitudeToDB + clamp + sub + linalg.norm and their autograd
+ * replay (scheduling_dps.py:204-212). */
+int dm_stft_guidance(const dm_stft_tables* tab, int mode, int clamp, int hop, const float* y, long long y_bstride,
+                     long long Ly, const float* mask, int B, const float* ref, long long ref_bstride,
+                     const float* noise, float sigma, float* out, float* ypbar, float* partial, int frames_per_tile,
+                     dm_stream_t stream);
+
+/* out (B, 64, T) = clamp(mel filterbank applied to a materialised magnitude (B, 513, T), +-80)
+ * (PhaseRetrievalOperator.transform, operator.py:153-154: MelScale matmul + clamp, no log). */
+int dm_mel_project(const dm_stft_tables* tab, const float* mag, int B, long long T, int clamp, float* out,
+                   dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Residual in the measurement ("wav_form") space and the adjoint / finalise family
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define DM_RESID_CHUNK 4096
+/* d = meas - y * (mask ? mask : 1); ybar = -d * (mask ? mask : 1) ... written UNSCALED to ybar (B, n);
+ * partial[b * ntiles + c] = sum of d^2 over chunk c of DM_RESID_CHUNK elements.  (scheduling_dps.py:202-203,211) */
+int dm_residual_wav(const float* y, long long y_bstride, long long n, int B, const float* mask, const float* meas,
+                    long long meas_bstride, float* ybar, float* partial, dm_stream_t stream);
+
+/* loss[b] = sqrt(sum partial[b, :]); dwav[b, j] = (1/loss[b]) * fold(ybar[b])[j] * (mask ? mask[j] : 1)
+ * pad = 512: ybar is a reflect-padded cotangent (B, Ly + 1024) from dm_stft_guidance, folded back here
+ *            (reflect adjoint); pad = 0: ybar is (B, Ly).
+ * Serves identity / inpainting (operator.py:132-133 VJP) / phase retrieval.  dwav == NULL: loss only. */
+int dm_fold_adjoint(const float* ybar, int pad, long long Ly, int B, const float* mask, const float* partial,
+                    int ntiles, float* dwav, long long dwav_bstride, float* loss, dm_stream_t stream);
+
+/* torchaudio sinc resampling as used by SuperResolutionOperator.forward (operator.py:180,203-205):
+ * y[j*new + p] = sum_k xz[orig*j + k] * kernel[p, k], xz = zero-pad (width, width + orig), Ly = ceil(new*L/orig). */
+int dm_resample_fwd(const float* x, long long x_bstride, long long L, int B, const float* kernel, int n_new,
+                    int taps, int orig, int width, float* y, long long Ly, dm_stream_t stream);
+/* VJP of the above fused with the reflect fold and the 1/loss scale. */
+int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
+                        const float* kernel, int n_new, int taps, int orig, int width, float* dwav,
+                        long long dwav_bstride, long long L, float* loss, dm_stream_t stream);
+
+/* Dereverberation (operator.py:244-250): y[i] = sum_k xz[i+k] ir[k], zero padding K/2, by overlap-save FFT.
+ * tw4096: [4096][2] exp(-2 pi i m/4096); w8192: [2049][2] exp(-2 pi i k/8192).  K <= DM_RIR_MAX_TAPS.
+ * spec: caller-owned (2 * 4097) floats, written by dm_rir_spectrum, read by the other two. */
+#define DM_RIR_FFT 8192
+#define DM_RIR_MAX_TAPS 6144
+int dm_rir_spectrum(const float* ir, int K, const float* tw4096, const float* w8192, float* spec,
+                    dm_stream_t stream);
+int dm_rir_correlate(const float* x, long long x_bstride, long long L, int B, const float* spec, int K,
+                     const float* tw4096, const float* w8192, float* y, long long Ly, dm_stream_t stream);
+/* xbar[j] = (1/loss) * sum_k fold(ybar)[j + K/2 - k] ir[k]    */
+int dm_rir_adjoint(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
+                   const float* spec, int K, const float* tw4096, const float* w8192, float* dwav,
+                   long long dwav_bstride, long long L, float* loss, dm_stream_t stream);
+
+/* y[b, j] = x[b, j] * mask[j]   (MusicInpaintingOperator.forward, operator.py:132-133) */
+int dm_mask_apply(const float* x, long long x_bstride, long long L, int B, const float* mask, float* y,
+                  dm_stream_t stream);
+
+/* y += sigma * noise  (GaussianNoise.forward, noise.py:13-18, with the torch-drawn noise as an input) */
+int dm_add_scaled(float* y, const float* noise, float sigma, long long n, dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * FAD embedding statistics (fadtk/fad.py:41-47, fadtk/utils.py:13-46): raw moments of an (N, d) fp16 block,
+ * accumulated (+=) into acc = [n | sum x (d) | sum x x^T (d*d)] in float64.  All-reducing acc over ranks (one NCCL
+ * sum) and finalising mu = sx/n, cov = (sxx - n mu mu^T)/(n-1) equals the reference's Chan merge.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int dm_fad_moments(const void* x_f16, long long N, int d, double* acc, dm_stream_t stream);
+/* mu (d) and cov (d, d) in float64 from acc */
+int dm_fad_finalize(const double* acc, int d, double* mu, double* cov, dm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DM_ABI_H_ */

@@ -1,6 +1,7 @@
 // Host emulation of the device phase functions in diffmusic_b200/csrc/{fft_core,stft_frame}.cuh.
 // TEST INFRASTRUCTURE: compiled with g++ by tests/test_cpu_emulation.py; never shipped, never on the product path.
 // Every phase is run for all 64 "threads" of a frame group before the next phase starts (= the GPU barrier).
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -97,5 +98,73 @@ void emul_stft_guidance(const EmulTables* e, int mode, int clamp, const float* y
     if (mode == 0) run<kModeMelDb>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
     else if (mode == 1) run<kModePhaseMel>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
     else run<kModePhaseWav>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
+}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Overlap-save RIR correlation / adjoint (diffmusic_b200/csrc/rir_block.cuh), same block loop as rir_conv.cu
+#include "../../diffmusic_b200/csrc/rir_block.cuh"
+
+namespace {
+struct EmulRir {
+    std::vector<float> buf;
+    RirSmem s;
+    EmulRir() : buf(kRirSmemFloats, 0.f) {
+        float* p = buf.data();
+        s.a_re = p; p += padded_len(kRirH); s.a_im = p; p += padded_len(kRirH);
+        s.b_re = p; p += padded_len(kRirH); s.b_im = p;
+    }
+};
+struct SrcX {
+    const float* x; long long off, L; float scale;
+    float operator()(int n) const { long long i = off + n; return (i >= 0 && i < L) ? x[i] * scale : 0.f; }
+};
+}  // namespace
+
+extern "C" {
+void emul_rir_spectrum(const float* ir, int K, const float* tw4096, const float* w8192, float* spec) {
+    EmulRir e;
+    const cf* tw = reinterpret_cast<const cf*>(tw4096);
+    const cf* w = reinterpret_cast<const cf*>(w8192);
+    SrcX src{ir, 0, K, 1.f};
+    RirStore st{nullptr, 0, 0, 0.f};
+    for (int ph = 0; ph < 4; ++ph)
+        for (int tid = 0; tid < kRirThreads; ++tid) rir_block_phase<false>(ph, tid, tw, w, nullptr, e.s, src, st);
+    for (int tid = 0; tid < kRirThreads; ++tid)
+        rir_unpack_spectrum(tid, PadLoad{e.s.b_re, e.s.b_im}, w, reinterpret_cast<cf*>(spec));
+}
+
+void emul_rir_correlate(const float* x, long long L, const float* spec, int K, const float* tw4096,
+                        const float* w8192, float* y) {
+    EmulRir e;
+    RirGeom g = rir_geom(L, K);
+    const cf* tw = reinterpret_cast<const cf*>(tw4096);
+    const cf* w = reinterpret_cast<const cf*>(w8192);
+    const long long nblk = (g.nout + g.valid - 1) / g.valid;
+    for (long long b = 0; b < nblk; ++b) {
+        long long i0 = b * g.valid;
+        SrcX src{x, i0 - g.pad, L, 1.f};
+        RirStore st{y + i0, 0, (int)std::min<long long>(g.valid, g.nout - i0), 1.0f / kRirN};
+        for (int ph = 0; ph < kRirPhases; ++ph)
+            for (int tid = 0; tid < kRirThreads; ++tid)
+                rir_block_phase<true>(ph, tid, tw, w, reinterpret_cast<const cf*>(spec), e.s, src, st);
+    }
+}
+
+void emul_rir_adjoint(const float* ybar, long long L, const float* spec, int K, const float* tw4096,
+                      const float* w8192, float scale, float* xbar) {
+    EmulRir e;
+    RirGeom g = rir_geom(L, K);
+    const cf* tw = reinterpret_cast<const cf*>(tw4096);
+    const cf* w = reinterpret_cast<const cf*>(w8192);
+    const long long nblk = (L + g.valid - 1) / g.valid;
+    for (long long b = 0; b < nblk; ++b) {
+        long long j0 = b * g.valid;
+        SrcX src{ybar, j0 + g.pad - (K - 1), g.nout, scale};
+        RirStore st{xbar + j0, K - 1, (int)std::min<long long>(g.valid, L - j0), 1.0f / kRirN};
+        for (int ph = 0; ph < kRirPhases; ++ph)
+            for (int tid = 0; tid < kRirThreads; ++tid)
+                rir_block_phase<false>(ph, tid, tw, w, reinterpret_cast<const cf*>(spec), e.s, src, st);
+    }
 }
 }

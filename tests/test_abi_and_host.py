@@ -1,0 +1,129 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol include/dm_abi.h declares; the host-side
+mirror keeps the reference's names, signatures and integer work (no kernel is launched here)."""
+import inspect
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from diffmusic_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from diffmusic_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "dm_abi.h")).read()
+    declared = set(re.findall(r"\b(dm_[a-z0-9_]+)\s*\(", header))
+    declared -= {"dm_stft_tables"}
+    assert len(declared) >= 24
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in dm_abi.h but not exported"
+        assert name in _lib.EXPORTS, f"{name} has no ctypes signature in _lib.py"
+    assert set(_lib.EXPORTS) <= declared
+    assert lib.dm_version() == 100
+    assert lib.dm_launch_count() == 0
+
+
+def test_no_cpu_fallback_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("needs a CPU-only box")
+    import diffmusic_b200 as dm
+    from diffmusic_b200._lib import DiffMusicB200Error
+    op = dm.IdentityOperator(16000)
+    with pytest.raises(DiffMusicB200Error):
+        op.transform(torch.zeros(1, 16000))
+    with pytest.raises(DiffMusicB200Error):
+        op.guidance_loss(torch.zeros(1, 16000), torch.zeros(1, 16000))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "diffmusic_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_masks_bit_exact(golden_ops):
+    import diffmusic_b200 as dm
+    kw = dict(audio_length_in_s=10, sample_rate=16000, mask_percentage=0.3, interval_s=1, mask_duration_s=0.1)
+    cases = {"mask_box_10s": dict(mask_type="box", start_inpainting_s=2, end_inpainting_s=3),
+             "mask_boxfrac_10s": dict(mask_type="box", start_inpainting_s=1.37, end_inpainting_s=2.913),
+             "mask_periodic_10s": dict(mask_type="periodic", start_inpainting_s=None, end_inpainting_s=None)}
+    for key, c in cases.items():
+        op = dm.MusicInpaintingOperator(**kw, **c)
+        assert op.mask.shape == (1, 160000) and op.mask.dtype == torch.float32
+        assert np.array_equal(np.packbits(op.mask[0].numpy().astype(np.uint8)), golden_ops[key]), key
+    torch.manual_seed(7)
+    op = dm.MusicInpaintingOperator(mask_type="random", start_inpainting_s=None, end_inpainting_s=None, **kw)
+    assert np.array_equal(np.packbits(op.mask[0].numpy().astype(np.uint8)), golden_ops["mask_random_seed7_10s"])
+
+
+def test_impulse_response_draw(golden_ops):
+    import diffmusic_b200 as dm
+    for K, decay in ((800, 0.85), (5000, 0.99), (801, 0.9)):
+        op = dm.MusicDereverberationOperator(ir_length=K, decay_factor=decay)
+        torch.manual_seed(100 + K)
+        ir = op.generate_impulse_response(ir_length=K, decay_factor=decay)
+        assert np.array_equal(ir.numpy(), golden_ops[f"dereverb_ir_K{K}"])
+
+
+def test_scheduler_surface(golden_steps):
+    """names, ctor kwargs, step signatures and defaults of SURVEY.md 8(b)."""
+    import diffmusic_b200 as dm
+    from tests import stubs
+    defaults = {"ddim": (0.0, None), "dps": (0.0, 5e-4), "mpgd": (0.0, 1.0), "dsg": (1.0, 0.08),
+                "diffmusic": (0.0, 0.08)}
+    for name, (eta, rate) in defaults.items():
+        cls = dm.get_scheduler(name)
+        s = cls(operator="op", **stubs.MUSICLDM_SCHED)
+        assert s.operator == "op" and s.config.clip_sample is False and s.config.steps_offset == 1
+        assert s.order == 1 and s.init_noise_sigma == 1.0
+        s.set_timesteps(500)
+        assert np.array_equal(np.asarray(s.timesteps), golden_steps["timesteps_500"])
+        assert np.array_equal(s.alphas_cumprod.numpy(), golden_steps["alphas_cumprod"])
+        assert float(s.final_alpha_cumprod) == float(golden_steps["final_alpha_cumprod"])
+        x = torch.zeros(2)
+        assert s.scale_model_input(x, 3) is x
+        sig = inspect.signature(s.step)
+        for p in ("model_output", "timestep", "sample", "eta", "generator", "variance_noise", "measurement", "vae",
+                  "vocoder", "original_waveform_length"):
+            assert p in sig.parameters, (name, p)
+        assert sig.parameters["eta"].default == eta
+        if rate is not None:
+            assert sig.parameters["ip_guidance_rate"].default == rate
+            assert sig.parameters["supervised_space"].default == "mel_spectrogram"
+        assert any(p.kind == p.VAR_KEYWORD for p in sig.parameters.values())  # swallows ditto_optimizer, init_latents
+        assert hasattr(s, "optim_prompt")
+    with pytest.raises(ValueError):
+        dm.get_scheduler("nope")
+    with pytest.raises(ValueError):
+        dm.get_noiser("nope", 0.0)
+    assert isinstance(dm.get_noiser("gaussian", 0.0), dm.GaussianNoise)
+    assert isinstance(dm.get_noiser("poisson", 1.0), dm.PoissonNoise)
+
+
+def test_dropin_namespace_imports():
+    """the reference's import paths resolve to this package when diffmusic_b200/dropin is first on sys.path."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "from diffmusic.schedulers import get_scheduler;"
+            "from diffmusic.schedulers.utils import InverseProblemSchedulerOutput;"
+            "from diffmusic.inverse_problem import get_noiser;"
+            "from diffmusic.inverse_problem.operator import (IdentityOperator, MusicInpaintingOperator,"
+            " PhaseRetrievalOperator, SuperResolutionOperator, MusicDereverberationOperator, StyleGuidanceOperator);"
+            "import diffmusic_b200; assert get_scheduler('dsg') is diffmusic_b200.DSGScheduler; print('ok')"
+            % (ROOT, os.path.join(ROOT, "diffmusic_b200", "dropin")))
+    out = subprocess.check_output([sys.executable, "-c", code], text=True)
+    assert out.strip().endswith("ok")

@@ -180,3 +180,34 @@ def test_phase_guidance(emul, space):
     loss, g = _torch_loss_grad(op, wav, meas, space)
     assert abs(np.sqrt(ss) - loss) < 1e-4 * loss
     assert rel_l2(_fold(ypbar, L) / np.sqrt(ss), g) < 1e-4
+
+
+@pytest.mark.parametrize("K,L", [(800, 5000), (801, 4097), (5000, 9000), (6144, 3000)])
+def test_rir_overlap_save(emul, K, L):
+    """dereverberation correlation + its adjoint through the device phase functions vs torch conv1d / autograd."""
+    g = torch.Generator().manual_seed(K)
+    h = torch.randn(1, K, generator=g)
+    h = torch.cumsum(h, 1) * 0.99
+    h = h / h.abs().max()
+    x = torch.randn(1, L, generator=g)
+    tw = tables.twiddles(4096).numpy().copy()
+    w = tables.half_twiddles(8192).numpy().copy()
+    spec = np.zeros((4097, 2), np.float32)
+    hn = h[0].numpy().copy()
+    emul.emul_rir_spectrum(_ptr(hn), K, _ptr(tw), _ptr(w), _ptr(spec))
+    want = np.fft.rfft(hn.astype(np.float64), 8192)
+    assert rel_l2(np.stack([spec[:, 0], spec[:, 1]]), np.stack([want.real, want.imag])) < 1e-6
+    xx = x.clone().requires_grad_(True)
+    y = oo.a_dereverb(xx, h)
+    nout = y.shape[1]
+    assert nout == L + 2 * (K // 2) - K + 1
+    got = np.zeros(nout, np.float32)
+    xn = x[0].numpy().copy()
+    emul.emul_rir_correlate(_ptr(xn), C.c_longlong(L), _ptr(spec), K, _ptr(tw), _ptr(w), _ptr(got))
+    assert rel_l2(got, y[0].detach()) < 2e-6
+    yb = torch.randn(1, nout, generator=g)
+    (gx,) = torch.autograd.grad((y * yb).sum(), xx)
+    gotb = np.zeros(L, np.float32)
+    ybn = yb[0].numpy().copy()
+    emul.emul_rir_adjoint(_ptr(ybn), C.c_longlong(L), _ptr(spec), K, _ptr(tw), _ptr(w), C.c_float(0.5), _ptr(gotb))
+    assert rel_l2(gotb, 0.5 * gx[0]) < 2e-6

@@ -1,0 +1,339 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI by the host-side mirror,
+against (a) the committed golden fixtures produced by the reference's own Python and (b) the CPU oracle on the same
+seeded inputs.  Tolerance: <= 1e-4 relative L2 for operator outputs, gradients and per-step latents in fp32
+(BASELINE.json north_star); masks / indices bit-exact (tests/test_abi_and_host.py)."""
+import numpy as np
+import pytest
+import torch
+
+import diffmusic_b200 as dm
+from oracle import operators as oo
+from oracle import steps as osteps
+from tests import stubs
+from tests.conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+L1, LP = 16000, 4000
+DEV = "cuda"
+
+
+def _noiser():
+    return dm.get_noiser("gaussian", 0.0)
+
+
+def _inpaint(seconds=1, start=0.25, end=0.5):
+    return dm.MusicInpaintingOperator(audio_length_in_s=seconds, sample_rate=16000, mask_type="box",
+                                      start_inpainting_s=start, end_inpainting_s=end, mask_percentage=0.3,
+                                      mask_duration_s=0.1, interval_s=1, noiser=_noiser())
+
+
+def _loss_grad(op, wav, meas, space):
+    w = wav.clone().requires_grad_(True)
+    loss = op.guidance_loss(w, meas, space)
+    (g,) = torch.autograd.grad(loss.sum(), w)
+    return loss.detach(), g
+
+
+# ------------------------------------------------------------------------------------------------ operators vs golden
+def test_forward_and_transform_vs_golden(golden_ops):
+    wav = stubs.synth_clips(2, L1).to(DEV)
+    ident, inp = dm.IdentityOperator(16000), _inpaint()
+    assert rel_l2(ident.transform(wav), golden_ops["identity_transform"]) < TOL
+    assert ident.forward(wav) is wav
+    y = inp.forward(wav)
+    assert np.array_equal(y.cpu().numpy(), golden_ops["inpaint_forward"])  # x * {0,1}: exact
+    assert rel_l2(inp.transform(y), golden_ops["inpaint_transform"]) < TOL
+    for s in (2, 10):
+        sr = dm.SuperResolutionOperator(sample_rate=16000, scale=s, noiser=_noiser())
+        y = sr.forward(wav)
+        assert y.shape == golden_ops[f"superres_forward_s{s}"].shape
+        assert rel_l2(y, golden_ops[f"superres_forward_s{s}"]) < TOL
+        assert rel_l2(sr.transform(y), golden_ops[f"superres_transform_s{s}"]) < TOL
+    ph = dm.PhaseRetrievalOperator(noiser=_noiser())
+    mag = ph.forward(wav[:, :LP])
+    assert mag.shape == golden_ops["phase_forward"].shape
+    assert rel_l2(mag, golden_ops["phase_forward"]) < TOL
+    assert rel_l2(ph.transform(mag), golden_ops["phase_transform"]) < TOL
+    for K, decay in ((800, 0.85), (5000, 0.99), (801, 0.9)):
+        dv = dm.MusicDereverberationOperator(ir_length=K, decay_factor=decay, noiser=_noiser())
+        torch.manual_seed(100 + K)
+        y = dv.forward(wav)
+        assert np.array_equal(dv.last_ir.numpy(), golden_ops[f"dereverb_ir_K{K}"])
+        assert y.shape == golden_ops[f"dereverb_forward_K{K}"].shape
+        assert rel_l2(y, golden_ops[f"dereverb_forward_K{K}"]) < TOL
+
+
+def test_forward_accepts_cpu_tensors_like_run_py(golden_ops):
+    """run.py:286,312 builds the measurement from CPU tensors; result comes back on the CPU."""
+    wav = stubs.synth_clips(2, L1)
+    sr = dm.SuperResolutionOperator(sample_rate=16000, scale=2, noiser=_noiser())
+    y = sr.forward(wav)
+    assert y.device.type == "cpu" and rel_l2(y, golden_ops["superres_forward_s2"]) < TOL
+    m = dm.IdentityOperator(16000).transform(wav)
+    assert m.device.type == "cpu" and rel_l2(m, golden_ops["identity_transform"]) < TOL
+
+
+def test_gaussian_noise_matches_reference_draw(golden_ops):
+    wav = stubs.synth_clips(1, L1)[:, :256]
+    torch.manual_seed(5)
+    out = dm.get_noiser("gaussian", 0.05)(wav)
+    assert np.array_equal(out.numpy(), golden_ops["gaussian_noise_s0.05_seed5"])
+    # CUDA tensors: same torch draw, added by dm_add_scaled
+    torch.manual_seed(5)
+    n = torch.randn_like(wav.to(DEV))
+    torch.manual_seed(5)
+    out = dm.get_noiser("gaussian", 0.05)(wav.to(DEV))
+    assert rel_l2(out, wav.to(DEV) + n * 0.05) < 1e-7
+
+
+@pytest.mark.parametrize("space", ["mel_spectrogram", "wav_form"])
+def test_loss_and_vjp_vs_golden(golden_ops, space):
+    wav = stubs.synth_clips(1, L1).to(DEV)
+    ref = stubs.synth_clips(1, L1, first=50).to(DEV)
+    ops = {"inpaint": _inpaint(),
+           "superres_s2": dm.SuperResolutionOperator(16000, scale=2, noiser=_noiser()),
+           "superres_s10": dm.SuperResolutionOperator(16000, scale=10, noiser=_noiser())}
+    if space == "mel_spectrogram":
+        ops["identity"] = dm.IdentityOperator(16000)
+    for name, op in ops.items():
+        loss, g = _loss_grad(op, wav, op.forward(ref), space)
+        gl = float(golden_ops[f"{name}_{space}_loss"])
+        assert abs(float(loss) - gl) <= TOL * abs(gl), name
+        assert rel_l2(g, golden_ops[f"{name}_{space}_grad"]) < TOL, name
+    for K, decay in ((800, 0.85), (5000, 0.99), (801, 0.9)):
+        dv = dm.MusicDereverberationOperator(ir_length=K, decay_factor=decay, noiser=_noiser())
+        torch.manual_seed(100 + K)
+        meas = dv.forward(ref)
+        torch.manual_seed(100 + K)
+        loss, g = _loss_grad(dv, wav, meas, space)
+        gl = float(golden_ops[f"dereverb_K{K}_{space}_loss"])
+        assert abs(float(loss) - gl) <= TOL * abs(gl), K
+        assert rel_l2(g, golden_ops[f"dereverb_K{K}_{space}_grad"]) < TOL, K
+    ph = dm.PhaseRetrievalOperator(noiser=_noiser())
+    loss, g = _loss_grad(ph, wav[:, :LP], ph.forward(ref[:, :LP]), space)
+    gl = float(golden_ops[f"phase_{space}_loss"])
+    assert abs(float(loss) - gl) <= TOL * abs(gl)
+    assert rel_l2(g, golden_ops[f"phase_{space}_grad"]) < TOL
+
+
+def test_loss_only_path_matches():
+    """no_grad evaluation (loss only) equals the loss of the fused forward+VJP launch."""
+    wav = stubs.synth_clips(2, L1).to(DEV)
+    ref = stubs.synth_clips(1, L1, first=50).to(DEV)
+    for op in (_inpaint(), dm.SuperResolutionOperator(16000, 2, _noiser()),
+               dm.MusicDereverberationOperator(800, 0.85, _noiser())):
+        torch.manual_seed(1)
+        meas = op.forward(ref)
+        torch.manual_seed(2)
+        with torch.no_grad():
+            l0 = op.guidance_loss(wav, meas, "mel_spectrogram")
+        torch.manual_seed(2)
+        l1, _ = _loss_grad(op, wav, meas, "mel_spectrogram")
+        assert torch.equal(l0, l1)
+
+
+# ------------------------------------------------------------------------------------------------ scheduler steps
+def _ops():
+    return {"inpainting": _inpaint(),
+            "super_resolution": dm.SuperResolutionOperator(sample_rate=16000, scale=2, noiser=_noiser()),
+            "phase_retrieval": dm.PhaseRetrievalOperator(noiser=_noiser()),
+            "dereverberation": dm.MusicDereverberationOperator(ir_length=800, decay_factor=0.85, noiser=_noiser()),
+            "identity": dm.IdentityOperator(sample_rate=16000)}
+
+
+RATES = {"ddim": None, "dps": 5e-4, "mpgd": 0.005, "dsg": 0.08, "diffmusic": 0.08}
+
+
+def test_steps_vs_reference_golden(golden_steps):
+    """all 33 (scheduler, operator, space, eta, t) cases the reference's own scheduler files were run on."""
+    vae, voc = stubs.StubVAE().to(DEV), stubs.StubVocoder().to(DEV)
+    ref_wav = stubs.synth_clips(1, L1, first=50).to(DEV)
+    x, e = stubs.synth_latents(1, 25)
+    x, e = x.to(DEV), e.to(DEV)
+    ops = _ops()
+    cases = [k[:-5] for k in golden_steps.files if k.endswith("|prev")]
+    assert len(cases) == 33
+    worst = 0.0
+    for key in cases:
+        sched_name, op_name, space, eta, t = key.split("|")
+        eta, t = float(eta[3:]), int(t[1:])
+        op = ops[op_name]
+        sched = dm.get_scheduler(sched_name)(operator=op, **stubs.MUSICLDM_SCHED)
+        sched.set_timesteps(500)
+        torch.manual_seed(321)
+        meas = op.forward(ref_wav)
+        kwargs = dict(eta=eta, generator=torch.Generator().manual_seed(3000), measurement=meas, vae=vae, vocoder=voc,
+                      original_waveform_length=L1)
+        if RATES[sched_name] is not None:
+            kwargs.update(ip_guidance_rate=RATES[sched_name], supervised_space=space)
+        torch.manual_seed(654 + t)
+        out = sched.step(e, t, x, **kwargs)
+        ep, e0 = rel_l2(out.prev_sample, golden_steps[key + "|prev"]), rel_l2(out.pred_original_sample,
+                                                                               golden_steps[key + "|x0"])
+        worst = max(worst, ep, e0)
+        assert ep < TOL and e0 < TOL, (key, ep, e0)
+        gl = float(golden_steps[key + "|loss"].ravel()[0])
+        assert abs(float(out.loss.float().ravel()[0]) - gl) <= TOL * max(1.0, abs(gl)), key
+        assert not out.prev_sample.requires_grad and out.loss.numel() == 1
+    print("worst rel-L2 over 33 reference step cases:", worst)
+
+
+@pytest.mark.parametrize("sched_name,op_name,eta", [("dps", "super_resolution", 0.0), ("mpgd", "inpainting", 1.0),
+                                                    ("dsg", "phase_retrieval", 1.0), ("diffmusic", "inpainting", 1.0),
+                                                    ("diffmusic", "dereverberation", 1.0)])
+def test_batched_step_is_per_clip(sched_name, op_name, eta):
+    """B = 3 with a list of generators == three independent batch-1 oracle steps."""
+    B = 3
+    vae, voc = stubs.StubVAE(), stubs.StubVocoder()
+    ref_wav = stubs.synth_clips(B, L1, first=50)
+    x, e = stubs.synth_latents(B, 25)
+    mask = oo.inpaint_mask(1, 16000, "box", 0.25, 0.5)
+    ir = None
+    if op_name == "dereverberation":
+        torch.manual_seed(9)
+        ir = oo.draw_impulse_response(800, 0.85)
+    oops = {"inpainting": oo.OracleOperator("inpainting", mask=mask),
+            "super_resolution": oo.OracleOperator("super_resolution", scale=2),
+            "phase_retrieval": oo.OracleOperator("phase_retrieval"),
+            "dereverberation": oo.OracleOperator("dereverberation", fixed_ir=ir)}
+    oop = oops[op_name]
+    meas = oop.forward(ref_wav)  # per-clip measurements (B, ...)
+    base = osteps.make_base(**stubs.MUSICLDM_SCHED)
+    base.set_timesteps(500)
+    t = 501
+    want = osteps.per_clip_step(sched_name, base, oop, e, t, x, generators=stubs.step_generators(B),
+                                measurement=meas, eta=eta, ip_guidance_rate=RATES[sched_name], vae=vae, vocoder=voc,
+                                original_waveform_length=L1, supervised_space="mel_spectrogram")
+    op = _ops()[op_name]
+    if ir is not None:
+        op.generate_impulse_response = lambda ir_length, decay_factor: ir  # same IR as the oracle
+    sched = dm.get_scheduler(sched_name)(operator=op, **stubs.MUSICLDM_SCHED)
+    sched.set_timesteps(500)
+    got = sched.step(e.to(DEV), t, x.to(DEV), eta=eta, generator=stubs.step_generators(B),
+                     measurement=meas.to(DEV), vae=vae.to(DEV), vocoder=voc.to(DEV), original_waveform_length=L1,
+                     ip_guidance_rate=RATES[sched_name], supervised_space="mel_spectrogram")
+    assert rel_l2(got.prev_sample, want.prev_sample) < TOL
+    assert rel_l2(got.pred_original_sample, want.pred_original_sample) < TOL
+    assert rel_l2(got.loss_per_clip, want.loss) < TOL
+    assert abs(float(got.loss) - float(torch.linalg.norm(want.loss))) < TOL * float(torch.linalg.norm(want.loss))
+    for i in range(B):  # every clip individually, not just in aggregate
+        assert rel_l2(got.prev_sample[i], want.prev_sample[i]) < TOL
+
+
+def test_step_argument_errors():
+    op = _inpaint()
+    sched = dm.DPSScheduler(operator=op, **stubs.MUSICLDM_SCHED)
+    sched.set_timesteps(500)
+    x, e = stubs.synth_latents(1, 25)
+    vae, voc = stubs.StubVAE().to(DEV), stubs.StubVocoder().to(DEV)
+    meas = op.forward(stubs.synth_clips(1, L1).to(DEV))
+    kw = dict(measurement=meas, vae=vae, vocoder=voc, original_waveform_length=L1)
+    with pytest.raises(ValueError):
+        sched.step(e.to(DEV), 501, x.to(DEV), supervised_space="nope", **kw)
+    with pytest.raises(ValueError):
+        sched.step(e.to(DEV), 501, x.to(DEV), eta=1.0, generator=torch.Generator().manual_seed(0),
+                   variance_noise=torch.zeros_like(x).to(DEV), **kw)
+    # unknown kwargs the pipelines pass are swallowed
+    out = sched.step(e.to(DEV), 501, x.to(DEV), ditto_optimizer=None, init_latents=None, **kw)
+    assert torch.isfinite(out.loss)
+    # DDIM accepts missing encoder_hidden_states (superset of the reference)
+    d = dm.DDIMScheduler(operator=op, **stubs.MUSICLDM_SCHED)
+    d.set_timesteps(500)
+    o = d.step(e.to(DEV), 501, x.to(DEV), **kw)
+    assert o.loss.tolist() == [501] and o.encoder_hidden_states is None
+
+
+def test_nan_propagates_to_loss_like_the_reference():
+    """pipeline_musicldm.py:742: the caller restarts on torch.isnan(out.loss); a NaN waveform must surface there."""
+    op = _inpaint()
+    wav = stubs.synth_clips(1, L1).to(DEV)
+    meas = op.forward(wav)
+    bad = wav.clone()
+    bad[0, 9000] = float("nan")
+    loss, g = _loss_grad(op, bad, meas, "mel_spectrogram")
+    assert torch.isnan(loss).all()
+    # zero residual -> zero gradient (torch.linalg.norm backward is masked at 0)
+    loss, g = _loss_grad(op, wav, meas, "wav_form")
+    assert float(loss) == 0.0 and float(g.abs().max()) == 0.0
+
+
+def test_bit_reproducible():
+    op = dm.SuperResolutionOperator(16000, 2, _noiser())
+    wav = stubs.synth_clips(4, L1).to(DEV)
+    meas = op.forward(stubs.synth_clips(1, L1, first=50).to(DEV))
+    a = _loss_grad(op, wav, meas, "mel_spectrogram")
+    b = _loss_grad(op, wav, meas, "mel_spectrogram")
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize("op_name", ["inpainting", "super_resolution", "dereverberation", "phase_retrieval"])
+def test_full_size_10s_against_oracle(op_name):
+    """BASELINE config shapes (10 s, L = 160000, T = 1001) against the CPU oracle: loss and gradient."""
+    L, B = 160000, 2
+    wav = stubs.synth_clips(B, L)
+    ref = stubs.synth_clips(1, L, first=50)
+    mask = oo.inpaint_mask(10, 16000, "box", 2, 3)
+    torch.manual_seed(77)
+    ir = oo.draw_impulse_response(5000, 0.99)
+    oop = {"inpainting": oo.OracleOperator("inpainting", mask=mask),
+           "super_resolution": oo.OracleOperator("super_resolution", scale=2),
+           "dereverberation": oo.OracleOperator("dereverberation", fixed_ir=ir),
+           "phase_retrieval": oo.OracleOperator("phase_retrieval")}[op_name]
+    op = {"inpainting": _inpaint(10, 2, 3),
+          "super_resolution": dm.SuperResolutionOperator(16000, 2, _noiser()),
+          "dereverberation": dm.MusicDereverberationOperator(5000, 0.99, _noiser()),
+          "phase_retrieval": dm.PhaseRetrievalOperator(noiser=_noiser())}[op_name]
+    if op_name == "dereverberation":
+        op.generate_impulse_response = lambda ir_length, decay_factor: ir
+    meas = oop.forward(ref)
+    assert rel_l2(op.forward(ref.to(DEV)), meas) < TOL
+    for i in range(B):
+        w = wav[i:i + 1].clone().requires_grad_(True)
+        want = torch.linalg.norm(oop.transform(meas) - oop.transform(oop.forward(w)))
+        (gw,) = torch.autograd.grad(want, w)
+        loss, g = _loss_grad(op, wav[i:i + 1].to(DEV), meas.to(DEV), "mel_spectrogram")
+        assert abs(float(loss) - float(want)) < TOL * float(want)
+        assert rel_l2(g, gw) < TOL
+
+
+def test_operator_linearity_and_adjoint_identity():
+    """size-independent properties at full size: A is linear; <A x, y> == <x, A^T y> for the VJP kernels."""
+    L, B = 160000, 2
+    g = torch.Generator().manual_seed(4)
+    x1, x2 = torch.randn(B, L, generator=g).to(DEV), torch.randn(B, L, generator=g).to(DEV)
+    torch.manual_seed(3)
+    ir = oo.draw_impulse_response(5000, 0.99)
+    dv = dm.MusicDereverberationOperator(5000, 0.99, _noiser())
+    dv.generate_impulse_response = lambda ir_length, decay_factor: ir
+    for op in (_inpaint(10, 2, 3), dm.SuperResolutionOperator(16000, 2, _noiser()), dv):
+        a = op.forward(x1 + 2.0 * x2)
+        b = op.forward(x1) + 2.0 * op.forward(x2)
+        assert rel_l2(a, b) < 1e-5
+        # adjoint identity through the wav-space fused path: loss = ||m - A x||, grad = -A^T (m - A x)/loss
+        m = torch.randn_like(op.forward(x1))
+        loss, grad = _loss_grad(op, x1, m, "wav_form")
+        d = m - op.forward(x1)
+        for i in range(B):
+            lhs = float((op.forward(x2)[i].double() * d[i].double()).sum())        # <A x2, d>
+            rhs = float(-(x2[i].double() * grad[i].double()).sum() * float(loss[i]))  # <x2, A^T d>
+            assert abs(lhs - rhs) <= 2e-4 * max(abs(lhs), abs(rhs), 1.0)
+
+
+# ------------------------------------------------------------------------------------------------ FAD statistics
+@pytest.mark.parametrize("n,d", [(40, 128), (1000, 512), (4990, 768), (333, 1024)])
+def test_fad_statistics_vs_numpy(n, d):
+    from diffmusic_b200 import fad
+    from oracle import fad as ofad
+    rng = np.random.default_rng(d)
+    X = (rng.standard_normal((n, d)) * 0.7 + rng.standard_normal(d) * 0.3).astype(np.float16)
+    mu, cov = fad.calc_embd_statistics(X)
+    wmu, wcov = ofad.calc_embd_statistics(X.astype(np.float64))
+    assert rel_l2(mu, wmu) < 1e-6 and rel_l2(cov, wcov) < 1e-5
+    # file-wise online merge (fadtk/utils.py:19-46) == one pass over all frames
+    parts = np.array_split(X, 7)
+    mu2, cov2 = fad.calculate_embd_statistics_online(parts)
+    omu, ocov = ofad.embd_statistics_online([p.astype(np.float64) for p in parts])
+    assert rel_l2(mu2, omu) < 1e-6 and rel_l2(cov2, ocov) < 1e-5
+    assert np.allclose(cov2, cov2.T)
