@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kThreads) ew_update_kernel(EwParams p, long lo
 #pragma unroll
             for (int i = 0; i < W; ++i) {
                 float t = dvd(sub(x[i], mul(p.sqrt_b, a[i])), p.sqrt_a);
-                if (p.clip) t = fminf(fmaxf(t, -p.clip_range), p.clip_range);
+                if (p.clip) t = t < -p.clip_range ? -p.clip_range : (t > p.clip_range ? p.clip_range : t);  // NaN-preserving
                 o[i] = t;
             }
             stv<W>(p.x0_out, v, o);

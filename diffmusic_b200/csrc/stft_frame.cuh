@@ -21,6 +21,10 @@ constexpr int kBins = 513;  // one-sided bins
 constexpr int kMels = 64;
 constexpr int kGroupThreads = 64;
 
+// clamp that propagates NaN like torch.clamp (fminf/fmaxf would swallow it and hide a diverged sample from the
+// pipelines' NaN guard, pipeline_musicldm.py:742)
+DM_HD float clamp_nan(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
 enum StftMode { kModeMelDb = 0, kModePhaseMel = 1, kModePhaseWav = 2 };
 
 // Device/host constant tables (built on the host by diffmusic_b200/tables.py from torch / torchaudio tensors).
@@ -102,19 +106,19 @@ DM_HD float mel_residual(int m, const StftTables& t, FrameSmem s, bool clamp, bo
     for (int i = 0; i < n; ++i) acc = fmaf(w[i], s.p[k0 + i], acc);
     float val, dval_dmel;  // transformed value and its derivative w.r.t. the mel energy
     if (MODE == kModeMelDb) {
-        float c = fmaxf(acc, 1e-10f);
+        float c = acc < 1e-10f ? 1e-10f : acc;  // torch.clamp(min=amin): NaN stays NaN
         float db = 10.0f * log10f(c);
         dval_dmel = (acc >= 1e-10f) ? (4.342944819032518f / c) : 0.f;  // 10 / ln(10) / mel
         val = db;
         if (clamp) {
-            val = fminf(fmaxf(db, -80.f), 80.f);
+            val = clamp_nan(db, -80.f, 80.f);
             if (!(db >= -80.f && db <= 80.f)) dval_dmel = 0.f;
         }
     } else {  // phase_mel: clamp(mel of magnitude, +-80), no log
         val = acc;
         dval_dmel = 1.f;
         if (clamp) {
-            val = fminf(fmaxf(acc, -80.f), 80.f);
+            val = clamp_nan(acc, -80.f, 80.f);
             if (!(acc >= -80.f && acc <= 80.f)) dval_dmel = 0.f;
         }
     }

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(128) mel_project_kernel(const float* __restric
     const float* src = mag + ((long long)b * kBins + k0) * T + t;
     float acc = 0.f;
     for (int i = 0; i < n; ++i) acc = fmaf(__ldg(w + i), src[(long long)i * T], acc);
-    if (clamp) acc = fminf(fmaxf(acc, -80.f), 80.f);
+    if (clamp) acc = clamp_nan(acc, -80.f, 80.f);
     out[((long long)b * kMels + m) * T + t] = acc;
 }
 
