@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="call scheduler.step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -230,15 +231,22 @@ def main():
     _ops_mod._lib.call = timed_call
     _sch_mod._lib.call = timed_call
 
-    def one_step(i, host):
-        if host:
-            xs, es = x_pin.to(device, non_blocking=True), e_pin.to(device, non_blocking=True)
+    import diffmusic_b200 as dm
+    graphed = None if args.eager else dm.GraphedGuidedStep(sched, tuple(x_d.shape), clone_outputs=False, **kw)
+
+    def one_step(i, host, eager=False):
+        t = ts[i % len(ts)]
+        xs, es = (x_pin, e_pin) if host else (x_d, e_d)
+        if graphed is None or eager:
+            if host:
+                xs, es = xs.to(device, non_blocking=True), es.to(device, non_blocking=True)
+            out = sched.step(es, t, xs, generator=gens, **kw)
         else:
-            xs, es = x_d, e_d
-        out = sched.step(es, ts[i % len(ts)], xs, generator=gens, **kw)
+            out = graphed(es, t, xs, generator=gens)  # copies (H2D when host) into its static buffers, then replays
         if host:
             prev_pin.copy_(out.prev_sample, non_blocking=True)
-            loss_pin.copy_(out.loss_per_clip, non_blocking=True)
+            lo = out.loss_per_clip if out.loss_per_clip is not None else out.loss.float().to(device)
+            loss_pin[: lo.numel()].copy_(lo.reshape(-1), non_blocking=True)
         return out
 
     def timed_region(host):
@@ -249,7 +257,6 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        timed_call.on = not host
         launches0 = _lib.launch_count()
         for i in range(args.steps):
             flush.fill_(float(i))  # evict L2 between timed iterations (not timed)
@@ -259,8 +266,9 @@ def main():
             t.record()
             per_step.append((s, t))
         torch.cuda.synchronize()
-        timed_call.on = False
         launches = _lib.launch_count() - launches0
+        if graphed is not None:
+            launches += graphed.kernels_per_replay * args.steps  # kernel nodes replayed from the captured graph
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -272,8 +280,16 @@ def main():
 
     with ClockSampler(local) as clk:
         total_ms, launches = timed_region(host=False)
-        dom_ms = [s.elapsed_time(t) for s, t in dom_events]
         e2e_ms, _ = timed_region(host=True)
+        # the dominant kernel, timed live with CUDA events on its launching stream inside eager steps (a graph replay
+        # has no per-kernel event hooks), L2 flushed before every step as above
+        timed_call.on = True
+        for i in range(args.steps):
+            flush.fill_(float(i))
+            one_step(args.warmup + i, False, eager=True)
+        torch.cuda.synchronize()
+        timed_call.on = False
+        dom_ms = [s.elapsed_time(t) for s, t in dom_events]
     clocks = clk.summary()
 
     if rank == 0:
@@ -300,6 +316,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": WORKLOADS[args.workload][5], "name": args.workload, "clips_per_gpu": B,
+                           "mode": "eager scheduler.step" if graphed is None else "CUDA-graph replay of scheduler.step",
                            "l2": "flushed between timed steps (256 MB write)",
                            "networks": "torch stand-ins for vae.decode / vocoder (stay in PyTorch, inside the step)"},
                 "e2e": {"value": e2e_value, "unit": "clip-steps/s", "h2d_bytes_per_step": 2 * x_h.numel() * 4,

@@ -26,13 +26,14 @@ _SIGNATURES = {
     "dm_last_error": (C.c_char_p, []),
     "dm_launch_count": (C.c_ulonglong, []),
     "dm_reset_launch_count": (None, []),
-    "dm_sched_x0": (c_i, [c_p, c_p, c_p, c_ll, c_f, c_f, c_i, c_f, c_p]),
-    "dm_sched_ddim_update": (c_i, [c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_p]),
-    "dm_sched_dps_update": (c_i, [c_p, c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_p]),
-    "dm_sched_mpgd_update": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_p]),
-    "dm_sched_dsg_update": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_p]),
+    "dm_sched_x0": (c_i, [c_p, c_p, c_p, c_ll, c_f, c_f, c_i, c_f, c_p, c_p]),
+    "dm_sched_ddim_update": (c_i, [c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_p, c_p]),
+    "dm_sched_dps_update": (c_i, [c_p, c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_p, c_p]),
+    "dm_sched_mpgd_update": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_p, c_p]),
+    "dm_sched_dsg_update": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_p,
+                                  c_p]),
     "dm_sched_diffmusic_update": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
-                                        c_p]),
+                                        c_p, c_p]),
     "dm_stft_num_tiles": (c_i, [c_ll, c_i, c_i]),
     "dm_stft_guidance": (c_i, [C.POINTER(StftTables), c_i, c_i, c_i, c_p, c_ll, c_ll, c_p, c_i, c_p, c_ll, c_p, c_f,
                                c_p, c_p, c_p, c_i, c_p]),

@@ -40,6 +40,17 @@ inline int fail(int code, const char* fmt, A... a) {
             return dm::fail(DM_ERR_CUDA, "%s: %s failed: %s", __func__, #call, cudaGetErrorString(e__));   \
     } while (0)
 
+// Raise the dynamic shared-memory limit of a kernel.  The limit only ever grows, and the call is skipped once it is
+// large enough, so steady-state launches (and CUDA-graph capture) make no non-stream runtime calls.
+#define DM_SMEM_ONCE(kernel, bytes)                                                                        \
+    do {                                                                                                   \
+        static size_t have__ = 0;                                                                          \
+        if ((size_t)(bytes) > have__) {                                                                    \
+            DM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            have__ = (size_t)(bytes);                                                                      \
+        }                                                                                                  \
+    } while (0)
+
 inline cudaStream_t as_stream(dm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline int num_sms() {

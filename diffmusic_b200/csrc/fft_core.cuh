@@ -20,6 +20,9 @@ namespace dm {
 struct cf {
     float x, y;
 };
+struct alignas(8) f2 {  // 64-bit pair for vector shared-memory accesses
+    float x, y;
+};
 
 DM_HD cf cmul(cf a, cf b) { return cf{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 DM_HD cf cadd(cf a, cf b) { return cf{a.x + b.x, a.y + b.y}; }
@@ -77,6 +80,35 @@ DM_HD void stockham_pass(int j, const cf* __restrict__ tw, Load load, Store stor
             if (SIGN > 0) w.y = -w.y;
             v[r] = cmul(v[r], w);
         }
+    }
+    dft8<SIGN>(v);
+    const int j0 = (j / NS) * NS * 8 + k;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) store(j0 + q * NS, v[q]);
+}
+
+// Same pass with the thread's seven twiddles held in registers.  Thread j of a group always owns the same k, so a
+// kernel that transforms many frames loads w[] once (thread_twiddles) instead of 7 conflicted shared-memory reads per
+// pass and frame.  w[r-1] is the FORWARD twiddle exp(-2 pi i r k / (8 NS)); conjugated here for SIGN = +1.
+template <int N, int NS>
+DM_HD void thread_twiddles(int j, const cf* __restrict__ tw, cf (&w)[7]) {
+    constexpr int TWS = N / (NS * 8);
+    const int k = j % NS;
+#pragma unroll
+    for (int r = 1; r < 8; ++r) w[r - 1] = tw[r * k * TWS];
+}
+template <int N, int NS, int SIGN, class Load, class Store>
+DM_HD void stockham_pass_rt(int j, const cf (&w)[7], Load load, Store store) {
+    constexpr int T = N / 8;
+    const int k = j % NS;
+    cf v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = load(j + r * T);
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+        cf t = w[r - 1];
+        if (SIGN > 0) t.y = -t.y;
+        v[r] = cmul(v[r], t);
     }
     dft8<SIGN>(v);
     const int j0 = (j / NS) * NS * 8 + k;

@@ -72,56 +72,81 @@ __global__ void __launch_bounds__(kEwThreads) fold_adjoint_kernel(const float* _
 }
 
 // ---------------------------------------------------------------------------------------------------- resampling
+// Both directions stage the input span of a CTA's output chunk in shared memory once (coalesced, with the reflect
+// fold and the 1/loss scale applied on the way in for the adjoint) and then run the short FIR out of shared memory
+// with 32-bit index arithmetic.
+constexpr int kRsChunk = 2048;  // outputs per CTA
+
 __global__ void __launch_bounds__(kEwThreads) resample_fwd_kernel(const float* __restrict__ x, long long x_bstride,
                                                                   long long L, const float* __restrict__ kernel,
                                                                   int n_new, int taps, int orig, int width,
-                                                                  float* __restrict__ y, long long Ly) {
-    extern __shared__ float kw[];  // [n_new * taps]
-    for (int i = threadIdx.x; i < n_new * taps; i += kEwThreads) kw[i] = kernel[i];
-    __syncthreads();
+                                                                  float* __restrict__ y, long long Ly, int span) {
+    extern __shared__ float sm[];
+    float* kw = sm;                   // [n_new * taps]
+    float* xs = sm + n_new * taps;    // [span] input samples orig*j_lo - width ...
     const int b = blockIdx.y;
+    const long long o0 = (long long)blockIdx.x * kRsChunk;
+    const int no = (int)min((long long)kRsChunk, Ly - o0);
+    const long long j_lo = o0 / n_new;
+    const long long x_lo = (long long)orig * j_lo - width;
+    for (int i = threadIdx.x; i < n_new * taps; i += kEwThreads) kw[i] = __ldg(kernel + i);
     const float* xb = x + (long long)b * x_bstride;
-    const long long o = (long long)blockIdx.x * kEwThreads + threadIdx.x;
-    if (o >= Ly) return;
-    const long long j = o / n_new;
-    const int ph = (int)(o - j * n_new);
-    const float* w = kw + ph * taps;
-    const long long i0 = (long long)orig * j - width;
-    float acc = 0.f;
-    for (int k = 0; k < taps; ++k) {
-        long long i = i0 + k;
-        if (i >= 0 && i < L) acc = fmaf(xb[i], w[k], acc);
+    for (int i = threadIdx.x; i < span; i += kEwThreads) {
+        long long g = x_lo + i;
+        xs[i] = (g >= 0 && g < L) ? xb[g] : 0.f;
     }
-    y[(long long)b * Ly + o] = acc;
+    __syncthreads();
+    const int ph0 = (int)(o0 - j_lo * n_new);
+    for (int t = threadIdx.x; t < no; t += kEwThreads) {
+        const int q = ph0 + t;
+        const int jr = q / n_new, ph = q - jr * n_new;  // block index relative to j_lo, phase
+        const float* w = kw + ph * taps;
+        const float* xv = xs + jr * orig;
+        float acc = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < taps; ++k) acc = fmaf(xv[k], w[k], acc);
+        y[(long long)b * Ly + o0 + t] = acc;
+    }
 }
 
 __global__ void __launch_bounds__(kEwThreads) resample_adjoint_kernel(
     const float* __restrict__ ybar, int pad, long long Ly, const float* __restrict__ partial, int ntiles,
     const float* __restrict__ kernel, int n_new, int taps, int orig, int width, float* __restrict__ dwav,
-    long long dwav_bstride, long long L, float* __restrict__ loss) {
-    extern __shared__ float kw[];
+    long long dwav_bstride, long long L, float* __restrict__ loss, int span) {
+    extern __shared__ float sm[];
     __shared__ float scratch[2];
-    for (int i = threadIdx.x; i < n_new * taps; i += kEwThreads) kw[i] = kernel[i];
+    float* kw = sm;                 // [n_new * taps]
+    float* ys = sm + n_new * taps;  // [span] folded, scaled cotangent of the resampled signal
     const int b = blockIdx.y;
-    const float l = clip_loss(partial + (long long)b * ntiles, ntiles, scratch);  // contains __syncthreads
+    const float l = clip_loss(partial + (long long)b * ntiles, ntiles, scratch);
     if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[b] = l;
     const float sc = inv_loss(l);
-    const long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x;
-    if (i >= L) return;
+    const long long i0 = (long long)blockIdx.x * kRsChunk;
+    const int ni = (int)min((long long)kRsChunk, L - i0);
+    // blocks j with 0 <= i + width - orig*j < taps for some i of the chunk
+    const long long num = i0 + width - taps + 1;
+    const long long j_lo = num <= 0 ? 0 : (num + orig - 1) / orig;
+    const long long o_lo = j_lo * n_new;
+    for (int i = threadIdx.x; i < n_new * taps; i += kEwThreads) kw[i] = __ldg(kernel + i);
     const float* yb = ybar + (long long)b * (Ly + 2 * pad);
-    // output blocks j with 0 <= i + width - orig*j < taps
-    const long long num = i + width - taps + 1;
-    const long long jlo = num <= 0 ? 0 : (num + orig - 1) / orig;
-    const long long jhi = (i + width) / orig;
-    float acc = 0.f;
-    for (long long j = jlo; j <= jhi; ++j) {
-        const int k = (int)(i + width - (long long)orig * j);
-        for (int ph = 0; ph < n_new; ++ph) {
-            const long long o = j * n_new + ph;
-            if (o < Ly) acc = fmaf(ybar_at(yb, pad, o, Ly), kw[ph * taps + k], acc);
-        }
+    for (int i = threadIdx.x; i < span; i += kEwThreads) {
+        long long o = o_lo + i;
+        ys[i] = (o < Ly) ? ybar_at(yb, pad, o, Ly) * sc : 0.f;
     }
-    dwav[(long long)b * dwav_bstride + i] = acc * sc;
+    __syncthreads();
+    for (int t = threadIdx.x; t < ni; t += kEwThreads) {
+        const long long i = i0 + t;
+        const long long n2 = i + width - taps + 1;
+        const int ja = (int)((n2 <= 0 ? 0 : (n2 + orig - 1) / orig) - j_lo);  // relative first block
+        const int jb = (int)((i + width) / orig - j_lo);                      // relative last block
+        float acc = 0.f;
+        for (int j = ja; j <= jb; ++j) {
+            const int k = (int)(i + width - (long long)orig * (j_lo + j));
+            const float* yv = ys + j * n_new;
+            for (int ph = 0; ph < n_new; ++ph) acc = fmaf(yv[ph], kw[ph * taps + k], acc);
+        }
+        dwav[(long long)b * dwav_bstride + i] = acc;
+    }
 }
 
 __global__ void __launch_bounds__(kEwThreads) mask_apply_kernel(const float* __restrict__ x, long long x_bstride,
@@ -174,10 +199,15 @@ extern "C" int dm_resample_fwd(const float* x, long long x_bstride, long long L,
                                dm_stream_t stream) {
     DM_REQUIRE(x && kernel && y && L > 0 && B > 0 && Ly > 0);
     DM_REQUIRE(n_new >= 1 && taps >= 1 && orig >= 1 && width >= 0);
-    DM_REQUIRE((size_t)n_new * taps * sizeof(float) <= 48 * 1024);
-    const int nblk = (int)((Ly + kEwThreads - 1) / kEwThreads);
-    resample_fwd_kernel<<<dim3(nblk, B), kEwThreads, (size_t)n_new * taps * sizeof(float), as_stream(stream)>>>(
-        x, x_bstride, L, kernel, n_new, taps, orig, width, y, Ly);
+    // input span of one chunk: blocks j_lo .. j_lo + ceil((chunk + n_new - 1)/n_new), each orig apart, plus the taps
+    const int span = ((kRsChunk + n_new - 1) / n_new + 1) * orig + taps;
+    const size_t smem = ((size_t)n_new * taps + span) * sizeof(float);
+    if (smem > 200 * 1024) return fail(DM_ERR_UNSUPPORTED, "%s: resampling ratio %d/%d needs %zu B of shared memory",
+                                       __func__, n_new, orig, smem);
+    DM_SMEM_ONCE(resample_fwd_kernel, smem);
+    const int nblk = (int)((Ly + kRsChunk - 1) / kRsChunk);
+    resample_fwd_kernel<<<dim3(nblk, B), kEwThreads, smem, as_stream(stream)>>>(x, x_bstride, L, kernel, n_new, taps,
+                                                                                orig, width, y, Ly, span);
     DM_LAUNCHED();
     return DM_OK;
 }
@@ -187,10 +217,15 @@ extern "C" int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int
                                    long long dwav_bstride, long long L, float* loss, dm_stream_t stream) {
     DM_REQUIRE(ybar && partial && kernel && dwav && L > 0 && B > 0 && Ly > 0 && ntiles > 0);
     DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 513));
-    DM_REQUIRE((size_t)n_new * taps * sizeof(float) <= 48 * 1024);
-    const int nblk = (int)((L + kEwThreads - 1) / kEwThreads);
-    resample_adjoint_kernel<<<dim3(nblk, B), kEwThreads, (size_t)n_new * taps * sizeof(float), as_stream(stream)>>>(
-        ybar, pad, Ly, partial, ntiles, kernel, n_new, taps, orig, width, dwav, dwav_bstride, L, loss);
+    // cotangent span of one chunk of inputs: (chunk + taps)/orig + 2 blocks of n_new samples
+    const int span = ((kRsChunk + taps) / orig + 2) * n_new;
+    const size_t smem = ((size_t)n_new * taps + span) * sizeof(float);
+    if (smem > 200 * 1024) return fail(DM_ERR_UNSUPPORTED, "%s: resampling ratio %d/%d needs %zu B of shared memory",
+                                       __func__, n_new, orig, smem);
+    DM_SMEM_ONCE(resample_adjoint_kernel, smem);
+    const int nblk = (int)((L + kRsChunk - 1) / kRsChunk);
+    resample_adjoint_kernel<<<dim3(nblk, B), kEwThreads, smem, as_stream(stream)>>>(
+        ybar, pad, Ly, partial, ntiles, kernel, n_new, taps, orig, width, dwav, dwav_bstride, L, loss, span);
     DM_LAUNCHED();
     return DM_OK;
 }

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kRirThreads) rir_spectrum_kernel(const float* 
     rir_unpack_spectrum(threadIdx.x, PadLoad{s.b_re, s.b_im}, w8192, spec);
 }
 
-__global__ void __launch_bounds__(kRirThreads) rir_correlate_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(kRirThreads, 2) rir_correlate_kernel(const float* __restrict__ x,
                                                                     long long x_bstride, RirGeom g,
                                                                     const cf* __restrict__ spec,
                                                                     const cf* __restrict__ tw,
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kRirThreads) rir_correlate_kernel(const float*
     }
 }
 
-__global__ void __launch_bounds__(kRirThreads) rir_adjoint_kernel(const float* __restrict__ ybar, int pad,
+__global__ void __launch_bounds__(kRirThreads, 2) rir_adjoint_kernel(const float* __restrict__ ybar, int pad,
                                                                   RirGeom g, const float* __restrict__ partial,
                                                                   int ntiles, const cf* __restrict__ spec,
                                                                   const cf* __restrict__ tw,
@@ -111,8 +111,7 @@ extern "C" int dm_rir_spectrum(const float* ir, int K, const float* tw4096, cons
                                dm_stream_t stream) {
     DM_REQUIRE(ir && tw4096 && w8192 && spec);
     DM_REQUIRE(K >= 1 && K <= DM_RIR_MAX_TAPS);
-    DM_CUDA(cudaFuncSetAttribute(rir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kRirSmemBytes));
+    DM_SMEM_ONCE(rir_spectrum_kernel, kRirSmemBytes);
     rir_spectrum_kernel<<<1, kRirThreads, kRirSmemBytes, as_stream(stream)>>>(
         ir, K, reinterpret_cast<const cf*>(tw4096), reinterpret_cast<const cf*>(w8192), reinterpret_cast<cf*>(spec));
     DM_LAUNCHED();
@@ -127,8 +126,7 @@ extern "C" int dm_rir_correlate(const float* x, long long x_bstride, long long L
     RirGeom g = rir_geom(L, K);
     DM_REQUIRE(Ly == g.nout);
     const int nblk = (int)((g.nout + g.valid - 1) / g.valid);
-    DM_CUDA(cudaFuncSetAttribute(rir_correlate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kRirSmemBytes));
+    DM_SMEM_ONCE(rir_correlate_kernel, kRirSmemBytes);
     rir_correlate_kernel<<<dim3(nblk, B), kRirThreads, kRirSmemBytes, as_stream(stream)>>>(
         x, x_bstride, g, reinterpret_cast<const cf*>(spec), reinterpret_cast<const cf*>(tw4096),
         reinterpret_cast<const cf*>(w8192), y);
@@ -145,8 +143,7 @@ extern "C" int dm_rir_adjoint(const float* ybar, int pad, long long Ly, int B, c
     DM_REQUIRE(Ly == g.nout);
     DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 513));
     const int nblk = (int)((L + g.valid - 1) / g.valid);
-    DM_CUDA(cudaFuncSetAttribute(rir_adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kRirSmemBytes));
+    DM_SMEM_ONCE(rir_adjoint_kernel, kRirSmemBytes);
     rir_adjoint_kernel<<<dim3(nblk, B), kRirThreads, kRirSmemBytes, as_stream(stream)>>>(
         ybar, pad, g, partial, ntiles, reinterpret_cast<const cf*>(spec), reinterpret_cast<const cf*>(tw4096),
         reinterpret_cast<const cf*>(w8192), dwav, dwav_bstride, loss);

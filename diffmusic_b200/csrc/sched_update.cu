@@ -66,12 +66,26 @@ struct EwParams {
     float* x0_out;
     float sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate, clip_range;
     int clip;
+    const float* coef;  // optional device-resident [sqrt_a, sqrt_b, sqrt_p, dir_coef, std, r]: overrides the by-value
+                        // scalars so a captured CUDA graph can be replayed for every timestep
 };
+
+__device__ __forceinline__ void load_coef(const float* __restrict__ c, float& sqrt_a, float& sqrt_b, float& sqrt_p,
+                                          float& dir_coef, float& std) {
+    if (c != nullptr) {
+        sqrt_a = __ldg(c + 0);
+        sqrt_b = __ldg(c + 1);
+        sqrt_p = __ldg(c + 2);
+        dir_coef = __ldg(c + 3);
+        std = __ldg(c + 4);
+    }
+}
 
 enum EwKind { kX0 = 0, kDdim = 1, kDps = 2, kMpgd = 3 };
 
 template <int KIND, int W>
 __global__ void __launch_bounds__(kThreads) ew_update_kernel(EwParams p, long long nvec) {
+    load_coef(p.coef, p.sqrt_a, p.sqrt_b, p.sqrt_p, p.dir_coef, p.std);
     const long long stride = (long long)gridDim.x * kThreads;
     for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += stride) {
         float x[W], a[W], g[W], z[W], o[W], o2[W];
@@ -132,6 +146,7 @@ struct NormParams {
     float* prev;
     long long n_clip;
     float sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, threshold;
+    const float* coef;  // optional device-resident coefficients (see EwParams::coef)
 };
 
 // block-level sum of up to 3 doubles, result broadcast through smem slot `out[0..2]`
@@ -170,6 +185,11 @@ enum NormKind { kDsg = 0, kDiffMusic = 1 };
 template <int KIND, int W>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) norm_update_kernel(NormParams p) {
     cg::cluster_group cluster = cg::this_cluster();
+    if (p.coef != nullptr) {
+        float unused_b;
+        load_coef(p.coef, p.sqrt_a, unused_b, p.sqrt_p, p.dir_coef, p.std);
+        p.r = __ldg(p.coef + 5);
+    }
     __shared__ double wred[(kThreads / 32) * 3];
     __shared__ double slot1[3], slot2[3];
     const unsigned rank = cluster.block_rank();
@@ -287,9 +307,10 @@ static int launch_norm(const NormParams& p, int n_clips, cudaStream_t st) {
 using namespace dm;
 
 extern "C" int dm_sched_x0(const float* x, const float* eps, float* x0, long long n, float sqrt_a, float sqrt_b,
-                           int clip, float clip_range, dm_stream_t stream) {
+                           int clip, float clip_range, const float* coef, dm_stream_t stream) {
     DM_REQUIRE(x && eps && x0 && n > 0);
     EwParams p{};
+    p.coef = coef;
     p.x = x;
     p.eps = eps;
     p.x0_out = x0;
@@ -303,9 +324,11 @@ extern "C" int dm_sched_x0(const float* x, const float* eps, float* x0, long lon
 }
 
 extern "C" int dm_sched_ddim_update(const float* x, const float* x0, float* prev, long long n, float sqrt_a,
-                                    float sqrt_b, float sqrt_p, float sqrt_1mp, dm_stream_t stream) {
+                                    float sqrt_b, float sqrt_p, float sqrt_1mp, const float* coef,
+                                    dm_stream_t stream) {
     DM_REQUIRE(x && x0 && prev && n > 0);
     EwParams p{};
+    p.coef = coef;
     p.x = x;
     p.x0 = x0;
     p.prev = prev;
@@ -320,9 +343,10 @@ extern "C" int dm_sched_ddim_update(const float* x, const float* x0, float* prev
 
 extern "C" int dm_sched_dps_update(const float* x, const float* x0, const float* g0, const float* z, float* prev,
                                    long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std,
-                                   float rate, dm_stream_t stream) {
+                                   float rate, const float* coef, dm_stream_t stream) {
     DM_REQUIRE(x && x0 && g0 && prev && n > 0);
     EwParams p{};
+    p.coef = coef;
     p.x = x;
     p.x0 = x0;
     p.g0 = g0;
@@ -341,9 +365,11 @@ extern "C" int dm_sched_dps_update(const float* x, const float* x0, const float*
 
 extern "C" int dm_sched_mpgd_update(const float* x, const float* x0, const float* g0, const float* z, float* prev,
                                     float* x0_out, long long n, float sqrt_a, float sqrt_b, float sqrt_p,
-                                    float dir_coef, float std, float rate, dm_stream_t stream) {
+                                    float dir_coef, float std, float rate, const float* coef,
+                                    dm_stream_t stream) {
     DM_REQUIRE(x && x0 && g0 && prev && x0_out && n > 0);
     EwParams p{};
+    p.coef = coef;
     p.x = x;
     p.x0 = x0;
     p.g0 = g0;
@@ -363,9 +389,10 @@ extern "C" int dm_sched_mpgd_update(const float* x, const float* x0, const float
 
 extern "C" int dm_sched_dsg_update(const float* x0, const float* eps, const float* g0, const float* z, float* prev,
                                    int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef,
-                                   float std, float rate, float r, float grad_scale, float e, dm_stream_t stream) {
+                                   float std, float rate, float r, float grad_scale, float e, const float* coef,
+                                   dm_stream_t stream) {
     DM_REQUIRE(x0 && eps && g0 && z && prev && n_clips > 0 && n_clip > 0);
-    NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, 0.f};
+    NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, 0.f, coef};
     launch_norm<kDsg>(p, n_clips, as_stream(stream));
     DM_LAUNCHED();
     return DM_OK;
@@ -374,9 +401,10 @@ extern "C" int dm_sched_dsg_update(const float* x0, const float* eps, const floa
 extern "C" int dm_sched_diffmusic_update(const float* x0, const float* eps, const float* g0, const float* z,
                                          float* prev, int n_clips, long long n_clip, float sqrt_a, float sqrt_p,
                                          float dir_coef, float std, float rate, float grad_scale, float e,
-                                         float threshold, dm_stream_t stream) {
+                                         float threshold, const float* coef, dm_stream_t stream) {
     DM_REQUIRE(x0 && eps && g0 && z && prev && n_clips > 0 && n_clip > 0);
-    NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, 0.f, grad_scale, e, threshold};
+    NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, 0.f, grad_scale, e, threshold,
+                 coef};
     launch_norm<kDiffMusic>(p, n_clips, as_stream(stream));
     DM_LAUNCHED();
     return DM_OK;

@@ -55,16 +55,39 @@ struct FrameSmem {
 };
 constexpr int kFrameSmemFloats = 4 * padded_len(kH) + 3 * 520 + 64 + 72;
 
+// Per-thread constants of the frame pipeline (thread gt of a 64-thread group always owns the same twiddles and the
+// same mel band), loaded once per CTA.
+struct ThreadConsts {
+    cf w8[7];    // pass NS = 8 twiddles
+    cf w64[7];   // pass NS = 64 twiddles
+    int mel_k0, mel_n;
+};
+DM_HD void load_thread_consts(int gt, const StftTables& t, ThreadConsts& c) {
+    thread_twiddles<kH, 8>(gt, t.tw512, c.w8);
+    thread_twiddles<kH, 64>(gt, t.tw512, c.w64);
+    c.mel_k0 = t.mel_kstart[gt];
+    c.mel_n = t.mel_klen[gt];
+}
+
 // ---- forward FFT: three Stockham passes. frame[] is the (already masked) signal tile in shared memory. ----
-DM_HD void fwd_pass1(int tid, const StftTables& t, const float* frame, const float* window, FrameSmem s) {
-    auto load = [&](int i) { return cf{frame[2 * i] * window[2 * i], frame[2 * i + 1] * window[2 * i + 1]}; };
-    stockham_pass<kH, 1, -1>(tid, t.tw512, load, PadStore{s.a_re, s.a_im});
+// ALIGNED8: frame and window are 8-byte aligned (even hop), so sample pairs are fetched with one 64-bit access.
+template <bool ALIGNED8>
+DM_HD void fwd_pass1(int tid, const float* frame, const float* window, FrameSmem s) {
+    auto load = [&](int i) {
+        if (ALIGNED8) {
+            const f2 f = reinterpret_cast<const f2*>(frame)[i];
+            const f2 w = reinterpret_cast<const f2*>(window)[i];
+            return cf{f.x * w.x, f.y * w.y};
+        }
+        return cf{frame[2 * i] * window[2 * i], frame[2 * i + 1] * window[2 * i + 1]};
+    };
+    stockham_pass<kH, 1, -1>(tid, nullptr, load, PadStore{s.a_re, s.a_im});
 }
-DM_HD void fwd_pass2(int tid, const cf* tw, FrameSmem s) {
-    stockham_pass<kH, 8, -1>(tid, tw, PadLoad{s.a_re, s.a_im}, PadStore{s.b_re, s.b_im});
+DM_HD void fwd_pass2(int tid, const ThreadConsts& c, FrameSmem s) {
+    stockham_pass_rt<kH, 8, -1>(tid, c.w8, PadLoad{s.a_re, s.a_im}, PadStore{s.b_re, s.b_im});
 }
-DM_HD void fwd_pass3(int tid, const cf* tw, FrameSmem s) {
-    stockham_pass<kH, 64, -1>(tid, tw, PadLoad{s.b_re, s.b_im}, PadStore{s.a_re, s.a_im});
+DM_HD void fwd_pass3(int tid, const ThreadConsts& c, FrameSmem s) {
+    stockham_pass_rt<kH, 64, -1>(tid, c.w64, PadLoad{s.b_re, s.b_im}, PadStore{s.a_re, s.a_im});
 }
 
 // ---- unpack Z (in a_re/a_im, natural order) to the real-FFT spectrum X and the per-bin energy ----
@@ -98,12 +121,12 @@ DM_HD void fwd_unpack(int tid, const cf* w1024, FrameSmem s) {
 // ---- mel projection + dB + clamp + residual (threads 0..63, one mel band each). Returns d^2 (0 if no ref). ----
 // out_val receives the transformed value (what operator.transform returns); melbar gets dLoss_unscaled/dMel.
 template <int MODE>
-DM_HD float mel_residual(int m, const StftTables& t, FrameSmem s, bool clamp, bool has_ref, float ref_val,
-                         float* out_val) {
-    const int k0 = t.mel_kstart[m], n = t.mel_klen[m];
-    const float* w = t.mel_w + m * t.mel_wstride;
+DM_HD float mel_residual(int m, const ThreadConsts& c, const float* melw_t, FrameSmem s, bool clamp, bool has_ref,
+                         float ref_val, float* out_val) {
+    // melw_t is the banded filterbank TRANSPOSED to [i][64] so the 64 band-threads read consecutive words
+    const int k0 = c.mel_k0, n = c.mel_n;
     float acc = 0.f;
-    for (int i = 0; i < n; ++i) acc = fmaf(w[i], s.p[k0 + i], acc);
+    for (int i = 0; i < n; ++i) acc = fmaf(melw_t[i * kMels + m], s.p[k0 + i], acc);
     float val, dval_dmel;  // transformed value and its derivative w.r.t. the mel energy
     if (MODE == kModeMelDb) {
         float c = acc < 1e-10f ? 1e-10f : acc;  // torch.clamp(min=amin): NaN stays NaN
@@ -179,14 +202,14 @@ DM_HD void bwd_pack(int tid, const StftTables& t, FrameSmem s) {
 }
 
 // ---- inverse FFT: b -> a -> b -> a ; afterwards frame gradient n is a_re[pad(n/2)] (n even) / a_im (n odd) ----
-DM_HD void inv_pass1(int tid, const cf* tw, FrameSmem s) {
-    stockham_pass<kH, 1, +1>(tid, tw, PadLoad{s.b_re, s.b_im}, PadStore{s.a_re, s.a_im});
+DM_HD void inv_pass1(int tid, FrameSmem s) {
+    stockham_pass<kH, 1, +1>(tid, nullptr, PadLoad{s.b_re, s.b_im}, PadStore{s.a_re, s.a_im});
 }
-DM_HD void inv_pass2(int tid, const cf* tw, FrameSmem s) {
-    stockham_pass<kH, 8, +1>(tid, tw, PadLoad{s.a_re, s.a_im}, PadStore{s.b_re, s.b_im});
+DM_HD void inv_pass2(int tid, const ThreadConsts& c, FrameSmem s) {
+    stockham_pass_rt<kH, 8, +1>(tid, c.w8, PadLoad{s.a_re, s.a_im}, PadStore{s.b_re, s.b_im});
 }
-DM_HD void inv_pass3(int tid, const cf* tw, FrameSmem s) {
-    stockham_pass<kH, 64, +1>(tid, tw, PadLoad{s.b_re, s.b_im}, PadStore{s.a_re, s.a_im});
+DM_HD void inv_pass3(int tid, const ThreadConsts& c, FrameSmem s) {
+    stockham_pass_rt<kH, 64, +1>(tid, c.w64, PadLoad{s.b_re, s.b_im}, PadStore{s.a_re, s.a_im});
 }
 DM_HD float frame_grad_sample(const FrameSmem& s, int n) {
     int p = padi(n >> 1);

@@ -51,10 +51,10 @@ __global__ void __launch_bounds__(kCtaThreads) stft_guidance_kernel(const StftPa
     float* sig = smem;
     float* acc = sig + span_alloc;
     float* tilebuf = acc + span_alloc;                    // [nf][kTileLd] ref (guidance) or out (transform)
-    float* win = tilebuf + tile_floats(p.nf);                // [1024]
-    cf* tw = reinterpret_cast<cf*>(win + kNfft);          // [512]
-    cf* w1024 = tw + kH;                                  // [257] (+3 pad)
-    float* grp = reinterpret_cast<float*>(w1024 + 260);
+    float* win = tilebuf + tile_floats(p.nf);             // [1024]
+    cf* w1024 = reinterpret_cast<cf*>(win + kNfft);       // [257] (+3 pad)
+    float* melw_t = reinterpret_cast<float*>(w1024 + 260);  // [mel_wstride][64] transposed banded filterbank
+    float* grp = melw_t + p.tab.mel_wstride * kMels;
     float* red = grp + kGroups * kFrameSmemFloats;        // [8]
     FrameSmem s;
     {
@@ -71,8 +71,10 @@ __global__ void __launch_bounds__(kCtaThreads) stft_guidance_kernel(const StftPa
     }
     StftTables tab = p.tab;
     tab.window = win;
-    tab.tw512 = tw;
     tab.w1024 = w1024;
+    ThreadConsts tc;  // this thread's twiddles and mel band: identical for every frame it will process
+    load_thread_consts(gt, p.tab, tc);
+    const bool aligned8 = (p.hop & 1) == 0;
 
     // ---- stage the signal span, tables and the reference tile ----
     const float* yb = p.y + (long long)b * p.y_bstride;
@@ -84,7 +86,10 @@ __global__ void __launch_bounds__(kCtaThreads) stft_guidance_kernel(const StftPa
         acc[i] = 0.f;
     }
     for (int i = tid; i < kNfft; i += kCtaThreads) win[i] = __ldg(p.tab.window + i);
-    for (int i = tid; i < kH; i += kCtaThreads) tw[i] = p.tab.tw512[i];
+    for (int i = tid; i < p.tab.mel_wstride * kMels; i += kCtaThreads) {
+        int m = i / p.tab.mel_wstride, j = i - m * p.tab.mel_wstride;
+        melw_t[j * kMels + m] = __ldg(p.tab.mel_w + i);
+    }
     for (int i = tid; i < 257; i += kCtaThreads) w1024[i] = p.tab.w1024[i];
     if (gt < 8) s.melbar[64 + gt] = 0.f;
     if (MODE != kModePhaseWav && has_ref) {
@@ -103,11 +108,12 @@ __global__ void __launch_bounds__(kCtaThreads) stft_guidance_kernel(const StftPa
         const bool active = f < nfr;
         if (active) {
             const float* frame = sig + f * p.hop;
-            fwd_pass1(gt, tab, frame, win, s);
+            if (aligned8) fwd_pass1<true>(gt, frame, win, s);
+            else fwd_pass1<false>(gt, frame, win, s);
             group_sync(g);
-            fwd_pass2(gt, tw, s);
+            fwd_pass2(gt, tc, s);
             group_sync(g);
-            fwd_pass3(gt, tw, s);
+            fwd_pass3(gt, tc, s);
             group_sync(g);
             fwd_unpack<MODE>(gt, w1024, s);
             group_sync(g);
@@ -130,19 +136,19 @@ __global__ void __launch_bounds__(kCtaThreads) stft_guidance_kernel(const StftPa
                 }
             } else {
                 float v;
-                lsum += mel_residual<MODE>(gt, tab, s, p.clamp != 0, has_ref, has_ref ? tilebuf[f * kTileLd + gt] : 0.f,
-                                           &v);
+                lsum += mel_residual<MODE>(gt, tc, melw_t, s, p.clamp != 0, has_ref,
+                                           has_ref ? tilebuf[f * kTileLd + gt] : 0.f, &v);
                 if (p.out) tilebuf[f * kTileLd + gt] = v;
             }
             if (want_grad) {
                 group_sync(g);
                 bwd_pack<MODE>(gt, tab, s);
                 group_sync(g);
-                inv_pass1(gt, tw, s);
+                inv_pass1(gt, s);
                 group_sync(g);
-                inv_pass2(gt, tw, s);
+                inv_pass2(gt, tc, s);
                 group_sync(g);
-                inv_pass3(gt, tw, s);
+                inv_pass3(gt, tc, s);
             }
         }
         if (want_grad) {
@@ -209,9 +215,10 @@ __global__ void __launch_bounds__(128) mel_project_kernel(const float* __restric
     out[((long long)b * kMels + m) * T + t] = acc;
 }
 
-static size_t stft_smem_bytes(int nf, int hop) {
+static size_t stft_smem_bytes(int nf, int hop, int mel_wstride) {
     size_t span = (size_t)(nf - 1) * hop + kNfft;
-    size_t fl = 2 * span + (size_t)tile_floats(nf) + kNfft + 2 * kH + 2 * 260 + (size_t)kGroups * kFrameSmemFloats + 8;
+    size_t fl = 2 * span + (size_t)tile_floats(nf) + kNfft + 2 * 260 + (size_t)mel_wstride * kMels +
+                (size_t)kGroups * kFrameSmemFloats + 8;
     return fl * sizeof(float);
 }
 
@@ -259,15 +266,15 @@ extern "C" int dm_stft_guidance(const dm_stft_tables* tab, int mode, int clamp, 
     p.out = out;
     p.ypbar = ypbar;
     p.partial = partial;
-    size_t smem = stft_smem_bytes(p.nf, hop);
+    DM_REQUIRE(tab->mel_wstride >= 1 && tab->mel_wstride <= 64);
+    size_t smem = stft_smem_bytes(p.nf, hop, tab->mel_wstride);
     if (smem > 227 * 1024) return fail(DM_ERR_UNSUPPORTED, "%s: tile needs %zu B of shared memory", __func__, smem);
     dim3 grid(p.ntiles, B), block(kCtaThreads);
     cudaStream_t st = as_stream(stream);
-#define DM_LAUNCH_STFT(M)                                                                                     \
-    do {                                                                                                      \
-        DM_CUDA(cudaFuncSetAttribute(stft_guidance_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                     (int)smem));                                                             \
-        stft_guidance_kernel<M><<<grid, block, smem, st>>>(p);                                                \
+#define DM_LAUNCH_STFT(M)                                          \
+    do {                                                           \
+        DM_SMEM_ONCE(stft_guidance_kernel<M>, smem);               \
+        stft_guidance_kernel<M><<<grid, block, smem, st>>>(p);     \
     } while (0)
     if (mode == DM_STFT_MEL_DB) DM_LAUNCH_STFT(kModeMelDb);
     else if (mode == DM_STFT_PHASE_MEL) DM_LAUNCH_STFT(kModePhaseMel);

@@ -1,0 +1,115 @@
+"""CUDA-graph capture of a whole guided step.
+
+One guided step moves ~2-3 MB per clip and is launch-bound (SURVEY.md 7.3 "tiny problem sizes", 8(f) rank 4): ~40
+kernel launches (ours + the torch networks and their autograd) cost more host time than device time.
+`GraphedGuidedStep` captures `scheduler.step(...)` once -- x0 kernel, vae.decode, vocoder, fused operator/loss/VJP
+kernels, torch autograd back through the networks, fused update kernel -- and replays it for every timestep:
+
+  * latents go through static input buffers; the per-timestep scalars are 24 bytes in a device coefficient vector the
+    scheduler kernels read (`coef` argument of dm_sched_*), so nothing timestep-dependent is baked into the graph;
+  * all randomness stays in torch and outside the graph: the step noise is drawn before the replay with exactly the
+    draws, order and generator semantics of the eager step (`draw_step_noise`), the dereverberation impulse response is
+    drawn on the host as the reference does (operator.py:238-242) and copied into a static buffer;
+  * nothing inside the step synchronises with the host (the slerp branch is resolved on the device).
+"""
+from __future__ import annotations
+
+import torch
+
+from .schedulers import InverseProblemSchedulerOutput
+
+
+class GraphedGuidedStep:
+    """Callable with the call shape of `scheduler.step(model_output, timestep, sample, generator=...)`.
+
+    step_kwargs are the fixed keyword arguments of the step: eta, measurement, vae, vocoder,
+    original_waveform_length, ip_guidance_rate, supervised_space, eps.
+    Returned tensors are fresh copies unless clone_outputs=False (then they are valid until the next call).
+    """
+
+    def __init__(self, scheduler, sample_shape, *, dtype=torch.float32, device=None, clone_outputs=True,
+                 warmup_timestep=None, **step_kwargs):
+        self.sched = scheduler
+        self.kw = dict(step_kwargs)
+        self.eta = float(self.kw.get("eta", _default_eta(scheduler)))
+        self.kw["eta"] = self.eta
+        self.clone = clone_outputs
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.x = torch.zeros(sample_shape, device=dev, dtype=dtype)
+        self.e = torch.zeros(sample_shape, device=dev, dtype=dtype)
+        self.B = sample_shape[0]
+        self.n_clip = self.x.numel() // self.B
+        needs_noise = scheduler.noise_mode == "always" or (self.eta > 0 and type(scheduler).__name__ != "DDIMScheduler")
+        self.z = torch.zeros(sample_shape, device=dev, dtype=torch.float32) if needs_noise else None
+        self.coef = torch.zeros(8, device=dev, dtype=torch.float32)
+        self.coef_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.op = scheduler.operator
+        self._ir_host = self._ir_dev = None
+        if hasattr(self.op, "generate_impulse_response"):  # dereverberation: IR redrawn on the host every step
+            self._ir_host = torch.zeros(self.op.ir_length, dtype=torch.float32).pin_memory()
+            self._ir_dev = torch.zeros(self.op.ir_length, device=dev, dtype=torch.float32)
+            self.op.static_ir = self._ir_dev
+        t0 = int(scheduler.timesteps[0]) if warmup_timestep is None else int(warmup_timestep)
+        self._prepare(t0, None, None)
+        scheduler._coef_dev = self.coef
+        # warm-up on a side stream (allocator pools, lazy module init, cached measurement transform), then capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._run(t0)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import _lib
+        n0 = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._run(t0)
+        #: number of this library's kernels inside one replay (kernel nodes captured from dm_* calls)
+        self.kernels_per_replay = _lib.launch_count() - n0
+        scheduler._coef_dev = None
+        if self._ir_dev is not None:
+            self.op.static_ir = None  # eager calls on the same operator keep drawing their own impulse responses
+
+    def _run(self, t):
+        return self.sched.step(self.e, t, self.x, _noise=self.z if self.z is not None else _NO_NOISE, **self.kw)
+
+    def _prepare(self, timestep, generator, variance_noise):
+        """host-side per-step work: RNG draws (reference order), coefficients, impulse response."""
+        if self.z is not None:
+            z = self.sched.draw_step_noise(self.eta, generator, variance_noise, self.e)
+            self.z.copy_(z, non_blocking=True)
+        elif self.eta > 0:
+            self.sched.draw_step_noise(self.eta, generator, variance_noise, self.e)  # DDIM: discarded draw
+        self.coef_host.copy_(self.sched.coef_vector(timestep, self.eta, self.n_clip))
+        self.coef.copy_(self.coef_host, non_blocking=True)
+        if self._ir_host is not None:
+            ir = self.op.generate_impulse_response(ir_length=self.op.ir_length, decay_factor=self.op.decay_factor)
+            self.op.last_ir = ir
+            self._ir_host.copy_(ir.reshape(-1))
+            self._ir_dev.copy_(self._ir_host, non_blocking=True)
+
+    def __call__(self, model_output, timestep, sample, generator=None, variance_noise=None, **ignored):
+        self.x.copy_(sample, non_blocking=True)
+        self.e.copy_(model_output, non_blocking=True)
+        self._prepare(int(timestep), generator, variance_noise)
+        self.graph.replay()
+        o = self.out
+        if not self.clone:
+            return o
+        return InverseProblemSchedulerOutput(
+            prev_sample=o.prev_sample.clone(), pred_original_sample=o.pred_original_sample.clone(),
+            loss=o.loss.clone() if o.loss.is_cuda else torch.tensor([int(timestep)]),
+            loss_per_clip=None if o.loss_per_clip is None else o.loss_per_clip.clone())
+
+
+class _NoNoise:
+    """sentinel: 'noise handled by the caller, and there is none' (eta == 0)."""
+
+
+_NO_NOISE = _NoNoise()
+
+
+def _default_eta(scheduler):
+    import inspect
+    return inspect.signature(scheduler.step).parameters["eta"].default

@@ -146,7 +146,7 @@ class BaseOperator:
         """noiser(y) (noise.py:13-18) with the noise drawn by torch exactly where the reference draws it, then
         back to the caller's device."""
         sigma = self._sigma()
-        if self.noiser is not None and not isinstance(self.noiser, GaussianNoise):
+        if self.noiser is not None and not hasattr(self.noiser, "sigma"):
             return self.noiser(y.to(like.device))  # e.g. PoissonNoise: host numpy path of the reference, out of scope
         if self.noiser is not None:
             if not like.is_cuda:
@@ -167,6 +167,13 @@ class BaseOperator:
         if supervised_space not in ("wav_form", "mel_spectrogram"):
             raise ValueError("supervised_space should be either 'wav_form' or 'mel_spectrogram")
         return _GuidanceLoss.apply(wav, self, measurement, supervised_space)
+
+    def fused_loss_and_grad(self, wav, measurement, supervised_space="mel_spectrogram"):
+        """(loss (B,), dLoss/dwav (B, L)) from one fused forward+VJP kernel chain; what the schedulers call."""
+        if supervised_space not in ("wav_form", "mel_spectrogram"):
+            raise ValueError("supervised_space should be either 'wav_form' or 'mel_spectrogram")
+        _lib.require_cuda(wav)
+        return self._fused(_as_f32_rows(wav), measurement, supervised_space, True)
 
     def _ref_mel(self, measurement):
         """transform(measurement), cached: the reference recomputes it every step (scheduling_dps.py:205)."""
@@ -459,6 +466,9 @@ class MusicDereverberationOperator(BaseOperator):
         ir /= ir.abs().max()
         return ir.unsqueeze(0)
 
+    # ---- CUDA-graph support: the impulse response lives in a static device buffer the caller refreshes per step ----
+    static_ir = None  # set by GraphedGuidedStep while it captures
+
     def _rir_tables(self, device):
         cache = self.__dict__.setdefault("_rir_cache", {})
         if str(device) not in cache:
@@ -495,8 +505,11 @@ class MusicDereverberationOperator(BaseOperator):
 
     def _fused(self, wav, measurement, space, want_grad):
         B, L = wav.shape
-        ir = self.generate_impulse_response(ir_length=self.ir_length, decay_factor=self.decay_factor)
-        self.last_ir = ir
+        if self.static_ir is not None:
+            ir = self.static_ir  # refreshed by GraphedGuidedStep before every replay (same host-side draw)
+        else:
+            ir = self.generate_impulse_response(ir_length=self.ir_length, decay_factor=self.decay_factor)
+            self.last_ir = ir
         spec, K = self._spectrum(ir, wav.device)
         y = self._correlate(wav, spec, K)
         if self._sigma() != 0.0:
@@ -526,6 +539,8 @@ class StyleGuidanceOperator(BaseOperator):
 
     def forward(self, data, **kwargs):
         return data
+
+    fused_loss_and_grad = None  # no fused kernel: generic path
 
     def guidance_loss(self, wav, measurement, supervised_space="mel_spectrogram"):
         return generic_guidance_loss(self, wav, measurement, supervised_space)

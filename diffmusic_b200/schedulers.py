@@ -72,6 +72,21 @@ class _GuidedBase(DDIMBase):
         return dict(sqrt_a=_f(a_t ** 0.5), sqrt_b=_f(b_t ** 0.5), sqrt_p=_f(a_prev ** 0.5),
                     sqrt_1mp=_f((1 - a_prev) ** 0.5), dir_coef=_f((1 - a_prev - std ** 2) ** 0.5), std=_f(std))
 
+    # ---- CUDA-graph support: when `_coef_dev` is set (GraphedGuidedStep), kernels read the per-timestep scalars from
+    # this device tensor instead of the by-value arguments, so one captured graph serves every timestep ----
+    _coef_dev = None
+
+    def _coef_ptr(self):
+        return None if self._coef_dev is None else self._coef_dev.data_ptr()
+
+    def coef_vector(self, timestep, eta, n_clip):
+        """[sqrt_a, sqrt_b, sqrt_p, dir_coef, std, r, 0, 0] as fp32 -- the layout dm_sched_* read from `coef`."""
+        c = self._coeffs(timestep, eta)
+        dirc = c["sqrt_1mp"] if isinstance(self, DDIMScheduler) else c["dir_coef"]
+        r = _f(torch.sqrt(torch.tensor(n_clip)) * c["std"])
+        return torch.tensor([c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], dirc, c["std"], r, 0.0, 0.0],
+                            dtype=torch.float32)
+
     def _check_supported(self):
         if self.config.prediction_type != "epsilon" or self.config.thresholding:
             raise NotImplementedError("the fused x0 kernel covers prediction_type='epsilon' without dynamic "
@@ -87,32 +102,41 @@ class _GuidedBase(DDIMBase):
         self._check_supported()
         x0 = torch.empty_like(x)
         _lib.call("dm_sched_x0", x.data_ptr(), eps.data_ptr(), x0.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"],
-                  int(bool(self.config.clip_sample)), float(self.config.clip_sample_range), _lib.stream())
+                  int(bool(self.config.clip_sample)), float(self.config.clip_sample_range), self._coef_ptr(),
+                  _lib.stream())
         return x0
 
-    @staticmethod
-    def _base_rng_side_effect(eta, generator, variance_noise, model_output):
-        """diffusers DDIMScheduler.step draws (and the reference discards) one noise tensor when eta > 0."""
-        if eta > 0:
-            if variance_noise is not None and generator is not None:
-                raise ValueError("Cannot pass both generator and variance_noise. Please make sure that either "
-                                 "`generator` or `variance_noise` stays `None`.")
-            if variance_noise is None:
-                randn_tensor(model_output.shape, generator=generator, device=model_output.device,
-                             dtype=model_output.dtype)
+    #: which noise the step consumes: "eta" = base-step draw (discarded) + own z when eta > 0 (DDIM/DPS/MPGD);
+    #: "always" = exactly one z per step, independent of eta (DSG/DiffMusic, scheduling_dsg.py:215-220)
+    noise_mode = "eta"
 
-    @staticmethod
-    def _own_noise(eta, generator, variance_noise, model_output):
-        """scheduling_dps.py:180-191: the step's own z (None when eta == 0)."""
+    def draw_step_noise(self, eta, generator, variance_noise, model_output):
+        """All RNG consumption of one step, in the reference's order, done up front (the values do not depend on
+        where in the step they are drawn; only the per-generator order matters and is kept):
+          DDIM/DPS/MPGD, eta > 0: the diffusers base step draws one tensor the reference discards
+          (scheduling_dps.py:166-175), then the step's own z (:180-191); a given `variance_noise` replaces both draws.
+          DSG/DiffMusic: one z per step (base step is called without eta, so it never draws).
+        Returns z as fp32 (or None)."""
+        shape, dev, dt = model_output.shape, model_output.device, model_output.dtype
+        if self.noise_mode == "always":
+            return randn_tensor(shape, generator=generator, device=dev, dtype=dt).float().contiguous()
         if not eta > 0:
             return None
         if variance_noise is not None and generator is not None:
             raise ValueError("Cannot pass both generator and variance_noise. Please make sure that either "
                              "`generator` or `variance_noise` stays `None`.")
         if variance_noise is None:
-            variance_noise = randn_tensor(model_output.shape, generator=generator, device=model_output.device,
-                                          dtype=model_output.dtype)
+            randn_tensor(shape, generator=generator, device=dev, dtype=dt)  # base-step draw, discarded
+            if isinstance(self, DDIMScheduler):
+                return None
+            variance_noise = randn_tensor(shape, generator=generator, device=dev, dtype=dt)
         return variance_noise.detach().float().contiguous()
+
+    def _noise_arg(self, given, eta, generator, variance_noise, model_output):
+        """step noise: drawn here (eager) unless the caller already did (`_noise`, used by GraphedGuidedStep)."""
+        if given is None:
+            return self.draw_step_noise(eta, generator, variance_noise, model_output)
+        return given if isinstance(given, torch.Tensor) else None
 
     def _guidance(self, x0, measurement, vae, vocoder, L, supervised_space, model_dtype):
         """loss (per clip) and G0 = dLoss/dx0 through vae.decode + vocoder (torch autograd) and the fused operator
@@ -125,11 +149,17 @@ class _GuidedBase(DDIMBase):
             mel = vae.decode(1 / vae.config.scaling_factor * leaf.to(model_dtype)).sample
             wav = op.inverse_transform(mel, vocoder)
             wav = wav[:, :L]
-            if hasattr(op, "guidance_loss"):
-                losses = op.guidance_loss(wav, measurement, supervised_space)
+            if getattr(op, "fused_loss_and_grad", None) is not None:
+                # one fused kernel chain gives the per-clip loss AND dLoss/dwav; torch only continues the VJP through
+                # the vocoder and the VAE decoder (no autograd node, no extra elementwise pass on the waveform)
+                losses, dwav = op.fused_loss_and_grad(wav.detach(), measurement, supervised_space)
+                (g0,) = torch.autograd.grad(wav, leaf, grad_outputs=dwav.to(wav.dtype))
             else:
-                losses = generic_guidance_loss(op, wav, measurement, supervised_space)
-            (g0,) = torch.autograd.grad(losses.sum(), leaf)
+                if hasattr(op, "guidance_loss"):
+                    losses = op.guidance_loss(wav, measurement, supervised_space)
+                else:
+                    losses = generic_guidance_loss(op, wav, measurement, supervised_space)
+                (g0,) = torch.autograd.grad(losses.sum(), leaf)
         return losses.detach(), g0.float().contiguous()
 
     @staticmethod
@@ -162,14 +192,14 @@ class DDIMScheduler(_GuidedBase):
     def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output: bool = False,
              generator=None, variance_noise=None, return_dict: bool = True, measurement=None, vae=None, vocoder=None,
              original_waveform_length: int = 0, encoder_hidden_states=None, encoder_hidden_states_1=None, *args,
-             **kwargs):
+             _noise=None, **kwargs):
         c = self._coeffs(timestep, eta)
         x, eps = self._prep(sample), self._prep(model_output)
+        self._noise_arg(_noise, eta, generator, variance_noise, model_output)
         x0 = self._x0(x, eps, c)
-        self._base_rng_side_effect(eta, generator, variance_noise, model_output)
         prev = torch.empty_like(x)
         _lib.call("dm_sched_ddim_update", x.data_ptr(), x0.data_ptr(), prev.data_ptr(), x.numel(), c["sqrt_a"],
-                  c["sqrt_b"], c["sqrt_p"], c["sqrt_1mp"], _lib.stream())
+                  c["sqrt_b"], c["sqrt_p"], c["sqrt_1mp"], self._coef_ptr(), _lib.stream())
         return InverseProblemSchedulerOutput(
             prev_sample=prev.to(sample.dtype), pred_original_sample=x0.to(sample.dtype),
             loss=torch.tensor([int(timestep)]),
@@ -183,18 +213,17 @@ class DPSScheduler(_GuidedBase):
     def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output: bool = False,
              generator=None, variance_noise=None, return_dict: bool = True, measurement=None,
              ip_guidance_rate: float = 5e-4, vae=None, vocoder=None, original_waveform_length: int = 0,
-             supervised_space: str = "mel_spectrogram", *args, **kwargs):
+             supervised_space: str = "mel_spectrogram", *args, _noise=None, **kwargs):
         c = self._coeffs(timestep, eta)
         x, eps = self._prep(sample), self._prep(model_output)
+        z = self._noise_arg(_noise, eta, generator, variance_noise, model_output)
         x0 = self._x0(x, eps, c)
-        self._base_rng_side_effect(eta, generator, variance_noise, model_output)
-        z = self._own_noise(eta, generator, variance_noise, model_output)
         losses, g0 = self._guidance(x0, measurement, vae, vocoder, original_waveform_length, supervised_space,
                                     sample.dtype)
         prev = torch.empty_like(x)
         _lib.call("dm_sched_dps_update", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), _lib.ptr(z), prev.data_ptr(),
                   x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"], float(ip_guidance_rate),
-                  _lib.stream())
+                  self._coef_ptr(), _lib.stream())
         return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
                                              pred_original_sample=x0.to(sample.dtype), loss=self._loss_out(losses),
                                              loss_per_clip=losses)
@@ -206,18 +235,17 @@ class MPGDScheduler(_GuidedBase):
     def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output: bool = False,
              generator=None, variance_noise=None, return_dict: bool = True, measurement=None,
              ip_guidance_rate: float = 1.0, vae=None, vocoder=None, original_waveform_length: int = 0,
-             supervised_space: str = "mel_spectrogram", *args, **kwargs):
+             supervised_space: str = "mel_spectrogram", *args, _noise=None, **kwargs):
         c = self._coeffs(timestep, eta)
         x, eps = self._prep(sample), self._prep(model_output)
+        z = self._noise_arg(_noise, eta, generator, variance_noise, model_output)
         x0 = self._x0(x, eps, c)
-        self._base_rng_side_effect(eta, generator, variance_noise, model_output)
         losses, g0 = self._guidance(x0, measurement, vae, vocoder, original_waveform_length, supervised_space,
                                     sample.dtype)
-        z = self._own_noise(eta, generator, variance_noise, model_output)
         prev, x0_new = torch.empty_like(x), torch.empty_like(x)
         _lib.call("dm_sched_mpgd_update", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), _lib.ptr(z), prev.data_ptr(),
                   x0_new.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"],
-                  float(ip_guidance_rate), _lib.stream())
+                  float(ip_guidance_rate), self._coef_ptr(), _lib.stream())
         return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
                                              pred_original_sample=x0_new.to(sample.dtype),
                                              loss=self._loss_out(losses), loss_per_clip=losses)
@@ -226,15 +254,16 @@ class MPGDScheduler(_GuidedBase):
 class _SphericalBase(_GuidedBase):
     """DSG and DiffMusic share everything up to the per-clip mixing rule."""
 
+    noise_mode = "always"
+
     def _spherical_step(self, kernel, model_output, timestep, sample, eta, generator, variance_noise, measurement,
-                        vae, vocoder, L, ip_guidance_rate, eps, supervised_space):
+                        vae, vocoder, L, ip_guidance_rate, eps, supervised_space, _noise=None):
         c = self._coeffs(timestep, eta)
         x, e = self._prep(sample), self._prep(model_output)
+        # one draw per step (scheduling_dsg.py:215-220; `variance_noise` is not consulted by the reference there)
+        z = self._noise_arg(_noise, eta, generator, variance_noise, model_output)
         x0 = self._x0(x, e, c)  # base step called without eta (scheduling_dsg.py:178-186): no RNG side effect
         losses, g0 = self._guidance(x0, measurement, vae, vocoder, L, supervised_space, sample.dtype)
-        # one draw per step, AFTER the gradient (scheduling_dsg.py:215-220); variance_noise is not consulted there
-        z = randn_tensor(model_output.shape, generator=generator, device=model_output.device,
-                         dtype=model_output.dtype).float().contiguous()
         B = x.shape[0]
         n_clip = x.numel() // B
         prev = torch.empty_like(x)
@@ -243,11 +272,11 @@ class _SphericalBase(_GuidedBase):
             r = _f(torch.sqrt(torch.tensor(n_clip)) * c["std"])
             _lib.call("dm_sched_dsg_update", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), z.data_ptr(),
                       prev.data_ptr(), B, n_clip, c["sqrt_a"], c["sqrt_p"], c["dir_coef"], c["std"],
-                      float(ip_guidance_rate), r, 1.0 / 1000.0, float(eps), _lib.stream())
+                      float(ip_guidance_rate), r, 1.0 / 1000.0, float(eps), self._coef_ptr(), _lib.stream())
         else:
             _lib.call("dm_sched_diffmusic_update", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), z.data_ptr(),
                       prev.data_ptr(), B, n_clip, c["sqrt_a"], c["sqrt_p"], c["dir_coef"], c["std"],
-                      float(ip_guidance_rate), 1.0 / 1000.0, float(eps), 0.9995, _lib.stream())
+                      float(ip_guidance_rate), 1.0 / 1000.0, float(eps), 0.9995, self._coef_ptr(), _lib.stream())
         return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
                                              pred_original_sample=x0.to(sample.dtype), loss=self._loss_out(losses),
                                              loss_per_clip=losses)
@@ -259,10 +288,10 @@ class DSGScheduler(_SphericalBase):
     def step(self, model_output, timestep, sample, eta: float = 1.0, use_clipped_model_output: bool = False,
              generator=None, variance_noise=None, return_dict: bool = True, measurement=None, vae=None, vocoder=None,
              original_waveform_length: int = 0, ip_guidance_rate: float = 0.08, eps: float = 1e-8,
-             supervised_space: str = "mel_spectrogram", *args, **kwargs):
+             supervised_space: str = "mel_spectrogram", *args, _noise=None, **kwargs):
         return self._spherical_step("dsg", model_output, timestep, sample, eta, generator, variance_noise,
                                     measurement, vae, vocoder, original_waveform_length, ip_guidance_rate, eps,
-                                    supervised_space)
+                                    supervised_space, _noise)
 
 
 class DiffMusicScheduler(_SphericalBase):
@@ -282,10 +311,10 @@ class DiffMusicScheduler(_SphericalBase):
     def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output: bool = False,
              generator=None, variance_noise=None, return_dict: bool = True, measurement=None, vae=None, vocoder=None,
              original_waveform_length: int = 0, ip_guidance_rate: float = 0.08, eps: float = 1e-8,
-             supervised_space: str = "mel_spectrogram", *args, **kwargs):
+             supervised_space: str = "mel_spectrogram", *args, _noise=None, **kwargs):
         return self._spherical_step("diffmusic", model_output, timestep, sample, eta, generator, variance_noise,
                                     measurement, vae, vocoder, original_waveform_length, ip_guidance_rate, eps,
-                                    supervised_space)
+                                    supervised_space, _noise)
 
 
 def get_scheduler(scheduler_name):

@@ -36,40 +36,44 @@ void dm_reset_launch_count(void);
  * Scalars are the fp32 values the reference computes on the host (scheduling_dps.py:157-162):
  *   sqrt_a = alpha_prod_t ** 0.5, sqrt_b = (1 - alpha_prod_t) ** 0.5, sqrt_p = alpha_prod_t_prev ** 0.5,
  *   dir_coef = (1 - alpha_prod_t_prev - std_dev_t ** 2) ** 0.5, std = eta * variance ** 0.5.
+ * `coef` (may be NULL): DEVICE array [sqrt_a, sqrt_b, sqrt_p, dir_coef (ddim: sqrt_1mp), std, r]; when given it
+ * overrides the by-value scalars, so a CUDA graph captured once can be replayed for every timestep by updating 24
+ * bytes of device memory (the guided loop is launch-bound: SURVEY.md 7.3 "tiny problem sizes").
  * ---------------------------------------------------------------------------------------------------------------- */
 
 /* x0 = (x - sqrt_b * eps) / sqrt_a, optionally clamped to +-clip_range.
  * Replaces diffusers DDIMScheduler.step(...).pred_original_sample as called at scheduling_ddim.py:84-93,
  * scheduling_dps.py:166-175, scheduling_mpgd.py:164-173, scheduling_dsg.py:178-186, scheduling_diffmusic.py:180-188. */
 int dm_sched_x0(const float* x, const float* eps, float* x0, long long n, float sqrt_a, float sqrt_b, int clip,
-                float clip_range, dm_stream_t stream);
+                float clip_range, const float* coef, dm_stream_t stream);
 
 /* scheduling_ddim.py:95-96: e = (x - sqrt_a x0)/sqrt_b ; prev = sqrt_p x0 + sqrt_1mp e */
 int dm_sched_ddim_update(const float* x, const float* x0, float* prev, long long n, float sqrt_a, float sqrt_b,
-                         float sqrt_p, float sqrt_1mp, dm_stream_t stream);
+                         float sqrt_p, float sqrt_1mp, const float* coef, dm_stream_t stream);
 
 /* scheduling_dps.py:177-213: prev = sqrt_p x0 + dir_coef (x - sqrt_a x0)/sqrt_b (+ std z) - rate * g0 / sqrt_a.
  * g0 = dLoss/dx0 (from torch autograd through vocoder + VAE); z may be NULL when eta == 0. */
 int dm_sched_dps_update(const float* x, const float* x0, const float* g0, const float* z, float* prev, long long n,
                         float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std, float rate,
-                        dm_stream_t stream);
+                        const float* coef, dm_stream_t stream);
 
 /* scheduling_mpgd.py:199-218: x0' = x0 - rate g0 ; prev = sqrt_p x0' + dir_coef (x - sqrt_a x0')/sqrt_b (+ std z) */
 int dm_sched_mpgd_update(const float* x, const float* x0, const float* g0, const float* z, float* prev,
                          float* x0_out, long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef,
-                         float std, float rate, dm_stream_t stream);
+                         float std, float rate, const float* coef, dm_stream_t stream);
 
 /* scheduling_dsg.py:189-224 with per-clip norms: g = grad_scale * g0 / sqrt_a ; mean = sqrt_p x0 + dir_coef eps ;
  * d* = -r g/(|g|+e) ; mix = std z + rate (d* - std z) ; prev = mean + r mix/(|mix|+e).  r = sqrt(n_clip) * std. */
 int dm_sched_dsg_update(const float* x0, const float* eps, const float* g0, const float* z, float* prev, int n_clips,
                         long long n_clip, float sqrt_a, float sqrt_p, float dir_coef, float std, float rate, float r,
-                        float grad_scale, float e, dm_stream_t stream);
+                        float grad_scale, float e, const float* coef, dm_stream_t stream);
 
 /* scheduling_diffmusic.py:191-223 + slerp (59-68), branch resolved on the device: g as above ;
  * u = -g/(|g|+e) |z| ; c = <z/|z|, u/|u|> ; m = |c| > thr ? z + rate (u - z) : slerp ; prev = mean + std m. */
 int dm_sched_diffmusic_update(const float* x0, const float* eps, const float* g0, const float* z, float* prev,
                               int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef, float std,
-                              float rate, float grad_scale, float e, float threshold, dm_stream_t stream);
+                              float rate, float grad_scale, float e, float threshold, const float* coef,
+                              dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * STFT / mel guidance  (operator.py:24-36,123-124 T_mel ; 153-154 phase mel ; 162-171 |STFT|)

@@ -56,15 +56,20 @@ static void run(const EmulTables& e, int clamp, const float* y, long long Ly, in
     s.b_re = p; p += padded_len(kH); s.b_im = p; p += padded_len(kH);
     s.x_re = p; p += 520; s.x_im = p; p += 520; s.p = p; p += 520; s.mel = p; p += 64; s.melbar = p;
     if (ypbar) std::memset(ypbar, 0, sizeof(float) * (Ly + 1024));
+    std::vector<ThreadConsts> tc(64);
+    for (int tid = 0; tid < 64; ++tid) load_thread_consts(tid, t, tc[tid]);
+    std::vector<float> melw_t((size_t)e.mel_wstride * kMels);
+    for (int m = 0; m < kMels; ++m)
+        for (int i = 0; i < e.mel_wstride; ++i) melw_t[(size_t)i * kMels + m] = e.mel_w[m * e.mel_wstride + i];
     double acc = 0.0;
     for (long long f = 0; f < T; ++f) {
         for (int n = 0; n < kNfft; ++n) {
             long long j = reflect_src(f * hop + n, Ly);
             frame[n] = y[j] * (mask ? mask[j] : 1.f);
         }
-        for (int tid = 0; tid < 64; ++tid) fwd_pass1(tid, t, frame.data(), t.window, s);
-        for (int tid = 0; tid < 64; ++tid) fwd_pass2(tid, t.tw512, s);
-        for (int tid = 0; tid < 64; ++tid) fwd_pass3(tid, t.tw512, s);
+        for (int tid = 0; tid < 64; ++tid) fwd_pass1<false>(tid, frame.data(), t.window, s);
+        for (int tid = 0; tid < 64; ++tid) fwd_pass2(tid, tc[tid], s);
+        for (int tid = 0; tid < 64; ++tid) fwd_pass3(tid, tc[tid], s);
         for (int tid = 0; tid < 64; ++tid) fwd_unpack<MODE>(tid, t.w1024, s);
         if (MODE == kModePhaseWav) {
             for (int k = 0; k < kBins; ++k) {
@@ -75,16 +80,17 @@ static void run(const EmulTables& e, int clamp, const float* y, long long Ly, in
         } else {
             for (int m = 0; m < 64; ++m) {
                 float v;
-                float d2 = mel_residual<MODE>(m, t, s, clamp != 0, ref != nullptr, ref ? ref[m * T + f] : 0.f, &v);
+                float d2 = mel_residual<MODE>(m, tc[m], melw_t.data(), s, clamp != 0, ref != nullptr,
+                                              ref ? ref[m * T + f] : 0.f, &v);
                 acc += d2;
                 if (out) out[m * T + f] = v;
             }
         }
         if (!ypbar) continue;
         for (int tid = 0; tid < 64; ++tid) bwd_pack<MODE>(tid, t, s);
-        for (int tid = 0; tid < 64; ++tid) inv_pass1(tid, t.tw512, s);
-        for (int tid = 0; tid < 64; ++tid) inv_pass2(tid, t.tw512, s);
-        for (int tid = 0; tid < 64; ++tid) inv_pass3(tid, t.tw512, s);
+        for (int tid = 0; tid < 64; ++tid) inv_pass1(tid, s);
+        for (int tid = 0; tid < 64; ++tid) inv_pass2(tid, tc[tid], s);
+        for (int tid = 0; tid < 64; ++tid) inv_pass3(tid, tc[tid], s);
         for (int n = 0; n < kNfft; ++n) ypbar[f * hop + n] += frame_grad_sample(s, n) * t.window[n];
     }
     (void)nrow;

@@ -337,3 +337,36 @@ def test_fad_statistics_vs_numpy(n, d):
     omu, ocov = ofad.embd_statistics_online([p.astype(np.float64) for p in parts])
     assert rel_l2(mu2, omu) < 1e-6 and rel_l2(cov2, ocov) < 1e-5
     assert np.allclose(cov2, cov2.T)
+
+
+# ------------------------------------------------------------------------------------------------ CUDA-graph replay
+@pytest.mark.parametrize("sched_name,op_name,eta", [("ddim", "inpainting", 0.0), ("dps", "super_resolution", 0.0),
+                                                    ("dps", "inpainting", 0.5), ("mpgd", "inpainting", 1.0),
+                                                    ("dsg", "phase_retrieval", 1.0),
+                                                    ("diffmusic", "dereverberation", 1.0)])
+def test_graphed_step_equals_eager_step(sched_name, op_name, eta):
+    """one captured graph replayed over several timesteps == the eager `.step` (same generators, same IR draws)."""
+    B = 2
+    vae, voc = stubs.StubVAE().to(DEV), stubs.StubVocoder().to(DEV)
+    x, e = stubs.synth_latents(B, 25)
+    x, e = x.to(DEV), e.to(DEV)
+    op = _ops()[op_name]
+    sched = dm.get_scheduler(sched_name)(operator=op, **stubs.MUSICLDM_SCHED)
+    sched.set_timesteps(500)
+    torch.manual_seed(321)
+    meas = op.forward(stubs.synth_clips(1, L1, first=50).to(DEV))
+    kw = dict(eta=eta, measurement=meas, vae=vae, vocoder=voc, original_waveform_length=L1)
+    if RATES[sched_name] is not None:
+        kw.update(ip_guidance_rate=RATES[sched_name], supervised_space="mel_spectrogram")
+    graphed = dm.GraphedGuidedStep(sched, tuple(x.shape), **kw)
+    g_eager, g_graph = stubs.step_generators(B), stubs.step_generators(B)
+    xe, xg = x.clone(), x.clone()
+    for t in (999, 501, 1):
+        torch.manual_seed(40 + t)  # dereverb IR (global CPU generator)
+        a = sched.step(e, t, xe, generator=g_eager, **kw)
+        torch.manual_seed(40 + t)
+        b = graphed(e, t, xg, generator=g_graph)
+        assert rel_l2(b.prev_sample, a.prev_sample) < 1e-6, t
+        assert rel_l2(b.pred_original_sample, a.pred_original_sample) < 1e-6, t
+        assert abs(float(b.loss.float().ravel()[0]) - float(a.loss.float().ravel()[0])) <= 1e-6 * abs(float(a.loss.float().ravel()[0])) + 1e-12
+        xe, xg = a.prev_sample, b.prev_sample  # chain the trajectory
