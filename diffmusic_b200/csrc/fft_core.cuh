@@ -116,6 +116,47 @@ DM_HD void stockham_pass_rt(int j, const cf (&w)[7], Load load, Store store) {
     for (int q = 0; q < 8; ++q) store(j0 + q * NS, v[q]);
 }
 
+// Padded split-array I/O with the index arithmetic strength-reduced: for the radix-8 access patterns the padded
+// address is one padi() per thread plus compile-time strides (padi(j + r*T) = padi(j) + r*(T + T/8) when 8 | T, and
+// padi(j0 + q*NS) = padi(j0) + q*(NS + NS/8) when 8 | NS; for NS = 1 the eight outputs are contiguous).
+template <int N>
+DM_HD void load8_pad(const float* __restrict__ re, const float* __restrict__ im, int j, cf (&v)[8]) {
+    constexpr int S = N / 8 + N / 64;
+    const int b = padi(j);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = cf{re[b + r * S], im[b + r * S]};
+}
+template <int NS>
+DM_HD void store8_pad(float* __restrict__ re, float* __restrict__ im, int j, const cf (&v)[8]) {
+    constexpr int S = (NS == 1) ? 1 : NS + NS / 8;
+    const int k = j % NS;
+    const int b = padi((j / NS) * NS * 8 + k);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        re[b + q * S] = v[q].x;
+        im[b + q * S] = v[q].y;
+    }
+}
+template <int SIGN>
+DM_HD void twiddle8(cf (&v)[8], const cf (&w)[7]) {
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+        cf t = w[r - 1];
+        if (SIGN > 0) t.y = -t.y;
+        v[r] = cmul(v[r], t);
+    }
+}
+// padded -> padded pass with register twiddles (NS > 1)
+template <int N, int NS, int SIGN>
+DM_HD void stockham_pass_pad(int j, const cf (&w)[7], const float* in_re, const float* in_im, float* out_re,
+                             float* out_im) {
+    cf v[8];
+    load8_pad<N>(in_re, in_im, j, v);
+    twiddle8<SIGN>(v, w);
+    dft8<SIGN>(v);
+    store8_pad<NS>(out_re, out_im, j, v);
+}
+
 // Split-array accessors with padding.
 struct PadLoad {
     const float* re;

@@ -1,0 +1,67 @@
+// Polyphase evaluation of torchaudio's sinc resampling FIR (integer decimation: new_freq/gcd == 1) and of its
+// adjoint, as host/device per-thread bodies (validated on the CPU by tests/cpu_emul, see fft_core.cuh).
+//
+//   forward  y[j]    = sum_k  xz[orig*j + k] * w[k]                     xz = x zero-padded by `width` on the left
+//   adjoint  xbar[i] = sum_j  ybar[j] * w[i + width - orig*j]           
+//
+// Splitting k = kappa + orig*m makes both sums sliding windows in m: a thread that owns R = 4 consecutive outputs of
+// one phase reuses every staged sample and every weight four times (2 shared-memory loads per 4 FMAs instead of 8).
+#pragma once
+#include "fft_core.cuh"
+
+namespace dm {
+
+constexpr int kFirR = 4;  // outputs per thread
+
+// ---- forward: outputs j0 .. j0+3 (block-relative), xs[n] = xz[orig*j_first + n] staged by the caller ----
+// Needs xs[orig*(j0 + mm) + kappa] for mm < M + 3, i.e. up to orig*(j0 + 3) + taps - 1.
+DM_HD void fir_fwd4(const float* xs, const float* w, int taps, int orig, int j0, float (&acc)[kFirR]) {
+#pragma unroll
+    for (int c = 0; c < kFirR; ++c) acc[c] = 0.f;
+    for (int kappa = 0; kappa < orig; ++kappa) {
+        const int M = (taps - kappa + orig - 1) / orig;  // taps of this phase
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;    // weights m = mm, mm-1, mm-2, mm-3
+        const float* xp = xs + orig * j0 + kappa;
+        for (int mm = 0; mm < M + kFirR - 1; ++mm) {
+            w3 = w2;
+            w2 = w1;
+            w1 = w0;
+            w0 = (mm < M) ? w[kappa + orig * mm] : 0.f;
+            const float xv = xp[orig * mm];
+            acc[0] = fmaf(xv, w0, acc[0]);
+            acc[1] = fmaf(xv, w1, acc[1]);
+            acc[2] = fmaf(xv, w2, acc[2]);
+            acc[3] = fmaf(xv, w3, acc[3]);
+        }
+    }
+}
+
+// ---- adjoint: outputs t0, t0+orig, t0+2*orig, t0+3*orig (chunk-relative input positions of one phase) ----
+// ys[n] = (folded, scaled) ybar[j_base + n] staged by the caller with zeros outside [0, Ly);
+// A = (i0 + width - taps + 1) - j_base*orig in (-orig, 0].
+DM_HD void fir_adj4(const float* ys, const float* w, int taps, int orig, int A, int t0, float (&acc)[kFirR]) {
+    const int hi0 = A + taps - 1 + t0;  // (i + width) - j_base*orig for the first output, >= 0
+    const int jb0 = hi0 / orig;
+    const int kappa = hi0 - jb0 * orig;
+    const int M = (taps - kappa + orig - 1) / orig;
+#pragma unroll
+    for (int c = 0; c < kFirR; ++c) acc[c] = 0.f;
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;  // weights m = mm, mm-1, mm-2, mm-3 (outputs c = 3, 2, 1, 0)
+    const float* yp = ys + jb0 + kFirR - 1;
+    for (int mm = 0; mm < M + kFirR - 1; ++mm) {
+        w3 = w2;
+        w2 = w1;
+        w1 = w0;
+        w0 = (mm < M) ? w[kappa + orig * mm] : 0.f;
+        const float yv = yp[-mm];
+        acc[3] = fmaf(yv, w0, acc[3]);
+        acc[2] = fmaf(yv, w1, acc[2]);
+        acc[1] = fmaf(yv, w2, acc[1]);
+        acc[0] = fmaf(yv, w3, acc[0]);
+    }
+}
+
+// signed ceil-division (orig > 0)
+DM_HD long long ceil_div_ll(long long a, long long b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
+
+}  // namespace dm

@@ -1,6 +1,7 @@
 // Bandwidth-bound pieces of the guidance path: wav-space residual, reflect-fold + mask adjoint, sinc resampling
 // forward / adjoint, noise add.  All coalesced, per-clip reductions through per-chunk partial slots (deterministic).
 #include "dm_common.cuh"
+#include "fir_poly.cuh"
 
 namespace dm {
 
@@ -134,19 +135,90 @@ __global__ void __launch_bounds__(kEwThreads) resample_adjoint_kernel(
         ys[i] = (o < Ly) ? ybar_at(yb, pad, o, Ly) * sc : 0.f;
     }
     __syncthreads();
+    // 32-bit arithmetic relative to the chunk: i + width - taps + 1 = j_lo*orig + A + t
+    const int A = (int)(num - j_lo * orig);
     for (int t = threadIdx.x; t < ni; t += kEwThreads) {
-        const long long i = i0 + t;
-        const long long n2 = i + width - taps + 1;
-        const int ja = (int)((n2 <= 0 ? 0 : (n2 + orig - 1) / orig) - j_lo);  // relative first block
-        const int jb = (int)((i + width) / orig - j_lo);                      // relative last block
+        const int lo = A + t;                              // first tap position, relative
+        const int ja = lo <= 0 ? 0 : (lo + orig - 1) / orig;
+        const int hi = lo + taps - 1;                      // i + width, relative; >= 0 because taps >= orig
+        const int jb = hi / orig;
         float acc = 0.f;
         for (int j = ja; j <= jb; ++j) {
-            const int k = (int)(i + width - (long long)orig * (j_lo + j));
+            const int k = hi - orig * j;
             const float* yv = ys + j * n_new;
             for (int ph = 0; ph < n_new; ++ph) acc = fmaf(yv[ph], kw[ph * taps + k], acc);
         }
-        dwav[(long long)b * dwav_bstride + i] = acc;
+        dwav[(long long)b * dwav_bstride + i0 + t] = acc;
     }
+}
+
+// ---- integer decimation (n_new == 1: scale 2 and 10 of run.py / operator.py): polyphase, 4 outputs per thread ----
+__global__ void __launch_bounds__(kEwThreads) resample_fwd_poly_kernel(const float* __restrict__ x,
+                                                                       long long x_bstride, long long L,
+                                                                       const float* __restrict__ kernel, int taps,
+                                                                       int orig, int width, float* __restrict__ y,
+                                                                       long long Ly, int span) {
+    extern __shared__ float sm[];
+    float* kw = sm;            // [taps]
+    float* xs = kw + taps;     // [span] xz[orig*o0 ...]
+    float* outs = xs + span;   // [kRsChunk]
+    const int b = blockIdx.y;
+    const long long o0 = (long long)blockIdx.x * kRsChunk;
+    const int no = (int)min((long long)kRsChunk, Ly - o0);
+    const long long x_lo = (long long)orig * o0 - width;
+    for (int i = threadIdx.x; i < taps; i += kEwThreads) kw[i] = __ldg(kernel + i);
+    const float* xb = x + (long long)b * x_bstride;
+    for (int i = threadIdx.x; i < span; i += kEwThreads) {
+        long long g = x_lo + i;
+        xs[i] = (g >= 0 && g < L) ? xb[g] : 0.f;
+    }
+    __syncthreads();
+    for (int j0 = threadIdx.x * kFirR; j0 < no; j0 += kEwThreads * kFirR) {
+        float acc[kFirR];
+        fir_fwd4(xs, kw, taps, orig, j0, acc);
+#pragma unroll
+        for (int c = 0; c < kFirR; ++c) outs[j0 + c] = acc[c];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < no; t += kEwThreads) y[(long long)b * Ly + o0 + t] = outs[t];
+}
+
+__global__ void __launch_bounds__(kEwThreads) resample_adjoint_poly_kernel(
+    const float* __restrict__ ybar, int pad, long long Ly, const float* __restrict__ partial, int ntiles,
+    const float* __restrict__ kernel, int taps, int orig, int width, float* __restrict__ dwav,
+    long long dwav_bstride, long long L, float* __restrict__ loss, int span, int chunk) {
+    extern __shared__ float sm[];
+    __shared__ float scratch[2];
+    float* kw = sm;            // [taps]
+    float* ys = kw + taps;     // [span]
+    float* outs = ys + span;   // [chunk]
+    const int b = blockIdx.y;
+    const float l = clip_loss(partial + (long long)b * ntiles, ntiles, scratch);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[b] = l;
+    const float sc = inv_loss(l);
+    const long long i0 = (long long)blockIdx.x * chunk;
+    const int ni = (int)min((long long)chunk, L - i0);
+    const long long num = i0 + width - taps + 1;
+    const long long j_base = ceil_div_ll(num, orig);  // may be negative: the staged window then starts with zeros
+    const int A = (int)(num - j_base * orig);
+    for (int i = threadIdx.x; i < taps; i += kEwThreads) kw[i] = __ldg(kernel + i);
+    const float* yb = ybar + (long long)b * (Ly + 2 * pad);
+    for (int i = threadIdx.x; i < span; i += kEwThreads) {
+        long long o = j_base + i;
+        ys[i] = (o >= 0 && o < Ly) ? ybar_at(yb, pad, o, Ly) * sc : 0.f;
+    }
+    __syncthreads();
+    const int items = chunk / kFirR;  // (phase, unit) pairs; chunk is a multiple of orig * kFirR
+    for (int wi = threadIdx.x; wi < items; wi += kEwThreads) {
+        const int phi = wi % orig, u = wi / orig;
+        const int t0 = phi + orig * kFirR * u;
+        float acc[kFirR];
+        fir_adj4(ys, kw, taps, orig, A, t0, acc);
+#pragma unroll
+        for (int c = 0; c < kFirR; ++c) outs[t0 + orig * c] = acc[c];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ni; t += kEwThreads) dwav[(long long)b * dwav_bstride + i0 + t] = outs[t];
 }
 
 __global__ void __launch_bounds__(kEwThreads) mask_apply_kernel(const float* __restrict__ x, long long x_bstride,
@@ -199,6 +271,17 @@ extern "C" int dm_resample_fwd(const float* x, long long x_bstride, long long L,
                                dm_stream_t stream) {
     DM_REQUIRE(x && kernel && y && L > 0 && B > 0 && Ly > 0);
     DM_REQUIRE(n_new >= 1 && taps >= 1 && orig >= 1 && width >= 0);
+    if (n_new == 1) {  // integer decimation: polyphase kernel
+        const int span1 = orig * (kRsChunk + kFirR) + taps;
+        const size_t smem1 = ((size_t)taps + span1 + kRsChunk) * sizeof(float);
+        if (smem1 <= 200 * 1024) {
+            DM_SMEM_ONCE(resample_fwd_poly_kernel, smem1);
+            resample_fwd_poly_kernel<<<dim3((unsigned)((Ly + kRsChunk - 1) / kRsChunk), B), kEwThreads, smem1,
+                                       as_stream(stream)>>>(x, x_bstride, L, kernel, taps, orig, width, y, Ly, span1);
+            DM_LAUNCHED();
+            return DM_OK;
+        }
+    }
     // input span of one chunk: blocks j_lo .. j_lo + ceil((chunk + n_new - 1)/n_new), each orig apart, plus the taps
     const int span = ((kRsChunk + n_new - 1) / n_new + 1) * orig + taps;
     const size_t smem = ((size_t)n_new * taps + span) * sizeof(float);
@@ -217,6 +300,18 @@ extern "C" int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int
                                    long long dwav_bstride, long long L, float* loss, dm_stream_t stream) {
     DM_REQUIRE(ybar && partial && kernel && dwav && L > 0 && B > 0 && Ly > 0 && ntiles > 0);
     DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 513));
+    if (n_new == 1 && taps >= orig) {  // integer decimation: polyphase kernel
+        const int unit = orig * kFirR;
+        const int chunk = unit * ((kRsChunk + unit - 1) / unit);
+        const int span1 = (taps + chunk) / orig + kFirR + 2;
+        const size_t smem1 = ((size_t)taps + span1 + chunk) * sizeof(float);
+        DM_SMEM_ONCE(resample_adjoint_poly_kernel, smem1);
+        resample_adjoint_poly_kernel<<<dim3((unsigned)((L + chunk - 1) / chunk), B), kEwThreads, smem1,
+                                       as_stream(stream)>>>(ybar, pad, Ly, partial, ntiles, kernel, taps, orig, width,
+                                                            dwav, dwav_bstride, L, loss, span1, chunk);
+        DM_LAUNCHED();
+        return DM_OK;
+    }
     // cotangent span of one chunk of inputs: (chunk + taps)/orig + 2 blocks of n_new samples
     const int span = ((kRsChunk + taps) / orig + 2) * n_new;
     const size_t smem = ((size_t)n_new * taps + span) * sizeof(float);

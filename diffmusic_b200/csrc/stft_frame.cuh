@@ -81,13 +81,17 @@ DM_HD void fwd_pass1(int tid, const float* frame, const float* window, FrameSmem
         }
         return cf{frame[2 * i] * window[2 * i], frame[2 * i + 1] * window[2 * i + 1]};
     };
-    stockham_pass<kH, 1, -1>(tid, nullptr, load, PadStore{s.a_re, s.a_im});
+    cf v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = load(tid + r * (kH / 8));
+    dft8<-1>(v);
+    store8_pad<1>(s.a_re, s.a_im, tid, v);
 }
 DM_HD void fwd_pass2(int tid, const ThreadConsts& c, FrameSmem s) {
-    stockham_pass_rt<kH, 8, -1>(tid, c.w8, PadLoad{s.a_re, s.a_im}, PadStore{s.b_re, s.b_im});
+    stockham_pass_pad<kH, 8, -1>(tid, c.w8, s.a_re, s.a_im, s.b_re, s.b_im);
 }
 DM_HD void fwd_pass3(int tid, const ThreadConsts& c, FrameSmem s) {
-    stockham_pass_rt<kH, 64, -1>(tid, c.w64, PadLoad{s.b_re, s.b_im}, PadStore{s.a_re, s.a_im});
+    stockham_pass_pad<kH, 64, -1>(tid, c.w64, s.b_re, s.b_im, s.a_re, s.a_im);
 }
 
 // ---- unpack Z (in a_re/a_im, natural order) to the real-FFT spectrum X and the per-bin energy ----
@@ -126,6 +130,7 @@ DM_HD float mel_residual(int m, const ThreadConsts& c, const float* melw_t, Fram
     // melw_t is the banded filterbank TRANSPOSED to [i][64] so the 64 band-threads read consecutive words
     const int k0 = c.mel_k0, n = c.mel_n;
     float acc = 0.f;
+#pragma unroll 4
     for (int i = 0; i < n; ++i) acc = fmaf(melw_t[i * kMels + m], s.p[k0 + i], acc);
     float val, dval_dmel;  // transformed value and its derivative w.r.t. the mel energy
     if (MODE == kModeMelDb) {
@@ -203,13 +208,16 @@ DM_HD void bwd_pack(int tid, const StftTables& t, FrameSmem s) {
 
 // ---- inverse FFT: b -> a -> b -> a ; afterwards frame gradient n is a_re[pad(n/2)] (n even) / a_im (n odd) ----
 DM_HD void inv_pass1(int tid, FrameSmem s) {
-    stockham_pass<kH, 1, +1>(tid, nullptr, PadLoad{s.b_re, s.b_im}, PadStore{s.a_re, s.a_im});
+    cf v[8];
+    load8_pad<kH>(s.b_re, s.b_im, tid, v);
+    dft8<+1>(v);
+    store8_pad<1>(s.a_re, s.a_im, tid, v);
 }
 DM_HD void inv_pass2(int tid, const ThreadConsts& c, FrameSmem s) {
-    stockham_pass_rt<kH, 8, +1>(tid, c.w8, PadLoad{s.a_re, s.a_im}, PadStore{s.b_re, s.b_im});
+    stockham_pass_pad<kH, 8, +1>(tid, c.w8, s.a_re, s.a_im, s.b_re, s.b_im);
 }
 DM_HD void inv_pass3(int tid, const ThreadConsts& c, FrameSmem s) {
-    stockham_pass_rt<kH, 64, +1>(tid, c.w64, PadLoad{s.b_re, s.b_im}, PadStore{s.a_re, s.a_im});
+    stockham_pass_pad<kH, 64, +1>(tid, c.w64, s.b_re, s.b_im, s.a_re, s.a_im);
 }
 DM_HD float frame_grad_sample(const FrameSmem& s, int n) {
     int p = padi(n >> 1);

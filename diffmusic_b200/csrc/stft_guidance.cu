@@ -153,24 +153,31 @@ __global__ void __launch_bounds__(kCtaThreads) stft_guidance_kernel(const StftPa
         }
         if (want_grad) {
             __syncthreads();
-            // overlap-add the (up to) 4 frame gradients of this round, fixed order -> deterministic
+            // overlap-add the (up to) 4 frame gradients of this round frame by frame (fixed order -> deterministic);
+            // all 256 threads take one complex output (= two samples) per iteration, a barrier separates frames
+            // because consecutive frames overlap by 1024 - hop samples
             const int fr0 = r * kGroups;
             const int nact = min(kGroups, nfr - fr0);
-            const int lo = fr0 * p.hop, hi = (fr0 + nact - 1) * p.hop + kNfft;
-            for (int i = lo + tid; i < hi; i += kCtaThreads) {
-                float a = acc[i];
-                for (int q = 0; q < nact; ++q) {
-                    int off = i - (fr0 + q) * p.hop;
-                    if (off >= 0 && off < kNfft) {
-                        const float* gq = grp + q * kFrameSmemFloats;
-                        int pp = padi(off >> 1);
-                        float v = (off & 1) ? gq[padded_len(kH) + pp] : gq[pp];
-                        a = fmaf(v, win[off], a);
+            for (int q = 0; q < nact; ++q) {
+                const float* gq = grp + q * kFrameSmemFloats;
+                float* ap = acc + (fr0 + q) * p.hop;
+                for (int h = tid; h < kH; h += kCtaThreads) {
+                    const int pp = padi(h);
+                    const float re = gq[pp], im = gq[padded_len(kH) + pp];
+                    if (aligned8) {
+                        f2* a2 = reinterpret_cast<f2*>(ap) + h;
+                        const f2 w2 = reinterpret_cast<const f2*>(win)[h];
+                        f2 v = *a2;
+                        v.x = fmaf(re, w2.x, v.x);
+                        v.y = fmaf(im, w2.y, v.y);
+                        *a2 = v;
+                    } else {
+                        ap[2 * h] = fmaf(re, win[2 * h], ap[2 * h]);
+                        ap[2 * h + 1] = fmaf(im, win[2 * h + 1], ap[2 * h + 1]);
                     }
                 }
-                acc[i] = a;
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
 

@@ -64,12 +64,16 @@ class _DeviceTables:
 
 
 def _frames_per_tile(B, T, device):
-    """largest tile (fewest re-staged samples) that still gives >= 2 CTAs per SM; never below 8 frames."""
-    sms = torch.cuda.get_device_properties(device).multi_processor_count
-    for nf in (32, 16):
-        if B * math.ceil(T / nf) >= 2 * sms:
-            return nf
-    return 8
+    """frames per CTA tile.  The kernel keeps 2 CTAs resident per SM up to 17 frames per tile (shared memory); among
+    8..17 pick the size whose CTA count fills whole waves of 2 x SMs best (tail effect), larger tiles on ties."""
+    slots = 2 * torch.cuda.get_device_properties(device).multi_processor_count
+    best, best_eff = 8, -1.0
+    for nf in range(8, 18):
+        ctas = B * math.ceil(T / nf)
+        eff = ctas / (math.ceil(ctas / slots) * slots)
+        if eff >= best_eff - 1e-9:
+            best, best_eff = nf, max(eff, best_eff)
+    return best
 
 
 class BaseOperator:

@@ -174,3 +174,49 @@ void emul_rir_adjoint(const float* ybar, long long L, const float* spec, int K, 
     }
 }
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Polyphase sinc-resampling FIR and its adjoint (diffmusic_b200/csrc/fir_poly.cuh), same chunk loops as guidance_ops.cu
+#include "../../diffmusic_b200/csrc/fir_poly.cuh"
+
+extern "C" {
+void emul_resample_fwd(const float* x, long long L, const float* kernel, int taps, int orig, int width, float* y,
+                       long long Ly) {
+    const int CH = 2048;
+    const int span = orig * (CH + kFirR) + taps;
+    std::vector<float> xs(span), outs(CH + kFirR);
+    for (long long o0 = 0; o0 < Ly; o0 += CH) {
+        const int no = (int)std::min<long long>(CH, Ly - o0);
+        const long long x_lo = (long long)orig * o0 - width;
+        for (int i = 0; i < span; ++i) { long long g = x_lo + i; xs[i] = (g >= 0 && g < L) ? x[g] : 0.f; }
+        for (int j0 = 0; j0 < no; j0 += kFirR) {
+            float acc[kFirR];
+            fir_fwd4(xs.data(), kernel, taps, orig, j0, acc);
+            for (int c = 0; c < kFirR; ++c) outs[j0 + c] = acc[c];
+        }
+        for (int t = 0; t < no; ++t) y[o0 + t] = outs[t];
+    }
+}
+
+void emul_resample_adjoint(const float* ybar, long long Ly, const float* kernel, int taps, int orig, int width,
+                           float scale, float* xbar, long long L) {
+    const int unit = orig * kFirR;
+    const int chunk = unit * ((2048 + unit - 1) / unit);
+    const int span = (taps + chunk) / orig + kFirR + 2;
+    std::vector<float> ys(span), outs(chunk);
+    for (long long i0 = 0; i0 < L; i0 += chunk) {
+        const int ni = (int)std::min<long long>(chunk, L - i0);
+        const long long num = i0 + width - taps + 1;
+        const long long j_base = ceil_div_ll(num, orig);
+        const int A = (int)(num - j_base * orig);
+        for (int i = 0; i < span; ++i) { long long o = j_base + i; ys[i] = (o >= 0 && o < Ly) ? ybar[o] * scale : 0.f; }
+        for (int wi = 0; wi < chunk / kFirR; ++wi) {
+            const int phi = wi % orig, u = wi / orig, t0 = phi + orig * kFirR * u;
+            float acc[kFirR];
+            fir_adj4(ys.data(), kernel, taps, orig, A, t0, acc);
+            for (int c = 0; c < kFirR; ++c) outs[t0 + orig * c] = acc[c];
+        }
+        for (int t = 0; t < ni; ++t) xbar[i0 + t] = outs[t];
+    }
+}
+}

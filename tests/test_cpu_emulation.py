@@ -211,3 +211,29 @@ def test_rir_overlap_save(emul, K, L):
     ybn = yb[0].numpy().copy()
     emul.emul_rir_adjoint(_ptr(ybn), C.c_longlong(L), _ptr(spec), K, _ptr(tw), _ptr(w), C.c_float(0.5), _ptr(gotb))
     assert rel_l2(gotb, 0.5 * gx[0]) < 2e-6
+
+
+@pytest.mark.parametrize("scale,L", [(2, 16000), (2, 4099), (10, 16000), (10, 5003), (4, 7777)])
+def test_polyphase_resample(emul, scale, L):
+    """integer-decimation sinc FIR and its adjoint through the device per-thread bodies vs torchaudio / autograd."""
+    import torchaudio
+    kern, width, orig, new = tables.sinc_resample_kernel(16000, 16000 // scale)
+    assert new == 1 and orig == scale
+    g = torch.Generator().manual_seed(scale * 7 + L)
+    x = torch.randn(1, L, generator=g)
+    rs = torchaudio.transforms.Resample(16000, 16000 // scale)
+    xx = x.clone().requires_grad_(True)
+    y = rs(xx)
+    Ly = y.shape[1]
+    k = kern[0].numpy().copy()
+    got = np.zeros(Ly, np.float32)
+    xn = x[0].numpy().copy()
+    emul.emul_resample_fwd(_ptr(xn), C.c_longlong(L), _ptr(k), len(k), orig, width, _ptr(got), C.c_longlong(Ly))
+    assert rel_l2(got, y[0].detach()) < 2e-6
+    yb = torch.randn(1, Ly, generator=g)
+    (gx,) = torch.autograd.grad((y * yb).sum(), xx)
+    gotb = np.zeros(L, np.float32)
+    ybn = yb[0].numpy().copy()
+    emul.emul_resample_adjoint(_ptr(ybn), C.c_longlong(Ly), _ptr(k), len(k), orig, width, C.c_float(0.25), _ptr(gotb),
+                               C.c_longlong(L))
+    assert rel_l2(gotb, 0.25 * gx[0]) < 2e-6
