@@ -18,6 +18,7 @@ class EmbeddingMoments:
 
     def __init__(self, d, device=None):
         self.d = int(d)
+        # the accumulator may live on the CPU (gloo tests of the exchange step); update()/finalize() need CUDA
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.acc = torch.zeros(1 + self.d + self.d * self.d, device=self.device, dtype=torch.float64)
 
@@ -26,6 +27,8 @@ class EmbeddingMoments:
         if it already is fp16-representable is the caller's business: fp32 input is rounded to fp16 like the cache)."""
         if embd.dim() != 2 or embd.shape[1] != self.d:
             raise ValueError(f"expected (n, {self.d}) embeddings, got {tuple(embd.shape)}")
+        if self.device.type != "cuda":
+            raise _lib.DiffMusicB200Error("dm_fad_moments needs a CUDA accumulator (no CPU fallback)")
         x = embd.to(device=self.device, dtype=torch.float16).contiguous()
         if x.shape[0] == 0:
             return self
@@ -44,6 +47,8 @@ class EmbeddingMoments:
 
     def finalize(self):
         """(mu (d,), cov (d, d)) float64 on the device; cov is zeros when fewer than 2 frames (fadtk/utils.py:42-46)."""
+        if self.device.type != "cuda":
+            raise _lib.DiffMusicB200Error("dm_fad_finalize needs a CUDA accumulator (no CPU fallback)")
         mu = torch.empty(self.d, device=self.device, dtype=torch.float64)
         cov = torch.empty((self.d, self.d), device=self.device, dtype=torch.float64)
         _lib.call("dm_fad_finalize", self.acc.data_ptr(), self.d, mu.data_ptr(), cov.data_ptr(), _lib.stream())
