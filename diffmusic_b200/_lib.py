@@ -48,6 +48,7 @@ _SIGNATURES = {
     "dm_rir_adjoint": (c_i, [c_p, c_i, c_ll, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_ll, c_ll, c_p, c_p]),
     "dm_add_scaled": (c_i, [c_p, c_p, c_f, c_ll, c_p]),
     "dm_fad_moments": (c_i, [c_p, c_ll, c_i, c_p, c_p]),
+    "dm_fad_moments_ex": (c_i, [c_p, c_ll, c_i, c_p, c_i, c_p]),
     "dm_fad_finalize": (c_i, [c_p, c_i, c_p, c_p, c_p]),
 }
 

@@ -101,19 +101,37 @@ __global__ void __launch_bounds__(kFadThreads) fad_finalize_kernel(const double*
 
 }  // namespace dm
 
+namespace dm {
+int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, cudaStream_t st);  // fad_tc.cu
+}
+
 using namespace dm;
 
 extern "C" int dm_fad_moments(const void* x_f16, long long N, int d, double* acc, dm_stream_t stream) {
+    return dm_fad_moments_ex(x_f16, N, d, acc, DM_FAD_AUTO, stream);
+}
+
+extern "C" int dm_fad_moments_ex(const void* x_f16, long long N, int d, double* acc, int engine,
+                                 dm_stream_t stream) {
     DM_REQUIRE(x_f16 && acc && N > 0 && d > 0);
+    DM_REQUIRE(engine == DM_FAD_AUTO || engine == DM_FAD_SIMT || engine == DM_FAD_TCGEN05);
     const __half* X = reinterpret_cast<const __half*>(x_f16);
+    bool xtx_done = false;
+    if (engine != DM_FAD_SIMT) {
+        int rc = fad_xtx_tc(x_f16, N, d, acc + 1 + d, as_stream(stream));
+        if (rc == DM_OK) xtx_done = true;
+        else if (engine == DM_FAD_TCGEN05 || rc != DM_ERR_UNSUPPORTED) return rc;
+    }
     const int nt = (d + kFadTile - 1) / kFadTile;
     // enough row slabs to fill the machine, each long enough to amortise the float64 atomics
     long long want = std::max<long long>(1, (2LL * num_sms()) / std::max(1, nt * (nt + 1) / 2));
     long long rows = std::max<long long>(256, (N + want - 1) / want);
     rows = (rows + kFadSlab - 1) / kFadSlab * kFadSlab;
     const int nz = (int)((N + rows - 1) / rows);
-    fad_xtx_kernel<<<dim3(nt, nt, nz), kFadThreads, 0, as_stream(stream)>>>(X, N, d, rows, acc + 1 + d);
-    DM_LAUNCHED();
+    if (!xtx_done) {
+        fad_xtx_kernel<<<dim3(nt, nt, nz), kFadThreads, 0, as_stream(stream)>>>(X, N, d, rows, acc + 1 + d);
+        DM_LAUNCHED();
+    }
     const long long crow = std::max<long long>(64, (N + 63) / 64);
     fad_colsum_kernel<<<dim3((d + kFadThreads - 1) / kFadThreads, (unsigned)((N + crow - 1) / crow)), kFadThreads, 0,
                         as_stream(stream)>>>(X, N, d, crow, acc);

@@ -1,0 +1,306 @@
+// FAD second moments  S += X^T X  on the 5th-generation tensor cores (tcgen05), operands fed by TMA.
+//
+//   X : (N, d) fp16 row-major (what fadtk caches, model_loader.py:46-48).  fp16 x fp16 products are exact in fp32, the
+//   TMEM accumulator is fp32 and is drained into float64 REGISTER accumulators every kFlush K-blocks (1024 rows), so the
+//   only rounding is the fp32 running sum inside one 1024-row slab; np.cov (fadtk/fad.py:47) is float64.
+//
+//   C tile (128 x 128) = A^T-tile * B-tile with A = X[:, i-block], B = X[:, j-block]: both operands are "MN-major"
+//   (contiguous along the output dimension), which kind::f16 supports directly -- no transpose pass over X.
+//   TMA loads 64-column x 64-row boxes with the 128-byte swizzle straight into the canonical UMMA layout:
+//       atom = 64 (MN) x 8 (K) fp16 = 1024 B, K groups every 1024 B (SBO), MN halves every 8192 B (LBO).
+//
+//   Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected thread),
+//   warps 2..9 = epilogue: TMEM -> registers (tcgen05.ld) -> float64 accumulators; two TMEM accumulator stages let the
+//   drain of slab s overlap the MMAs of slab s+1.  Upper-triangular tiles only; the mirror is written on the way out.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "dm_common.cuh"
+
+namespace dm {
+
+constexpr int kTile = 128;          // output tile (M = N = 128)
+constexpr int kBoxCols = 64;        // TMA box: 64 fp16 = 128 B (one swizzle row)
+constexpr int kBlockK = 64;         // rows of X per pipeline stage
+constexpr int kUmmaK = 16;          // K of one tcgen05.mma (fp16)
+constexpr int kStages = 6;
+constexpr int kAccStages = 2;
+constexpr int kFlush = 16;          // K-blocks per TMEM slab (1024 rows) before draining to float64
+constexpr int kTcThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr uint32_t kBoxBytes = kBoxCols * kBlockK * 2;          // 8 KB
+constexpr uint32_t kOperandBytes = 2 * kBoxBytes;               // 128 columns x 64 rows = 16 KB
+constexpr uint32_t kStageBytes = 2 * kOperandBytes;             // A + B
+constexpr uint32_t kTmemCols = kAccStages * kTile;              // 256 fp32 columns
+constexpr size_t kTcSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// UMMA shared-memory descriptor, MN-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((kBoxBytes >> 4) & 0x3FFF) << 16;  // LBO: next 64 MN elements = next TMA box
+    d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;      // SBO: next 8 K rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both MN-major, N = 128, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | ((kTile >> 3) << 17) |
+                            ((kTile >> 4) << 24);
+
+struct FadTcParams {
+    int d, ntile;           // columns, tiles per side
+    long long N, rows_per_cta;
+    double* sxx;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+    fad_xtx_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FadTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+    uint64_t* full = bars;                       // [kStages]  TMA -> MMA
+    uint64_t* empty = bars + kStages;            // [kStages]  MMA -> TMA
+    uint64_t* tfull = bars + 2 * kStages;        // [kAccStages] MMA -> epilogue
+    uint64_t* tempty = tfull + kAccStages;       // [kAccStages] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // linear upper-triangular tile index -> (ti, tj), tj >= ti
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= p.ntile - ti) {
+        rem -= p.ntile - ti;
+        ++ti;
+    }
+    const int tj = ti + rem;
+    const bool diag = (ti == tj);
+    const long long r_begin = (long long)blockIdx.y * p.rows_per_cta;
+    const long long r_end = min(p.N, r_begin + p.rows_per_cta);
+    const int nkb = r_end > r_begin ? (int)((r_end - r_begin + kBlockK - 1) / kBlockK) : 0;
+    const int nslab = (nkb + kFlush - 1) / kFlush;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < kAccStages; ++s) {
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], kEpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kStages;
+                mbar_wait(&empty[s], ((kb / kStages) & 1) ^ 1);
+                uint8_t* a = smem + (size_t)s * kStageBytes;
+                uint8_t* b = a + kOperandBytes;
+                const int row = (int)(r_begin + (long long)kb * kBlockK);
+                mbar_expect_tx(&full[s], diag ? kOperandBytes : 2 * kOperandBytes);
+                tma_load_2d(&tmap, &full[s], a, ti * kTile, row);
+                tma_load_2d(&tmap, &full[s], a + kBoxBytes, ti * kTile + kBoxCols, row);
+                if (!diag) {
+                    tma_load_2d(&tmap, &full[s], b, tj * kTile, row);
+                    tma_load_2d(&tmap, &full[s], b + kBoxBytes, tj * kTile + kBoxCols, row);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kStages;
+                const int slab = kb / kFlush, as = slab % kAccStages;
+                if (kb % kFlush == 0) {  // new slab: its TMEM stage must have been drained
+                    mbar_wait(&tempty[as], ((slab / kAccStages) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                mbar_wait(&full[s], (kb / kStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * kStageBytes);
+                const uint32_t b_addr = diag ? a_addr : a_addr + kOperandBytes;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * kTile);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    const uint32_t koff = (uint32_t)k * kUmmaK * 128u;  // 16 K rows x 128 B
+                    umma_f16(d_tmem, make_desc_mn_sw128(a_addr + koff), make_desc_mn_sw128(b_addr + koff), kIdesc,
+                             (kb % kFlush != 0 || k != 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);  // smem stage free once these MMAs have read it
+                if (kb % kFlush == kFlush - 1 || kb == nkb - 1) umma_commit(&tfull[as]);
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> float64 registers =====================
+        const int e = warp - 2;
+        const int quarter = warp & 3;           // TMEM lanes a warp may touch: 32 * (warp % 4) ...
+        const int half = e >> 2;                // which 64 of the 128 accumulator columns
+        double acc[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) acc[c] = 0.0;
+        for (int slab = 0; slab < nslab; ++slab) {
+            const int as = slab % kAccStages;
+            mbar_wait(&tfull[as], (slab / kAccStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kTile + half * 64);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                tmem_ld32(taddr + h * 32, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 32; ++c) acc[h * 32 + c] += (double)__uint_as_float(v[c]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+        // ---- add the tile into the float64 accumulator (and its mirror) ----
+        const int gi = ti * kTile + quarter * 32 + lane;
+        if (gi < p.d && nkb > 0) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+                const int gj = tj * kTile + half * 64 + c;
+                if (gj < p.d) {
+                    atomicAdd(&p.sxx[(long long)gi * p.d + gj], acc[c]);
+                    if (!diag) atomicAdd(&p.sxx[(long long)gj * p.d + gi], acc[c]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// returns DM_ERR_UNSUPPORTED when the shape cannot go through TMA (caller falls back to the SIMT kernel)
+int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, cudaStream_t st) {
+    if (d % 8 != 0 || (reinterpret_cast<uintptr_t>(x_f16) & 15) != 0 || N > 0x7fffffffLL)
+        return fail(DM_ERR_UNSUPPORTED, "%s: TMA needs d %% 8 == 0 and a 16-byte aligned base", __func__);
+    EncodeTiledFn enc = encode_tiled();
+    if (enc == nullptr) return fail(DM_ERR_CUDA, "%s: cuTensorMapEncodeTiled not available", __func__);
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)N};
+    const cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
+    const cuuint32_t box[2] = {kBoxCols, kBlockK};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x_f16), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DM_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", __func__, (int)r);
+    FadTcParams p;
+    p.d = d;
+    p.ntile = (d + kTile - 1) / kTile;
+    p.N = N;
+    p.sxx = sxx;
+    const int ntri = p.ntile * (p.ntile + 1) / 2;
+    // one CTA per SM (192 KB of pipeline stages): split the rows so the grid covers the machine about once, in
+    // multiples of the flush slab so every CTA drains whole slabs
+    long long splits = std::max<long long>(1, num_sms() / ntri);
+    long long rows = (N + splits - 1) / splits;
+    const long long slab_rows = (long long)kFlush * kBlockK;
+    rows = std::max<long long>(slab_rows, (rows + slab_rows - 1) / slab_rows * slab_rows);
+    p.rows_per_cta = rows;
+    const int gy = (int)((N + rows - 1) / rows);
+    DM_SMEM_ONCE(fad_xtx_tc_kernel, kTcSmemBytes);
+    fad_xtx_tc_kernel<<<dim3(ntri, gy), kTcThreads, kTcSmemBytes, st>>>(tmap, p);
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+}  // namespace dm

@@ -16,8 +16,11 @@ from . import _lib
 class EmbeddingMoments:
     """Accumulator of raw moments for one embedding model of width d."""
 
-    def __init__(self, d, device=None):
+    ENGINES = {"auto": 0, "simt": 1, "tcgen05": 2}
+
+    def __init__(self, d, device=None, engine="auto"):
         self.d = int(d)
+        self.engine = self.ENGINES[engine]
         # the accumulator may live on the CPU (gloo tests of the exchange step); update()/finalize() need CUDA
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.acc = torch.zeros(1 + self.d + self.d * self.d, device=self.device, dtype=torch.float64)
@@ -32,7 +35,8 @@ class EmbeddingMoments:
         x = embd.to(device=self.device, dtype=torch.float16).contiguous()
         if x.shape[0] == 0:
             return self
-        _lib.call("dm_fad_moments", x.data_ptr(), x.shape[0], self.d, self.acc.data_ptr(), _lib.stream())
+        _lib.call("dm_fad_moments_ex", x.data_ptr(), x.shape[0], self.d, self.acc.data_ptr(), self.engine,
+                  _lib.stream())
         return self
 
     def all_reduce(self, group=None):

@@ -172,6 +172,12 @@ int dm_add_scaled(float* y, const float* noise, float sigma, long long n, dm_str
  * sum) and finalising mu = sx/n, cov = (sxx - n mu mu^T)/(n-1) equals the reference's Chan merge.
  * ---------------------------------------------------------------------------------------------------------------- */
 int dm_fad_moments(const void* x_f16, long long N, int d, double* acc, dm_stream_t stream);
+/* same with the engine for sum x x^T chosen explicitly: AUTO = tcgen05 + TMA when d % 8 == 0 and X is 16-byte aligned
+ * (TMA requirements), else the SIMT tile kernel. */
+#define DM_FAD_AUTO 0
+#define DM_FAD_SIMT 1
+#define DM_FAD_TCGEN05 2
+int dm_fad_moments_ex(const void* x_f16, long long N, int d, double* acc, int engine, dm_stream_t stream);
 /* mu (d) and cov (d, d) in float64 from acc */
 int dm_fad_finalize(const double* acc, int d, double* mu, double* cov, dm_stream_t stream);
 

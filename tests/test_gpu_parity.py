@@ -322,6 +322,23 @@ def test_operator_linearity_and_adjoint_identity():
 
 
 # ------------------------------------------------------------------------------------------------ FAD statistics
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+@pytest.mark.parametrize("n,d", [(40, 128), (1000, 512), (4990, 768), (333, 1024), (70000, 768), (2500, 200)])
+def test_fad_moments_engines(n, d, engine):
+    """sum x x^T through the SIMT tile kernel and through the tcgen05 + TMA kernel against float64 NumPy."""
+    from diffmusic_b200 import fad
+    rng = np.random.default_rng(d + n)
+    X = (rng.standard_normal((n, d)) * 0.7 + rng.standard_normal(d) * 0.3).astype(np.float16)
+    mom = fad.EmbeddingMoments(d, engine=engine).update(torch.from_numpy(X))
+    acc = mom.acc.cpu().numpy()
+    X64 = X.astype(np.float64)
+    assert acc[0] == n
+    assert rel_l2(acc[1:1 + d], X64.sum(0)) < 1e-7
+    got, want = acc[1 + d:].reshape(d, d), X64.T @ X64
+    assert rel_l2(got, want) < 2e-6, (engine, rel_l2(got, want))
+    assert np.array_equal(got, got.T)
+
+
 @pytest.mark.parametrize("n,d", [(40, 128), (1000, 512), (4990, 768), (333, 1024)])
 def test_fad_statistics_vs_numpy(n, d):
     from diffmusic_b200 import fad
