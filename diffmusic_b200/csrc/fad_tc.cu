@@ -1,8 +1,8 @@
 // FAD second moments  S += X^T X  on the 5th-generation tensor cores (tcgen05), operands fed by TMA.
 //
 //   X : (N, d) fp16 row-major (what fadtk caches, model_loader.py:46-48).  fp16 x fp16 products are exact in fp32, the
-//   TMEM accumulator is fp32 and is drained into float64 REGISTER accumulators every kFlush K-blocks (1024 rows), so the
-//   only rounding is the fp32 running sum inside one 1024-row slab; np.cov (fadtk/fad.py:47) is float64.
+//   TMEM accumulator is fp32 and is drained into float64 REGISTER accumulators every kFlush K-blocks (256 rows), so the
+//   only rounding is the fp32 running sum inside one 256-row slab; np.cov (fadtk/fad.py:47) is float64.
 //
 //   C tile (128 x 128) = A^T-tile * B-tile with A = X[:, i-block], B = X[:, j-block]: both operands are "MN-major"
 //   (contiguous along the output dimension), which kind::f16 supports directly -- no transpose pass over X.
@@ -27,7 +27,7 @@ constexpr int kBlockK = 64;         // rows of X per pipeline stage
 constexpr int kUmmaK = 16;          // K of one tcgen05.mma (fp16)
 constexpr int kStages = 6;
 constexpr int kAccStages = 2;
-constexpr int kFlush = 16;          // K-blocks per TMEM slab (1024 rows) before draining to float64
+constexpr int kFlush = 4;           // K-blocks per TMEM slab (256 rows) before draining to float64
 constexpr int kTcThreads = 320;
 constexpr int kEpiWarps = 8;
 constexpr uint32_t kBoxBytes = kBoxCols * kBlockK * 2;          // 8 KB
