@@ -86,6 +86,40 @@ __global__ void __launch_bounds__(kFadThreads) fad_colsum_kernel(const __half* _
     atomicAdd(&acc[1 + c], s);
 }
 
+// Column sums at HBM speed for d % 8 == 0: thread (p, g) owns 8 consecutive columns (one 128-bit load per row) and every
+// P-th row of the block's slab; fp32 partials over 32 rows, float64 across, one float64 atomic per column at the end.
+__global__ void __launch_bounds__(1024) fad_colsum_vec_kernel(const __half* __restrict__ X, long long N, int d, int G,
+                                                              int P, long long rows_per_cta,
+                                                              double* __restrict__ acc) {
+    const int g = threadIdx.x % G, pr = threadIdx.x / G;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&acc[0], (double)N);
+    if (pr >= P) return;
+    const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+    const long long r_end = min(N, r_begin + rows_per_cta);
+    double s[8];
+    float part[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.0, part[i] = 0.f;
+    int cnt = 0;
+    for (long long r = r_begin + pr; r < r_end; r += P) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(X + r * d) + g);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            part[2 * i] += f.x;
+            part[2 * i + 1] += f.y;
+        }
+        if (++cnt == 32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] += part[i], part[i] = 0.f;
+            cnt = 0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&acc[1 + g * 8 + i], s[i] + (double)part[i]);
+}
+
 __global__ void __launch_bounds__(kFadThreads) fad_finalize_kernel(const double* __restrict__ acc, int d,
                                                                    double* __restrict__ mu,
                                                                    double* __restrict__ cov) {
@@ -132,10 +166,19 @@ extern "C" int dm_fad_moments_ex(const void* x_f16, long long N, int d, double* 
         fad_xtx_kernel<<<dim3(nt, nt, nz), kFadThreads, 0, as_stream(stream)>>>(X, N, d, rows, acc + 1 + d);
         DM_LAUNCHED();
     }
-    const long long crow = std::max<long long>(64, (N + 63) / 64);
-    fad_colsum_kernel<<<dim3((d + kFadThreads - 1) / kFadThreads, (unsigned)((N + crow - 1) / crow)), kFadThreads, 0,
-                        as_stream(stream)>>>(X, N, d, crow, acc);
-    DM_LAUNCHED();
+    if (d % 8 == 0 && d / 8 <= 1024 && (reinterpret_cast<uintptr_t>(x_f16) & 15) == 0) {
+        const int G = d / 8, P = 1024 / G;
+        const long long want_ctas = 4LL * num_sms();
+        const long long rows = std::max<long long>(P, (N + want_ctas - 1) / want_ctas);
+        fad_colsum_vec_kernel<<<(unsigned)((N + rows - 1) / rows), G * P, 0, as_stream(stream)>>>(X, N, d, G, P, rows,
+                                                                                                acc);
+        DM_LAUNCHED();
+    } else {
+        const long long crow = std::max<long long>(64, (N + 63) / 64);
+        fad_colsum_kernel<<<dim3((d + kFadThreads - 1) / kFadThreads, (unsigned)((N + crow - 1) / crow)), kFadThreads,
+                            0, as_stream(stream)>>>(X, N, d, crow, acc);
+        DM_LAUNCHED();
+    }
     return DM_OK;
 }
 

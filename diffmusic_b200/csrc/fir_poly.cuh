@@ -12,22 +12,26 @@
 namespace dm {
 
 constexpr int kFirR = 4;  // outputs per thread
+// staged-input index padding: thread t of the forward kernel reads xs[orig * 4 t + ...], a stride of 4*orig words;
+// one extra word every 32 spreads that over all banks (same idea as padi() in fft_core.cuh)
+DM_HD int fir_pad(int i) { return i + (i >> 5); }
+DM_HDC int fir_padded_len(int n) { return n + (n >> 5) + 1; }
 
 // ---- forward: outputs j0 .. j0+3 (block-relative), xs[n] = xz[orig*j_first + n] staged by the caller ----
-// Needs xs[orig*(j0 + mm) + kappa] for mm < M + 3, i.e. up to orig*(j0 + 3) + taps - 1.
+// Needs xs[fir_pad(orig*(j0 + mm) + kappa)] for mm < M + 3, i.e. logical indices up to orig*(j0 + 3) + taps - 1.
 DM_HD void fir_fwd4(const float* xs, const float* w, int taps, int orig, int j0, float (&acc)[kFirR]) {
 #pragma unroll
     for (int c = 0; c < kFirR; ++c) acc[c] = 0.f;
     for (int kappa = 0; kappa < orig; ++kappa) {
         const int M = (taps - kappa + orig - 1) / orig;  // taps of this phase
         float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;    // weights m = mm, mm-1, mm-2, mm-3
-        const float* xp = xs + orig * j0 + kappa;
+        const int x0 = orig * j0 + kappa;
         for (int mm = 0; mm < M + kFirR - 1; ++mm) {
             w3 = w2;
             w2 = w1;
             w1 = w0;
             w0 = (mm < M) ? w[kappa + orig * mm] : 0.f;
-            const float xv = xp[orig * mm];
+            const float xv = xs[fir_pad(x0 + orig * mm)];
             acc[0] = fmaf(xv, w0, acc[0]);
             acc[1] = fmaf(xv, w1, acc[1]);
             acc[2] = fmaf(xv, w2, acc[2]);

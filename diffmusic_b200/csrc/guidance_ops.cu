@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(kEwThreads) resample_fwd_poly_kernel(const flo
                                                                        long long Ly, int span) {
     extern __shared__ float sm[];
     float* kw = sm;            // [taps]
-    float* xs = kw + taps;     // [span] xz[orig*o0 ...]
-    float* outs = xs + span;   // [kRsChunk]
+    float* xs = kw + taps;                     // [fir_padded_len(span)] xz[orig*o0 ...], bank-padded
+    float* outs = xs + fir_padded_len(span);   // [kRsChunk]
     const int b = blockIdx.y;
     const long long o0 = (long long)blockIdx.x * kRsChunk;
     const int no = (int)min((long long)kRsChunk, Ly - o0);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kEwThreads) resample_fwd_poly_kernel(const flo
     const float* xb = x + (long long)b * x_bstride;
     for (int i = threadIdx.x; i < span; i += kEwThreads) {
         long long g = x_lo + i;
-        xs[i] = (g >= 0 && g < L) ? xb[g] : 0.f;
+        xs[fir_pad(i)] = (g >= 0 && g < L) ? xb[g] : 0.f;
     }
     __syncthreads();
     for (int j0 = threadIdx.x * kFirR; j0 < no; j0 += kEwThreads * kFirR) {
@@ -273,7 +273,7 @@ extern "C" int dm_resample_fwd(const float* x, long long x_bstride, long long L,
     DM_REQUIRE(n_new >= 1 && taps >= 1 && orig >= 1 && width >= 0);
     if (n_new == 1) {  // integer decimation: polyphase kernel
         const int span1 = orig * (kRsChunk + kFirR) + taps;
-        const size_t smem1 = ((size_t)taps + span1 + kRsChunk) * sizeof(float);
+        const size_t smem1 = ((size_t)taps + fir_padded_len(span1) + kRsChunk) * sizeof(float);
         if (smem1 <= 200 * 1024) {
             DM_SMEM_ONCE(resample_fwd_poly_kernel, smem1);
             resample_fwd_poly_kernel<<<dim3((unsigned)((Ly + kRsChunk - 1) / kRsChunk), B), kEwThreads, smem1,

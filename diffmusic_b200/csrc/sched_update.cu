@@ -19,17 +19,6 @@ constexpr int kThreads = 256;
 constexpr int kCluster = 8;
 
 template <int W>
-struct VecT;
-template <>
-struct VecT<4> {
-    using type = float4;
-};
-template <>
-struct VecT<1> {
-    using type = float;
-};
-
-template <int W>
 __device__ __forceinline__ void ldv(const float* __restrict__ p, long long v, float (&o)[W]) {
     if (W == 4) {
         float4 t = reinterpret_cast<const float4*>(p)[v];
@@ -198,7 +187,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
     const long long chunk = (nv_clip + kCluster - 1) / kCluster;
     const long long lo = rank * chunk, hi = min(nv_clip, lo + chunk);
     const long long off = clip * nv_clip;  // in vectors
-    const float kappa_num = p.grad_scale;  // g = (grad_scale * g0) / sqrt_a   (scheduling_dsg.py:210, autograd)
+    const float gscale = p.grad_scale;  // g = (grad_scale * g0) / sqrt_a   (scheduling_dsg.py:210, autograd)
 
     // ---- sweep 1: |g|^2 (+ |z|^2 and <z, g> for DiffMusic) ----
     double s_gg = 0.0, s_zz = 0.0, s_gz = 0.0;
@@ -209,7 +198,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
         float a = 0.f, b = 0.f, c = 0.f;
 #pragma unroll
         for (int i = 0; i < W; ++i) {
-            float gi = dvd(mul(kappa_num, g[i]), p.sqrt_a);
+            float gi = dvd(mul(gscale, g[i]), p.sqrt_a);
             a = fmaf(gi, gi, a);
             if (KIND == kDiffMusic) {
                 b = fmaf(z[i], z[i], b);
@@ -237,7 +226,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
             float a = 0.f;
 #pragma unroll
             for (int i = 0; i < W; ++i) {
-                float gi = dvd(mul(kappa_num, g[i]), p.sqrt_a);
+                float gi = dvd(mul(gscale, g[i]), p.sqrt_a);
                 float dstar = dvd(mul(-p.r, gi), add(gn, p.e));
                 float ds = mul(p.std, z[i]);
                 float mix = add(ds, mul(p.rate, sub(dstar, ds)));
@@ -274,7 +263,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
 #pragma unroll
         for (int i = 0; i < W; ++i) {
             float mean = add(mul(p.sqrt_p, x0[i]), mul(p.dir_coef, ep[i]));
-            float gi = dvd(mul(kappa_num, g[i]), p.sqrt_a);
+            float gi = dvd(mul(gscale, g[i]), p.sqrt_a);
             if (KIND == kDsg) {
                 float dstar = dvd(mul(-p.r, gi), add(gn, p.e));
                 float ds = mul(p.std, z[i]);

@@ -184,11 +184,11 @@ void emul_resample_fwd(const float* x, long long L, const float* kernel, int tap
                        long long Ly) {
     const int CH = 2048;
     const int span = orig * (CH + kFirR) + taps;
-    std::vector<float> xs(span), outs(CH + kFirR);
+    std::vector<float> xs(fir_padded_len(span)), outs(CH + kFirR);
     for (long long o0 = 0; o0 < Ly; o0 += CH) {
         const int no = (int)std::min<long long>(CH, Ly - o0);
         const long long x_lo = (long long)orig * o0 - width;
-        for (int i = 0; i < span; ++i) { long long g = x_lo + i; xs[i] = (g >= 0 && g < L) ? x[g] : 0.f; }
+        for (int i = 0; i < span; ++i) { long long g = x_lo + i; xs[fir_pad(i)] = (g >= 0 && g < L) ? x[g] : 0.f; }
         for (int j0 = 0; j0 < no; j0 += kFirR) {
             float acc[kFirR];
             fir_fwd4(xs.data(), kernel, taps, orig, j0, acc);
