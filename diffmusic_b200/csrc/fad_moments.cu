@@ -93,7 +93,6 @@ __global__ void __launch_bounds__(1024) fad_colsum_vec_kernel(const __half* __re
                                                               double* __restrict__ acc) {
     const int g = threadIdx.x % G, pr = threadIdx.x / G;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&acc[0], (double)N);
-    if (pr >= P) return;
     const long long r_begin = (long long)blockIdx.x * rows_per_cta;
     const long long r_end = min(N, r_begin + rows_per_cta);
     double s[8];
@@ -116,8 +115,16 @@ __global__ void __launch_bounds__(1024) fad_colsum_vec_kernel(const __half* __re
             cnt = 0;
         }
     }
+    // block-level reduction over the P row groups in shared memory, then ONE float64 atomic per column per CTA
+    extern __shared__ double red[];  // [P][d]
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&acc[1 + g * 8 + i], s[i] + (double)part[i]);
+    for (int i = 0; i < 8; ++i) red[(size_t)pr * d + g * 8 + i] = s[i] + (double)part[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        double t = 0.0;
+        for (int q = 0; q < P; ++q) t += red[(size_t)q * d + c];
+        atomicAdd(&acc[1 + c], t);
+    }
 }
 
 __global__ void __launch_bounds__(kFadThreads) fad_finalize_kernel(const double* __restrict__ acc, int d,
@@ -167,11 +174,13 @@ extern "C" int dm_fad_moments_ex(const void* x_f16, long long N, int d, double* 
         DM_LAUNCHED();
     }
     if (d % 8 == 0 && d / 8 <= 1024 && (reinterpret_cast<uintptr_t>(x_f16) & 15) == 0) {
-        const int G = d / 8, P = 1024 / G;
-        const long long want_ctas = 4LL * num_sms();
-        const long long rows = std::max<long long>(P, (N + want_ctas - 1) / want_ctas);
-        fad_colsum_vec_kernel<<<(unsigned)((N + rows - 1) / rows), G * P, 0, as_stream(stream)>>>(X, N, d, G, P, rows,
-                                                                                                acc);
+        const int G = d / 8, P = 1024 / G;  // G * P <= 1024 threads, every thread owns (row group, 8 columns)
+        const long long want_ctas = 2LL * num_sms();
+        const long long rows = std::max<long long>(8LL * P, (N + want_ctas - 1) / want_ctas);
+        const size_t smem = (size_t)P * d * sizeof(double);
+        DM_SMEM_ONCE(fad_colsum_vec_kernel, smem);
+        fad_colsum_vec_kernel<<<(unsigned)((N + rows - 1) / rows), G * P, smem, as_stream(stream)>>>(X, N, d, G, P,
+                                                                                                   rows, acc);
         DM_LAUNCHED();
     } else {
         const long long crow = std::max<long long>(64, (N + 63) / 64);

@@ -69,6 +69,29 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                                  uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%4, %5}], [%2], %3;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t"
@@ -117,6 +140,13 @@ struct FadTcParams {
     double* sxx;
 };
 
+// kCluster == 2: the two CTAs of a cluster own tiles (ti, tj) and (ti, tj+1) of the same row range, i.e. they need the
+// SAME A operand (column block ti).  Each CTA fetches one 64-column half of A and TMA-multicasts it into both CTAs'
+// shared memory, so the L2 -> SM traffic per CTA drops from A + B to A/2 + B (the kernel is L2-fabric bound, see
+// profiles/README.md).  A stage may be refilled only when BOTH consumers are done with it: the MMA warp's commit is
+// multicast to both CTAs' `empty` barriers (count 2).
+// kCluster == 1: the leftover tile of rows with an odd number of upper-triangular tiles, no multicast.
+template <int kCluster>
 __global__ void __launch_bounds__(kTcThreads, 1)
     fad_xtx_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FadTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -129,14 +159,29 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // linear upper-triangular tile index -> (ti, tj), tj >= ti
-    int ti = 0, rem = blockIdx.x;
-    while (rem >= p.ntile - ti) {
-        rem -= p.ntile - ti;
-        ++ti;
+    // tile assignment over the upper triangle (tj >= ti).  Row ti has n = ntile - ti tiles: n/2 pairs handled by
+    // 2-CTA clusters, and when n is odd its last tile (ti, ntile-1) by a single CTA.
+    const uint32_t crank = (kCluster == 2) ? cluster_ctarank() : 0;
+    int ti = 0, tj;
+    if (kCluster == 2) {
+        int pair = blockIdx.x >> 1;
+        while (pair >= (p.ntile - ti) / 2) {
+            pair -= (p.ntile - ti) / 2;
+            ++ti;
+        }
+        tj = ti + 2 * pair + (int)crank;
+    } else {
+        int single = blockIdx.x;
+        for (;; ++ti) {
+            if ((p.ntile - ti) & 1) {
+                if (single == 0) break;
+                --single;
+            }
+        }
+        tj = p.ntile - 1;
     }
-    const int tj = ti + rem;
     const bool diag = (ti == tj);
+    constexpr uint16_t kAllCtas = (uint16_t)((1u << kCluster) - 1);
     const long long r_begin = (long long)blockIdx.y * p.rows_per_cta;
     const long long r_end = min(p.N, r_begin + p.rows_per_cta);
     const int nkb = r_end > r_begin ? (int)((r_end - r_begin + kBlockK - 1) / kBlockK) : 0;
@@ -145,7 +190,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], kCluster);  // every CTA that received a multicast half must release the stage
         }
         for (int s = 0; s < kAccStages; ++s) {
             mbar_init(&tfull[s], 1);
@@ -160,6 +205,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (kCluster > 1) cluster_sync_all();  // peer barriers are initialised before any multicast / remote arrive
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -173,8 +219,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 uint8_t* b = a + kOperandBytes;
                 const int row = (int)(r_begin + (long long)kb * kBlockK);
                 mbar_expect_tx(&full[s], diag ? kOperandBytes : 2 * kOperandBytes);
-                tma_load_2d(&tmap, &full[s], a, ti * kTile, row);
-                tma_load_2d(&tmap, &full[s], a + kBoxBytes, ti * kTile + kBoxCols, row);
+                if (kCluster == 2) {  // my half of the shared A operand goes to both CTAs
+                    tma_load_2d_mcast(&tmap, &full[s], a + crank * kBoxBytes, ti * kTile + (int)crank * kBoxCols, row,
+                                      kAllCtas);
+                } else {
+                    tma_load_2d(&tmap, &full[s], a, ti * kTile, row);
+                    tma_load_2d(&tmap, &full[s], a + kBoxBytes, ti * kTile + kBoxCols, row);
+                }
                 if (!diag) {
                     tma_load_2d(&tmap, &full[s], b, tj * kTile, row);
                     tma_load_2d(&tmap, &full[s], b + kBoxBytes, tj * kTile + kBoxCols, row);
@@ -202,7 +253,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     umma_f16(d_tmem, make_desc_mn_sw128(a_addr + koff), make_desc_mn_sw128(b_addr + koff), kIdesc,
                              (kb % kFlush != 0 || k != 0) ? 1u : 0u);
                 }
-                umma_commit(&empty[s]);  // smem stage free once these MMAs have read it
+                // smem stage free (in every CTA that multicasts into it) once these MMAs have read it
+                if (kCluster == 2) umma_commit_mcast(&empty[s], kAllCtas);
+                else umma_commit(&empty[s]);
                 if (kb % kFlush == kFlush - 1 || kb == nkb - 1) umma_commit(&tfull[as]);
             }
         }
@@ -246,6 +299,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (kCluster > 1) cluster_sync_all();  // the peer may still arrive on / multicast into this CTA's shared memory
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
@@ -288,18 +342,45 @@ int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, cudaStream_t 
     p.ntile = (d + kTile - 1) / kTile;
     p.N = N;
     p.sxx = sxx;
-    const int ntri = p.ntile * (p.ntile + 1) / 2;
-    // one CTA per SM (192 KB of pipeline stages): split the rows so the grid covers the machine about once, in
-    // multiples of the flush slab so every CTA drains whole slabs
-    long long splits = std::max<long long>(1, num_sms() / ntri);
-    long long rows = (N + splits - 1) / splits;
+    int npairs = 0, nsingles = 0;
+    for (int ti = 0; ti < p.ntile; ++ti) {
+        npairs += (p.ntile - ti) / 2;
+        nsingles += (p.ntile - ti) & 1;
+    }
+    // one CTA per SM (192 KB of pipeline stages): each launch splits the rows so that its grid covers the machine about
+    // once, in multiples of the flush slab so every CTA drains whole slabs
     const long long slab_rows = (long long)kFlush * kBlockK;
-    rows = std::max<long long>(slab_rows, (rows + slab_rows - 1) / slab_rows * slab_rows);
-    p.rows_per_cta = rows;
-    const int gy = (int)((N + rows - 1) / rows);
-    DM_SMEM_ONCE(fad_xtx_tc_kernel, kTcSmemBytes);
-    fad_xtx_tc_kernel<<<dim3(ntri, gy), kTcThreads, kTcSmemBytes, st>>>(tmap, p);
-    DM_LAUNCHED();
+    auto rows_for = [&](int tiles) {
+        long long splits = std::max<long long>(1, num_sms() / tiles);
+        long long rows = (N + splits - 1) / splits;
+        return std::max<long long>(slab_rows, (rows + slab_rows - 1) / slab_rows * slab_rows);
+    };
+    if (npairs > 0) {
+        p.rows_per_cta = rows_for(2 * npairs);
+        const int gy = (int)((N + p.rows_per_cta - 1) / p.rows_per_cta);
+        DM_SMEM_ONCE(fad_xtx_tc_kernel<2>, kTcSmemBytes);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * npairs, gy);
+        cfg.blockDim = dim3(kTcThreads);
+        cfg.dynamicSmemBytes = kTcSmemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DM_CUDA(cudaLaunchKernelEx(&cfg, fad_xtx_tc_kernel<2>, tmap, p));
+        DM_LAUNCHED();
+    }
+    if (nsingles > 0) {
+        p.rows_per_cta = rows_for(nsingles);
+        const int gy = (int)((N + p.rows_per_cta - 1) / p.rows_per_cta);
+        DM_SMEM_ONCE(fad_xtx_tc_kernel<1>, kTcSmemBytes);
+        fad_xtx_tc_kernel<1><<<dim3(nsingles, gy), kTcThreads, kTcSmemBytes, st>>>(tmap, p);
+        DM_LAUNCHED();
+    }
     return DM_OK;
 }
 
