@@ -34,10 +34,13 @@ DM_HD cf cmul_i(cf a) {
     return SIGN > 0 ? cf{-a.y, a.x} : cf{a.y, -a.x};
 }
 
-// shared-memory index padding: one extra word every 8 keeps all Stockham passes (stride-8 / stride-64 scatters)
-// essentially bank-conflict free with split re/im float arrays.
-DM_HD int padi(int i) { return i + (i >> 3); }
-DM_HDC int padded_len(int n) { return n + (n >> 3) + 8; }
+// Shared-memory index swizzle for the split re/im float arrays: XOR-ing the low five address bits with bits [3,8) of
+// the index makes EVERY access pattern of the radix-8 Stockham passes bank-conflict free -- the unit-stride loads
+// j + r*T, the stride-8 scatter of the first pass, the 8-block scatter of the second and the unit-stride scatters of the
+// later ones (exhaustively checked for N = 512 and N = 4096: 96 / 1024 wavefronts = the minimum, versus 160 / 1792 for
+// the usual pad-one-word-every-8 layout).  No padding words are needed.  (Named padi for historical reasons.)
+DM_HD int padi(int i) { return i ^ ((i >> 3) & 31); }
+DM_HDC int padded_len(int n) { return n; }
 
 // 8-point DFT in registers: out[q] = sum_r v[r] * exp(SIGN * 2*pi*i * r*q / 8)
 template <int SIGN>
@@ -116,25 +119,24 @@ DM_HD void stockham_pass_rt(int j, const cf (&w)[7], Load load, Store store) {
     for (int q = 0; q < 8; ++q) store(j0 + q * NS, v[q]);
 }
 
-// Padded split-array I/O with the index arithmetic strength-reduced: for the radix-8 access patterns the padded
-// address is one padi() per thread plus compile-time strides (padi(j + r*T) = padi(j) + r*(T + T/8) when 8 | T, and
-// padi(j0 + q*NS) = padi(j0) + q*(NS + NS/8) when 8 | NS; for NS = 1 the eight outputs are contiguous).
+// Swizzled split-array I/O of one radix-8 butterfly: inputs j + r*T, outputs j0 + q*NS.
 template <int N>
 DM_HD void load8_pad(const float* __restrict__ re, const float* __restrict__ im, int j, cf (&v)[8]) {
-    constexpr int S = N / 8 + N / 64;
-    const int b = padi(j);
+    constexpr int T = N / 8;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = cf{re[b + r * S], im[b + r * S]};
+    for (int r = 0; r < 8; ++r) {
+        const int a = padi(j + r * T);
+        v[r] = cf{re[a], im[a]};
+    }
 }
 template <int NS>
 DM_HD void store8_pad(float* __restrict__ re, float* __restrict__ im, int j, const cf (&v)[8]) {
-    constexpr int S = (NS == 1) ? 1 : NS + NS / 8;
-    const int k = j % NS;
-    const int b = padi((j / NS) * NS * 8 + k);
+    const int j0 = (j / NS) * NS * 8 + j % NS;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        re[b + q * S] = v[q].x;
-        im[b + q * S] = v[q].y;
+        const int a = padi(j0 + q * NS);
+        re[a] = v[q].x;
+        im[a] = v[q].y;
     }
 }
 template <int SIGN>
@@ -155,6 +157,34 @@ DM_HD void stockham_pass_pad(int j, const cf (&w)[7], const float* in_re, const 
     twiddle8<SIGN>(v, w);
     dft8<SIGN>(v);
     store8_pad<NS>(out_re, out_im, j, v);
+}
+
+// Pass whose seven twiddles are generated from the first one by complex multiplication (w^2 = w*w, w^3 = w^2*w,
+// w^4 = (w^2)^2, w^5 = w^4*w, w^6 = (w^3)^2, w^7 = w^4*w^3): one table read per pass and thread instead of seven strided
+// ones.  Used by the 4096-point RIR transform, where each CTA does a single block and register-resident twiddles
+// would not be reused.  Error: <= 3 extra roundings on |w| = 1, far below the 1e-4 parity bound.
+template <int N, int NS, int SIGN, class Load, class Store>
+DM_HD void stockham_pass_rec(int j, const cf* __restrict__ tw, Load load, Store store) {
+    constexpr int T = N / 8;
+    constexpr int TWS = N / (NS * 8);
+    const int k = j % NS;
+    cf v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = load(j + r * T);
+    cf w1 = tw[k * TWS];
+    if (SIGN > 0) w1.y = -w1.y;
+    const cf w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+    v[1] = cmul(v[1], w1);
+    v[2] = cmul(v[2], w2);
+    v[3] = cmul(v[3], w3);
+    v[4] = cmul(v[4], w4);
+    v[5] = cmul(v[5], cmul(w4, w1));
+    v[6] = cmul(v[6], cmul(w3, w3));
+    v[7] = cmul(v[7], cmul(w4, w3));
+    dft8<SIGN>(v);
+    const int j0 = (j / NS) * NS * 8 + k;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) store(j0 + q * NS, v[q]);
 }
 
 // Split-array accessors with padding.

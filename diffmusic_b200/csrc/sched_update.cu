@@ -171,7 +171,33 @@ __device__ __forceinline__ void cluster_sum3(cg::cluster_group& cluster, double*
 
 enum NormKind { kDsg = 0, kDiffMusic = 1 };
 
-template <int KIND, int W>
+// per-element pieces of B.4 / B.5, written once and used by all sweeps
+struct NormScalars {
+    float gn, zn, w0, w1, mix_scale;
+    bool lin;
+};
+__device__ __forceinline__ float elem_g(const NormParams& p, float g0) { return dvd(mul(p.grad_scale, g0), p.sqrt_a); }
+__device__ __forceinline__ float elem_mix(const NormParams& p, float gn, float g0, float z) {
+    const float dstar = dvd(mul(-p.r, elem_g(p, g0)), add(gn, p.e));  // scheduling_dsg.py:214
+    const float ds = mul(p.std, z);
+    return add(ds, mul(p.rate, sub(dstar, ds)));                       // :221-222
+}
+template <int KIND>
+__device__ __forceinline__ float elem_out(const NormParams& p, const NormScalars& c, float x0, float ep, float g0,
+                                          float z) {
+    const float mean = add(mul(p.sqrt_p, x0), mul(p.dir_coef, ep));
+    if (KIND == kDsg) return add(mean, dvd(mul(p.r, elem_mix(p, c.gn, g0, z)), c.mix_scale));  // :224
+    const float u = -mul(dvd(elem_g(p, g0), add(c.gn, p.e)), c.zn);      // -normalized_grad, scheduling_diffmusic.py:221
+    const float m = c.lin ? add(z, mul(p.rate, sub(u, z))) : add(mul(c.w0, z), mul(c.w1, u));  // slerp :59-68
+    return add(mean, mul(p.std, m));
+}
+
+// One 8-CTA cluster per clip.  CACHED: every thread keeps its <= kIt vectors of x0 / eps / g0 / z in registers, so the
+// clip is read from memory exactly once (all loads issued up front, their latency overlaps the reductions); otherwise
+// (clips longer than 8 * 256 * kIt * W elements) the later sweeps re-read from L2.
+constexpr int kIt = 4;
+
+template <int KIND, int W, bool CACHED>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) norm_update_kernel(NormParams p) {
     cg::cluster_group cluster = cg::this_cluster();
     if (p.coef != nullptr) {
@@ -187,18 +213,31 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
     const long long chunk = (nv_clip + kCluster - 1) / kCluster;
     const long long lo = rank * chunk, hi = min(nv_clip, lo + chunk);
     const long long off = clip * nv_clip;  // in vectors
-    const float gscale = p.grad_scale;  // g = (grad_scale * g0) / sqrt_a   (scheduling_dsg.py:210, autograd)
+
+    float rx0[CACHED ? kIt : 1][W], rep[CACHED ? kIt : 1][W], rg[CACHED ? kIt : 1][W], rz[CACHED ? kIt : 1][W];
+    if (CACHED) {
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const long long v = lo + threadIdx.x + (long long)it * kThreads;
+            if (v < hi) {
+                ldv<W>(p.g0, off + v, rg[it]);
+                ldv<W>(p.z, off + v, rz[it]);
+                ldv<W>(p.x0, off + v, rx0[it]);
+                ldv<W>(p.eps, off + v, rep[it]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < W; ++i) rg[it][i] = rz[it][i] = rx0[it][i] = rep[it][i] = 0.f;
+            }
+        }
+    }
 
     // ---- sweep 1: |g|^2 (+ |z|^2 and <z, g> for DiffMusic) ----
     double s_gg = 0.0, s_zz = 0.0, s_gz = 0.0;
-    for (long long v = lo + threadIdx.x; v < hi; v += kThreads) {
-        float g[W], z[W];
-        ldv<W>(p.g0, off + v, g);
-        if (KIND == kDiffMusic) ldv<W>(p.z, off + v, z);
+    auto acc1 = [&](const float (&g)[W], const float (&z)[W]) {
         float a = 0.f, b = 0.f, c = 0.f;
 #pragma unroll
         for (int i = 0; i < W; ++i) {
-            float gi = dvd(mul(gscale, g[i]), p.sqrt_a);
+            const float gi = elem_g(p, g[i]);
             a = fmaf(gi, gi, a);
             if (KIND == kDiffMusic) {
                 b = fmaf(z[i], z[i], b);
@@ -208,74 +247,88 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
         s_gg += a;
         s_zz += b;
         s_gz += c;
+    };
+    if (CACHED) {
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) acc1(rg[it], rz[it]);  // out-of-range slots hold zeros
+    } else {
+        for (long long v = lo + threadIdx.x; v < hi; v += kThreads) {
+            float g[W], z[W] = {};
+            ldv<W>(p.g0, off + v, g);
+            if (KIND == kDiffMusic) ldv<W>(p.z, off + v, z);
+            acc1(g, z);
+        }
     }
     block_sum3(s_gg, s_zz, s_gz, wred, slot1);
     double t1[3];
     cluster_sum3(cluster, slot1, t1);
-    const float gn = sqrtf((float)t1[0]);
+    NormScalars c{};
+    c.gn = sqrtf((float)t1[0]);
 
-    float w0 = 0.f, w1 = 0.f, mix_scale = 0.f, zn = 0.f;
-    bool lin = false;
     if (KIND == kDsg) {
-        // ---- sweep 2: |mix|^2, mix = std z + rate (d* - std z), d* = -r g/(|g|+e)   (scheduling_dsg.py:214-223) ----
+        // ---- sweep 2: |mix|^2 (scheduling_dsg.py:214-223) ----
         double s_mm = 0.0;
-        for (long long v = lo + threadIdx.x; v < hi; v += kThreads) {
-            float g[W], z[W];
-            ldv<W>(p.g0, off + v, g);
-            ldv<W>(p.z, off + v, z);
+        auto acc2 = [&](const float (&g)[W], const float (&z)[W], bool live) {
             float a = 0.f;
 #pragma unroll
             for (int i = 0; i < W; ++i) {
-                float gi = dvd(mul(gscale, g[i]), p.sqrt_a);
-                float dstar = dvd(mul(-p.r, gi), add(gn, p.e));
-                float ds = mul(p.std, z[i]);
-                float mix = add(ds, mul(p.rate, sub(dstar, ds)));
+                const float mix = elem_mix(p, c.gn, g[i], z[i]);
                 a = fmaf(mix, mix, a);
             }
-            s_mm += a;
+            if (live) s_mm += a;
+        };
+        if (CACHED) {
+#pragma unroll
+            for (int it = 0; it < kIt; ++it) acc2(rg[it], rz[it], lo + threadIdx.x + (long long)it * kThreads < hi);
+        } else {
+            for (long long v = lo + threadIdx.x; v < hi; v += kThreads) {
+                float g[W], z[W];
+                ldv<W>(p.g0, off + v, g);
+                ldv<W>(p.z, off + v, z);
+                acc2(g, z, true);
+            }
         }
         __syncthreads();  // wred reuse
         block_sum3(s_mm, 0.0, 0.0, wred, slot2);
         double t2[3];
         cluster_sum3(cluster, slot2, t2);
-        mix_scale = add(sqrtf((float)t2[0]), p.e);
+        c.mix_scale = add(sqrtf((float)t2[0]), p.e);
     } else {
         // ---- slerp weights (scheduling_diffmusic.py:59-68), per clip, on the device ----
-        zn = sqrtf((float)t1[1]);
+        c.zn = sqrtf((float)t1[1]);
         // u = -g/(gn+e) * zn ; |u| = gn/(gn+e) * zn ; cos = <z,u>/(|z||u|) = -<z,g>/(gn zn)   (NaN when gn == 0, as ref)
-        const float c = (float)(-t1[2] / ((double)gn * (double)zn));
-        lin = fabsf(c) > p.threshold;  // data-dependent branch of slerp, resolved here instead of on the host
-        if (!lin) {
-            const float th = acosf(c);
+        const float cs = (float)(-t1[2] / ((double)c.gn * (double)c.zn));
+        c.lin = fabsf(cs) > p.threshold;  // data-dependent branch of slerp, resolved here instead of on the host
+        if (!c.lin) {
+            const float th = acosf(cs);
             const float sn = sinf(th);
-            w0 = dvd(sinf(mul(1.f - p.rate, th)), sn);
-            w1 = dvd(sinf(mul(p.rate, th)), sn);
+            c.w0 = dvd(sinf(mul(1.f - p.rate, th)), sn);
+            c.w1 = dvd(sinf(mul(p.rate, th)), sn);
         }
     }
 
     // ---- final sweep: write prev ----
-    for (long long v = lo + threadIdx.x; v < hi; v += kThreads) {
-        float x0[W], ep[W], g[W], z[W], o[W];
-        ldv<W>(p.x0, off + v, x0);
-        ldv<W>(p.eps, off + v, ep);
-        ldv<W>(p.g0, off + v, g);
-        ldv<W>(p.z, off + v, z);
+    auto emit = [&](long long v, const float (&x0)[W], const float (&ep)[W], const float (&g)[W], const float (&z)[W]) {
+        float o[W];
 #pragma unroll
-        for (int i = 0; i < W; ++i) {
-            float mean = add(mul(p.sqrt_p, x0[i]), mul(p.dir_coef, ep[i]));
-            float gi = dvd(mul(gscale, g[i]), p.sqrt_a);
-            if (KIND == kDsg) {
-                float dstar = dvd(mul(-p.r, gi), add(gn, p.e));
-                float ds = mul(p.std, z[i]);
-                float mix = add(ds, mul(p.rate, sub(dstar, ds)));
-                o[i] = add(mean, dvd(mul(p.r, mix), mix_scale));
-            } else {
-                float u = -mul(dvd(gi, add(gn, p.e)), zn);
-                float m = lin ? add(z[i], mul(p.rate, sub(u, z[i]))) : add(mul(w0, z[i]), mul(w1, u));
-                o[i] = add(mean, mul(p.std, m));
-            }
-        }
+        for (int i = 0; i < W; ++i) o[i] = elem_out<KIND>(p, c, x0[i], ep[i], g[i], z[i]);
         stv<W>(p.prev, off + v, o);
+    };
+    if (CACHED) {
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const long long v = lo + threadIdx.x + (long long)it * kThreads;
+            if (v < hi) emit(v, rx0[it], rep[it], rg[it], rz[it]);
+        }
+    } else {
+        for (long long v = lo + threadIdx.x; v < hi; v += kThreads) {
+            float x0[W], ep[W], g[W], z[W];
+            ldv<W>(p.x0, off + v, x0);
+            ldv<W>(p.eps, off + v, ep);
+            ldv<W>(p.g0, off + v, g);
+            ldv<W>(p.z, off + v, z);
+            emit(v, x0, ep, g, z);
+        }
     }
     cluster.sync();  // keep every CTA's shared memory alive until all remote reads are done
 }
@@ -284,10 +337,15 @@ template <int KIND>
 static int launch_norm(const NormParams& p, int n_clips, cudaStream_t st) {
     const bool vec = (p.n_clip % 4 == 0) && aligned16(p.x0) && aligned16(p.eps) && aligned16(p.g0) &&
                      aligned16(p.z) && aligned16(p.prev);
-    if (vec)
-        norm_update_kernel<KIND, 4><<<n_clips * kCluster, kThreads, 0, st>>>(p);
+    const int W = vec ? 4 : 1;
+    const long long chunk = (p.n_clip / W + kCluster - 1) / kCluster;
+    const bool cached = vec && chunk <= (long long)kIt * kThreads;  // the 10 s latent: 1000 vectors per CTA
+    if (cached)
+        norm_update_kernel<KIND, 4, true><<<n_clips * kCluster, kThreads, 0, st>>>(p);
+    else if (vec)
+        norm_update_kernel<KIND, 4, false><<<n_clips * kCluster, kThreads, 0, st>>>(p);
     else
-        norm_update_kernel<KIND, 1><<<n_clips * kCluster, kThreads, 0, st>>>(p);
+        norm_update_kernel<KIND, 1, false><<<n_clips * kCluster, kThreads, 0, st>>>(p);
     return 0;
 }
 

@@ -387,3 +387,65 @@ def test_graphed_step_equals_eager_step(sched_name, op_name, eta):
         assert rel_l2(b.pred_original_sample, a.pred_original_sample) < 1e-6, t
         assert abs(float(b.loss.float().ravel()[0]) - float(a.loss.float().ravel()[0])) <= 1e-6 * abs(float(a.loss.float().ravel()[0])) + 1e-12
         xe, xg = a.prev_sample, b.prev_sample  # chain the trajectory
+
+
+# ------------------------------------------------------------------------------------------------ update kernels, all paths
+@pytest.mark.parametrize("n_clip", [3200, 32000, 38400, 3203])
+@pytest.mark.parametrize("kind", ["dsg", "diffmusic"])
+def test_norm_update_kernel_paths(kind, n_clip):
+    """dm_sched_{dsg,diffmusic}_update against the reference algebra (scheduling_dsg.py:189-224,
+    scheduling_diffmusic.py:59-68,191-223) for the register-cached path (<= 32768 elements per clip), the re-reading
+    path (longer clips) and the scalar path (n_clip % 4 != 0); 3 clips, per-clip norms."""
+    from diffmusic_b200 import _lib
+    B = 3
+    g = torch.Generator().manual_seed(n_clip)
+    x0, ep, g0, z = (torch.randn(B, n_clip, generator=g) for _ in range(4))
+    g0 = g0 * 37.0
+    sa, sp, dirc, std, rate, e = 0.7311, 0.8123, 0.5377, 0.2214, 0.08, 1e-8
+    r = float(torch.sqrt(torch.tensor(n_clip)) * std)
+    want = []
+    for b in range(B):
+        gb = g0[b] * (1.0 / 1000.0) / sa
+        mean = sp * x0[b] + dirc * ep[b]
+        gn = torch.linalg.norm(gb)
+        if kind == "dsg":
+            d_star = -r * gb / (gn + e)
+            d_s = std * z[b]
+            mix = d_s + rate * (d_star - d_s)
+            want.append(mean + r * mix / (torch.linalg.norm(mix) + e))
+        else:
+            gt = gb / (gn + e) * torch.linalg.norm(z[b])
+            want.append(mean + std * osteps.slerp(z[b], -gt, rate))
+    want = torch.stack(want)
+    d = [t.to(DEV).contiguous() for t in (x0, ep, g0, z)]
+    prev = torch.empty_like(d[0])
+    if kind == "dsg":
+        _lib.call("dm_sched_dsg_update", d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
+                  prev.data_ptr(), B, n_clip, sa, sp, dirc, std, rate, r, 1.0 / 1000.0, e, None, _lib.stream())
+    else:
+        _lib.call("dm_sched_diffmusic_update", d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
+                  prev.data_ptr(), B, n_clip, sa, sp, dirc, std, rate, 1.0 / 1000.0, e, 0.9995, None, _lib.stream())
+    assert rel_l2(prev, want) < 2e-6
+    for b in range(B):
+        assert rel_l2(prev[b], want[b]) < 2e-6
+
+
+def test_slerp_linear_branch_on_device():
+    """|cos| > 0.9995 (z and -g nearly parallel): the kernel takes the linear-interpolation branch per clip."""
+    from diffmusic_b200 import _lib
+    n = 3200
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(2, n, generator=g)
+    g0 = torch.stack([-z[0] * 5.0 + 1e-4 * torch.randn(n, generator=g), torch.randn(n, generator=g)])  # clip 0 parallel
+    x0, ep = torch.randn(2, n, generator=g), torch.randn(2, n, generator=g)
+    sa, sp, dirc, std, rate, e = 0.9, 0.8, 0.5, 0.3, 0.08, 1e-8
+    want = []
+    for b in range(2):
+        gb = g0[b] * 1e-3 / sa
+        gt = gb / (torch.linalg.norm(gb) + e) * torch.linalg.norm(z[b])
+        want.append(sp * x0[b] + dirc * ep[b] + std * osteps.slerp(z[b], -gt, rate))
+    d = [t.to(DEV).contiguous() for t in (x0, ep, g0, z)]
+    prev = torch.empty_like(d[0])
+    _lib.call("dm_sched_diffmusic_update", d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
+              prev.data_ptr(), 2, n, sa, sp, dirc, std, rate, 1e-3, e, 0.9995, None, _lib.stream())
+    assert rel_l2(prev, torch.stack(want)) < 2e-6
