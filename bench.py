@@ -44,6 +44,11 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+# `ncu --set full` captures (profiles/README.md); null where no capture of that workload exists.
+NCU_TRAFFIC_BYTES = {"cfg2": 10.51e6}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -307,7 +312,9 @@ def main():
         dom = statistics.mean(dom_ms) if dom_ms else None
         achieved = bytes_launch / (dom * 1e-3) / 1e9 if dom else None
         roofline = {"bound": "hbm", "kernel": "stft_guidance_kernel", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                    "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                    "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if dom else None,
+                    "traffic_source": "profiles/r01/stft_guidance_full_raw.csv (ncu --set full, per launch)",
                     "bytes_per_launch": bytes_launch, "ms_per_launch": dom, "launches_timed": len(dom_ms),
                     "peak_source": peak_src,
                     "note": "compute/shared-memory bound FFT kernel: algorithmic HBM bytes are the floor, see DESIGN.md"}

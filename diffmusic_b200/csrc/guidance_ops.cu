@@ -258,7 +258,7 @@ extern "C" int dm_fold_adjoint(const float* ybar, int pad, long long Ly, int B, 
                                dm_stream_t stream) {
     DM_REQUIRE(partial && Ly > 0 && B > 0 && ntiles > 0);
     DM_REQUIRE((dwav == nullptr && loss != nullptr) || ybar != nullptr);
-    DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 513));
+    DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 512));
     const int nblk = dwav ? (int)((Ly + kEwThreads * 8 - 1) / (kEwThreads * 8)) : 1;
     fold_adjoint_kernel<<<dim3(nblk, B), kEwThreads, 0, as_stream(stream)>>>(ybar, pad, Ly, mask, partial, ntiles,
                                                                              dwav, dwav_bstride, loss);
@@ -299,7 +299,7 @@ extern "C" int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int
                                    const float* kernel, int n_new, int taps, int orig, int width, float* dwav,
                                    long long dwav_bstride, long long L, float* loss, dm_stream_t stream) {
     DM_REQUIRE(ybar && partial && kernel && dwav && L > 0 && B > 0 && Ly > 0 && ntiles > 0);
-    DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 513));
+    DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 512));
     if (n_new == 1 && taps >= orig) {  // integer decimation: polyphase kernel
         const int unit = orig * kFirR;
         const int chunk = unit * ((kRsChunk + unit - 1) / unit);

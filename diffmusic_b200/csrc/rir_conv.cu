@@ -141,7 +141,7 @@ extern "C" int dm_rir_adjoint(const float* ybar, int pad, long long Ly, int B, c
     DM_REQUIRE(K >= 1 && K <= DM_RIR_MAX_TAPS);
     RirGeom g = rir_geom(L, K);
     DM_REQUIRE(Ly == g.nout);
-    DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 513));
+    DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 512));
     const int nblk = (int)((L + g.valid - 1) / g.valid);
     DM_SMEM_ONCE(rir_adjoint_kernel, kRirSmemBytes);
     rir_adjoint_kernel<<<dim3(nblk, B), kRirThreads, kRirSmemBytes, as_stream(stream)>>>(

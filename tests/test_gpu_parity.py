@@ -449,3 +449,58 @@ def test_slerp_linear_branch_on_device():
     _lib.call("dm_sched_diffmusic_update", d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
               prev.data_ptr(), 2, n, sa, sp, dirc, std, rate, 1e-3, e, 0.9995, None, _lib.stream())
     assert rel_l2(prev, torch.stack(want)) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("L", [513, 1000, 1023, 16001, 40000])
+def test_ragged_lengths_against_oracle(L):
+    """shortest legal clip (reflect padding needs L > 512), fewer frames than one tile, L not a multiple of the hop."""
+    wav = stubs.synth_clips(2, L).to(DEV)
+    ref = stubs.synth_clips(1, L, first=50)
+    op, oop = dm.IdentityOperator(16000), oo.OracleOperator("identity")
+    assert rel_l2(op.transform(wav), oop.transform(wav.cpu())) < TOL
+    loss, g = _loss_grad(op, wav, ref.to(DEV), "mel_spectrogram")
+    for i in range(2):
+        w = wav[i:i + 1].cpu().clone().requires_grad_(True)
+        want = torch.linalg.norm(oop.transform(ref) - oop.transform(w))
+        (gw,) = torch.autograd.grad(want, w)
+        assert abs(float(loss[i]) - float(want)) < TOL * float(want)
+        assert rel_l2(g[i:i + 1], gw) < TOL
+    sr, osr = dm.SuperResolutionOperator(16000, 2, _noiser()), oo.OracleOperator("super_resolution", scale=2)
+    assert rel_l2(sr.forward(wav), osr.forward(wav.cpu())) < TOL
+    if L >= 1000:
+        dv = dm.MusicDereverberationOperator(800, 0.85, _noiser())
+        torch.manual_seed(L)
+        y = dv.forward(wav)
+        assert rel_l2(y, oo.a_dereverb(wav.cpu(), dv.last_ir)) < TOL
+
+
+def test_shape_errors_are_python_exceptions():
+    inp = _inpaint()
+    with pytest.raises(ValueError):
+        inp.forward(torch.zeros(1, 12345, device=DEV))          # mask / data length mismatch
+    op = dm.IdentityOperator(16000)
+    with pytest.raises(ValueError):
+        op.guidance_loss(torch.zeros(1, 16000, device=DEV), torch.zeros(1, 8000, device=DEV), "mel_spectrogram")
+    with pytest.raises(ValueError):
+        op.guidance_loss(torch.zeros(1, 16000, device=DEV), torch.zeros(1, 16000, device=DEV), "nope")
+    with pytest.raises(Exception):
+        op.transform(torch.zeros(1, 300, device=DEV))             # shorter than the reflect padding
+    with pytest.raises(NotImplementedError):
+        dm.PhaseRetrievalOperator(n_fft=2048, hop_length=512, win_length=2048)
+    with pytest.raises(NotImplementedError):
+        dm.MusicDereverberationOperator(ir_length=9000)
+
+
+def test_large_batch_matches_small_batches():
+    """B = 48 in one launch == the same clips in batches of 1 (no cross-clip coupling anywhere)."""
+    L, B = 16000, 48
+    wav = stubs.synth_clips(B, L).to(DEV)
+    meas = stubs.synth_clips(1, L, first=50).to(DEV)
+    op = dm.SuperResolutionOperator(16000, 2, _noiser())
+    m = op.forward(meas)
+    loss, g = _loss_grad(op, wav, m, "mel_spectrogram")
+    for i in (0, 17, 47):
+        li, gi = _loss_grad(op, wav[i:i + 1], m, "mel_spectrogram")
+        # tile boundaries (hence the fp32 summation grouping) depend on the launch shape: equal to rounding, not bitwise
+        assert rel_l2(li, loss[i:i + 1]) < 1e-6 and rel_l2(gi, g[i:i + 1]) < 1e-5
