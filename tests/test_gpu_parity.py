@@ -504,3 +504,94 @@ def test_large_batch_matches_small_batches():
         li, gi = _loss_grad(op, wav[i:i + 1], m, "mel_spectrogram")
         # tile boundaries (hence the fp32 summation grouping) depend on the launch shape: equal to rounding, not bitwise
         assert rel_l2(li, loss[i:i + 1]) < 1e-6 and rel_l2(gi, g[i:i + 1]) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ remaining section-8 rows
+def test_generic_ratio_resample_kernels():
+    """non-integer ratio (24 kHz -> 16 kHz: orig 3, new 2) goes through the generic FIR kernels (a3)."""
+    import torchaudio
+    from diffmusic_b200 import _lib, tables
+    kern, width, orig, new = tables.sinc_resample_kernel(24000, 16000)
+    assert (orig, new) == (3, 2)
+    L, B = 7001, 2
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, L, generator=g)
+    rs = torchaudio.transforms.Resample(24000, 16000)
+    xx = x.clone().requires_grad_(True)
+    y = rs(xx)
+    Ly = y.shape[1]
+    xd, kd = x.to(DEV).contiguous(), kern.to(DEV).contiguous()
+    yd = torch.empty(B, Ly, device=DEV)
+    _lib.call("dm_resample_fwd", xd.data_ptr(), xd.stride(0), L, B, kd.data_ptr(), kd.shape[0], kd.shape[1], orig,
+              width, yd.data_ptr(), Ly, _lib.stream())
+    assert rel_l2(yd, y.detach()) < 1e-5
+    yb = torch.randn(B, Ly, generator=g)
+    (gx,) = torch.autograd.grad((y * yb).sum(), xx)
+    ybd = yb.to(DEV).contiguous()
+    partial = torch.ones(B, 1, device=DEV)          # loss = 1 -> scale 1
+    dwav, loss = torch.empty(B, L, device=DEV), torch.empty(B, device=DEV)
+    _lib.call("dm_resample_adjoint", ybd.data_ptr(), 0, Ly, B, partial.data_ptr(), 1, kd.data_ptr(), kd.shape[0],
+              kd.shape[1], orig, width, dwav.data_ptr(), dwav.stride(0), L, loss.data_ptr(), _lib.stream())
+    assert rel_l2(dwav, gx) < 1e-5 and torch.allclose(loss.cpu(), torch.ones(B))
+
+
+def test_style_guidance_mpgd_generic_path():
+    """BASELINE config 5: StyleGuidanceOperator (forward = identity, transform = user torch callable) + MPGD: the
+    residual comes from torch (no fused kernel), x0 and the MPGD update from the CUDA kernels."""
+    class FakeClap:
+        def get_gram_matrix(self, audio):           # (B, L) -> (B, 64, 64) gram of 64 strided feature maps
+            f = audio.reshape(audio.shape[0], 64, -1)
+            return f @ f.transpose(1, 2) / f.shape[-1]
+
+    B = 2
+    vae, voc = stubs.StubVAE(), stubs.StubVocoder()
+    x, e = stubs.synth_latents(B, 25)
+    ref = stubs.synth_clips(B, L1, first=50)
+    op = dm.StyleGuidanceOperator(FakeClap())
+    meas = op.forward(ref)
+
+    class OracleStyle:
+        forward = staticmethod(lambda d, **k: d)
+        transform = staticmethod(lambda a: FakeClap().get_gram_matrix(a.float()))
+        inverse_transform = staticmethod(lambda m, v: v(m.squeeze(1) if m.dim() == 4 else m))
+
+    base = osteps.make_base(**stubs.MUSICLDM_SCHED)
+    base.set_timesteps(500)
+    want = osteps.per_clip_step("mpgd", base, OracleStyle, e, 501, x, measurement=meas, eta=0.0,
+                                ip_guidance_rate=0.005, vae=vae, vocoder=voc, original_waveform_length=L1,
+                                supervised_space="mel_spectrogram")
+    sched = dm.MPGDScheduler(operator=op, **stubs.MUSICLDM_SCHED)
+    sched.set_timesteps(500)
+    got = sched.step(e.to(DEV), 501, x.to(DEV), eta=0.0, measurement=meas.to(DEV), vae=vae.to(DEV),
+                     vocoder=voc.to(DEV), original_waveform_length=L1, ip_guidance_rate=0.005)
+    assert rel_l2(got.prev_sample, want.prev_sample) < TOL
+    assert rel_l2(got.pred_original_sample, want.pred_original_sample) < TOL
+    assert rel_l2(got.loss_per_clip, want.loss) < TOL
+
+
+def test_noisy_operator_inside_guidance():
+    """GaussianNoise with sigma > 0 attached to an operator (noise.py:13-18): the noise is drawn by torch on the
+    tensor's device exactly where the reference draws it, and added by dm_add_scaled; the VJP is unaffected."""
+    sigma = 0.05
+    wav = stubs.synth_clips(1, L1).to(DEV)
+    ref = stubs.synth_clips(1, L1, first=50).to(DEV)
+    op = dm.SuperResolutionOperator(16000, 2, dm.get_noiser("gaussian", sigma))
+    clean = dm.SuperResolutionOperator(16000, 2, _noiser())
+    torch.manual_seed(11)
+    y = op.forward(wav)
+    torch.manual_seed(11)
+    n = torch.randn_like(clean.forward(wav))
+    assert rel_l2(y, clean.forward(wav) + sigma * n) < 1e-6
+    meas = clean.forward(ref)
+    torch.manual_seed(12)
+    loss, g = _loss_grad(op, wav, meas, "mel_spectrogram")
+    # same draw, evaluated by the CPU oracle on the noisy prediction
+    torch.manual_seed(12)
+    n = torch.randn_like(meas)
+    w = wav.cpu().clone().requires_grad_(True)
+    oop = oo.OracleOperator("super_resolution", scale=2)
+    pred = oop.forward(w) + sigma * n.cpu()
+    want = torch.linalg.norm(oop.transform(meas.cpu()) - oop.transform(pred))
+    (gw,) = torch.autograd.grad(want, w)
+    assert abs(float(loss) - float(want)) < TOL * float(want)
+    assert rel_l2(g, gw) < TOL
