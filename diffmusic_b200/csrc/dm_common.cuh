@@ -51,6 +51,17 @@ inline int fail(int code, const char* fmt, A... a) {
         }                                                                                                  \
     } while (0)
 
+// ask for the largest shared-memory carve-out once (kernels that want 3 x ~74 KB CTAs resident per SM)
+#define DM_CARVEOUT_ONCE(kernel)                                                                           \
+    do {                                                                                                   \
+        static bool done__ = false;                                                                        \
+        if (!done__) {                                                                                     \
+            DM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,           \
+                                         cudaSharedmemCarveoutMaxShared));                                 \
+            done__ = true;                                                                                 \
+        }                                                                                                  \
+    } while (0)
+
 inline cudaStream_t as_stream(dm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline int num_sms() {

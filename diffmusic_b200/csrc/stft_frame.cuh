@@ -41,19 +41,30 @@ struct StftTables {
     const float* bin_w1;     // [513]  fb[k, m0+1] (0 if none)
 };
 
-// Shared-memory working set of one frame group (all float).
+// Shared-memory working set of one frame group (all float): two swizzled complex buffers and the mel cotangent.
+// The spectrum and the per-bin energy do not get arrays of their own, they live in the FFT buffers while those are dead:
+//   X[k], k = 0..511 (forward spectrum, kept for the VJP) in b_re/b_im at the swizzled slot of k, with the two real
+//        bins packed into slot 0 = (Re X[0], Re X[512]);
+//   P[k] (|X|^2 or |X|; later the magnitude cotangent in phase_wav mode) in a_re at the swizzled slot of k, P[512] in aux.
+// Both are written by the thread that has just read the same slots (unpack / pack work on the pair k, 512-k in place),
+// so no other thread's data is clobbered.  8.8 KB per group instead of 15 KB -> 3 CTAs per SM.
 struct FrameSmem {
-    float* a_re;  // [padded_len(512)]
+    float* a_re;    // [512]
     float* a_im;
     float* b_re;
     float* b_im;
-    float* x_re;  // [520] spectrum X[0..512]
-    float* x_im;
-    float* p;     // [520] |X|^2 or |X|, later reused for magbar in phase_wav mode
-    float* mel;   // [64]
     float* melbar;  // [72] (index 64 must read as 0)
+    float* aux;     // [8]  aux[0] = P[512]
 };
-constexpr int kFrameSmemFloats = 4 * padded_len(kH) + 3 * 520 + 64 + 72;
+constexpr int kFrameSmemFloats = 4 * padded_len(kH) + 72 + 8;
+
+DM_HD float& p_at(const FrameSmem& s, int k) { return k == kH ? s.aux[0] : s.a_re[padi(k)]; }
+DM_HD cf x_at(const FrameSmem& s, int k) {
+    if (k == 0) return cf{s.b_re[padi(0)], 0.f};
+    if (k == kH) return cf{s.b_im[padi(0)], 0.f};
+    const int a = padi(k);
+    return cf{s.b_re[a], s.b_im[a]};
+}
 
 // Per-thread constants of the frame pipeline (thread gt of a 64-thread group always owns the same twiddles and the
 // same mel band), loaded once per CTA.
@@ -94,30 +105,37 @@ DM_HD void fwd_pass3(int tid, const ThreadConsts& c, FrameSmem s) {
     stockham_pass_pad<kH, 64, -1>(tid, c.w64, s.b_re, s.b_im, s.a_re, s.a_im);
 }
 
-// ---- unpack Z (in a_re/a_im, natural order) to the real-FFT spectrum X and the per-bin energy ----
+// ---- unpack Z (in a_re/a_im, natural order) to the real-FFT spectrum X (-> b) and the per-bin energy (-> a_re) ----
 template <int MODE>
 DM_HD void fwd_unpack(int tid, const cf* w1024, FrameSmem s) {
     PadLoad Z{s.a_re, s.a_im};
-    auto put = [&](int k, cf x) {
-        s.x_re[k] = x.x;
-        s.x_im[k] = x.y;
+    auto energy = [](cf x) {
         float e = x.x * x.x + x.y * x.y;
-        s.p[k] = (MODE == kModeMelDb) ? e : sqrtf(e);
+        return (MODE == kModeMelDb) ? e : sqrtf(e);
     };
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int k = tid + 64 * i;  // 0..255
         if (k == 0) {
-            cf z0 = Z(0);
-            put(0, cf{z0.x + z0.y, 0.f});
-            put(kH, cf{z0.x - z0.y, 0.f});
-            cf zq = Z(kH / 2);
-            put(kH / 2, cconj(zq));
+            const cf z0 = Z(0), zq = Z(kH / 2);
+            const cf x0 = cf{z0.x + z0.y, 0.f}, xh = cf{z0.x - z0.y, 0.f}, xq = cconj(zq);
+            s.b_re[padi(0)] = x0.x;  // slot 0 packs the two real bins
+            s.b_im[padi(0)] = xh.x;
+            s.b_re[padi(kH / 2)] = xq.x;
+            s.b_im[padi(kH / 2)] = xq.y;
+            s.a_re[padi(0)] = energy(x0);
+            s.aux[0] = energy(xh);
+            s.a_re[padi(kH / 2)] = energy(xq);
         } else {
+            const int ak = padi(k), ac = padi(kH - k);
             cf xk, xc;
-            rfft_unpack_pair(Z(k), Z(kH - k), w1024[k], xk, xc);
-            put(k, xk);
-            put(kH - k, xc);
+            rfft_unpack_pair(cf{s.a_re[ak], s.a_im[ak]}, cf{s.a_re[ac], s.a_im[ac]}, w1024[k], xk, xc);
+            s.b_re[ak] = xk.x;
+            s.b_im[ak] = xk.y;
+            s.b_re[ac] = xc.x;
+            s.b_im[ac] = xc.y;
+            s.a_re[ak] = energy(xk);
+            s.a_re[ac] = energy(xc);
         }
     }
 }
@@ -131,7 +149,7 @@ DM_HD float mel_residual(int m, const ThreadConsts& c, const float* melw_t, Fram
     const int k0 = c.mel_k0, n = c.mel_n;
     float acc = 0.f;
 #pragma unroll 4
-    for (int i = 0; i < n; ++i) acc = fmaf(melw_t[i * kMels + m], s.p[k0 + i], acc);
+    for (int i = 0; i < n; ++i) acc = fmaf(melw_t[i * kMels + m], s.a_re[padi(k0 + i)], acc);  // bin 512 has no weight
     float val, dval_dmel;  // transformed value and its derivative w.r.t. the mel energy
     if (MODE == kModeMelDb) {
         float c = acc < 1e-10f ? 1e-10f : acc;  // torch.clamp(min=amin): NaN stays NaN
@@ -151,7 +169,6 @@ DM_HD float mel_residual(int m, const ThreadConsts& c, const float* melw_t, Fram
         }
     }
     *out_val = val;
-    s.mel[m] = acc;
     float d = 0.f;
     if (has_ref) {
         d = ref_val - val;
@@ -161,13 +178,14 @@ DM_HD float mel_residual(int m, const ThreadConsts& c, const float* melw_t, Fram
 }
 
 // ---- backward: spectrum cotangent -> Hermitian-packed Z for the inverse FFT (written to b_re/b_im) ----
-// For MODE == kModePhaseWav, s.p[] must already hold magbar[k] = -(ref - |X|) (written by the caller).
+// For MODE == kModePhaseWav, P[] must already hold magbar[k] = -(ref - |X|) (written by the caller through p_at).
+// In place: a thread reads X at the slots of its pair (k, 512-k) from b and writes the packed Z to the same slots.
 template <int MODE>
 DM_HD cf xbar_of_bin(int k, const StftTables& t, const FrameSmem& s) {
-    cf x = cf{s.x_re[k], s.x_im[k]};
+    const cf x = x_at(s, k);
     float g;
     if (MODE == kModePhaseWav) {
-        g = s.p[k];
+        g = p_at(s, k);
     } else {
         int m0 = t.bin_m0[k];
         g = t.bin_w0[k] * s.melbar[m0] + t.bin_w1[k] * s.melbar[m0 + 1];

@@ -36,7 +36,7 @@ struct StftParams {
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kGroupThreads)); }
 
 template <int MODE>
-__global__ void __launch_bounds__(kCtaThreads) stft_guidance_kernel(const StftParams p) {
+__global__ void __launch_bounds__(kCtaThreads, 3) stft_guidance_kernel(const StftParams p) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, g = tid / kGroupThreads, gt = tid % kGroupThreads;
     const int b = blockIdx.y, tile = blockIdx.x;
@@ -63,11 +63,8 @@ __global__ void __launch_bounds__(kCtaThreads) stft_guidance_kernel(const StftPa
         s.a_im = q; q += padded_len(kH);
         s.b_re = q; q += padded_len(kH);
         s.b_im = q; q += padded_len(kH);
-        s.x_re = q; q += 520;
-        s.x_im = q; q += 520;
-        s.p = q; q += 520;
-        s.mel = q; q += 64;
-        s.melbar = q;
+        s.melbar = q; q += 72;
+        s.aux = q;
     }
     StftTables tab = p.tab;
     tab.window = win;
@@ -120,18 +117,18 @@ __global__ void __launch_bounds__(kCtaThreads) stft_guidance_kernel(const StftPa
             if (MODE != kModeMelDb && p.noise != nullptr) {  // GaussianNoise on the magnitude (operator.py:171)
                 const long long t = f0 + f;
                 for (int k = gt; k < kBins; k += kGroupThreads)
-                    s.p[k] += p.sigma * __ldg(p.noise + ((long long)b * kBins + k) * p.T + t);
+                    p_at(s, k) += p.sigma * __ldg(p.noise + ((long long)b * kBins + k) * p.T + t);
                 group_sync(g);
             }
             if (MODE == kModePhaseWav) {
                 const long long t = f0 + f;
                 for (int k = gt; k < kBins; k += kGroupThreads) {
-                    float mag = s.p[k];
+                    float mag = p_at(s, k);
                     if (p.out) p.out[((long long)b * kBins + k) * p.T + t] = mag;
                     if (has_ref) {
                         float d = __ldg(p.ref + (long long)b * p.ref_bstride + (long long)k * p.T + t) - mag;
                         lsum = fmaf(d, d, lsum);
-                        s.p[k] = -d;
+                        p_at(s, k) = -d;
                     }
                 }
             } else {
@@ -281,6 +278,7 @@ extern "C" int dm_stft_guidance(const dm_stft_tables* tab, int mode, int clamp, 
 #define DM_LAUNCH_STFT(M)                                          \
     do {                                                           \
         DM_SMEM_ONCE(stft_guidance_kernel<M>, smem);               \
+        DM_CARVEOUT_ONCE(stft_guidance_kernel<M>);                 \
         stft_guidance_kernel<M><<<grid, block, smem, st>>>(p);     \
     } while (0)
     if (mode == DM_STFT_MEL_DB) DM_LAUNCH_STFT(kModeMelDb);

@@ -64,11 +64,12 @@ class _DeviceTables:
 
 
 def _frames_per_tile(B, T, device):
-    """frames per CTA tile.  The kernel keeps 2 CTAs resident per SM up to 17 frames per tile (shared memory); among
-    8..17 pick the size whose CTA count fills whole waves of 2 x SMs best (tail effect), larger tiles on ties."""
-    slots = 2 * torch.cuda.get_device_properties(device).multi_processor_count
-    best, best_eff = 8, -1.0
-    for nf in range(8, 18):
+    """frames per CTA tile.  Up to 10 frames per tile the kernel's shared memory (~73 KB) lets 3 CTAs stay resident per
+    SM; among 6..10 pick the size whose CTA count fills whole waves of 3 x SMs best (tail effect), larger tiles on
+    ties (fewer re-staged samples).  6 is the minimum for the bit-reproducible two-tile overlap."""
+    slots = 3 * torch.cuda.get_device_properties(device).multi_processor_count
+    best, best_eff = 6, -1.0
+    for nf in range(6, 11):
         ctas = B * math.ceil(T / nf)
         eff = ctas / (math.ceil(ctas / slots) * slots)
         if eff >= best_eff - 1e-9:

@@ -21,7 +21,7 @@ import torchaudio
 N_FFT = 1024
 N_BINS = 513
 N_MELS = 64
-MEL_WSTRIDE = 48
+MEL_WSTRIDE = 42  # longest band of the 64-band HTK filterbank spans 41 bins
 
 
 def hann_window():

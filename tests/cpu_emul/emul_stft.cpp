@@ -54,7 +54,7 @@ static void run(const EmulTables& e, int clamp, const float* y, long long Ly, in
     FrameSmem s;
     s.a_re = p; p += padded_len(kH); s.a_im = p; p += padded_len(kH);
     s.b_re = p; p += padded_len(kH); s.b_im = p; p += padded_len(kH);
-    s.x_re = p; p += 520; s.x_im = p; p += 520; s.p = p; p += 520; s.mel = p; p += 64; s.melbar = p;
+    s.melbar = p; p += 72; s.aux = p;
     if (ypbar) std::memset(ypbar, 0, sizeof(float) * (Ly + 1024));
     std::vector<ThreadConsts> tc(64);
     for (int tid = 0; tid < 64; ++tid) load_thread_consts(tid, t, tc[tid]);
@@ -73,9 +73,9 @@ static void run(const EmulTables& e, int clamp, const float* y, long long Ly, in
         for (int tid = 0; tid < 64; ++tid) fwd_unpack<MODE>(tid, t.w1024, s);
         if (MODE == kModePhaseWav) {
             for (int k = 0; k < kBins; ++k) {
-                float mag = s.p[k];
+                float mag = p_at(s, k);
                 if (out) out[k * T + f] = mag;
-                if (ref) { float d = ref[k * T + f] - mag; acc += (double)d * d; s.p[k] = -d; }
+                if (ref) { float d = ref[k * T + f] - mag; acc += (double)d * d; p_at(s, k) = -d; }
             }
         } else {
             for (int m = 0; m < 64; ++m) {
