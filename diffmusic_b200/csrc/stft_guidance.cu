@@ -137,7 +137,9 @@ __global__ void __launch_bounds__(kCtaThreads, 3) stft_guidance_kernel(const Stf
                                            has_ref ? tilebuf[f * kTileLd + gt] : 0.f, &v);
                 if (p.out) tilebuf[f * kTileLd + gt] = v;
             }
-            if (want_grad) {
+            if (!want_grad) {
+                group_sync(g);  // P lives in a_re: everyone must be done reading it before the next frame's pass 1
+            } else {
                 group_sync(g);
                 bwd_pack<MODE>(gt, tab, s);
                 group_sync(g);
