@@ -120,24 +120,77 @@ DM_HD void stockham_pass_rt(int j, const cf (&w)[7], Load load, Store store) {
 }
 
 // Swizzled split-array I/O of one radix-8 butterfly: inputs j + r*T, outputs j0 + q*NS.
+// The swizzled addresses have closed forms with ONE variable term per thread and compile-time constants per r / q,
+// because the index pieces occupy disjoint bit fields (so + is ^ and the mask (i >> 3) & 31 splits the same way):
+//   loads   j + r*T        T = 64 : (padi(j) ^ ((r & 3) << 3)) + 64 r          T = 512 : padi(j) + 512 r
+//   NS = 1  8 j + q               : ((8 j) ^ (j & 31)) ^ q
+//   NS = 8  64 a + k + 8 q        : (64 a ^ k ^ ((a & 3) << 3)) ^ (9 q)          a = j >> 3, k = j & 7
+//   NS = 64 512 c + l + 64 q      : (((512 c + l) ^ (l >> 3)) ^ ((q & 3) << 3)) + 64 q     c = j >> 6, l = j & 63
+//   NS = 512 j + 512 q            : padi(j) + 512 q
+// (checked against padi() itself for every j, r, q in tests/cpu_emul; one LOP3/IADD per access instead of five.)
+template <int N>
+DM_HD int ld_addr(int b0, int r) {
+    static_assert(N == 512 || N == 4096, "closed forms derived for N = 512 and N = 4096");
+    return N == 512 ? ((b0 ^ ((r & 3) << 3)) + 64 * r) : (b0 + 512 * r);
+}
 template <int N>
 DM_HD void load8_pad(const float* __restrict__ re, const float* __restrict__ im, int j, cf (&v)[8]) {
-    constexpr int T = N / 8;
+    const int b0 = padi(j);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        const int a = padi(j + r * T);
+        const int a = ld_addr<N>(b0, r);
         v[r] = cf{re[a], im[a]};
     }
 }
-template <int NS>
+template <int N, int NS>
+DM_HD int st_base(int j) {
+    if (NS == 1) return (8 * j) ^ (j & 31);
+    if (NS == 8) return (64 * (j >> 3)) ^ (j & 7) ^ (((j >> 3) & 3) << 3);
+    if (NS == 64) return ((512 * (j >> 6) + (j & 63)) ^ ((j & 63) >> 3));
+    return padi(j);  // NS == 512
+}
+template <int N, int NS>
+DM_HD int st_addr(int b, int q) {
+    static_assert(NS == 1 || NS == 8 || NS == 64 || (NS == 512 && N == 4096), "unsupported pass");
+    if (NS == 1) return b ^ q;
+    if (NS == 8) return b ^ (9 * q);
+    if (NS == 64) return (b ^ ((q & 3) << 3)) + 64 * q;
+    return b + 512 * q;
+}
+template <int N, int NS>
 DM_HD void store8_pad(float* __restrict__ re, float* __restrict__ im, int j, const cf (&v)[8]) {
-    const int j0 = (j / NS) * NS * 8 + j % NS;
+    const int b = st_base<N, NS>(j);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const int a = padi(j0 + q * NS);
+        const int a = st_addr<N, NS>(b, q);
         re[a] = v[q].x;
         im[a] = v[q].y;
     }
+}
+// seven twiddles of thread j generated from the first by complex multiplication (see stockham_pass_rec)
+template <int N, int NS, int SIGN>
+DM_HD void twiddle8_rec(int j, const cf* __restrict__ tw, cf (&v)[8]) {
+    constexpr int TWS = N / (NS * 8);
+    cf w1 = tw[(j % NS) * TWS];
+    if (SIGN > 0) w1.y = -w1.y;
+    const cf w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+    v[1] = cmul(v[1], w1);
+    v[2] = cmul(v[2], w2);
+    v[3] = cmul(v[3], w3);
+    v[4] = cmul(v[4], w4);
+    v[5] = cmul(v[5], cmul(w4, w1));
+    v[6] = cmul(v[6], cmul(w3, w3));
+    v[7] = cmul(v[7], cmul(w4, w3));
+}
+// smem -> smem pass with recurrence twiddles (the 4096-point transform)
+template <int N, int NS, int SIGN>
+DM_HD void stockham_pass_rec_pad(int j, const cf* __restrict__ tw, const float* in_re, const float* in_im,
+                                 float* out_re, float* out_im) {
+    cf v[8];
+    load8_pad<N>(in_re, in_im, j, v);
+    twiddle8_rec<N, NS, SIGN>(j, tw, v);
+    dft8<SIGN>(v);
+    store8_pad<N, NS>(out_re, out_im, j, v);
 }
 template <int SIGN>
 DM_HD void twiddle8(cf (&v)[8], const cf (&w)[7]) {
@@ -156,7 +209,7 @@ DM_HD void stockham_pass_pad(int j, const cf (&w)[7], const float* in_re, const 
     load8_pad<N>(in_re, in_im, j, v);
     twiddle8<SIGN>(v, w);
     dft8<SIGN>(v);
-    store8_pad<NS>(out_re, out_im, j, v);
+    store8_pad<N, NS>(out_re, out_im, j, v);
 }
 
 // Pass whose seven twiddles are generated from the first one by complex multiplication (w^2 = w*w, w^3 = w^2*w,

@@ -105,13 +105,13 @@ DM_HD void rir_block_phase(int ph, int tid, const cf* tw, const cf* w8192, const
     PadStore sa{s.a_re, s.a_im}, sb{s.b_re, s.b_im};
     switch (ph) {
         case 0: stockham_pass<kRirH, 1, -1>(tid, tw, RirLoad<Src>{src}, sa); break;
-        case 1: stockham_pass_rec<kRirH, 8, -1>(tid, tw, la, sb); break;
-        case 2: stockham_pass_rec<kRirH, 64, -1>(tid, tw, lb, sa); break;
-        case 3: stockham_pass_rec<kRirH, 512, -1>(tid, tw, la, sb); break;
+        case 1: stockham_pass_rec_pad<kRirH, 8, -1>(tid, tw, s.a_re, s.a_im, s.b_re, s.b_im); break;
+        case 2: stockham_pass_rec_pad<kRirH, 64, -1>(tid, tw, s.b_re, s.b_im, s.a_re, s.a_im); break;
+        case 3: stockham_pass_rec_pad<kRirH, 512, -1>(tid, tw, s.a_re, s.a_im, s.b_re, s.b_im); break;
         case 4: rir_pointwise<CONJ>(tid, lb, sa, spec, w8192); break;
         case 5: stockham_pass<kRirH, 1, +1>(tid, tw, la, sb); break;
-        case 6: stockham_pass_rec<kRirH, 8, +1>(tid, tw, lb, sa); break;
-        case 7: stockham_pass_rec<kRirH, 64, +1>(tid, tw, la, sb); break;
+        case 6: stockham_pass_rec_pad<kRirH, 8, +1>(tid, tw, s.b_re, s.b_im, s.a_re, s.a_im); break;
+        case 7: stockham_pass_rec_pad<kRirH, 64, +1>(tid, tw, s.a_re, s.a_im, s.b_re, s.b_im); break;
         default: stockham_pass_rec<kRirH, 512, +1>(tid, tw, lb, st); break;
     }
 }

@@ -34,7 +34,7 @@ struct StftTables {
     const cf* w1024;         // [257]  exp(-2 pi i k / 1024)
     const int* mel_kstart;   // [64]   first bin with non-zero weight
     const int* mel_klen;     // [64]   number of consecutive non-zero bins
-    const float* mel_w;      // [64 * mel_wstride] banded filterbank weights fb[kstart+i, m]
+    const float* mel_w;      // [mel_wstride][64] banded filterbank, transposed: mel_w[i * 64 + m] = fb[kstart[m] + i, m]
     int mel_wstride;
     const int* bin_m0;       // [513]  first mel band touching bin k
     const float* bin_w0;     // [513]  fb[k, m0]
@@ -96,7 +96,7 @@ DM_HD void fwd_pass1(int tid, const float* frame, const float* window, FrameSmem
 #pragma unroll
     for (int r = 0; r < 8; ++r) v[r] = load(tid + r * (kH / 8));
     dft8<-1>(v);
-    store8_pad<1>(s.a_re, s.a_im, tid, v);
+    store8_pad<kH, 1>(s.a_re, s.a_im, tid, v);
 }
 DM_HD void fwd_pass2(int tid, const ThreadConsts& c, FrameSmem s) {
     stockham_pass_pad<kH, 8, -1>(tid, c.w8, s.a_re, s.a_im, s.b_re, s.b_im);
@@ -229,7 +229,7 @@ DM_HD void inv_pass1(int tid, FrameSmem s) {
     cf v[8];
     load8_pad<kH>(s.b_re, s.b_im, tid, v);
     dft8<+1>(v);
-    store8_pad<1>(s.a_re, s.a_im, tid, v);
+    store8_pad<kH, 1>(s.a_re, s.a_im, tid, v);
 }
 DM_HD void inv_pass2(int tid, const ThreadConsts& c, FrameSmem s) {
     stockham_pass_pad<kH, 8, +1>(tid, c.w8, s.a_re, s.a_im, s.b_re, s.b_im);

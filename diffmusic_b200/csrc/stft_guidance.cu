@@ -83,10 +83,7 @@ __global__ void __launch_bounds__(kCtaThreads, 3) stft_guidance_kernel(const Stf
         acc[i] = 0.f;
     }
     for (int i = tid; i < kNfft; i += kCtaThreads) win[i] = __ldg(p.tab.window + i);
-    for (int i = tid; i < p.tab.mel_wstride * kMels; i += kCtaThreads) {
-        int m = i / p.tab.mel_wstride, j = i - m * p.tab.mel_wstride;
-        melw_t[j * kMels + m] = __ldg(p.tab.mel_w + i);
-    }
+    for (int i = tid; i < p.tab.mel_wstride * kMels; i += kCtaThreads) melw_t[i] = __ldg(p.tab.mel_w + i);
     for (int i = tid; i < 257; i += kCtaThreads) w1024[i] = p.tab.w1024[i];
     if (gt < 8) s.melbar[64 + gt] = 0.f;
     if (MODE != kModePhaseWav && has_ref) {
@@ -213,10 +210,9 @@ __global__ void __launch_bounds__(128) mel_project_kernel(const float* __restric
     const int m = blockIdx.y, b = blockIdx.z;
     if (t >= T) return;
     const int k0 = tab.mel_kstart[m], n = tab.mel_klen[m];
-    const float* w = tab.mel_w + m * tab.mel_wstride;
     const float* src = mag + ((long long)b * kBins + k0) * T + t;
     float acc = 0.f;
-    for (int i = 0; i < n; ++i) acc = fmaf(__ldg(w + i), src[(long long)i * T], acc);
+    for (int i = 0; i < n; ++i) acc = fmaf(__ldg(tab.mel_w + i * kMels + m), src[(long long)i * T], acc);
     if (clamp) acc = clamp_nan(acc, -80.f, 80.f);
     out[((long long)b * kMels + m) * T + t] = acc;
 }

@@ -56,7 +56,9 @@ def mel_tables(fb: torch.Tensor):
     """Sparse views of the triangular filterbank.
 
     Returns dict with
-      mel_kstart (64,) int32, mel_klen (64,) int32, mel_w (64, MEL_WSTRIDE) fp32   -- per band: consecutive bins
+      mel_kstart (64,) int32, mel_klen (64,) int32, mel_w (MEL_WSTRIDE, 64) fp32   -- per band: consecutive bins,
+                                                         stored TRANSPOSED (mel_w[i, m] = fb[kstart[m] + i, m]) so that
+                                                         the 64 band-threads of a frame group read consecutive words
       bin_m0 (513,) int32, bin_w0 (513,), bin_w1 (513,) fp32                       -- per bin: <= 2 adjacent bands
     """
     fb = fb.detach().cpu().to(torch.float32)
@@ -88,7 +90,8 @@ def mel_tables(fb: torch.Tensor):
         w0[k] = float(fb[k, ms[0]])
         if ms.size == 2:
             w1[k] = float(fb[k, ms[1]])
-    return dict(mel_kstart=torch.from_numpy(kstart), mel_klen=torch.from_numpy(klen), mel_w=torch.from_numpy(w),
+    return dict(mel_kstart=torch.from_numpy(kstart), mel_klen=torch.from_numpy(klen),
+                mel_w=torch.from_numpy(np.ascontiguousarray(w.T)),
                 bin_m0=torch.from_numpy(m0), bin_w0=torch.from_numpy(w0), bin_w1=torch.from_numpy(w1))
 
 

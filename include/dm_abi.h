@@ -84,7 +84,7 @@ typedef struct dm_stft_tables {
     const float* w1024;    /* [257][2] exp(-2 pi i k/1024) */
     const int* mel_kstart; /* [64] */
     const int* mel_klen;   /* [64] */
-    const float* mel_w;    /* [64][mel_wstride] banded filterbank */
+    const float* mel_w;    /* [mel_wstride][64] banded filterbank, transposed: mel_w[i*64+m] = fb[kstart[m]+i, m] */
     int mel_wstride;
     const int* bin_m0;     /* [513] */
     const float* bin_w0;   /* [513] */

@@ -58,9 +58,7 @@ static void run(const EmulTables& e, int clamp, const float* y, long long Ly, in
     if (ypbar) std::memset(ypbar, 0, sizeof(float) * (Ly + 1024));
     std::vector<ThreadConsts> tc(64);
     for (int tid = 0; tid < 64; ++tid) load_thread_consts(tid, t, tc[tid]);
-    std::vector<float> melw_t((size_t)e.mel_wstride * kMels);
-    for (int m = 0; m < kMels; ++m)
-        for (int i = 0; i < e.mel_wstride; ++i) melw_t[(size_t)i * kMels + m] = e.mel_w[m * e.mel_wstride + i];
+    std::vector<float> melw_t(e.mel_w, e.mel_w + (size_t)e.mel_wstride * kMels);  // already [i][64]
     double acc = 0.0;
     for (long long f = 0; f < T; ++f) {
         for (int n = 0; n < kNfft; ++n) {
@@ -219,4 +217,25 @@ void emul_resample_adjoint(const float* ybar, long long Ly, const float* kernel,
         for (int t = 0; t < ni; ++t) xbar[i0 + t] = outs[t];
     }
 }
+}
+
+// exhaustive check of the closed-form swizzled addresses (fft_core.cuh) against padi() of the logical index
+extern "C" int emul_check_swizzle_forms() {
+    int bad = 0;
+    for (int j = 0; j < 64; ++j)
+        for (int r = 0; r < 8; ++r) {
+            bad += ld_addr<512>(padi(j), r) != padi(j + 64 * r);
+            bad += st_addr<512, 1>(st_base<512, 1>(j), r) != padi(8 * j + r);
+            bad += st_addr<512, 8>(st_base<512, 8>(j), r) != padi((j / 8) * 64 + j % 8 + 8 * r);
+            bad += st_addr<512, 64>(st_base<512, 64>(j), r) != padi(j + 64 * r);
+        }
+    for (int j = 0; j < 512; ++j)
+        for (int r = 0; r < 8; ++r) {
+            bad += ld_addr<4096>(padi(j), r) != padi(j + 512 * r);
+            bad += st_addr<4096, 1>(st_base<4096, 1>(j), r) != padi(8 * j + r);
+            bad += st_addr<4096, 8>(st_base<4096, 8>(j), r) != padi((j / 8) * 64 + j % 8 + 8 * r);
+            bad += st_addr<4096, 64>(st_base<4096, 64>(j), r) != padi((j / 64) * 512 + j % 64 + 64 * r);
+            bad += st_addr<4096, 512>(st_base<4096, 512>(j), r) != padi(j + 512 * r);
+        }
+    return bad;
 }
