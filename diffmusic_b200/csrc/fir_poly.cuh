@@ -17,11 +17,37 @@ constexpr int kFirR = 4;  // outputs per thread
 DM_HD int fir_pad(int i) { return i + (i >> 5); }
 DM_HDC int fir_padded_len(int n) { return n + (n >> 5) + 1; }
 
+// ORIG / TAPS > 0 are compile-time specialisations (the reference's scale 2: orig 2, 28 taps; scale 10: orig 10, 132
+// taps): the window loops unroll completely, the rotating weight registers and the tail selects disappear.
+// ORIG = TAPS = 0 is the generic run-time version.
+
 // ---- forward: outputs j0 .. j0+3 (block-relative), xs[n] = xz[orig*j_first + n] staged by the caller ----
 // Needs xs[fir_pad(orig*(j0 + mm) + kappa)] for mm < M + 3, i.e. logical indices up to orig*(j0 + 3) + taps - 1.
-DM_HD void fir_fwd4(const float* xs, const float* w, int taps, int orig, int j0, float (&acc)[kFirR]) {
+template <int ORIG = 0, int TAPS = 0>
+DM_HD void fir_fwd4(const float* xs, const float* w, int taps_rt, int orig_rt, int j0, float (&acc)[kFirR]) {
+    const int orig = ORIG > 0 ? ORIG : orig_rt, taps = TAPS > 0 ? TAPS : taps_rt;
 #pragma unroll
     for (int c = 0; c < kFirR; ++c) acc[c] = 0.f;
+    if (ORIG > 0) {
+#pragma unroll
+        for (int kappa = 0; kappa < (ORIG > 0 ? ORIG : 1); ++kappa) {
+            constexpr int O = ORIG > 0 ? ORIG : 1, TP = TAPS > 0 ? TAPS : 1;
+            const int M = (TP - kappa + O - 1) / O;
+            const int x0 = O * j0 + kappa;
+#pragma unroll
+            for (int mm = 0; mm < (TP + O - 1) / O + kFirR - 1; ++mm) {
+                if (mm < M + kFirR - 1) {
+                    const float xv = xs[fir_pad(x0 + O * mm)];
+#pragma unroll
+                    for (int c = 0; c < kFirR; ++c) {
+                        const int m = mm - c;  // tap index of output c fed by this sample
+                        if (m >= 0 && m < M) acc[c] = fmaf(xv, w[kappa + O * m], acc[c]);
+                    }
+                }
+            }
+        }
+        return;
+    }
     for (int kappa = 0; kappa < orig; ++kappa) {
         const int M = (taps - kappa + orig - 1) / orig;  // taps of this phase
         float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;    // weights m = mm, mm-1, mm-2, mm-3
@@ -43,15 +69,36 @@ DM_HD void fir_fwd4(const float* xs, const float* w, int taps, int orig, int j0,
 // ---- adjoint: outputs t0, t0+orig, t0+2*orig, t0+3*orig (chunk-relative input positions of one phase) ----
 // ys[n] = (folded, scaled) ybar[j_base + n] staged by the caller with zeros outside [0, Ly);
 // A = (i0 + width - taps + 1) - j_base*orig in (-orig, 0].
-DM_HD void fir_adj4(const float* ys, const float* w, int taps, int orig, int A, int t0, float (&acc)[kFirR]) {
+template <int ORIG = 0, int TAPS = 0>
+DM_HD void fir_adj4(const float* ys, const float* w, int taps_rt, int orig_rt, int A, int t0, float (&acc)[kFirR]) {
+    const int orig = ORIG > 0 ? ORIG : orig_rt, taps = TAPS > 0 ? TAPS : taps_rt;
     const int hi0 = A + taps - 1 + t0;  // (i + width) - j_base*orig for the first output, >= 0
     const int jb0 = hi0 / orig;
     const int kappa = hi0 - jb0 * orig;
     const int M = (taps - kappa + orig - 1) / orig;
 #pragma unroll
     for (int c = 0; c < kFirR; ++c) acc[c] = 0.f;
-    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;  // weights m = mm, mm-1, mm-2, mm-3 (outputs c = 3, 2, 1, 0)
     const float* yp = ys + jb0 + kFirR - 1;
+    if (ORIG > 0) {
+        // kappa is a run-time phase, but M only takes the values MMAX or MMAX - 1: run MMAX taps with a zero weight
+        // for the (possibly) missing last one
+        constexpr int O = ORIG > 0 ? ORIG : 1, TP = TAPS > 0 ? TAPS : 1;
+        constexpr int MMAX = (TP + O - 1) / O;
+        float wk[MMAX];
+#pragma unroll
+        for (int m = 0; m < MMAX; ++m) wk[m] = (m < M) ? w[kappa + O * m] : 0.f;
+#pragma unroll
+        for (int mm = 0; mm < MMAX + kFirR - 1; ++mm) {
+            const float yv = yp[-mm];
+#pragma unroll
+            for (int c = 0; c < kFirR; ++c) {
+                const int m = mm - (kFirR - 1 - c);  // output c pairs sample jb0 + 3 - mm with tap mm - (3 - c)
+                if (m >= 0 && m < MMAX) acc[c] = fmaf(yv, wk[m], acc[c]);
+            }
+        }
+        return;
+    }
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;  // weights m = mm, mm-1, mm-2, mm-3 (outputs c = 3, 2, 1, 0)
     for (int mm = 0; mm < M + kFirR - 1; ++mm) {
         w3 = w2;
         w2 = w1;

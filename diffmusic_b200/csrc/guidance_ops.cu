@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(kEwThreads) resample_adjoint_kernel(
 }
 
 // ---- integer decimation (n_new == 1: scale 2 and 10 of run.py / operator.py): polyphase, 4 outputs per thread ----
+template <int ORIG, int TAPS>
 __global__ void __launch_bounds__(kEwThreads) resample_fwd_poly_kernel(const float* __restrict__ x,
                                                                        long long x_bstride, long long L,
                                                                        const float* __restrict__ kernel, int taps,
@@ -168,14 +169,14 @@ __global__ void __launch_bounds__(kEwThreads) resample_fwd_poly_kernel(const flo
     const long long x_lo = (long long)orig * o0 - width;
     for (int i = threadIdx.x; i < taps; i += kEwThreads) kw[i] = __ldg(kernel + i);
     const float* xb = x + (long long)b * x_bstride;
-    for (int i = threadIdx.x; i < span; i += kEwThreads) {
-        long long g = x_lo + i;
-        xs[fir_pad(i)] = (g >= 0 && g < L) ? xb[g] : 0.f;
-    }
+    // valid staged range in 32-bit block-relative indices: 0 <= x_lo + i < L
+    const int i_lo = (int)max(0LL, -x_lo), i_hi = (int)min((long long)span, L - x_lo);
+    const float* xrel = xb + x_lo;
+    for (int i = threadIdx.x; i < span; i += kEwThreads) xs[fir_pad(i)] = (i >= i_lo && i < i_hi) ? xrel[i] : 0.f;
     __syncthreads();
     for (int j0 = threadIdx.x * kFirR; j0 < no; j0 += kEwThreads * kFirR) {
         float acc[kFirR];
-        fir_fwd4(xs, kw, taps, orig, j0, acc);
+        fir_fwd4<ORIG, TAPS>(xs, kw, taps, orig, j0, acc);
 #pragma unroll
         for (int c = 0; c < kFirR; ++c) outs[j0 + c] = acc[c];
     }
@@ -183,15 +184,16 @@ __global__ void __launch_bounds__(kEwThreads) resample_fwd_poly_kernel(const flo
     for (int t = threadIdx.x; t < no; t += kEwThreads) y[(long long)b * Ly + o0 + t] = outs[t];
 }
 
+template <int ORIG, int TAPS>
 __global__ void __launch_bounds__(kEwThreads) resample_adjoint_poly_kernel(
     const float* __restrict__ ybar, int pad, long long Ly, const float* __restrict__ partial, int ntiles,
     const float* __restrict__ kernel, int taps, int orig, int width, float* __restrict__ dwav,
     long long dwav_bstride, long long L, float* __restrict__ loss, int span, int chunk) {
     extern __shared__ float sm[];
     __shared__ float scratch[2];
-    float* kw = sm;            // [taps]
-    float* ys = kw + taps;     // [span]
-    float* outs = ys + span;   // [chunk]
+    float* kw = sm;              // [taps]
+    float* ys = kw + taps + 1;   // [span], ys[-1] = 0 (the specialised body may touch it with a zero weight)
+    float* outs = ys + span;     // [chunk]
     const int b = blockIdx.y;
     const float l = clip_loss(partial + (long long)b * ntiles, ntiles, scratch);
     if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[b] = l;
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(kEwThreads) resample_adjoint_poly_kernel(
     const int A = (int)(num - j_base * orig);
     for (int i = threadIdx.x; i < taps; i += kEwThreads) kw[i] = __ldg(kernel + i);
     const float* yb = ybar + (long long)b * (Ly + 2 * pad);
+    if (threadIdx.x == 0) ys[-1] = 0.f;
     for (int i = threadIdx.x; i < span; i += kEwThreads) {
         long long o = j_base + i;
         ys[i] = (o >= 0 && o < Ly) ? ybar_at(yb, pad, o, Ly) * sc : 0.f;
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(kEwThreads) resample_adjoint_poly_kernel(
         const int phi = wi % orig, u = wi / orig;
         const int t0 = phi + orig * kFirR * u;
         float acc[kFirR];
-        fir_adj4(ys, kw, taps, orig, A, t0, acc);
+        fir_adj4<ORIG, TAPS>(ys, kw, taps, orig, A, t0, acc);
 #pragma unroll
         for (int c = 0; c < kFirR; ++c) outs[t0 + orig * c] = acc[c];
     }
@@ -275,9 +278,17 @@ extern "C" int dm_resample_fwd(const float* x, long long x_bstride, long long L,
         const int span1 = orig * (kRsChunk + kFirR) + taps;
         const size_t smem1 = ((size_t)taps + fir_padded_len(span1) + kRsChunk) * sizeof(float);
         if (smem1 <= 200 * 1024) {
-            DM_SMEM_ONCE(resample_fwd_poly_kernel, smem1);
-            resample_fwd_poly_kernel<<<dim3((unsigned)((Ly + kRsChunk - 1) / kRsChunk), B), kEwThreads, smem1,
-                                       as_stream(stream)>>>(x, x_bstride, L, kernel, taps, orig, width, y, Ly, span1);
+            const dim3 grid((unsigned)((Ly + kRsChunk - 1) / kRsChunk), B);
+#define DM_RS_FWD(O, T)                                                                                          \
+    do {                                                                                                         \
+        DM_SMEM_ONCE((resample_fwd_poly_kernel<O, T>), smem1);                                                   \
+        resample_fwd_poly_kernel<O, T><<<grid, kEwThreads, smem1, as_stream(stream)>>>(x, x_bstride, L, kernel, taps, \
+                                                                                       orig, width, y, Ly, span1);   \
+    } while (0)
+            if (orig == 2 && taps == 28) DM_RS_FWD(2, 28);          // scale 2 (run.py:188)
+            else if (orig == 10 && taps == 132) DM_RS_FWD(10, 132);  // scale 10 (operator.py:179 default)
+            else DM_RS_FWD(0, 0);
+#undef DM_RS_FWD
             DM_LAUNCHED();
             return DM_OK;
         }
@@ -304,11 +315,18 @@ extern "C" int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int
         const int unit = orig * kFirR;
         const int chunk = unit * ((kRsChunk + unit - 1) / unit);
         const int span1 = (taps + chunk) / orig + kFirR + 2;
-        const size_t smem1 = ((size_t)taps + span1 + chunk) * sizeof(float);
-        DM_SMEM_ONCE(resample_adjoint_poly_kernel, smem1);
-        resample_adjoint_poly_kernel<<<dim3((unsigned)((L + chunk - 1) / chunk), B), kEwThreads, smem1,
-                                       as_stream(stream)>>>(ybar, pad, Ly, partial, ntiles, kernel, taps, orig, width,
-                                                            dwav, dwav_bstride, L, loss, span1, chunk);
+        const size_t smem1 = ((size_t)taps + 1 + span1 + chunk) * sizeof(float);
+        const dim3 grid((unsigned)((L + chunk - 1) / chunk), B);
+#define DM_RS_ADJ(O, T)                                                                                           \
+    do {                                                                                                          \
+        DM_SMEM_ONCE((resample_adjoint_poly_kernel<O, T>), smem1);                                                \
+        resample_adjoint_poly_kernel<O, T><<<grid, kEwThreads, smem1, as_stream(stream)>>>(                       \
+            ybar, pad, Ly, partial, ntiles, kernel, taps, orig, width, dwav, dwav_bstride, L, loss, span1, chunk); \
+    } while (0)
+        if (orig == 2 && taps == 28) DM_RS_ADJ(2, 28);
+        else if (orig == 10 && taps == 132) DM_RS_ADJ(10, 132);
+        else DM_RS_ADJ(0, 0);
+#undef DM_RS_ADJ
         DM_LAUNCHED();
         return DM_OK;
     }

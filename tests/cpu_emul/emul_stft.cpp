@@ -189,7 +189,9 @@ void emul_resample_fwd(const float* x, long long L, const float* kernel, int tap
         for (int i = 0; i < span; ++i) { long long g = x_lo + i; xs[fir_pad(i)] = (g >= 0 && g < L) ? x[g] : 0.f; }
         for (int j0 = 0; j0 < no; j0 += kFirR) {
             float acc[kFirR];
-            fir_fwd4(xs.data(), kernel, taps, orig, j0, acc);
+            if (orig == 2 && taps == 28) fir_fwd4<2, 28>(xs.data(), kernel, taps, orig, j0, acc);
+            else if (orig == 10 && taps == 132) fir_fwd4<10, 132>(xs.data(), kernel, taps, orig, j0, acc);
+            else fir_fwd4(xs.data(), kernel, taps, orig, j0, acc);
             for (int c = 0; c < kFirR; ++c) outs[j0 + c] = acc[c];
         }
         for (int t = 0; t < no; ++t) y[o0 + t] = outs[t];
@@ -201,7 +203,8 @@ void emul_resample_adjoint(const float* ybar, long long Ly, const float* kernel,
     const int unit = orig * kFirR;
     const int chunk = unit * ((2048 + unit - 1) / unit);
     const int span = (taps + chunk) / orig + kFirR + 2;
-    std::vector<float> ys(span), outs(chunk);
+    std::vector<float> ybuf(span + 1, 0.f), outs(chunk);
+    float* ys = ybuf.data() + 1;  // ys[-1] = 0
     for (long long i0 = 0; i0 < L; i0 += chunk) {
         const int ni = (int)std::min<long long>(chunk, L - i0);
         const long long num = i0 + width - taps + 1;
@@ -211,7 +214,9 @@ void emul_resample_adjoint(const float* ybar, long long Ly, const float* kernel,
         for (int wi = 0; wi < chunk / kFirR; ++wi) {
             const int phi = wi % orig, u = wi / orig, t0 = phi + orig * kFirR * u;
             float acc[kFirR];
-            fir_adj4(ys.data(), kernel, taps, orig, A, t0, acc);
+            if (orig == 2 && taps == 28) fir_adj4<2, 28>(ys, kernel, taps, orig, A, t0, acc);
+            else if (orig == 10 && taps == 132) fir_adj4<10, 132>(ys, kernel, taps, orig, A, t0, acc);
+            else fir_adj4(ys, kernel, taps, orig, A, t0, acc);
             for (int c = 0; c < kFirR; ++c) outs[t0 + orig * c] = acc[c];
         }
         for (int t = 0; t < ni; ++t) xbar[i0 + t] = outs[t];
