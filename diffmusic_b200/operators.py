@@ -63,6 +63,15 @@ class _DeviceTables:
         self.ref = C.byref(self.struct)
 
 
+def _grad_buffer(dwav, B, L, device):
+    """(B, L) fp32 destination of dLoss/dwav: a fresh tensor, or the caller's (possibly row-strided) view."""
+    if dwav is None:
+        return torch.empty((B, L), device=device, dtype=torch.float32)
+    if tuple(dwav.shape) != (B, L) or dwav.dtype != torch.float32 or dwav.stride(1) != 1 or dwav.device != device:
+        raise ValueError("dwav must be a (B, L) fp32 view with unit inner stride on the waveform's device")
+    return dwav
+
+
 def _frames_per_tile(B, T, device):
     """frames per CTA tile.  Up to 10 frames per tile the kernel's shared memory (~73 KB) lets 3 CTAs stay resident per
     SM; among 6..10 pick the size whose CTA count fills whole waves of 3 x SMs best (tail effect), larger tiles on
@@ -173,12 +182,14 @@ class BaseOperator:
             raise ValueError("supervised_space should be either 'wav_form' or 'mel_spectrogram")
         return _GuidanceLoss.apply(wav, self, measurement, supervised_space)
 
-    def fused_loss_and_grad(self, wav, measurement, supervised_space="mel_spectrogram"):
-        """(loss (B,), dLoss/dwav (B, L)) from one fused forward+VJP kernel chain; what the schedulers call."""
+    def fused_loss_and_grad(self, wav, measurement, supervised_space="mel_spectrogram", dwav=None):
+        """(loss (B,), dLoss/dwav (B, L)) from one fused forward+VJP kernel chain; what the schedulers call.
+        `dwav` may be a preallocated (B, L) view with a row stride (e.g. the head of a (B, L_vocoder) buffer, so the
+        gradient of the `[:, :L]` slice needs no extra zero-fill + copy)."""
         if supervised_space not in ("wav_form", "mel_spectrogram"):
             raise ValueError("supervised_space should be either 'wav_form' or 'mel_spectrogram")
         _lib.require_cuda(wav)
-        return self._fused(_as_f32_rows(wav), measurement, supervised_space, True)
+        return self._fused(_as_f32_rows(wav), measurement, supervised_space, True, dwav)
 
     def _ref_mel(self, measurement):
         """transform(measurement), cached: the reference recomputes it every step (scheduling_dps.py:205)."""
@@ -191,7 +202,7 @@ class BaseOperator:
         return cache["val"]
 
     # subclasses implement: _fused(wav_rows, measurement, space, want_grad) -> (loss (B,), dwav (B, L) or None)
-    def _fused(self, wav, measurement, space, want_grad):
+    def _fused(self, wav, measurement, space, want_grad, dwav=None):
         raise NotImplementedError
 
     def _residual_wav(self, y, meas, mask=None):
@@ -206,14 +217,14 @@ class BaseOperator:
                   0 if meas.shape[0] == 1 else meas.stride(0), ybar.data_ptr(), partial.data_ptr(), _lib.stream())
         return ybar, partial, nt
 
-    def _fold_adjoint(self, ybar, pad, Ly, B, partial, ntiles, mask, want_grad):
+    def _fold_adjoint(self, ybar, pad, Ly, B, partial, ntiles, mask, want_grad, dwav=None):
         dev = partial.device
         loss = torch.empty((B,), device=dev, dtype=torch.float32)
         if not want_grad:  # loss only
             _lib.call("dm_fold_adjoint", None, pad, Ly, B, None, partial.data_ptr(), ntiles, None, 0,
                       loss.data_ptr(), _lib.stream())
             return loss, None
-        dwav = torch.empty((B, Ly), device=dev, dtype=torch.float32)
+        dwav = _grad_buffer(dwav, B, Ly, dev)
         _lib.call("dm_fold_adjoint", ybar.data_ptr(), pad, Ly, B, _lib.ptr(mask), partial.data_ptr(), ntiles,
                   dwav.data_ptr(), dwav.stride(0), loss.data_ptr(), _lib.stream())
         return loss, dwav
@@ -264,10 +275,10 @@ class IdentityOperator(BaseOperator):
     def forward(self, data, **kwargs):
         return data
 
-    def _fused(self, wav, measurement, space, want_grad):
+    def _fused(self, wav, measurement, space, want_grad, dwav=None):
         B, L = wav.shape
         ybar, pad, partial, nt = self._space_stage(wav, measurement, space, want_grad)
-        return self._fold_adjoint(ybar, pad, L, B, partial, nt, None, want_grad)
+        return self._fold_adjoint(ybar, pad, L, B, partial, nt, None, want_grad, dwav)
 
 
 class MusicInpaintingOperator(BaseOperator):
@@ -331,7 +342,7 @@ class MusicInpaintingOperator(BaseOperator):
                   _lib.stream())
         return self._finish_forward(y.reshape(data.shape), data)
 
-    def _fused(self, wav, measurement, space, want_grad):
+    def _fused(self, wav, measurement, space, want_grad, dwav=None):
         B, L = wav.shape
         mask = self._mask_on(wav.device)
         if mask.numel() != L:
@@ -341,7 +352,7 @@ class MusicInpaintingOperator(BaseOperator):
             ybar, pad, partial, nt = self._space_stage(y, measurement, space, want_grad)
         else:
             ybar, pad, partial, nt = self._space_stage(wav, measurement, space, want_grad, mask=mask)
-        return self._fold_adjoint(ybar, pad, L, B, partial, nt, mask, want_grad)
+        return self._fold_adjoint(ybar, pad, L, B, partial, nt, mask, want_grad, dwav)
 
 
 class PhaseRetrievalOperator(BaseOperator):
@@ -375,7 +386,7 @@ class PhaseRetrievalOperator(BaseOperator):
         mag = self._stft(_MODE_PHASE_WAV, y, out_rows=513, clamp=False)
         return self._finish_forward(mag.reshape(*lead, 513, mag.shape[-1]), data)
 
-    def _fused(self, wav, measurement, space, want_grad):
+    def _fused(self, wav, measurement, space, want_grad, dwav=None):
         B, L = wav.shape
         sigma = self._sigma()
         T = 1 + L // _HOP
@@ -390,7 +401,7 @@ class PhaseRetrievalOperator(BaseOperator):
                 raise ValueError(f"measurement {tuple(ref.shape)} does not match |STFT| of the prediction (513, {T})")
             ypbar, partial, nt = self._stft(_MODE_PHASE_WAV, wav, ref=ref.reshape(-1, 513, T), want_grad=want_grad,
                                             clamp=False, noise=noise, sigma=sigma)
-        return self._fold_adjoint(ypbar, 512, L, B, partial, nt, None, want_grad)
+        return self._fold_adjoint(ypbar, 512, L, B, partial, nt, None, want_grad, dwav)
 
 
 class SuperResolutionOperator(BaseOperator):
@@ -429,7 +440,7 @@ class SuperResolutionOperator(BaseOperator):
         y = self._resample(x)
         return self._finish_forward(y.reshape(*lead, y.shape[-1]), data)
 
-    def _fused(self, wav, measurement, space, want_grad):
+    def _fused(self, wav, measurement, space, want_grad, dwav=None):
         B, L = wav.shape
         y = self._resample(wav)
         if self._sigma() != 0.0:
@@ -439,10 +450,10 @@ class SuperResolutionOperator(BaseOperator):
         if not want_grad:
             return self._fold_adjoint(None, pad, Ly, B, partial, nt, None, False)
         if self.kernel is None:
-            return self._fold_adjoint(ybar, pad, L, B, partial, nt, None, True)
+            return self._fold_adjoint(ybar, pad, L, B, partial, nt, None, True, dwav)
         k = self._kernel_on(wav.device)
         loss = torch.empty((B,), device=wav.device, dtype=torch.float32)
-        dwav = torch.empty((B, L), device=wav.device, dtype=torch.float32)
+        dwav = _grad_buffer(dwav, B, L, wav.device)
         _lib.call("dm_resample_adjoint", ybar.data_ptr(), pad, Ly, B, partial.data_ptr(), nt, k.data_ptr(),
                   k.shape[0], k.shape[1], self.orig, self.width, dwav.data_ptr(), dwav.stride(0), L, loss.data_ptr(),
                   _lib.stream())
@@ -508,7 +519,7 @@ class MusicDereverberationOperator(BaseOperator):
         y = self._correlate(x, spec, K)
         return self._finish_forward(y.reshape(*lead, y.shape[-1]), data)
 
-    def _fused(self, wav, measurement, space, want_grad):
+    def _fused(self, wav, measurement, space, want_grad, dwav=None):
         B, L = wav.shape
         if self.static_ir is not None:
             ir = self.static_ir  # refreshed by GraphedGuidedStep before every replay (same host-side draw)
@@ -525,7 +536,7 @@ class MusicDereverberationOperator(BaseOperator):
             return self._fold_adjoint(None, pad, Ly, B, partial, nt, None, False)
         tw, w = self._rir_tables(wav.device)
         loss = torch.empty((B,), device=wav.device, dtype=torch.float32)
-        dwav = torch.empty((B, L), device=wav.device, dtype=torch.float32)
+        dwav = _grad_buffer(dwav, B, L, wav.device)
         _lib.call("dm_rir_adjoint", ybar.data_ptr(), pad, Ly, B, partial.data_ptr(), nt, spec.data_ptr(), K,
                   tw.data_ptr(), w.data_ptr(), dwav.data_ptr(), dwav.stride(0), L, loss.data_ptr(), _lib.stream())
         return loss, dwav

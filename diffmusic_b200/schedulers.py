@@ -147,11 +147,21 @@ class _GuidedBase(DDIMBase):
         with torch.enable_grad():
             leaf = x0.detach().requires_grad_(True)
             mel = vae.decode(1 / vae.config.scaling_factor * leaf.to(model_dtype)).sample
-            wav = op.inverse_transform(mel, vocoder)
-            wav = wav[:, :L]
-            if getattr(op, "fused_loss_and_grad", None) is not None:
+            wav_full = op.inverse_transform(mel, vocoder)
+            wav = wav_full[:, :L]
+            if getattr(op, "fused_loss_and_grad", None) is not None and wav_full.dtype == torch.float32 \
+                    and wav_full.dim() == 2 and wav_full.stride(1) == 1:
                 # one fused kernel chain gives the per-clip loss AND dLoss/dwav; torch only continues the VJP through
-                # the vocoder and the VAE decoder (no autograd node, no extra elementwise pass on the waveform)
+                # the vocoder and the VAE decoder.  The cotangent is written straight into a buffer shaped like the
+                # vocoder output (zero tail beyond L = the adjoint of the `[:, :L]` slice), so autograd
+                # starts at the vocoder output: no slice-backward zero-fill + copy of the whole waveform.
+                Lw = wav.shape[1]
+                dfull = torch.empty_like(wav_full)
+                if wav_full.shape[1] > Lw:
+                    dfull[:, Lw:].zero_()
+                losses, _ = op.fused_loss_and_grad(wav.detach(), measurement, supervised_space, dwav=dfull[:, :Lw])
+                (g0,) = torch.autograd.grad(wav_full, leaf, grad_outputs=dfull)
+            elif getattr(op, "fused_loss_and_grad", None) is not None:
                 losses, dwav = op.fused_loss_and_grad(wav.detach(), measurement, supervised_space)
                 (g0,) = torch.autograd.grad(wav, leaf, grad_outputs=dwav.to(wav.dtype))
             else:
