@@ -595,3 +595,23 @@ def test_noisy_operator_inside_guidance():
     (gw,) = torch.autograd.grad(want, w)
     assert abs(float(loss) - float(want)) < TOL * float(want)
     assert rel_l2(g, gw) < TOL
+
+
+def test_fp16_pipeline_dtype_is_accepted():
+    """run.py:218 loads the pipelines in fp16: latents, noise prediction and the networks are half precision.  The
+    scheduler computes in fp32 (operators up-cast with .float(), operator.py:154,205,248) and returns the caller's
+    dtype; the result stays close to the fp32 step."""
+    B = 2
+    vae, voc = stubs.StubVAE().to(DEV), stubs.StubVocoder().to(DEV)
+    x, e = stubs.synth_latents(B, 25)
+    op = dm.SuperResolutionOperator(16000, 2, _noiser())
+    meas = op.forward(stubs.synth_clips(1, L1, first=50).to(DEV))
+    sched = dm.DPSScheduler(operator=op, **stubs.MUSICLDM_SCHED)
+    sched.set_timesteps(500)
+    kw = dict(measurement=meas, original_waveform_length=L1, ip_guidance_rate=5e-4)
+    full = sched.step(e.to(DEV), 501, x.to(DEV), vae=vae, vocoder=voc, **kw)
+    half = sched.step(e.to(DEV).half(), 501, x.to(DEV).half(), vae=vae.half(), vocoder=voc.half(), **kw)
+    assert half.prev_sample.dtype == torch.float16 and half.pred_original_sample.dtype == torch.float16
+    assert torch.isfinite(half.prev_sample).all() and torch.isfinite(half.loss)
+    assert rel_l2(half.prev_sample.float(), full.prev_sample) < 5e-3
+    assert abs(float(half.loss) - float(full.loss)) < 2e-2 * float(full.loss)
