@@ -33,6 +33,32 @@ struct StftParams {
     float* partial;
 };
 
+// ---- TMA bulk copy (cp.async.bulk) of an interior tile's contiguous signal span into shared memory ----
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load_span(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_addr_u32(bar))
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_addr_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kGroupThreads)); }
 
 template <int MODE>
@@ -74,13 +100,29 @@ __global__ void __launch_bounds__(kCtaThreads, 3) stft_guidance_kernel(const Stf
     const bool aligned8 = (p.hop & 1) == 0;
 
     // ---- stage the signal span, tables and the reference tile ----
+    // Interior tiles (no reflection) take their contiguous span with ONE TMA bulk copy (cp.async.bulk, completion on an
+    // mbarrier) issued by thread 0 while all threads fill the tables; edge tiles mirror sample by sample.
     const float* yb = p.y + (long long)b * p.y_bstride;
-    for (int i = tid; i < span; i += kCtaThreads) {
-        long long j = reflect_src(base + i, p.Ly);
-        float v = __ldg(yb + j);
-        if (p.mask) v *= __ldg(p.mask + j);
-        sig[i] = v;
-        acc[i] = 0.f;
+    __shared__ __align__(8) uint64_t stage_bar;
+    const float* span_src = yb + (base - kNfft / 2);
+    const bool interior = base >= kNfft / 2 && base - kNfft / 2 + span <= p.Ly &&
+                          (reinterpret_cast<uintptr_t>(span_src) & 15) == 0 && (span & 3) == 0;
+    if (interior) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&stage_bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_load_span(sig, span_src, (uint32_t)span * 4u, &stage_bar);
+        }
+        for (int i = tid; i < span; i += kCtaThreads) acc[i] = 0.f;
+    } else {
+        for (int i = tid; i < span; i += kCtaThreads) {
+            long long j = reflect_src(base + i, p.Ly);
+            float v = __ldg(yb + j);
+            if (p.mask) v *= __ldg(p.mask + j);
+            sig[i] = v;
+            acc[i] = 0.f;
+        }
     }
     for (int i = tid; i < kNfft; i += kCtaThreads) win[i] = __ldg(p.tab.window + i);
     for (int i = tid; i < p.tab.mel_wstride * kMels; i += kCtaThreads) melw_t[i] = __ldg(p.tab.mel_w + i);
@@ -93,7 +135,15 @@ __global__ void __launch_bounds__(kCtaThreads, 3) stft_guidance_kernel(const Stf
             tilebuf[f * kTileLd + m] = __ldg(rb + (long long)m * p.T + f0 + f);
         }
     }
-    __syncthreads();
+    __syncthreads();  // tables / tile visible, and the mbarrier initialisation precedes every wait
+    if (interior) {
+        mbar_wait_parity(&stage_bar, 0);  // bulk copy landed (async proxy writes are visible after the wait)
+        if (p.mask) {                     // inpainting A(x) = x * mask on the staged span
+            const float* mk = p.mask + (base - kNfft / 2);
+            for (int i = tid; i < span; i += kCtaThreads) sig[i] *= __ldg(mk + i);
+            __syncthreads();
+        }
+    }
 
     float lsum = 0.f;
     const int rounds = (nfr + kGroups - 1) / kGroups;
