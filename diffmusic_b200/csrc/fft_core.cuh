@@ -38,9 +38,9 @@ DM_HD cf cmul_i(cf a) {
 // the index makes EVERY access pattern of the radix-8 Stockham passes bank-conflict free -- the unit-stride loads
 // j + r*T, the stride-8 scatter of the first pass, the 8-block scatter of the second and the unit-stride scatters of the
 // later ones (exhaustively checked for N = 512 and N = 4096: 96 / 1024 wavefronts = the minimum, versus 160 / 1792 for
-// the usual pad-one-word-every-8 layout).  No padding words are needed.  (Named padi for historical reasons.)
-DM_HD int padi(int i) { return i ^ ((i >> 3) & 31); }
-DM_HDC int padded_len(int n) { return n; }
+// the usual pad-one-word-every-8 layout).  No padding words are needed.
+DM_HD int swz(int i) { return i ^ ((i >> 3) & 31); }
+DM_HDC int swz_len(int n) { return n; }
 
 // 8-point DFT in registers: out[q] = sum_r v[r] * exp(SIGN * 2*pi*i * r*q / 8)
 template <int SIGN>
@@ -100,42 +100,23 @@ DM_HD void thread_twiddles(int j, const cf* __restrict__ tw, cf (&w)[7]) {
 #pragma unroll
     for (int r = 1; r < 8; ++r) w[r - 1] = tw[r * k * TWS];
 }
-template <int N, int NS, int SIGN, class Load, class Store>
-DM_HD void stockham_pass_rt(int j, const cf (&w)[7], Load load, Store store) {
-    constexpr int T = N / 8;
-    const int k = j % NS;
-    cf v[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = load(j + r * T);
-#pragma unroll
-    for (int r = 1; r < 8; ++r) {
-        cf t = w[r - 1];
-        if (SIGN > 0) t.y = -t.y;
-        v[r] = cmul(v[r], t);
-    }
-    dft8<SIGN>(v);
-    const int j0 = (j / NS) * NS * 8 + k;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) store(j0 + q * NS, v[q]);
-}
-
 // Swizzled split-array I/O of one radix-8 butterfly: inputs j + r*T, outputs j0 + q*NS.
 // The swizzled addresses have closed forms with ONE variable term per thread and compile-time constants per r / q,
 // because the index pieces occupy disjoint bit fields (so + is ^ and the mask (i >> 3) & 31 splits the same way):
-//   loads   j + r*T        T = 64 : (padi(j) ^ ((r & 3) << 3)) + 64 r          T = 512 : padi(j) + 512 r
+//   loads   j + r*T        T = 64 : (swz(j) ^ ((r & 3) << 3)) + 64 r          T = 512 : swz(j) + 512 r
 //   NS = 1  8 j + q               : ((8 j) ^ (j & 31)) ^ q
 //   NS = 8  64 a + k + 8 q        : (64 a ^ k ^ ((a & 3) << 3)) ^ (9 q)          a = j >> 3, k = j & 7
 //   NS = 64 512 c + l + 64 q      : (((512 c + l) ^ (l >> 3)) ^ ((q & 3) << 3)) + 64 q     c = j >> 6, l = j & 63
-//   NS = 512 j + 512 q            : padi(j) + 512 q
-// (checked against padi() itself for every j, r, q in tests/cpu_emul; one LOP3/IADD per access instead of five.)
+//   NS = 512 j + 512 q            : swz(j) + 512 q
+// (checked against swz() itself for every j, r, q in tests/cpu_emul; one LOP3/IADD per access instead of five.)
 template <int N>
 DM_HD int ld_addr(int b0, int r) {
     static_assert(N == 512 || N == 4096, "closed forms derived for N = 512 and N = 4096");
     return N == 512 ? ((b0 ^ ((r & 3) << 3)) + 64 * r) : (b0 + 512 * r);
 }
 template <int N>
-DM_HD void load8_pad(const float* __restrict__ re, const float* __restrict__ im, int j, cf (&v)[8]) {
-    const int b0 = padi(j);
+DM_HD void load8_swz(const float* __restrict__ re, const float* __restrict__ im, int j, cf (&v)[8]) {
+    const int b0 = swz(j);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int a = ld_addr<N>(b0, r);
@@ -147,7 +128,7 @@ DM_HD int st_base(int j) {
     if (NS == 1) return (8 * j) ^ (j & 31);
     if (NS == 8) return (64 * (j >> 3)) ^ (j & 7) ^ (((j >> 3) & 3) << 3);
     if (NS == 64) return ((512 * (j >> 6) + (j & 63)) ^ ((j & 63) >> 3));
-    return padi(j);  // NS == 512
+    return swz(j);  // NS == 512
 }
 template <int N, int NS>
 DM_HD int st_addr(int b, int q) {
@@ -158,7 +139,7 @@ DM_HD int st_addr(int b, int q) {
     return b + 512 * q;
 }
 template <int N, int NS>
-DM_HD void store8_pad(float* __restrict__ re, float* __restrict__ im, int j, const cf (&v)[8]) {
+DM_HD void store8_swz(float* __restrict__ re, float* __restrict__ im, int j, const cf (&v)[8]) {
     const int b = st_base<N, NS>(j);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -167,7 +148,10 @@ DM_HD void store8_pad(float* __restrict__ re, float* __restrict__ im, int j, con
         im[a] = v[q].y;
     }
 }
-// seven twiddles of thread j generated from the first by complex multiplication (see stockham_pass_rec)
+// Seven twiddles of thread j generated from the first one by complex multiplication (w^2 = w*w, w^3 = w^2*w,
+// w^4 = (w^2)^2, w^5 = w^4*w, w^6 = (w^3)^2, w^7 = w^4*w^3): one table read per pass and thread instead of seven strided
+// ones.  Used by the 4096-point RIR transform, where each CTA does a single block and register-resident twiddles would
+// not be reused.  Error: <= 3 extra roundings on |w| = 1, far below the 1e-4 parity bound.
 template <int N, int NS, int SIGN>
 DM_HD void twiddle8_rec(int j, const cf* __restrict__ tw, cf (&v)[8]) {
     constexpr int TWS = N / (NS * 8);
@@ -184,13 +168,13 @@ DM_HD void twiddle8_rec(int j, const cf* __restrict__ tw, cf (&v)[8]) {
 }
 // smem -> smem pass with recurrence twiddles (the 4096-point transform)
 template <int N, int NS, int SIGN>
-DM_HD void stockham_pass_rec_pad(int j, const cf* __restrict__ tw, const float* in_re, const float* in_im,
+DM_HD void stockham_pass_rec_swz(int j, const cf* __restrict__ tw, const float* in_re, const float* in_im,
                                  float* out_re, float* out_im) {
     cf v[8];
-    load8_pad<N>(in_re, in_im, j, v);
+    load8_swz<N>(in_re, in_im, j, v);
     twiddle8_rec<N, NS, SIGN>(j, tw, v);
     dft8<SIGN>(v);
-    store8_pad<N, NS>(out_re, out_im, j, v);
+    store8_swz<N, NS>(out_re, out_im, j, v);
 }
 template <int SIGN>
 DM_HD void twiddle8(cf (&v)[8], const cf (&w)[7]) {
@@ -203,57 +187,29 @@ DM_HD void twiddle8(cf (&v)[8], const cf (&w)[7]) {
 }
 // padded -> padded pass with register twiddles (NS > 1)
 template <int N, int NS, int SIGN>
-DM_HD void stockham_pass_pad(int j, const cf (&w)[7], const float* in_re, const float* in_im, float* out_re,
+DM_HD void stockham_pass_swz(int j, const cf (&w)[7], const float* in_re, const float* in_im, float* out_re,
                              float* out_im) {
     cf v[8];
-    load8_pad<N>(in_re, in_im, j, v);
+    load8_swz<N>(in_re, in_im, j, v);
     twiddle8<SIGN>(v, w);
     dft8<SIGN>(v);
-    store8_pad<N, NS>(out_re, out_im, j, v);
+    store8_swz<N, NS>(out_re, out_im, j, v);
 }
 
-// Pass whose seven twiddles are generated from the first one by complex multiplication (w^2 = w*w, w^3 = w^2*w,
-// w^4 = (w^2)^2, w^5 = w^4*w, w^6 = (w^3)^2, w^7 = w^4*w^3): one table read per pass and thread instead of seven strided
-// ones.  Used by the 4096-point RIR transform, where each CTA does a single block and register-resident twiddles
-// would not be reused.  Error: <= 3 extra roundings on |w| = 1, far below the 1e-4 parity bound.
-template <int N, int NS, int SIGN, class Load, class Store>
-DM_HD void stockham_pass_rec(int j, const cf* __restrict__ tw, Load load, Store store) {
-    constexpr int T = N / 8;
-    constexpr int TWS = N / (NS * 8);
-    const int k = j % NS;
-    cf v[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = load(j + r * T);
-    cf w1 = tw[k * TWS];
-    if (SIGN > 0) w1.y = -w1.y;
-    const cf w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
-    v[1] = cmul(v[1], w1);
-    v[2] = cmul(v[2], w2);
-    v[3] = cmul(v[3], w3);
-    v[4] = cmul(v[4], w4);
-    v[5] = cmul(v[5], cmul(w4, w1));
-    v[6] = cmul(v[6], cmul(w3, w3));
-    v[7] = cmul(v[7], cmul(w4, w3));
-    dft8<SIGN>(v);
-    const int j0 = (j / NS) * NS * 8 + k;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) store(j0 + q * NS, v[q]);
-}
-
-// Split-array accessors with padding.
-struct PadLoad {
+// Swizzled split-array accessors (used by the phases that touch arbitrary indices: unpack / pack / first / last pass).
+struct SwzLoad {
     const float* re;
     const float* im;
     DM_HD cf operator()(int i) const {
-        int p = padi(i);
+        int p = swz(i);
         return cf{re[p], im[p]};
     }
 };
-struct PadStore {
+struct SwzStore {
     float* re;
     float* im;
     DM_HD void operator()(int i, cf c) const {
-        int p = padi(i);
+        int p = swz(i);
         re[p] = c.x;
         im[p] = c.y;
     }

@@ -13,7 +13,7 @@ namespace dm {
 
 constexpr int kFirR = 4;  // outputs per thread
 // staged-input index padding: thread t of the forward kernel reads xs[orig * 4 t + ...], a stride of 4*orig words;
-// one extra word every 32 spreads that over all banks (same idea as padi() in fft_core.cuh)
+// one extra word every 32 spreads that over all banks (same idea as swz() in fft_core.cuh)
 DM_HD int fir_pad(int i) { return i + (i >> 5); }
 DM_HDC int fir_padded_len(int n) { return n + (n >> 5) + 1; }
 

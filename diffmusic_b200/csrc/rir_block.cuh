@@ -17,15 +17,15 @@ constexpr int kRirH = 4096;      // complex FFT length
 constexpr int kRirThreads = 512;
 
 struct RirSmem {
-    float* a_re;  // [padded_len(4096)]
+    float* a_re;  // [swz_len(4096)]
     float* a_im;
     float* b_re;
     float* b_im;
 };
-constexpr int kRirSmemFloats = 4 * padded_len(kRirH);
+constexpr int kRirSmemFloats = 4 * swz_len(kRirH);
 
 // spectrum of the impulse response: ir zero-padded to 8192, H[k], k = 0..4096, from the packed FFT Z (in `z`)
-DM_HD void rir_unpack_spectrum(int tid, PadLoad Z, const cf* w8192, cf* spec) {
+DM_HD void rir_unpack_spectrum(int tid, SwzLoad Z, const cf* w8192, cf* spec) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int k = tid + kRirThreads * i;  // 0..2047
@@ -46,7 +46,7 @@ DM_HD void rir_unpack_spectrum(int tid, PadLoad Z, const cf* w8192, cf* spec) {
 // Pointwise spectral product on packed data: Zin (FFT of the packed real block) -> Zout (packed spectrum of the
 // product, ready for the unnormalised inverse).  CONJ = true multiplies by conj(H) (cross-correlation).
 template <bool CONJ>
-DM_HD void rir_pointwise(int tid, PadLoad Zin, PadStore Zout, const cf* spec, const cf* w8192) {
+DM_HD void rir_pointwise(int tid, SwzLoad Zin, SwzStore Zout, const cf* spec, const cf* w8192) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int k = tid + kRirThreads * i;  // 0..2047
@@ -101,18 +101,26 @@ struct RirStore {
 template <bool CONJ, class Src>
 DM_HD void rir_block_phase(int ph, int tid, const cf* tw, const cf* w8192, const cf* spec, RirSmem s, Src src,
                            RirStore st) {
-    PadLoad la{s.a_re, s.a_im}, lb{s.b_re, s.b_im};
-    PadStore sa{s.a_re, s.a_im}, sb{s.b_re, s.b_im};
+    SwzLoad la{s.a_re, s.a_im}, lb{s.b_re, s.b_im};
+    SwzStore sa{s.a_re, s.a_im}, sb{s.b_re, s.b_im};
     switch (ph) {
         case 0: stockham_pass<kRirH, 1, -1>(tid, tw, RirLoad<Src>{src}, sa); break;
-        case 1: stockham_pass_rec_pad<kRirH, 8, -1>(tid, tw, s.a_re, s.a_im, s.b_re, s.b_im); break;
-        case 2: stockham_pass_rec_pad<kRirH, 64, -1>(tid, tw, s.b_re, s.b_im, s.a_re, s.a_im); break;
-        case 3: stockham_pass_rec_pad<kRirH, 512, -1>(tid, tw, s.a_re, s.a_im, s.b_re, s.b_im); break;
+        case 1: stockham_pass_rec_swz<kRirH, 8, -1>(tid, tw, s.a_re, s.a_im, s.b_re, s.b_im); break;
+        case 2: stockham_pass_rec_swz<kRirH, 64, -1>(tid, tw, s.b_re, s.b_im, s.a_re, s.a_im); break;
+        case 3: stockham_pass_rec_swz<kRirH, 512, -1>(tid, tw, s.a_re, s.a_im, s.b_re, s.b_im); break;
         case 4: rir_pointwise<CONJ>(tid, lb, sa, spec, w8192); break;
         case 5: stockham_pass<kRirH, 1, +1>(tid, tw, la, sb); break;
-        case 6: stockham_pass_rec_pad<kRirH, 8, +1>(tid, tw, s.b_re, s.b_im, s.a_re, s.a_im); break;
-        case 7: stockham_pass_rec_pad<kRirH, 64, +1>(tid, tw, s.a_re, s.a_im, s.b_re, s.b_im); break;
-        default: stockham_pass_rec<kRirH, 512, +1>(tid, tw, lb, st); break;
+        case 6: stockham_pass_rec_swz<kRirH, 8, +1>(tid, tw, s.b_re, s.b_im, s.a_re, s.a_im); break;
+        case 7: stockham_pass_rec_swz<kRirH, 64, +1>(tid, tw, s.a_re, s.a_im, s.b_re, s.b_im); break;
+        default: {  // last inverse pass: swizzled loads, recurrence twiddles, outputs go through the store functor
+            cf v[8];
+            load8_swz<kRirH>(s.b_re, s.b_im, tid, v);
+            twiddle8_rec<kRirH, 512, +1>(tid, tw, v);
+            dft8<+1>(v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) st(tid + q * 512, v[q]);
+            break;
+        }
     }
 }
 constexpr int kRirPhases = 9;

@@ -36,9 +36,9 @@ struct SrcFolded {  // scaled, reflect-folded cotangent
 __device__ __forceinline__ RirSmem carve(float* smem) {
     RirSmem s;
     s.a_re = smem;
-    s.a_im = s.a_re + padded_len(kRirH);
-    s.b_re = s.a_im + padded_len(kRirH);
-    s.b_im = s.b_re + padded_len(kRirH);
+    s.a_im = s.a_re + swz_len(kRirH);
+    s.b_re = s.a_im + swz_len(kRirH);
+    s.b_im = s.b_re + swz_len(kRirH);
     return s;
 }
 
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kRirThreads) rir_spectrum_kernel(const float* 
         rir_block_phase<false>(ph, threadIdx.x, tw, w8192, nullptr, s, src, st);
         __syncthreads();
     }
-    rir_unpack_spectrum(threadIdx.x, PadLoad{s.b_re, s.b_im}, w8192, spec);
+    rir_unpack_spectrum(threadIdx.x, SwzLoad{s.b_re, s.b_im}, w8192, spec);
 }
 
 __global__ void __launch_bounds__(kRirThreads, 2) rir_correlate_kernel(const float* __restrict__ x,

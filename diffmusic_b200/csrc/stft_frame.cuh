@@ -56,13 +56,13 @@ struct FrameSmem {
     float* melbar;  // [72] (index 64 must read as 0)
     float* aux;     // [8]  aux[0] = P[512]
 };
-constexpr int kFrameSmemFloats = 4 * padded_len(kH) + 72 + 8;
+constexpr int kFrameSmemFloats = 4 * swz_len(kH) + 72 + 8;
 
-DM_HD float& p_at(const FrameSmem& s, int k) { return k == kH ? s.aux[0] : s.a_re[padi(k)]; }
+DM_HD float& p_at(const FrameSmem& s, int k) { return k == kH ? s.aux[0] : s.a_re[swz(k)]; }
 DM_HD cf x_at(const FrameSmem& s, int k) {
-    if (k == 0) return cf{s.b_re[padi(0)], 0.f};
-    if (k == kH) return cf{s.b_im[padi(0)], 0.f};
-    const int a = padi(k);
+    if (k == 0) return cf{s.b_re[swz(0)], 0.f};
+    if (k == kH) return cf{s.b_im[swz(0)], 0.f};
+    const int a = swz(k);
     return cf{s.b_re[a], s.b_im[a]};
 }
 
@@ -96,19 +96,19 @@ DM_HD void fwd_pass1(int tid, const float* frame, const float* window, FrameSmem
 #pragma unroll
     for (int r = 0; r < 8; ++r) v[r] = load(tid + r * (kH / 8));
     dft8<-1>(v);
-    store8_pad<kH, 1>(s.a_re, s.a_im, tid, v);
+    store8_swz<kH, 1>(s.a_re, s.a_im, tid, v);
 }
 DM_HD void fwd_pass2(int tid, const ThreadConsts& c, FrameSmem s) {
-    stockham_pass_pad<kH, 8, -1>(tid, c.w8, s.a_re, s.a_im, s.b_re, s.b_im);
+    stockham_pass_swz<kH, 8, -1>(tid, c.w8, s.a_re, s.a_im, s.b_re, s.b_im);
 }
 DM_HD void fwd_pass3(int tid, const ThreadConsts& c, FrameSmem s) {
-    stockham_pass_pad<kH, 64, -1>(tid, c.w64, s.b_re, s.b_im, s.a_re, s.a_im);
+    stockham_pass_swz<kH, 64, -1>(tid, c.w64, s.b_re, s.b_im, s.a_re, s.a_im);
 }
 
 // ---- unpack Z (in a_re/a_im, natural order) to the real-FFT spectrum X (-> b) and the per-bin energy (-> a_re) ----
 template <int MODE>
 DM_HD void fwd_unpack(int tid, const cf* w1024, FrameSmem s) {
-    PadLoad Z{s.a_re, s.a_im};
+    SwzLoad Z{s.a_re, s.a_im};
     auto energy = [](cf x) {
         float e = x.x * x.x + x.y * x.y;
         return (MODE == kModeMelDb) ? e : sqrtf(e);
@@ -119,15 +119,15 @@ DM_HD void fwd_unpack(int tid, const cf* w1024, FrameSmem s) {
         if (k == 0) {
             const cf z0 = Z(0), zq = Z(kH / 2);
             const cf x0 = cf{z0.x + z0.y, 0.f}, xh = cf{z0.x - z0.y, 0.f}, xq = cconj(zq);
-            s.b_re[padi(0)] = x0.x;  // slot 0 packs the two real bins
-            s.b_im[padi(0)] = xh.x;
-            s.b_re[padi(kH / 2)] = xq.x;
-            s.b_im[padi(kH / 2)] = xq.y;
-            s.a_re[padi(0)] = energy(x0);
+            s.b_re[swz(0)] = x0.x;  // slot 0 packs the two real bins
+            s.b_im[swz(0)] = xh.x;
+            s.b_re[swz(kH / 2)] = xq.x;
+            s.b_im[swz(kH / 2)] = xq.y;
+            s.a_re[swz(0)] = energy(x0);
             s.aux[0] = energy(xh);
-            s.a_re[padi(kH / 2)] = energy(xq);
+            s.a_re[swz(kH / 2)] = energy(xq);
         } else {
-            const int ak = padi(k), ac = padi(kH - k);
+            const int ak = swz(k), ac = swz(kH - k);
             cf xk, xc;
             rfft_unpack_pair(cf{s.a_re[ak], s.a_im[ak]}, cf{s.a_re[ac], s.a_im[ac]}, w1024[k], xk, xc);
             s.b_re[ak] = xk.x;
@@ -149,7 +149,7 @@ DM_HD float mel_residual(int m, const ThreadConsts& c, const float* melw_t, Fram
     const int k0 = c.mel_k0, n = c.mel_n;
     float acc = 0.f;
 #pragma unroll 4
-    for (int i = 0; i < n; ++i) acc = fmaf(melw_t[i * kMels + m], s.a_re[padi(k0 + i)], acc);  // bin 512 has no weight
+    for (int i = 0; i < n; ++i) acc = fmaf(melw_t[i * kMels + m], s.a_re[swz(k0 + i)], acc);  // bin 512 has no weight
     float val, dval_dmel;  // transformed value and its derivative w.r.t. the mel energy
     if (MODE == kModeMelDb) {
         float c = acc < 1e-10f ? 1e-10f : acc;  // torch.clamp(min=amin): NaN stays NaN
@@ -202,7 +202,7 @@ DM_HD cf xbar_of_bin(int k, const StftTables& t, const FrameSmem& s) {
 
 template <int MODE>
 DM_HD void bwd_pack(int tid, const StftTables& t, FrameSmem s) {
-    PadStore Zb{s.b_re, s.b_im};
+    SwzStore Zb{s.b_re, s.b_im};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int k = tid + 64 * i;  // 0..255
@@ -227,18 +227,18 @@ DM_HD void bwd_pack(int tid, const StftTables& t, FrameSmem s) {
 // ---- inverse FFT: b -> a -> b -> a ; afterwards frame gradient n is a_re[pad(n/2)] (n even) / a_im (n odd) ----
 DM_HD void inv_pass1(int tid, FrameSmem s) {
     cf v[8];
-    load8_pad<kH>(s.b_re, s.b_im, tid, v);
+    load8_swz<kH>(s.b_re, s.b_im, tid, v);
     dft8<+1>(v);
-    store8_pad<kH, 1>(s.a_re, s.a_im, tid, v);
+    store8_swz<kH, 1>(s.a_re, s.a_im, tid, v);
 }
 DM_HD void inv_pass2(int tid, const ThreadConsts& c, FrameSmem s) {
-    stockham_pass_pad<kH, 8, +1>(tid, c.w8, s.a_re, s.a_im, s.b_re, s.b_im);
+    stockham_pass_swz<kH, 8, +1>(tid, c.w8, s.a_re, s.a_im, s.b_re, s.b_im);
 }
 DM_HD void inv_pass3(int tid, const ThreadConsts& c, FrameSmem s) {
-    stockham_pass_pad<kH, 64, +1>(tid, c.w64, s.b_re, s.b_im, s.a_re, s.a_im);
+    stockham_pass_swz<kH, 64, +1>(tid, c.w64, s.b_re, s.b_im, s.a_re, s.a_im);
 }
 DM_HD float frame_grad_sample(const FrameSmem& s, int n) {
-    int p = padi(n >> 1);
+    int p = swz(n >> 1);
     return (n & 1) ? s.a_im[p] : s.a_re[p];
 }
 

@@ -85,10 +85,10 @@ __global__ void __launch_bounds__(kCtaThreads, 3) stft_guidance_kernel(const Stf
     FrameSmem s;
     {
         float* q = grp + g * kFrameSmemFloats;
-        s.a_re = q; q += padded_len(kH);
-        s.a_im = q; q += padded_len(kH);
-        s.b_re = q; q += padded_len(kH);
-        s.b_im = q; q += padded_len(kH);
+        s.a_re = q; q += swz_len(kH);
+        s.a_im = q; q += swz_len(kH);
+        s.b_re = q; q += swz_len(kH);
+        s.b_im = q; q += swz_len(kH);
         s.melbar = q; q += 72;
         s.aux = q;
     }
@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(kCtaThreads, 3) stft_guidance_kernel(const Stf
                 const float* gq = grp + q * kFrameSmemFloats;
                 float* ap = acc + (fr0 + q) * p.hop;
                 for (int h = tid; h < kH; h += kCtaThreads) {
-                    const int pp = padi(h);
-                    const float re = gq[pp], im = gq[padded_len(kH) + pp];
+                    const int pp = swz(h);
+                    const float re = gq[pp], im = gq[swz_len(kH) + pp];
                     if (aligned8) {
                         f2* a2 = reinterpret_cast<f2*>(ap) + h;
                         const f2 w2 = reinterpret_cast<const f2*>(win)[h];

@@ -13,11 +13,11 @@ extern "C" {
 
 // complex FFT of size 512 / 4096 through the Stockham passes (in: interleaved re,im; out likewise)
 void emul_fft(int n, int inverse, const float* tw, const float* in, float* out) {
-    std::vector<float> are(padded_len(n)), aim(padded_len(n)), bre(padded_len(n)), bim(padded_len(n));
+    std::vector<float> are(swz_len(n)), aim(swz_len(n)), bre(swz_len(n)), bim(swz_len(n));
     const cf* t = reinterpret_cast<const cf*>(tw);
-    for (int i = 0; i < n; ++i) { are[padi(i)] = in[2 * i]; aim[padi(i)] = in[2 * i + 1]; }
-    PadLoad la{are.data(), aim.data()}, lb{bre.data(), bim.data()};
-    PadStore sa{are.data(), aim.data()}, sb{bre.data(), bim.data()};
+    for (int i = 0; i < n; ++i) { are[swz(i)] = in[2 * i]; aim[swz(i)] = in[2 * i + 1]; }
+    SwzLoad la{are.data(), aim.data()}, lb{bre.data(), bim.data()};
+    SwzStore sa{are.data(), aim.data()}, sb{bre.data(), bim.data()};
     const float* rr; const float* ri;
     if (n == 512) {
         for (int j = 0; j < 64; ++j) inverse ? stockham_pass<512, 1, 1>(j, t, la, sb) : stockham_pass<512, 1, -1>(j, t, la, sb);
@@ -31,7 +31,7 @@ void emul_fft(int n, int inverse, const float* tw, const float* in, float* out) 
         for (int j = 0; j < 512; ++j) inverse ? stockham_pass<4096, 512, 1>(j, t, lb, sa) : stockham_pass<4096, 512, -1>(j, t, lb, sa);
         rr = are.data(); ri = aim.data();
     }
-    for (int i = 0; i < n; ++i) { out[2 * i] = rr[padi(i)]; out[2 * i + 1] = ri[padi(i)]; }
+    for (int i = 0; i < n; ++i) { out[2 * i] = rr[swz(i)]; out[2 * i + 1] = ri[swz(i)]; }
 }
 
 }  // extern "C"
@@ -52,8 +52,8 @@ static void run(const EmulTables& e, int clamp, const float* y, long long Ly, in
     std::vector<float> buf(kFrameSmemFloats, 0.f), frame(kNfft);
     float* p = buf.data();
     FrameSmem s;
-    s.a_re = p; p += padded_len(kH); s.a_im = p; p += padded_len(kH);
-    s.b_re = p; p += padded_len(kH); s.b_im = p; p += padded_len(kH);
+    s.a_re = p; p += swz_len(kH); s.a_im = p; p += swz_len(kH);
+    s.b_re = p; p += swz_len(kH); s.b_im = p; p += swz_len(kH);
     s.melbar = p; p += 72; s.aux = p;
     if (ypbar) std::memset(ypbar, 0, sizeof(float) * (Ly + 1024));
     std::vector<ThreadConsts> tc(64);
@@ -115,8 +115,8 @@ struct EmulRir {
     RirSmem s;
     EmulRir() : buf(kRirSmemFloats, 0.f) {
         float* p = buf.data();
-        s.a_re = p; p += padded_len(kRirH); s.a_im = p; p += padded_len(kRirH);
-        s.b_re = p; p += padded_len(kRirH); s.b_im = p;
+        s.a_re = p; p += swz_len(kRirH); s.a_im = p; p += swz_len(kRirH);
+        s.b_re = p; p += swz_len(kRirH); s.b_im = p;
     }
 };
 struct SrcX {
@@ -135,7 +135,7 @@ void emul_rir_spectrum(const float* ir, int K, const float* tw4096, const float*
     for (int ph = 0; ph < 4; ++ph)
         for (int tid = 0; tid < kRirThreads; ++tid) rir_block_phase<false>(ph, tid, tw, w, nullptr, e.s, src, st);
     for (int tid = 0; tid < kRirThreads; ++tid)
-        rir_unpack_spectrum(tid, PadLoad{e.s.b_re, e.s.b_im}, w, reinterpret_cast<cf*>(spec));
+        rir_unpack_spectrum(tid, SwzLoad{e.s.b_re, e.s.b_im}, w, reinterpret_cast<cf*>(spec));
 }
 
 void emul_rir_correlate(const float* x, long long L, const float* spec, int K, const float* tw4096,
@@ -224,23 +224,23 @@ void emul_resample_adjoint(const float* ybar, long long Ly, const float* kernel,
 }
 }
 
-// exhaustive check of the closed-form swizzled addresses (fft_core.cuh) against padi() of the logical index
+// exhaustive check of the closed-form swizzled addresses (fft_core.cuh) against swz() of the logical index
 extern "C" int emul_check_swizzle_forms() {
     int bad = 0;
     for (int j = 0; j < 64; ++j)
         for (int r = 0; r < 8; ++r) {
-            bad += ld_addr<512>(padi(j), r) != padi(j + 64 * r);
-            bad += st_addr<512, 1>(st_base<512, 1>(j), r) != padi(8 * j + r);
-            bad += st_addr<512, 8>(st_base<512, 8>(j), r) != padi((j / 8) * 64 + j % 8 + 8 * r);
-            bad += st_addr<512, 64>(st_base<512, 64>(j), r) != padi(j + 64 * r);
+            bad += ld_addr<512>(swz(j), r) != swz(j + 64 * r);
+            bad += st_addr<512, 1>(st_base<512, 1>(j), r) != swz(8 * j + r);
+            bad += st_addr<512, 8>(st_base<512, 8>(j), r) != swz((j / 8) * 64 + j % 8 + 8 * r);
+            bad += st_addr<512, 64>(st_base<512, 64>(j), r) != swz(j + 64 * r);
         }
     for (int j = 0; j < 512; ++j)
         for (int r = 0; r < 8; ++r) {
-            bad += ld_addr<4096>(padi(j), r) != padi(j + 512 * r);
-            bad += st_addr<4096, 1>(st_base<4096, 1>(j), r) != padi(8 * j + r);
-            bad += st_addr<4096, 8>(st_base<4096, 8>(j), r) != padi((j / 8) * 64 + j % 8 + 8 * r);
-            bad += st_addr<4096, 64>(st_base<4096, 64>(j), r) != padi((j / 64) * 512 + j % 64 + 64 * r);
-            bad += st_addr<4096, 512>(st_base<4096, 512>(j), r) != padi(j + 512 * r);
+            bad += ld_addr<4096>(swz(j), r) != swz(j + 512 * r);
+            bad += st_addr<4096, 1>(st_base<4096, 1>(j), r) != swz(8 * j + r);
+            bad += st_addr<4096, 8>(st_base<4096, 8>(j), r) != swz((j / 8) * 64 + j % 8 + 8 * r);
+            bad += st_addr<4096, 64>(st_base<4096, 64>(j), r) != swz((j / 64) * 512 + j % 64 + 64 * r);
+            bad += st_addr<4096, 512>(st_base<4096, 512>(j), r) != swz(j + 512 * r);
         }
     return bad;
 }
