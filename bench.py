@@ -9,8 +9,9 @@ T_mel + loss + VJP kernels -> torch autograd back through the stand-ins -> fused
 Default workload = BASELINE.json configs[1]: super_resolution (scale 2) + DPS, batch 16 x 10 s @ 16 kHz on one B200.
 
   value : clip-steps/s with inputs resident in HBM (CUDA events per step, L2 flushed between steps, max over ranks)
-  e2e   : the same through the public `.step` API with PINNED HOST latents in and prev_sample + loss out, the
-          host<->device copies inside the timed region
+  e2e   : the same through the public API (`HostPipelinedStep` over `GraphedGuidedStep`) with PINNED HOST latents in
+          and prev_sample + per-clip loss out, every host<->device copy inside a timed bracket; the copies of
+          neighbouring steps overlap the step on separate streams (`serial_ms_per_step` = no overlap)
   roofline     : dominant kernel (stft_guidance_kernel), algorithmic bytes / CUDA-event time, vs MEASURED_PEAKS hbm_gbs
   cpu_baseline : the CPU oracle (torch restatement of the reference's scheduler.step) on this box's host cores, on a
                  bounded sample of the same workload
@@ -187,6 +188,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serial-e2e", action="store_true", help="e2e with the copies on the compute stream (no overlap)")
     ap.add_argument("--eager", action="store_true", help="call scheduler.step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -254,6 +256,55 @@ def main():
             loss_pin[: lo.numel()].copy_(lo.reshape(-1), non_blocking=True)
         return out
 
+    def pipelined_region():
+        """e2e through HostPipelinedStep: pinned-host latents in, prev_sample + per-clip loss out, uploads of step i+1
+        and downloads of step i-1 overlapped with step i.  Every copy is issued after the start event of a timed
+        bracket and waited for before the end event of one (the last download gets a bracket of its own)."""
+        xs_pin = [x_pin, x_h.clone().pin_memory()]
+        es_pin = [e_pin, e_h.clone().pin_memory()]
+        prevs_pin = [prev_pin, torch.empty_like(x_h).pin_memory()]
+        losses_pin = [loss_pin, torch.empty(B).pin_memory()]
+
+        def sequence(n, first, timed):
+            pipe = dm.HostPipelinedStep(graphed)
+            brackets = []
+            for i in range(n):
+                if timed:
+                    flush.fill_(float(i))
+                s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                if i == 0:
+                    pipe.prefetch(es_pin[0], xs_pin[0], after=s)
+                if i + 1 < n:
+                    pipe.prefetch(es_pin[(i + 1) % 2], xs_pin[(i + 1) % 2], after=s)
+                pipe.step(ts[(first + i) % len(ts)], prevs_pin[i % 2], losses_pin[i % 2], generator=gens)
+                t.record()
+                brackets.append((s, t))
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            pipe.drain()
+            t.record()
+            brackets.append((s, t))
+            return brackets
+
+        sequence(args.warmup, 0, False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        brackets = sequence(args.steps, args.warmup, True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if not torch.isfinite(prevs_pin[(args.steps - 1) % 2]).all():
+            raise RuntimeError("pipelined e2e produced non-finite latents")
+        total_ms = sum(s.elapsed_time(t) for s, t in brackets)
+        tt = torch.tensor([total_ms], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     def timed_region(host):
         per_step = []
         for i in range(args.warmup):
@@ -285,7 +336,8 @@ def main():
 
     with ClockSampler(local) as clk:
         total_ms, launches = timed_region(host=False)
-        e2e_ms, _ = timed_region(host=True)
+        e2e_serial_ms, _ = timed_region(host=True)
+        e2e_ms = pipelined_region() if (graphed is not None and not args.serial_e2e) else e2e_serial_ms
         # the dominant kernel, timed live with CUDA events on its launching stream inside eager steps (a graph replay
         # has no per-kernel event hooks), L2 flushed before every step as above
         timed_call.on = True
@@ -327,7 +379,10 @@ def main():
                            "l2": "flushed between timed steps (256 MB write)",
                            "networks": "torch stand-ins for vae.decode / vocoder (stay in PyTorch, inside the step)"},
                 "e2e": {"value": e2e_value, "unit": "clip-steps/s", "h2d_bytes_per_step": 2 * x_h.numel() * 4,
-                        "d2h_bytes_per_step": x_h.numel() * 4 + B * 4, "ms_per_step": e2e_ms / args.steps},
+                        "d2h_bytes_per_step": x_h.numel() * 4 + B * 4, "ms_per_step": e2e_ms / args.steps,
+                        "mode": "serial copies" if e2e_ms is e2e_serial_ms else
+                        "HostPipelinedStep: uploads / downloads of neighbouring steps overlap the step (3 streams)",
+                        "serial_ms_per_step": e2e_serial_ms / args.steps},
                 "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

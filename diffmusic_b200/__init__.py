@@ -11,6 +11,6 @@ from .operators import (BaseOperator, IdentityOperator, MusicDereverberationOper
 from .schedulers import (DDIMScheduler, DiffMusicScheduler, DPSScheduler, DSGScheduler,  # noqa: F401
                          InverseProblemSchedulerOutput, MPGDScheduler, get_scheduler)
 
-from .graph import GraphedGuidedStep  # noqa: F401,E402
+from .graph import GraphedGuidedStep, HostPipelinedStep  # noqa: F401,E402
 
 __version__ = "0.1.0"

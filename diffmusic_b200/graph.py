@@ -89,13 +89,13 @@ class GraphedGuidedStep:
             self._ir_host.copy_(ir.reshape(-1))
             self._ir_dev.copy_(self._ir_host, non_blocking=True)
 
-    def __call__(self, model_output, timestep, sample, generator=None, variance_noise=None, **ignored):
+    def __call__(self, model_output, timestep, sample, generator=None, variance_noise=None, _borrow=False, **ignored):
         self.x.copy_(sample, non_blocking=True)
         self.e.copy_(model_output, non_blocking=True)
         self._prepare(int(timestep), generator, variance_noise)
         self.graph.replay()
         o = self.out
-        if not self.clone:
+        if _borrow or not self.clone:
             return o
         return InverseProblemSchedulerOutput(
             prev_sample=o.prev_sample.clone(), pred_original_sample=o.pred_original_sample.clone(),
@@ -113,3 +113,85 @@ _NO_NOISE = _NoNoise()
 def _default_eta(scheduler):
     import inspect
     return inspect.signature(scheduler.step).parameters["eta"].default
+
+
+class HostPipelinedStep:
+    """Guided steps whose latents live in PINNED HOST memory, with the PCIe copies overlapped with the step itself.
+
+    The reference moves one clip at a time between host and device around every call (run.py:286-312).  Here three
+    streams work on consecutive steps at once: an upload stream brings step i+1's `(model_output, sample)` into one of
+    two device staging slots while the captured graph of step i replays on the compute stream, and a download stream
+    returns step i's `prev_sample` and per-clip loss while step i+1 computes.  All ordering is by CUDA events; nothing
+    synchronises with the host until `drain()`.
+
+        pipe = HostPipelinedStep(graphed)
+        pipe.prefetch(e_host[0], x_host[0])
+        for i, t in enumerate(timesteps):
+            if i + 1 < n: pipe.prefetch(e_host[i + 1], x_host[i + 1])
+            pipe.step(t, prev_host[i], loss_host[i])
+        pipe.drain()
+    """
+
+    def __init__(self, graphed: GraphedGuidedStep):
+        self.g = graphed
+        dev = graphed.x.device
+        self.dev = dev
+        self.up, self.down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        mk = lambda: torch.empty_like(graphed.x)  # noqa: E731
+        self.x_st, self.e_st, self.prev_st = [mk(), mk()], [mk(), mk()], [mk(), mk()]
+        self.loss_st = [torch.zeros(graphed.B, device=dev, dtype=torch.float32) for _ in range(2)]
+        ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]  # noqa: E731
+        self.uploaded, self.slot_free, self.computed, self.downloaded = ev(), ev(), ev(), ev()
+        self.n_up = self.n_run = 0
+        self.bytes_up = 2 * graphed.x.numel() * graphed.x.element_size()
+        self.bytes_down = graphed.x.numel() * graphed.x.element_size() + graphed.B * 4
+
+    def prefetch(self, model_output_host, sample_host, after=None):
+        """Queue the upload of the NEXT step's inputs (at most two steps may be in flight).  `after`: an event the
+        upload must not start before (bench.py uses it to keep the copy inside the timed region)."""
+        if self.n_up - self.n_run >= 2:
+            raise RuntimeError("HostPipelinedStep: two uploads already in flight; call step() first")
+        k = self.n_up % 2
+        if after is not None:
+            self.up.wait_event(after)
+        if self.n_up >= 2:
+            self.up.wait_event(self.slot_free[k])  # the step that last used this slot has consumed it
+        with torch.cuda.stream(self.up):
+            self.x_st[k].copy_(sample_host, non_blocking=True)
+            self.e_st[k].copy_(model_output_host, non_blocking=True)
+            self.uploaded[k].record(self.up)
+        self.n_up += 1
+
+    def step(self, timestep, prev_sample_host, loss_host=None, generator=None, variance_noise=None):
+        """Run the step whose inputs were prefetched first; its results land in the given pinned host tensors once
+        `drain()` (or the second-next `step`) has returned."""
+        if self.n_run >= self.n_up:
+            raise RuntimeError("HostPipelinedStep: step() without a prefetched input")
+        k = self.n_run % 2
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.uploaded[k])
+        out = self.g(self.e_st[k], timestep, self.x_st[k], generator=generator, variance_noise=variance_noise,
+                     _borrow=True)
+        self.slot_free[k].record(cur)  # inputs were copied into the graph's static buffers before the replay
+        if self.n_run >= 2:
+            cur.wait_event(self.downloaded[k])  # the staging slot's previous content has reached the host
+        self.prev_st[k].copy_(out.prev_sample, non_blocking=True)
+        if loss_host is not None and out.loss_per_clip is not None:
+            self.loss_st[k].copy_(out.loss_per_clip.reshape(-1), non_blocking=True)
+        self.computed[k].record(cur)
+        self.down.wait_event(self.computed[k])
+        with torch.cuda.stream(self.down):
+            prev_sample_host.copy_(self.prev_st[k], non_blocking=True)
+            if loss_host is not None:
+                loss_host.copy_(self.loss_st[k], non_blocking=True)
+            self.downloaded[k].record(self.down)
+        if self.n_run >= 1:
+            cur.wait_event(self.downloaded[1 - k])  # step i returns only after step i-1's results are on the host
+        self.n_run += 1
+
+    def drain(self):
+        """Make the current stream wait for every queued download (call before reading the host outputs)."""
+        cur = torch.cuda.current_stream(self.dev)
+        for k in range(2):
+            if self.n_run > k:
+                cur.wait_event(self.downloaded[k])

@@ -389,6 +389,43 @@ def test_graphed_step_equals_eager_step(sched_name, op_name, eta):
         xe, xg = a.prev_sample, b.prev_sample  # chain the trajectory
 
 
+def test_host_pipelined_steps_equal_direct_replays():
+    """HostPipelinedStep (pinned-host latents, uploads / downloads overlapped on side streams) returns exactly what the
+    same graph gives for device-resident inputs, for a run long enough to reuse both staging slots several times."""
+    B, n = 3, 7
+    vae, voc = stubs.StubVAE().to(DEV), stubs.StubVocoder().to(DEV)
+    op = _ops()["super_resolution"]
+    sched = dm.get_scheduler("dps")(operator=op, **stubs.MUSICLDM_SCHED)
+    sched.set_timesteps(500)
+    meas = op.forward(stubs.synth_clips(1, L1, first=50).to(DEV))
+    kw = dict(eta=0.0, measurement=meas, vae=vae, vocoder=voc, original_waveform_length=L1, ip_guidance_rate=5e-4,
+              supervised_space="mel_spectrogram")
+    graphed = dm.GraphedGuidedStep(sched, (B, 8, 25, 16), **kw)
+    lat = [stubs.synth_latents(B, 25, first=10 * i) for i in range(n)]
+    ts = [int(t) for t in sched.timesteps[:n]]
+    want = []
+    for (x, e), t in zip(lat, ts):
+        o = graphed(e.to(DEV), t, x.to(DEV))
+        want.append((o.prev_sample.cpu(), o.loss_per_clip.reshape(-1).cpu()))
+    xs = [x.pin_memory() for x, _ in lat]
+    es = [e.pin_memory() for _, e in lat]
+    prev = [torch.empty_like(xs[0]).pin_memory() for _ in range(n)]
+    loss = [torch.empty(B).pin_memory() for _ in range(n)]
+    pipe = dm.HostPipelinedStep(graphed)
+    pipe.prefetch(es[0], xs[0])
+    for i in range(n):
+        if i + 1 < n:
+            pipe.prefetch(es[i + 1], xs[i + 1])
+        pipe.step(ts[i], prev[i], loss[i])
+    with pytest.raises(RuntimeError):
+        pipe.step(ts[0], prev[0], loss[0])  # nothing prefetched
+    pipe.drain()
+    torch.cuda.synchronize()
+    for i in range(n):
+        assert torch.equal(prev[i], want[i][0]), i
+        assert torch.equal(loss[i], want[i][1]), i
+
+
 # ------------------------------------------------------------------------------------------------ update kernels, all paths
 @pytest.mark.parametrize("n_clip", [3200, 32000, 38400, 3203])
 @pytest.mark.parametrize("kind", ["dsg", "diffmusic"])
