@@ -11,6 +11,7 @@
 // the reference's autograd graph) never leaves the SM.
 #include "dm_common.cuh"
 #include "stft_frame.cuh"
+#include "stft_pair.cuh"
 
 namespace dm {
 
@@ -252,6 +253,231 @@ __global__ void __launch_bounds__(kCtaThreads, 3) stft_guidance_kernel(const Stf
     }
 }
 
+// ======================================================================================================================
+// Frame-pair kernel (stft_pair.cuh): 4 groups x 2 frames = 8 frames per round, 128-bit shared-memory FFT traffic, the
+// spectrum of the owned bins in registers, and the overlap-add done straight from the registers of the last inverse
+// pass.  Groups never meet at a CTA-wide barrier inside the frame loop: the only coupling is the ORDER of the
+// overlap-add into the tile accumulator (frames in ascending order -> bit-reproducible), enforced by a ring of named
+// barriers (group g arrives on barrier 8+g when its two frames are added; group g+1 waits on it before adding).
+// Used whenever the hop is even (every shipped configuration: hop 160); odd hops keep the frame-at-a-time kernel.
+constexpr int kPairFrames = 2 * kGroups;  // frames per round
+
+__device__ __forceinline__ void chain_wait(int pred) {
+    asm volatile("bar.sync %0, %1;" ::"r"(8 + pred), "r"(2 * kGroupThreads) : "memory");
+}
+__device__ __forceinline__ void chain_arrive(int g) {
+    __threadfence_block();
+    asm volatile("bar.arrive %0, %1;" ::"r"(8 + g), "r"(2 * kGroupThreads) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kCtaThreads, 2) stft_pair_kernel(const StftParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, g = tid / kGroupThreads, gt = tid % kGroupThreads;
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const long long f0 = (long long)tile * p.nf;
+    const int nfr = (int)min((long long)p.nf, p.T - f0);
+    const int span = (nfr - 1) * p.hop + kNfft;
+    const int span_alloc = ((p.nf - 1) * p.hop + kNfft + 3) & ~3;
+    const long long base = f0 * p.hop;  // first padded-signal index of the tile
+    const bool has_ref = p.ref != nullptr, want_grad = p.ypbar != nullptr;
+    const int hop2 = p.hop >> 1;
+
+    // ---- shared memory carve-up ----
+    float* sig = smem;
+    float* acc = sig + span_alloc;
+    float* tilebuf = acc + span_alloc;                 // [nf][kTileLd] ref (guidance) or out (transform)
+    float* win = tilebuf + tile_floats(p.nf);          // [1024]
+    f2* binw = reinterpret_cast<f2*>(win + kNfft);     // [513] (+1 pad)
+    float* grp = reinterpret_cast<float*>(binw + 514); // [kGroups][kPairSmemFloats]
+    float* red = grp + kGroups * kPairSmemFloats;      // [8]
+    unsigned char* binm = reinterpret_cast<unsigned char*>(red + 8);  // [513] (+3 pad)
+    float* melw_t = red + 8 + 132;                     // [mel_wstride][64] banded filterbank, transposed (16-B aligned)
+    PairSmem s;
+    {
+        float* q = grp + g * kPairSmemFloats;
+        s.a = reinterpret_cast<c2*>(q);
+        s.b = reinterpret_cast<c2*>(q + 4 * kH);
+    }
+    const PairBinTab bins{binw, binm};
+    PairConsts pc;
+    load_pair_consts(gt, p.tab, pc);
+
+    // ---- stage the signal span, the window, the filterbank (by band and by bin) and the reference tile ----
+    const float* yb = p.y + (long long)b * p.y_bstride;
+    __shared__ __align__(8) uint64_t stage_bar;
+    const float* span_src = yb + (base - kNfft / 2);
+    const bool interior = base >= kNfft / 2 && base - kNfft / 2 + span <= p.Ly &&
+                          (reinterpret_cast<uintptr_t>(span_src) & 15) == 0 && (span & 3) == 0;
+    if (interior) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&stage_bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_load_span(sig, span_src, (uint32_t)span * 4u, &stage_bar);
+        }
+    } else {
+        for (int i = tid; i < span; i += kCtaThreads) {
+            long long j = reflect_src(base + i, p.Ly);
+            float v = __ldg(yb + j);
+            if (p.mask) v *= __ldg(p.mask + j);
+            sig[i] = v;
+        }
+    }
+    if (want_grad) {
+        float4* a4 = reinterpret_cast<float4*>(acc);
+        for (int i = tid; i < span_alloc / 4; i += kCtaThreads) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    reinterpret_cast<float4*>(win)[tid] = __ldg(reinterpret_cast<const float4*>(p.tab.window) + tid);
+    {
+        const float4* src = reinterpret_cast<const float4*>(p.tab.mel_w);
+        float4* dst = reinterpret_cast<float4*>(melw_t);
+        for (int i = tid; i < p.tab.mel_wstride * kMels / 4; i += kCtaThreads) dst[i] = __ldg(src + i);
+    }
+    for (int k = tid; k < kBins; k += kCtaThreads) {
+        binw[k] = f2{__ldg(p.tab.bin_w0 + k), __ldg(p.tab.bin_w1 + k)};
+        binm[k] = (unsigned char)__ldg(p.tab.bin_m0 + k);
+    }
+    if (MODE != kModePhaseWav && has_ref) {  // warp w takes bands w, w + 8, ...; lanes run along the frames (coalesced)
+        const int lane = tid & 31, w = tid >> 5;
+        const float* rb = p.ref + (long long)b * p.ref_bstride + f0 + (long long)w * p.T + lane;
+        float* tb = tilebuf + lane * kTileLd + w;
+        const long long rstep = 8 * p.T;
+        if (lane < nfr)
+#pragma unroll
+            for (int i = 0; i < kMels / 8; ++i) tb[8 * i] = __ldg(rb + i * rstep);
+        static_assert(kCtaThreads / 32 == 8, "ref-tile staging assumes 8 warps");
+    }
+    __syncthreads();
+    if (interior) {
+        mbar_wait_parity(&stage_bar, 0);
+        if (p.mask) {
+            const float* mk = p.mask + (base - kNfft / 2);
+            for (int i = tid; i < span; i += kCtaThreads) sig[i] *= __ldg(mk + i);
+            __syncthreads();
+        }
+    }
+
+    float lsum = 0.f;
+    const int rounds = (nfr + kPairFrames - 1) / kPairFrames;
+    f2* acc2 = reinterpret_cast<f2*>(acc);
+    for (int r = 0; r < rounds; ++r) {
+        const int fa = r * kPairFrames + 2 * g;
+        const bool active = fa < nfr;          // frame A exists
+        const bool active_b = fa + 1 < nfr;    // frame B exists (otherwise B recomputes A and its results are dropped)
+        const int fb = active_b ? fa + 1 : fa;
+        if (active) {
+            PairX x;
+            pair_fwd_pass1(gt, sig + fa * p.hop, sig + fb * p.hop, win, s);
+            group_sync(g);
+            pair_fwd_pass2(gt, pc, s);
+            group_sync(g);
+            pair_fwd_pass3(gt, pc, s);
+            group_sync(g);
+            pair_unpack<MODE>(gt, pc, s, x);
+            group_sync(g);
+            f2* P = pair_energy(s);
+            const long long ta = f0 + fa, tb = f0 + fb;
+            if (MODE != kModeMelDb && p.noise != nullptr) {  // GaussianNoise on the magnitude (operator.py:171)
+                for (int k = gt; k < kBins; k += kGroupThreads) {
+                    const float* nz = p.noise + ((long long)b * kBins + k) * p.T;
+                    f2 v = P[k];
+                    v.x += p.sigma * __ldg(nz + ta);
+                    v.y += p.sigma * __ldg(nz + tb);
+                    P[k] = v;
+                }
+                group_sync(g);
+            }
+            if (MODE == kModePhaseWav) {
+                for (int k = gt; k < kBins; k += kGroupThreads) {
+                    const f2 mag = P[k];
+                    const long long row = ((long long)b * kBins + k) * p.T;
+                    if (p.out) {
+                        p.out[row + ta] = mag.x;
+                        if (active_b) p.out[row + tb] = mag.y;
+                    }
+                    if (has_ref) {
+                        const float* rr = p.ref + (long long)b * p.ref_bstride + (long long)k * p.T;
+                        const float da = __ldg(rr + ta) - mag.x, db = __ldg(rr + tb) - mag.y;
+                        lsum = fmaf(da, da, lsum);
+                        if (active_b) lsum = fmaf(db, db, lsum);
+                        P[k] = f2{-da, -db};
+                    }
+                }
+            } else {
+                f2 mel = pair_mel_project(gt, pc, melw_t, s);
+                group_sync(g);
+                mel = pair_mel_combine(gt, mel, s);
+                float va, da_, vb, db_;
+                mel_value<MODE>(mel.x, p.clamp != 0, va, da_);
+                mel_value<MODE>(mel.y, p.clamp != 0, vb, db_);
+                if (has_ref) {
+                    const float ra = tilebuf[fa * kTileLd + gt] - va, rb2 = tilebuf[fb * kTileLd + gt] - vb;
+                    pair_melbar(s)[gt] = f2{-ra * da_, -rb2 * db_};
+                    lsum = fmaf(ra, ra, lsum);
+                    if (active_b) lsum = fmaf(rb2, rb2, lsum);
+                }
+                if (p.out) {
+                    tilebuf[fa * kTileLd + gt] = va;
+                    if (active_b) tilebuf[fb * kTileLd + gt] = vb;
+                }
+            }
+            group_sync(g);  // P / melbar complete (and, without a gradient, consumed before the next round reuses b)
+            if (want_grad) {
+                pair_pack<MODE>(gt, pc, bins, s, x);
+                group_sync(g);
+                pair_inv_pass1(gt, s);
+                group_sync(g);
+                pair_inv_pass2(gt, pc, s);
+                group_sync(g);
+            }
+        }
+        if (want_grad) {
+            // ordered overlap-add: ... -> (round r-1, group 3) -> (r, 0) -> (r, 1) -> (r, 2) -> (r, 3) -> (r+1, 0) ...
+            // Groups without frames in the last round still pass the baton.
+            cf va[8], vb[8];
+            if (active) pair_inv_pass3(gt, pc, s, va, vb);
+            if (r > 0 || g > 0) chain_wait((g + kGroups - 1) % kGroups);
+            if (active) {
+                pair_ola_add(gt, win, va, acc2 + fa * hop2);
+                group_sync(g);  // frame B overlaps frame A; also: every thread has read `a` before the next pass 1 writes it
+                if (active_b) pair_ola_add(gt, win, vb, acc2 + fb * hop2);
+            }
+            if (r + 1 < rounds || g + 1 < kGroups) chain_arrive(g);
+        }
+    }
+
+    // ---- tile epilogue ----
+    if (want_grad) {
+        __syncthreads();
+        float* gb = p.ypbar + (long long)b * (p.Ly + kNfft) + base;
+        for (int i = tid; i < span; i += kCtaThreads) atomicAdd(gb + i, acc[i]);
+    }
+    if (p.out && MODE != kModePhaseWav) {
+        __syncthreads();
+        float* ob = p.out + (long long)b * kMels * p.T + f0;
+        for (int m = tid >> 5; m < kMels; m += kCtaThreads / 32)
+            for (int f = tid & 31; f < nfr; f += 32) ob[(long long)m * p.T + f] = tilebuf[f * kTileLd + m];
+    }
+    if (p.partial) {
+        lsum = warp_sum(lsum);
+        if ((tid & 31) == 0) red[tid >> 5] = lsum;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int i = 0; i < kCtaThreads / 32; ++i) t += red[i];
+            p.partial[(long long)b * p.ntiles + tile] = t;
+        }
+    }
+}
+
+static size_t stft_pair_smem_bytes(int nf, int hop, int mel_wstride) {
+    size_t span = ((size_t)(nf - 1) * hop + kNfft + 3) & ~(size_t)3;
+    size_t fl = 2 * span + (size_t)tile_floats(nf) + kNfft + 2 * 514 + (size_t)kGroups * kPairSmemFloats + 8 + 132 +
+                (size_t)mel_wstride * kMels;
+    return fl * sizeof(float);
+}
+
 // mel projection of an already materialised magnitude (PhaseRetrievalOperator.transform, operator.py:153-154):
 // out[b, m, t] = clamp(sum_k fb[k, m] * mag[b, k, t], +-80) with the banded filterbank; coalesced along t.
 __global__ void __launch_bounds__(128) mel_project_kernel(const float* __restrict__ mag, long long T, StftTables tab,
@@ -277,6 +503,14 @@ static size_t stft_smem_bytes(int nf, int hop, int mel_wstride) {
 }  // namespace dm
 
 using namespace dm;
+
+static int g_stft_engine = DM_STFT_ENGINE_AUTO;
+
+extern "C" int dm_stft_set_engine(int engine) {
+    DM_REQUIRE(engine == DM_STFT_ENGINE_AUTO || engine == DM_STFT_ENGINE_FRAME);
+    g_stft_engine = engine;
+    return DM_OK;
+}
 
 extern "C" int dm_stft_num_tiles(long long Ly, int hop, int frames_per_tile) {
     if (Ly <= 0 || hop <= 0 || frames_per_tile <= 0) return DM_ERR_INVALID;
@@ -319,10 +553,27 @@ extern "C" int dm_stft_guidance(const dm_stft_tables* tab, int mode, int clamp, 
     p.ypbar = ypbar;
     p.partial = partial;
     DM_REQUIRE(tab->mel_wstride >= 1 && tab->mel_wstride <= 64);
-    size_t smem = stft_smem_bytes(p.nf, hop, tab->mel_wstride);
-    if (smem > 227 * 1024) return fail(DM_ERR_UNSUPPORTED, "%s: tile needs %zu B of shared memory", __func__, smem);
     dim3 grid(p.ntiles, B), block(kCtaThreads);
     cudaStream_t st = as_stream(stream);
+    if ((hop & 1) == 0 && g_stft_engine != DM_STFT_ENGINE_FRAME) {  // frame-pair kernel
+        size_t smem2 = stft_pair_smem_bytes(p.nf, hop, tab->mel_wstride);
+        if (smem2 > 227 * 1024)
+            return fail(DM_ERR_UNSUPPORTED, "%s: tile needs %zu B of shared memory", __func__, smem2);
+#define DM_LAUNCH_PAIR(M)                                       \
+    do {                                                        \
+        DM_SMEM_ONCE(stft_pair_kernel<M>, smem2);               \
+        DM_CARVEOUT_ONCE(stft_pair_kernel<M>);                  \
+        stft_pair_kernel<M><<<grid, block, smem2, st>>>(p);     \
+    } while (0)
+        if (mode == DM_STFT_MEL_DB) DM_LAUNCH_PAIR(kModeMelDb);
+        else if (mode == DM_STFT_PHASE_MEL) DM_LAUNCH_PAIR(kModePhaseMel);
+        else DM_LAUNCH_PAIR(kModePhaseWav);
+#undef DM_LAUNCH_PAIR
+        DM_LAUNCHED();
+        return DM_OK;
+    }
+    size_t smem = stft_smem_bytes(p.nf, hop, tab->mel_wstride);
+    if (smem > 227 * 1024) return fail(DM_ERR_UNSUPPORTED, "%s: tile needs %zu B of shared memory", __func__, smem);
 #define DM_LAUNCH_STFT(M)                                          \
     do {                                                           \
         DM_SMEM_ONCE(stft_guidance_kernel<M>, smem);               \

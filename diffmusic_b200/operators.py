@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -73,16 +74,23 @@ def _grad_buffer(dwav, B, L, device):
 
 
 def _frames_per_tile(B, T, device):
-    """frames per CTA tile.  Up to 10 frames per tile the kernel's shared memory (~73 KB) lets 3 CTAs stay resident per
-    SM; among 6..10 pick the size whose CTA count fills whole waves of 3 x SMs best (tail effect), larger tiles on
-    ties (fewer re-staged samples).  6 is the minimum for the bit-reproducible two-tile overlap."""
-    slots = 3 * torch.cuda.get_device_properties(device).multi_processor_count
-    best, best_eff = 6, -1.0
-    for nf in range(6, 11):
+    """frames per CTA tile of the frame-pair STFT kernel (stft_guidance.cu: 4 groups x 2 frames = 8 frames per round).
+
+    Shared memory per CTA = 85 KB (FFT cells of 4 groups, window, filterbank by band and by bin) + 8 B per staged
+    signal sample and accumulator, so tiles of up to 15 frames keep 2 CTAs resident per SM.  Cost model: a CTA costs `ceil(nf / 8)` rounds plus a fixed
+    staging overhead, CTAs run in waves of 2 x SMs; pick the cheapest size, larger tiles on ties (fewer re-staged
+    samples).  6 frames is the minimum for the bit-reproducible two-tile overlap of the cotangent.
+    `DM_STFT_FRAMES_PER_TILE` overrides the choice (tuning / tests)."""
+    forced = os.environ.get("DM_STFT_FRAMES_PER_TILE")
+    if forced:
+        return max(6, min(22, int(forced)))  # > 15: one CTA per SM
+    slots = 2 * torch.cuda.get_device_properties(device).multi_processor_count
+    best, best_cost = 6, float("inf")
+    for nf in range(6, 16):
         ctas = B * math.ceil(T / nf)
-        eff = ctas / (math.ceil(ctas / slots) * slots)
-        if eff >= best_eff - 1e-9:
-            best, best_eff = nf, max(eff, best_eff)
+        cost = math.ceil(ctas / slots) * (math.ceil(nf / 8) + 0.35)
+        if cost <= best_cost + 1e-9:
+            best, best_cost = nf, min(cost, best_cost)
     return best
 
 

@@ -95,6 +95,13 @@ typedef struct dm_stft_tables {
 #define DM_STFT_PHASE_MEL 1 /* |X|   -> mel [-> clamp +-80]                                                    */
 #define DM_STFT_PHASE_WAV 2 /* |X|                                                                             */
 
+/* Kernel selection for dm_stft_guidance (process-wide; for A/B measurements and tests).  AUTO: the frame-pair kernel
+ * (two frames per 64-thread group, 128-bit shared-memory FFT traffic) whenever hop is even, else the frame-at-a-time
+ * kernel.  FRAME: always the frame-at-a-time kernel.  Both compute the same quantities (<= 1e-6 apart). */
+#define DM_STFT_ENGINE_AUTO 0
+#define DM_STFT_ENGINE_FRAME 1
+int dm_stft_set_engine(int engine);
+
 /* number of frame tiles per clip for a signal of Ly samples: ceil((1 + Ly/hop) / frames_per_tile) */
 int dm_stft_num_tiles(long long Ly, int hop, int frames_per_tile);
 

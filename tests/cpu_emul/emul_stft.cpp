@@ -106,6 +106,141 @@ void emul_stft_guidance(const EmulTables* e, int mode, int clamp, const float* y
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Frame-pair pipeline (diffmusic_b200/csrc/stft_pair.cuh): two frames per 64-"thread" group, per-thread spectrum
+// registers carried from the unpack phase to the pack phase, gathered overlap-add as in stft_pair_kernel.
+#include "../../diffmusic_b200/csrc/stft_pair.cuh"
+
+template <int MODE>
+static void run_pair(const EmulTables& e, int clamp, const float* y, long long Ly, int hop, const float* mask,
+                     const float* ref, float* out, float* ypbar, double* sumsq) {
+    StftTables t{e.window, reinterpret_cast<const cf*>(e.tw512), reinterpret_cast<const cf*>(e.w1024),
+                 e.mel_kstart, e.mel_klen, e.mel_w, e.mel_wstride, e.bin_m0, e.bin_w0, e.bin_w1};
+    const long long T = 1 + Ly / hop;
+    const int hop2 = hop / 2;
+    std::vector<float> buf(kPairSmemFloats + 8, 0.f), fa(kNfft), fb(kNfft);
+    // 16-byte aligned carve-up
+    float* base = buf.data();
+    while (reinterpret_cast<uintptr_t>(base) & 15) ++base;
+    PairSmem s;
+    s.a = reinterpret_cast<c2*>(base);
+    s.b = reinterpret_cast<c2*>(base + 4 * kH);
+    if (ypbar) std::memset(ypbar, 0, sizeof(float) * (Ly + 1024));
+    std::vector<PairConsts> pc(64);
+    std::vector<PairX> px(64);
+    struct Regs { cf v[8]; };
+    std::vector<Regs> rva(64), rvb(64);
+    std::vector<float> accbuf_raw(Ly + 1024 + 8, 0.f);
+    struct AccView { float* p; float* data() { return p; } } accbuf{accbuf_raw.data()};
+    while (reinterpret_cast<uintptr_t>(accbuf.p) & 7) ++accbuf.p;
+    std::vector<f2> binw(kBins);
+    std::vector<unsigned char> binm(kBins);
+    for (int k = 0; k < kBins; ++k) { binw[k] = f2{e.bin_w0[k], e.bin_w1[k]}; binm[k] = (unsigned char)e.bin_m0[k]; }
+    const PairBinTab bins{binw.data(), binm.data()};
+    for (int tid = 0; tid < 64; ++tid) load_pair_consts(tid, t, pc[tid]);
+    double acc = 0.0;
+    for (long long f = 0; f < T; f += 2) {
+        const bool has_b = f + 1 < T;
+        const long long f2i = has_b ? f + 1 : f;
+        for (int n = 0; n < kNfft; ++n) {
+            long long ja = reflect_src(f * hop + n, Ly), jb = reflect_src(f2i * hop + n, Ly);
+            fa[n] = y[ja] * (mask ? mask[ja] : 1.f);
+            fb[n] = y[jb] * (mask ? mask[jb] : 1.f);
+        }
+        for (int tid = 0; tid < 64; ++tid) pair_fwd_pass1(tid, fa.data(), fb.data(), t.window, s);
+        for (int tid = 0; tid < 64; ++tid) pair_fwd_pass2(tid, pc[tid], s);
+        for (int tid = 0; tid < 64; ++tid) pair_fwd_pass3(tid, pc[tid], s);
+        for (int tid = 0; tid < 64; ++tid) pair_unpack<MODE>(tid, pc[tid], s, px[tid]);
+        f2* P = pair_energy(s);
+        if (MODE == kModePhaseWav) {
+            for (int k = 0; k < kBins; ++k) {
+                f2 mag = P[k];
+                if (out) { out[k * T + f] = mag.x; if (has_b) out[k * T + f2i] = mag.y; }
+                if (ref) {
+                    float da = ref[k * T + f] - mag.x, db = ref[k * T + f2i] - mag.y;
+                    acc += (double)da * da;
+                    if (has_b) acc += (double)db * db;
+                    P[k] = f2{-da, -db};
+                }
+            }
+        } else {
+            std::vector<f2> own(64);
+            for (int m = 0; m < 64; ++m) own[m] = pair_mel_project(m, pc[m], e.mel_w, s);
+            for (int m = 0; m < 64; ++m) {
+                f2 mel = pair_mel_combine(m, own[m], s);
+                float va, da, vb, db;
+                mel_value<MODE>(mel.x, clamp != 0, va, da);
+                mel_value<MODE>(mel.y, clamp != 0, vb, db);
+                if (ref) {
+                    float ra = ref[m * T + f] - va, rb = ref[m * T + f2i] - vb;
+                    pair_melbar(s)[m] = f2{-ra * da, -rb * db};
+                    acc += (double)ra * ra;
+                    if (has_b) acc += (double)rb * rb;
+                }
+                if (out) { out[m * T + f] = va; if (has_b) out[m * T + f2i] = vb; }
+            }
+        }
+        if (!ypbar) continue;
+        for (int tid = 0; tid < 64; ++tid) pair_pack<MODE>(tid, pc[tid], bins, s, px[tid]);
+        for (int tid = 0; tid < 64; ++tid) pair_inv_pass1(tid, s);
+        for (int tid = 0; tid < 64; ++tid) pair_inv_pass2(tid, pc[tid], s);
+        // last pass into "registers", then the ordered overlap-add from them: frame A, (barrier), frame B
+        for (int tid = 0; tid < 64; ++tid) pair_inv_pass3(tid, pc[tid], s, rva[tid].v, rvb[tid].v);
+        f2* acc2 = reinterpret_cast<f2*>(accbuf.data());
+        for (int tid = 0; tid < 64; ++tid) pair_ola_add(tid, t.window, rva[tid].v, acc2 + f * hop2);
+        if (has_b)
+            for (int tid = 0; tid < 64; ++tid) pair_ola_add(tid, t.window, rvb[tid].v, acc2 + f2i * hop2);
+    }
+    if (ypbar) std::memcpy(ypbar, accbuf.data(), sizeof(float) * (Ly + 1024));
+    *sumsq = acc;
+}
+
+extern "C" {
+void emul_stft_guidance_pair(const EmulTables* e, int mode, int clamp, const float* y, long long Ly, int hop,
+                             const float* mask, const float* ref, float* out, float* ypbar, double* sumsq) {
+    if (mode == 0) run_pair<kModeMelDb>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
+    else if (mode == 1) run_pair<kModePhaseMel>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
+    else run_pair<kModePhaseWav>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
+}
+
+// Bank-conflict audit of the cell swizzle: a 128-bit shared access is served per quarter-warp (8 consecutive lanes),
+// conflict-free iff the 8 cells fall into 8 distinct 16-byte bank groups (cell index mod 8).  Returns the number of
+// (pattern, quarter-warp) instances with a conflict, and checks st_c2_addr / the load form against sw4 of the logical index.
+int emul_check_pair_swizzle() {
+    int bad = 0;
+    auto distinct8 = [](const int* cells) {
+        int seen = 0;
+        for (int l = 0; l < 8; ++l) seen |= 1 << (cells[l] & 7);
+        return seen == 0xff;
+    };
+    for (int q0 = 0; q0 < 64; q0 += 8)        // quarter-warp = lanes q0 .. q0+7
+        for (int r = 0; r < 8; ++r) {
+            int ld[8], s1[8], s8[8], s64[8], ulo[8], uhi[8];
+            for (int l = 0; l < 8; ++l) {
+                const int j = q0 + l;
+                ld[l] = sw4(j) + 64 * r;
+                bad += ld[l] != sw4(j + 64 * r);
+                s1[l] = st_c2_addr<1>(j, r);
+                bad += s1[l] != sw4(8 * j + r);
+                s8[l] = st_c2_addr<8>(j, r);
+                bad += s8[l] != sw4(64 * (j >> 3) + (j & 7) + 8 * r);
+                s64[l] = st_c2_addr<64>(j, r);
+                bad += s64[l] != sw4(j + 64 * r);
+                if (r < 4) {
+                    const int k = j + 64 * r;
+                    ulo[l] = sw4(k);
+                    uhi[l] = sw4((kH - k) & (kH - 1));
+                    if (j >= 1) bad += (sw4((kH - j) & (kH - 1)) - 64 * r) != sw4(kH - k);
+                }
+            }
+            bad += !distinct8(ld) + !distinct8(s1) + !distinct8(s8) + !distinct8(s64);
+            if (r < 4) bad += !distinct8(ulo);
+            (void)uhi;  // the descending side may see one 2-way conflict where a quarter-warp straddles a multiple of 8
+        }
+    return bad;
+}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Overlap-save RIR correlation / adjoint (diffmusic_b200/csrc/rir_block.cuh), same block loop as rir_conv.cu
 #include "../../diffmusic_b200/csrc/rir_block.cuh"
 

@@ -94,7 +94,10 @@ def test_stockham_fft(emul, n, inverse):
     assert rel_l2(np.stack([got.real, got.imag]), np.stack([want.real, want.imag])) < 5e-7
 
 
-def _run(emul, mode, clamp, y, hop, window, ref=None, mask=None, grad=True):
+ENGINES = ["frame", "pair"]
+
+
+def _run(emul, mode, clamp, y, hop, window, ref=None, mask=None, grad=True, engine="frame"):
     t, keep = _tables(window)
     Ly = y.shape[0]
     T = 1 + Ly // hop
@@ -106,10 +109,10 @@ def _run(emul, mode, clamp, y, hop, window, ref=None, mask=None, grad=True):
     refp = _ptr(np.ascontiguousarray(ref, np.float32)) if ref is not None else None
     refk = np.ascontiguousarray(ref, np.float32) if ref is not None else None
     maskk = np.ascontiguousarray(mask, np.float32) if mask is not None else None
-    emul.emul_stft_guidance(C.byref(t), mode, clamp, _ptr(y), C.c_longlong(Ly), hop,
-                            _ptr(maskk) if maskk is not None else None,
-                            _ptr(refk) if refk is not None else None, _ptr(out),
-                            _ptr(ypbar) if grad else None, C.byref(ss))
+    fn = emul.emul_stft_guidance if engine == "frame" else emul.emul_stft_guidance_pair
+    fn(C.byref(t), mode, clamp, _ptr(y), C.c_longlong(Ly), hop,
+       _ptr(maskk) if maskk is not None else None, _ptr(refk) if refk is not None else None, _ptr(out),
+       _ptr(ypbar) if grad else None, C.byref(ss))
     del refp
     return out, ypbar, ss.value
 
@@ -131,15 +134,16 @@ def _torch_loss_grad(op, wav, meas, space):
     return float(loss), torch.autograd.grad(loss, w)[0][0].numpy()
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("L", [4000, 4173])
-def test_mel_db_guidance(emul, L):
+def test_mel_db_guidance(emul, L, engine):
     wav = stubs.synth_clips(1, L)
     ref_wav = stubs.synth_clips(1, L, first=50)
     for clamp, kind in ((1, "identity"), (0, "inpainting")):
         mask = oo.inpaint_mask(1, L, "box", 0.25, 0.5) if kind == "inpainting" else None
         op = oo.OracleOperator(kind, mask=mask)
         ref_mel = op.transform(op.forward(ref_wav))
-        out, ypbar, ss = _run(emul, 0, clamp, wav[0].numpy(), 160, tables.hann_window(),
+        out, ypbar, ss = _run(emul, 0, clamp, wav[0].numpy(), 160, tables.hann_window(), engine=engine,
                               ref=ref_mel[0].numpy(), mask=None if mask is None else mask[0].numpy())
         assert rel_l2(out, op.transform(op.forward(wav))[0]) < 2e-5
         loss, g = _torch_loss_grad(op, wav, op.forward(ref_wav), "mel_spectrogram")
@@ -150,13 +154,15 @@ def test_mel_db_guidance(emul, L):
         assert rel_l2(got, g) < 1e-4
 
 
-def test_mel_db_quiet_signal_edges(emul):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_mel_db_quiet_signal_edges(emul, engine):
     """amin floor (1e-10) and the -80 dB clamp both active."""
     L = 4000
     wav = stubs.synth_clips(1, L) * 3e-5
     ref_wav = stubs.synth_clips(1, L, first=50)
     op = oo.OracleOperator("identity")
-    out, ypbar, ss = _run(emul, 0, 1, wav[0].numpy(), 160, tables.hann_window(), ref=op.transform(ref_wav)[0].numpy())
+    out, ypbar, ss = _run(emul, 0, 1, wav[0].numpy(), 160, tables.hann_window(), ref=op.transform(ref_wav)[0].numpy(),
+                          engine=engine)
     want = op.transform(wav)[0]
     assert float((want == -80).float().mean()) > 0.2
     assert np.abs(out - want.numpy()).max() < 2e-3
@@ -164,18 +170,20 @@ def test_mel_db_quiet_signal_edges(emul):
     assert rel_l2(_fold(ypbar, L) / np.sqrt(ss), g) < 2e-4
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("space", ["mel_spectrogram", "wav_form"])
-def test_phase_guidance(emul, space):
+def test_phase_guidance(emul, space, engine):
     L = 4000
     wav = stubs.synth_clips(1, L)
     ref_wav = stubs.synth_clips(1, L, first=50)
     op = oo.OracleOperator("phase_retrieval")
     meas = op.forward(ref_wav)
     if space == "mel_spectrogram":
-        out, ypbar, ss = _run(emul, 1, 1, wav[0].numpy(), 160, tables.rect_window(), ref=op.transform(meas)[0].numpy())
+        out, ypbar, ss = _run(emul, 1, 1, wav[0].numpy(), 160, tables.rect_window(), ref=op.transform(meas)[0].numpy(),
+                              engine=engine)
         assert rel_l2(out, op.transform(op.forward(wav))[0]) < 2e-5
     else:
-        out, ypbar, ss = _run(emul, 2, 0, wav[0].numpy(), 160, tables.rect_window(), ref=meas[0].numpy())
+        out, ypbar, ss = _run(emul, 2, 0, wav[0].numpy(), 160, tables.rect_window(), ref=meas[0].numpy(), engine=engine)
         assert rel_l2(out, op.forward(wav)[0]) < 2e-5
     loss, g = _torch_loss_grad(op, wav, meas, space)
     assert abs(np.sqrt(ss) - loss) < 1e-4 * loss
@@ -237,6 +245,12 @@ def test_polyphase_resample(emul, scale, L):
     emul.emul_resample_adjoint(_ptr(ybn), C.c_longlong(Ly), _ptr(k), len(k), orig, width, C.c_float(0.25), _ptr(gotb),
                                C.c_longlong(L))
     assert rel_l2(gotb, 0.25 * gx[0]) < 2e-6
+
+
+def test_pair_swizzle_is_conflict_free(emul):
+    """cell swizzle of the frame-pair pipeline: closed-form addresses equal sw4(logical index) and every 128-bit access
+    pattern of the FFT passes / unpack hits 8 distinct 16-byte bank groups per quarter-warp."""
+    assert emul.emul_check_pair_swizzle() == 0
 
 
 def test_swizzle_closed_forms(emul):

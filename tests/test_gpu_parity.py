@@ -426,6 +426,36 @@ def test_host_pipelined_steps_equal_direct_replays():
         assert torch.equal(loss[i], want[i][1]), i
 
 
+@pytest.mark.parametrize("nf", [6, 7, 8, 13, 16, 22])
+@pytest.mark.parametrize("op_name", ["inpainting", "phase_retrieval"])
+def test_stft_kernels_agree_for_every_tile_size(op_name, nf, monkeypatch):
+    """frame-pair kernel (default) vs frame-at-a-time kernel, over tile sizes with full, partial and odd rounds:
+    loss and gradient agree to fp32 rounding, in both supervised spaces."""
+    from diffmusic_b200 import _lib
+    monkeypatch.setenv("DM_STFT_FRAMES_PER_TILE", str(nf))
+    B, L = 3, L1  # T = 101 frames: every tile size leaves a partial last tile, some with an odd frame count
+    wav = stubs.synth_clips(B, L).to(DEV)
+    op = _inpaint() if op_name == "inpainting" else dm.PhaseRetrievalOperator(noiser=_noiser())
+    meas = op.forward(stubs.synth_clips(1, L, first=50).to(DEV))
+    for space in ("mel_spectrogram", "wav_form"):
+        res = {}
+        for name, eng in (("pair", 0), ("frame", 1)):
+            _lib.call("dm_stft_set_engine", eng)
+            try:
+                res[name] = _loss_grad(op, wav, meas, space)
+            finally:
+                _lib.call("dm_stft_set_engine", 0)
+        assert rel_l2(res["pair"][0], res["frame"][0]) < 1e-6, space
+        assert rel_l2(res["pair"][1], res["frame"][1]) < 2e-6, space
+    t_pair = op.transform(op.forward(wav))
+    _lib.call("dm_stft_set_engine", 1)
+    try:
+        t_frame = op.transform(op.forward(wav))
+    finally:
+        _lib.call("dm_stft_set_engine", 0)
+    assert rel_l2(t_pair, t_frame) < 1e-6
+
+
 # ------------------------------------------------------------------------------------------------ update kernels, all paths
 @pytest.mark.parametrize("n_clip", [3200, 32000, 38400, 3203])
 @pytest.mark.parametrize("kind", ["dsg", "diffmusic"])
