@@ -51,6 +51,10 @@ _SIGNATURES = {
     "dm_fad_moments": (c_i, [c_p, c_ll, c_i, c_p, c_p]),
     "dm_fad_moments_ex": (c_i, [c_p, c_ll, c_i, c_p, c_i, c_p]),
     "dm_fad_finalize": (c_i, [c_p, c_i, c_p, c_p, c_p]),
+    "dm_fad_gather_rows": (c_i, [c_p, c_ll, c_i, c_p, c_ll, c_p, c_p]),
+    "dm_sym_eig_jacobi": (c_i, [c_p, c_i, c_i, C.c_double, c_p, c_p, c_p]),
+    "dm_frechet_workspace_doubles": (c_ll, [c_i]),
+    "dm_frechet_distance": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, C.c_double, c_p, c_p, c_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

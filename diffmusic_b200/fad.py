@@ -83,3 +83,94 @@ def calculate_embd_statistics_online(arrays, group=None):
     mom.all_reduce(group)
     mu, cov = mom.finalize()
     return mu.cpu().numpy(), cov.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Frechet distance and FAD-inf (fadtk/fad.py:50-119, 303-350)
+JACOBI_MAX_SWEEPS = 30
+JACOBI_TOL = 1e-14
+
+
+def _as_dev_f64(a, device):
+    return torch.as_tensor(a).to(device=device, dtype=torch.float64).contiguous()
+
+
+def frechet_distance_device(mu1, cov1, mu2, cov2):
+    """Device tensors in, (4,) float64 device tensor out: [d^2, tr sqrt(C1 C2), sweeps of the two Jacobi solves].
+    No host synchronisation (dm_frechet_distance)."""
+    _lib.require_cuda(mu1, cov1, mu2, cov2)
+    d = mu1.numel()
+    if mu2.numel() != d:
+        raise AssertionError(f"Training and test mean vectors have different lengths ({tuple(mu1.shape)} vs "
+                             f"{tuple(mu2.shape)})")
+    if tuple(cov1.shape) != (d, d) or tuple(cov2.shape) != (d, d):
+        raise AssertionError(f"Training and test covariances have different dimensions ({tuple(cov1.shape)} vs "
+                             f"{tuple(cov2.shape)})")
+    work = torch.empty(int(_lib.load().dm_frechet_workspace_doubles(d)), device=mu1.device, dtype=torch.float64)
+    out = torch.empty(4, device=mu1.device, dtype=torch.float64)
+    _lib.call("dm_frechet_distance", mu1.data_ptr(), cov1.data_ptr(), mu2.data_ptr(), cov2.data_ptr(), d,
+              JACOBI_MAX_SWEEPS, JACOBI_TOL, work.data_ptr(), out.data_ptr(), _lib.stream())
+    return out
+
+
+def calc_frechet_distance(mu1, cov1, mu2, cov2, eps=1e-6):
+    """fadtk/fad.py:50-119 on the GPU.  Same value as the reference's eigenvalue method (sum of sqrt of eig(C1 C2)),
+    obtained from two symmetric Jacobi eigen-solves (csrc/fad_frechet.cu); `eps` is accepted for signature parity -- the
+    symmetric formulation has no singular-product failure mode to patch."""
+    import numpy as np
+    mu1, mu2 = np.atleast_1d(mu1), np.atleast_1d(mu2)
+    cov1, cov2 = np.atleast_2d(cov1), np.atleast_2d(cov2)
+    assert mu1.shape == mu2.shape, \
+        f'Training and test mean vectors have different lengths ({mu1.shape} vs {mu2.shape})'
+    assert cov1.shape == cov2.shape, \
+        f'Training and test covariances have different dimensions ({cov1.shape} vs {cov2.shape})'
+    if not torch.cuda.is_available():
+        raise _lib.DiffMusicB200Error("dm_frechet_distance needs CUDA (no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = frechet_distance_device(_as_dev_f64(mu1, dev), _as_dev_f64(cov1, dev), _as_dev_f64(mu2, dev),
+                                  _as_dev_f64(cov2, dev))
+    return float(out[0].item())
+
+
+class FADInfResults(tuple):
+    """(score, slope, r2, points) -- fadtk/fad.py:34-38."""
+    __slots__ = ()
+    _fields = ("score", "slope", "r2", "points")
+
+    def __new__(cls, score, slope, r2, points):
+        return tuple.__new__(cls, (score, slope, r2, points))
+
+    score = property(lambda s: s[0])
+    slope = property(lambda s: s[1])
+    r2 = property(lambda s: s[2])
+    points = property(lambda s: s[3])
+
+
+def score_inf(mu_base, cov_base, embeds, steps=25, min_n=500):
+    """fadtk/fad.py:303-350 with the statistics on the GPU: for `steps` sample sizes n between min_n and len(embeds),
+    draw n rows with replacement (np.random.choice -- the reference's generator and draw order, so a seeded run picks
+    the same rows), gather them on the device, take mean / covariance with the tcgen05 moment kernel and the Frechet
+    distance against the baseline; FAD-inf is the intercept of the linear fit over 1/n."""
+    import numpy as np
+    if not torch.cuda.is_available():
+        raise _lib.DiffMusicB200Error("score_inf needs CUDA (no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = torch.as_tensor(embeds).to(device=dev, dtype=torch.float16).contiguous()
+    N, d = x.shape
+    mu_b, cov_b = _as_dev_f64(np.atleast_1d(mu_base), dev), _as_dev_f64(np.atleast_2d(cov_base), dev)
+    ns = [int(n) for n in np.linspace(min_n, N, steps)]
+    scores = []
+    for n in ns:
+        indices = np.random.choice(N, size=n, replace=True)
+        idx = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int64)).to(dev)
+        sub = torch.empty((n, d), device=dev, dtype=torch.float16)
+        _lib.call("dm_fad_gather_rows", x.data_ptr(), N, d, idx.data_ptr(), n, sub.data_ptr(), _lib.stream())
+        mu, cov = EmbeddingMoments(d, device=dev).update(sub).finalize()
+        scores.append(frechet_distance_device(mu_b, cov_b, mu, cov)[0])
+    fad = torch.stack(scores).cpu().numpy()  # one synchronisation for the whole sweep
+    results = [[n, float(s)] for n, s in zip(ns, fad)]
+    ys = np.array(results)
+    xs = 1 / np.array(ns)
+    slope, intercept = np.polyfit(xs, ys[:, 1], 1)
+    r2 = 1 - np.sum((ys[:, 1] - (slope * xs + intercept)) ** 2) / np.sum((ys[:, 1] - np.mean(ys[:, 1])) ** 2)
+    return FADInfResults(score=intercept, slope=slope, r2=r2, points=results)

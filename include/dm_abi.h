@@ -188,6 +188,27 @@ int dm_fad_moments_ex(const void* x_f16, long long N, int d, double* acc, int en
 /* mu (d) and cov (d, d) in float64 from acc */
 int dm_fad_finalize(const double* acc, int d, double* mu, double* cov, dm_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Frechet distance and the FAD-inf bootstrap (fadtk/fad.py:50-119 `calc_frechet_distance`, :303-350 `score_inf`).
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* out_f16[r, :] = x_f16[idx[r], :]  -- embeds[np.random.choice(N, n)] of score_inf (fad.py:331-332); idx is int64 on
+ * the device (drawn by the caller with the reference's NumPy generator). */
+int dm_fad_gather_rows(const void* x_f16, long long N, int d, const long long* idx, long long n, void* out_f16,
+                       dm_stream_t stream);
+/* Singular values (= eigenvalues for a symmetric PSD input) of the d x d row-major float64 matrix W by one-sided
+ * Jacobi row rotations, in place (W ends with mutually orthogonal rows); eig[k] = |row k|.  state: 8 x uint64 of device
+ * scratch; state[3] = sweeps executed.  All launches of max_sweeps sweeps are enqueued; they become no-ops once the
+ * largest normalised inner product of a sweep is <= tol. */
+int dm_sym_eig_jacobi(double* W, int d, int max_sweeps, double tol, double* eig, unsigned long long* state,
+                      dm_stream_t stream);
+/* doubles of device scratch for dm_frechet_distance */
+long long dm_frechet_workspace_doubles(int d);
+/* out[0] = |mu1-mu2|^2 + tr C1 + tr C2 - 2 tr sqrt(C1 C2), out[1] = tr sqrt(C1 C2), out[2..3] = Jacobi sweeps used.
+ * mu*: (d), cov*: (d, d) row-major float64 on the device (what dm_fad_finalize writes). */
+int dm_frechet_distance(const double* mu1, const double* cov1, const double* mu2, const double* cov2, int d,
+                        int max_sweeps, double tol, double* work, double* out, dm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

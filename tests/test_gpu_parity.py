@@ -356,6 +356,82 @@ def test_fad_statistics_vs_numpy(n, d):
     assert np.allclose(cov2, cov2.T)
 
 
+# ------------------------------------------------------------------------------------------------ Frechet distance
+def _gauss_stats(rng, n, d, scale, shift):
+    x = (rng.standard_normal((n, d)) * scale + shift)
+    return x.mean(0), np.cov(x, rowvar=False)
+
+
+@pytest.mark.parametrize("d", [1, 2, 7, 64, 128, 257, 512])
+def test_jacobi_eigenvalues_vs_numpy(d):
+    """one-sided Jacobi row rotations (dm_sym_eig_jacobi): eigenvalues of a symmetric PSD matrix vs numpy eigvalsh."""
+    from diffmusic_b200 import _lib
+    rng = np.random.default_rng(d)
+    a = rng.standard_normal((d + 3, d))
+    c = a.T @ a / (d + 2)
+    w = torch.from_numpy(c.copy()).to(DEV)
+    eig = torch.empty(d, device=DEV, dtype=torch.float64)
+    state = torch.zeros(8, device=DEV, dtype=torch.int64)
+    _lib.call("dm_sym_eig_jacobi", w.data_ptr(), d, 30, 1e-14, eig.data_ptr(), state.data_ptr(), _lib.stream())
+    got = np.sort(eig.cpu().numpy())
+    want = np.sort(np.linalg.eigvalsh(c))
+    assert np.abs(got - want).max() <= 1e-12 * want.max()
+    assert 1 <= int(state[3]) < 30 or d == 1  # converged before the sweep cap
+    g = w.cpu().numpy() @ w.cpu().numpy().T  # rows ended orthogonal
+    off = g - np.diag(np.diag(g))
+    assert np.abs(off).max() <= 1e-12 * np.abs(np.diag(g)).max()
+
+
+@pytest.mark.parametrize("d,n1,n2", [(16, 100, 80), (128, 2000, 1500), (512, 3000, 2500), (768, 4000, 4000),
+                                     (64, 40, 500), (128, 30, 20), (1024, 600, 2000)])
+def test_frechet_distance_vs_reference_formula(d, n1, n2):
+    """dm_frechet_distance vs the restated fadtk calc_frechet_distance (scipy eig of C1 C2), incl. rank-deficient
+    covariances (n < d), where the reference itself only resolves tr sqrt(C1 C2) to ~1e-8 relative."""
+    from diffmusic_b200 import fad
+    from oracle import fad as ofad
+    rng = np.random.default_rng(d + n1)
+    mu1, c1 = _gauss_stats(rng, n1, d, rng.uniform(0.1, 2.0, d), rng.standard_normal(d))
+    mu2, c2 = _gauss_stats(rng, n2, d, 1.3, 0.2)
+    got = fad.calc_frechet_distance(mu1, c1, mu2, c2)
+    want = float(np.real(ofad.calc_frechet_distance(mu1, c1, mu2, c2)))
+    tol = 1e-9 if min(n1, n2) > d else 5e-7
+    assert abs(got - want) <= tol * abs(want), (got, want)
+    assert fad.calc_frechet_distance(mu1, c1, mu1, c1) <= 1e-9 * np.trace(c1)  # identical Gaussians -> 0
+    with pytest.raises(AssertionError):
+        fad.calc_frechet_distance(mu1, c1, mu2[:-1], c2[:-1, :-1])
+
+
+def test_fad_inf_matches_reference_loop():
+    """score_inf: same NumPy draws as the reference loop, statistics / distances on the GPU."""
+    from diffmusic_b200 import fad
+    from oracle import fad as ofad
+    rng = np.random.default_rng(5)
+    d, N = 128, 6000
+    emb = (rng.standard_normal((N, d)) * rng.uniform(0.5, 1.5, d) + 0.1).astype(np.float16)
+    mu_b, cov_b = _gauss_stats(rng, 5000, d, 1.0, 0.0)
+    np.random.seed(123)
+    want = ofad.score_inf(mu_b, cov_b, emb.astype(np.float64), steps=7, min_n=500)
+    np.random.seed(123)
+    got = fad.score_inf(mu_b, cov_b, emb, steps=7, min_n=500)
+    assert [p[0] for p in got.points] == [p[0] for p in want[3]]
+    for (n, a), (_, b) in zip(got.points, want[3]):
+        # the covariance comes from the tcgen05 moment kernel (fp32 TMEM accumulation over 256-row slabs, summed in
+        # float64): ~1e-6 relative per entry, see test_fad_statistics_vs_numpy
+        assert abs(a - np.real(b)) <= 2e-6 * abs(b), n
+    assert abs(got.score - want[0]) <= 1e-5 * abs(want[0]) and abs(got.slope - want[1]) <= 1e-3 * abs(want[1])
+    assert abs(got.r2 - want[2]) <= 1e-4
+
+
+def test_gather_rows_exact():
+    from diffmusic_b200 import _lib
+    for d in (128, 100):
+        x = torch.randn(1000, d, device=DEV).half()
+        idx = torch.randint(0, 1000, (3333,), device=DEV)
+        out = torch.empty((3333, d), device=DEV, dtype=torch.float16)
+        _lib.call("dm_fad_gather_rows", x.data_ptr(), 1000, d, idx.data_ptr(), 3333, out.data_ptr(), _lib.stream())
+        assert torch.equal(out, x[idx])
+
+
 # ------------------------------------------------------------------------------------------------ CUDA-graph replay
 @pytest.mark.parametrize("sched_name,op_name,eta", [("ddim", "inpainting", 0.0), ("dps", "super_resolution", 0.0),
                                                     ("dps", "inpainting", 0.5), ("mpgd", "inpainting", 1.0),
