@@ -12,7 +12,7 @@ Default workload = BASELINE.json configs[1]: super_resolution (scale 2) + DPS, b
   e2e   : the same through the public API (`HostPipelinedStep` over `GraphedGuidedStep`) with PINNED HOST latents in
           and prev_sample + per-clip loss out, every host<->device copy inside a timed bracket; the copies of
           neighbouring steps overlap the step on separate streams (`serial_ms_per_step` = no overlap)
-  roofline     : dominant kernel (stft_guidance_kernel), algorithmic bytes / CUDA-event time, vs MEASURED_PEAKS hbm_gbs
+  roofline     : dominant kernel (stft_pair_kernel, the fused STFT / mel / loss / VJP pass), algorithmic bytes / CUDA-event time, vs MEASURED_PEAKS hbm_gbs
   cpu_baseline : the CPU oracle (torch restatement of the reference's scheduler.step) on this box's host cores, on a
                  bounded sample of the same workload
 `--impl reference` times that CPU oracle alone, with every host thread, and prints the same line with impl=reference.
@@ -47,7 +47,7 @@ WORKLOADS = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
 # `ncu --set full` captures (profiles/README.md); null where no capture of that workload exists.
-NCU_TRAFFIC_BYTES = {"cfg2": 10.51e6}
+NCU_TRAFFIC_BYTES = {"cfg2": 10.52e6}
 
 
 def peaks():
@@ -165,7 +165,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    clips = 2 if WORKLOADS[args.workload][1] != "dereverberation" else 1
+    # the workload's own batch per step (dereverberation: one clip -- its K = 5000 direct convolution costs seconds)
+    clips = WORKLOADS[args.workload][2] if WORKLOADS[args.workload][1] != "dereverberation" else 1
     rate, sec = cpu_oracle_rate(args.workload, clips, args.steps, min(args.warmup, 1), threads)
     sample = f"{clips} clip(s) per step of the same workload, {args.steps} steps, oracle per_clip_step on CPU"
     line = {"impl": "reference", "metric": "guided denoising steps/s (10 s clips)", "value": rate,
@@ -363,10 +364,10 @@ def main():
         peak, peak_src = peaks()
         dom = statistics.mean(dom_ms) if dom_ms else None
         achieved = bytes_launch / (dom * 1e-3) / 1e9 if dom else None
-        roofline = {"bound": "hbm", "kernel": "stft_guidance_kernel", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": "stft_pair_kernel", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                     "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if dom else None,
-                    "traffic_source": "profiles/r01/stft_guidance_full_raw.csv (ncu --set full, per launch)",
+                    "traffic_source": "profiles/r01/stft_pair_full_raw.csv (ncu --set full, per launch)",
                     "bytes_per_launch": bytes_launch, "ms_per_launch": dom, "launches_timed": len(dom_ms),
                     "peak_source": peak_src,
                     "note": "compute/shared-memory bound FFT kernel: algorithmic HBM bytes are the floor, see DESIGN.md"}
@@ -386,11 +387,13 @@ def main():
                 "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            clips = 2 if op_name != "dereverberation" else 1
-            rate, sec = cpu_oracle_rate(args.workload, clips, 3, 1, threads)
+            clips = B if op_name != "dereverberation" else 1
+            _, probe = cpu_oracle_rate(args.workload, clips, 1, 1, threads)
+            n_cpu = max(3, min(300, int(12.0 / max(probe, 1e-3))))  # ~12 s of host work
+            rate, sec = cpu_oracle_rate(args.workload, clips, n_cpu, 0, threads)
             line["cpu_baseline"] = {"value": rate, "unit": "clip-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{clips} clip(s) x 3 steps of the same workload through the CPU oracle "
-                                              f"(oracle/steps.py per_clip_step), {sec:.2f} s per step"}
+                                    "sample": f"{clips} clip(s) x {n_cpu} steps of the same workload through the CPU "
+                                              f"oracle (oracle/steps.py per_clip_step), {sec:.3f} s per step"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
