@@ -209,6 +209,22 @@ long long dm_frechet_workspace_doubles(int d);
 int dm_frechet_distance(const double* mu1, const double* cov1, const double* mu2, const double* cov2, int d,
                         int max_sweeps, double tol, double* work, double* out, dm_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Evaluation metrics (diffmusic/metrics/lsd.py:17-40, mse.py:9-29).
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* out (B, T = 1 + L/hop): per-frame sqrt(mean over the 513 bins of (log10(|STFT ref| + eps) - log10(|STFT est| + eps))^2),
+ * n_fft = win = 1024 with tab->window, centred frames, zero padding (librosa >= 0.10) or reflection.  `est` is always
+ * sanitised like np.nan_to_num(nan=0, posinf=1, neginf=-1) (lsd.py:23), `ref` only if sanitize_ref.  hop even. */
+int dm_lsd_frames(const dm_stft_tables* tab, const float* ref, long long ref_bstride, const float* est,
+                  long long est_bstride, long long L, int B, int hop, int pad_reflect, int sanitize_ref, float eps,
+                  float* out, dm_stream_t stream);
+/* out[b] = mean_i (nan_to_num(ref[b, i]) - nan_to_num(est[b, i]))^2 over i < n; partial: B x dm_mse_num_chunks(n)
+ * float64 of device scratch (fixed summation order: bit-reproducible). */
+long long dm_mse_num_chunks(long long n);
+int dm_mse(const float* ref, long long ref_bstride, const float* est, long long est_bstride, long long n, int B,
+           double* partial, float* out, dm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

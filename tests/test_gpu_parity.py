@@ -432,6 +432,50 @@ def test_gather_rows_exact():
         assert torch.equal(out, x[idx])
 
 
+# ------------------------------------------------------------------------------------------------ eval metrics
+@pytest.mark.parametrize("hop,pad", [(160, "constant"), (512, "constant"), (512, "reflect"), (1024, "constant")])
+def test_log_spectral_distance_vs_reference_formula(hop, pad):
+    from diffmusic_b200 import metrics
+    from oracle import metrics as om
+    L = 16000 + 37
+    bg = stubs.synth_clips(3, L).numpy()
+    ev = (stubs.synth_clips(3, L, first=7) * 0.8).numpy()
+    ev[1, 100] = np.nan
+    ev[2, 5000] = np.inf
+    ev[2, 5001] = -np.inf
+    lsd = metrics.LogSpectralDistance(16000, 1024, hop, 1e-10, pad_mode=pad)
+    want = om.lsd_score(bg, ev, 1024, hop, 1e-10, output_mean=False, pad_mode=pad)
+    got = lsd.score(bg, ev, output_mean=False)
+    assert got.shape == want.shape == (3,)
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+    assert abs(lsd.score(bg, ev) - float(om.lsd_score(bg, ev, 1024, hop, 1e-10, pad_mode=pad))) <= 2e-5 * want.mean()
+    assert lsd.score(bg, bg) == 0.0
+    with pytest.raises(NotImplementedError):
+        metrics.LogSpectralDistance(n_fft=2048)
+
+
+def test_mean_squared_error_vs_reference_formula():
+    from diffmusic_b200 import metrics
+    from oracle import metrics as om
+    bg = stubs.synth_clips(4, 40001).numpy()
+    ev = stubs.synth_clips(4, 40001, first=9).numpy()
+    ev[0, 3] = np.nan
+    bg[1, 7] = np.inf
+    for red in ("mean", "sum"):
+        got = metrics.MeanSquaredError(red).score(bg, ev)
+        want = float(om.mse_score(bg, ev, red))
+        assert abs(got - want) <= 1e-6 * abs(want)
+    ragged_bg = [bg[0], bg[1][:30000]]
+    ragged_ev = [ev[0][:25000], ev[1]]
+    got = metrics.MeanSquaredError("sum").score(ragged_bg, ragged_ev)
+    want = sum(float(np.mean((np.nan_to_num(a[:min(len(a), len(b))], nan=0, posinf=1, neginf=-1)
+                              - np.nan_to_num(b[:min(len(a), len(b))], nan=0, posinf=1, neginf=-1)) ** 2))
+               for a, b in zip(ragged_bg, ragged_ev))
+    assert abs(got - want) <= 1e-6 * abs(want)
+    with pytest.raises(AssertionError):
+        metrics.MeanSquaredError("median")
+
+
 # ------------------------------------------------------------------------------------------------ CUDA-graph replay
 @pytest.mark.parametrize("sched_name,op_name,eta", [("ddim", "inpainting", 0.0), ("dps", "super_resolution", 0.0),
                                                     ("dps", "inpainting", 0.5), ("mpgd", "inpainting", 1.0),
