@@ -112,6 +112,38 @@ DM_HD void fir_adj4(const float* ys, const float* w, int taps_rt, int orig_rt, i
     }
 }
 
+// ---- register-window bodies for the reference's scale-2 filter (orig 2, 28 taps, width 13; operator.py:180 with
+//      run.py:188): a thread owns 8 consecutive outputs and keeps its whole input window in registers, so the FIR runs
+//      without shared memory and the global traffic is 128-bit loads / stores only. ----
+constexpr int kFir2Taps = 28, kFir2Width = 13, kFir2Out = 8;
+constexpr int kFir2FwdWin = 48;  // x[2 j0 - 16 .. 2 j0 + 31]: 12 aligned float4 (j0 % 8 == 0)
+constexpr int kFir2AdjWin = 20;  // ybar[i0/2 - 8 .. i0/2 + 11]: 5 aligned float4 (i0 % 8 == 0)
+// y[j0 + c] = sum_k xz[2 (j0 + c) + k - 13] h[k] ; win[n] = xz[2 j0 - 16 + n]
+DM_HD void fir2_fwd8(const float (&win)[kFir2FwdWin], const float (&h)[kFir2Taps], float (&y)[kFir2Out]) {
+#pragma unroll
+    for (int c = 0; c < kFir2Out; ++c) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < kFir2Taps; ++k) a = fmaf(win[3 + 2 * c + k], h[k], a);
+        y[c] = a;
+    }
+}
+// xbar[i0 + 2 u]     = sum_t ybar[m - 7 + t] h[27 - 2 t]   (m = i0/2 + u, u < 4, t < 14)
+// xbar[i0 + 2 u + 1] = sum_t ybar[m - 6 + t] h[26 - 2 t] ; win[n] = ybar[i0/2 - 8 + n]
+DM_HD void fir2_adj8(const float (&win)[kFir2AdjWin], const float (&h)[kFir2Taps], float (&x)[kFir2Out]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        float e = 0.f, o = 0.f;
+#pragma unroll
+        for (int t = 0; t < 14; ++t) {
+            e = fmaf(win[u + 1 + t], h[27 - 2 * t], e);
+            o = fmaf(win[u + 2 + t], h[26 - 2 * t], o);
+        }
+        x[2 * u] = e;
+        x[2 * u + 1] = o;
+    }
+}
+
 // signed ceil-division (orig > 0)
 DM_HD long long ceil_div_ll(long long a, long long b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
 

@@ -224,6 +224,111 @@ __global__ void __launch_bounds__(kEwThreads) resample_adjoint_poly_kernel(
     for (int t = threadIdx.x; t < ni; t += kEwThreads) dwav[(long long)b * dwav_bstride + i0 + t] = outs[t];
 }
 
+// ---- scale 2 (orig 2, 28 taps, width 13): register-window kernels, no shared-memory staging ----
+// Each thread produces 8 consecutive outputs from a window of aligned float4 loads (all issued before anything else, so
+// a CTA has its whole input in flight at once); threads whose window crosses a row end or the reflect-fold region take
+// a guarded scalar path.
+__device__ __forceinline__ void load_taps28(const float* __restrict__ kernel, float (&h)[kFir2Taps]) {
+#pragma unroll
+    for (int q = 0; q < kFir2Taps / 4; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(kernel) + q);
+        h[4 * q] = t.x;
+        h[4 * q + 1] = t.y;
+        h[4 * q + 2] = t.z;
+        h[4 * q + 3] = t.w;
+    }
+}
+
+__global__ void __launch_bounds__(kEwThreads) resample2_fwd_reg_kernel(const float* __restrict__ x, long long x_bstride,
+                                                                       long long L, const float* __restrict__ kernel,
+                                                                       float* __restrict__ y, long long Ly) {
+    const int b = blockIdx.y;
+    const long long j0 = ((long long)blockIdx.x * kEwThreads + threadIdx.x) * kFir2Out;
+    if (j0 >= Ly) return;
+    const float* xb = x + (long long)b * x_bstride;
+    const long long x0 = 2 * j0 - 16;
+    float win[kFir2FwdWin];
+    if (x0 >= 0 && x0 + kFir2FwdWin <= L) {
+        const float4* src = reinterpret_cast<const float4*>(xb + x0);
+#pragma unroll
+        for (int q = 0; q < kFir2FwdWin / 4; ++q) {
+            const float4 t = src[q];
+            win[4 * q] = t.x;
+            win[4 * q + 1] = t.y;
+            win[4 * q + 2] = t.z;
+            win[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int n = 0; n < kFir2FwdWin; ++n) {
+            const long long g = x0 + n;
+            win[n] = (g >= 0 && g < L) ? xb[g] : 0.f;
+        }
+    }
+    float h[kFir2Taps], out[kFir2Out];
+    load_taps28(kernel, h);
+    fir2_fwd8(win, h, out);
+    float* yb = y + (long long)b * Ly + j0;
+    if (j0 + kFir2Out <= Ly) {
+        reinterpret_cast<float4*>(yb)[0] = make_float4(out[0], out[1], out[2], out[3]);
+        reinterpret_cast<float4*>(yb)[1] = make_float4(out[4], out[5], out[6], out[7]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < kFir2Out; ++c)
+            if (j0 + c < Ly) yb[c] = out[c];
+    }
+}
+
+__global__ void __launch_bounds__(kEwThreads) resample2_adjoint_reg_kernel(
+    const float* __restrict__ ybar, int pad, long long Ly, const float* __restrict__ partial, int ntiles,
+    const float* __restrict__ kernel, float* __restrict__ dwav, long long dwav_bstride, long long L,
+    float* __restrict__ loss) {
+    __shared__ float scratch[2];
+    const int b = blockIdx.y;
+    const long long i0 = ((long long)blockIdx.x * kEwThreads + threadIdx.x) * kFir2Out;
+    const float* yb = ybar + (long long)b * (Ly + 2 * pad);
+    const long long m0 = i0 / 2 - 8;  // first cotangent sample of the window
+    float win[kFir2AdjWin];
+    if (i0 < L) {
+        // no fold terms for 513 <= j <= Ly - 514 (pad = 512); without padding any in-range window is plain
+        const bool plain = pad ? (m0 >= 513 && m0 + kFir2AdjWin <= Ly - 513) : (m0 >= 0 && m0 + kFir2AdjWin <= Ly);
+        if (plain) {
+            const float4* src = reinterpret_cast<const float4*>(yb + pad + m0);
+#pragma unroll
+            for (int q = 0; q < kFir2AdjWin / 4; ++q) {
+                const float4 t = src[q];
+                win[4 * q] = t.x;
+                win[4 * q + 1] = t.y;
+                win[4 * q + 2] = t.z;
+                win[4 * q + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < kFir2AdjWin; ++n) {
+                const long long j = m0 + n;
+                win[n] = (j >= 0 && j < Ly) ? ybar_at(yb, pad, j, Ly) : 0.f;
+            }
+        }
+    }
+    // the per-clip scale is only needed at the very end: the window loads above are already in flight
+    const float l = clip_loss(partial + (long long)b * ntiles, ntiles, scratch);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[b] = l;
+    if (i0 >= L) return;
+    const float sc = inv_loss(l);
+    float h[kFir2Taps], out[kFir2Out];
+    load_taps28(kernel, h);
+    fir2_adj8(win, h, out);
+    float* ob = dwav + (long long)b * dwav_bstride + i0;
+    if (i0 + kFir2Out <= L) {
+        reinterpret_cast<float4*>(ob)[0] = make_float4(out[0] * sc, out[1] * sc, out[2] * sc, out[3] * sc);
+        reinterpret_cast<float4*>(ob)[1] = make_float4(out[4] * sc, out[5] * sc, out[6] * sc, out[7] * sc);
+    } else {
+#pragma unroll
+        for (int c = 0; c < kFir2Out; ++c)
+            if (i0 + c < L) ob[c] = out[c] * sc;
+    }
+}
+
 __global__ void __launch_bounds__(kEwThreads) mask_apply_kernel(const float* __restrict__ x, long long x_bstride,
                                                                 long long L, const float* __restrict__ mask,
                                                                 float* __restrict__ y) {
@@ -278,6 +383,15 @@ extern "C" int dm_resample_fwd(const float* x, long long x_bstride, long long L,
         const int span1 = orig * (kRsChunk + kFirR) + taps;
         const size_t smem1 = ((size_t)taps + fir_padded_len(span1) + kRsChunk) * sizeof(float);
         if (smem1 <= 200 * 1024) {
+            if (orig == 2 && taps == kFir2Taps && width == kFir2Width && x_bstride % 4 == 0 && Ly % 4 == 0 &&
+                (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(kernel) & 15) == 0) {
+                const long long nthr = (Ly + kFir2Out - 1) / kFir2Out;
+                resample2_fwd_reg_kernel<<<dim3((unsigned)((nthr + kEwThreads - 1) / kEwThreads), B), kEwThreads, 0,
+                                           as_stream(stream)>>>(x, x_bstride, L, kernel, y, Ly);
+                DM_LAUNCHED();
+                return DM_OK;
+            }
             const dim3 grid((unsigned)((Ly + kRsChunk - 1) / kRsChunk), B);
 #define DM_RS_FWD(O, T)                                                                                          \
     do {                                                                                                         \
@@ -311,6 +425,16 @@ extern "C" int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int
                                    long long dwav_bstride, long long L, float* loss, dm_stream_t stream) {
     DM_REQUIRE(ybar && partial && kernel && dwav && L > 0 && B > 0 && Ly > 0 && ntiles > 0);
     DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 512));
+    if (n_new == 1 && orig == 2 && taps == kFir2Taps && width == kFir2Width && dwav_bstride % 4 == 0 &&
+        (Ly + 2 * pad) % 4 == 0 && (reinterpret_cast<uintptr_t>(ybar) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(dwav) & 15) == 0 && (reinterpret_cast<uintptr_t>(kernel) & 15) == 0) {
+        const long long nthr = (L + kFir2Out - 1) / kFir2Out;
+        resample2_adjoint_reg_kernel<<<dim3((unsigned)((nthr + kEwThreads - 1) / kEwThreads), B), kEwThreads, 0,
+                                       as_stream(stream)>>>(ybar, pad, Ly, partial, ntiles, kernel, dwav, dwav_bstride,
+                                                            L, loss);
+        DM_LAUNCHED();
+        return DM_OK;
+    }
     if (n_new == 1 && taps >= orig) {  // integer decimation: polyphase kernel
         const int unit = orig * kFirR;
         const int chunk = unit * ((kRsChunk + unit - 1) / unit);

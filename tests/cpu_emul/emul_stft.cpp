@@ -359,6 +359,30 @@ void emul_resample_adjoint(const float* ybar, long long Ly, const float* kernel,
 }
 }
 
+// register-window scale-2 bodies (fir2_fwd8 / fir2_adj8), windows built exactly as the kernels build them
+extern "C" {
+void emul_resample2_fwd(const float* x, long long L, const float* kernel, float* y, long long Ly) {
+    float h[kFir2Taps];
+    for (int k = 0; k < kFir2Taps; ++k) h[k] = kernel[k];
+    for (long long j0 = 0; j0 < Ly; j0 += kFir2Out) {
+        float win[kFir2FwdWin], out[kFir2Out];
+        for (int n = 0; n < kFir2FwdWin; ++n) { long long g = 2 * j0 - 16 + n; win[n] = (g >= 0 && g < L) ? x[g] : 0.f; }
+        fir2_fwd8(win, h, out);
+        for (int c = 0; c < kFir2Out; ++c) if (j0 + c < Ly) y[j0 + c] = out[c];
+    }
+}
+void emul_resample2_adjoint(const float* ybar, long long Ly, const float* kernel, float scale, float* xbar, long long L) {
+    float h[kFir2Taps];
+    for (int k = 0; k < kFir2Taps; ++k) h[k] = kernel[k];
+    for (long long i0 = 0; i0 < L; i0 += kFir2Out) {
+        float win[kFir2AdjWin], out[kFir2Out];
+        for (int n = 0; n < kFir2AdjWin; ++n) { long long j = i0 / 2 - 8 + n; win[n] = (j >= 0 && j < Ly) ? ybar[j] : 0.f; }
+        fir2_adj8(win, h, out);
+        for (int c = 0; c < kFir2Out; ++c) if (i0 + c < L) xbar[i0 + c] = out[c] * scale;
+    }
+}
+}
+
 // exhaustive check of the closed-form swizzled addresses (fft_core.cuh) against swz() of the logical index
 extern "C" int emul_check_swizzle_forms() {
     int bad = 0;

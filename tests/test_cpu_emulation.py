@@ -247,6 +247,30 @@ def test_polyphase_resample(emul, scale, L):
     assert rel_l2(gotb, 0.25 * gx[0]) < 2e-6
 
 
+@pytest.mark.parametrize("L", [16000, 4099, 57])
+def test_register_window_scale2_resample(emul, L):
+    """fir2_fwd8 / fir2_adj8 (8 outputs per thread from a register window) vs torchaudio Resample(16000, 8000) / autograd."""
+    import torchaudio
+    kern, width, orig, new = tables.sinc_resample_kernel(16000, 8000)
+    assert (orig, new, width, kern.shape[-1]) == (2, 1, 13, 28)
+    g = torch.Generator().manual_seed(L)
+    x = torch.randn(1, L, generator=g)
+    xx = x.clone().requires_grad_(True)
+    y = torchaudio.transforms.Resample(16000, 8000)(xx)
+    Ly = y.shape[1]
+    k = kern[0].numpy().copy()
+    got = np.zeros(Ly, np.float32)
+    xn = x[0].numpy().copy()
+    emul.emul_resample2_fwd(_ptr(xn), C.c_longlong(L), _ptr(k), _ptr(got), C.c_longlong(Ly))
+    assert rel_l2(got, y[0].detach()) < 2e-6
+    yb = torch.randn(1, Ly, generator=g)
+    (gx,) = torch.autograd.grad((y * yb).sum(), xx)
+    gotb = np.zeros(L, np.float32)
+    ybn = yb[0].numpy().copy()
+    emul.emul_resample2_adjoint(_ptr(ybn), C.c_longlong(Ly), _ptr(k), C.c_float(0.25), _ptr(gotb), C.c_longlong(L))
+    assert rel_l2(gotb, 0.25 * gx[0]) < 2e-6
+
+
 def test_pair_swizzle_is_conflict_free(emul):
     """cell swizzle of the frame-pair pipeline: closed-form addresses equal sw4(logical index) and every 128-bit access
     pattern of the FFT passes / unpack hits 8 distinct 16-byte bank groups per quarter-warp."""
