@@ -34,6 +34,15 @@ _SIGNATURES = {
                                   c_p]),
     "dm_sched_diffmusic_update": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
                                         c_p, c_p]),
+    "dm_sched_x0_io": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_i, c_f, c_p, c_i, c_p]),
+    "dm_sched_ddim_update_io": (c_i, [c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_p, c_i, c_p]),
+    "dm_sched_dps_update_io": (c_i, [c_p, c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_p, c_i, c_p]),
+    "dm_sched_mpgd_update_io": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_p, c_i,
+                                      c_p]),
+    "dm_sched_dsg_update_io": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_p,
+                                     c_i, c_p]),
+    "dm_sched_diffmusic_update_io": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
+                                           c_f, c_p, c_i, c_p]),
     "dm_stft_set_engine": (c_i, [c_i]),
     "dm_stft_num_tiles": (c_i, [c_ll, c_i, c_i]),
     "dm_stft_guidance": (c_i, [C.POINTER(StftTables), c_i, c_i, c_i, c_p, c_ll, c_ll, c_p, c_i, c_p, c_ll, c_p, c_f,
@@ -96,6 +105,9 @@ def call(name, *args):
 def ptr(t):
     """Raw device pointer of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+IO_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
 
 def stream():

@@ -6,6 +6,8 @@
 // sweep served from L2.  Multiplications / additions are kept un-fused (__fmul_rn/__fadd_rn) where the reference's
 // eager torch ops round after every step, so results track the reference to the last bit or two.
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 
@@ -39,6 +41,50 @@ __device__ __forceinline__ void stv(float* __restrict__ p, long long v, const fl
     }
 }
 
+// Latent-typed tensors (what the pipeline hands in and gets back: sample, model_output, prev_sample,
+// pred_original_sample) may be fp32, fp16 or bf16 (the reference pipelines run in fp16, run.py:218); everything the
+// step keeps to itself (x0 for the guidance, the gradient, the noise) and all arithmetic stay fp32.
+template <int IO, int W>
+__device__ __forceinline__ void ldio(const void* __restrict__ p, long long v, float (&o)[W]) {
+    if (IO == DM_IO_F32) {
+        ldv<W>(static_cast<const float*>(p), v, o);
+    } else if (W == 4) {
+        const uint2 raw = reinterpret_cast<const uint2*>(p)[v];
+        if (IO == DM_IO_F16) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            o[0] = a.x; o[1 % W] = a.y; o[2 % W] = b.x; o[3 % W] = b.y;
+        } else {
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+            const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+            o[0] = a.x; o[1 % W] = a.y; o[2 % W] = b.x; o[3 % W] = b.y;
+        }
+    } else {
+        o[0] = IO == DM_IO_F16 ? __half2float(static_cast<const __half*>(p)[v])
+                               : __bfloat162float(static_cast<const __nv_bfloat16*>(p)[v]);
+    }
+}
+template <int IO, int W>
+__device__ __forceinline__ void stio(void* __restrict__ p, long long v, const float (&o)[W]) {
+    if (IO == DM_IO_F32) {
+        stv<W>(static_cast<float*>(p), v, o);
+    } else if (W == 4) {
+        uint2 raw;
+        if (IO == DM_IO_F16) {
+            *reinterpret_cast<__half2*>(&raw.x) = __floats2half2_rn(o[0], o[1 % W]);
+            *reinterpret_cast<__half2*>(&raw.y) = __floats2half2_rn(o[2 % W], o[3 % W]);
+        } else {
+            *reinterpret_cast<__nv_bfloat162*>(&raw.x) = __floats2bfloat162_rn(o[0], o[1 % W]);
+            *reinterpret_cast<__nv_bfloat162*>(&raw.y) = __floats2bfloat162_rn(o[2 % W], o[3 % W]);
+        }
+        reinterpret_cast<uint2*>(p)[v] = raw;
+    } else if (IO == DM_IO_F16) {
+        static_cast<__half*>(p)[v] = __float2half_rn(o[0]);
+    } else {
+        static_cast<__nv_bfloat16*>(p)[v] = __float2bfloat16_rn(o[0]);
+    }
+}
+
 __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
@@ -46,13 +92,14 @@ __device__ __forceinline__ float dvd(float a, float b) { return __fdiv_rn(a, b);
 
 // ------------------------------------------------------------------------------------------------ elementwise
 struct EwParams {
-    const float* x;
+    const void* x;    // latent-typed
     const float* x0;
-    const float* eps;
+    const void* eps;  // latent-typed
     const float* g0;
     const float* z;
-    float* prev;
-    float* x0_out;
+    void* prev;       // latent-typed
+    float* x0_out;    // fp32 x0 (kX0) / guided x0 (kMpgd) kept by the step
+    void* x0_pub;     // optional latent-typed copy of x0_out for the caller (pred_original_sample)
     float sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate, clip_range;
     int clip;
     const float* coef;  // optional device-resident [sqrt_a, sqrt_b, sqrt_p, dir_coef, std, r]: overrides the by-value
@@ -72,15 +119,15 @@ __device__ __forceinline__ void load_coef(const float* __restrict__ c, float& sq
 
 enum EwKind { kX0 = 0, kDdim = 1, kDps = 2, kMpgd = 3 };
 
-template <int KIND, int W>
+template <int KIND, int W, int IO>
 __global__ void __launch_bounds__(kThreads) ew_update_kernel(EwParams p, long long nvec) {
     load_coef(p.coef, p.sqrt_a, p.sqrt_b, p.sqrt_p, p.dir_coef, p.std);
     const long long stride = (long long)gridDim.x * kThreads;
     for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += stride) {
         float x[W], a[W], g[W], z[W], o[W], o2[W];
-        ldv<W>(p.x, v, x);
+        ldio<IO, W>(p.x, v, x);
         if (KIND == kX0) {
-            ldv<W>(p.eps, v, a);
+            ldio<IO, W>(p.eps, v, a);
 #pragma unroll
             for (int i = 0; i < W; ++i) {
                 float t = dvd(sub(x[i], mul(p.sqrt_b, a[i])), p.sqrt_a);
@@ -88,6 +135,7 @@ __global__ void __launch_bounds__(kThreads) ew_update_kernel(EwParams p, long lo
                 o[i] = t;
             }
             stv<W>(p.x0_out, v, o);
+            if (IO != DM_IO_F32 && p.x0_pub != nullptr) stio<IO, W>(p.x0_pub, v, o);
         } else {
             ldv<W>(p.x0, v, a);
             if (KIND != kDdim) ldv<W>(p.g0, v, g);
@@ -104,35 +152,48 @@ __global__ void __launch_bounds__(kThreads) ew_update_kernel(EwParams p, long lo
                 o[i] = prev;
                 o2[i] = x0;
             }
-            stv<W>(p.prev, v, o);
-            if (KIND == kMpgd) stv<W>(p.x0_out, v, o2);
+            stio<IO, W>(p.prev, v, o);
+            if (KIND == kMpgd) {
+                if (IO == DM_IO_F32 || p.x0_pub == nullptr) stv<W>(p.x0_out, v, o2);
+                else stio<IO, W>(p.x0_pub, v, o2);
+            }
         }
     }
 }
 
 static bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool aligned8(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+static bool io_ok(int io) { return io == DM_IO_F32 || io == DM_IO_F16 || io == DM_IO_BF16; }
+static bool aligned_io(const void* p, int io) { return io == DM_IO_F32 ? aligned16(p) : aligned8(p); }
 
-template <int KIND>
-static int launch_ew(const EwParams& p, long long n, cudaStream_t st) {
-    const bool vec = (n % 4 == 0) && aligned16(p.x) && aligned16(p.x0) && aligned16(p.eps) && aligned16(p.g0) &&
-                     aligned16(p.z) && aligned16(p.prev) && aligned16(p.x0_out);
+template <int KIND, int IO>
+static void launch_ew_io(const EwParams& p, long long n, cudaStream_t st) {
+    const bool vec = (n % 4 == 0) && aligned_io(p.x, IO) && aligned16(p.x0) && aligned_io(p.eps, IO) &&
+                     aligned16(p.g0) && aligned16(p.z) && aligned_io(p.prev, IO) && aligned16(p.x0_out) &&
+                     aligned_io(p.x0_pub, IO);
     const long long nvec = vec ? n / 4 : n;
     const int nblk = (int)std::max<long long>(1, std::min<long long>((nvec + kThreads - 1) / kThreads,
                                                                       (long long)num_sms() * 8));
     if (vec)
-        ew_update_kernel<KIND, 4><<<nblk, kThreads, 0, st>>>(p, nvec);
+        ew_update_kernel<KIND, 4, IO><<<nblk, kThreads, 0, st>>>(p, nvec);
     else
-        ew_update_kernel<KIND, 1><<<nblk, kThreads, 0, st>>>(p, nvec);
+        ew_update_kernel<KIND, 1, IO><<<nblk, kThreads, 0, st>>>(p, nvec);
+}
+template <int KIND>
+static int launch_ew(const EwParams& p, long long n, int io, cudaStream_t st) {
+    if (io == DM_IO_F16) launch_ew_io<KIND, DM_IO_F16>(p, n, st);
+    else if (io == DM_IO_BF16) launch_ew_io<KIND, DM_IO_BF16>(p, n, st);
+    else launch_ew_io<KIND, DM_IO_F32>(p, n, st);
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ per-clip norms
 struct NormParams {
     const float* x0;
-    const float* eps;
+    const void* eps;  // latent-typed
     const float* g0;
     const float* z;
-    float* prev;
+    void* prev;       // latent-typed
     long long n_clip;
     float sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, threshold;
     const float* coef;  // optional device-resident coefficients (see EwParams::coef)
@@ -197,7 +258,7 @@ __device__ __forceinline__ float elem_out(const NormParams& p, const NormScalars
 // (clips longer than 8 * 256 * kIt * W elements) the later sweeps re-read from L2.
 constexpr int kIt = 4;
 
-template <int KIND, int W, bool CACHED>
+template <int KIND, int W, bool CACHED, int IO>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) norm_update_kernel(NormParams p) {
     cg::cluster_group cluster = cg::this_cluster();
     if (p.coef != nullptr) {
@@ -223,7 +284,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
                 ldv<W>(p.g0, off + v, rg[it]);
                 ldv<W>(p.z, off + v, rz[it]);
                 ldv<W>(p.x0, off + v, rx0[it]);
-                ldv<W>(p.eps, off + v, rep[it]);
+                ldio<IO, W>(p.eps, off + v, rep[it]);
             } else {
 #pragma unroll
                 for (int i = 0; i < W; ++i) rg[it][i] = rz[it][i] = rx0[it][i] = rep[it][i] = 0.f;
@@ -312,7 +373,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
         float o[W];
 #pragma unroll
         for (int i = 0; i < W; ++i) o[i] = elem_out<KIND>(p, c, x0[i], ep[i], g[i], z[i]);
-        stv<W>(p.prev, off + v, o);
+        stio<IO, W>(p.prev, off + v, o);
     };
     if (CACHED) {
 #pragma unroll
@@ -324,7 +385,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
         for (long long v = lo + threadIdx.x; v < hi; v += kThreads) {
             float x0[W], ep[W], g[W], z[W];
             ldv<W>(p.x0, off + v, x0);
-            ldv<W>(p.eps, off + v, ep);
+            ldio<IO, W>(p.eps, off + v, ep);
             ldv<W>(p.g0, off + v, g);
             ldv<W>(p.z, off + v, z);
             emit(v, x0, ep, g, z);
@@ -333,19 +394,25 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
     cluster.sync();  // keep every CTA's shared memory alive until all remote reads are done
 }
 
-template <int KIND>
-static int launch_norm(const NormParams& p, int n_clips, cudaStream_t st) {
-    const bool vec = (p.n_clip % 4 == 0) && aligned16(p.x0) && aligned16(p.eps) && aligned16(p.g0) &&
-                     aligned16(p.z) && aligned16(p.prev);
+template <int KIND, int IO>
+static void launch_norm_io(const NormParams& p, int n_clips, cudaStream_t st) {
+    const bool vec = (p.n_clip % 4 == 0) && aligned16(p.x0) && aligned_io(p.eps, IO) && aligned16(p.g0) &&
+                     aligned16(p.z) && aligned_io(p.prev, IO);
     const int W = vec ? 4 : 1;
     const long long chunk = (p.n_clip / W + kCluster - 1) / kCluster;
     const bool cached = vec && chunk <= (long long)kIt * kThreads;  // the 10 s latent: 1000 vectors per CTA
     if (cached)
-        norm_update_kernel<KIND, 4, true><<<n_clips * kCluster, kThreads, 0, st>>>(p);
+        norm_update_kernel<KIND, 4, true, IO><<<n_clips * kCluster, kThreads, 0, st>>>(p);
     else if (vec)
-        norm_update_kernel<KIND, 4, false><<<n_clips * kCluster, kThreads, 0, st>>>(p);
+        norm_update_kernel<KIND, 4, false, IO><<<n_clips * kCluster, kThreads, 0, st>>>(p);
     else
-        norm_update_kernel<KIND, 1, false><<<n_clips * kCluster, kThreads, 0, st>>>(p);
+        norm_update_kernel<KIND, 1, false, IO><<<n_clips * kCluster, kThreads, 0, st>>>(p);
+}
+template <int KIND>
+static int launch_norm(const NormParams& p, int n_clips, int io, cudaStream_t st) {
+    if (io == DM_IO_F16) launch_norm_io<KIND, DM_IO_F16>(p, n_clips, st);
+    else if (io == DM_IO_BF16) launch_norm_io<KIND, DM_IO_BF16>(p, n_clips, st);
+    else launch_norm_io<KIND, DM_IO_F32>(p, n_clips, st);
     return 0;
 }
 
@@ -353,27 +420,33 @@ static int launch_norm(const NormParams& p, int n_clips, cudaStream_t st) {
 
 using namespace dm;
 
-extern "C" int dm_sched_x0(const float* x, const float* eps, float* x0, long long n, float sqrt_a, float sqrt_b,
-                           int clip, float clip_range, const float* coef, dm_stream_t stream) {
-    DM_REQUIRE(x && eps && x0 && n > 0);
+extern "C" int dm_sched_x0_io(const void* x, const void* eps, float* x0, void* x0_pub, long long n, float sqrt_a,
+                              float sqrt_b, int clip, float clip_range, const float* coef, int io_dtype,
+                              dm_stream_t stream) {
+    DM_REQUIRE(x && eps && x0 && n > 0 && io_ok(io_dtype));
     EwParams p{};
     p.coef = coef;
     p.x = x;
     p.eps = eps;
     p.x0_out = x0;
+    p.x0_pub = x0_pub;
     p.sqrt_a = sqrt_a;
     p.sqrt_b = sqrt_b;
     p.clip = clip;
     p.clip_range = clip_range;
-    launch_ew<kX0>(p, n, as_stream(stream));
+    launch_ew<kX0>(p, n, io_dtype, as_stream(stream));
     DM_LAUNCHED();
     return DM_OK;
 }
+extern "C" int dm_sched_x0(const float* x, const float* eps, float* x0, long long n, float sqrt_a, float sqrt_b,
+                           int clip, float clip_range, const float* coef, dm_stream_t stream) {
+    return dm_sched_x0_io(x, eps, x0, nullptr, n, sqrt_a, sqrt_b, clip, clip_range, coef, DM_IO_F32, stream);
+}
 
-extern "C" int dm_sched_ddim_update(const float* x, const float* x0, float* prev, long long n, float sqrt_a,
-                                    float sqrt_b, float sqrt_p, float sqrt_1mp, const float* coef,
-                                    dm_stream_t stream) {
-    DM_REQUIRE(x && x0 && prev && n > 0);
+extern "C" int dm_sched_ddim_update_io(const void* x, const float* x0, void* prev, long long n, float sqrt_a,
+                                       float sqrt_b, float sqrt_p, float sqrt_1mp, const float* coef, int io_dtype,
+                                       dm_stream_t stream) {
+    DM_REQUIRE(x && x0 && prev && n > 0 && io_ok(io_dtype));
     EwParams p{};
     p.coef = coef;
     p.x = x;
@@ -383,15 +456,20 @@ extern "C" int dm_sched_ddim_update(const float* x, const float* x0, float* prev
     p.sqrt_b = sqrt_b;
     p.sqrt_p = sqrt_p;
     p.dir_coef = sqrt_1mp;
-    launch_ew<kDdim>(p, n, as_stream(stream));
+    launch_ew<kDdim>(p, n, io_dtype, as_stream(stream));
     DM_LAUNCHED();
     return DM_OK;
 }
+extern "C" int dm_sched_ddim_update(const float* x, const float* x0, float* prev, long long n, float sqrt_a,
+                                    float sqrt_b, float sqrt_p, float sqrt_1mp, const float* coef,
+                                    dm_stream_t stream) {
+    return dm_sched_ddim_update_io(x, x0, prev, n, sqrt_a, sqrt_b, sqrt_p, sqrt_1mp, coef, DM_IO_F32, stream);
+}
 
-extern "C" int dm_sched_dps_update(const float* x, const float* x0, const float* g0, const float* z, float* prev,
-                                   long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std,
-                                   float rate, const float* coef, dm_stream_t stream) {
-    DM_REQUIRE(x && x0 && g0 && prev && n > 0);
+extern "C" int dm_sched_dps_update_io(const void* x, const float* x0, const float* g0, const float* z, void* prev,
+                                      long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef,
+                                      float std, float rate, const float* coef, int io_dtype, dm_stream_t stream) {
+    DM_REQUIRE(x && x0 && g0 && prev && n > 0 && io_ok(io_dtype));
     EwParams p{};
     p.coef = coef;
     p.x = x;
@@ -405,54 +483,82 @@ extern "C" int dm_sched_dps_update(const float* x, const float* x0, const float*
     p.dir_coef = dir_coef;
     p.std = std;
     p.rate = rate;
-    launch_ew<kDps>(p, n, as_stream(stream));
+    launch_ew<kDps>(p, n, io_dtype, as_stream(stream));
     DM_LAUNCHED();
     return DM_OK;
 }
+extern "C" int dm_sched_dps_update(const float* x, const float* x0, const float* g0, const float* z, float* prev,
+                                   long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std,
+                                   float rate, const float* coef, dm_stream_t stream) {
+    return dm_sched_dps_update_io(x, x0, g0, z, prev, n, sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate, coef, DM_IO_F32,
+                                  stream);
+}
 
+extern "C" int dm_sched_mpgd_update_io(const void* x, const float* x0, const float* g0, const float* z, void* prev,
+                                       void* x0_out, long long n, float sqrt_a, float sqrt_b, float sqrt_p,
+                                       float dir_coef, float std, float rate, const float* coef, int io_dtype,
+                                       dm_stream_t stream) {
+    DM_REQUIRE(x && x0 && g0 && prev && x0_out && n > 0 && io_ok(io_dtype));
+    EwParams p{};
+    p.coef = coef;
+    p.x = x;
+    p.x0 = x0;
+    p.g0 = g0;
+    p.z = z;
+    p.prev = prev;
+    if (io_dtype == DM_IO_F32) p.x0_out = static_cast<float*>(x0_out);
+    else p.x0_pub = x0_out;
+    p.sqrt_a = sqrt_a;
+    p.sqrt_b = sqrt_b;
+    p.sqrt_p = sqrt_p;
+    p.dir_coef = dir_coef;
+    p.std = std;
+    p.rate = rate;
+    launch_ew<kMpgd>(p, n, io_dtype, as_stream(stream));
+    DM_LAUNCHED();
+    return DM_OK;
+}
 extern "C" int dm_sched_mpgd_update(const float* x, const float* x0, const float* g0, const float* z, float* prev,
                                     float* x0_out, long long n, float sqrt_a, float sqrt_b, float sqrt_p,
                                     float dir_coef, float std, float rate, const float* coef,
                                     dm_stream_t stream) {
-    DM_REQUIRE(x && x0 && g0 && prev && x0_out && n > 0);
-    EwParams p{};
-    p.coef = coef;
-    p.x = x;
-    p.x0 = x0;
-    p.g0 = g0;
-    p.z = z;
-    p.prev = prev;
-    p.x0_out = x0_out;
-    p.sqrt_a = sqrt_a;
-    p.sqrt_b = sqrt_b;
-    p.sqrt_p = sqrt_p;
-    p.dir_coef = dir_coef;
-    p.std = std;
-    p.rate = rate;
-    launch_ew<kMpgd>(p, n, as_stream(stream));
+    return dm_sched_mpgd_update_io(x, x0, g0, z, prev, x0_out, n, sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate, coef,
+                                   DM_IO_F32, stream);
+}
+
+extern "C" int dm_sched_dsg_update_io(const float* x0, const void* eps, const float* g0, const float* z, void* prev,
+                                      int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef,
+                                      float std, float rate, float r, float grad_scale, float e, const float* coef,
+                                      int io_dtype, dm_stream_t stream) {
+    DM_REQUIRE(x0 && eps && g0 && z && prev && n_clips > 0 && n_clip > 0 && io_ok(io_dtype));
+    NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, 0.f, coef};
+    launch_norm<kDsg>(p, n_clips, io_dtype, as_stream(stream));
     DM_LAUNCHED();
     return DM_OK;
 }
-
 extern "C" int dm_sched_dsg_update(const float* x0, const float* eps, const float* g0, const float* z, float* prev,
                                    int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef,
                                    float std, float rate, float r, float grad_scale, float e, const float* coef,
                                    dm_stream_t stream) {
-    DM_REQUIRE(x0 && eps && g0 && z && prev && n_clips > 0 && n_clip > 0);
-    NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, 0.f, coef};
-    launch_norm<kDsg>(p, n_clips, as_stream(stream));
+    return dm_sched_dsg_update_io(x0, eps, g0, z, prev, n_clips, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, r,
+                                  grad_scale, e, coef, DM_IO_F32, stream);
+}
+
+extern "C" int dm_sched_diffmusic_update_io(const float* x0, const void* eps, const float* g0, const float* z,
+                                            void* prev, int n_clips, long long n_clip, float sqrt_a, float sqrt_p,
+                                            float dir_coef, float std, float rate, float grad_scale, float e,
+                                            float threshold, const float* coef, int io_dtype, dm_stream_t stream) {
+    DM_REQUIRE(x0 && eps && g0 && z && prev && n_clips > 0 && n_clip > 0 && io_ok(io_dtype));
+    NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, 0.f, grad_scale, e, threshold,
+                 coef};
+    launch_norm<kDiffMusic>(p, n_clips, io_dtype, as_stream(stream));
     DM_LAUNCHED();
     return DM_OK;
 }
-
 extern "C" int dm_sched_diffmusic_update(const float* x0, const float* eps, const float* g0, const float* z,
                                          float* prev, int n_clips, long long n_clip, float sqrt_a, float sqrt_p,
                                          float dir_coef, float std, float rate, float grad_scale, float e,
                                          float threshold, const float* coef, dm_stream_t stream) {
-    DM_REQUIRE(x0 && eps && g0 && z && prev && n_clips > 0 && n_clip > 0);
-    NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, 0.f, grad_scale, e, threshold,
-                 coef};
-    launch_norm<kDiffMusic>(p, n_clips, as_stream(stream));
-    DM_LAUNCHED();
-    return DM_OK;
+    return dm_sched_diffmusic_update_io(x0, eps, g0, z, prev, n_clips, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate,
+                                        grad_scale, e, threshold, coef, DM_IO_F32, stream);
 }

@@ -93,18 +93,26 @@ class _GuidedBase(DDIMBase):
                                       "thresholding (every shipped config, configs/model/*.yaml)")
 
     @staticmethod
-    def _prep(t):
-        _lib.require_cuda(t)
-        return t.detach().float().contiguous()
+    def _prep_pair(sample, model_output):
+        """(x, eps, io): the two latent-typed inputs as the kernels read them.  fp32 / fp16 / bf16 are consumed as they
+        are (dm_sched_*_io convert on load and store); anything else, or mixed dtypes, goes through
+        fp32."""
+        _lib.require_cuda(sample, model_output)
+        x, e = sample.detach(), model_output.detach()
+        if x.dtype != e.dtype or x.dtype not in _lib.IO_DTYPES:
+            x, e = x.float(), e.float()
+        return x.contiguous(), e.contiguous(), _lib.IO_DTYPES[x.dtype]
 
-    def _x0(self, x, eps, c):
-        """dm_sched_x0: pred_original_sample of the diffusers base step."""
+    def _x0(self, x, eps, c, io, publish=True):
+        """dm_sched_x0_io: pred_original_sample of the diffusers base step.  Returns (x0 fp32 kept by the step,
+        x0 in the latent dtype for the caller -- the same tensor for fp32 pipelines)."""
         self._check_supported()
-        x0 = torch.empty_like(x)
-        _lib.call("dm_sched_x0", x.data_ptr(), eps.data_ptr(), x0.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"],
-                  int(bool(self.config.clip_sample)), float(self.config.clip_sample_range), self._coef_ptr(),
-                  _lib.stream())
-        return x0
+        x0 = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        pub = torch.empty_like(x) if (io != 0 and publish) else None
+        _lib.call("dm_sched_x0_io", x.data_ptr(), eps.data_ptr(), x0.data_ptr(), _lib.ptr(pub), x.numel(), c["sqrt_a"],
+                  c["sqrt_b"], int(bool(self.config.clip_sample)), float(self.config.clip_sample_range),
+                  self._coef_ptr(), io, _lib.stream())
+        return x0, (x0 if pub is None else pub)
 
     #: which noise the step consumes: "eta" = base-step draw (discarded) + own z when eta > 0 (DDIM/DPS/MPGD);
     #: "always" = exactly one z per step, independent of eta (DSG/DiffMusic, scheduling_dsg.py:215-220)
@@ -187,8 +195,8 @@ class _GuidedBase(DDIMBase):
         written in the reference, a no-op on the embeddings (the SGD steps act on discarded clones, :94-96): it returns
         the embeddings detached.  Kept for API compatibility; the guided loss is still evaluated so errors surface."""
         c = self._coeffs(timestep, eta)
-        x, eps = self._prep(sample), self._prep(model_output)
-        x0 = self._x0(x, eps, c)
+        x, eps, io = self._prep_pair(sample, model_output)
+        x0, _ = self._x0(x, eps, c, io, publish=False)
         self._guidance(x0, measurement, vae, vocoder, original_waveform_length, supervised_space, sample.dtype)
         return InverseProblemSchedulerOutput(
             encoder_hidden_states=None if encoder_hidden_states is None else encoder_hidden_states.detach(),
@@ -204,14 +212,14 @@ class DDIMScheduler(_GuidedBase):
              original_waveform_length: int = 0, encoder_hidden_states=None, encoder_hidden_states_1=None, *args,
              _noise=None, **kwargs):
         c = self._coeffs(timestep, eta)
-        x, eps = self._prep(sample), self._prep(model_output)
+        x, eps, io = self._prep_pair(sample, model_output)
         self._noise_arg(_noise, eta, generator, variance_noise, model_output)
-        x0 = self._x0(x, eps, c)
+        x0, x0_pub = self._x0(x, eps, c, io)
         prev = torch.empty_like(x)
-        _lib.call("dm_sched_ddim_update", x.data_ptr(), x0.data_ptr(), prev.data_ptr(), x.numel(), c["sqrt_a"],
-                  c["sqrt_b"], c["sqrt_p"], c["sqrt_1mp"], self._coef_ptr(), _lib.stream())
+        _lib.call("dm_sched_ddim_update_io", x.data_ptr(), x0.data_ptr(), prev.data_ptr(), x.numel(), c["sqrt_a"],
+                  c["sqrt_b"], c["sqrt_p"], c["sqrt_1mp"], self._coef_ptr(), io, _lib.stream())
         return InverseProblemSchedulerOutput(
-            prev_sample=prev.to(sample.dtype), pred_original_sample=x0.to(sample.dtype),
+            prev_sample=prev.to(sample.dtype), pred_original_sample=x0_pub.to(sample.dtype),
             loss=torch.tensor([int(timestep)]),
             encoder_hidden_states=None if encoder_hidden_states is None else encoder_hidden_states.detach(),
             encoder_hidden_states_1=None if encoder_hidden_states_1 is None else encoder_hidden_states_1.detach())
@@ -225,18 +233,18 @@ class DPSScheduler(_GuidedBase):
              ip_guidance_rate: float = 5e-4, vae=None, vocoder=None, original_waveform_length: int = 0,
              supervised_space: str = "mel_spectrogram", *args, _noise=None, **kwargs):
         c = self._coeffs(timestep, eta)
-        x, eps = self._prep(sample), self._prep(model_output)
+        x, eps, io = self._prep_pair(sample, model_output)
         z = self._noise_arg(_noise, eta, generator, variance_noise, model_output)
-        x0 = self._x0(x, eps, c)
+        x0, x0_pub = self._x0(x, eps, c, io)
         losses, g0 = self._guidance(x0, measurement, vae, vocoder, original_waveform_length, supervised_space,
                                     sample.dtype)
         prev = torch.empty_like(x)
-        _lib.call("dm_sched_dps_update", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), _lib.ptr(z), prev.data_ptr(),
+        _lib.call("dm_sched_dps_update_io", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), _lib.ptr(z), prev.data_ptr(),
                   x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"], float(ip_guidance_rate),
-                  self._coef_ptr(), _lib.stream())
+                  self._coef_ptr(), io, _lib.stream())
         return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
-                                             pred_original_sample=x0.to(sample.dtype), loss=self._loss_out(losses),
-                                             loss_per_clip=losses)
+                                             pred_original_sample=x0_pub.to(sample.dtype),
+                                             loss=self._loss_out(losses), loss_per_clip=losses)
 
 
 class MPGDScheduler(_GuidedBase):
@@ -247,15 +255,15 @@ class MPGDScheduler(_GuidedBase):
              ip_guidance_rate: float = 1.0, vae=None, vocoder=None, original_waveform_length: int = 0,
              supervised_space: str = "mel_spectrogram", *args, _noise=None, **kwargs):
         c = self._coeffs(timestep, eta)
-        x, eps = self._prep(sample), self._prep(model_output)
+        x, eps, io = self._prep_pair(sample, model_output)
         z = self._noise_arg(_noise, eta, generator, variance_noise, model_output)
-        x0 = self._x0(x, eps, c)
+        x0, _ = self._x0(x, eps, c, io, publish=False)
         losses, g0 = self._guidance(x0, measurement, vae, vocoder, original_waveform_length, supervised_space,
                                     sample.dtype)
         prev, x0_new = torch.empty_like(x), torch.empty_like(x)
-        _lib.call("dm_sched_mpgd_update", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), _lib.ptr(z), prev.data_ptr(),
+        _lib.call("dm_sched_mpgd_update_io", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), _lib.ptr(z), prev.data_ptr(),
                   x0_new.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"],
-                  float(ip_guidance_rate), self._coef_ptr(), _lib.stream())
+                  float(ip_guidance_rate), self._coef_ptr(), io, _lib.stream())
         return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
                                              pred_original_sample=x0_new.to(sample.dtype),
                                              loss=self._loss_out(losses), loss_per_clip=losses)
@@ -269,10 +277,10 @@ class _SphericalBase(_GuidedBase):
     def _spherical_step(self, kernel, model_output, timestep, sample, eta, generator, variance_noise, measurement,
                         vae, vocoder, L, ip_guidance_rate, eps, supervised_space, _noise=None):
         c = self._coeffs(timestep, eta)
-        x, e = self._prep(sample), self._prep(model_output)
+        x, e, io = self._prep_pair(sample, model_output)
         # one draw per step (scheduling_dsg.py:215-220; `variance_noise` is not consulted by the reference there)
         z = self._noise_arg(_noise, eta, generator, variance_noise, model_output)
-        x0 = self._x0(x, e, c)  # base step called without eta (scheduling_dsg.py:178-186): no RNG side effect
+        x0, x0_pub = self._x0(x, e, c, io)  # base step called without eta (scheduling_dsg.py:178-186): no RNG draw
         losses, g0 = self._guidance(x0, measurement, vae, vocoder, L, supervised_space, sample.dtype)
         B = x.shape[0]
         n_clip = x.numel() // B
@@ -280,16 +288,16 @@ class _SphericalBase(_GuidedBase):
         if kernel == "dsg":
             # r = sqrt(c*h*w) * std as fp32 (scheduling_dsg.py:212-213)
             r = _f(torch.sqrt(torch.tensor(n_clip)) * c["std"])
-            _lib.call("dm_sched_dsg_update", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), z.data_ptr(),
+            _lib.call("dm_sched_dsg_update_io", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), z.data_ptr(),
                       prev.data_ptr(), B, n_clip, c["sqrt_a"], c["sqrt_p"], c["dir_coef"], c["std"],
-                      float(ip_guidance_rate), r, 1.0 / 1000.0, float(eps), self._coef_ptr(), _lib.stream())
+                      float(ip_guidance_rate), r, 1.0 / 1000.0, float(eps), self._coef_ptr(), io, _lib.stream())
         else:
-            _lib.call("dm_sched_diffmusic_update", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), z.data_ptr(),
+            _lib.call("dm_sched_diffmusic_update_io", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), z.data_ptr(),
                       prev.data_ptr(), B, n_clip, c["sqrt_a"], c["sqrt_p"], c["dir_coef"], c["std"],
-                      float(ip_guidance_rate), 1.0 / 1000.0, float(eps), 0.9995, self._coef_ptr(), _lib.stream())
+                      float(ip_guidance_rate), 1.0 / 1000.0, float(eps), 0.9995, self._coef_ptr(), io, _lib.stream())
         return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
-                                             pred_original_sample=x0.to(sample.dtype), loss=self._loss_out(losses),
-                                             loss_per_clip=losses)
+                                             pred_original_sample=x0_pub.to(sample.dtype),
+                                             loss=self._loss_out(losses), loss_per_clip=losses)
 
 
 class DSGScheduler(_SphericalBase):

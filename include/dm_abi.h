@@ -75,6 +75,33 @@ int dm_sched_diffmusic_update(const float* x0, const float* eps, const float* g0
                               float rate, float grad_scale, float e, float threshold, const float* coef,
                               dm_stream_t stream);
 
+/* ---- the same six entry points with a dtype for the LATENT-TYPED tensors ----
+ * The reference pipelines run in fp16 (run.py:218): `sample`, `model_output` come in and `prev_sample`,
+ * `pred_original_sample` go back in the pipeline's dtype.  With io_dtype = DM_IO_F16 / DM_IO_BF16 the kernels read x / eps
+ * and write prev (and x0_pub, the caller's copy of x0) in that type directly -- no cast kernels around the step; the
+ * step's own x0, the gradient g0, the noise z and all arithmetic stay fp32.  DM_IO_F32 = the functions above. */
+#define DM_IO_F32 0
+#define DM_IO_F16 1
+#define DM_IO_BF16 2
+int dm_sched_x0_io(const void* x, const void* eps, float* x0, void* x0_pub /* may be NULL */, long long n, float sqrt_a,
+                   float sqrt_b, int clip, float clip_range, const float* coef, int io_dtype, dm_stream_t stream);
+int dm_sched_ddim_update_io(const void* x, const float* x0, void* prev, long long n, float sqrt_a, float sqrt_b,
+                            float sqrt_p, float sqrt_1mp, const float* coef, int io_dtype, dm_stream_t stream);
+int dm_sched_dps_update_io(const void* x, const float* x0, const float* g0, const float* z, void* prev, long long n,
+                           float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std, float rate,
+                           const float* coef, int io_dtype, dm_stream_t stream);
+/* x0_out is latent-typed here (it is only handed back to the caller) */
+int dm_sched_mpgd_update_io(const void* x, const float* x0, const float* g0, const float* z, void* prev, void* x0_out,
+                            long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std,
+                            float rate, const float* coef, int io_dtype, dm_stream_t stream);
+int dm_sched_dsg_update_io(const float* x0, const void* eps, const float* g0, const float* z, void* prev, int n_clips,
+                           long long n_clip, float sqrt_a, float sqrt_p, float dir_coef, float std, float rate,
+                           float r, float grad_scale, float e, const float* coef, int io_dtype, dm_stream_t stream);
+int dm_sched_diffmusic_update_io(const float* x0, const void* eps, const float* g0, const float* z, void* prev,
+                                 int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef, float std,
+                                 float rate, float grad_scale, float e, float threshold, const float* coef,
+                                 int io_dtype, dm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * STFT / mel guidance  (operator.py:24-36,123-124 T_mel ; 153-154 phase mel ; 162-171 |STFT|)
  * ---------------------------------------------------------------------------------------------------------------- */

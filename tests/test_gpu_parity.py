@@ -802,3 +802,49 @@ def test_fp16_pipeline_dtype_is_accepted():
     assert torch.isfinite(half.prev_sample).all() and torch.isfinite(half.loss)
     assert rel_l2(half.prev_sample.float(), full.prev_sample) < 5e-3
     assert abs(float(half.loss) - float(full.loss)) < 2e-2 * float(full.loss)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n_lat", [25, 26])
+def test_latent_io_dtypes_are_exact_roundings_of_the_fp32_step(dt, n_lat):
+    """dm_sched_*_io read / write 16-bit latents directly: with no network in the loop (DDIM) the result must be the
+    fp32 step on the up-cast inputs, rounded once to the latent dtype -- bit for bit (vector and scalar paths)."""
+    B = 3
+    x, e = stubs.synth_latents(B, n_lat)
+    if n_lat == 26:  # odd element count per tensor -> scalar (W = 1) kernels
+        x, e = x[..., :15].contiguous(), e[..., :15].contiguous()
+    x, e = x.to(DEV).to(dt), e.to(DEV).to(dt)
+    sched = dm.DDIMScheduler(operator=None, **stubs.MUSICLDM_SCHED)
+    sched.set_timesteps(500)
+    for t in (999, 501, 1):
+        got = sched.step(e, t, x)
+        want = sched.step(e.float(), t, x.float())
+        assert got.prev_sample.dtype == dt and got.pred_original_sample.dtype == dt
+        assert torch.equal(got.prev_sample, want.prev_sample.to(dt)), t
+        assert torch.equal(got.pred_original_sample, want.pred_original_sample.to(dt)), t
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 5e-3), (torch.bfloat16, 4e-2)])
+@pytest.mark.parametrize("sched_name,op_name,eta", [("dps", "super_resolution", 0.0), ("mpgd", "inpainting", 1.0),
+                                                    ("dsg", "phase_retrieval", 1.0),
+                                                    ("diffmusic", "inpainting", 1.0)])
+def test_guided_steps_in_16_bit_pipelines(sched_name, op_name, eta, dt, tol):
+    """every guided scheduler with 16-bit latents and 16-bit networks (run.py:218) stays close to its fp32 step; the
+    outputs come back in the pipeline's dtype, the per-clip loss in fp32."""
+    B = 2
+    x, e = stubs.synth_latents(B, 25)
+    op = _ops()[op_name]
+    sched = dm.get_scheduler(sched_name)(operator=op, **stubs.MUSICLDM_SCHED)
+    sched.set_timesteps(500)
+    meas = op.forward(stubs.synth_clips(1, L1, first=50).to(DEV))
+    kw = dict(eta=eta, measurement=meas, original_waveform_length=L1, ip_guidance_rate=RATES[sched_name])
+    z = torch.randn(B, 8, 25, 16, generator=torch.Generator().manual_seed(7)).to(DEV)
+    vae, voc = stubs.StubVAE().to(DEV), stubs.StubVocoder().to(DEV)
+    full = sched.step(e.to(DEV), 501, x.to(DEV), vae=vae, vocoder=voc, _noise=z, **kw)
+    low = sched.step(e.to(DEV).to(dt), 501, x.to(DEV).to(dt), vae=stubs.StubVAE().to(DEV).to(dt),
+                     vocoder=stubs.StubVocoder().to(DEV).to(dt), _noise=z, **kw)
+    assert low.prev_sample.dtype == dt and low.pred_original_sample.dtype == dt
+    assert low.loss_per_clip.dtype == torch.float32 and torch.isfinite(low.prev_sample).all()
+    assert rel_l2(low.prev_sample.float(), full.prev_sample) < tol
+    assert rel_l2(low.pred_original_sample.float(), full.pred_original_sample) < tol
+    assert rel_l2(low.loss_per_clip, full.loss_per_clip) < 4 * tol
