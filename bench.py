@@ -257,6 +257,8 @@ def main():
             loss_pin[: lo.numel()].copy_(lo.reshape(-1), non_blocking=True)
         return out
 
+    host_ms = {}
+
     def pipelined_region():
         """e2e through HostPipelinedStep: pinned-host latents in, prev_sample + per-clip loss out, uploads of step i+1
         and downloads of step i-1 overlapped with step i.  Every copy is issued after the start event of a timed
@@ -269,6 +271,7 @@ def main():
         def sequence(n, first, timed):
             pipe = dm.HostPipelinedStep(graphed)
             brackets = []
+            t_host0 = time.perf_counter()
             for i in range(n):
                 if timed:
                     flush.fill_(float(i))
@@ -281,6 +284,7 @@ def main():
                 pipe.step(ts[(first + i) % len(ts)], prevs_pin[i % 2], losses_pin[i % 2], generator=gens)
                 t.record()
                 brackets.append((s, t))
+            host_ms["e2e"] = (time.perf_counter() - t_host0) * 1e3 / max(n, 1)  # host enqueue time per step
             s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             pipe.drain()
@@ -315,6 +319,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         launches0 = _lib.launch_count()
+        t_host0 = time.perf_counter()
         for i in range(args.steps):
             flush.fill_(float(i))  # evict L2 between timed iterations (not timed)
             s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -322,6 +327,7 @@ def main():
             one_step(args.warmup + i, host)
             t.record()
             per_step.append((s, t))
+        host_ms["host" if host else "device"] = (time.perf_counter() - t_host0) * 1e3 / args.steps
         torch.cuda.synchronize()
         launches = _lib.launch_count() - launches0
         if graphed is not None:
@@ -383,7 +389,9 @@ def main():
                         "d2h_bytes_per_step": x_h.numel() * 4 + B * 4, "ms_per_step": e2e_ms / args.steps,
                         "mode": "serial copies" if e2e_ms is e2e_serial_ms else
                         "HostPipelinedStep: uploads / downloads of neighbouring steps overlap the step (3 streams)",
-                        "serial_ms_per_step": e2e_serial_ms / args.steps},
+                        "serial_ms_per_step": e2e_serial_ms / args.steps,
+                        "host_enqueue_ms_per_step": host_ms.get("e2e")},
+                "host_enqueue_ms_per_step": host_ms.get("device"),
                 "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -42,7 +42,7 @@ class GraphedGuidedStep:
         needs_noise = scheduler.noise_mode == "always" or (self.eta > 0 and type(scheduler).__name__ != "DDIMScheduler")
         self.z = torch.zeros(sample_shape, device=dev, dtype=torch.float32) if needs_noise else None
         self.coef = torch.zeros(8, device=dev, dtype=torch.float32)
-        self.coef_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._coef_rows = {}
         self.op = scheduler.operator
         self._ir_host = self._ir_dev = None
         if hasattr(self.op, "generate_impulse_response"):  # dereverberation: IR redrawn on the host every step
@@ -81,8 +81,11 @@ class GraphedGuidedStep:
             self.z.copy_(z, non_blocking=True)
         elif self.eta > 0:
             self.sched.draw_step_noise(self.eta, generator, variance_noise, self.e)  # DDIM: discarded draw
-        self.coef_host.copy_(self.sched.coef_vector(timestep, self.eta, self.n_clip))
-        self.coef.copy_(self.coef_host, non_blocking=True)
+        row = self._coef_rows.get(timestep)
+        if row is None:  # one pinned 32-byte row per timestep, built once (host-side scalar math is slow)
+            row = self.sched.coef_vector(timestep, self.eta, self.n_clip).clone().pin_memory()
+            self._coef_rows[timestep] = row
+        self.coef.copy_(row, non_blocking=True)
         if self._ir_host is not None:
             ir = self.op.generate_impulse_response(ir_length=self.op.ir_length, decay_factor=self.op.decay_factor)
             self.op.last_ir = ir

@@ -62,6 +62,15 @@ class _GuidedBase(DDIMBase):
 
     # ---- coefficient prep (scheduling_dps.py:157-162): 0-d fp32 CPU tensors, exactly the reference's arithmetic ----
     def _coeffs(self, timestep, eta):
+        """per-timestep scalars, memoised: the ~15 0-d torch ops below cost more host time than a whole graph replay
+        takes on the device, and the guided loop visits each (timestep, eta) once per clip batch."""
+        key = (int(timestep), float(eta), self.num_inference_steps)
+        cache = self.__dict__.setdefault("_coef_cache", {})
+        if key not in cache:
+            cache[key] = self._coeffs_uncached(timestep, eta)
+        return cache[key]
+
+    def _coeffs_uncached(self, timestep, eta):
         t = int(timestep)
         t_prev = t - self.config.num_train_timesteps // self.num_inference_steps
         a_t = self.alphas_cumprod[t]
@@ -81,11 +90,15 @@ class _GuidedBase(DDIMBase):
 
     def coef_vector(self, timestep, eta, n_clip):
         """[sqrt_a, sqrt_b, sqrt_p, dir_coef, std, r, 0, 0] as fp32 -- the layout dm_sched_* read from `coef`."""
-        c = self._coeffs(timestep, eta)
-        dirc = c["sqrt_1mp"] if isinstance(self, DDIMScheduler) else c["dir_coef"]
-        r = _f(torch.sqrt(torch.tensor(n_clip)) * c["std"])
-        return torch.tensor([c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], dirc, c["std"], r, 0.0, 0.0],
-                            dtype=torch.float32)
+        key = ("vec", int(timestep), float(eta), self.num_inference_steps, int(n_clip))
+        cache = self.__dict__.setdefault("_coef_cache", {})
+        if key not in cache:
+            c = self._coeffs(timestep, eta)
+            dirc = c["sqrt_1mp"] if isinstance(self, DDIMScheduler) else c["dir_coef"]
+            r = _f(torch.sqrt(torch.tensor(n_clip)) * c["std"])
+            cache[key] = torch.tensor([c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], dirc, c["std"], r, 0.0, 0.0],
+                                      dtype=torch.float32)
+        return cache[key]
 
     def _check_supported(self):
         if self.config.prediction_type != "epsilon" or self.config.thresholding:
