@@ -43,6 +43,13 @@ _SIGNATURES = {
                                      c_i, c_p]),
     "dm_sched_diffmusic_update_io": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
                                            c_f, c_p, c_i, c_p]),
+    "dm_stft_guidance_io": (c_i, [C.POINTER(StftTables), c_i, c_i, c_i, c_p, c_i, c_ll, c_ll, c_p, c_i, c_p, c_ll, c_p,
+                                  c_f, c_p, c_p, c_p, c_i, c_p]),
+    "dm_residual_wav_io": (c_i, [c_p, c_i, c_ll, c_ll, c_i, c_p, c_p, c_ll, c_p, c_p, c_p]),
+    "dm_fold_adjoint_io": (c_i, [c_p, c_i, c_ll, c_i, c_p, c_p, c_i, c_p, c_i, c_ll, c_p, c_p]),
+    "dm_resample_fwd_io": (c_i, [c_p, c_i, c_ll, c_ll, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_ll, c_p]),
+    "dm_resample_adjoint_io": (c_i, [c_p, c_i, c_ll, c_i, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_ll, c_ll,
+                                     c_p, c_p]),
     "dm_stft_set_engine": (c_i, [c_i]),
     "dm_stft_num_tiles": (c_i, [c_ll, c_i, c_i]),
     "dm_stft_guidance": (c_i, [C.POINTER(StftTables), c_i, c_i, c_i, c_p, c_ll, c_ll, c_p, c_i, c_p, c_ll, c_p, c_f,

@@ -62,6 +62,7 @@ inline int fail(int code, const char* fmt, A... a) {
         }                                                                                                  \
     } while (0)
 
+inline bool io_dtype_ok(int io) { return io == DM_IO_F32 || io == DM_IO_F16 || io == DM_IO_BF16; }
 inline cudaStream_t as_stream(dm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline int num_sms() {
@@ -77,6 +78,28 @@ inline int num_sms() {
 
 // ---- device helpers ----
 #if defined(__CUDACC__)
+}  // namespace dm
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+namespace dm {
+// Waveform-typed tensors (the vocoder output handed to the operators, and dLoss/dwav handed back to autograd) may be
+// fp32, fp16 or bf16 (DM_IO_*): converted on load / store, all arithmetic in fp32.
+__device__ __forceinline__ float ld_wave(const void* __restrict__ p, int io, long long i) {
+    if (io == DM_IO_F16) return __half2float(static_cast<const __half*>(p)[i]);
+    if (io == DM_IO_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+    return static_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void st_wave(void* __restrict__ p, int io, long long i, float v) {
+    if (io == DM_IO_F16) static_cast<__half*>(p)[i] = __float2half_rn(v);
+    else if (io == DM_IO_BF16) static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+    else static_cast<float*>(p)[i] = v;
+}
+__device__ __forceinline__ const void* wave_row(const void* p, int io, long long elems) {
+    return static_cast<const char*>(p) + elems * (io == DM_IO_F32 ? 4 : 2);
+}
+__device__ __forceinline__ void* wave_row(void* p, int io, long long elems) {
+    return static_cast<char*>(p) + elems * (io == DM_IO_F32 ? 4 : 2);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -19,7 +19,8 @@ __device__ __forceinline__ float ybar_at(const float* __restrict__ yb, int pad, 
 }
 
 // ---------------------------------------------------------------------------------------------------- residual
-__global__ void __launch_bounds__(kEwThreads) residual_wav_kernel(const float* __restrict__ y, long long y_bstride,
+__global__ void __launch_bounds__(kEwThreads) residual_wav_kernel(const void* __restrict__ y, int y_io,
+                                                                  long long y_bstride,
                                                                   long long n, const float* __restrict__ mask,
                                                                   const float* __restrict__ meas,
                                                                   long long meas_bstride, float* __restrict__ ybar,
@@ -28,12 +29,12 @@ __global__ void __launch_bounds__(kEwThreads) residual_wav_kernel(const float* _
     const int b = blockIdx.y;
     const long long lo = (long long)blockIdx.x * DM_RESID_CHUNK;
     const long long hi = min(n, lo + DM_RESID_CHUNK);
-    const float* yb = y + (long long)b * y_bstride;
+    const void* yb = wave_row(y, y_io, (long long)b * y_bstride);
     const float* mb = meas + (long long)b * meas_bstride;
     float* ob = ybar + (long long)b * n;
     float s = 0.f;
     for (long long i = lo + threadIdx.x; i < hi; i += kEwThreads) {
-        float v = yb[i];
+        float v = ld_wave(yb, y_io, i);
         if (mask) v *= __ldg(mask + i);
         float d = mb[i] - v;
         ob[i] = -d;
@@ -53,7 +54,8 @@ __global__ void __launch_bounds__(kEwThreads) residual_wav_kernel(const float* _
 __global__ void __launch_bounds__(kEwThreads) fold_adjoint_kernel(const float* __restrict__ ybar, int pad,
                                                                   long long Ly, const float* __restrict__ mask,
                                                                   const float* __restrict__ partial, int ntiles,
-                                                                  float* __restrict__ dwav, long long dwav_bstride,
+                                                                  void* __restrict__ dwav, int dwav_io,
+                                                                  long long dwav_bstride,
                                                                   float* __restrict__ loss) {
     __shared__ float scratch[2];
     const int b = blockIdx.y;
@@ -62,13 +64,13 @@ __global__ void __launch_bounds__(kEwThreads) fold_adjoint_kernel(const float* _
     if (dwav == nullptr) return;  // loss only
     const float sc = inv_loss(l);
     const float* yb = ybar + (long long)b * (Ly + 2 * pad);
-    float* ob = dwav + (long long)b * dwav_bstride;
+    void* ob = wave_row(dwav, dwav_io, (long long)b * dwav_bstride);
     const long long lo = (long long)blockIdx.x * (kEwThreads * 8);
     const long long hi = min(Ly, lo + kEwThreads * 8);
     for (long long j = lo + threadIdx.x; j < hi; j += kEwThreads) {
         float v = ybar_at(yb, pad, j, Ly) * sc;
         if (mask) v *= __ldg(mask + j);
-        ob[j] = v;
+        st_wave(ob, dwav_io, j, v);
     }
 }
 
@@ -239,30 +241,61 @@ __device__ __forceinline__ void load_taps28(const float* __restrict__ kernel, fl
     }
 }
 
-__global__ void __launch_bounds__(kEwThreads) resample2_fwd_reg_kernel(const float* __restrict__ x, long long x_bstride,
+// 8 consecutive 16-bit values (one 128-bit load) to fp32
+template <int IO>
+__device__ __forceinline__ void unpack8(const uint4 raw, float* o) {
+    const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f;
+        if (IO == DM_IO_F16) f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        o[2 * i] = f.x;
+        o[2 * i + 1] = f.y;
+    }
+}
+template <int IO>
+__device__ __forceinline__ uint4 pack8(const float* v) {
+    unsigned w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (IO == DM_IO_F16) *reinterpret_cast<__half2*>(&w[i]) = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        else *reinterpret_cast<__nv_bfloat162*>(&w[i]) = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int IO>
+__global__ void __launch_bounds__(kEwThreads) resample2_fwd_reg_kernel(const void* __restrict__ x, long long x_bstride,
                                                                        long long L, const float* __restrict__ kernel,
                                                                        float* __restrict__ y, long long Ly) {
     const int b = blockIdx.y;
     const long long j0 = ((long long)blockIdx.x * kEwThreads + threadIdx.x) * kFir2Out;
     if (j0 >= Ly) return;
-    const float* xb = x + (long long)b * x_bstride;
+    const void* xb = wave_row(x, IO, (long long)b * x_bstride);
     const long long x0 = 2 * j0 - 16;
     float win[kFir2FwdWin];
     if (x0 >= 0 && x0 + kFir2FwdWin <= L) {
-        const float4* src = reinterpret_cast<const float4*>(xb + x0);
+        if (IO == DM_IO_F32) {
+            const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(xb) + x0);
 #pragma unroll
-        for (int q = 0; q < kFir2FwdWin / 4; ++q) {
-            const float4 t = src[q];
-            win[4 * q] = t.x;
-            win[4 * q + 1] = t.y;
-            win[4 * q + 2] = t.z;
-            win[4 * q + 3] = t.w;
+            for (int q = 0; q < kFir2FwdWin / 4; ++q) {
+                const float4 t = src[q];
+                win[4 * q] = t.x;
+                win[4 * q + 1] = t.y;
+                win[4 * q + 2] = t.z;
+                win[4 * q + 3] = t.w;
+            }
+        } else {
+            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const unsigned short*>(xb) + x0);
+#pragma unroll
+            for (int q = 0; q < kFir2FwdWin / 8; ++q) unpack8<IO>(src[q], win + 8 * q);
         }
     } else {
 #pragma unroll
         for (int n = 0; n < kFir2FwdWin; ++n) {
             const long long g = x0 + n;
-            win[n] = (g >= 0 && g < L) ? xb[g] : 0.f;
+            win[n] = (g >= 0 && g < L) ? ld_wave(xb, IO, g) : 0.f;
         }
     }
     float h[kFir2Taps], out[kFir2Out];
@@ -279,9 +312,10 @@ __global__ void __launch_bounds__(kEwThreads) resample2_fwd_reg_kernel(const flo
     }
 }
 
+template <int IO>
 __global__ void __launch_bounds__(kEwThreads) resample2_adjoint_reg_kernel(
     const float* __restrict__ ybar, int pad, long long Ly, const float* __restrict__ partial, int ntiles,
-    const float* __restrict__ kernel, float* __restrict__ dwav, long long dwav_bstride, long long L,
+    const float* __restrict__ kernel, void* __restrict__ dwav, long long dwav_bstride, long long L,
     float* __restrict__ loss) {
     __shared__ float scratch[2];
     const int b = blockIdx.y;
@@ -318,14 +352,20 @@ __global__ void __launch_bounds__(kEwThreads) resample2_adjoint_reg_kernel(
     float h[kFir2Taps], out[kFir2Out];
     load_taps28(kernel, h);
     fir2_adj8(win, h, out);
-    float* ob = dwav + (long long)b * dwav_bstride + i0;
+    void* ob = wave_row(dwav, IO, (long long)b * dwav_bstride + i0);
+#pragma unroll
+    for (int c = 0; c < kFir2Out; ++c) out[c] *= sc;
     if (i0 + kFir2Out <= L) {
-        reinterpret_cast<float4*>(ob)[0] = make_float4(out[0] * sc, out[1] * sc, out[2] * sc, out[3] * sc);
-        reinterpret_cast<float4*>(ob)[1] = make_float4(out[4] * sc, out[5] * sc, out[6] * sc, out[7] * sc);
+        if (IO == DM_IO_F32) {
+            reinterpret_cast<float4*>(ob)[0] = make_float4(out[0], out[1], out[2], out[3]);
+            reinterpret_cast<float4*>(ob)[1] = make_float4(out[4], out[5], out[6], out[7]);
+        } else {
+            *reinterpret_cast<uint4*>(ob) = pack8<IO>(out);
+        }
     } else {
 #pragma unroll
         for (int c = 0; c < kFir2Out; ++c)
-            if (i0 + c < L) ob[c] = out[c] * sc;
+            if (i0 + c < L) st_wave(ob, IO, c, out[c]);
     }
 }
 
@@ -350,26 +390,95 @@ __global__ void __launch_bounds__(kEwThreads) add_scaled_kernel(float* __restric
 
 using namespace dm;
 
-extern "C" int dm_residual_wav(const float* y, long long y_bstride, long long n, int B, const float* mask,
-                               const float* meas, long long meas_bstride, float* ybar, float* partial,
-                               dm_stream_t stream) {
-    DM_REQUIRE(y && meas && ybar && partial && n > 0 && B > 0);
+extern "C" int dm_residual_wav_io(const void* y, int y_dtype, long long y_bstride, long long n, int B,
+                                  const float* mask, const float* meas, long long meas_bstride, float* ybar,
+                                  float* partial, dm_stream_t stream) {
+    DM_REQUIRE(y && meas && ybar && partial && n > 0 && B > 0 && io_dtype_ok(y_dtype));
     const int ntiles = (int)((n + DM_RESID_CHUNK - 1) / DM_RESID_CHUNK);
-    residual_wav_kernel<<<dim3(ntiles, B), kEwThreads, 0, as_stream(stream)>>>(y, y_bstride, n, mask, meas,
+    residual_wav_kernel<<<dim3(ntiles, B), kEwThreads, 0, as_stream(stream)>>>(y, y_dtype, y_bstride, n, mask, meas,
                                                                                meas_bstride, ybar, partial, ntiles);
     DM_LAUNCHED();
     return DM_OK;
+}
+extern "C" int dm_residual_wav(const float* y, long long y_bstride, long long n, int B, const float* mask,
+                               const float* meas, long long meas_bstride, float* ybar, float* partial,
+                               dm_stream_t stream) {
+    return dm_residual_wav_io(y, DM_IO_F32, y_bstride, n, B, mask, meas, meas_bstride, ybar, partial, stream);
 }
 
 extern "C" int dm_fold_adjoint(const float* ybar, int pad, long long Ly, int B, const float* mask,
                                const float* partial, int ntiles, float* dwav, long long dwav_bstride, float* loss,
                                dm_stream_t stream) {
-    DM_REQUIRE(partial && Ly > 0 && B > 0 && ntiles > 0);
+    return dm_fold_adjoint_io(ybar, pad, Ly, B, mask, partial, ntiles, dwav, DM_IO_F32, dwav_bstride, loss, stream);
+}
+extern "C" int dm_fold_adjoint_io(const float* ybar, int pad, long long Ly, int B, const float* mask,
+                                  const float* partial, int ntiles, void* dwav, int dwav_dtype, long long dwav_bstride,
+                                  float* loss, dm_stream_t stream) {
+    DM_REQUIRE(partial && Ly > 0 && B > 0 && ntiles > 0 && io_dtype_ok(dwav_dtype));
     DM_REQUIRE((dwav == nullptr && loss != nullptr) || ybar != nullptr);
     DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 512));
     const int nblk = dwav ? (int)((Ly + kEwThreads * 8 - 1) / (kEwThreads * 8)) : 1;
     fold_adjoint_kernel<<<dim3(nblk, B), kEwThreads, 0, as_stream(stream)>>>(ybar, pad, Ly, mask, partial, ntiles,
-                                                                             dwav, dwav_bstride, loss);
+                                                                             dwav, dwav_dtype, dwav_bstride, loss);
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+template <int IO>
+static void launch_rs2_fwd(const void* x, long long x_bstride, long long L, int B, const float* kernel, float* y,
+                           long long Ly, cudaStream_t st) {
+    const long long nthr = (Ly + kFir2Out - 1) / kFir2Out;
+    resample2_fwd_reg_kernel<IO><<<dim3((unsigned)((nthr + kEwThreads - 1) / kEwThreads), B), kEwThreads, 0, st>>>(
+        x, x_bstride, L, kernel, y, Ly);
+}
+template <int IO>
+static void launch_rs2_adj(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
+                           const float* kernel, void* dwav, long long dwav_bstride, long long L, float* loss,
+                           cudaStream_t st) {
+    const long long nthr = (L + kFir2Out - 1) / kFir2Out;
+    resample2_adjoint_reg_kernel<IO><<<dim3((unsigned)((nthr + kEwThreads - 1) / kEwThreads), B), kEwThreads, 0, st>>>(
+        ybar, pad, Ly, partial, ntiles, kernel, dwav, dwav_bstride, L, loss);
+}
+static bool rs2_filter(int n_new, int orig, int taps, int width, const float* kernel) {
+    return n_new == 1 && orig == 2 && taps == kFir2Taps && width == kFir2Width &&
+           (reinterpret_cast<uintptr_t>(kernel) & 15) == 0;
+}
+
+// 16-bit waveforms: only the reference's scale-2 filter (register-window kernels) reads / writes them directly;
+// other ratios return DM_ERR_UNSUPPORTED and the caller converts to fp32 first.
+extern "C" int dm_resample_fwd_io(const void* x, int x_dtype, long long x_bstride, long long L, int B,
+                                  const float* kernel, int n_new, int taps, int orig, int width, float* y, long long Ly,
+                                  dm_stream_t stream) {
+    DM_REQUIRE(x && kernel && y && L > 0 && B > 0 && Ly > 0 && io_dtype_ok(x_dtype));
+    if (x_dtype == DM_IO_F32)
+        return dm_resample_fwd(static_cast<const float*>(x), x_bstride, L, B, kernel, n_new, taps, orig, width, y, Ly,
+                               stream);
+    if (!(rs2_filter(n_new, orig, taps, width, kernel) && x_bstride % 8 == 0 && Ly % 4 == 0 &&
+          (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0))
+        return fail(DM_ERR_UNSUPPORTED, "%s: 16-bit input needs the scale-2 filter and 16-byte aligned rows", __func__);
+    if (x_dtype == DM_IO_F16) launch_rs2_fwd<DM_IO_F16>(x, x_bstride, L, B, kernel, y, Ly, as_stream(stream));
+    else launch_rs2_fwd<DM_IO_BF16>(x, x_bstride, L, B, kernel, y, Ly, as_stream(stream));
+    DM_LAUNCHED();
+    return DM_OK;
+}
+extern "C" int dm_resample_adjoint_io(const float* ybar, int pad, long long Ly, int B, const float* partial,
+                                      int ntiles, const float* kernel, int n_new, int taps, int orig, int width,
+                                      void* dwav, int dwav_dtype, long long dwav_bstride, long long L, float* loss,
+                                      dm_stream_t stream) {
+    DM_REQUIRE(ybar && partial && kernel && dwav && L > 0 && B > 0 && Ly > 0 && ntiles > 0 && io_dtype_ok(dwav_dtype));
+    if (dwav_dtype == DM_IO_F32)
+        return dm_resample_adjoint(ybar, pad, Ly, B, partial, ntiles, kernel, n_new, taps, orig, width,
+                                   static_cast<float*>(dwav), dwav_bstride, L, loss, stream);
+    DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 512));
+    if (!(rs2_filter(n_new, orig, taps, width, kernel) && dwav_bstride % 8 == 0 && (Ly + 2 * pad) % 4 == 0 &&
+          (reinterpret_cast<uintptr_t>(ybar) & 15) == 0 && (reinterpret_cast<uintptr_t>(dwav) & 15) == 0))
+        return fail(DM_ERR_UNSUPPORTED, "%s: 16-bit output needs the scale-2 filter and 16-byte aligned rows", __func__);
+    if (dwav_dtype == DM_IO_F16)
+        launch_rs2_adj<DM_IO_F16>(ybar, pad, Ly, B, partial, ntiles, kernel, dwav, dwav_bstride, L, loss,
+                                  as_stream(stream));
+    else
+        launch_rs2_adj<DM_IO_BF16>(ybar, pad, Ly, B, partial, ntiles, kernel, dwav, dwav_bstride, L, loss,
+                                   as_stream(stream));
     DM_LAUNCHED();
     return DM_OK;
 }
@@ -386,9 +495,7 @@ extern "C" int dm_resample_fwd(const float* x, long long x_bstride, long long L,
             if (orig == 2 && taps == kFir2Taps && width == kFir2Width && x_bstride % 4 == 0 && Ly % 4 == 0 &&
                 (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(kernel) & 15) == 0) {
-                const long long nthr = (Ly + kFir2Out - 1) / kFir2Out;
-                resample2_fwd_reg_kernel<<<dim3((unsigned)((nthr + kEwThreads - 1) / kEwThreads), B), kEwThreads, 0,
-                                           as_stream(stream)>>>(x, x_bstride, L, kernel, y, Ly);
+                launch_rs2_fwd<DM_IO_F32>(x, x_bstride, L, B, kernel, y, Ly, as_stream(stream));
                 DM_LAUNCHED();
                 return DM_OK;
             }
@@ -428,10 +535,8 @@ extern "C" int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int
     if (n_new == 1 && orig == 2 && taps == kFir2Taps && width == kFir2Width && dwav_bstride % 4 == 0 &&
         (Ly + 2 * pad) % 4 == 0 && (reinterpret_cast<uintptr_t>(ybar) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(dwav) & 15) == 0 && (reinterpret_cast<uintptr_t>(kernel) & 15) == 0) {
-        const long long nthr = (L + kFir2Out - 1) / kFir2Out;
-        resample2_adjoint_reg_kernel<<<dim3((unsigned)((nthr + kEwThreads - 1) / kEwThreads), B), kEwThreads, 0,
-                                       as_stream(stream)>>>(ybar, pad, Ly, partial, ntiles, kernel, dwav, dwav_bstride,
-                                                            L, loss);
+        launch_rs2_adj<DM_IO_F32>(ybar, pad, Ly, B, partial, ntiles, kernel, dwav, dwav_bstride, L, loss,
+                                  as_stream(stream));
         DM_LAUNCHED();
         return DM_OK;
     }

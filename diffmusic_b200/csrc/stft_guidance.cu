@@ -24,7 +24,8 @@ struct StftParams {
     StftTables tab;
     int clamp, hop, B, nf, ntiles;
     long long Ly, T, y_bstride, ref_bstride;
-    const float* y;
+    const void* y;  // waveform-typed (y_io)
+    int y_io;
     const float* mask;
     const float* ref;
     const float* noise;
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kCtaThreads, 3) stft_guidance_kernel(const Stf
     // ---- stage the signal span, tables and the reference tile ----
     // Interior tiles (no reflection) take their contiguous span with ONE TMA bulk copy (cp.async.bulk, completion on an
     // mbarrier) issued by thread 0 while all threads fill the tables; edge tiles mirror sample by sample.
-    const float* yb = p.y + (long long)b * p.y_bstride;
+    const float* yb = static_cast<const float*>(p.y) + (long long)b * p.y_bstride;  // this kernel: fp32 only
     __shared__ __align__(8) uint64_t stage_bar;
     const float* span_src = yb + (base - kNfft / 2);
     const bool interior = base >= kNfft / 2 && base - kNfft / 2 + span <= p.Ly &&
@@ -304,10 +305,11 @@ __global__ void __launch_bounds__(kCtaThreads, 2) stft_pair_kernel(const StftPar
     load_pair_consts(gt, p.tab, pc);
 
     // ---- stage the signal span, the window, the filterbank (by band and by bin) and the reference tile ----
-    const float* yb = p.y + (long long)b * p.y_bstride;
+    const void* yb = wave_row(p.y, p.y_io, (long long)b * p.y_bstride);
     __shared__ __align__(8) uint64_t stage_bar;
-    const float* span_src = yb + (base - kNfft / 2);
-    const bool interior = base >= kNfft / 2 && base - kNfft / 2 + span <= p.Ly &&
+    const float* span_src = static_cast<const float*>(yb) + (base - kNfft / 2);
+    // fp32 interior tiles: one TMA bulk copy; 16-bit waveforms and edge tiles: converted / mirrored sample by sample
+    const bool interior = p.y_io == DM_IO_F32 && base >= kNfft / 2 && base - kNfft / 2 + span <= p.Ly &&
                           (reinterpret_cast<uintptr_t>(span_src) & 15) == 0 && (span & 3) == 0;
     if (interior) {
         if (tid == 0) {
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(kCtaThreads, 2) stft_pair_kernel(const StftPar
     } else {
         for (int i = tid; i < span; i += kCtaThreads) {
             long long j = reflect_src(base + i, p.Ly);
-            float v = __ldg(yb + j);
+            float v = ld_wave(yb, p.y_io, j);
             if (p.mask) v *= __ldg(p.mask + j);
             sig[i] = v;
         }
@@ -522,7 +524,16 @@ extern "C" int dm_stft_guidance(const dm_stft_tables* tab, int mode, int clamp, 
                                 long long y_bstride, long long Ly, const float* mask, int B, const float* ref,
                                 long long ref_bstride, const float* noise, float sigma, float* out, float* ypbar,
                                 float* partial, int frames_per_tile, dm_stream_t stream) {
-    DM_REQUIRE(tab != nullptr && y != nullptr);
+    return dm_stft_guidance_io(tab, mode, clamp, hop, y, DM_IO_F32, y_bstride, Ly, mask, B, ref, ref_bstride, noise,
+                               sigma, out, ypbar, partial, frames_per_tile, stream);
+}
+
+extern "C" int dm_stft_guidance_io(const dm_stft_tables* tab, int mode, int clamp, int hop, const void* y, int y_dtype,
+                                   long long y_bstride, long long Ly, const float* mask, int B, const float* ref,
+                                   long long ref_bstride, const float* noise, float sigma, float* out, float* ypbar,
+                                   float* partial, int frames_per_tile, dm_stream_t stream) {
+    DM_REQUIRE(tab != nullptr && y != nullptr && io_dtype_ok(y_dtype));
+    DM_REQUIRE(y_dtype == DM_IO_F32 || (hop & 1) == 0);  // 16-bit waveforms: frame-pair kernel only
     DM_REQUIRE(mode >= 0 && mode <= 2);
     DM_REQUIRE(B > 0 && Ly > kNfft / 2);  // reflect padding needs pad < length (torch.stft raises otherwise)
     DM_REQUIRE(hop > 0 && hop <= kNfft);
@@ -545,6 +556,7 @@ extern "C" int dm_stft_guidance(const dm_stft_tables* tab, int mode, int clamp, 
     p.y_bstride = y_bstride;
     p.ref_bstride = ref_bstride;
     p.y = y;
+    p.y_io = y_dtype;
     p.mask = mask;
     p.ref = ref;
     p.noise = noise;
@@ -555,7 +567,7 @@ extern "C" int dm_stft_guidance(const dm_stft_tables* tab, int mode, int clamp, 
     DM_REQUIRE(tab->mel_wstride >= 1 && tab->mel_wstride <= 64);
     dim3 grid(p.ntiles, B), block(kCtaThreads);
     cudaStream_t st = as_stream(stream);
-    if ((hop & 1) == 0 && g_stft_engine != DM_STFT_ENGINE_FRAME) {  // frame-pair kernel
+    if ((hop & 1) == 0 && (g_stft_engine != DM_STFT_ENGINE_FRAME || y_dtype != DM_IO_F32)) {  // frame-pair kernel
         size_t smem2 = stft_pair_smem_bytes(p.nf, hop, tab->mel_wstride);
         if (smem2 > 227 * 1024)
             return fail(DM_ERR_UNSUPPORTED, "%s: tile needs %zu B of shared memory", __func__, smem2);

@@ -48,6 +48,18 @@ def _as_f32_rows(t):
     return t
 
 
+def _wave_rows(t):
+    """2-D rows with unit inner stride in a dtype the waveform-typed kernels read directly (fp32 / fp16 / bf16);
+    returns (rows, DM_IO code).  Other dtypes go through fp32."""
+    if t.dtype not in _lib.IO_DTYPES:
+        t = t.float()
+    if t.dim() == 1:
+        t = t.unsqueeze(0)
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    return t, _lib.IO_DTYPES[t.dtype]
+
+
 class _DeviceTables:
     """Per-device constant tables (window, twiddles, sparse mel tables) and the ctypes struct pointing at them."""
 
@@ -64,12 +76,13 @@ class _DeviceTables:
         self.ref = C.byref(self.struct)
 
 
-def _grad_buffer(dwav, B, L, device):
-    """(B, L) fp32 destination of dLoss/dwav: a fresh tensor, or the caller's (possibly row-strided) view."""
+def _grad_buffer(dwav, B, L, device, dtype=torch.float32):
+    """(B, L) destination of dLoss/dwav in the waveform's dtype: a fresh tensor, or the caller's (possibly row-strided)
+    view."""
     if dwav is None:
-        return torch.empty((B, L), device=device, dtype=torch.float32)
-    if tuple(dwav.shape) != (B, L) or dwav.dtype != torch.float32 or dwav.stride(1) != 1 or dwav.device != device:
-        raise ValueError("dwav must be a (B, L) fp32 view with unit inner stride on the waveform's device")
+        return torch.empty((B, L), device=device, dtype=dtype)
+    if tuple(dwav.shape) != (B, L) or dwav.dtype != dtype or dwav.stride(1) != 1 or dwav.device != device:
+        raise ValueError(f"dwav must be a (B, L) {dtype} view with unit inner stride on the waveform's device")
     return dwav
 
 
@@ -98,6 +111,8 @@ class BaseOperator:
     """operator.py:6-14 plus the shared kernel plumbing."""
 
     sample_rate = 16000
+    #: the fused loss + VJP chain reads fp16 / bf16 waveforms and writes dLoss/dwav in that dtype directly
+    wave16 = False
     clamp_transform = True     # every T_mel clamps to +-80 except MusicInpaintingOperator (operator.py:123-124)
     window_kind = "hann"
     noiser = None
@@ -134,6 +149,7 @@ class BaseOperator:
         transform mode (ref None) -> returns out (B, R, T); guidance mode -> returns (ypbar or None, partial, ntiles)."""
         B, Ly = y.shape
         dev = y.device
+        y_io = _lib.IO_DTYPES[y.dtype]
         T = 1 + Ly // _HOP
         nf = _frames_per_tile(B, T, dev)
         ntiles = math.ceil(T / nf)
@@ -141,7 +157,7 @@ class BaseOperator:
         clamp = self.clamp_transform if clamp is None else clamp
         if ref is None:
             out = torch.empty((B, out_rows, T), device=dev, dtype=torch.float32)
-            _lib.call("dm_stft_guidance", tab.ref, mode, int(clamp), _HOP, y.data_ptr(), y.stride(0), Ly,
+            _lib.call("dm_stft_guidance_io", tab.ref, mode, int(clamp), _HOP, y.data_ptr(), y_io, y.stride(0), Ly,
                       _lib.ptr(mask), B, None, 0, _lib.ptr(noise), float(sigma), out.data_ptr(), None, None, nf,
                       _lib.stream())
             return out
@@ -151,9 +167,9 @@ class BaseOperator:
         ref_b = 0 if ref.shape[0] == 1 else ref.stride(0)
         partial = torch.empty((B, ntiles), device=dev, dtype=torch.float32)
         ypbar = torch.zeros((B, Ly + 1024), device=dev, dtype=torch.float32) if want_grad else None
-        _lib.call("dm_stft_guidance", tab.ref, mode, int(clamp), _HOP, y.data_ptr(), y.stride(0), Ly, _lib.ptr(mask),
-                  B, ref.data_ptr(), ref_b, _lib.ptr(noise), float(sigma), None, _lib.ptr(ypbar), partial.data_ptr(),
-                  nf, _lib.stream())
+        _lib.call("dm_stft_guidance_io", tab.ref, mode, int(clamp), _HOP, y.data_ptr(), y_io, y.stride(0), Ly,
+                  _lib.ptr(mask), B, ref.data_ptr(), ref_b, _lib.ptr(noise), float(sigma), None, _lib.ptr(ypbar),
+                  partial.data_ptr(), nf, _lib.stream())
         return ypbar, partial, ntiles
 
     def _mel_db(self, wav):
@@ -197,7 +213,13 @@ class BaseOperator:
         if supervised_space not in ("wav_form", "mel_spectrogram"):
             raise ValueError("supervised_space should be either 'wav_form' or 'mel_spectrogram")
         _lib.require_cuda(wav)
-        return self._fused(_as_f32_rows(wav), measurement, supervised_space, True, dwav)
+        rows = _wave_rows(wav)[0] if self.wave16_ok(wav) else _as_f32_rows(wav)
+        return self._fused(rows, measurement, supervised_space, True, dwav)
+
+    def wave16_ok(self, wav):
+        """True when the fused chain can consume `wav` in its own 16-bit dtype (and will return dLoss/dwav in it)."""
+        return (self.wave16 and wav.dtype in (torch.float16, torch.bfloat16) and wav.dim() == 2 and wav.stride(1) == 1
+                and self._sigma() == 0.0)
 
     def _ref_mel(self, measurement):
         """transform(measurement), cached: the reference recomputes it every step (scheduling_dps.py:205)."""
@@ -221,20 +243,21 @@ class BaseOperator:
         meas = _as_f32_rows(meas.reshape(meas.shape[0], -1))
         if meas.shape[1] != n:
             raise ValueError(f"measurement has {meas.shape[1]} samples per clip, prediction has {n}")
-        _lib.call("dm_residual_wav", y.data_ptr(), y.stride(0), n, B, _lib.ptr(mask), meas.data_ptr(),
-                  0 if meas.shape[0] == 1 else meas.stride(0), ybar.data_ptr(), partial.data_ptr(), _lib.stream())
+        _lib.call("dm_residual_wav_io", y.data_ptr(), _lib.IO_DTYPES[y.dtype], y.stride(0), n, B, _lib.ptr(mask),
+                  meas.data_ptr(), 0 if meas.shape[0] == 1 else meas.stride(0), ybar.data_ptr(), partial.data_ptr(),
+                  _lib.stream())
         return ybar, partial, nt
 
-    def _fold_adjoint(self, ybar, pad, Ly, B, partial, ntiles, mask, want_grad, dwav=None):
+    def _fold_adjoint(self, ybar, pad, Ly, B, partial, ntiles, mask, want_grad, dwav=None, dtype=torch.float32):
         dev = partial.device
         loss = torch.empty((B,), device=dev, dtype=torch.float32)
         if not want_grad:  # loss only
             _lib.call("dm_fold_adjoint", None, pad, Ly, B, None, partial.data_ptr(), ntiles, None, 0,
                       loss.data_ptr(), _lib.stream())
             return loss, None
-        dwav = _grad_buffer(dwav, B, Ly, dev)
-        _lib.call("dm_fold_adjoint", ybar.data_ptr(), pad, Ly, B, _lib.ptr(mask), partial.data_ptr(), ntiles,
-                  dwav.data_ptr(), dwav.stride(0), loss.data_ptr(), _lib.stream())
+        dwav = _grad_buffer(dwav, B, Ly, dev, dtype)
+        _lib.call("dm_fold_adjoint_io", ybar.data_ptr(), pad, Ly, B, _lib.ptr(mask), partial.data_ptr(), ntiles,
+                  dwav.data_ptr(), _lib.IO_DTYPES[dtype], dwav.stride(0), loss.data_ptr(), _lib.stream())
         return loss, dwav
 
     def _space_stage(self, y, measurement, space, want_grad, mask=None):
@@ -283,10 +306,12 @@ class IdentityOperator(BaseOperator):
     def forward(self, data, **kwargs):
         return data
 
+    wave16 = True
+
     def _fused(self, wav, measurement, space, want_grad, dwav=None):
         B, L = wav.shape
         ybar, pad, partial, nt = self._space_stage(wav, measurement, space, want_grad)
-        return self._fold_adjoint(ybar, pad, L, B, partial, nt, None, want_grad, dwav)
+        return self._fold_adjoint(ybar, pad, L, B, partial, nt, None, want_grad, dwav, wav.dtype)
 
 
 class MusicInpaintingOperator(BaseOperator):
@@ -294,6 +319,7 @@ class MusicInpaintingOperator(BaseOperator):
     is fused into the frame load of the STFT kernel and into the adjoint."""
 
     clamp_transform = False  # operator.py:123-124: no clamp for inpainting
+    wave16 = True
 
     def __init__(self, audio_length_in_s, sample_rate, mask_type, start_inpainting_s, end_inpainting_s,
                  mask_percentage, mask_duration_s, interval_s, noiser=None):
@@ -360,13 +386,14 @@ class MusicInpaintingOperator(BaseOperator):
             ybar, pad, partial, nt = self._space_stage(y, measurement, space, want_grad)
         else:
             ybar, pad, partial, nt = self._space_stage(wav, measurement, space, want_grad, mask=mask)
-        return self._fold_adjoint(ybar, pad, L, B, partial, nt, mask, want_grad, dwav)
+        return self._fold_adjoint(ybar, pad, L, B, partial, nt, mask, want_grad, dwav, wav.dtype)
 
 
 class PhaseRetrievalOperator(BaseOperator):
     """operator.py:136-171: A(x) = |STFT(x)| with a rectangular window; transform = clamp(mel of magnitude)."""
 
     window_kind = "rect"
+    wave16 = True
 
     def __init__(self, n_fft=1024, hop_length=160, win_length=1024, noiser=None):
         if (n_fft, hop_length, win_length) != (1024, 160, 1024):
@@ -409,7 +436,7 @@ class PhaseRetrievalOperator(BaseOperator):
                 raise ValueError(f"measurement {tuple(ref.shape)} does not match |STFT| of the prediction (513, {T})")
             ypbar, partial, nt = self._stft(_MODE_PHASE_WAV, wav, ref=ref.reshape(-1, 513, T), want_grad=want_grad,
                                             clamp=False, noise=noise, sigma=sigma)
-        return self._fold_adjoint(ypbar, 512, L, B, partial, nt, None, want_grad, dwav)
+        return self._fold_adjoint(ypbar, 512, L, B, partial, nt, None, want_grad, dwav, wav.dtype)
 
 
 class SuperResolutionOperator(BaseOperator):
@@ -424,6 +451,13 @@ class SuperResolutionOperator(BaseOperator):
     def transform(self, audio):
         return self._mel_db(audio)
 
+    def wave16_ok(self, wav):
+        # the register-window kernels of the reference's scale-2 filter move 16-bit rows with 128-bit accesses
+        return (wav.dtype in (torch.float16, torch.bfloat16) and wav.dim() == 2 and wav.stride(1) == 1
+                and self._sigma() == 0.0 and self.kernel is not None
+                and (self.orig, self.new, self.width, self.kernel.shape[-1]) == (2, 1, 13, 28)
+                and wav.stride(0) % 8 == 0 and wav.data_ptr() % 16 == 0 and wav.shape[1] % 8 == 0)
+
     def _kernel_on(self, device):
         cache = self.__dict__.setdefault("_k_cache", {})
         if str(device) not in cache:
@@ -437,8 +471,8 @@ class SuperResolutionOperator(BaseOperator):
         Ly = int(math.ceil(self.new * L / self.orig))
         k = self._kernel_on(x.device)
         y = torch.empty((B, Ly), device=x.device, dtype=torch.float32)
-        _lib.call("dm_resample_fwd", x.data_ptr(), x.stride(0), L, B, k.data_ptr(), k.shape[0], k.shape[1],
-                  self.orig, self.width, y.data_ptr(), Ly, _lib.stream())
+        _lib.call("dm_resample_fwd_io", x.data_ptr(), _lib.IO_DTYPES[x.dtype], x.stride(0), L, B, k.data_ptr(),
+                  k.shape[0], k.shape[1], self.orig, self.width, y.data_ptr(), Ly, _lib.stream())
         return y
 
     def forward(self, data, **kwargs):
@@ -461,10 +495,10 @@ class SuperResolutionOperator(BaseOperator):
             return self._fold_adjoint(ybar, pad, L, B, partial, nt, None, True, dwav)
         k = self._kernel_on(wav.device)
         loss = torch.empty((B,), device=wav.device, dtype=torch.float32)
-        dwav = _grad_buffer(dwav, B, L, wav.device)
-        _lib.call("dm_resample_adjoint", ybar.data_ptr(), pad, Ly, B, partial.data_ptr(), nt, k.data_ptr(),
-                  k.shape[0], k.shape[1], self.orig, self.width, dwav.data_ptr(), dwav.stride(0), L, loss.data_ptr(),
-                  _lib.stream())
+        dwav = _grad_buffer(dwav, B, L, wav.device, wav.dtype)
+        _lib.call("dm_resample_adjoint_io", ybar.data_ptr(), pad, Ly, B, partial.data_ptr(), nt, k.data_ptr(),
+                  k.shape[0], k.shape[1], self.orig, self.width, dwav.data_ptr(), _lib.IO_DTYPES[wav.dtype],
+                  dwav.stride(0), L, loss.data_ptr(), _lib.stream())
         return loss, dwav
 
 

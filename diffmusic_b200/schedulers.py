@@ -170,12 +170,13 @@ class _GuidedBase(DDIMBase):
             mel = vae.decode(1 / vae.config.scaling_factor * leaf.to(model_dtype)).sample
             wav_full = op.inverse_transform(mel, vocoder)
             wav = wav_full[:, :L]
-            if getattr(op, "fused_loss_and_grad", None) is not None and wav_full.dtype == torch.float32 \
-                    and wav_full.dim() == 2 and wav_full.stride(1) == 1:
+            if getattr(op, "fused_loss_and_grad", None) is not None and wav_full.dim() == 2 \
+                    and wav_full.stride(1) == 1 and (wav_full.dtype == torch.float32 or op.wave16_ok(wav)):
                 # one fused kernel chain gives the per-clip loss AND dLoss/dwav; torch only continues the VJP through
                 # the vocoder and the VAE decoder.  The cotangent is written straight into a buffer shaped like the
                 # vocoder output (zero tail beyond L = the adjoint of the `[:, :L]` slice), so autograd
-                # starts at the vocoder output: no slice-backward zero-fill + copy of the whole waveform.
+                # starts at the vocoder output: no slice-backward zero-fill + copy of the whole waveform.  fp16 / bf16
+                # pipelines: the kernels read the 16-bit waveform and write the 16-bit cotangent directly.
                 Lw = wav.shape[1]
                 dfull = torch.empty_like(wav_full)
                 if wav_full.shape[1] > Lw:

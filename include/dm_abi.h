@@ -217,6 +217,26 @@ int dm_fad_finalize(const double* acc, int d, double* mu, double* cov, dm_stream
 
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * 16-bit WAVEFORMS: in an fp16 / bf16 pipeline the vocoder output and the cotangent handed back
+ * to autograd are 16-bit.  These variants read the waveform / write dLoss/dwav in that type (DM_IO_*), everything in
+ * between stays fp32.  y_bstride / dwav_bstride are in ELEMENTS of the given type.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int dm_stft_guidance_io(const dm_stft_tables* tab, int mode, int clamp, int hop, const void* y, int y_dtype,
+                        long long y_bstride, long long Ly, const float* mask, int B, const float* ref,
+                        long long ref_bstride, const float* noise, float sigma, float* out, float* ypbar,
+                        float* partial, int frames_per_tile, dm_stream_t stream);
+int dm_residual_wav_io(const void* y, int y_dtype, long long y_bstride, long long n, int B, const float* mask,
+                       const float* meas, long long meas_bstride, float* ybar, float* partial, dm_stream_t stream);
+int dm_fold_adjoint_io(const float* ybar, int pad, long long Ly, int B, const float* mask, const float* partial,
+                       int ntiles, void* dwav, int dwav_dtype, long long dwav_bstride, float* loss, dm_stream_t stream);
+/* 16-bit types: the reference's scale-2 filter only (orig 2, 28 taps), else DM_ERR_UNSUPPORTED */
+int dm_resample_fwd_io(const void* x, int x_dtype, long long x_bstride, long long L, int B, const float* kernel,
+                       int n_new, int taps, int orig, int width, float* y, long long Ly, dm_stream_t stream);
+int dm_resample_adjoint_io(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
+                           const float* kernel, int n_new, int taps, int orig, int width, void* dwav, int dwav_dtype,
+                           long long dwav_bstride, long long L, float* loss, dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Frechet distance and the FAD-inf bootstrap (fadtk/fad.py:50-119 `calc_frechet_distance`, :303-350 `score_inf`).
  * ---------------------------------------------------------------------------------------------------------------- */
 /* out_f16[r, :] = x_f16[idx[r], :]  -- embeds[np.random.choice(N, n)] of score_inf (fad.py:331-332); idx is int64 on

@@ -848,3 +848,26 @@ def test_guided_steps_in_16_bit_pipelines(sched_name, op_name, eta, dt, tol):
     assert rel_l2(low.prev_sample.float(), full.prev_sample) < tol
     assert rel_l2(low.pred_original_sample.float(), full.pred_original_sample) < tol
     assert rel_l2(low.loss_per_clip, full.loss_per_clip) < 4 * tol
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("op_name", ["identity", "inpainting", "super_resolution", "phase_retrieval"])
+@pytest.mark.parametrize("space", ["mel_spectrogram", "wav_form"])
+def test_16_bit_waveforms_are_consumed_directly(op_name, space, dt):
+    """fused loss + VJP on a 16-bit waveform == the fp32 chain on the up-cast waveform, the gradient rounded once to the
+    waveform dtype; also for a row-strided view and a preallocated strided gradient buffer (what the schedulers pass)."""
+    B, L = 3, L1
+    ops = dict(_ops(), identity=dm.IdentityOperator(16000))
+    op = ops[op_name]
+    full = torch.zeros(B, L + 32, device=DEV, dtype=dt)
+    full[:, :L] = stubs.synth_clips(B, L).to(DEV).to(dt)
+    wav = full[:, :L]
+    assert op.wave16_ok(wav)
+    meas = op.forward(stubs.synth_clips(1, L, first=50).to(DEV))
+    loss32, g32 = op.fused_loss_and_grad(wav.float(), meas, space)
+    dfull = torch.full_like(full, 7.0)
+    loss16, g16 = op.fused_loss_and_grad(wav, meas, space, dwav=dfull[:, :L])
+    assert g16.dtype == dt and g16.data_ptr() == dfull.data_ptr()
+    assert torch.equal(loss16, loss32)
+    assert torch.equal(g16, g32.to(dt))
+    assert torch.all(dfull[:, L:] == 7.0)  # nothing written past L
