@@ -95,11 +95,14 @@ struct EwParams {
     const void* x;    // latent-typed
     const float* x0;
     const void* eps;  // latent-typed
-    const float* g0;
+    const void* g0;   // latent-typed: dLoss/d(leaf) as autograd returns it, leaf = leaf_scale * x0 (see x0_leaf)
     const float* z;
     void* prev;       // latent-typed
     float* x0_out;    // fp32 x0 (kX0) / guided x0 (kMpgd) kept by the step
     void* x0_pub;     // optional latent-typed copy of x0_out for the caller (pred_original_sample)
+    void* x0_leaf;    // kX0, optional latent-typed: leaf_scale * x0 = the VAE decoder input 1/scaling_factor * x0
+                      // (scheduling_dps.py:195-197), so torch needs no scaling kernel (nor its backward)
+    float leaf_scale; // kX0: the factor above; updates: dLoss/dx0 = leaf_scale * g0 (chain rule of that scaling)
     float sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate, clip_range;
     int clip;
     const float* coef;  // optional device-resident [sqrt_a, sqrt_b, sqrt_p, dir_coef, std, r]: overrides the by-value
@@ -136,9 +139,18 @@ __global__ void __launch_bounds__(kThreads) ew_update_kernel(EwParams p, long lo
             }
             stv<W>(p.x0_out, v, o);
             if (IO != DM_IO_F32 && p.x0_pub != nullptr) stio<IO, W>(p.x0_pub, v, o);
+            if (p.x0_leaf != nullptr) {
+#pragma unroll
+                for (int i = 0; i < W; ++i) o2[i] = mul(p.leaf_scale, o[i]);
+                stio<IO, W>(p.x0_leaf, v, o2);
+            }
         } else {
             ldv<W>(p.x0, v, a);
-            if (KIND != kDdim) ldv<W>(p.g0, v, g);
+            if (KIND != kDdim) {
+                ldio<IO, W>(p.g0, v, g);
+#pragma unroll
+                for (int i = 0; i < W; ++i) g[i] = mul(g[i], p.leaf_scale);  // dLoss/dx0 (autograd of leaf_scale * x0)
+            }
             const bool has_z = (KIND != kDdim) && p.z != nullptr;
             if (has_z) ldv<W>(p.z, v, z);
 #pragma unroll
@@ -169,8 +181,8 @@ static bool aligned_io(const void* p, int io) { return io == DM_IO_F32 ? aligned
 template <int KIND, int IO>
 static void launch_ew_io(const EwParams& p, long long n, cudaStream_t st) {
     const bool vec = (n % 4 == 0) && aligned_io(p.x, IO) && aligned16(p.x0) && aligned_io(p.eps, IO) &&
-                     aligned16(p.g0) && aligned16(p.z) && aligned_io(p.prev, IO) && aligned16(p.x0_out) &&
-                     aligned_io(p.x0_pub, IO);
+                     aligned_io(p.g0, IO) && aligned16(p.z) && aligned_io(p.prev, IO) && aligned16(p.x0_out) &&
+                     aligned_io(p.x0_pub, IO) && aligned_io(p.x0_leaf, IO);
     const long long nvec = vec ? n / 4 : n;
     const int nblk = (int)std::max<long long>(1, std::min<long long>((nvec + kThreads - 1) / kThreads,
                                                                       (long long)num_sms() * 8));
@@ -191,13 +203,21 @@ static int launch_ew(const EwParams& p, long long n, int io, cudaStream_t st) {
 struct NormParams {
     const float* x0;
     const void* eps;  // latent-typed
-    const float* g0;
+    const void* g0;   // latent-typed, dLoss/d(leaf); dLoss/dx0 = leaf_scale * g0
     const float* z;
     void* prev;       // latent-typed
     long long n_clip;
     float sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, threshold;
     const float* coef;  // optional device-resident coefficients (see EwParams::coef)
+    float leaf_scale;
 };
+// g0 as loaded (dLoss/d leaf) -> dLoss/dx0
+template <int IO, int W>
+__device__ __forceinline__ void ldg0(const NormParams& p, long long v, float (&g)[W]) {
+    ldio<IO, W>(p.g0, v, g);
+#pragma unroll
+    for (int i = 0; i < W; ++i) g[i] = mul(g[i], p.leaf_scale);
+}
 
 // block-level sum of up to 3 doubles, result broadcast through smem slot `out[0..2]`
 __device__ __forceinline__ void block_sum3(double a, double b, double c, double* wred, double* out) {
@@ -281,7 +301,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
         for (int it = 0; it < kIt; ++it) {
             const long long v = lo + threadIdx.x + (long long)it * kThreads;
             if (v < hi) {
-                ldv<W>(p.g0, off + v, rg[it]);
+                ldg0<IO, W>(p, off + v, rg[it]);
                 ldv<W>(p.z, off + v, rz[it]);
                 ldv<W>(p.x0, off + v, rx0[it]);
                 ldio<IO, W>(p.eps, off + v, rep[it]);
@@ -315,7 +335,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
     } else {
         for (long long v = lo + threadIdx.x; v < hi; v += kThreads) {
             float g[W], z[W] = {};
-            ldv<W>(p.g0, off + v, g);
+            ldg0<IO, W>(p, off + v, g);
             if (KIND == kDiffMusic) ldv<W>(p.z, off + v, z);
             acc1(g, z);
         }
@@ -344,7 +364,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
         } else {
             for (long long v = lo + threadIdx.x; v < hi; v += kThreads) {
                 float g[W], z[W];
-                ldv<W>(p.g0, off + v, g);
+                ldg0<IO, W>(p, off + v, g);
                 ldv<W>(p.z, off + v, z);
                 acc2(g, z, true);
             }
@@ -386,7 +406,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
             float x0[W], ep[W], g[W], z[W];
             ldv<W>(p.x0, off + v, x0);
             ldio<IO, W>(p.eps, off + v, ep);
-            ldv<W>(p.g0, off + v, g);
+            ldg0<IO, W>(p, off + v, g);
             ldv<W>(p.z, off + v, z);
             emit(v, x0, ep, g, z);
         }
@@ -396,7 +416,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
 
 template <int KIND, int IO>
 static void launch_norm_io(const NormParams& p, int n_clips, cudaStream_t st) {
-    const bool vec = (p.n_clip % 4 == 0) && aligned16(p.x0) && aligned_io(p.eps, IO) && aligned16(p.g0) &&
+    const bool vec = (p.n_clip % 4 == 0) && aligned16(p.x0) && aligned_io(p.eps, IO) && aligned_io(p.g0, IO) &&
                      aligned16(p.z) && aligned_io(p.prev, IO);
     const int W = vec ? 4 : 1;
     const long long chunk = (p.n_clip / W + kCluster - 1) / kCluster;
@@ -420,9 +440,9 @@ static int launch_norm(const NormParams& p, int n_clips, int io, cudaStream_t st
 
 using namespace dm;
 
-extern "C" int dm_sched_x0_io(const void* x, const void* eps, float* x0, void* x0_pub, long long n, float sqrt_a,
-                              float sqrt_b, int clip, float clip_range, const float* coef, int io_dtype,
-                              dm_stream_t stream) {
+extern "C" int dm_sched_x0_io(const void* x, const void* eps, float* x0, void* x0_pub, void* x0_leaf, float leaf_scale,
+                              long long n, float sqrt_a, float sqrt_b, int clip, float clip_range, const float* coef,
+                              int io_dtype, dm_stream_t stream) {
     DM_REQUIRE(x && eps && x0 && n > 0 && io_ok(io_dtype));
     EwParams p{};
     p.coef = coef;
@@ -430,6 +450,8 @@ extern "C" int dm_sched_x0_io(const void* x, const void* eps, float* x0, void* x
     p.eps = eps;
     p.x0_out = x0;
     p.x0_pub = x0_pub;
+    p.x0_leaf = x0_leaf;
+    p.leaf_scale = leaf_scale;
     p.sqrt_a = sqrt_a;
     p.sqrt_b = sqrt_b;
     p.clip = clip;
@@ -440,7 +462,8 @@ extern "C" int dm_sched_x0_io(const void* x, const void* eps, float* x0, void* x
 }
 extern "C" int dm_sched_x0(const float* x, const float* eps, float* x0, long long n, float sqrt_a, float sqrt_b,
                            int clip, float clip_range, const float* coef, dm_stream_t stream) {
-    return dm_sched_x0_io(x, eps, x0, nullptr, n, sqrt_a, sqrt_b, clip, clip_range, coef, DM_IO_F32, stream);
+    return dm_sched_x0_io(x, eps, x0, nullptr, nullptr, 1.f, n, sqrt_a, sqrt_b, clip, clip_range, coef, DM_IO_F32,
+                          stream);
 }
 
 extern "C" int dm_sched_ddim_update_io(const void* x, const float* x0, void* prev, long long n, float sqrt_a,
@@ -466,11 +489,13 @@ extern "C" int dm_sched_ddim_update(const float* x, const float* x0, float* prev
     return dm_sched_ddim_update_io(x, x0, prev, n, sqrt_a, sqrt_b, sqrt_p, sqrt_1mp, coef, DM_IO_F32, stream);
 }
 
-extern "C" int dm_sched_dps_update_io(const void* x, const float* x0, const float* g0, const float* z, void* prev,
-                                      long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef,
-                                      float std, float rate, const float* coef, int io_dtype, dm_stream_t stream) {
+extern "C" int dm_sched_dps_update_io(const void* x, const float* x0, const void* g0, float leaf_scale, const float* z,
+                                      void* prev, long long n, float sqrt_a, float sqrt_b, float sqrt_p,
+                                      float dir_coef, float std, float rate, const float* coef, int io_dtype,
+                                      dm_stream_t stream) {
     DM_REQUIRE(x && x0 && g0 && prev && n > 0 && io_ok(io_dtype));
     EwParams p{};
+    p.leaf_scale = leaf_scale;
     p.coef = coef;
     p.x = x;
     p.x0 = x0;
@@ -490,16 +515,17 @@ extern "C" int dm_sched_dps_update_io(const void* x, const float* x0, const floa
 extern "C" int dm_sched_dps_update(const float* x, const float* x0, const float* g0, const float* z, float* prev,
                                    long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std,
                                    float rate, const float* coef, dm_stream_t stream) {
-    return dm_sched_dps_update_io(x, x0, g0, z, prev, n, sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate, coef, DM_IO_F32,
-                                  stream);
+    return dm_sched_dps_update_io(x, x0, g0, 1.f, z, prev, n, sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate, coef,
+                                  DM_IO_F32, stream);
 }
 
-extern "C" int dm_sched_mpgd_update_io(const void* x, const float* x0, const float* g0, const float* z, void* prev,
-                                       void* x0_out, long long n, float sqrt_a, float sqrt_b, float sqrt_p,
+extern "C" int dm_sched_mpgd_update_io(const void* x, const float* x0, const void* g0, float leaf_scale, const float* z,
+                                       void* prev, void* x0_out, long long n, float sqrt_a, float sqrt_b, float sqrt_p,
                                        float dir_coef, float std, float rate, const float* coef, int io_dtype,
                                        dm_stream_t stream) {
     DM_REQUIRE(x && x0 && g0 && prev && x0_out && n > 0 && io_ok(io_dtype));
     EwParams p{};
+    p.leaf_scale = leaf_scale;
     p.coef = coef;
     p.x = x;
     p.x0 = x0;
@@ -522,16 +548,17 @@ extern "C" int dm_sched_mpgd_update(const float* x, const float* x0, const float
                                     float* x0_out, long long n, float sqrt_a, float sqrt_b, float sqrt_p,
                                     float dir_coef, float std, float rate, const float* coef,
                                     dm_stream_t stream) {
-    return dm_sched_mpgd_update_io(x, x0, g0, z, prev, x0_out, n, sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate, coef,
-                                   DM_IO_F32, stream);
+    return dm_sched_mpgd_update_io(x, x0, g0, 1.f, z, prev, x0_out, n, sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate,
+                                   coef, DM_IO_F32, stream);
 }
 
-extern "C" int dm_sched_dsg_update_io(const float* x0, const void* eps, const float* g0, const float* z, void* prev,
-                                      int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef,
-                                      float std, float rate, float r, float grad_scale, float e, const float* coef,
-                                      int io_dtype, dm_stream_t stream) {
+extern "C" int dm_sched_dsg_update_io(const float* x0, const void* eps, const void* g0, float leaf_scale, const float* z,
+                                      void* prev, int n_clips, long long n_clip, float sqrt_a, float sqrt_p,
+                                      float dir_coef, float std, float rate, float r, float grad_scale, float e,
+                                      const float* coef, int io_dtype, dm_stream_t stream) {
     DM_REQUIRE(x0 && eps && g0 && z && prev && n_clips > 0 && n_clip > 0 && io_ok(io_dtype));
-    NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, 0.f, coef};
+    NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, 0.f, coef,
+                 leaf_scale};
     launch_norm<kDsg>(p, n_clips, io_dtype, as_stream(stream));
     DM_LAUNCHED();
     return DM_OK;
@@ -540,17 +567,18 @@ extern "C" int dm_sched_dsg_update(const float* x0, const float* eps, const floa
                                    int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef,
                                    float std, float rate, float r, float grad_scale, float e, const float* coef,
                                    dm_stream_t stream) {
-    return dm_sched_dsg_update_io(x0, eps, g0, z, prev, n_clips, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, r,
+    return dm_sched_dsg_update_io(x0, eps, g0, 1.f, z, prev, n_clips, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, r,
                                   grad_scale, e, coef, DM_IO_F32, stream);
 }
 
-extern "C" int dm_sched_diffmusic_update_io(const float* x0, const void* eps, const float* g0, const float* z,
-                                            void* prev, int n_clips, long long n_clip, float sqrt_a, float sqrt_p,
-                                            float dir_coef, float std, float rate, float grad_scale, float e,
-                                            float threshold, const float* coef, int io_dtype, dm_stream_t stream) {
+extern "C" int dm_sched_diffmusic_update_io(const float* x0, const void* eps, const void* g0, float leaf_scale,
+                                            const float* z, void* prev, int n_clips, long long n_clip, float sqrt_a,
+                                            float sqrt_p, float dir_coef, float std, float rate, float grad_scale,
+                                            float e, float threshold, const float* coef, int io_dtype,
+                                            dm_stream_t stream) {
     DM_REQUIRE(x0 && eps && g0 && z && prev && n_clips > 0 && n_clip > 0 && io_ok(io_dtype));
     NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, 0.f, grad_scale, e, threshold,
-                 coef};
+                 coef, leaf_scale};
     launch_norm<kDiffMusic>(p, n_clips, io_dtype, as_stream(stream));
     DM_LAUNCHED();
     return DM_OK;
@@ -559,6 +587,6 @@ extern "C" int dm_sched_diffmusic_update(const float* x0, const float* eps, cons
                                          float* prev, int n_clips, long long n_clip, float sqrt_a, float sqrt_p,
                                          float dir_coef, float std, float rate, float grad_scale, float e,
                                          float threshold, const float* coef, dm_stream_t stream) {
-    return dm_sched_diffmusic_update_io(x0, eps, g0, z, prev, n_clips, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate,
+    return dm_sched_diffmusic_update_io(x0, eps, g0, 1.f, z, prev, n_clips, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate,
                                         grad_scale, e, threshold, coef, DM_IO_F32, stream);
 }

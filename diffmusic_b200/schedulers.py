@@ -116,16 +116,23 @@ class _GuidedBase(DDIMBase):
             x, e = x.float(), e.float()
         return x.contiguous(), e.contiguous(), _lib.IO_DTYPES[x.dtype]
 
-    def _x0(self, x, eps, c, io, publish=True):
+    def _x0(self, x, eps, c, io, publish=True, leaf_scale=None):
         """dm_sched_x0_io: pred_original_sample of the diffusers base step.  Returns (x0 fp32 kept by the step,
-        x0 in the latent dtype for the caller -- the same tensor for fp32 pipelines)."""
+        x0 in the latent dtype for the caller -- the same tensor for fp32 pipelines, leaf): `leaf` = leaf_scale * x0
+        in the latent dtype (the VAE decoder input of scheduling_dps.py:195-197) when leaf_scale is given."""
         self._check_supported()
         x0 = torch.empty(x.shape, device=x.device, dtype=torch.float32)
         pub = torch.empty_like(x) if (io != 0 and publish) else None
-        _lib.call("dm_sched_x0_io", x.data_ptr(), eps.data_ptr(), x0.data_ptr(), _lib.ptr(pub), x.numel(), c["sqrt_a"],
-                  c["sqrt_b"], int(bool(self.config.clip_sample)), float(self.config.clip_sample_range),
-                  self._coef_ptr(), io, _lib.stream())
-        return x0, (x0 if pub is None else pub)
+        leaf = torch.empty_like(x) if leaf_scale is not None else None
+        _lib.call("dm_sched_x0_io", x.data_ptr(), eps.data_ptr(), x0.data_ptr(), _lib.ptr(pub), _lib.ptr(leaf),
+                  float(leaf_scale or 1.0), x.numel(), c["sqrt_a"], c["sqrt_b"], int(bool(self.config.clip_sample)),
+                  float(self.config.clip_sample_range), self._coef_ptr(), io, _lib.stream())
+        return x0, (x0 if pub is None else pub), leaf
+
+    @staticmethod
+    def _leaf_scale(vae):
+        """1 / vae.config.scaling_factor as the fp32 value torch multiplies by (scheduling_dps.py:195-197)."""
+        return float(torch.tensor(1 / vae.config.scaling_factor, dtype=torch.float32))
 
     #: which noise the step consumes: "eta" = base-step draw (discarded) + own z when eta > 0 (DDIM/DPS/MPGD);
     #: "always" = exactly one z per step, independent of eta (DSG/DiffMusic, scheduling_dsg.py:215-220)
@@ -159,15 +166,21 @@ class _GuidedBase(DDIMBase):
             return self.draw_step_noise(eta, generator, variance_noise, model_output)
         return given if isinstance(given, torch.Tensor) else None
 
-    def _guidance(self, x0, measurement, vae, vocoder, L, supervised_space, model_dtype):
-        """loss (per clip) and G0 = dLoss/dx0 through vae.decode + vocoder (torch autograd) and the fused operator
-        kernels (scheduling_dps.py:195-212).  x0 is re-leafed: the UNet is never differentiated."""
+    def _guidance(self, leaf, measurement, vae, vocoder, L, supervised_space, model_dtype=None):
+        """loss (per clip) and dLoss/d(leaf) through vae.decode + vocoder (torch autograd) and the fused operator
+        kernels (scheduling_dps.py:195-212).  `leaf` = 1/scaling_factor * x0 from dm_sched_x0_io, in the pipeline's
+        dtype: autograd starts there (the UNet is never differentiated; the scaling and its backward are
+        inside our kernels), and the gradient goes to the update kernel as autograd returns it."""
         if supervised_space not in ("wav_form", "mel_spectrogram"):
             raise ValueError("supervised_space should be either 'wav_form' or 'mel_spectrogram")
         op = self.operator
+        io_dtype = leaf.dtype
         with torch.enable_grad():
-            leaf = x0.detach().requires_grad_(True)
-            mel = vae.decode(1 / vae.config.scaling_factor * leaf.to(model_dtype)).sample
+            leaf = leaf.detach()
+            if model_dtype is not None and leaf.dtype != model_dtype:  # exotic / mixed input dtypes went through fp32
+                leaf = leaf.to(model_dtype)
+            leaf.requires_grad_(True)
+            mel = vae.decode(leaf).sample
             wav_full = op.inverse_transform(mel, vocoder)
             wav = wav_full[:, :L]
             if getattr(op, "fused_loss_and_grad", None) is not None and wav_full.dim() == 2 \
@@ -178,21 +191,31 @@ class _GuidedBase(DDIMBase):
                 # starts at the vocoder output: no slice-backward zero-fill + copy of the whole waveform.  fp16 / bf16
                 # pipelines: the kernels read the 16-bit waveform and write the 16-bit cotangent directly.
                 Lw = wav.shape[1]
-                dfull = torch.empty_like(wav_full)
-                if wav_full.shape[1] > Lw:
-                    dfull[:, Lw:].zero_()
+                dfull = self._cotangent_buffer(wav_full, Lw)
                 losses, _ = op.fused_loss_and_grad(wav.detach(), measurement, supervised_space, dwav=dfull[:, :Lw])
-                (g0,) = torch.autograd.grad(wav_full, leaf, grad_outputs=dfull)
+                (g,) = torch.autograd.grad(wav_full, leaf, grad_outputs=dfull)
             elif getattr(op, "fused_loss_and_grad", None) is not None:
                 losses, dwav = op.fused_loss_and_grad(wav.detach(), measurement, supervised_space)
-                (g0,) = torch.autograd.grad(wav, leaf, grad_outputs=dwav.to(wav.dtype))
+                (g,) = torch.autograd.grad(wav, leaf, grad_outputs=dwav.to(wav.dtype))
             else:
                 if hasattr(op, "guidance_loss"):
                     losses = op.guidance_loss(wav, measurement, supervised_space)
                 else:
                     losses = generic_guidance_loss(op, wav, measurement, supervised_space)
-                (g0,) = torch.autograd.grad(losses.sum(), leaf)
-        return losses.detach(), g0.float().contiguous()
+                (g,) = torch.autograd.grad(losses.sum(), leaf)
+        return losses.detach(), g.to(io_dtype).contiguous()
+
+    def _cotangent_buffer(self, wav_full, Lw):
+        """vocoder-shaped cotangent buffer, kept between steps: the kernels overwrite [:, :Lw] every step and never touch
+        the tail, which is zeroed once here (no per-step fill kernel)."""
+        key = (tuple(wav_full.shape), wav_full.dtype, wav_full.device, Lw)
+        cache = self.__dict__.setdefault("_dfull_cache", {})
+        buf = cache.get(key)
+        if buf is None:
+            buf = torch.zeros_like(wav_full)
+            cache.clear()
+            cache[key] = buf
+        return buf
 
     @staticmethod
     def _loss_out(losses):
@@ -210,8 +233,8 @@ class _GuidedBase(DDIMBase):
         the embeddings detached.  Kept for API compatibility; the guided loss is still evaluated so errors surface."""
         c = self._coeffs(timestep, eta)
         x, eps, io = self._prep_pair(sample, model_output)
-        x0, _ = self._x0(x, eps, c, io, publish=False)
-        self._guidance(x0, measurement, vae, vocoder, original_waveform_length, supervised_space, sample.dtype)
+        _, _, leaf = self._x0(x, eps, c, io, publish=False, leaf_scale=self._leaf_scale(vae))
+        self._guidance(leaf, measurement, vae, vocoder, original_waveform_length, supervised_space, sample.dtype)
         return InverseProblemSchedulerOutput(
             encoder_hidden_states=None if encoder_hidden_states is None else encoder_hidden_states.detach(),
             encoder_hidden_states_1=None if encoder_hidden_states_1 is None else encoder_hidden_states_1.detach())
@@ -228,7 +251,7 @@ class DDIMScheduler(_GuidedBase):
         c = self._coeffs(timestep, eta)
         x, eps, io = self._prep_pair(sample, model_output)
         self._noise_arg(_noise, eta, generator, variance_noise, model_output)
-        x0, x0_pub = self._x0(x, eps, c, io)
+        x0, x0_pub, _ = self._x0(x, eps, c, io)
         prev = torch.empty_like(x)
         _lib.call("dm_sched_ddim_update_io", x.data_ptr(), x0.data_ptr(), prev.data_ptr(), x.numel(), c["sqrt_a"],
                   c["sqrt_b"], c["sqrt_p"], c["sqrt_1mp"], self._coef_ptr(), io, _lib.stream())
@@ -249,12 +272,13 @@ class DPSScheduler(_GuidedBase):
         c = self._coeffs(timestep, eta)
         x, eps, io = self._prep_pair(sample, model_output)
         z = self._noise_arg(_noise, eta, generator, variance_noise, model_output)
-        x0, x0_pub = self._x0(x, eps, c, io)
-        losses, g0 = self._guidance(x0, measurement, vae, vocoder, original_waveform_length, supervised_space,
+        ls = self._leaf_scale(vae)
+        x0, x0_pub, leaf = self._x0(x, eps, c, io, leaf_scale=ls)
+        losses, g0 = self._guidance(leaf, measurement, vae, vocoder, original_waveform_length, supervised_space,
                                     sample.dtype)
         prev = torch.empty_like(x)
-        _lib.call("dm_sched_dps_update_io", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), _lib.ptr(z), prev.data_ptr(),
-                  x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"], float(ip_guidance_rate),
+        _lib.call("dm_sched_dps_update_io", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), ls, _lib.ptr(z),
+                  prev.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"], float(ip_guidance_rate),
                   self._coef_ptr(), io, _lib.stream())
         return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
                                              pred_original_sample=x0_pub.to(sample.dtype),
@@ -271,12 +295,13 @@ class MPGDScheduler(_GuidedBase):
         c = self._coeffs(timestep, eta)
         x, eps, io = self._prep_pair(sample, model_output)
         z = self._noise_arg(_noise, eta, generator, variance_noise, model_output)
-        x0, _ = self._x0(x, eps, c, io, publish=False)
-        losses, g0 = self._guidance(x0, measurement, vae, vocoder, original_waveform_length, supervised_space,
+        ls = self._leaf_scale(vae)
+        x0, _, leaf = self._x0(x, eps, c, io, publish=False, leaf_scale=ls)
+        losses, g0 = self._guidance(leaf, measurement, vae, vocoder, original_waveform_length, supervised_space,
                                     sample.dtype)
         prev, x0_new = torch.empty_like(x), torch.empty_like(x)
-        _lib.call("dm_sched_mpgd_update_io", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), _lib.ptr(z), prev.data_ptr(),
-                  x0_new.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"],
+        _lib.call("dm_sched_mpgd_update_io", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), ls, _lib.ptr(z),
+                  prev.data_ptr(), x0_new.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"],
                   float(ip_guidance_rate), self._coef_ptr(), io, _lib.stream())
         return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
                                              pred_original_sample=x0_new.to(sample.dtype),
@@ -294,19 +319,21 @@ class _SphericalBase(_GuidedBase):
         x, e, io = self._prep_pair(sample, model_output)
         # one draw per step (scheduling_dsg.py:215-220; `variance_noise` is not consulted by the reference there)
         z = self._noise_arg(_noise, eta, generator, variance_noise, model_output)
-        x0, x0_pub = self._x0(x, e, c, io)  # base step called without eta (scheduling_dsg.py:178-186): no RNG draw
-        losses, g0 = self._guidance(x0, measurement, vae, vocoder, L, supervised_space, sample.dtype)
+        ls = self._leaf_scale(vae)
+        # base step called without eta (scheduling_dsg.py:178-186): no RNG draw
+        x0, x0_pub, leaf = self._x0(x, e, c, io, leaf_scale=ls)
+        losses, g0 = self._guidance(leaf, measurement, vae, vocoder, L, supervised_space, sample.dtype)
         B = x.shape[0]
         n_clip = x.numel() // B
         prev = torch.empty_like(x)
         if kernel == "dsg":
             # r = sqrt(c*h*w) * std as fp32 (scheduling_dsg.py:212-213)
             r = _f(torch.sqrt(torch.tensor(n_clip)) * c["std"])
-            _lib.call("dm_sched_dsg_update_io", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), z.data_ptr(),
+            _lib.call("dm_sched_dsg_update_io", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), ls, z.data_ptr(),
                       prev.data_ptr(), B, n_clip, c["sqrt_a"], c["sqrt_p"], c["dir_coef"], c["std"],
                       float(ip_guidance_rate), r, 1.0 / 1000.0, float(eps), self._coef_ptr(), io, _lib.stream())
         else:
-            _lib.call("dm_sched_diffmusic_update_io", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), z.data_ptr(),
+            _lib.call("dm_sched_diffmusic_update_io", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), ls, z.data_ptr(),
                       prev.data_ptr(), B, n_clip, c["sqrt_a"], c["sqrt_p"], c["dir_coef"], c["std"],
                       float(ip_guidance_rate), 1.0 / 1000.0, float(eps), 0.9995, self._coef_ptr(), io, _lib.stream())
         return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),

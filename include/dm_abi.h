@@ -83,23 +83,30 @@ int dm_sched_diffmusic_update(const float* x0, const float* eps, const float* g0
 #define DM_IO_F32 0
 #define DM_IO_F16 1
 #define DM_IO_BF16 2
-int dm_sched_x0_io(const void* x, const void* eps, float* x0, void* x0_pub /* may be NULL */, long long n, float sqrt_a,
-                   float sqrt_b, int clip, float clip_range, const float* coef, int io_dtype, dm_stream_t stream);
+int dm_sched_x0_io(const void* x, const void* eps, float* x0, void* x0_pub /* may be NULL */,
+                   void* x0_leaf /* may be NULL */, float leaf_scale, long long n, float sqrt_a, float sqrt_b, int clip,
+                   float clip_range, const float* coef, int io_dtype, dm_stream_t stream);
 int dm_sched_ddim_update_io(const void* x, const float* x0, void* prev, long long n, float sqrt_a, float sqrt_b,
                             float sqrt_p, float sqrt_1mp, const float* coef, int io_dtype, dm_stream_t stream);
-int dm_sched_dps_update_io(const void* x, const float* x0, const float* g0, const float* z, void* prev, long long n,
-                           float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std, float rate,
-                           const float* coef, int io_dtype, dm_stream_t stream);
+/* The reference differentiates through `1 / vae.config.scaling_factor * x0` (scheduling_dps.py:195-197): two torch
+ * kernels (the scaling and its backward) around the networks.  Here dm_sched_x0_io also writes the scaled, latent-typed
+ * decoder input x0_leaf = leaf_scale * x0, autograd runs from that leaf, and the update kernels take g0 = dLoss/d(leaf)
+ * in the latent dtype together with leaf_scale: dLoss/dx0 = leaf_scale * g0, applied first, exactly where torch's
+ * multiply-backward would have rounded it. */
+int dm_sched_dps_update_io(const void* x, const float* x0, const void* g0, float leaf_scale, const float* z, void* prev,
+                           long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std,
+                           float rate, const float* coef, int io_dtype, dm_stream_t stream);
 /* x0_out is latent-typed here (it is only handed back to the caller) */
-int dm_sched_mpgd_update_io(const void* x, const float* x0, const float* g0, const float* z, void* prev, void* x0_out,
-                            long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std,
-                            float rate, const float* coef, int io_dtype, dm_stream_t stream);
-int dm_sched_dsg_update_io(const float* x0, const void* eps, const float* g0, const float* z, void* prev, int n_clips,
-                           long long n_clip, float sqrt_a, float sqrt_p, float dir_coef, float std, float rate,
-                           float r, float grad_scale, float e, const float* coef, int io_dtype, dm_stream_t stream);
-int dm_sched_diffmusic_update_io(const float* x0, const void* eps, const float* g0, const float* z, void* prev,
-                                 int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef, float std,
-                                 float rate, float grad_scale, float e, float threshold, const float* coef,
+int dm_sched_mpgd_update_io(const void* x, const float* x0, const void* g0, float leaf_scale, const float* z, void* prev,
+                            void* x0_out, long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef,
+                            float std, float rate, const float* coef, int io_dtype, dm_stream_t stream);
+int dm_sched_dsg_update_io(const float* x0, const void* eps, const void* g0, float leaf_scale, const float* z,
+                           void* prev, int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef,
+                           float std, float rate, float r, float grad_scale, float e, const float* coef, int io_dtype,
+                           dm_stream_t stream);
+int dm_sched_diffmusic_update_io(const float* x0, const void* eps, const void* g0, float leaf_scale, const float* z,
+                                 void* prev, int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef,
+                                 float std, float rate, float grad_scale, float e, float threshold, const float* coef,
                                  int io_dtype, dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------

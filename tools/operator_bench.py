@@ -103,7 +103,7 @@ def main():
         sched = dm.get_scheduler(name)(operator=None, **stubs.MUSICLDM_SCHED)
         sched.set_timesteps(500)
         c = sched._coeffs(501, 1.0)
-        x0, _ = sched._x0(x, e, c, 0)
+        x0 = sched._x0(x, e, c, 0)[0]
         prev = torch.empty_like(x)
         from diffmusic_b200 import _lib
         st = _lib.stream
