@@ -92,6 +92,13 @@ class GraphedGuidedStep:
             self._ir_host.copy_(ir.reshape(-1))
             self._ir_dev.copy_(self._ir_host, non_blocking=True)
 
+    def replay_in_place(self, timestep, generator=None, variance_noise=None):
+        """Replay on whatever the caller has already put into the static inputs `self.x` / `self.e` (e.g. uploaded
+        straight from pinned host memory); returns the static output object, valid until the next replay."""
+        self._prepare(int(timestep), generator, variance_noise)
+        self.graph.replay()
+        return self.out
+
     def __call__(self, model_output, timestep, sample, generator=None, variance_noise=None, _borrow=False, **ignored):
         self.x.copy_(sample, non_blocking=True)
         self.e.copy_(model_output, non_blocking=True)
@@ -135,14 +142,23 @@ class HostPipelinedStep:
         pipe.drain()
     """
 
-    def __init__(self, graphed: GraphedGuidedStep):
-        self.g = graphed
+    def __init__(self, graphed, second=None):
+        """graphed: a GraphedGuidedStep.  second (optional): another GraphedGuidedStep captured with the same arguments;
+        with two graphs the uploads land directly in the static inputs of the graph that will consume them and the
+        downloads read its static outputs -- no device-to-device staging copies at all."""
+        self.g = [graphed] if second is None else [graphed, second]
+        if second is not None and (second.x.shape != graphed.x.shape or second.x.dtype != graphed.x.dtype):
+            raise ValueError("the two captured steps must have the same latent shape and dtype")
         dev = graphed.x.device
         self.dev = dev
+        self.direct = second is not None
         self.up, self.down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        mk = lambda: torch.empty_like(graphed.x)  # noqa: E731
-        self.x_st, self.e_st, self.prev_st = [mk(), mk()], [mk(), mk()], [mk(), mk()]
-        self.loss_st = [torch.zeros(graphed.B, device=dev, dtype=torch.float32) for _ in range(2)]
+        if self.direct:
+            self.x_st, self.e_st = [graphed.x, second.x], [graphed.e, second.e]
+        else:
+            mk = lambda: torch.empty_like(graphed.x)  # noqa: E731
+            self.x_st, self.e_st, self.prev_st = [mk(), mk()], [mk(), mk()], [mk(), mk()]
+            self.loss_st = [torch.zeros(graphed.B, device=dev, dtype=torch.float32) for _ in range(2)]
         ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]  # noqa: E731
         self.uploaded, self.slot_free, self.computed, self.downloaded = ev(), ev(), ev(), ev()
         self.n_up = self.n_run = 0
@@ -173,20 +189,27 @@ class HostPipelinedStep:
         k = self.n_run % 2
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(self.uploaded[k])
-        out = self.g(self.e_st[k], timestep, self.x_st[k], generator=generator, variance_noise=variance_noise,
-                     _borrow=True)
-        self.slot_free[k].record(cur)  # inputs were copied into the graph's static buffers before the replay
         if self.n_run >= 2:
-            cur.wait_event(self.downloaded[k])  # the staging slot's previous content has reached the host
-        self.prev_st[k].copy_(out.prev_sample, non_blocking=True)
-        if loss_host is not None and out.loss_per_clip is not None:
-            self.loss_st[k].copy_(out.loss_per_clip.reshape(-1), non_blocking=True)
+            cur.wait_event(self.downloaded[k])  # this slot's previous results have reached the host
+        if self.direct:
+            out = self.g[k].replay_in_place(timestep, generator=generator, variance_noise=variance_noise)
+            prev_src = out.prev_sample
+            loss_src = None if out.loss_per_clip is None else out.loss_per_clip.reshape(-1)
+        else:
+            out = self.g[0](self.e_st[k], timestep, self.x_st[k], generator=generator, variance_noise=variance_noise,
+                            _borrow=True)
+            self.prev_st[k].copy_(out.prev_sample, non_blocking=True)
+            prev_src, loss_src = self.prev_st[k], None
+            if loss_host is not None and out.loss_per_clip is not None:
+                self.loss_st[k].copy_(out.loss_per_clip.reshape(-1), non_blocking=True)
+                loss_src = self.loss_st[k]
+        self.slot_free[k].record(cur)  # the inputs of this slot have been consumed
         self.computed[k].record(cur)
         self.down.wait_event(self.computed[k])
         with torch.cuda.stream(self.down):
-            prev_sample_host.copy_(self.prev_st[k], non_blocking=True)
-            if loss_host is not None:
-                loss_host.copy_(self.loss_st[k], non_blocking=True)
+            prev_sample_host.copy_(prev_src, non_blocking=True)
+            if loss_host is not None and loss_src is not None:
+                loss_host.copy_(loss_src, non_blocking=True)
             self.downloaded[k].record(self.down)
         if self.n_run >= 1:
             cur.wait_event(self.downloaded[1 - k])  # step i returns only after step i-1's results are on the host

@@ -509,7 +509,8 @@ def test_graphed_step_equals_eager_step(sched_name, op_name, eta):
         xe, xg = a.prev_sample, b.prev_sample  # chain the trajectory
 
 
-def test_host_pipelined_steps_equal_direct_replays():
+@pytest.mark.parametrize("two_graphs", [False, True])
+def test_host_pipelined_steps_equal_direct_replays(two_graphs):
     """HostPipelinedStep (pinned-host latents, uploads / downloads overlapped on side streams) returns exactly what the
     same graph gives for device-resident inputs, for a run long enough to reuse both staging slots several times."""
     B, n = 3, 7
@@ -531,7 +532,8 @@ def test_host_pipelined_steps_equal_direct_replays():
     es = [e.pin_memory() for _, e in lat]
     prev = [torch.empty_like(xs[0]).pin_memory() for _ in range(n)]
     loss = [torch.empty(B).pin_memory() for _ in range(n)]
-    pipe = dm.HostPipelinedStep(graphed)
+    second = dm.GraphedGuidedStep(sched, (B, 8, 25, 16), **kw) if two_graphs else None
+    pipe = dm.HostPipelinedStep(graphed, second)
     pipe.prefetch(es[0], xs[0])
     for i in range(n):
         if i + 1 < n:
