@@ -224,7 +224,7 @@ def main():
     orig_call = _lib.call
 
     def timed_call(name, *a):
-        if name == "dm_stft_guidance" and timed_call.on:
+        if name in ("dm_stft_guidance", "dm_stft_guidance_io") and timed_call.on:
             s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             orig_call(name, *a)
