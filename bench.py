@@ -208,7 +208,20 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner to STDOUT when the first communicator comes up; stdout must carry exactly one
+        # JSON line, so fd 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            warm = torch.zeros(1, device=device)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     sched, op, x_h, e_h, kw, B = build_case(args.workload, device, first_clip=rank * 64)
     x_d, e_d = x_h.to(device), e_h.to(device)

@@ -127,3 +127,17 @@ def test_dropin_namespace_imports():
             % (ROOT, os.path.join(ROOT, "diffmusic_b200", "dropin")))
     out = subprocess.check_output([sys.executable, "-c", code], text=True)
     assert out.strip().endswith("ok")
+
+
+def test_bench_hooks_the_entry_point_the_operators_call():
+    """bench.py times the dominant kernel by wrapping _lib.call for the STFT guidance entry point: the name it matches
+    must be the one diffmusic_b200/operators.py actually calls (a silent mismatch leaves roofline.achieved null)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ops = open(os.path.join(root, "diffmusic_b200", "operators.py")).read()
+    bench = open(os.path.join(root, "bench.py")).read()
+    called = set(re.findall(r'_lib\.call\("(dm_stft_guidance\w*)"', ops))
+    assert called, "operators.py no longer calls a dm_stft_guidance* entry point?"
+    hooked = set(re.findall(r'"(dm_stft_guidance\w*)"', bench))
+    assert called <= hooked, (called, hooked)
