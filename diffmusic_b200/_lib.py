@@ -37,13 +37,13 @@ _SIGNATURES = {
     "dm_sched_x0_io": (c_i, [c_p, c_p, c_p, c_p, c_p, c_f, c_ll, c_f, c_f, c_i, c_f, c_p, c_i, c_p]),
     "dm_sched_ddim_update_io": (c_i, [c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_p, c_i, c_p]),
     "dm_sched_dps_update_io": (c_i, [c_p, c_p, c_p, c_f, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_p, c_i,
-                                     c_p]),
+                                     c_p, c_i, c_p, c_p]),
     "dm_sched_mpgd_update_io": (c_i, [c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_p,
-                                      c_i, c_p]),
+                                      c_i, c_p, c_i, c_p, c_p]),
     "dm_sched_dsg_update_io": (c_i, [c_p, c_p, c_p, c_f, c_p, c_p, c_i, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
-                                     c_p, c_i, c_p]),
+                                     c_p, c_i, c_p, c_p, c_p]),
     "dm_sched_diffmusic_update_io": (c_i, [c_p, c_p, c_p, c_f, c_p, c_p, c_i, c_ll, c_f, c_f, c_f, c_f, c_f, c_f,
-                                           c_f, c_f, c_p, c_i, c_p]),
+                                           c_f, c_f, c_p, c_i, c_p, c_p, c_p]),
     "dm_stft_guidance_io": (c_i, [C.POINTER(StftTables), c_i, c_i, c_i, c_p, c_i, c_ll, c_ll, c_p, c_i, c_p, c_ll, c_p,
                                   c_f, c_p, c_p, c_p, c_i, c_p]),
     "dm_residual_wav_io": (c_i, [c_p, c_i, c_ll, c_ll, c_i, c_p, c_p, c_ll, c_p, c_p, c_p]),

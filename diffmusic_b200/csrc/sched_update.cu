@@ -103,11 +103,21 @@ struct EwParams {
     void* x0_leaf;    // kX0, optional latent-typed: leaf_scale * x0 = the VAE decoder input 1/scaling_factor * x0
                       // (scheduling_dps.py:195-197), so torch needs no scaling kernel (nor its backward)
     float leaf_scale; // kX0: the factor above; updates: dLoss/dx0 = leaf_scale * g0 (chain rule of that scaling)
+    const float* losses;  // optional per-clip losses (n_losses of them) and where to put their 2-norm: the 0-d `loss` of
+    int n_losses;         // the reference (torch.linalg.norm over the whole batch, scheduling_dps.py:211) without a
+    float* loss_total;    // reduction kernel of its own
     float sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate, clip_range;
     int clip;
     const float* coef;  // optional device-resident [sqrt_a, sqrt_b, sqrt_p, dir_coef, std, r]: overrides the by-value
                         // scalars so a captured CUDA graph can be replayed for every timestep
 };
+
+// batch loss = sqrt(sum_b loss_b^2) by one thread (B <= a few hundred); NaN / Inf propagate
+__device__ __forceinline__ void write_loss_total(const float* __restrict__ losses, int n, float* __restrict__ out) {
+    float s = 0.f;
+    for (int b = 0; b < n; ++b) s = fmaf(losses[b], losses[b], s);
+    *out = n == 1 ? losses[0] : sqrtf(s);
+}
 
 __device__ __forceinline__ void load_coef(const float* __restrict__ c, float& sqrt_a, float& sqrt_b, float& sqrt_p,
                                           float& dir_coef, float& std) {
@@ -125,6 +135,8 @@ enum EwKind { kX0 = 0, kDdim = 1, kDps = 2, kMpgd = 3 };
 template <int KIND, int W, int IO>
 __global__ void __launch_bounds__(kThreads) ew_update_kernel(EwParams p, long long nvec) {
     load_coef(p.coef, p.sqrt_a, p.sqrt_b, p.sqrt_p, p.dir_coef, p.std);
+    if (KIND != kX0 && p.loss_total != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+        write_loss_total(p.losses, p.n_losses, p.loss_total);
     const long long stride = (long long)gridDim.x * kThreads;
     for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += stride) {
         float x[W], a[W], g[W], z[W], o[W], o2[W];
@@ -210,6 +222,9 @@ struct NormParams {
     float sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, threshold;
     const float* coef;  // optional device-resident coefficients (see EwParams::coef)
     float leaf_scale;
+    const float* losses;  // see EwParams
+    int n_losses;
+    float* loss_total;
 };
 // g0 as loaded (dLoss/d leaf) -> dLoss/dx0
 template <int IO, int W>
@@ -288,6 +303,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) nor
     }
     __shared__ double wred[(kThreads / 32) * 3];
     __shared__ double slot1[3], slot2[3];
+    if (p.loss_total != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+        write_loss_total(p.losses, p.n_losses, p.loss_total);
     const unsigned rank = cluster.block_rank();
     const long long clip = blockIdx.x / kCluster;
     const long long nv_clip = p.n_clip / W;
@@ -492,10 +509,14 @@ extern "C" int dm_sched_ddim_update(const float* x, const float* x0, float* prev
 extern "C" int dm_sched_dps_update_io(const void* x, const float* x0, const void* g0, float leaf_scale, const float* z,
                                       void* prev, long long n, float sqrt_a, float sqrt_b, float sqrt_p,
                                       float dir_coef, float std, float rate, const float* coef, int io_dtype,
-                                      dm_stream_t stream) {
+                                      const float* losses, int n_losses, float* loss_total, dm_stream_t stream) {
     DM_REQUIRE(x && x0 && g0 && prev && n > 0 && io_ok(io_dtype));
+    DM_REQUIRE(loss_total == nullptr || (losses != nullptr && n_losses > 0));
     EwParams p{};
     p.leaf_scale = leaf_scale;
+    p.losses = losses;
+    p.n_losses = n_losses;
+    p.loss_total = loss_total;
     p.coef = coef;
     p.x = x;
     p.x0 = x0;
@@ -516,16 +537,20 @@ extern "C" int dm_sched_dps_update(const float* x, const float* x0, const float*
                                    long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std,
                                    float rate, const float* coef, dm_stream_t stream) {
     return dm_sched_dps_update_io(x, x0, g0, 1.f, z, prev, n, sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate, coef,
-                                  DM_IO_F32, stream);
+                                  DM_IO_F32, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int dm_sched_mpgd_update_io(const void* x, const float* x0, const void* g0, float leaf_scale, const float* z,
                                        void* prev, void* x0_out, long long n, float sqrt_a, float sqrt_b, float sqrt_p,
                                        float dir_coef, float std, float rate, const float* coef, int io_dtype,
-                                       dm_stream_t stream) {
+                                       const float* losses, int n_losses, float* loss_total, dm_stream_t stream) {
     DM_REQUIRE(x && x0 && g0 && prev && x0_out && n > 0 && io_ok(io_dtype));
+    DM_REQUIRE(loss_total == nullptr || (losses != nullptr && n_losses > 0));
     EwParams p{};
     p.leaf_scale = leaf_scale;
+    p.losses = losses;
+    p.n_losses = n_losses;
+    p.loss_total = loss_total;
     p.coef = coef;
     p.x = x;
     p.x0 = x0;
@@ -549,16 +574,18 @@ extern "C" int dm_sched_mpgd_update(const float* x, const float* x0, const float
                                     float dir_coef, float std, float rate, const float* coef,
                                     dm_stream_t stream) {
     return dm_sched_mpgd_update_io(x, x0, g0, 1.f, z, prev, x0_out, n, sqrt_a, sqrt_b, sqrt_p, dir_coef, std, rate,
-                                   coef, DM_IO_F32, stream);
+                                   coef, DM_IO_F32, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int dm_sched_dsg_update_io(const float* x0, const void* eps, const void* g0, float leaf_scale, const float* z,
                                       void* prev, int n_clips, long long n_clip, float sqrt_a, float sqrt_p,
                                       float dir_coef, float std, float rate, float r, float grad_scale, float e,
-                                      const float* coef, int io_dtype, dm_stream_t stream) {
+                                      const float* coef, int io_dtype, const float* losses, float* loss_total,
+                                      dm_stream_t stream) {
     DM_REQUIRE(x0 && eps && g0 && z && prev && n_clips > 0 && n_clip > 0 && io_ok(io_dtype));
+    DM_REQUIRE(loss_total == nullptr || losses != nullptr);
     NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, r, grad_scale, e, 0.f, coef,
-                 leaf_scale};
+                 leaf_scale, losses, n_clips, loss_total};
     launch_norm<kDsg>(p, n_clips, io_dtype, as_stream(stream));
     DM_LAUNCHED();
     return DM_OK;
@@ -568,17 +595,18 @@ extern "C" int dm_sched_dsg_update(const float* x0, const float* eps, const floa
                                    float std, float rate, float r, float grad_scale, float e, const float* coef,
                                    dm_stream_t stream) {
     return dm_sched_dsg_update_io(x0, eps, g0, 1.f, z, prev, n_clips, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, r,
-                                  grad_scale, e, coef, DM_IO_F32, stream);
+                                  grad_scale, e, coef, DM_IO_F32, nullptr, nullptr, stream);
 }
 
 extern "C" int dm_sched_diffmusic_update_io(const float* x0, const void* eps, const void* g0, float leaf_scale,
                                             const float* z, void* prev, int n_clips, long long n_clip, float sqrt_a,
                                             float sqrt_p, float dir_coef, float std, float rate, float grad_scale,
                                             float e, float threshold, const float* coef, int io_dtype,
-                                            dm_stream_t stream) {
+                                            const float* losses, float* loss_total, dm_stream_t stream) {
     DM_REQUIRE(x0 && eps && g0 && z && prev && n_clips > 0 && n_clip > 0 && io_ok(io_dtype));
+    DM_REQUIRE(loss_total == nullptr || losses != nullptr);
     NormParams p{x0, eps, g0, z, prev, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate, 0.f, grad_scale, e, threshold,
-                 coef, leaf_scale};
+                 coef, leaf_scale, losses, n_clips, loss_total};
     launch_norm<kDiffMusic>(p, n_clips, io_dtype, as_stream(stream));
     DM_LAUNCHED();
     return DM_OK;
@@ -588,5 +616,5 @@ extern "C" int dm_sched_diffmusic_update(const float* x0, const float* eps, cons
                                          float dir_coef, float std, float rate, float grad_scale, float e,
                                          float threshold, const float* coef, dm_stream_t stream) {
     return dm_sched_diffmusic_update_io(x0, eps, g0, 1.f, z, prev, n_clips, n_clip, sqrt_a, sqrt_p, dir_coef, std, rate,
-                                        grad_scale, e, threshold, coef, DM_IO_F32, stream);
+                                        grad_scale, e, threshold, coef, DM_IO_F32, nullptr, nullptr, stream);
 }

@@ -218,11 +218,11 @@ class _GuidedBase(DDIMBase):
         return buf
 
     @staticmethod
-    def _loss_out(losses):
-        """0-d loss like the reference's torch.linalg.norm over the whole batch (= the per-clip norm for B = 1)."""
-        if losses.numel() == 1:
-            return losses.reshape(())
-        return torch.linalg.norm(losses)
+    def _loss_slot(losses):
+        """(contiguous fp32 per-clip losses, 0-d device tensor the update kernel fills with their 2-norm): the
+        reference's 0-d `loss` = torch.linalg.norm over the whole batch (= the per-clip norm for B = 1)."""
+        losses = losses.float().contiguous()
+        return losses, torch.empty((), device=losses.device, dtype=torch.float32)
 
     def optim_prompt(self, model_output, timestep, sample, encoder_hidden_states=None, encoder_hidden_states_1=None,
                      eta=0.0, use_clipped_model_output=False, generator=None, variance_noise=None, return_dict=True,
@@ -277,12 +277,14 @@ class DPSScheduler(_GuidedBase):
         losses, g0 = self._guidance(leaf, measurement, vae, vocoder, original_waveform_length, supervised_space,
                                     sample.dtype)
         prev = torch.empty_like(x)
+        losses, total = self._loss_slot(losses)
         _lib.call("dm_sched_dps_update_io", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), ls, _lib.ptr(z),
-                  prev.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"], float(ip_guidance_rate),
-                  self._coef_ptr(), io, _lib.stream())
+                  prev.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"],
+                  float(ip_guidance_rate), self._coef_ptr(), io, losses.data_ptr(), losses.numel(), total.data_ptr(),
+                  _lib.stream())
         return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
                                              pred_original_sample=x0_pub.to(sample.dtype),
-                                             loss=self._loss_out(losses), loss_per_clip=losses)
+                                             loss=total, loss_per_clip=losses)
 
 
 class MPGDScheduler(_GuidedBase):
@@ -300,12 +302,14 @@ class MPGDScheduler(_GuidedBase):
         losses, g0 = self._guidance(leaf, measurement, vae, vocoder, original_waveform_length, supervised_space,
                                     sample.dtype)
         prev, x0_new = torch.empty_like(x), torch.empty_like(x)
+        losses, total = self._loss_slot(losses)
         _lib.call("dm_sched_mpgd_update_io", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), ls, _lib.ptr(z),
-                  prev.data_ptr(), x0_new.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"], c["std"],
-                  float(ip_guidance_rate), self._coef_ptr(), io, _lib.stream())
+                  prev.data_ptr(), x0_new.data_ptr(), x.numel(), c["sqrt_a"], c["sqrt_b"], c["sqrt_p"], c["dir_coef"],
+                  c["std"], float(ip_guidance_rate), self._coef_ptr(), io, losses.data_ptr(), losses.numel(),
+                  total.data_ptr(), _lib.stream())
         return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
                                              pred_original_sample=x0_new.to(sample.dtype),
-                                             loss=self._loss_out(losses), loss_per_clip=losses)
+                                             loss=total, loss_per_clip=losses)
 
 
 class _SphericalBase(_GuidedBase):
@@ -326,19 +330,22 @@ class _SphericalBase(_GuidedBase):
         B = x.shape[0]
         n_clip = x.numel() // B
         prev = torch.empty_like(x)
+        losses, total = self._loss_slot(losses)
         if kernel == "dsg":
             # r = sqrt(c*h*w) * std as fp32 (scheduling_dsg.py:212-213)
             r = _f(torch.sqrt(torch.tensor(n_clip)) * c["std"])
             _lib.call("dm_sched_dsg_update_io", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), ls, z.data_ptr(),
                       prev.data_ptr(), B, n_clip, c["sqrt_a"], c["sqrt_p"], c["dir_coef"], c["std"],
-                      float(ip_guidance_rate), r, 1.0 / 1000.0, float(eps), self._coef_ptr(), io, _lib.stream())
+                      float(ip_guidance_rate), r, 1.0 / 1000.0, float(eps), self._coef_ptr(), io, losses.data_ptr(),
+                      total.data_ptr(), _lib.stream())
         else:
             _lib.call("dm_sched_diffmusic_update_io", x0.data_ptr(), e.data_ptr(), g0.data_ptr(), ls, z.data_ptr(),
                       prev.data_ptr(), B, n_clip, c["sqrt_a"], c["sqrt_p"], c["dir_coef"], c["std"],
-                      float(ip_guidance_rate), 1.0 / 1000.0, float(eps), 0.9995, self._coef_ptr(), io, _lib.stream())
+                      float(ip_guidance_rate), 1.0 / 1000.0, float(eps), 0.9995, self._coef_ptr(), io,
+                      losses.data_ptr(), total.data_ptr(), _lib.stream())
         return InverseProblemSchedulerOutput(prev_sample=prev.to(sample.dtype),
                                              pred_original_sample=x0_pub.to(sample.dtype),
-                                             loss=self._loss_out(losses), loss_per_clip=losses)
+                                             loss=total, loss_per_clip=losses)
 
 
 class DSGScheduler(_SphericalBase):

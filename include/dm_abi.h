@@ -92,22 +92,27 @@ int dm_sched_ddim_update_io(const void* x, const float* x0, void* prev, long lon
  * kernels (the scaling and its backward) around the networks.  Here dm_sched_x0_io also writes the scaled, latent-typed
  * decoder input x0_leaf = leaf_scale * x0, autograd runs from that leaf, and the update kernels take g0 = dLoss/d(leaf)
  * in the latent dtype together with leaf_scale: dLoss/dx0 = leaf_scale * g0, applied first, exactly where torch's
- * multiply-backward would have rounded it. */
+ * multiply-backward would have rounded it.
+ * losses / loss_total (may be NULL): per-clip losses of the batch and where to put their 2-norm = the reference's 0-d
+ * `loss` (torch.linalg.norm over the whole batch, scheduling_dps.py:211), written by one thread of the update kernel. */
 int dm_sched_dps_update_io(const void* x, const float* x0, const void* g0, float leaf_scale, const float* z, void* prev,
                            long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef, float std,
-                           float rate, const float* coef, int io_dtype, dm_stream_t stream);
+                           float rate, const float* coef, int io_dtype, const float* losses, int n_losses,
+                           float* loss_total, dm_stream_t stream);
 /* x0_out is latent-typed here (it is only handed back to the caller) */
 int dm_sched_mpgd_update_io(const void* x, const float* x0, const void* g0, float leaf_scale, const float* z, void* prev,
                             void* x0_out, long long n, float sqrt_a, float sqrt_b, float sqrt_p, float dir_coef,
-                            float std, float rate, const float* coef, int io_dtype, dm_stream_t stream);
+                            float std, float rate, const float* coef, int io_dtype, const float* losses, int n_losses,
+                            float* loss_total, dm_stream_t stream);
 int dm_sched_dsg_update_io(const float* x0, const void* eps, const void* g0, float leaf_scale, const float* z,
                            void* prev, int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef,
                            float std, float rate, float r, float grad_scale, float e, const float* coef, int io_dtype,
-                           dm_stream_t stream);
+                           const float* losses /* n_clips */, float* loss_total, dm_stream_t stream);
 int dm_sched_diffmusic_update_io(const float* x0, const void* eps, const void* g0, float leaf_scale, const float* z,
                                  void* prev, int n_clips, long long n_clip, float sqrt_a, float sqrt_p, float dir_coef,
                                  float std, float rate, float grad_scale, float e, float threshold, const float* coef,
-                                 int io_dtype, dm_stream_t stream);
+                                 int io_dtype, const float* losses /* n_clips */, float* loss_total,
+                                 dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * STFT / mel guidance  (operator.py:24-36,123-124 T_mel ; 153-154 phase mel ; 162-171 |STFT|)

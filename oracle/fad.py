@@ -3,6 +3,12 @@
 fadtk/fad.py:41-47 (`calc_embd_statistics`) and fadtk/utils.py:13-46 (`_process_file`,
 `calculate_embd_statistics_online`).  fadtk/utils.py cannot be imported here (hypy_utils is absent); its arithmetic
 is np.mean / np.cov (float64) and a pairwise (Chan) merge, restated below on in-memory arrays instead of .npy files.
+
+`calc_frechet_distance` / `score_inf` restate fadtk/fad.py:50-119, 303-350 with the same SciPy / NumPy calls.  PARITY
+UNPINNED for these two: fadtk/fad.py itself cannot be imported (hypy_utils, embedding-model loaders), and the reference's
+only FAD test (fadtk/test, samples_FAD_scores.csv) needs network models and a missing statistics blob.  What pins them
+here instead: closed forms (identical Gaussians -> 0, commuting covariances -> sum (sqrt(a) - sqrt(b))^2), checked in
+tests/test_oracle_vs_golden.py.
 """
 from __future__ import annotations
 

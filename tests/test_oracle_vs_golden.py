@@ -128,3 +128,44 @@ def test_steps_match_reference(golden_steps):
         assert rel_l2(o.pred_original_sample, golden_steps[key + "|x0"]) < 5e-6, key
         gl = float(golden_steps[key + "|loss"].ravel()[0])
         assert abs(float(o.loss.float().ravel()[0]) - gl) <= 1e-5 * max(1.0, abs(gl)), key
+
+
+# ------------------------------------------------------------------------------------------------ section 8(f) oracles
+def test_frechet_oracle_closed_forms():
+    """oracle.fad.calc_frechet_distance (restated fadtk/fad.py:50-119) against closed forms: identical Gaussians -> 0;
+    covariances sharing an eigenbasis -> |dmu|^2 + sum_i (sqrt(a_i) - sqrt(b_i))^2."""
+    from oracle import fad as ofad
+    rng = np.random.default_rng(0)
+    d = 24
+    q, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    a, b = rng.uniform(0.1, 3.0, d), rng.uniform(0.1, 3.0, d)
+    c1, c2 = (q * a) @ q.T, (q * b) @ q.T
+    mu1, mu2 = rng.standard_normal(d), rng.standard_normal(d)
+    want = np.sum((mu1 - mu2) ** 2) + np.sum((np.sqrt(a) - np.sqrt(b)) ** 2)
+    got = float(np.real(ofad.calc_frechet_distance(mu1, c1, mu2, c2)))
+    assert abs(got - want) < 1e-9 * want
+    assert abs(float(np.real(ofad.calc_frechet_distance(mu1, c1, mu1, c1)))) < 1e-9
+    np.random.seed(3)
+    emb = rng.standard_normal((900, d)) * np.sqrt(a)
+    score, slope, r2, pts = ofad.score_inf(mu1 * 0, c1, emb, steps=5, min_n=100)
+    assert [p[0] for p in pts] == [100, 300, 500, 700, 900] and np.isfinite([score, slope, r2]).all()
+    assert slope > 0  # the finite-sample bias of FAD shrinks like 1/n
+
+
+def test_metric_oracles_closed_forms():
+    """oracle.metrics: LSD of a clip with itself is 0, scaling a clip by c shifts every log-magnitude by log10(c);
+    MSE of constant offsets; nan_to_num sanitising as in lsd.py:23 / mse.py:14-15."""
+    from oracle import metrics as om
+    x = stubs.synth_clips(2, 8000).numpy()
+    assert om.lsd_score(x, x, 1024, 512) == 0.0
+    got = om.lsd_score(x, 10.0 * x, 1024, 512, eps=0.0)
+    assert abs(got - 1.0) < 1e-4
+    y = x.copy()
+    y[0, 5] = np.nan
+    y[1, 9] = np.inf
+    z = x.copy()
+    z[0, 5], z[1, 9] = 0.0, 1.0
+    assert om.lsd_score(x, y, 1024, 512) == om.lsd_score(x, z, 1024, 512)
+    assert abs(om.mse_score(x, x + 0.5) - 0.25) < 1e-6
+    assert abs(om.mse_score(x, x + 0.5, "sum") - 0.5) < 1e-6
+    assert om.mse_score(x, y) == om.mse_score(x, z)
