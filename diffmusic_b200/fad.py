@@ -87,7 +87,8 @@ def calculate_embd_statistics_online(arrays, group=None):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # Frechet distance and FAD-inf (fadtk/fad.py:50-119, 303-350)
-JACOBI_MAX_SWEEPS = 30
+JACOBI_MAX_SWEEPS = 40        # cap of the retry
+JACOBI_FIRST_SWEEPS = 16      # launches enqueued up front: sweeps * (d - 1) per solve, no-ops once converged
 JACOBI_TOL = 1e-14
 
 
@@ -95,9 +96,10 @@ def _as_dev_f64(a, device):
     return torch.as_tensor(a).to(device=device, dtype=torch.float64).contiguous()
 
 
-def frechet_distance_device(mu1, cov1, mu2, cov2):
+def frechet_distance_device(mu1, cov1, mu2, cov2, max_sweeps=JACOBI_FIRST_SWEEPS):
     """Device tensors in, (4,) float64 device tensor out: [d^2, tr sqrt(C1 C2), sweeps of the two Jacobi solves].
-    No host synchronisation (dm_frechet_distance)."""
+    No host synchronisation (dm_frechet_distance).  A solve that used all `max_sweeps` sweeps may not have converged:
+    callers that can read the result check out[2:4] and retry with JACOBI_MAX_SWEEPS (`_frechet_checked`)."""
     _lib.require_cuda(mu1, cov1, mu2, cov2)
     d = mu1.numel()
     if mu2.numel() != d:
@@ -109,8 +111,18 @@ def frechet_distance_device(mu1, cov1, mu2, cov2):
     work = torch.empty(int(_lib.load().dm_frechet_workspace_doubles(d)), device=mu1.device, dtype=torch.float64)
     out = torch.empty(4, device=mu1.device, dtype=torch.float64)
     _lib.call("dm_frechet_distance", mu1.data_ptr(), cov1.data_ptr(), mu2.data_ptr(), cov2.data_ptr(), d,
-              JACOBI_MAX_SWEEPS, JACOBI_TOL, work.data_ptr(), out.data_ptr(), _lib.stream())
+              int(max_sweeps), JACOBI_TOL, work.data_ptr(), out.data_ptr(), _lib.stream())
     return out
+
+
+def _frechet_checked(outs, args):
+    """outs: list of (4,) device results of frechet_distance_device(*args[i]) with JACOBI_FIRST_SWEEPS; one host read
+    for all of them, and a re-run with the full sweep budget for any solve that hit the cap."""
+    host = torch.stack(outs).cpu()
+    for i in range(len(outs)):
+        if max(float(host[i, 2]), float(host[i, 3])) >= JACOBI_FIRST_SWEEPS:
+            host[i] = frechet_distance_device(*args[i], max_sweeps=JACOBI_MAX_SWEEPS).cpu()
+    return host
 
 
 def calc_frechet_distance(mu1, cov1, mu2, cov2, eps=1e-6):
@@ -127,9 +139,8 @@ def calc_frechet_distance(mu1, cov1, mu2, cov2, eps=1e-6):
     if not torch.cuda.is_available():
         raise _lib.DiffMusicB200Error("dm_frechet_distance needs CUDA (no CPU fallback)")
     dev = torch.device("cuda", torch.cuda.current_device())
-    out = frechet_distance_device(_as_dev_f64(mu1, dev), _as_dev_f64(cov1, dev), _as_dev_f64(mu2, dev),
-                                  _as_dev_f64(cov2, dev))
-    return float(out[0].item())
+    args = (_as_dev_f64(mu1, dev), _as_dev_f64(cov1, dev), _as_dev_f64(mu2, dev), _as_dev_f64(cov2, dev))
+    return float(_frechet_checked([frechet_distance_device(*args)], [args])[0, 0])
 
 
 class FADInfResults(tuple):
@@ -159,15 +170,16 @@ def score_inf(mu_base, cov_base, embeds, steps=25, min_n=500):
     N, d = x.shape
     mu_b, cov_b = _as_dev_f64(np.atleast_1d(mu_base), dev), _as_dev_f64(np.atleast_2d(cov_base), dev)
     ns = [int(n) for n in np.linspace(min_n, N, steps)]
-    scores = []
+    outs, args = [], []
     for n in ns:
         indices = np.random.choice(N, size=n, replace=True)
         idx = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int64)).to(dev)
         sub = torch.empty((n, d), device=dev, dtype=torch.float16)
         _lib.call("dm_fad_gather_rows", x.data_ptr(), N, d, idx.data_ptr(), n, sub.data_ptr(), _lib.stream())
         mu, cov = EmbeddingMoments(d, device=dev).update(sub).finalize()
-        scores.append(frechet_distance_device(mu_b, cov_b, mu, cov)[0])
-    fad = torch.stack(scores).cpu().numpy()  # one synchronisation for the whole sweep
+        args.append((mu_b, cov_b, mu, cov))
+        outs.append(frechet_distance_device(*args[-1]))
+    fad = _frechet_checked(outs, args)[:, 0].numpy()  # one synchronisation for the whole sweep (+ rare retries)
     results = [[n, float(s)] for n, s in zip(ns, fad)]
     ys = np.array(results)
     xs = 1 / np.array(ns)

@@ -873,3 +873,24 @@ def test_16_bit_waveforms_are_consumed_directly(op_name, space, dt):
     assert torch.equal(loss16, loss32)
     assert torch.equal(g16, g32.to(dt))
     assert torch.all(dfull[:, L:] == 7.0)  # nothing written past L
+
+
+def test_graphed_step_in_fp16_equals_eager_fp16():
+    """the captured graph with 16-bit static latents (run.py:218 pipelines) replays the 16-bit kernel paths."""
+    B, dt = 2, torch.float16
+    vae, voc = stubs.StubVAE().to(DEV).to(dt), stubs.StubVocoder().to(DEV).to(dt)
+    x, e = stubs.synth_latents(B, 25)
+    x, e = x.to(DEV).to(dt), e.to(DEV).to(dt)
+    op = _ops()["super_resolution"]
+    sched = dm.get_scheduler("dps")(operator=op, **stubs.MUSICLDM_SCHED)
+    sched.set_timesteps(500)
+    meas = op.forward(stubs.synth_clips(1, L1, first=50).to(DEV))
+    kw = dict(eta=0.0, measurement=meas, vae=vae, vocoder=voc, original_waveform_length=L1, ip_guidance_rate=5e-4,
+              supervised_space="mel_spectrogram")
+    graphed = dm.GraphedGuidedStep(sched, tuple(x.shape), dtype=dt, **kw)
+    for t in (999, 501, 1):
+        a = sched.step(e, t, x, **kw)
+        b = graphed(e, t, x)
+        assert b.prev_sample.dtype == dt
+        assert torch.equal(a.prev_sample, b.prev_sample) and torch.equal(a.pred_original_sample, b.pred_original_sample)
+        assert torch.equal(a.loss, b.loss) and torch.equal(a.loss_per_clip, b.loss_per_clip)
