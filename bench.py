@@ -236,13 +236,18 @@ def main():
     dom_events = []
     orig_call = _lib.call
 
+    other_events = {}
+
     def timed_call(name, *a):
-        if name in ("dm_stft_guidance", "dm_stft_guidance_io") and timed_call.on:
+        if timed_call.on:
             s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             orig_call(name, *a)
             t.record()
-            dom_events.append((s, t))
+            if name in ("dm_stft_guidance", "dm_stft_guidance_io"):
+                dom_events.append((s, t))
+            else:
+                other_events.setdefault(name, []).append((s, t))
         else:
             orig_call(name, *a)
 
@@ -370,9 +375,13 @@ def main():
         e2e_ms = pipelined_region() if (graphed is not None and not args.serial_e2e) else e2e_serial_ms
         # the dominant kernel, timed live with CUDA events on its launching stream inside eager steps (a graph replay
         # has no per-kernel event hooks), L2 flushed before every step as above
+        # An eager step is host-bound (~0.9 ms of Python dispatch for ~0.2 ms of device work): with an empty queue every
+        # event bracket would also contain that kernel's launch latency.  ~1.2 ms of L2-flush fills are queued first,
+        # so the host runs ahead and the step's kernels execute back to back, as they do inside the replayed graph.
         timed_call.on = True
         for i in range(args.steps):
-            flush.fill_(float(i))
+            for j in range(24):
+                flush.fill_(float(i + j))
             one_step(args.warmup + i, False, eager=True)
         torch.cuda.synchronize()
         timed_call.on = False
@@ -400,6 +409,23 @@ def main():
                     "bytes_per_launch": bytes_launch, "ms_per_launch": dom, "launches_timed": len(dom_ms),
                     "peak_source": peak_src,
                     "note": "compute/shared-memory bound FFT kernel: algorithmic HBM bytes are the floor, see DESIGN.md"}
+        # the other kernels of ours inside the step, same live timing (eager steps, cold L2): algorithmic bytes per call
+        lat = 4 * x_h.numel()
+        Lw = L10 + 32  # stand-in vocoder output length
+        alg = {"dm_sched_x0_io": 4 * lat, "dm_sched_ddim_update_io": 3 * lat, "dm_sched_dps_update_io": 4 * lat,
+               "dm_sched_mpgd_update_io": 5 * lat, "dm_sched_dsg_update_io": 5 * lat,
+               "dm_sched_diffmusic_update_io": 5 * lat, "dm_resample_fwd_io": B * (4 * L10 + 4 * Ly),
+               "dm_resample_adjoint_io": B * (4 * (Ly + 1024) + 4 * L10),
+               "dm_fold_adjoint_io": B * (4 * (Ly + 1024) + 4 * L10),
+               "dm_rir_correlate": B * (4 * L10 + 4 * Ly), "dm_rir_adjoint": B * (4 * (Ly + 1024) + 4 * L10)}
+        others = []
+        for name, evs in sorted(other_events.items()):
+            ms = statistics.mean(s.elapsed_time(t) for s, t in evs)
+            row = {"call": name, "ms": ms, "calls_timed": len(evs)}
+            if name in alg and ms > 0:
+                row.update(bytes=alg[name], GBps=alg[name] / (ms * 1e-3) / 1e9, frac=alg[name] / (ms * 1e-3) / 1e9 / peak)
+            others.append(row)
+        roofline["other_calls"] = others
         line = {"metric": "guided denoising steps/s (10 s clips)", "value": value, "unit": "clip-steps/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
