@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(kEwThreads) fold_adjoint_kernel(const float* _
 // with 32-bit index arithmetic.
 constexpr int kRsChunk = 2048;  // outputs per CTA
 
-__global__ void __launch_bounds__(kEwThreads) resample_fwd_kernel(const float* __restrict__ x, long long x_bstride,
+__global__ void __launch_bounds__(kEwThreads) resample_fwd_kernel(const void* __restrict__ x, int x_io,
+                                                                  long long x_bstride,
                                                                   long long L, const float* __restrict__ kernel,
                                                                   int n_new, int taps, int orig, int width,
                                                                   float* __restrict__ y, long long Ly, int span) {
@@ -93,10 +94,10 @@ __global__ void __launch_bounds__(kEwThreads) resample_fwd_kernel(const float* _
     const long long j_lo = o0 / n_new;
     const long long x_lo = (long long)orig * j_lo - width;
     for (int i = threadIdx.x; i < n_new * taps; i += kEwThreads) kw[i] = __ldg(kernel + i);
-    const float* xb = x + (long long)b * x_bstride;
+    const void* xb = wave_row(x, x_io, (long long)b * x_bstride);
     for (int i = threadIdx.x; i < span; i += kEwThreads) {
         long long g = x_lo + i;
-        xs[i] = (g >= 0 && g < L) ? xb[g] : 0.f;
+        xs[i] = (g >= 0 && g < L) ? ld_wave(xb, x_io, g) : 0.f;
     }
     __syncthreads();
     const int ph0 = (int)(o0 - j_lo * n_new);
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(kEwThreads) resample_fwd_kernel(const float* _
 
 __global__ void __launch_bounds__(kEwThreads) resample_adjoint_kernel(
     const float* __restrict__ ybar, int pad, long long Ly, const float* __restrict__ partial, int ntiles,
-    const float* __restrict__ kernel, int n_new, int taps, int orig, int width, float* __restrict__ dwav,
+    const float* __restrict__ kernel, int n_new, int taps, int orig, int width, void* __restrict__ dwav, int dw_io,
     long long dwav_bstride, long long L, float* __restrict__ loss, int span) {
     extern __shared__ float sm[];
     __shared__ float scratch[2];
@@ -150,13 +151,13 @@ __global__ void __launch_bounds__(kEwThreads) resample_adjoint_kernel(
             const float* yv = ys + j * n_new;
             for (int ph = 0; ph < n_new; ++ph) acc = fmaf(yv[ph], kw[ph * taps + k], acc);
         }
-        dwav[(long long)b * dwav_bstride + i0 + t] = acc;
+        st_wave(dwav, dw_io, (long long)b * dwav_bstride + i0 + t, acc);
     }
 }
 
 // ---- integer decimation (n_new == 1: scale 2 and 10 of run.py / operator.py): polyphase, 4 outputs per thread ----
 template <int ORIG, int TAPS>
-__global__ void __launch_bounds__(kEwThreads) resample_fwd_poly_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(kEwThreads) resample_fwd_poly_kernel(const void* __restrict__ x, int x_io,
                                                                        long long x_bstride, long long L,
                                                                        const float* __restrict__ kernel, int taps,
                                                                        int orig, int width, float* __restrict__ y,
@@ -170,11 +171,11 @@ __global__ void __launch_bounds__(kEwThreads) resample_fwd_poly_kernel(const flo
     const int no = (int)min((long long)kRsChunk, Ly - o0);
     const long long x_lo = (long long)orig * o0 - width;
     for (int i = threadIdx.x; i < taps; i += kEwThreads) kw[i] = __ldg(kernel + i);
-    const float* xb = x + (long long)b * x_bstride;
+    const void* xb = wave_row(x, x_io, (long long)b * x_bstride);
     // valid staged range in 32-bit block-relative indices: 0 <= x_lo + i < L
     const int i_lo = (int)max(0LL, -x_lo), i_hi = (int)min((long long)span, L - x_lo);
-    const float* xrel = xb + x_lo;
-    for (int i = threadIdx.x; i < span; i += kEwThreads) xs[fir_pad(i)] = (i >= i_lo && i < i_hi) ? xrel[i] : 0.f;
+    for (int i = threadIdx.x; i < span; i += kEwThreads)
+        xs[fir_pad(i)] = (i >= i_lo && i < i_hi) ? ld_wave(xb, x_io, x_lo + i) : 0.f;
     __syncthreads();
     for (int j0 = threadIdx.x * kFirR; j0 < no; j0 += kEwThreads * kFirR) {
         float acc[kFirR];
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kEwThreads) resample_fwd_poly_kernel(const flo
 template <int ORIG, int TAPS>
 __global__ void __launch_bounds__(kEwThreads) resample_adjoint_poly_kernel(
     const float* __restrict__ ybar, int pad, long long Ly, const float* __restrict__ partial, int ntiles,
-    const float* __restrict__ kernel, int taps, int orig, int width, float* __restrict__ dwav,
+    const float* __restrict__ kernel, int taps, int orig, int width, void* __restrict__ dwav, int dw_io,
     long long dwav_bstride, long long L, float* __restrict__ loss, int span, int chunk) {
     extern __shared__ float sm[];
     __shared__ float scratch[2];
@@ -223,7 +224,8 @@ __global__ void __launch_bounds__(kEwThreads) resample_adjoint_poly_kernel(
         for (int c = 0; c < kFirR; ++c) outs[t0 + orig * c] = acc[c];
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < ni; t += kEwThreads) dwav[(long long)b * dwav_bstride + i0 + t] = outs[t];
+    for (int t = threadIdx.x; t < ni; t += kEwThreads)
+        st_wave(dwav, dw_io, (long long)b * dwav_bstride + i0 + t, outs[t]);
 }
 
 // ---- scale 2 (orig 2, 28 taps, width 13): register-window kernels, no shared-memory staging ----
@@ -444,69 +446,42 @@ static bool rs2_filter(int n_new, int orig, int taps, int width, const float* ke
            (reinterpret_cast<uintptr_t>(kernel) & 15) == 0;
 }
 
-// 16-bit waveforms: only the reference's scale-2 filter (register-window kernels) reads / writes them directly;
-// other ratios return DM_ERR_UNSUPPORTED and the caller converts to fp32 first.
-extern "C" int dm_resample_fwd_io(const void* x, int x_dtype, long long x_bstride, long long L, int B,
-                                  const float* kernel, int n_new, int taps, int orig, int width, float* y, long long Ly,
-                                  dm_stream_t stream) {
-    DM_REQUIRE(x && kernel && y && L > 0 && B > 0 && Ly > 0 && io_dtype_ok(x_dtype));
-    if (x_dtype == DM_IO_F32)
-        return dm_resample_fwd(static_cast<const float*>(x), x_bstride, L, B, kernel, n_new, taps, orig, width, y, Ly,
-                               stream);
-    if (!(rs2_filter(n_new, orig, taps, width, kernel) && x_bstride % 8 == 0 && Ly % 4 == 0 &&
-          (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0))
-        return fail(DM_ERR_UNSUPPORTED, "%s: 16-bit input needs the scale-2 filter and 16-byte aligned rows", __func__);
-    if (x_dtype == DM_IO_F16) launch_rs2_fwd<DM_IO_F16>(x, x_bstride, L, B, kernel, y, Ly, as_stream(stream));
-    else launch_rs2_fwd<DM_IO_BF16>(x, x_bstride, L, B, kernel, y, Ly, as_stream(stream));
-    DM_LAUNCHED();
-    return DM_OK;
+// ---- resampling entry points: one typed core per direction (the waveform side is fp32 / fp16 / bf16) ----
+template <int IO>
+static bool rs2_fwd_ok(const void* x, long long x_bstride, const float* y, long long Ly) {
+    const long long q = IO == DM_IO_F32 ? 4 : 8;  // row stride in elements that keeps rows 16-byte aligned
+    return x_bstride % q == 0 && Ly % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(y) & 15) == 0;
 }
-extern "C" int dm_resample_adjoint_io(const float* ybar, int pad, long long Ly, int B, const float* partial,
-                                      int ntiles, const float* kernel, int n_new, int taps, int orig, int width,
-                                      void* dwav, int dwav_dtype, long long dwav_bstride, long long L, float* loss,
-                                      dm_stream_t stream) {
-    DM_REQUIRE(ybar && partial && kernel && dwav && L > 0 && B > 0 && Ly > 0 && ntiles > 0 && io_dtype_ok(dwav_dtype));
-    if (dwav_dtype == DM_IO_F32)
-        return dm_resample_adjoint(ybar, pad, Ly, B, partial, ntiles, kernel, n_new, taps, orig, width,
-                                   static_cast<float*>(dwav), dwav_bstride, L, loss, stream);
-    DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 512));
-    if (!(rs2_filter(n_new, orig, taps, width, kernel) && dwav_bstride % 8 == 0 && (Ly + 2 * pad) % 4 == 0 &&
-          (reinterpret_cast<uintptr_t>(ybar) & 15) == 0 && (reinterpret_cast<uintptr_t>(dwav) & 15) == 0))
-        return fail(DM_ERR_UNSUPPORTED, "%s: 16-bit output needs the scale-2 filter and 16-byte aligned rows", __func__);
-    if (dwav_dtype == DM_IO_F16)
-        launch_rs2_adj<DM_IO_F16>(ybar, pad, Ly, B, partial, ntiles, kernel, dwav, dwav_bstride, L, loss,
-                                  as_stream(stream));
-    else
-        launch_rs2_adj<DM_IO_BF16>(ybar, pad, Ly, B, partial, ntiles, kernel, dwav, dwav_bstride, L, loss,
-                                   as_stream(stream));
-    DM_LAUNCHED();
-    return DM_OK;
-}
-
-extern "C" int dm_resample_fwd(const float* x, long long x_bstride, long long L, int B, const float* kernel,
-                               int n_new, int taps, int orig, int width, float* y, long long Ly,
-                               dm_stream_t stream) {
-    DM_REQUIRE(x && kernel && y && L > 0 && B > 0 && Ly > 0);
+static int resample_fwd_core(const void* x, int x_io, long long x_bstride, long long L, int B, const float* kernel,
+                             int n_new, int taps, int orig, int width, float* y, long long Ly, cudaStream_t st) {
+    DM_REQUIRE(x && kernel && y && L > 0 && B > 0 && Ly > 0 && io_dtype_ok(x_io));
     DM_REQUIRE(n_new >= 1 && taps >= 1 && orig >= 1 && width >= 0);
-    if (n_new == 1) {  // integer decimation: polyphase kernel
+    if (rs2_filter(n_new, orig, taps, width, kernel)) {  // scale 2: register-window kernel
+        if (x_io == DM_IO_F32 && rs2_fwd_ok<DM_IO_F32>(x, x_bstride, y, Ly)) {
+            launch_rs2_fwd<DM_IO_F32>(x, x_bstride, L, B, kernel, y, Ly, st);
+            DM_LAUNCHED();
+            return DM_OK;
+        }
+        if (x_io != DM_IO_F32 && rs2_fwd_ok<DM_IO_F16>(x, x_bstride, y, Ly)) {
+            if (x_io == DM_IO_F16) launch_rs2_fwd<DM_IO_F16>(x, x_bstride, L, B, kernel, y, Ly, st);
+            else launch_rs2_fwd<DM_IO_BF16>(x, x_bstride, L, B, kernel, y, Ly, st);
+            DM_LAUNCHED();
+            return DM_OK;
+        }
+    }
+    if (n_new == 1) {  // integer decimation: polyphase kernel out of shared memory
         const int span1 = orig * (kRsChunk + kFirR) + taps;
         const size_t smem1 = ((size_t)taps + fir_padded_len(span1) + kRsChunk) * sizeof(float);
         if (smem1 <= 200 * 1024) {
-            if (orig == 2 && taps == kFir2Taps && width == kFir2Width && x_bstride % 4 == 0 && Ly % 4 == 0 &&
-                (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-                (reinterpret_cast<uintptr_t>(kernel) & 15) == 0) {
-                launch_rs2_fwd<DM_IO_F32>(x, x_bstride, L, B, kernel, y, Ly, as_stream(stream));
-                DM_LAUNCHED();
-                return DM_OK;
-            }
             const dim3 grid((unsigned)((Ly + kRsChunk - 1) / kRsChunk), B);
-#define DM_RS_FWD(O, T)                                                                                          \
-    do {                                                                                                         \
-        DM_SMEM_ONCE((resample_fwd_poly_kernel<O, T>), smem1);                                                   \
-        resample_fwd_poly_kernel<O, T><<<grid, kEwThreads, smem1, as_stream(stream)>>>(x, x_bstride, L, kernel, taps, \
-                                                                                       orig, width, y, Ly, span1);   \
+#define DM_RS_FWD(O, T)                                                                                     \
+    do {                                                                                                    \
+        DM_SMEM_ONCE((resample_fwd_poly_kernel<O, T>), smem1);                                              \
+        resample_fwd_poly_kernel<O, T><<<grid, kEwThreads, smem1, st>>>(x, x_io, x_bstride, L, kernel, taps, orig, \
+                                                                        width, y, Ly, span1);               \
     } while (0)
-            if (orig == 2 && taps == 28) DM_RS_FWD(2, 28);          // scale 2 (run.py:188)
+            if (orig == 2 && taps == 28) DM_RS_FWD(2, 28);          // scale 2 (run.py:188), unaligned rows
             else if (orig == 10 && taps == 132) DM_RS_FWD(10, 132);  // scale 10 (operator.py:179 default)
             else DM_RS_FWD(0, 0);
 #undef DM_RS_FWD
@@ -521,22 +496,26 @@ extern "C" int dm_resample_fwd(const float* x, long long x_bstride, long long L,
                                        __func__, n_new, orig, smem);
     DM_SMEM_ONCE(resample_fwd_kernel, smem);
     const int nblk = (int)((Ly + kRsChunk - 1) / kRsChunk);
-    resample_fwd_kernel<<<dim3(nblk, B), kEwThreads, smem, as_stream(stream)>>>(x, x_bstride, L, kernel, n_new, taps,
-                                                                                orig, width, y, Ly, span);
+    resample_fwd_kernel<<<dim3(nblk, B), kEwThreads, smem, st>>>(x, x_io, x_bstride, L, kernel, n_new, taps, orig,
+                                                                 width, y, Ly, span);
     DM_LAUNCHED();
     return DM_OK;
 }
 
-extern "C" int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
-                                   const float* kernel, int n_new, int taps, int orig, int width, float* dwav,
-                                   long long dwav_bstride, long long L, float* loss, dm_stream_t stream) {
-    DM_REQUIRE(ybar && partial && kernel && dwav && L > 0 && B > 0 && Ly > 0 && ntiles > 0);
+static int resample_adjoint_core(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
+                                 const float* kernel, int n_new, int taps, int orig, int width, void* dwav, int dw_io,
+                                 long long dwav_bstride, long long L, float* loss, cudaStream_t st) {
+    DM_REQUIRE(ybar && partial && kernel && dwav && L > 0 && B > 0 && Ly > 0 && ntiles > 0 && io_dtype_ok(dw_io));
     DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 512));
-    if (n_new == 1 && orig == 2 && taps == kFir2Taps && width == kFir2Width && dwav_bstride % 4 == 0 &&
+    if (rs2_filter(n_new, orig, taps, width, kernel) && dwav_bstride % (dw_io == DM_IO_F32 ? 4 : 8) == 0 &&
         (Ly + 2 * pad) % 4 == 0 && (reinterpret_cast<uintptr_t>(ybar) & 15) == 0 &&
-        (reinterpret_cast<uintptr_t>(dwav) & 15) == 0 && (reinterpret_cast<uintptr_t>(kernel) & 15) == 0) {
-        launch_rs2_adj<DM_IO_F32>(ybar, pad, Ly, B, partial, ntiles, kernel, dwav, dwav_bstride, L, loss,
-                                  as_stream(stream));
+        (reinterpret_cast<uintptr_t>(dwav) & 15) == 0) {
+        if (dw_io == DM_IO_F32)
+            launch_rs2_adj<DM_IO_F32>(ybar, pad, Ly, B, partial, ntiles, kernel, dwav, dwav_bstride, L, loss, st);
+        else if (dw_io == DM_IO_F16)
+            launch_rs2_adj<DM_IO_F16>(ybar, pad, Ly, B, partial, ntiles, kernel, dwav, dwav_bstride, L, loss, st);
+        else
+            launch_rs2_adj<DM_IO_BF16>(ybar, pad, Ly, B, partial, ntiles, kernel, dwav, dwav_bstride, L, loss, st);
         DM_LAUNCHED();
         return DM_OK;
     }
@@ -546,11 +525,12 @@ extern "C" int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int
         const int span1 = (taps + chunk) / orig + kFirR + 2;
         const size_t smem1 = ((size_t)taps + 1 + span1 + chunk) * sizeof(float);
         const dim3 grid((unsigned)((L + chunk - 1) / chunk), B);
-#define DM_RS_ADJ(O, T)                                                                                           \
-    do {                                                                                                          \
-        DM_SMEM_ONCE((resample_adjoint_poly_kernel<O, T>), smem1);                                                \
-        resample_adjoint_poly_kernel<O, T><<<grid, kEwThreads, smem1, as_stream(stream)>>>(                       \
-            ybar, pad, Ly, partial, ntiles, kernel, taps, orig, width, dwav, dwav_bstride, L, loss, span1, chunk); \
+#define DM_RS_ADJ(O, T)                                                                                         \
+    do {                                                                                                        \
+        DM_SMEM_ONCE((resample_adjoint_poly_kernel<O, T>), smem1);                                              \
+        resample_adjoint_poly_kernel<O, T><<<grid, kEwThreads, smem1, st>>>(ybar, pad, Ly, partial, ntiles, kernel, \
+                                                                            taps, orig, width, dwav, dw_io,     \
+                                                                            dwav_bstride, L, loss, span1, chunk); \
     } while (0)
         if (orig == 2 && taps == 28) DM_RS_ADJ(2, 28);
         else if (orig == 10 && taps == 132) DM_RS_ADJ(10, 132);
@@ -566,10 +546,36 @@ extern "C" int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int
                                        __func__, n_new, orig, smem);
     DM_SMEM_ONCE(resample_adjoint_kernel, smem);
     const int nblk = (int)((L + kRsChunk - 1) / kRsChunk);
-    resample_adjoint_kernel<<<dim3(nblk, B), kEwThreads, smem, as_stream(stream)>>>(
-        ybar, pad, Ly, partial, ntiles, kernel, n_new, taps, orig, width, dwav, dwav_bstride, L, loss, span);
+    resample_adjoint_kernel<<<dim3(nblk, B), kEwThreads, smem, st>>>(ybar, pad, Ly, partial, ntiles, kernel, n_new, taps,
+                                                                     orig, width, dwav, dw_io, dwav_bstride, L, loss,
+                                                                     span);
     DM_LAUNCHED();
     return DM_OK;
+}
+
+extern "C" int dm_resample_fwd_io(const void* x, int x_dtype, long long x_bstride, long long L, int B,
+                                  const float* kernel, int n_new, int taps, int orig, int width, float* y, long long Ly,
+                                  dm_stream_t stream) {
+    return resample_fwd_core(x, x_dtype, x_bstride, L, B, kernel, n_new, taps, orig, width, y, Ly, as_stream(stream));
+}
+extern "C" int dm_resample_fwd(const float* x, long long x_bstride, long long L, int B, const float* kernel,
+                               int n_new, int taps, int orig, int width, float* y, long long Ly,
+                               dm_stream_t stream) {
+    return resample_fwd_core(x, DM_IO_F32, x_bstride, L, B, kernel, n_new, taps, orig, width, y, Ly,
+                             as_stream(stream));
+}
+extern "C" int dm_resample_adjoint_io(const float* ybar, int pad, long long Ly, int B, const float* partial,
+                                      int ntiles, const float* kernel, int n_new, int taps, int orig, int width,
+                                      void* dwav, int dwav_dtype, long long dwav_bstride, long long L, float* loss,
+                                      dm_stream_t stream) {
+    return resample_adjoint_core(ybar, pad, Ly, B, partial, ntiles, kernel, n_new, taps, orig, width, dwav, dwav_dtype,
+                                 dwav_bstride, L, loss, as_stream(stream));
+}
+extern "C" int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
+                                   const float* kernel, int n_new, int taps, int orig, int width, float* dwav,
+                                   long long dwav_bstride, long long L, float* loss, dm_stream_t stream) {
+    return resample_adjoint_core(ybar, pad, Ly, B, partial, ntiles, kernel, n_new, taps, orig, width, dwav, DM_IO_F32,
+                                 dwav_bstride, L, loss, as_stream(stream));
 }
 
 extern "C" int dm_mask_apply(const float* x, long long x_bstride, long long L, int B, const float* mask, float* y,

@@ -84,12 +84,20 @@ struct RirLoad {
 };
 // Output store of the last inverse pass: keeps samples shift <= s < shift + valid, scaled by 1/8192.
 struct RirStore {
-    float* out;        // already offset to the first output sample of this block
+    float* out;        // already offset to the first output sample of this block (a 16-bit pointer when io != 0)
     int shift, valid;  // valid is clipped to the end of the signal by the caller
     float scale;
+    int io = 0;        // DM_IO_* of the destination (the adjoint writes dLoss/dwav in the waveform's dtype)
     DM_HD void put(int s, float v) const {
         int m = s - shift;
-        if (m >= 0 && m < valid) out[m] = v * scale;
+        if (m < 0 || m >= valid) return;
+#if defined(__CUDA_ARCH__)
+        if (io != 0) {
+            st_wave(out, io, m, v * scale);
+            return;
+        }
+#endif
+        out[m] = v * scale;
     }
     DM_HD void operator()(int i, cf c) const {
         put(2 * i, c.x);

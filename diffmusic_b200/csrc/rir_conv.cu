@@ -13,12 +13,13 @@ __device__ __forceinline__ float fold_at_rir(const float* __restrict__ yp, long 
     return v;
 }
 
-struct SrcPlain {
-    const float* x;
+struct SrcPlain {  // waveform-typed input (fp32 / fp16 / bf16)
+    const void* x;
+    int io;
     long long off, L;
     __device__ __forceinline__ float operator()(int n) const {
         long long i = off + n;
-        return (i >= 0 && i < L) ? __ldg(x + i) : 0.f;
+        return (i >= 0 && i < L) ? ld_wave(x, io, i) : 0.f;
     }
 };
 struct SrcFolded {  // scaled, reflect-folded cotangent
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(kRirThreads) rir_spectrum_kernel(const float* 
                                                                    cf* __restrict__ spec) {
     extern __shared__ __align__(16) float smem[];
     RirSmem s = carve(smem);
-    SrcPlain src{ir, 0, K};
+    SrcPlain src{ir, DM_IO_F32, 0, K};
     RirStore st{nullptr, 0, 0, 0.f};
 #pragma unroll
     for (int ph = 0; ph < 4; ++ph) {
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(kRirThreads) rir_spectrum_kernel(const float* 
     rir_unpack_spectrum(threadIdx.x, SwzLoad{s.b_re, s.b_im}, w8192, spec);
 }
 
-__global__ void __launch_bounds__(kRirThreads, 2) rir_correlate_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(kRirThreads, 2) rir_correlate_kernel(const void* __restrict__ x, int x_io,
                                                                     long long x_bstride, RirGeom g,
                                                                     const cf* __restrict__ spec,
                                                                     const cf* __restrict__ tw,
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(kRirThreads, 2) rir_correlate_kernel(const flo
     RirSmem s = carve(smem);
     const int b = blockIdx.y;
     const long long i0 = (long long)blockIdx.x * g.valid;
-    SrcPlain src{x + (long long)b * x_bstride, i0 - g.pad, g.L};
+    SrcPlain src{wave_row(x, x_io, (long long)b * x_bstride), x_io, i0 - g.pad, g.L};
     RirStore st{y + (long long)b * g.nout + i0, 0, (int)min((long long)g.valid, g.nout - i0), 1.0f / kRirN};
 #pragma unroll
     for (int ph = 0; ph < kRirPhases; ++ph) {
@@ -82,7 +83,8 @@ __global__ void __launch_bounds__(kRirThreads, 2) rir_adjoint_kernel(const float
                                                                   int ntiles, const cf* __restrict__ spec,
                                                                   const cf* __restrict__ tw,
                                                                   const cf* __restrict__ w8192,
-                                                                  float* __restrict__ dwav, long long dwav_bstride,
+                                                                  void* __restrict__ dwav, int dw_io,
+                                                                  long long dwav_bstride,
                                                                   float* __restrict__ loss) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float scratch[2];
@@ -92,8 +94,8 @@ __global__ void __launch_bounds__(kRirThreads, 2) rir_adjoint_kernel(const float
     if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[b] = l;
     const long long j0 = (long long)blockIdx.x * g.valid;
     SrcFolded src{ybar + (long long)b * (g.nout + 2 * pad), j0 + g.pad - (g.K - 1), g.nout, pad, inv_loss(l)};
-    RirStore st{dwav + (long long)b * dwav_bstride + j0, g.K - 1, (int)min((long long)g.valid, g.L - j0),
-                1.0f / kRirN};
+    RirStore st{static_cast<float*>(wave_row(dwav, dw_io, (long long)b * dwav_bstride + j0)), g.K - 1,
+                (int)min((long long)g.valid, g.L - j0), 1.0f / kRirN, dw_io};
 #pragma unroll
     for (int ph = 0; ph < kRirPhases; ++ph) {
         rir_block_phase<false>(ph, threadIdx.x, tw, w8192, spec, s, src, st);
@@ -121,14 +123,19 @@ extern "C" int dm_rir_spectrum(const float* ir, int K, const float* tw4096, cons
 extern "C" int dm_rir_correlate(const float* x, long long x_bstride, long long L, int B, const float* spec, int K,
                                 const float* tw4096, const float* w8192, float* y, long long Ly,
                                 dm_stream_t stream) {
-    DM_REQUIRE(x && spec && tw4096 && w8192 && y && L > 0 && B > 0);
+    return dm_rir_correlate_io(x, DM_IO_F32, x_bstride, L, B, spec, K, tw4096, w8192, y, Ly, stream);
+}
+extern "C" int dm_rir_correlate_io(const void* x, int x_dtype, long long x_bstride, long long L, int B,
+                                   const float* spec, int K, const float* tw4096, const float* w8192, float* y,
+                                   long long Ly, dm_stream_t stream) {
+    DM_REQUIRE(x && spec && tw4096 && w8192 && y && L > 0 && B > 0 && io_dtype_ok(x_dtype));
     DM_REQUIRE(K >= 1 && K <= DM_RIR_MAX_TAPS);
     RirGeom g = rir_geom(L, K);
     DM_REQUIRE(Ly == g.nout);
     const int nblk = (int)((g.nout + g.valid - 1) / g.valid);
     DM_SMEM_ONCE(rir_correlate_kernel, kRirSmemBytes);
     rir_correlate_kernel<<<dim3(nblk, B), kRirThreads, kRirSmemBytes, as_stream(stream)>>>(
-        x, x_bstride, g, reinterpret_cast<const cf*>(spec), reinterpret_cast<const cf*>(tw4096),
+        x, x_dtype, x_bstride, g, reinterpret_cast<const cf*>(spec), reinterpret_cast<const cf*>(tw4096),
         reinterpret_cast<const cf*>(w8192), y);
     DM_LAUNCHED();
     return DM_OK;
@@ -137,7 +144,14 @@ extern "C" int dm_rir_correlate(const float* x, long long x_bstride, long long L
 extern "C" int dm_rir_adjoint(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
                               const float* spec, int K, const float* tw4096, const float* w8192, float* dwav,
                               long long dwav_bstride, long long L, float* loss, dm_stream_t stream) {
+    return dm_rir_adjoint_io(ybar, pad, Ly, B, partial, ntiles, spec, K, tw4096, w8192, dwav, DM_IO_F32, dwav_bstride, L,
+                             loss, stream);
+}
+extern "C" int dm_rir_adjoint_io(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
+                                 const float* spec, int K, const float* tw4096, const float* w8192, void* dwav,
+                                 int dwav_dtype, long long dwav_bstride, long long L, float* loss, dm_stream_t stream) {
     DM_REQUIRE(ybar && partial && spec && tw4096 && w8192 && dwav && L > 0 && B > 0 && ntiles > 0);
+    DM_REQUIRE(io_dtype_ok(dwav_dtype));
     DM_REQUIRE(K >= 1 && K <= DM_RIR_MAX_TAPS);
     RirGeom g = rir_geom(L, K);
     DM_REQUIRE(Ly == g.nout);
@@ -146,7 +160,7 @@ extern "C" int dm_rir_adjoint(const float* ybar, int pad, long long Ly, int B, c
     DM_SMEM_ONCE(rir_adjoint_kernel, kRirSmemBytes);
     rir_adjoint_kernel<<<dim3(nblk, B), kRirThreads, kRirSmemBytes, as_stream(stream)>>>(
         ybar, pad, g, partial, ntiles, reinterpret_cast<const cf*>(spec), reinterpret_cast<const cf*>(tw4096),
-        reinterpret_cast<const cf*>(w8192), dwav, dwav_bstride, loss);
+        reinterpret_cast<const cf*>(w8192), dwav, dwav_dtype, dwav_bstride, loss);
     DM_LAUNCHED();
     return DM_OK;
 }

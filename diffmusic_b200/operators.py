@@ -451,12 +451,7 @@ class SuperResolutionOperator(BaseOperator):
     def transform(self, audio):
         return self._mel_db(audio)
 
-    def wave16_ok(self, wav):
-        # the register-window kernels of the reference's scale-2 filter move 16-bit rows with 128-bit accesses
-        return (wav.dtype in (torch.float16, torch.bfloat16) and wav.dim() == 2 and wav.stride(1) == 1
-                and self._sigma() == 0.0 and self.kernel is not None
-                and (self.orig, self.new, self.width, self.kernel.shape[-1]) == (2, 1, 13, 28)
-                and wav.stride(0) % 8 == 0 and wav.data_ptr() % 16 == 0 and wav.shape[1] % 8 == 0)
+    wave16 = True  # scale 2 with 16-byte aligned rows: register-window kernels; otherwise the staged kernels convert
 
     def _kernel_on(self, device):
         cache = self.__dict__.setdefault("_k_cache", {})
@@ -506,6 +501,8 @@ class MusicDereverberationOperator(BaseOperator):
     """operator.py:208-250: A(x) = conv1d(x, ir, padding=K//2) with a random impulse response REDRAWN ON EVERY forward
     call from the global CPU generator (reference quirk kept: operator.py:246).  Evaluated by overlap-save FFT."""
 
+    wave16 = True
+
     def __init__(self, ir_length=800, decay_factor=0.85, noiser=None):
         if ir_length > _RIR_MAX_TAPS:
             raise NotImplementedError(f"ir_length {ir_length} > {_RIR_MAX_TAPS} (one 8192-point FFT block)")
@@ -546,8 +543,8 @@ class MusicDereverberationOperator(BaseOperator):
         tw, w = self._rir_tables(x.device)
         Ly = L + 2 * (K // 2) - K + 1
         y = torch.empty((B, Ly), device=x.device, dtype=torch.float32)
-        _lib.call("dm_rir_correlate", x.data_ptr(), x.stride(0), L, B, spec.data_ptr(), K, tw.data_ptr(),
-                  w.data_ptr(), y.data_ptr(), Ly, _lib.stream())
+        _lib.call("dm_rir_correlate_io", x.data_ptr(), _lib.IO_DTYPES[x.dtype], x.stride(0), L, B, spec.data_ptr(), K,
+                  tw.data_ptr(), w.data_ptr(), y.data_ptr(), Ly, _lib.stream())
         return y
 
     def forward(self, data, ir=None, **kwargs):
@@ -578,9 +575,10 @@ class MusicDereverberationOperator(BaseOperator):
             return self._fold_adjoint(None, pad, Ly, B, partial, nt, None, False)
         tw, w = self._rir_tables(wav.device)
         loss = torch.empty((B,), device=wav.device, dtype=torch.float32)
-        dwav = _grad_buffer(dwav, B, L, wav.device)
-        _lib.call("dm_rir_adjoint", ybar.data_ptr(), pad, Ly, B, partial.data_ptr(), nt, spec.data_ptr(), K,
-                  tw.data_ptr(), w.data_ptr(), dwav.data_ptr(), dwav.stride(0), L, loss.data_ptr(), _lib.stream())
+        dwav = _grad_buffer(dwav, B, L, wav.device, wav.dtype)
+        _lib.call("dm_rir_adjoint_io", ybar.data_ptr(), pad, Ly, B, partial.data_ptr(), nt, spec.data_ptr(), K,
+                  tw.data_ptr(), w.data_ptr(), dwav.data_ptr(), _lib.IO_DTYPES[wav.dtype], dwav.stride(0), L,
+                  loss.data_ptr(), _lib.stream())
         return loss, dwav
 
 

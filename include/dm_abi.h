@@ -241,12 +241,16 @@ int dm_residual_wav_io(const void* y, int y_dtype, long long y_bstride, long lon
                        const float* meas, long long meas_bstride, float* ybar, float* partial, dm_stream_t stream);
 int dm_fold_adjoint_io(const float* ybar, int pad, long long Ly, int B, const float* mask, const float* partial,
                        int ntiles, void* dwav, int dwav_dtype, long long dwav_bstride, float* loss, dm_stream_t stream);
-/* 16-bit types: the reference's scale-2 filter only (orig 2, 28 taps), else DM_ERR_UNSUPPORTED */
 int dm_resample_fwd_io(const void* x, int x_dtype, long long x_bstride, long long L, int B, const float* kernel,
                        int n_new, int taps, int orig, int width, float* y, long long Ly, dm_stream_t stream);
 int dm_resample_adjoint_io(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
                            const float* kernel, int n_new, int taps, int orig, int width, void* dwav, int dwav_dtype,
                            long long dwav_bstride, long long L, float* loss, dm_stream_t stream);
+int dm_rir_correlate_io(const void* x, int x_dtype, long long x_bstride, long long L, int B, const float* spec, int K,
+                        const float* tw4096, const float* w8192, float* y, long long Ly, dm_stream_t stream);
+int dm_rir_adjoint_io(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
+                      const float* spec, int K, const float* tw4096, const float* w8192, void* dwav, int dwav_dtype,
+                      long long dwav_bstride, long long L, float* loss, dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Frechet distance and the FAD-inf bootstrap (fadtk/fad.py:50-119 `calc_frechet_distance`, :303-350 `score_inf`).

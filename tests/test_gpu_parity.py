@@ -853,21 +853,25 @@ def test_guided_steps_in_16_bit_pipelines(sched_name, op_name, eta, dt, tol):
 
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("op_name", ["identity", "inpainting", "super_resolution", "phase_retrieval"])
+@pytest.mark.parametrize("op_name", ["identity", "inpainting", "super_resolution", "super_resolution_x10",
+                                     "phase_retrieval", "dereverberation"])
 @pytest.mark.parametrize("space", ["mel_spectrogram", "wav_form"])
 def test_16_bit_waveforms_are_consumed_directly(op_name, space, dt):
     """fused loss + VJP on a 16-bit waveform == the fp32 chain on the up-cast waveform, the gradient rounded once to the
     waveform dtype; also for a row-strided view and a preallocated strided gradient buffer (what the schedulers pass)."""
     B, L = 3, L1
-    ops = dict(_ops(), identity=dm.IdentityOperator(16000))
+    ops = dict(_ops(), identity=dm.IdentityOperator(16000),
+               super_resolution_x10=dm.SuperResolutionOperator(sample_rate=16000, scale=10, noiser=_noiser()))
     op = ops[op_name]
     full = torch.zeros(B, L + 32, device=DEV, dtype=dt)
     full[:, :L] = stubs.synth_clips(B, L).to(DEV).to(dt)
     wav = full[:, :L]
     assert op.wave16_ok(wav)
     meas = op.forward(stubs.synth_clips(1, L, first=50).to(DEV))
+    torch.manual_seed(5)  # dereverberation draws its impulse response inside the fused chain
     loss32, g32 = op.fused_loss_and_grad(wav.float(), meas, space)
     dfull = torch.full_like(full, 7.0)
+    torch.manual_seed(5)
     loss16, g16 = op.fused_loss_and_grad(wav, meas, space, dwav=dfull[:, :L])
     assert g16.dtype == dt and g16.data_ptr() == dfull.data_ptr()
     assert torch.equal(loss16, loss32)
