@@ -186,3 +186,36 @@ def score_inf(mu_base, cov_base, embeds, steps=25, min_n=500):
     slope, intercept = np.polyfit(xs, ys[:, 1], 1)
     r2 = 1 - np.sum((ys[:, 1] - (slope * xs + intercept)) ** 2) / np.sum((ys[:, 1] - np.mean(ys[:, 1])) ** 2)
     return FADInfResults(score=intercept, slope=slope, r2=r2, points=results)
+
+
+def patch_fadtk(fad_module=None, utils_module=None):
+    """Point an imported `fadtk` at the GPU implementations: `fadtk.fad.calc_embd_statistics`,
+    `fadtk.fad.calc_frechet_distance` (fad.py:41-47, 50-119) and `fadtk.utils.calculate_embd_statistics_online`
+    (utils.py:19-46, which takes a list of .npy paths -- accepted here as well).  `fadtk` is a regular package, so unlike
+    the `diffmusic` namespace it cannot be shadowed on sys.path; call this once after importing it:
+
+        import fadtk.fad, fadtk.utils
+        from diffmusic_b200.fad import patch_fadtk
+        patch_fadtk(fadtk.fad, fadtk.utils)
+
+    `FrechetAudioDistanceTK.score` / `score_inf` / `load_stats` then run their statistics and distances on the GPU (they
+    look the functions up in the module namespace at call time).  Returns the names that were replaced."""
+    done = []
+    if fad_module is None:
+        import fadtk.fad as fad_module  # noqa: PLC0415
+    for name, fn in (("calc_embd_statistics", calc_embd_statistics), ("calc_frechet_distance", calc_frechet_distance)):
+        if hasattr(fad_module, name):
+            setattr(fad_module, name, fn)
+            done.append(f"{fad_module.__name__}.{name}")
+    if utils_module is None:
+        try:
+            import fadtk.utils as utils_module  # noqa: PLC0415
+        except Exception:  # hypy_utils & co. may be missing; the fad module is what the scores go through
+            utils_module = None
+    if utils_module is not None and hasattr(utils_module, "calculate_embd_statistics_online"):
+        utils_module.calculate_embd_statistics_online = calculate_embd_statistics_online
+        done.append(f"{utils_module.__name__}.calculate_embd_statistics_online")
+    if hasattr(fad_module, "calculate_embd_statistics_online"):  # `from .utils import *` copies it into fadtk.fad
+        fad_module.calculate_embd_statistics_online = calculate_embd_statistics_online
+        done.append(f"{fad_module.__name__}.calculate_embd_statistics_online")
+    return done

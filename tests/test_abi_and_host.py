@@ -141,3 +141,34 @@ def test_bench_hooks_the_entry_point_the_operators_call():
     assert called, "operators.py no longer calls a dm_stft_guidance* entry point?"
     hooked = set(re.findall(r'"(dm_stft_guidance\w*)"', bench))
     assert called <= hooked, (called, hooked)
+
+
+def test_metrics_dropin_and_fadtk_patch():
+    """the metrics shim resolves under the reference's import path next to the reference's own fad.py / kl.py, and
+    patch_fadtk swaps the three statistics functions of an fadtk-shaped module pair."""
+    import importlib
+    import os
+    import sys
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "diffmusic_b200", "dropin"))
+    try:
+        for name in [m for m in sys.modules if m == "diffmusic" or m.startswith("diffmusic.")]:
+            del sys.modules[name]
+        lsd = importlib.import_module("diffmusic.metrics.lsd")
+        mse = importlib.import_module("diffmusic.metrics.mse")
+        from diffmusic_b200 import metrics
+        assert lsd.LogSpectralDistance is metrics.LogSpectralDistance
+        assert mse.MeanSquaredError is metrics.MeanSquaredError
+    finally:
+        sys.path.pop(0)
+        for name in [m for m in sys.modules if m == "diffmusic" or m.startswith("diffmusic.")]:
+            del sys.modules[name]
+    from diffmusic_b200 import fad
+    f, u = types.ModuleType("fadtk.fad"), types.ModuleType("fadtk.utils")
+    f.calc_embd_statistics = f.calc_frechet_distance = f.calculate_embd_statistics_online = lambda *a: None
+    u.calculate_embd_statistics_online = lambda *a: None
+    done = fad.patch_fadtk(f, u)
+    assert f.calc_frechet_distance is fad.calc_frechet_distance and f.calc_embd_statistics is fad.calc_embd_statistics
+    assert u.calculate_embd_statistics_online is fad.calculate_embd_statistics_online
+    assert f.calculate_embd_statistics_online is fad.calculate_embd_statistics_online and len(done) == 4
