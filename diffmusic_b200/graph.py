@@ -67,6 +67,9 @@ class GraphedGuidedStep:
             self.out = self._run(t0)
         #: number of this library's kernels inside one replay (kernel nodes captured from dm_* calls)
         self.kernels_per_replay = _lib.launch_count() - n0
+        # the graph reads the operator's cached transform(measurement) at a fixed address: hold it, so an eager call with
+        # another measurement (which replaces the operator's one-entry cache) cannot release it under the graph
+        self._keepalive = dict(getattr(self.op, "_ref_cache", None) or {})
         scheduler._coef_dev = None
         if self._ir_dev is not None:
             self.op.static_ir = None  # eager calls on the same operator keep drawing their own impulse responses

@@ -207,14 +207,19 @@ class _GuidedBase(DDIMBase):
 
     def _cotangent_buffer(self, wav_full, Lw):
         """vocoder-shaped cotangent buffer, kept between steps: the kernels overwrite [:, :Lw] every step and never touch
-        the tail, which is zeroed once here (no per-step fill kernel)."""
+        the tail, which is zeroed once here (no per-step fill kernel).  A buffer that a CUDA graph captured is never
+        released (the graph replays into its address); otherwise at most a handful of shapes are kept."""
         key = (tuple(wav_full.shape), wav_full.dtype, wav_full.device, Lw)
         cache = self.__dict__.setdefault("_dfull_cache", {})
+        captured = self.__dict__.setdefault("_dfull_captured", set())
         buf = cache.get(key)
         if buf is None:
+            for old in [k for k in cache if k not in captured][:max(0, len(cache) - 3)]:
+                del cache[old]
             buf = torch.zeros_like(wav_full)
-            cache.clear()
             cache[key] = buf
+        if torch.cuda.is_current_stream_capturing():
+            captured.add(key)
         return buf
 
     @staticmethod
