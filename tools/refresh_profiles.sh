@@ -1,3 +1,9 @@
+#!/bin/bash
+# Reproduces the single-GPU evidence under profiles/r01 on a B200 box (run from the repo root, e.g. through gpurun):
+#   bench lines of all four workloads + the reference arm, the ncu launch list of the eager step and one
+#   `ncu --set full` capture of the dominant kernel (each profiler run only after the same command exited 0 plainly).
+# Afterwards, here:  cp gpurun_out/{launches.csv,prof_pair.ncu-rep,bench_*.json} profiles/r01/ ;
+#   ncu -i prof_pair.ncu-rep --page raw --csv > stft_pair_full_raw.csv ; tools/ncu_by_line.py ; tools/ncu_sass_summary.py
 set -x
 python bench.py > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err; tail -c 900 gpurun_out/bench_cfg2.json
 python bench.py --impl reference --steps 20 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; cat gpurun_out/bench_ref.json
