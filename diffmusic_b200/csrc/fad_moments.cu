@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kFadThreads) fad_finalize_kernel(const double*
 }  // namespace dm
 
 namespace dm {
-int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, cudaStream_t st);  // fad_tc.cu
+int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, bool pair_mma, cudaStream_t st);  // fad_tc.cu
 }
 
 using namespace dm;
@@ -155,13 +155,14 @@ extern "C" int dm_fad_moments(const void* x_f16, long long N, int d, double* acc
 extern "C" int dm_fad_moments_ex(const void* x_f16, long long N, int d, double* acc, int engine,
                                  dm_stream_t stream) {
     DM_REQUIRE(x_f16 && acc && N > 0 && d > 0);
-    DM_REQUIRE(engine == DM_FAD_AUTO || engine == DM_FAD_SIMT || engine == DM_FAD_TCGEN05);
+    DM_REQUIRE(engine == DM_FAD_AUTO || engine == DM_FAD_SIMT || engine == DM_FAD_TCGEN05 ||
+               engine == DM_FAD_TCGEN05_PAIR);
     const __half* X = reinterpret_cast<const __half*>(x_f16);
     bool xtx_done = false;
     if (engine != DM_FAD_SIMT) {
-        int rc = fad_xtx_tc(x_f16, N, d, acc + 1 + d, as_stream(stream));
+        int rc = fad_xtx_tc(x_f16, N, d, acc + 1 + d, engine == DM_FAD_TCGEN05_PAIR, as_stream(stream));
         if (rc == DM_OK) xtx_done = true;
-        else if (engine == DM_FAD_TCGEN05 || rc != DM_ERR_UNSUPPORTED) return rc;
+        else if (engine == DM_FAD_TCGEN05 || engine == DM_FAD_TCGEN05_PAIR || rc != DM_ERR_UNSUPPORTED) return rc;
     }
     const int nt = (d + kFadTile - 1) / kFadTile;
     // enough row slabs to fill the machine, each long enough to amortise the float64 atomics

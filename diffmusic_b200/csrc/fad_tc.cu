@@ -1,8 +1,12 @@
 // FAD second moments  S += X^T X  on the 5th-generation tensor cores (tcgen05), operands fed by TMA.
 //
 //   X : (N, d) fp16 row-major (what fadtk caches, model_loader.py:46-48).  fp16 x fp16 products are exact in fp32, the
-//   TMEM accumulator is fp32 and is drained into float64 REGISTER accumulators every kFlush K-blocks (256 rows), so the
-//   only rounding is the fp32 running sum inside one 256-row slab; np.cov (fadtk/fad.py:47) is float64.
+//   TMEM accumulator is fp32 and is drained into float64 REGISTER accumulators every kFlush K-blocks (512 rows), so the
+//   only rounding is the fp32 running sum inside one 512-row slab (measured: 1.8e-6 relative on sum x x^T, growing
+//   linearly with the slab length -- the tensor core's fp32 accumulation truncates); np.cov (fadtk/fad.py:47) is float64.
+//   Slab length and stage depth were tuned on the B200 (profiles/README.md): 64-row stages with 256-row slabs left the
+//   tensor pipe at 39 % (MMA-issue / hand-off overhead per stage and per slab), 128-row stages with 512-row slabs
+//   reach 55 %.
 //
 //   C tile (128 x 128) = A^T-tile * B-tile with A = X[:, i-block], B = X[:, j-block]: both operands are "MN-major"
 //   (contiguous along the output dimension), which kind::f16 supports directly -- no transpose pass over X.
@@ -23,11 +27,11 @@ namespace dm {
 
 constexpr int kTile = 128;          // output tile (M = N = 128)
 constexpr int kBoxCols = 64;        // TMA box: 64 fp16 = 128 B (one swizzle row)
-constexpr int kBlockK = 64;         // rows of X per pipeline stage
+constexpr int kBlockK = 128;        // rows of X per pipeline stage
 constexpr int kUmmaK = 16;          // K of one tcgen05.mma (fp16)
-constexpr int kStages = 6;
+constexpr int kStages = 3;
 constexpr int kAccStages = 2;
-constexpr int kFlush = 4;           // K-blocks per TMEM slab (256 rows) before draining to float64
+constexpr int kFlush = 4;           // K-blocks per TMEM slab (512 rows) before draining to float64
 constexpr int kTcThreads = 320;
 constexpr int kEpiWarps = 8;
 constexpr uint32_t kBoxBytes = kBoxCols * kBlockK * 2;          // 8 KB
@@ -306,6 +310,223 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
 }
 
+// ======================================================================================================================
+// cta_group::2 variant: a CTA PAIR (two SMs of one TPC) owns a 256 x 128 output super-tile -- column blocks (2 tp, 2 tp + 1)
+// of X against column block tj.  One tcgen05.mma.cta_group::2 (M = 256, N = 128) issued by the leader CTA drives the
+// tensor cores of both SMs: every CTA stages ITS 128 columns of A (16 KB per 64-row k-block) but only HALF of B (64
+// columns, 8 KB) -- the other half is read out of the peer's shared memory by the pair's MMA datapath.  Per SM and
+// 2.1 MFLOP that is 24 KB of L2 -> SM traffic instead of 32 KB for two independent 128 x 128 tiles.  Accumulators: each
+// CTA keeps its own 128 x 128 half in TMEM and drains it to float64 registers as above.
+// MEASURED (profiles/README.md): correct, but not faster than the multicast-cluster kernel above -- 43 % tensor-pipe
+// activity against 55 %: the super-tiles cover 24 block tiles where 21 are needed (the block below the diagonal of every
+// diagonal super-tile is wasted, diagonal tiles cannot share A = B), the total L2 read volume is the same 24 KB per
+// tile, and the two SMs of a pair stall together.  Kept as engine DM_FAD_TCGEN05_PAIR; DM_FAD_AUTO uses the kernel above.
+//   barriers   leader: full[s] (both CTAs' TMA loads land their transaction bytes there), tempty[a] (16 epilogue warps
+//              of both CTAs arrive);  every CTA: empty[s], tfull[a] (multicast tcgen05.commit of the leader).
+constexpr uint32_t kPairBBytes = kBoxBytes;                                  // 64 columns of B per CTA
+constexpr uint32_t kPairStageBytes = kOperandBytes + kPairBBytes;           // 24 KB per CTA and stage
+constexpr int kPairStages = 4;
+constexpr size_t kTc2SmemBytes = (size_t)kPairStages * kPairStageBytes + 1024 + 256;
+// instruction descriptor: as kIdesc with M = 256
+constexpr uint32_t kIdesc2 = (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | ((kTile >> 3) << 17) |
+                             ((256u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into this CTA's shared memory whose transaction bytes are accounted on a barrier given by its
+// shared::cluster address (the leader's `full` barrier)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0,
+                                                 int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+// bounded wait: a protocol error becomes a trap (-> a CUDA error at the next sync) instead of a hung GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    for (unsigned spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin > 64) __nanosleep(64);
+        if (spin > (1u << 24)) __trap();  // ~2 s: a protocol error, not a long wait
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+    fad_xtx_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const FadTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kPairStages * kPairStageBytes);
+    uint64_t* full = bars;                          // [kPairStages]  (leader's copy is the live one)
+    uint64_t* empty = bars + kPairStages;           // [kPairStages]
+    uint64_t* tfull = bars + 2 * kPairStages;       // [kAccStages]
+    uint64_t* tempty = tfull + kAccStages;          // [kAccStages]  (leader's copy is the live one)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+    // super-tile (tp, tj), tj >= 2 tp, enumerated row pair by row pair
+    int tp = 0, rem = blockIdx.x >> 1;
+    while (rem >= p.ntile - 2 * tp) {
+        rem -= p.ntile - 2 * tp;
+        ++tp;
+    }
+    const int tj = 2 * tp + rem;
+    const int bi = 2 * tp + (int)crank;  // the column block of X this CTA's half of the accumulator belongs to
+    const long long r_begin = (long long)blockIdx.y * p.rows_per_cta;
+    const long long r_end = min(p.N, r_begin + p.rows_per_cta);
+    const int nkb = r_end > r_begin ? (int)((r_end - r_begin + kBlockK - 1) / kBlockK) : 0;
+    const int nslab = (nkb + kFlush - 1) / kFlush;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPairStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < kAccStages; ++s) {
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], 2 * kEpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // same warp in both CTAs: the allocation is a pair-wide operation
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit / peer TMA signal
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kPairStages;
+                mbar_wait_bounded(&empty[s], ((kb / kPairStages) & 1) ^ 1);
+                uint8_t* a = smem + (size_t)s * kPairStageBytes;
+                uint8_t* b = a + kOperandBytes;
+                const int row = (int)(r_begin + (long long)kb * kBlockK);
+                if (leader) mbar_expect_tx(&full[s], 2 * kPairStageBytes);  // both CTAs' bytes land on this barrier
+                const uint32_t lead_full = mapa_rank(smem_u32(&full[s]), 0);
+                tma_load_2d_pair(&tmap, lead_full, a, bi * kTile, row);
+                tma_load_2d_pair(&tmap, lead_full, a + kBoxBytes, bi * kTile + kBoxCols, row);
+                tma_load_2d_pair(&tmap, lead_full, b, tj * kTile + (int)crank * kBoxCols, row);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kPairStages;
+                const int slab = kb / kFlush, as = slab % kAccStages;
+                if (kb % kFlush == 0) {
+                    mbar_wait_bounded(&tempty[as], ((slab / kAccStages) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                mbar_wait_bounded(&full[s], (kb / kPairStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * kPairStageBytes);
+                const uint32_t b_addr = a_addr + kOperandBytes;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * kTile);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    const uint32_t koff = (uint32_t)k * kUmmaK * 128u;
+                    umma_f16_pair(d_tmem, make_desc_mn_sw128(a_addr + koff), make_desc_mn_sw128(b_addr + koff), kIdesc2,
+                                  (kb % kFlush != 0 || k != 0) ? 1u : 0u);
+                }
+                umma_commit_pair(&empty[s]);
+                if (kb % kFlush == kFlush - 1 || kb == nkb - 1) umma_commit_pair(&tfull[as]);
+            }
+        }
+    } else {
+        // ===================== epilogue (both CTAs): TMEM -> float64 registers =====================
+        const int e = warp - 2;
+        const int quarter = warp & 3;
+        const int half = e >> 2;
+        const uint32_t lead_tempty0 = mapa_rank(smem_u32(&tempty[0]), 0);
+        double acc[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) acc[c] = 0.0;
+        for (int slab = 0; slab < nslab; ++slab) {
+            const int as = slab % kAccStages;
+            mbar_wait_bounded(&tfull[as], (slab / kAccStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kTile + half * 64);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                tmem_ld32(taddr + h * 32, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 32; ++c) acc[h * 32 + c] += (double)__uint_as_float(v[c]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_tempty0 + (uint32_t)(as * sizeof(uint64_t)));
+        }
+        // block (bi, tj): above the diagonal -> tile and mirror; on it -> tile; below it (bi = tj + 1) -> the mirror of
+        // block (tj, bi), which the super-tile (tp, tj + 1) writes
+        const int gi = bi * kTile + quarter * 32 + lane;
+        if (bi <= tj && gi < p.d && nkb > 0) {
+            const bool diag = bi == tj;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+                const int gj = tj * kTile + half * 64 + c;
+                if (gj < p.d) {
+                    atomicAdd(&p.sxx[(long long)gi * p.d + gj], acc[c]);
+                    if (!diag) atomicAdd(&p.sxx[(long long)gj * p.d + gi], acc[c]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();  // the peer may still arrive on this CTA's barriers / read its shared memory through the MMA
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -323,7 +544,7 @@ static EncodeTiledFn encode_tiled() {
 }
 
 // returns DM_ERR_UNSUPPORTED when the shape cannot go through TMA (caller falls back to the SIMT kernel)
-int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, cudaStream_t st) {
+int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, bool pair_mma, cudaStream_t st) {
     if (d % 8 != 0 || (reinterpret_cast<uintptr_t>(x_f16) & 15) != 0 || N > 0x7fffffffLL)
         return fail(DM_ERR_UNSUPPORTED, "%s: TMA needs d %% 8 == 0 and a 16-byte aligned base", __func__);
     EncodeTiledFn enc = encode_tiled();
@@ -347,9 +568,21 @@ int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, cudaStream_t 
         npairs += (p.ntile - ti) / 2;
         nsingles += (p.ntile - ti) & 1;
     }
+    const long long slab_rows = (long long)kFlush * kBlockK;
+    if (pair_mma) {  // cta_group::2: one CTA pair per 256 x 128 super-tile
+        int nsuper = 0;
+        for (int tp = 0; 2 * tp < p.ntile; ++tp) nsuper += p.ntile - 2 * tp;
+        long long splits = std::max<long long>(1, num_sms() / (2 * nsuper));
+        long long rows = (N + splits - 1) / splits;
+        p.rows_per_cta = std::max<long long>(slab_rows, (rows + slab_rows - 1) / slab_rows * slab_rows);
+        const int gy = (int)((N + p.rows_per_cta - 1) / p.rows_per_cta);
+        DM_SMEM_ONCE(fad_xtx_tc2_kernel, kTc2SmemBytes);
+        fad_xtx_tc2_kernel<<<dim3(2 * nsuper, gy), kTcThreads, kTc2SmemBytes, st>>>(tmap, p);
+        DM_LAUNCHED();
+        return DM_OK;
+    }
     // one CTA per SM (192 KB of pipeline stages): each launch splits the rows so that its grid covers the machine about
     // once, in multiples of the flush slab so every CTA drains whole slabs
-    const long long slab_rows = (long long)kFlush * kBlockK;
     auto rows_for = [&](int tiles) {
         long long splits = std::max<long long>(1, num_sms() / tiles);
         long long rows = (N + splits - 1) / splits;

@@ -16,7 +16,7 @@ from . import _lib
 class EmbeddingMoments:
     """Accumulator of raw moments for one embedding model of width d."""
 
-    ENGINES = {"auto": 0, "simt": 1, "tcgen05": 2}
+    ENGINES = {"auto": 0, "simt": 1, "tcgen05": 2, "tcgen05_pair": 3}
 
     def __init__(self, d, device=None, engine="auto"):
         self.d = int(d)

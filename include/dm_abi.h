@@ -223,6 +223,7 @@ int dm_fad_moments(const void* x_f16, long long N, int d, double* acc, dm_stream
 #define DM_FAD_AUTO 0
 #define DM_FAD_SIMT 1
 #define DM_FAD_TCGEN05 2
+#define DM_FAD_TCGEN05_PAIR 3 /* tcgen05.mma.cta_group::2: a CTA pair (two SMs) per 256 x 128 super-tile */
 int dm_fad_moments_ex(const void* x_f16, long long N, int d, double* acc, int engine, dm_stream_t stream);
 /* mu (d) and cov (d, d) in float64 from acc */
 int dm_fad_finalize(const double* acc, int d, double* mu, double* cov, dm_stream_t stream);

@@ -322,10 +322,13 @@ def test_operator_linearity_and_adjoint_identity():
 
 
 # ------------------------------------------------------------------------------------------------ FAD statistics
-@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
-@pytest.mark.parametrize("n,d", [(40, 128), (1000, 512), (4990, 768), (333, 1024), (70000, 768), (2500, 200)])
+@pytest.mark.parametrize("engine", ["simt", "tcgen05", "tcgen05_pair"])
+@pytest.mark.parametrize("n,d", [(40, 128), (1000, 512), (4990, 768), (333, 1024), (70000, 768), (2500, 200),
+                                 (3000, 640), (513, 384)])
 def test_fad_moments_engines(n, d, engine):
-    """sum x x^T through the SIMT tile kernel and through the tcgen05 + TMA kernel against float64 NumPy."""
+    """sum x x^T through the SIMT tile kernel, the tcgen05 + TMA kernel (one SM per 128 x 128 tile) and its
+    cta_group::2 variant (a CTA pair per 256 x 128 super-tile; odd tile counts leave a phantom block) against float64
+    NumPy."""
     from diffmusic_b200 import fad
     rng = np.random.default_rng(d + n)
     X = (rng.standard_normal((n, d)) * 0.7 + rng.standard_normal(d) * 0.3).astype(np.float16)
