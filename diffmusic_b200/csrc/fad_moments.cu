@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(kFadThreads) fad_finalize_kernel(const double*
 }  // namespace dm
 
 namespace dm {
-int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, bool pair_mma, cudaStream_t st);  // fad_tc.cu
+int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, double* sx, double* n_out, bool pair_mma,
+               cudaStream_t st);  // fad_tc.cu
 }
 
 using namespace dm;
@@ -160,7 +161,16 @@ extern "C" int dm_fad_moments_ex(const void* x_f16, long long N, int d, double* 
     const __half* X = reinterpret_cast<const __half*>(x_f16);
     bool xtx_done = false;
     if (engine != DM_FAD_SIMT) {
-        int rc = fad_xtx_tc(x_f16, N, d, acc + 1 + d, engine == DM_FAD_TCGEN05_PAIR, as_stream(stream));
+        // the tensor-core kernel also produces the column sums and the count (one extra N = 16 MMA per k-step on the
+        // diagonal tiles), so X is read exactly once; the cta_group::2 engine leaves them to the column-sum kernel
+        // Measured (tools/fad_bench.py, N = 511 k): fused sums win up to 6 column blocks (d = 512: 0.345 -> 0.273 ms,
+        // d = 768: 0.587 -> 0.525 ms); at d = 1024 the 8 diagonal CTAs become the stragglers (0.897 -> 0.931 ms) and the
+        // separate HBM-speed column-sum kernel stays.
+        const bool pair = engine == DM_FAD_TCGEN05_PAIR;
+        const bool fuse_sums = !pair && d <= 6 * 128;
+        int rc = fad_xtx_tc(x_f16, N, d, acc + 1 + d, fuse_sums ? acc + 1 : nullptr, fuse_sums ? acc : nullptr, pair,
+                            as_stream(stream));
+        if (rc == DM_OK && fuse_sums) return DM_OK;
         if (rc == DM_OK) xtx_done = true;
         else if (engine == DM_FAD_TCGEN05 || engine == DM_FAD_TCGEN05_PAIR || rc != DM_ERR_UNSUPPORTED) return rc;
     }

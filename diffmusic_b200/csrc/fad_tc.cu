@@ -37,8 +37,11 @@ constexpr int kEpiWarps = 8;
 constexpr uint32_t kBoxBytes = kBoxCols * kBlockK * 2;          // 8 KB
 constexpr uint32_t kOperandBytes = 2 * kBoxBytes;               // 128 columns x 64 rows = 16 KB
 constexpr uint32_t kStageBytes = 2 * kOperandBytes;             // A + B
-constexpr uint32_t kTmemCols = kAccStages * kTile;              // 256 fp32 columns
-constexpr size_t kTcSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kSumCols = 16;                                    // N of the column-sum MMA (the smallest N for M = 128)
+constexpr uint32_t kTmemCols = 512;                             // 2 x 128 accumulator columns + 2 x 16 column-sum columns
+constexpr uint32_t kSumTmemCol = kAccStages * kTile;            // first column of the column-sum accumulators
+constexpr uint32_t kOnesBytes = kBoxBytes;                      // a 64 x kBlockK tile of fp16 ones (any layout)
+constexpr size_t kTcSmemBytes = (size_t)kStages * kStageBytes + kOnesBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -137,11 +140,16 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both MN-major, N = 128, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | ((kTile >> 3) << 17) |
                             ((kTile >> 4) << 24);
+// the same with N = 16: A^T (128 x K) times a K x 16 block of ones = the column sums of the A block, 16 times over
+constexpr uint32_t kIdescSum = (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | ((kSumCols >> 3) << 17) |
+                               ((kTile >> 4) << 24);
 
 struct FadTcParams {
     int d, ntile;           // columns, tiles per side
     long long N, rows_per_cta;
     double* sxx;
+    double* sx;             // optional: column sums (d) and the row count, produced by the diagonal tiles with one extra
+    double* n_out;          // N = 16 MMA per k-step against a block of ones -- X is not read a second time for them
 };
 
 // kCluster == 2: the two CTAs of a cluster own tiles (ti, tj) and (ti, tj+1) of the same row range, i.e. they need the
@@ -155,7 +163,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     fad_xtx_tc_kernel(const __grid_constant__ CUtensorMap tmap, const FadTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+    uint8_t* ones = smem + (size_t)kStages * kStageBytes;  // fp16 ones: the B operand of the column-sum MMA
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ones + kOnesBytes);
     uint64_t* full = bars;                       // [kStages]  TMA -> MMA
     uint64_t* empty = bars + kStages;            // [kStages]  MMA -> TMA
     uint64_t* tfull = bars + 2 * kStages;        // [kAccStages] MMA -> epilogue
@@ -185,7 +194,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         tj = p.ntile - 1;
     }
     const bool diag = (ti == tj);
+    const bool sums = diag && p.sx != nullptr;  // every column block has exactly one diagonal tile
     constexpr uint16_t kAllCtas = (uint16_t)((1u << kCluster) - 1);
+    for (uint32_t i = threadIdx.x; i < kOnesBytes / 4; i += kTcThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3C003C00u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's reads
     const long long r_begin = (long long)blockIdx.y * p.rows_per_cta;
     const long long r_end = min(p.N, r_begin + p.rows_per_cta);
     const int nkb = r_end > r_begin ? (int)((r_end - r_begin + kBlockK - 1) / kBlockK) : 0;
@@ -257,6 +269,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     umma_f16(d_tmem, make_desc_mn_sw128(a_addr + koff), make_desc_mn_sw128(b_addr + koff), kIdesc,
                              (kb % kFlush != 0 || k != 0) ? 1u : 0u);
                 }
+                if (sums) {  // column sums of the A block: every element of the B operand is 1, so its layout is moot
+                    const uint64_t ones_desc = make_desc_mn_sw128(smem_u32(ones));
+                    const uint32_t s_tmem = tmem_base + kSumTmemCol + (uint32_t)(as * kSumCols);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_f16(s_tmem, make_desc_mn_sw128(a_addr + (uint32_t)k * kUmmaK * 128u), ones_desc, kIdescSum,
+                                 (kb % kFlush != 0 || k != 0) ? 1u : 0u);
+                }
                 // smem stage free (in every CTA that multicasts into it) once these MMAs have read it
                 if (kCluster == 2) umma_commit_mcast(&empty[s], kAllCtas);
                 else umma_commit(&empty[s]);
@@ -269,6 +289,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int quarter = warp & 3;           // TMEM lanes a warp may touch: 32 * (warp % 4) ...
         const int half = e >> 2;                // which 64 of the 128 accumulator columns
         double acc[64];
+        double sx_acc = 0.0;
 #pragma unroll
         for (int c = 0; c < 64; ++c) acc[c] = 0.0;
         for (int slab = 0; slab < nslab; ++slab) {
@@ -284,12 +305,23 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
                 for (int c = 0; c < 32; ++c) acc[h * 32 + c] += (double)__uint_as_float(v[c]);
             }
+            if (sums && half == 0) {  // lane = column of the A block; the 16 sum columns are identical, read the first
+                uint32_t sv;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];"
+                             : "=r"(sv)
+                             : "r"(tmem_base + ((uint32_t)(quarter * 32) << 16) + kSumTmemCol + (uint32_t)(as * kSumCols))
+                             : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                sx_acc += (double)__uint_as_float(sv);
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
         }
         // ---- add the tile into the float64 accumulator (and its mirror) ----
         const int gi = ti * kTile + quarter * 32 + lane;
+        if (sums && half == 0 && gi < p.d && nkb > 0) atomicAdd(&p.sx[gi], sx_acc);
+        if (sums && ti == 0 && blockIdx.y == 0 && e == 0 && lane == 0) atomicAdd(p.n_out, (double)p.N);
         if (gi < p.d && nkb > 0) {
 #pragma unroll
             for (int c = 0; c < 64; ++c) {
@@ -544,7 +576,9 @@ static EncodeTiledFn encode_tiled() {
 }
 
 // returns DM_ERR_UNSUPPORTED when the shape cannot go through TMA (caller falls back to the SIMT kernel)
-int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, bool pair_mma, cudaStream_t st) {
+// sx / n_out (may be NULL): column sums and row count, fused into the diagonal tiles (not by the cta_group::2 engine)
+int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, double* sx, double* n_out, bool pair_mma,
+               cudaStream_t st) {
     if (d % 8 != 0 || (reinterpret_cast<uintptr_t>(x_f16) & 15) != 0 || N > 0x7fffffffLL)
         return fail(DM_ERR_UNSUPPORTED, "%s: TMA needs d %% 8 == 0 and a 16-byte aligned base", __func__);
     EncodeTiledFn enc = encode_tiled();
@@ -563,6 +597,8 @@ int fad_xtx_tc(const void* x_f16, long long N, int d, double* sxx, bool pair_mma
     p.ntile = (d + kTile - 1) / kTile;
     p.N = N;
     p.sxx = sxx;
+    p.sx = pair_mma ? nullptr : sx;
+    p.n_out = pair_mma ? nullptr : n_out;
     int npairs = 0, nsingles = 0;
     for (int ti = 0; ti < p.ntile; ++ti) {
         npairs += (p.ntile - ti) / 2;

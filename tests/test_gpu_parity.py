@@ -336,7 +336,9 @@ def test_fad_moments_engines(n, d, engine):
     acc = mom.acc.cpu().numpy()
     X64 = X.astype(np.float64)
     assert acc[0] == n
-    assert rel_l2(acc[1:1 + d], X64.sum(0)) < 1e-7
+    # column sums: float64 throughout on the SIMT / cta_group::2 paths; on the tcgen05 path they come out of the tensor
+    # cores too (A^T times a block of ones, fp32 accumulation over 512-row slabs, float64 across slabs)
+    assert rel_l2(acc[1:1 + d], X64.sum(0)) < (1e-6 if engine == "tcgen05" and d % 8 == 0 and d <= 768 else 1e-7)
     got, want = acc[1 + d:].reshape(d, d), X64.T @ X64
     assert rel_l2(got, want) < 2e-6, (engine, rel_l2(got, want))
     assert np.array_equal(got, got.T)
