@@ -53,6 +53,8 @@ _SIGNATURES = {
                                      c_p, c_p]),
     "dm_rir_correlate_io": (c_i, [c_p, c_i, c_ll, c_ll, c_i, c_p, c_i, c_p, c_p, c_p, c_ll, c_p]),
     "dm_rir_adjoint_io": (c_i, [c_p, c_i, c_ll, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_i, c_ll, c_ll, c_p, c_p]),
+    "dm_randn_offset_increment": (c_ll, [c_ll]),
+    "dm_randn_clips": (c_i, [c_p, c_p, c_i, c_ll, c_i, c_p, c_p]),
     "dm_stft_set_engine": (c_i, [c_i]),
     "dm_stft_num_tiles": (c_i, [c_ll, c_i, c_i]),
     "dm_stft_guidance": (c_i, [C.POINTER(StftTables), c_i, c_i, c_i, c_p, c_ll, c_ll, c_p, c_i, c_p, c_ll, c_p, c_f,

@@ -132,10 +132,73 @@ except Exception:  # diffusers absent (this build container): stand-alone base
             self.timesteps = torch.from_numpy(ts).to(device)
 
 
+def _clip_generators(shape, generator, device, dtype, layout):
+    """The list of per-clip CUDA generators when the batched Philox kernel (csrc/rng_clips.cu) can stand in for the
+    reference's per-clip torch.randn loop, else None."""
+    from . import _lib
+    if not isinstance(generator, (list, tuple)) or len(generator) < 2 or len(generator) != shape[0]:
+        return None
+    if len(generator) > 128 or device.type != "cuda" or (layout not in (None, torch.strided)):
+        return None
+    if (dtype or torch.get_default_dtype()) not in _lib.IO_DTYPES:
+        return None
+    if any(g.device != device and not (g.device.type == "cuda" and g.device.index in (None, device.index))
+           for g in generator) or any(g.device.type != "cuda" for g in generator):
+        return None
+    return list(generator)
+
+
+def skip_randn(shape, generator, device=None, dtype=None):
+    """Consume exactly what `randn_tensor(shape, generator, ...)` would consume without producing the values (the
+    reference's discarded base-step draw, scheduling_dps.py:166-175): for per-clip CUDA generators that is an offset
+    bump, otherwise the draw itself."""
+    from . import _lib
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    gens = _clip_generators(shape, generator, device, dtype, None)
+    if gens is None:
+        randn_tensor(shape, generator=generator, device=device, dtype=dtype)
+        return
+    n = 1
+    for d in shape[1:]:
+        n *= int(d)
+    with torch.cuda.device(device):
+        inc = int(_lib.load().dm_randn_offset_increment(n))
+    for g in gens:
+        g.set_offset(g.get_offset() + inc)
+
+
+def randn_clips_f32(shape, generator, device=None, dtype=None):
+    """fp32 tensor holding the values of `randn_tensor(shape, generator=[g_0..g_{B-1}], dtype=dtype)` (rounded through
+    `dtype` when it is 16-bit), drawn for all clips by ONE kernel with torch's own Philox / curand_normal4 mapping and
+    each generator's (seed, offset); the generators' offsets advance as if torch had drawn.  None if the fused path
+    does not apply (single generator, CPU generators, other dtypes)."""
+    import ctypes as C
+    from . import _lib
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    gens = _clip_generators(shape, generator, device, dtype, None)
+    if gens is None:
+        return None
+    B = len(gens)
+    n = 1
+    for d in shape[1:]:
+        n *= int(d)
+    seeds = (C.c_ulonglong * B)(*[g.initial_seed() for g in gens])
+    offs = (C.c_ulonglong * B)(*[g.get_offset() for g in gens])
+    with torch.cuda.device(device):
+        out = torch.empty((B, n), device=device, dtype=torch.float32)
+        _lib.call("dm_randn_clips", seeds, offs, B, n, _lib.IO_DTYPES[dtype or torch.get_default_dtype()],
+                  out.data_ptr(), _lib.stream())
+        inc = int(_lib.load().dm_randn_offset_increment(n))
+    for g, o in zip(gens, offs):
+        g.set_offset(int(o) + inc)
+    return out.view(tuple(shape))
+
+
 def randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
     """Noise draw with the reference's generator semantics (diffmusic/torch_utils.py:31-76): a single generator draws
     the whole batch, a list draws one (1, ...) tensor per clip; CPU generators draw on the CPU and the result is moved.
-    Kept in torch so RNG streams are bit-identical to the reference (kernels never generate randomness)."""
+    Single generators draw through torch; a list of CUDA generators goes through one batched kernel that reproduces
+    torch's Philox stream for every clip bit for bit (csrc/rng_clips.cu, tests/test_gpu_parity.py)."""
     device = torch.device(device) if device is not None else torch.device("cpu")
     layout = layout or torch.strided
     where = device
@@ -149,6 +212,10 @@ def randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
     if isinstance(generator, (list, tuple)) and len(generator) == 1:
         generator = generator[0]
     if isinstance(generator, (list, tuple)):
+        fused = randn_clips_f32(shape, generator, where, dtype) if where.type == "cuda" and layout == torch.strided \
+            else None
+        if fused is not None:  # one launch for all clips, same values and generator states as the loop below
+            return fused.to(dtype or torch.get_default_dtype()).to(device)
         per = (1,) + tuple(shape[1:])
         out = torch.cat([torch.randn(per, generator=generator[i], device=where, dtype=dtype, layout=layout)
                          for i in range(shape[0])], dim=0)

@@ -19,7 +19,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .ddim_base import BaseOutput, DDIMBase, randn_tensor, register_to_config
+from .ddim_base import (BaseOutput, DDIMBase, randn_clips_f32, randn_tensor, register_to_config, skip_randn)
 from .operators import BaseOperator, generic_guidance_loss
 
 
@@ -147,18 +147,26 @@ class _GuidedBase(DDIMBase):
         Returns z as fp32 (or None)."""
         shape, dev, dt = model_output.shape, model_output.device, model_output.dtype
         if self.noise_mode == "always":
-            return randn_tensor(shape, generator=generator, device=dev, dtype=dt).float().contiguous()
+            return self._randn_f32(shape, generator, dev, dt)
         if not eta > 0:
             return None
         if variance_noise is not None and generator is not None:
             raise ValueError("Cannot pass both generator and variance_noise. Please make sure that either "
                              "`generator` or `variance_noise` stays `None`.")
         if variance_noise is None:
-            randn_tensor(shape, generator=generator, device=dev, dtype=dt)  # base-step draw, discarded
+            skip_randn(shape, generator, device=dev, dtype=dt)  # base-step draw, discarded by the reference
             if isinstance(self, DDIMScheduler):
                 return None
-            variance_noise = randn_tensor(shape, generator=generator, device=dev, dtype=dt)
+            return self._randn_f32(shape, generator, dev, dt)
         return variance_noise.detach().float().contiguous()
+
+    @staticmethod
+    def _randn_f32(shape, generator, dev, dt):
+        """the step noise as fp32: per-clip generator lists in one launch (ddim_base.randn_clips_f32), else torch"""
+        z = randn_clips_f32(shape, generator, dev, dt)
+        if z is None:
+            z = randn_tensor(shape, generator=generator, device=dev, dtype=dt).float().contiguous()
+        return z
 
     def _noise_arg(self, given, eta, generator, variance_noise, model_output):
         """step noise: drawn here (eager) unless the caller already did (`_noise`, used by GraphedGuidedStep)."""

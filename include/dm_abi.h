@@ -254,6 +254,18 @@ int dm_rir_adjoint_io(const float* ybar, int pad, long long Ly, int B, const flo
                       long long dwav_bstride, long long L, float* loss, dm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Per-clip step noise (diffmusic/torch_utils.py:31-76 `randn_tensor` with a LIST of generators: one torch.randn((1, ...),
+ * generator=g_b) per clip).  One launch draws all clips with torch's own Philox4x32-10 / curand_normal4 index mapping, from
+ * HOST arrays of each generator's (seed, offset) -- the values are bit-identical to the per-clip torch draws; the caller
+ * advances every generator's offset by dm_randn_offset_increment(n_per_clip) afterwards.  out: (n_clips, n_per_clip) fp32;
+ * round_dtype = DM_IO_F16 / DM_IO_BF16 rounds each value through that type first (what a 16-bit torch.randn returns).
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define DM_RNG_MAX_CLIPS 128
+long long dm_randn_offset_increment(long long n_per_clip);
+int dm_randn_clips(const unsigned long long* seeds, const unsigned long long* offsets, int n_clips,
+                   long long n_per_clip, int round_dtype, float* out, dm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Frechet distance and the FAD-inf bootstrap (fadtk/fad.py:50-119 `calc_frechet_distance`, :303-350 `score_inf`).
  * ---------------------------------------------------------------------------------------------------------------- */
 /* out_f16[r, :] = x_f16[idx[r], :]  -- embeds[np.random.choice(N, n)] of score_inf (fad.py:331-332); idx is int64 on

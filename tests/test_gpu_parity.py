@@ -903,3 +903,31 @@ def test_graphed_step_in_fp16_equals_eager_fp16():
         assert b.prev_sample.dtype == dt
         assert torch.equal(a.prev_sample, b.prev_sample) and torch.equal(a.pred_original_sample, b.pred_original_sample)
         assert torch.equal(a.loss, b.loss) and torch.equal(a.loss_per_clip, b.loss_per_clip)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(16, 8, 250, 16), (3, 8, 25, 16), (2, 1, 1, 7), (5, 4, 33, 1031), (2, 8, 9000, 16)])
+def test_batched_clip_noise_is_torch_randn_bit_for_bit(shape, dt):
+    """dm_randn_clips == the reference's per-clip loop torch.randn((1, ...), generator=g_b) (torch_utils.py:31-76):
+    same values, and the generators end in the same state (a second draw matches too)."""
+    from diffmusic_b200 import ddim_base
+    B = shape[0]
+    ga = [torch.Generator(device=DEV).manual_seed(100 + i) for i in range(B)]
+    gb = [torch.Generator(device=DEV).manual_seed(100 + i) for i in range(B)]
+    ga[0].set_offset(40)  # a generator that has been used before
+    gb[0].set_offset(40)
+    per = (1,) + shape[1:]
+    for _ in range(2):
+        want = torch.cat([torch.randn(per, generator=g, device=DEV, dtype=dt) for g in ga])
+        got = ddim_base.randn_clips_f32(shape, gb, torch.device(DEV), dt)
+        assert got is not None and got.dtype == torch.float32
+        assert torch.equal(got, want.float())
+        assert [g.get_offset() for g in ga] == [g.get_offset() for g in gb]
+    ddim_base.skip_randn(shape, gb, DEV, dt)
+    torch.cat([torch.randn(per, generator=g, device=DEV, dtype=dt) for g in ga])
+    assert [g.get_offset() for g in ga] == [g.get_offset() for g in gb]
+    assert torch.equal(ddim_base.randn_tensor(shape, generator=gb, device=DEV, dtype=dt),
+                       torch.cat([torch.randn(per, generator=g, device=DEV, dtype=dt) for g in ga]))
+    # single generators and CPU generators keep going through torch
+    assert ddim_base.randn_clips_f32(shape, gb[0], torch.device(DEV), dt) is None
+    assert ddim_base.randn_clips_f32(shape, [torch.Generator().manual_seed(1) for _ in range(B)], torch.device(DEV), dt) is None
