@@ -69,6 +69,7 @@ _SIGNATURES = {
     "dm_rir_correlate": (c_i, [c_p, c_ll, c_ll, c_i, c_p, c_i, c_p, c_p, c_p, c_ll, c_p]),
     "dm_rir_adjoint": (c_i, [c_p, c_i, c_ll, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_ll, c_ll, c_p, c_p]),
     "dm_add_scaled": (c_i, [c_p, c_p, c_f, c_ll, c_p]),
+    "dm_copy_f32": (c_i, [c_p, c_p, c_ll, c_p]),
     "dm_fad_moments": (c_i, [c_p, c_ll, c_i, c_p, c_p]),
     "dm_fad_moments_ex": (c_i, [c_p, c_ll, c_i, c_p, c_i, c_p]),
     "dm_fad_finalize": (c_i, [c_p, c_i, c_p, c_p, c_p]),

@@ -587,6 +587,20 @@ extern "C" int dm_mask_apply(const float* x, long long x_bstride, long long L, i
     return DM_OK;
 }
 
+__global__ void __launch_bounds__(kEwThreads) copy_f32_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                                              long long n) {
+    const long long stride = (long long)gridDim.x * kEwThreads;
+    for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
+extern "C" int dm_copy_f32(float* dst, const float* src, long long n, dm_stream_t stream) {
+    DM_REQUIRE(dst && src && n > 0);
+    const int nblk = (int)min((long long)num_sms() * 2, (n + kEwThreads - 1) / kEwThreads);
+    copy_f32_kernel<<<nblk, kEwThreads, 0, as_stream(stream)>>>(dst, src, n);
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
 extern "C" int dm_add_scaled(float* y, const float* noise, float sigma, long long n, dm_stream_t stream) {
     DM_REQUIRE(y && noise && n > 0);
     const int nblk = (int)min((long long)num_sms() * 8, (n + kEwThreads - 1) / kEwThreads);

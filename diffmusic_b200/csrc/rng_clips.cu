@@ -47,12 +47,15 @@ __global__ void __launch_bounds__(256) randn_clips_kernel(const __grid_constant_
 }
 
 static int rng_grid(long long n) {
-    int dev = 0, sms = 0, tpsm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&tpsm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
-    long long g = (n + 255) / 256;
-    const long long cap = (long long)sms * (tpsm / 256);
+    static long long cap = 0;  // #SM * (max threads per SM / 256): torch's grid cap (one device model per process)
+    if (cap == 0) {
+        int dev = 0, sms = 0, tpsm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&tpsm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+        cap = (long long)sms * (tpsm / 256);
+    }
+    const long long g = (n + 255) / 256;
     return (int)(g < cap ? g : cap);
 }
 

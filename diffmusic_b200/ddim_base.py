@@ -136,61 +136,78 @@ def _clip_generators(shape, generator, device, dtype, layout):
     """The list of per-clip CUDA generators when the batched Philox kernel (csrc/rng_clips.cu) can stand in for the
     reference's per-clip torch.randn loop, else None."""
     from . import _lib
-    if not isinstance(generator, (list, tuple)) or len(generator) < 2 or len(generator) != shape[0]:
+    if not isinstance(generator, (list, tuple)) or not 2 <= len(generator) <= 128 or len(generator) != shape[0]:
         return None
-    if len(generator) > 128 or device.type != "cuda" or (layout not in (None, torch.strided)):
+    if device.type != "cuda" or (layout not in (None, torch.strided)):
         return None
     if (dtype or torch.get_default_dtype()) not in _lib.IO_DTYPES:
         return None
-    if any(g.device != device and not (g.device.type == "cuda" and g.device.index in (None, device.index))
-           for g in generator) or any(g.device.type != "cuda" for g in generator):
-        return None
-    return list(generator)
+    for g in generator:
+        gd = g.device
+        if gd.type != "cuda" or (gd.index is not None and device.index is not None and gd.index != device.index):
+            return None
+    return generator
+
+
+_INC_CACHE = {}
+
+
+def _offset_increment(n, device):
+    """how far one draw of n values advances a generator's Philox offset (torch's launch geometry, per device model)"""
+    from . import _lib
+    inc = _INC_CACHE.get(n)
+    if inc is None:
+        with torch.cuda.device(device):
+            inc = _INC_CACHE[n] = int(_lib.load().dm_randn_offset_increment(n))
+    return inc
+
+
+def _clip_numel(shape):
+    n = 1
+    for d in shape[1:]:
+        n *= int(d)
+    return n
 
 
 def skip_randn(shape, generator, device=None, dtype=None):
     """Consume exactly what `randn_tensor(shape, generator, ...)` would consume without producing the values (the
     reference's discarded base-step draw, scheduling_dps.py:166-175): for per-clip CUDA generators that is an offset
     bump, otherwise the draw itself."""
-    from . import _lib
     device = torch.device(device) if device is not None else torch.device("cpu")
     gens = _clip_generators(shape, generator, device, dtype, None)
     if gens is None:
         randn_tensor(shape, generator=generator, device=device, dtype=dtype)
         return
-    n = 1
-    for d in shape[1:]:
-        n *= int(d)
-    with torch.cuda.device(device):
-        inc = int(_lib.load().dm_randn_offset_increment(n))
+    inc = _offset_increment(_clip_numel(shape), device)
     for g in gens:
         g.set_offset(g.get_offset() + inc)
 
 
-def randn_clips_f32(shape, generator, device=None, dtype=None):
+def randn_clips_f32(shape, generator, device=None, dtype=None, out=None):
     """fp32 tensor holding the values of `randn_tensor(shape, generator=[g_0..g_{B-1}], dtype=dtype)` (rounded through
     `dtype` when it is 16-bit), drawn for all clips by ONE kernel with torch's own Philox / curand_normal4 mapping and
-    each generator's (seed, offset); the generators' offsets advance as if torch had drawn.  None if the fused path
-    does not apply (single generator, CPU generators, other dtypes)."""
+    each generator's (seed, offset); the generators' offsets advance as if torch had drawn.  `out`: optional contiguous
+    fp32 destination of that shape.  None if the fused path does not apply (single generator, CPU generators, other
+    dtypes)."""
     import ctypes as C
     from . import _lib
     device = torch.device(device) if device is not None else torch.device("cpu")
     gens = _clip_generators(shape, generator, device, dtype, None)
     if gens is None:
         return None
-    B = len(gens)
-    n = 1
-    for d in shape[1:]:
-        n *= int(d)
+    B, n = len(gens), _clip_numel(shape)
+    offsets = [g.get_offset() for g in gens]
     seeds = (C.c_ulonglong * B)(*[g.initial_seed() for g in gens])
-    offs = (C.c_ulonglong * B)(*[g.get_offset() for g in gens])
-    with torch.cuda.device(device):
-        out = torch.empty((B, n), device=device, dtype=torch.float32)
-        _lib.call("dm_randn_clips", seeds, offs, B, n, _lib.IO_DTYPES[dtype or torch.get_default_dtype()],
-                  out.data_ptr(), _lib.stream())
-        inc = int(_lib.load().dm_randn_offset_increment(n))
-    for g, o in zip(gens, offs):
-        g.set_offset(int(o) + inc)
+    offs = (C.c_ulonglong * B)(*offsets)
+    if out is None:
+        out = torch.empty(tuple(shape), device=device, dtype=torch.float32)
+    elif out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != B * n or out.device != device:
+        raise ValueError("randn_clips_f32: `out` must be a contiguous fp32 tensor of the requested shape")
+    _lib.call("dm_randn_clips", seeds, offs, B, n, _lib.IO_DTYPES[dtype or torch.get_default_dtype()], out.data_ptr(),
+              torch.cuda.current_stream(device).cuda_stream)
+    inc = _offset_increment(n, device)
+    for g, o in zip(gens, offsets):
+        g.set_offset(o + inc)
     return out.view(tuple(shape))
 
 

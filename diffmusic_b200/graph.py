@@ -46,7 +46,11 @@ class GraphedGuidedStep:
         self.op = scheduler.operator
         self._ir_host = self._ir_dev = None
         if hasattr(self.op, "generate_impulse_response"):  # dereverberation: IR redrawn on the host every step
-            self._ir_host = torch.zeros(self.op.ir_length, dtype=torch.float32).pin_memory()
+            # a small ring of pinned staging rows: the host may run several steps ahead of the device, and a row must
+            # not be rewritten before its asynchronous upload has executed
+            self._ir_host = [torch.zeros(self.op.ir_length, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._ir_event = [None] * 4
+            self._ir_turn = 0
             self._ir_dev = torch.zeros(self.op.ir_length, device=dev, dtype=torch.float32)
             self.op.static_ir = self._ir_dev
         t0 = int(scheduler.timesteps[0]) if warmup_timestep is None else int(warmup_timestep)
@@ -80,8 +84,9 @@ class GraphedGuidedStep:
     def _prepare(self, timestep, generator, variance_noise):
         """host-side per-step work: RNG draws (reference order), coefficients, impulse response."""
         if self.z is not None:
-            z = self.sched.draw_step_noise(self.eta, generator, variance_noise, self.e)
-            self.z.copy_(z, non_blocking=True)
+            z = self.sched.draw_step_noise(self.eta, generator, variance_noise, self.e, out=self.z)
+            if z.data_ptr() != self.z.data_ptr():  # torch drew it (single generator / variance_noise given)
+                self.z.copy_(z, non_blocking=True)
         elif self.eta > 0:
             self.sched.draw_step_noise(self.eta, generator, variance_noise, self.e)  # DDIM: discarded draw
         row = self._coef_rows.get(timestep)
@@ -92,13 +97,26 @@ class GraphedGuidedStep:
         if self._ir_host is not None:
             ir = self.op.generate_impulse_response(ir_length=self.op.ir_length, decay_factor=self.op.decay_factor)
             self.op.last_ir = ir
-            self._ir_host.copy_(ir.reshape(-1))
-            self._ir_dev.copy_(self._ir_host, non_blocking=True)
+            k = self._ir_turn = (self._ir_turn + 1) % len(self._ir_host)
+            if self._ir_event[k] is not None:
+                self._ir_event[k].synchronize()  # its previous upload (4 steps ago) has executed: normally long done
+            self._ir_host[k].copy_(ir.reshape(-1))
+            # a kernel reads the pinned row over PCIe: a copy-engine transfer here would queue behind the bulk latent
+            # uploads / downloads of HostPipelinedStep and stall the compute stream at the start of every step
+            from . import _lib
+            _lib.call("dm_copy_f32", self._ir_dev.data_ptr(), self._ir_host[k].data_ptr(), self._ir_dev.numel(),
+                      torch.cuda.current_stream(self._ir_dev.device).cuda_stream)
+            ev = self._ir_event[k] = self._ir_event[k] or torch.cuda.Event()
+            ev.record()
 
-    def replay_in_place(self, timestep, generator=None, variance_noise=None):
+    def replay_in_place(self, timestep, generator=None, variance_noise=None, prepared_event=None):
         """Replay on whatever the caller has already put into the static inputs `self.x` / `self.e` (e.g. uploaded
-        straight from pinned host memory); returns the static output object, valid until the next replay."""
+        straight from pinned host memory); returns the static output object, valid until the next replay.
+        `prepared_event`: recorded after the step's small host-to-device transfers (coefficients, impulse response) and
+        before the graph launch."""
         self._prepare(int(timestep), generator, variance_noise)
+        if prepared_event is not None:
+            prepared_event.record()
         self.graph.replay()
         return self.out
 
@@ -164,6 +182,7 @@ class HostPipelinedStep:
             self.loss_st = [torch.zeros(graphed.B, device=dev, dtype=torch.float32) for _ in range(2)]
         ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]  # noqa: E731
         self.uploaded, self.slot_free, self.computed, self.downloaded = ev(), ev(), ev(), ev()
+        self.prepared = torch.cuda.Event()  # the last step's own small transfers are through (see prefetch)
         self.n_up = self.n_run = 0
         self.bytes_up = 2 * graphed.x.numel() * graphed.x.element_size()
         self.bytes_down = graphed.x.numel() * graphed.x.element_size() + graphed.B * 4
@@ -176,6 +195,11 @@ class HostPipelinedStep:
         k = self.n_up % 2
         if after is not None:
             self.up.wait_event(after)
+        if self.direct and self.n_run > 0:
+            # bulk uploads start only once the step issued last has its own few-KB transfers (coefficients, impulse
+            # response) behind it: on the PCIe link those would otherwise wait tens of microseconds behind 4 MB of
+            # latents at the very start of the step
+            self.up.wait_event(self.prepared)
         if self.n_up >= 2:
             self.up.wait_event(self.slot_free[k])  # the step that last used this slot has consumed it
         with torch.cuda.stream(self.up):
@@ -195,7 +219,8 @@ class HostPipelinedStep:
         if self.n_run >= 2:
             cur.wait_event(self.downloaded[k])  # this slot's previous results have reached the host
         if self.direct:
-            out = self.g[k].replay_in_place(timestep, generator=generator, variance_noise=variance_noise)
+            out = self.g[k].replay_in_place(timestep, generator=generator, variance_noise=variance_noise,
+                                            prepared_event=self.prepared)
             prev_src = out.prev_sample
             loss_src = None if out.loss_per_clip is None else out.loss_per_clip.reshape(-1)
         else:

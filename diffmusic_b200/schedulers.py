@@ -138,7 +138,7 @@ class _GuidedBase(DDIMBase):
     #: "always" = exactly one z per step, independent of eta (DSG/DiffMusic, scheduling_dsg.py:215-220)
     noise_mode = "eta"
 
-    def draw_step_noise(self, eta, generator, variance_noise, model_output):
+    def draw_step_noise(self, eta, generator, variance_noise, model_output, out=None):
         """All RNG consumption of one step, in the reference's order, done up front (the values do not depend on
         where in the step they are drawn; only the per-generator order matters and is kept):
           DDIM/DPS/MPGD, eta > 0: the diffusers base step draws one tensor the reference discards
@@ -147,7 +147,7 @@ class _GuidedBase(DDIMBase):
         Returns z as fp32 (or None)."""
         shape, dev, dt = model_output.shape, model_output.device, model_output.dtype
         if self.noise_mode == "always":
-            return self._randn_f32(shape, generator, dev, dt)
+            return self._randn_f32(shape, generator, dev, dt, out)
         if not eta > 0:
             return None
         if variance_noise is not None and generator is not None:
@@ -157,13 +157,14 @@ class _GuidedBase(DDIMBase):
             skip_randn(shape, generator, device=dev, dtype=dt)  # base-step draw, discarded by the reference
             if isinstance(self, DDIMScheduler):
                 return None
-            return self._randn_f32(shape, generator, dev, dt)
+            return self._randn_f32(shape, generator, dev, dt, out)
         return variance_noise.detach().float().contiguous()
 
     @staticmethod
-    def _randn_f32(shape, generator, dev, dt):
-        """the step noise as fp32: per-clip generator lists in one launch (ddim_base.randn_clips_f32), else torch"""
-        z = randn_clips_f32(shape, generator, dev, dt)
+    def _randn_f32(shape, generator, dev, dt, out=None):
+        """the step noise as fp32 (written into `out` when given and possible): per-clip generator lists in one launch
+        (ddim_base.randn_clips_f32), else torch"""
+        z = randn_clips_f32(shape, generator, dev, dt, out=out)
         if z is None:
             z = randn_tensor(shape, generator=generator, device=dev, dtype=dt).float().contiguous()
         return z

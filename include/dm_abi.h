@@ -209,6 +209,11 @@ int dm_rir_adjoint(const float* ybar, int pad, long long Ly, int B, const float*
 int dm_mask_apply(const float* x, long long x_bstride, long long L, int B, const float* mask, float* y,
                   dm_stream_t stream);
 
+/* dst[i] = src[i] by a kernel; src may be PINNED HOST memory (read over PCIe through unified addressing).  For the
+ * per-step impulse response of the dereverberation operator (operator.py:238-242, 20 KB drawn on the host): a copy-engine
+ * transfer on the compute stream would queue behind the bulk latent uploads / downloads of a pipelined loop. */
+int dm_copy_f32(float* dst, const float* src, long long n, dm_stream_t stream);
+
 /* y += sigma * noise  (GaussianNoise.forward, noise.py:13-18, with the torch-drawn noise as an input) */
 int dm_add_scaled(float* y, const float* noise, float sigma, long long n, dm_stream_t stream);
 
