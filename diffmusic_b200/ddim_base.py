@@ -204,7 +204,7 @@ def randn_clips_f32(shape, generator, device=None, dtype=None, out=None):
     elif out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != B * n or out.device != device:
         raise ValueError("randn_clips_f32: `out` must be a contiguous fp32 tensor of the requested shape")
     _lib.call("dm_randn_clips", seeds, offs, B, n, _lib.IO_DTYPES[dtype or torch.get_default_dtype()], out.data_ptr(),
-              torch.cuda.current_stream(device).cuda_stream)
+              _lib.stream(device))
     inc = _offset_increment(n, device)
     for g, o in zip(gens, offsets):
         g.set_offset(o + inc)

@@ -105,7 +105,7 @@ class GraphedGuidedStep:
             # uploads / downloads of HostPipelinedStep and stall the compute stream at the start of every step
             from . import _lib
             _lib.call("dm_copy_f32", self._ir_dev.data_ptr(), self._ir_host[k].data_ptr(), self._ir_dev.numel(),
-                      torch.cuda.current_stream(self._ir_dev.device).cuda_stream)
+                      _lib.stream(self._ir_dev.device))
             ev = self._ir_event[k] = self._ir_event[k] or torch.cuda.Event()
             ev.record()
 
