@@ -140,6 +140,8 @@ def _clip_generators(shape, generator, device, dtype, layout):
         return None
     if device.type != "cuda" or (layout not in (None, torch.strided)):
         return None
+    if device.index is not None and device.index != torch.cuda.current_device():
+        return None  # the kernel launches on the current device (one process per GPU is the deployment model)
     if (dtype or torch.get_default_dtype()) not in _lib.IO_DTYPES:
         return None
     for g in generator:
