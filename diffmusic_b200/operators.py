@@ -97,6 +97,9 @@ def _frames_per_tile(B, T, device):
     forced = os.environ.get("DM_STFT_FRAMES_PER_TILE")
     if forced:
         return max(6, min(22, int(forced)))  # > 15: one CTA per SM
+    key = (B, T, str(device))
+    if key in _NF_CACHE:
+        return _NF_CACHE[key]
     slots = 2 * torch.cuda.get_device_properties(device).multi_processor_count
     best, best_cost = 6, float("inf")
     for nf in range(6, 16):
@@ -104,7 +107,11 @@ def _frames_per_tile(B, T, device):
         cost = math.ceil(ctas / slots) * (math.ceil(nf / 8) + 0.35)
         if cost <= best_cost + 1e-9:
             best, best_cost = nf, min(cost, best_cost)
+    _NF_CACHE[key] = best
     return best
+
+
+_NF_CACHE = {}
 
 
 class BaseOperator:

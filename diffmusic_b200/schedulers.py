@@ -41,6 +41,9 @@ def _f(t):
     return float(t.item()) if isinstance(t, torch.Tensor) else float(t)
 
 
+_LEAF_SCALE_CACHE = {}
+
+
 class _GuidedBase(DDIMBase):
     """Shared constructor (scheduling_dps.py:22-61, identical in all five files) and helpers."""
 
@@ -132,7 +135,11 @@ class _GuidedBase(DDIMBase):
     @staticmethod
     def _leaf_scale(vae):
         """1 / vae.config.scaling_factor as the fp32 value torch multiplies by (scheduling_dps.py:195-197)."""
-        return float(torch.tensor(1 / vae.config.scaling_factor, dtype=torch.float32))
+        sf = vae.config.scaling_factor
+        v = _LEAF_SCALE_CACHE.get(sf)
+        if v is None:
+            v = _LEAF_SCALE_CACHE[sf] = float(torch.tensor(1 / sf, dtype=torch.float32))
+        return v
 
     #: which noise the step consumes: "eta" = base-step draw (discarded) + own z when eta > 0 (DDIM/DPS/MPGD);
     #: "always" = exactly one z per step, independent of eta (DSG/DiffMusic, scheduling_dsg.py:215-220)
