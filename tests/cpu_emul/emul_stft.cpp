@@ -2,6 +2,7 @@
 // TEST INFRASTRUCTURE: compiled with g++ by tests/test_cpu_emulation.py; never shipped, never on the product path.
 // Every phase is run for all 64 "threads" of a frame group before the next phase starts (= the GPU barrier).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -200,6 +201,45 @@ void emul_stft_guidance_pair(const EmulTables* e, int mode, int clamp, const flo
     if (mode == 0) run_pair<kModeMelDb>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
     else if (mode == 1) run_pair<kModePhaseMel>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
     else run_pair<kModePhaseWav>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
+}
+
+// LogSpectralDistance frames (csrc/metrics.cu lsd_pair_kernel): frame t of the reference clip rides as frame A, frame t of
+// the estimate as frame B of ONE pair FFT; per-frame distance from the magnitudes side by side in P.
+void emul_lsd_frames(const EmulTables* e, const float* ref, const float* est, long long L, int hop, int pad_reflect,
+                     float eps, float* out) {
+    StftTables t{e->window, reinterpret_cast<const cf*>(e->tw512), reinterpret_cast<const cf*>(e->w1024),
+                 e->mel_kstart, e->mel_klen, e->mel_w, e->mel_wstride, e->bin_m0, e->bin_w0, e->bin_w1};
+    const long long T = 1 + L / hop;
+    std::vector<float> buf(kPairSmemFloats + 8, 0.f), fa(kNfft), fb(kNfft);
+    float* base = buf.data();
+    while (reinterpret_cast<uintptr_t>(base) & 15) ++base;
+    PairSmem s;
+    s.a = reinterpret_cast<c2*>(base);
+    s.b = reinterpret_cast<c2*>(base + 4 * kH);
+    std::vector<PairConsts> pc(64);
+    std::vector<PairX> px(64);
+    for (int tid = 0; tid < 64; ++tid) load_pair_consts(tid, t, pc[tid]);
+    auto sanitize = [](float v) { return v != v ? 0.f : (std::isinf(v) ? (v > 0 ? 1.f : -1.f) : v); };
+    for (long long f = 0; f < T; ++f) {
+        for (int n = 0; n < kNfft; ++n) {
+            long long j = f * hop + n - kNfft / 2;
+            bool inside = j >= 0 && j < L;
+            if (!inside && pad_reflect) { j = reflect_src(f * hop + n, L); inside = true; }
+            fa[n] = inside ? ref[j] : 0.f;
+            fb[n] = inside ? sanitize(est[j]) : 0.f;
+        }
+        for (int tid = 0; tid < 64; ++tid) pair_fwd_pass1(tid, fa.data(), fb.data(), t.window, s);
+        for (int tid = 0; tid < 64; ++tid) pair_fwd_pass2(tid, pc[tid], s);
+        for (int tid = 0; tid < 64; ++tid) pair_fwd_pass3(tid, pc[tid], s);
+        for (int tid = 0; tid < 64; ++tid) pair_unpack<kModePhaseWav>(tid, pc[tid], s, px[tid]);
+        const f2* P = pair_energy(s);
+        float acc = 0.f;
+        for (int k = 0; k < kBins; ++k) {
+            const float d = log10f(P[k].x + eps) - log10f(P[k].y + eps);
+            acc += d * d;
+        }
+        out[f] = sqrtf(acc / kBins);
+    }
 }
 
 // Bank-conflict audit of the cell swizzle: a 128-bit shared access is served per quarter-warp (8 consecutive lanes),

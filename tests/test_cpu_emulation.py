@@ -271,6 +271,25 @@ def test_register_window_scale2_resample(emul, L):
     assert rel_l2(gotb, 0.25 * gx[0]) < 2e-6
 
 
+@pytest.mark.parametrize("hop,pad", [(160, "constant"), (512, "constant"), (512, "reflect")])
+def test_lsd_frames_through_the_pair_pipeline(emul, hop, pad):
+    """LogSpectralDistance per-frame distances through the frame-pair device code (reference clip = frame A, estimate =
+    frame B of one FFT) against the restated lsd.py, incl. the nan_to_num sanitising of the estimate."""
+    from oracle import metrics as om
+    L = 6000 + 37
+    bg = stubs.synth_clips(1, L).numpy()
+    ev = (stubs.synth_clips(1, L, first=7) * 0.8).numpy()
+    ev[0, 100] = np.nan
+    ev[0, 2000] = np.inf
+    t, keep = _tables(tables.hann_window())
+    T = 1 + L // hop
+    out = np.zeros(T, np.float32)
+    emul.emul_lsd_frames(C.byref(t), _ptr(bg[0].copy()), _ptr(ev[0].copy()), C.c_longlong(L), hop,
+                         int(pad == "reflect"), C.c_float(1e-10), _ptr(out))
+    want = om.lsd_score(bg, ev, 1024, hop, 1e-10, output_mean=False, pad_mode=pad)
+    assert abs(out.mean() - float(want[0])) <= 2e-5 * float(want[0])
+
+
 def test_pair_swizzle_is_conflict_free(emul):
     """cell swizzle of the frame-pair pipeline: closed-form addresses equal sw4(logical index) and every 128-bit access
     pattern of the FFT passes / unpack hits 8 distinct 16-byte bank groups per quarter-warp."""
