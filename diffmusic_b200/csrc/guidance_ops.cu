@@ -59,14 +59,39 @@ __global__ void __launch_bounds__(kEwThreads) fold_adjoint_kernel(const float* _
                                                                   float* __restrict__ loss) {
     __shared__ float scratch[2];
     const int b = blockIdx.y;
-    const float l = clip_loss(partial + (long long)b * ntiles, ntiles, scratch);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[b] = l;
-    if (dwav == nullptr) return;  // loss only
-    const float sc = inv_loss(l);
     const float* yb = ybar + (long long)b * (Ly + 2 * pad);
     void* ob = wave_row(dwav, dwav_io, (long long)b * dwav_bstride);
     const long long lo = (long long)blockIdx.x * (kEwThreads * 8);
     const long long hi = min(Ly, lo + kEwThreads * 8);
+    // interior chunks (no reflected samples fold into them) of 16-byte aligned fp32 rows: 128-bit loads and stores, the
+    // loads issued BEFORE the per-clip scale is reduced from the partial sums, so their latency hides behind it
+    const bool fast = dwav != nullptr && dwav_io == DM_IO_F32 && hi - lo == kEwThreads * 8 &&
+                      (pad == 0 || (lo >= 513 && hi <= Ly - 513)) && ((Ly + 2 * pad) & 3) == 0 &&
+                      (dwav_bstride & 3) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(ybar) | reinterpret_cast<uintptr_t>(dwav) |
+                        reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (fast) {
+        const float4* src = reinterpret_cast<const float4*>(yb + pad + lo);
+        v0 = src[threadIdx.x];
+        v1 = src[threadIdx.x + kEwThreads];
+        if (mask) {
+            const float4 m0 = __ldg(reinterpret_cast<const float4*>(mask + lo) + threadIdx.x);
+            const float4 m1 = __ldg(reinterpret_cast<const float4*>(mask + lo) + threadIdx.x + kEwThreads);
+            v0.x *= m0.x, v0.y *= m0.y, v0.z *= m0.z, v0.w *= m0.w;
+            v1.x *= m1.x, v1.y *= m1.y, v1.z *= m1.z, v1.w *= m1.w;
+        }
+    }
+    const float l = clip_loss(partial + (long long)b * ntiles, ntiles, scratch);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[b] = l;
+    if (dwav == nullptr) return;  // loss only
+    const float sc = inv_loss(l);
+    if (fast) {
+        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(ob) + lo);
+        dst[threadIdx.x] = make_float4(v0.x * sc, v0.y * sc, v0.z * sc, v0.w * sc);
+        dst[threadIdx.x + kEwThreads] = make_float4(v1.x * sc, v1.y * sc, v1.z * sc, v1.w * sc);
+        return;
+    }
     for (long long j = lo + threadIdx.x; j < hi; j += kEwThreads) {
         float v = ybar_at(yb, pad, j, Ly) * sc;
         if (mask) v *= __ldg(mask + j);
