@@ -1,0 +1,199 @@
+// mel_spectrogram_to_waveform_with_phase (diffmusic/pipelines/pipeline_musicldm.py:263-301, plpeline_audioldm2.py:681;
+// SURVEY.md 8f rank 3): mel -> torchaudio InverseMelScale -> times exp(i * original_phase) -> torch.istft -> clip / pad.
+//
+//   * InverseMelScale (driver "gels", filterbank 513 x 64 of full column rank) is the minimum-norm least-squares solution
+//     followed by relu: a FIXED 513 x 64 matrix W = fb (fb^T fb)^-1 applied to every frame.  The host computes W once in
+//     fp64 (tables.py); here it is a per-tile product out of L2 with the mel tile broadcast from shared memory.  The
+//     (B, 513, T) linear spectrogram and the complex spectrogram the reference materialises are never written.
+//   * torch.istft(n_fft 1024, hop, win 1024, window=None -> rectangular, center=True): irfft of every frame, overlap-add,
+//     division by the window envelope (= the number of frames covering a sample), trimmed by 512 on both sides; the
+//     frame-pair inverse FFT of stft_pair.cuh carries two frames per 64-thread group, the overlap-add runs in shared
+//     memory per tile and tiles are joined with atomics (<= 2 tiles meet in a sample, so the sum is order-independent).
+#include "dm_common.cuh"
+#include "stft_pair.cuh"
+
+namespace dm {
+
+constexpr int kIstftThreads = 256;
+constexpr int kIstftGroups = kIstftThreads / kGroupThreads;
+constexpr int kIstftFrames = 8;                  // frames per tile = one round of 4 groups x 2 frames
+constexpr int kSpecLd = 516;                     // cells per staged frame pair (513 bins, padded)
+
+__device__ __forceinline__ void istft_group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kGroupThreads));
+}
+
+struct IstftParams {
+    StftTables tab;
+    const float* winv_t;  // (64, 513): W^T
+    const float* mel;
+    long long mel_bstride, mel_mstride, mel_tstride;
+    const float* phase;   // (513, T) per clip (phase_bstride) or shared (0)
+    long long phase_bstride, T, ola_len;
+    int hop;
+    float* ola;           // (B, ola_len) zeroed
+};
+
+__global__ void __launch_bounds__(kIstftThreads, 2) istft_pair_kernel(const IstftParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, g = tid / kGroupThreads, gt = tid % kGroupThreads;
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const long long f0 = (long long)tile * kIstftFrames;
+    const int nfr = (int)min((long long)kIstftFrames, p.T - f0);
+    const int span = (nfr - 1) * p.hop + kNfft;
+    const int span_alloc = ((kIstftFrames - 1) * p.hop + kNfft + 3) & ~3;
+    const int hop2 = p.hop >> 1;
+
+    c2* spec = reinterpret_cast<c2*>(smem);                        // [kIstftFrames / 2][kSpecLd]
+    float* grp = smem + (kIstftFrames / 2) * kSpecLd * 4;          // [kIstftGroups][kPairSmemFloats]
+    float* acc = grp + kIstftGroups * kPairSmemFloats;             // [span_alloc]
+    float* mel_s = acc + span_alloc;                               // [64][kIstftFrames]
+    PairSmem s;
+    s.a = reinterpret_cast<c2*>(grp + g * kPairSmemFloats);
+    s.b = reinterpret_cast<c2*>(grp + g * kPairSmemFloats + 4 * kH);
+    PairConsts pc;
+    load_pair_consts(gt, p.tab, pc);
+
+    // ---- stage the mel tile (frames past the end read as zero) and clear the overlap-add span ----
+    const float* mb = p.mel + (long long)b * p.mel_bstride;
+    for (int i = tid; i < kMels * kIstftFrames; i += kIstftThreads) {
+        const int m = p.mel_mstride == 1 ? i % kMels : i / kIstftFrames;  // run along the contiguous axis
+        const int f = p.mel_mstride == 1 ? i / kMels : i % kIstftFrames;
+        mel_s[m * kIstftFrames + f] = f < nfr ? __ldg(mb + m * p.mel_mstride + (f0 + f) * p.mel_tstride) : 0.f;
+    }
+    for (int i = tid; i < span_alloc / 4; i += kIstftThreads)
+        reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+
+    // ---- linear magnitude of every bin of the tile: relu(W mel), times exp(i phase) -> pair-major spectrum cells ----
+    const float* phb = p.phase + (long long)b * p.phase_bstride;
+    for (int k = tid; k < kBins; k += kIstftThreads) {
+        float lin[kIstftFrames];
+#pragma unroll
+        for (int f = 0; f < kIstftFrames; ++f) lin[f] = 0.f;
+        const float* w = p.winv_t + k;
+#pragma unroll 4
+        for (int m = 0; m < kMels; ++m) {
+            const float wm = __ldg(w + m * kBins);
+            const float4 a = reinterpret_cast<const float4*>(mel_s + m * kIstftFrames)[0];
+            const float4 c = reinterpret_cast<const float4*>(mel_s + m * kIstftFrames)[1];
+            lin[0] = fmaf(wm, a.x, lin[0]);
+            lin[1] = fmaf(wm, a.y, lin[1]);
+            lin[2] = fmaf(wm, a.z, lin[2]);
+            lin[3] = fmaf(wm, a.w, lin[3]);
+            lin[4] = fmaf(wm, c.x, lin[4]);
+            lin[5] = fmaf(wm, c.y, lin[5]);
+            lin[6] = fmaf(wm, c.z, lin[6]);
+            lin[7] = fmaf(wm, c.w, lin[7]);
+        }
+        static_assert(kIstftFrames == 8, "the tile product is written for 8 frames");
+        const float* ph = phb + (long long)k * p.T + f0;
+        float xr[kIstftFrames], xi[kIstftFrames];
+#pragma unroll
+        for (int f = 0; f < kIstftFrames; ++f) {
+            const float mag = lin[f] < 0.f ? 0.f : lin[f];  // torch.relu: NaN stays NaN
+            float sn = 0.f, cs = 0.f;
+            if (f < nfr) sincosf(__ldg(ph + f), &sn, &cs);
+            xr[f] = mag * cs;
+            xi[f] = mag * sn;
+        }
+#pragma unroll
+        for (int q = 0; q < kIstftFrames / 2; ++q)
+            spec[q * kSpecLd + k] = c2{xr[2 * q], xi[2 * q], xr[2 * q + 1], xi[2 * q + 1]};
+    }
+    __syncthreads();
+
+    // ---- inverse FFT of the group's frame pair, then the overlap-add group by group ----
+    const int fa = 2 * g;
+    const bool active = fa < nfr, active_b = fa + 1 < nfr;  // a missing frame B has a zero spectrum and is dropped
+    cf va[8], vb[8];
+    if (active) {
+        PairX x;
+        pair_load_spectrum(gt, spec + g * kSpecLd, x);
+        pair_pack_spectrum(gt, pc, s, x);
+        istft_group_sync(g);
+        pair_inv_pass1(gt, s);
+        istft_group_sync(g);
+        pair_inv_pass2(gt, pc, s);
+        istft_group_sync(g);
+        pair_inv_pass3(gt, pc, s, va, vb);
+    }
+    f2* acc2 = reinterpret_cast<f2*>(acc);
+    for (int turn = 0; turn < kIstftGroups; ++turn) {
+        if (turn == g && active) {
+            pair_ola_add_rect(gt, va, acc2 + fa * hop2);
+            istft_group_sync(g);  // frame B overlaps frame A
+            if (active_b) pair_ola_add_rect(gt, vb, acc2 + (fa + 1) * hop2);
+        }
+        __syncthreads();
+    }
+    float* ob = p.ola + (long long)b * p.ola_len + f0 * p.hop;
+    for (int i = tid; i < span; i += kIstftThreads) atomicAdd(ob + i, acc[i]);
+}
+
+// out[b, j] = ola[b, j + 512] / 1024 / (frames covering padded sample j + 512) for j < hop (T - 1), zero padding after
+__global__ void __launch_bounds__(256) istft_finish_kernel(const float* __restrict__ ola, long long ola_len, long long T,
+                                                           int hop, float* __restrict__ out, long long out_len) {
+    const int b = blockIdx.y;
+    const long long n_valid = (long long)hop * (T - 1);
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < out_len;
+         j += (long long)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (j < n_valid) {
+            const long long i = j + kNfft / 2;
+            const long long t_hi = min(T - 1, i / hop);
+            const long long t_lo = i >= kNfft ? (i - kNfft) / hop + 1 : 0;
+            v = ola[(long long)b * ola_len + i] * (1.0f / kNfft) / (float)(t_hi - t_lo + 1);
+        }
+        out[(long long)b * out_len + j] = v;
+    }
+}
+
+static size_t istft_smem_bytes(int hop) {
+    size_t span = ((size_t)(kIstftFrames - 1) * hop + kNfft + 3) & ~(size_t)3;
+    return ((size_t)(kIstftFrames / 2) * kSpecLd * 4 + (size_t)kIstftGroups * kPairSmemFloats + span +
+            (size_t)kMels * kIstftFrames) * sizeof(float);
+}
+
+}  // namespace dm
+
+using namespace dm;
+
+extern "C" long long dm_istft_workspace_floats(int B, long long T, int hop) {
+    if (B <= 0 || T <= 0 || hop <= 0) return 0;
+    return (long long)B * ((long long)hop * (T - 1) + kNfft);
+}
+
+extern "C" int dm_istft_mel_phase(const dm_stft_tables* tab, const float* winv_t, const float* mel,
+                                  long long mel_bstride, long long mel_mstride, long long mel_tstride,
+                                  const float* phase, long long phase_bstride, int B, long long T, int hop, float* ola,
+                                  float* out, long long out_len, dm_stream_t stream) {
+    DM_REQUIRE(tab && winv_t && mel && phase && ola && out && B > 0 && T > 0 && out_len > 0);
+    DM_REQUIRE(hop > 0 && hop <= kNfft && (hop & 1) == 0);
+    IstftParams p;
+    p.tab = StftTables{tab->window, reinterpret_cast<const cf*>(tab->tw512), reinterpret_cast<const cf*>(tab->w1024),
+                       tab->mel_kstart, tab->mel_klen, tab->mel_w, tab->mel_wstride, tab->bin_m0, tab->bin_w0,
+                       tab->bin_w1};
+    p.winv_t = winv_t;
+    p.mel = mel;
+    p.mel_bstride = mel_bstride;
+    p.mel_mstride = mel_mstride;
+    p.mel_tstride = mel_tstride;
+    p.phase = phase;
+    p.phase_bstride = phase_bstride;
+    p.T = T;
+    p.hop = hop;
+    p.ola_len = (long long)hop * (T - 1) + kNfft;
+    p.ola = ola;
+    DM_CUDA(cudaMemsetAsync(ola, 0, sizeof(float) * (size_t)B * (size_t)p.ola_len, as_stream(stream)));
+    const size_t smem = istft_smem_bytes(hop);
+    if (smem > 227 * 1024) return fail(DM_ERR_UNSUPPORTED, "%s: tile needs %zu B of shared memory", __func__, smem);
+    DM_SMEM_ONCE(istft_pair_kernel, smem);
+    const dim3 grid((unsigned)((T + kIstftFrames - 1) / kIstftFrames), B);
+    istft_pair_kernel<<<grid, kIstftThreads, smem, as_stream(stream)>>>(p);
+    DM_LAUNCHED();
+    const unsigned fx = (unsigned)min((out_len + 255) / 256, 1184LL);
+    istft_finish_kernel<<<dim3(fx, B), 256, 0, as_stream(stream)>>>(ola, p.ola_len, T, hop, out, out_len);
+    DM_LAUNCHED();
+    return DM_OK;
+}

@@ -312,6 +312,56 @@ DM_HD void pair_pack(int j, const PairConsts& c, const PairBinTab& t, PairSmem s
     }
 }
 
+// ---- inverse STFT (torch.istft, istft.cu): the one-sided spectrum X of the owned bins (x, same ownership as the forward
+// unpack) -> Hermitian-packed Z cells (-> a), scaled so that the unnormalised inverse passes return 1024 * irfft(X):
+// interior bins enter as they are, only the real parts of DC / Nyquist act (as in irfft), Z[256] = 2 conj(X[256]).
+DM_HD void pair_pack_spectrum(int j, const PairConsts& c, PairSmem s, const PairX& x) {
+    c2* lo = s.a + sw4(j);
+    c2* hi = s.a + sw4((kH - j) & (kH - 1));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = j + 64 * i;
+        if (k == 0) {
+            const float y0a = x.lo[0][0].x, yha = x.hi[0][0].x, y0b = x.lo[0][1].x, yhb = x.hi[0][1].x;
+            s.a[0] = c2{y0a + yha, y0a - yha, y0b + yhb, y0b - yhb};
+            s.a[kH / 2] = c2{2.f * x.q[0].x, -2.f * x.q[0].y, 2.f * x.q[1].x, -2.f * x.q[1].y};
+        } else {
+            cf z[2][2];
+#pragma unroll
+            for (int f = 0; f < 2; ++f) irfft_pack_pair(x.lo[i][f], x.hi[i][f], c.wu[i], z[f][0], z[f][1]);
+            lo[64 * i] = c2{z[0][0].x, z[0][0].y, z[1][0].x, z[1][0].y};
+            c2* pc = (j == 0) ? (s.a + sw4(kH - k)) : (hi - 64 * i);
+            *pc = c2{z[0][1].x, z[0][1].y, z[1][1].x, z[1][1].y};
+        }
+    }
+}
+// Spectrum cells staged pair-major, spec[k] = (X_A[k], X_B[k]) for k = 0..512, into the owned-bin registers.
+DM_HD void pair_load_spectrum(int j, const c2* __restrict__ spec, PairX& x) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = j + 64 * i;
+        const c2 a = spec[k], b = spec[kH - k];  // k = 0: bins 0 and 512
+        x.lo[i][0] = cf{a.ax, a.ay};
+        x.lo[i][1] = cf{a.bx, a.by};
+        x.hi[i][0] = cf{b.ax, b.ay};
+        x.hi[i][1] = cf{b.bx, b.by};
+    }
+    const c2 q = spec[kH / 2];
+    x.q[0] = cf{q.ax, q.ay};
+    x.q[1] = cf{q.bx, q.by};
+}
+// rectangular-window overlap-add (torch.istft with window=None)
+DM_HD void pair_ola_add_rect(int j, const cf (&v)[8], f2* acc2) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int h = j + 64 * q;
+        f2 a = acc2[h];
+        a.x += v[q].x;
+        a.y += v[q].y;
+        acc2[h] = a;
+    }
+}
+
 // ---- inverse FFT of both frames: a -> b -> a -> registers, then windowed overlap-add from the registers ----
 DM_HD void pair_inv_pass1(int j, PairSmem s) {
     cf va[8], vb[8];

@@ -38,6 +38,15 @@ def mel_filterbank(sample_rate=16000):
                                                  "htk")
 
 
+def inverse_mel_matrix(sample_rate=16000):
+    """(64, 513) fp32 = W^T with W = fb (fb^T fb)^-1: torchaudio InverseMelScale(n_stft=513, n_mels=64, sample_rate)
+    solves `lstsq(fb^T, mel, driver="gels")` per frame; fb has full column rank (cond(fb^T fb) = 32), so the solution of
+    the under-determined system is the minimum-norm one, W mel.  Computed in float64 from the fp32 filterbank."""
+    fb = mel_filterbank(sample_rate).double()
+    w = fb @ torch.linalg.inv(fb.T @ fb)
+    return w.T.contiguous().float()
+
+
 def twiddles(n):
     """exp(-2 pi i m / n), m < n, computed in float64, stored as interleaved fp32 (n, 2)."""
     m = np.arange(n, dtype=np.float64)

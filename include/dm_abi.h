@@ -306,6 +306,20 @@ long long dm_mse_num_chunks(long long n);
 int dm_mse(const float* ref, long long ref_bstride, const float* est, long long est_bstride, long long n, int B,
            double* partial, float* out, dm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * mel_spectrogram_to_waveform_with_phase (diffmusic/pipelines/pipeline_musicldm.py:263-301, plpeline_audioldm2.py:681):
+ * torchaudio InverseMelScale(n_stft 513, n_mels 64, sr 16000) -- the minimum-norm least-squares solution, i.e. the fixed
+ * matrix W = fb (fb^T fb)^-1, then relu -- times exp(i * phase), then torch.istft(n_fft 1024, hop, win 1024, window=None,
+ * center=True), clipped / zero-padded to out_len.
+ * mel: element (b, m, t) at mel[b * mel_bstride + m * mel_mstride + t * mel_tstride] (the pipeline's (B, 1, T, 64) tensor
+ * is read in place: mstride 1, tstride 64); phase: (513, T) shared by the batch (phase_bstride 0) or (B, 513, T);
+ * winv_t: (64, 513) = W^T; ola: dm_istft_workspace_floats(B, T, hop) floats of device scratch (zeroed by the call);
+ * out: (B, out_len), out[b, j] = 0 for j >= hop (T - 1).  hop even. */
+long long dm_istft_workspace_floats(int B, long long T, int hop);
+int dm_istft_mel_phase(const dm_stft_tables* tab, const float* winv_t, const float* mel, long long mel_bstride,
+                       long long mel_mstride, long long mel_tstride, const float* phase, long long phase_bstride, int B,
+                       long long T, int hop, float* ola, float* out, long long out_len, dm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

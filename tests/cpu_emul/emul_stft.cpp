@@ -242,6 +242,74 @@ void emul_lsd_frames(const EmulTables* e, const float* ref, const float* est, lo
     }
 }
 
+// mel_spectrogram_to_waveform_with_phase (csrc/istft.cu): relu(W mel) * exp(i phase) per bin -> pair-major spectrum cells ->
+// pair_pack_spectrum -> the three inverse passes -> rectangular overlap-add -> envelope division and trimming.
+// mel: (64, T), phase: (513, T), winv_t: (64, 513), out: (out_len).
+void emul_istft_mel_phase(const EmulTables* e, const float* winv_t, const float* mel, const float* phase, long long T,
+                          int hop, float* out, long long out_len) {
+    StftTables t{e->window, reinterpret_cast<const cf*>(e->tw512), reinterpret_cast<const cf*>(e->w1024),
+                 e->mel_kstart, e->mel_klen, e->mel_w, e->mel_wstride, e->bin_m0, e->bin_w0, e->bin_w1};
+    std::vector<float> buf(kPairSmemFloats + 8, 0.f), cells(4 * 516 + 8, 0.f);
+    float* base = buf.data();
+    while (reinterpret_cast<uintptr_t>(base) & 15) ++base;
+    float* cb = cells.data();
+    while (reinterpret_cast<uintptr_t>(cb) & 15) ++cb;
+    PairSmem s;
+    s.a = reinterpret_cast<c2*>(base);
+    s.b = reinterpret_cast<c2*>(base + 4 * kH);
+    c2* spec = reinterpret_cast<c2*>(cb);
+    std::vector<PairConsts> pc(64);
+    std::vector<PairX> px(64);
+    for (int tid = 0; tid < 64; ++tid) load_pair_consts(tid, t, pc[tid]);
+    const long long ola_len = (long long)hop * (T - 1) + kNfft;
+    std::vector<float> ola(ola_len, 0.f);
+    for (long long fa = 0; fa < T; fa += 2) {
+        const bool has_b = fa + 1 < T;
+        for (int k = 0; k < kBins; ++k) {
+            float lin[2] = {0.f, 0.f};
+            for (int m = 0; m < kMels; ++m) {
+                lin[0] = fmaf(winv_t[m * kBins + k], mel[m * T + fa], lin[0]);
+                if (has_b) lin[1] = fmaf(winv_t[m * kBins + k], mel[m * T + fa + 1], lin[1]);
+            }
+            float x[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int f = 0; f < (has_b ? 2 : 1); ++f) {
+                const float mag = lin[f] < 0.f ? 0.f : lin[f];
+                const float ph = phase[k * T + fa + f];
+                x[2 * f] = mag * cosf(ph);
+                x[2 * f + 1] = mag * sinf(ph);
+            }
+            spec[k] = c2{x[0], x[1], x[2], x[3]};
+        }
+        for (int tid = 0; tid < 64; ++tid) pair_load_spectrum(tid, spec, px[tid]);
+        for (int tid = 0; tid < 64; ++tid) pair_pack_spectrum(tid, pc[tid], s, px[tid]);
+        for (int tid = 0; tid < 64; ++tid) pair_inv_pass1(tid, s);
+        for (int tid = 0; tid < 64; ++tid) pair_inv_pass2(tid, pc[tid], s);
+        std::vector<cf> va(64 * 8), vb(64 * 8);
+        for (int tid = 0; tid < 64; ++tid) {
+            cf a[8], b[8];
+            pair_inv_pass3(tid, pc[tid], s, a, b);
+            for (int q = 0; q < 8; ++q) { va[tid * 8 + q] = a[q]; vb[tid * 8 + q] = b[q]; }
+        }
+        for (int f = 0; f < (has_b ? 2 : 1); ++f)
+            for (int tid = 0; tid < 64; ++tid) {
+                cf v[8];
+                for (int q = 0; q < 8; ++q) v[q] = f ? vb[tid * 8 + q] : va[tid * 8 + q];
+                pair_ola_add_rect(tid, v, reinterpret_cast<f2*>(ola.data() + (fa + f) * hop));
+            }
+    }
+    const long long n_valid = (long long)hop * (T - 1);
+    for (long long j = 0; j < out_len; ++j) {
+        float v = 0.f;
+        if (j < n_valid) {
+            const long long i = j + kNfft / 2;
+            const long long t_hi = std::min(T - 1, i / hop);
+            const long long t_lo = i >= kNfft ? (i - kNfft) / hop + 1 : 0;
+            v = ola[i] * (1.0f / kNfft) / (float)(t_hi - t_lo + 1);
+        }
+        out[j] = v;
+    }
+}
+
 // Bank-conflict audit of the cell swizzle: a 128-bit shared access is served per quarter-warp (8 consecutive lanes),
 // conflict-free iff the 8 cells fall into 8 distinct 16-byte bank groups (cell index mod 8).  Returns the number of
 // (pattern, quarter-warp) instances with a conflict, and checks st_c2_addr / the load form against sw4 of the logical index.

@@ -81,3 +81,19 @@ MUSICLDM_SCHED = dict(num_train_timesteps=1000, beta_start=0.0015, beta_end=0.01
                       prediction_type="epsilon", thresholding=False, dynamic_thresholding_ratio=0.995,
                       clip_sample_range=1.0, sample_max_value=1.0, timestep_spacing="leading",
                       rescale_betas_zero_snr=False)  # configs/model/musicldm.yaml:7-22
+
+
+# ---- mel_spectrogram_to_waveform_with_phase cases (tests/golden/make_istft_golden.py, istft.npz) ----
+#: name -> (B, T, phase shared by the batch, seed, original_waveform_length: 0 = as is / clipped / zero-padded)
+ISTFT_CASES = {"b1_t26": (1, 26, True, 11, 0), "b3_t41_own_phase": (3, 41, False, 12, 6000),
+               "b2_t9": (2, 9, True, 13, 2000)}
+
+
+def istft_inputs(name):
+    """mel (B, 1, T, 64) in a dB-like range with negative-going frames (so that the relu of InverseMelScale acts) and
+    phase (1 or B, 513, T) in [-pi, pi)."""
+    B, T, shared, seed, _ = ISTFT_CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    mel = torch.rand(B, 1, T, 64, generator=g) * 6.0 - 1.0
+    phase = (torch.rand(1 if shared else B, 513, T, generator=g) * 2.0 - 1.0) * math.pi
+    return mel, phase

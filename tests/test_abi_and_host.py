@@ -172,3 +172,15 @@ def test_metrics_dropin_and_fadtk_patch():
     assert f.calc_frechet_distance is fad.calc_frechet_distance and f.calc_embd_statistics is fad.calc_embd_statistics
     assert u.calculate_embd_statistics_online is fad.calculate_embd_statistics_online
     assert f.calculate_embd_statistics_online is fad.calculate_embd_statistics_online and len(done) == 4
+
+
+def test_mel_to_waveform_with_phase_has_no_cpu_path():
+    """the export chain validates like the reference call and refuses CPU tensors (no fallback)."""
+    import diffmusic_b200 as dm
+    from diffmusic_b200._lib import DiffMusicB200Error
+    from tests import stubs
+    mel, phase = stubs.istft_inputs("b2_t9")
+    with pytest.raises(DiffMusicB200Error):
+        dm.mel_spectrogram_to_waveform_with_phase(mel, phase)
+    with pytest.raises(NotImplementedError):
+        dm.mel_spectrogram_to_waveform_with_phase(mel, phase, hop_length=161)

@@ -290,6 +290,27 @@ def test_lsd_frames_through_the_pair_pipeline(emul, hop, pad):
     assert abs(out.mean() - float(want[0])) <= 2e-5 * float(want[0])
 
 
+@pytest.mark.parametrize("name", ["b1_t26", "b3_t41_own_phase", "b2_t9"])
+def test_istft_through_the_pair_pipeline(emul, name):
+    """mel_spectrogram_to_waveform_with_phase through the device code of csrc/istft.cu (pair_load_spectrum,
+    pair_pack_spectrum, the inverse passes, rectangular overlap-add, envelope division) against the output of the
+    reference function itself (tests/golden/istft.npz)."""
+    want = np.load(os.path.join(ROOT, "tests", "golden", "istft.npz"))[name]
+    mel, phase = stubs.istft_inputs(name)
+    B, T, shared, _, length = stubs.ISTFT_CASES[name]
+    t, keep = _tables(tables.rect_window())
+    w_t = tables.inverse_mel_matrix(16000).numpy().copy()
+    out_len = want.shape[1]
+    for b in range(B):
+        m = np.ascontiguousarray(mel[b, 0].numpy().T)             # (64, T)
+        ph = np.ascontiguousarray(phase[0 if shared else b].numpy())
+        got = np.zeros(out_len, np.float32)
+        emul.emul_istft_mel_phase(C.byref(t), _ptr(w_t), _ptr(m), _ptr(ph), C.c_longlong(T), 160, _ptr(got),
+                                  C.c_longlong(out_len))
+        assert rel_l2(got, want[b]) < 3e-6
+        assert not got[160 * (T - 1):].any()
+
+
 def test_pair_swizzle_is_conflict_free(emul):
     """cell swizzle of the frame-pair pipeline: closed-form addresses equal sw4(logical index) and every 128-bit access
     pattern of the FFT passes / unpack hits 8 distinct 16-byte bank groups per quarter-warp."""

@@ -459,6 +459,67 @@ def test_log_spectral_distance_vs_reference_formula(hop, pad):
         metrics.LogSpectralDistance(n_fft=2048)
 
 
+@pytest.mark.parametrize("name", ["b1_t26", "b3_t41_own_phase", "b2_t9"])
+def test_mel_to_waveform_with_phase_vs_reference(name):
+    """mel_spectrogram_to_waveform_with_phase through dm_istft_mel_phase against the output of the reference function
+    itself (tests/golden/istft.npz: as-is, clipped and zero-padded lengths; phase shared by the batch or per clip) and
+    the float64 oracle."""
+    import os
+    from diffmusic_b200.istft import mel_spectrogram_to_waveform_with_phase
+    from oracle import istft as oi
+    from tests.conftest import GOLDEN
+    want = np.load(os.path.join(GOLDEN, "istft.npz"))[name]
+    mel, phase = stubs.istft_inputs(name)
+    length = stubs.ISTFT_CASES[name][4]
+    got = mel_spectrogram_to_waveform_with_phase(mel.to(DEV), phase.to(DEV), original_waveform_length=length)
+    assert got.dtype == torch.float32 and tuple(got.shape) == want.shape
+    assert rel_l2(got, want) < 3e-6       # fp32 on both sides
+    ref64 = oi.mel_spectrogram_to_waveform_with_phase(mel.numpy(), phase.numpy(), original_waveform_length=length)
+    assert rel_l2(got, ref64) < 2e-6
+    n = 160 * (stubs.ISTFT_CASES[name][1] - 1)
+    assert not got[:, n:].any()
+    # a (B, T, 64) mel without the channel axis and fp16 inputs (the pipeline runs in fp16) go through the same call
+    again = mel_spectrogram_to_waveform_with_phase(mel[:, 0].to(DEV), phase.to(DEV), original_waveform_length=length)
+    assert torch.equal(again, got)
+    half = mel_spectrogram_to_waveform_with_phase(mel.half().to(DEV), phase.to(DEV), original_waveform_length=length)
+    up = mel_spectrogram_to_waveform_with_phase(mel.half().float().to(DEV), phase.to(DEV),
+                                                original_waveform_length=length)
+    assert torch.equal(half, up)
+
+
+def test_mel_to_waveform_with_phase_full_size():
+    """BASELINE size (16 clips, 1001 frames -> 160 000 samples): two clips against the float64 oracle, every clip through
+    the positive homogeneity of the chain (relu(W (2 mel)) = 2 relu(W mel), and scaling by a power of two commutes with
+    every rounding, so doubling the mel doubles the waveform bit for bit); other hops and a two-frame input go against
+    the oracle."""
+    import math
+    from diffmusic_b200.istft import mel_spectrogram_to_waveform_with_phase
+    from oracle import istft as oi
+    B, T = 16, 1001
+    g = torch.Generator().manual_seed(21)
+    mel = torch.rand(B, 1, T, 64, generator=g) * 6.0 - 1.0
+    phase = (torch.rand(1, 513, T, generator=g) * 2.0 - 1.0) * math.pi
+    got = mel_spectrogram_to_waveform_with_phase(mel.to(DEV), phase.to(DEV), original_waveform_length=160000)
+    assert tuple(got.shape) == (B, 160000)
+    for b in (0, 15):
+        want = oi.mel_spectrogram_to_waveform_with_phase(mel[b:b + 1].numpy(), phase.numpy(),
+                                                         original_waveform_length=160000)
+        assert rel_l2(got[b:b + 1], want) < 2e-6
+    twice = mel_spectrogram_to_waveform_with_phase((2.0 * mel).to(DEV), phase.to(DEV), original_waveform_length=160000)
+    assert torch.equal(twice, 2.0 * got)
+    for hop, T2 in ((512, 37), (160, 2), (1024, 5)):
+        m2 = torch.rand(2, 1, T2, 64, generator=g) * 4.0
+        p2 = (torch.rand(2, 513, T2, generator=g) * 2.0 - 1.0) * math.pi
+        y = mel_spectrogram_to_waveform_with_phase(m2.to(DEV), p2.to(DEV), hop_length=hop)
+        want = oi.mel_spectrogram_to_waveform_with_phase(m2.numpy(), p2.numpy(), hop_length=hop)
+        assert tuple(y.shape) == want.shape == (2, hop * (T2 - 1))
+        assert rel_l2(y, want) < 2e-6
+    with pytest.raises(NotImplementedError):
+        mel_spectrogram_to_waveform_with_phase(mel.to(DEV), phase.to(DEV), n_fft=2048, win_length=2048)
+    with pytest.raises(RuntimeError):
+        mel_spectrogram_to_waveform_with_phase(mel.to(DEV), phase[..., :1000].to(DEV))
+
+
 def test_mean_squared_error_vs_reference_formula():
     from diffmusic_b200 import metrics
     from oracle import metrics as om

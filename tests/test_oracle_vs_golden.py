@@ -169,3 +169,38 @@ def test_metric_oracles_closed_forms():
     assert abs(om.mse_score(x, x + 0.5) - 0.25) < 1e-6
     assert abs(om.mse_score(x, x + 0.5, "sum") - 0.5) < 1e-6
     assert om.mse_score(x, y) == om.mse_score(x, z)
+
+
+@pytest.mark.parametrize("name", ["b1_t26", "b3_t41_own_phase", "b2_t9"])
+def test_istft_oracle_matches_reference(name):
+    """oracle/istft.py against the reference's own mel_spectrogram_to_waveform_with_phase (pipeline_musicldm.py:263-301,
+    run in the build container by tests/golden/make_istft_golden.py): InverseMelScale as the minimum-norm matrix, the
+    rectangular-window istft, clip / zero-pad to original_waveform_length."""
+    import os
+    from oracle import istft as oi
+    from tests.conftest import GOLDEN
+    want = np.load(os.path.join(GOLDEN, "istft.npz"))[name]
+    mel, phase = stubs.istft_inputs(name)
+    got = oi.mel_spectrogram_to_waveform_with_phase(mel.numpy(), phase.numpy(),
+                                                    original_waveform_length=stubs.ISTFT_CASES[name][4])
+    assert got.shape == want.shape
+    assert rel_l2(got, want) < 2e-6  # the reference runs lstsq + irfft in fp32
+    n = 160 * (stubs.ISTFT_CASES[name][1] - 1)
+    if want.shape[1] > n:
+        assert not want[:, n:].any() and not got[:, n:].any()
+
+
+def test_inverse_mel_scale_is_the_minimum_norm_matrix():
+    """live torchaudio InverseMelScale (lstsq, driver gels) == relu(fb (fb^T fb)^-1 mel), and the host table the kernel
+    reads (diffmusic_b200.tables.inverse_mel_matrix) is that matrix."""
+    import torchaudio
+    from diffmusic_b200 import tables
+    from oracle import istft as oi
+    g = torch.Generator().manual_seed(5)
+    mel = torch.rand(2, 64, 33, generator=g) * 8.0 - 2.0
+    live = torchaudio.transforms.InverseMelScale(n_stft=513, n_mels=64, sample_rate=16000)(mel)
+    assert rel_l2(oi.inverse_mel_scale(mel.numpy()), live) < 2e-6
+    w_t = tables.inverse_mel_matrix(16000)
+    assert w_t.shape == (64, 513) and w_t.dtype == torch.float32
+    assert rel_l2(torch.relu(torch.einsum("mk,bmt->bkt", w_t, mel)), live) < 2e-6
+    assert not w_t[:, 0].any() and not w_t[:, 512].any()  # the filterbank has no weight on DC / Nyquist

@@ -50,6 +50,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--torch-yardstick", action="store_true")
     a = ap.parse_args()
     B, dev = a.batch, torch.device("cuda", 0)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
@@ -134,6 +135,22 @@ def main():
                                                             c["sqrt_a"], c["sqrt_p"], c["dir_coef"], c["std"], 0.08,
                                                             1e-3, 1e-8, 0.9995, None, st()),
                 5 * lat, "one 8-CTA cluster per clip, single read")
+    # phase-preserving export (pipeline_musicldm.py:263-301): mel + shared phase in, waveform out
+    mel = torch.rand(B, 1, T, M, device=dev) * 6.0 - 1.0
+    ph = (torch.rand(1, F, T, device=dev) * 2.0 - 1.0) * 3.14159
+    add("export.mel_to_waveform_with_phase",
+        lambda: dm.mel_spectrogram_to_waveform_with_phase(mel, ph, original_waveform_length=L),
+        B * (4 * M * T + 4 * L) + 4 * F * T, "InverseMelScale + istft fused; phase shared by the batch")
+    if a.torch_yardstick:
+        import torchaudio
+        inv = torchaudio.transforms.InverseMelScale(n_stft=F, n_mels=M, sample_rate=16000).to(dev)
+        w = (inv.fb @ torch.linalg.inv(inv.fb.T @ inv.fb))
+
+        def eager():  # the same chain in eager torch on this GPU, lstsq replaced by its closed form (gels on CUDA
+            lin = torch.relu(w @ mel.squeeze(1).permute(0, 2, 1))  # needs a full-rank TALL system)
+            return torch.istft(lin * torch.exp(1j * ph.squeeze(0)), n_fft=1024, hop_length=160, win_length=1024)
+        add("export.mel_to_waveform_with_phase[torch eager]", eager, B * (4 * M * T + 4 * L) + 4 * F * T,
+            "yardstick: matmul + exp + cuFFT irfft + fold")
     print(json.dumps({"what": "operator HBM GB/s vs peak", "batch": B, "clip_samples": L, "hbm_peak_GBps": pk,
                       "l2": "flushed before every timed call", "rows": rows}, indent=1))
 
