@@ -34,6 +34,32 @@ struct IstftParams {
     float* ola;           // (B, ola_len) zeroed
 };
 
+// phases of bin k for the frames of the tile (rows of the (513, T) phase are 32-byte runs per thread: issued early, the
+// latency hides behind the band loop)
+__device__ __forceinline__ void istft_load_phase(const float* __restrict__ phb, long long T, long long f0, int nfr, int k,
+                                                 float (&ph)[kIstftFrames]) {
+    const float* src = phb + (long long)k * T + f0;
+#pragma unroll
+    for (int f = 0; f < kIstftFrames; ++f) ph[f] = f < nfr ? __ldg(src + f) : 0.f;
+}
+// bin k of the tile: relu, times exp(i phase), stored as (frame 2q, frame 2q + 1) cells; frames past the end have a
+// zero magnitude (their mel tile is zero)
+__device__ __forceinline__ void istft_emit(c2* spec, int k, const float (&lin)[kIstftFrames],
+                                           const float (&ph)[kIstftFrames]) {
+    float xr[kIstftFrames], xi[kIstftFrames];
+#pragma unroll
+    for (int f = 0; f < kIstftFrames; ++f) {
+        const float mag = lin[f] < 0.f ? 0.f : lin[f];  // torch.relu: NaN stays NaN
+        float sn, cs;
+        sincosf(ph[f], &sn, &cs);
+        xr[f] = mag * cs;
+        xi[f] = mag * sn;
+    }
+#pragma unroll
+    for (int q = 0; q < kIstftFrames / 2; ++q)
+        spec[q * kSpecLd + k] = c2{xr[2 * q], xi[2 * q], xr[2 * q + 1], xi[2 * q + 1]};
+}
+
 __global__ void __launch_bounds__(kIstftThreads, 2) istft_pair_kernel(const IstftParams p) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, g = tid / kGroupThreads, gt = tid % kGroupThreads;
@@ -54,6 +80,12 @@ __global__ void __launch_bounds__(kIstftThreads, 2) istft_pair_kernel(const Istf
     PairConsts pc;
     load_pair_consts(gt, p.tab, pc);
 
+    // ---- phases of the two bins this thread will emit: in flight while the mel tile is staged ----
+    const float* phb = p.phase + (long long)b * p.phase_bstride;
+    float ph0[kIstftFrames], ph1[kIstftFrames];
+    istft_load_phase(phb, p.T, f0, nfr, tid, ph0);
+    istft_load_phase(phb, p.T, f0, nfr, tid + kIstftThreads, ph1);
+
     // ---- stage the mel tile (frames past the end read as zero) and clear the overlap-add span ----
     const float* mb = p.mel + (long long)b * p.mel_bstride;
     for (int i = tid; i < kMels * kIstftFrames; i += kIstftThreads) {
@@ -66,40 +98,45 @@ __global__ void __launch_bounds__(kIstftThreads, 2) istft_pair_kernel(const Istf
     __syncthreads();
 
     // ---- linear magnitude of every bin of the tile: relu(W mel), times exp(i phase) -> pair-major spectrum cells ----
-    const float* phb = p.phase + (long long)b * p.phase_bstride;
-    for (int k = tid; k < kBins; k += kIstftThreads) {
-        float lin[kIstftFrames];
+    // thread t carries bins t and t + 256 through one pass over the 64 bands (16 accumulators per W / mel load pair);
+    // the odd bin 512 is split over warp 0 (lane = 8 * band quarter + frame) and reduced with two shuffles.
+    {
+        float l0[kIstftFrames], l1[kIstftFrames];
 #pragma unroll
-        for (int f = 0; f < kIstftFrames; ++f) lin[f] = 0.f;
-        const float* w = p.winv_t + k;
+        for (int f = 0; f < kIstftFrames; ++f) l0[f] = l1[f] = 0.f;
+        const float* w = p.winv_t + tid;
 #pragma unroll 4
         for (int m = 0; m < kMels; ++m) {
-            const float wm = __ldg(w + m * kBins);
+            const float w0 = __ldg(w + m * kBins), w1 = __ldg(w + m * kBins + kIstftThreads);
             const float4 a = reinterpret_cast<const float4*>(mel_s + m * kIstftFrames)[0];
             const float4 c = reinterpret_cast<const float4*>(mel_s + m * kIstftFrames)[1];
-            lin[0] = fmaf(wm, a.x, lin[0]);
-            lin[1] = fmaf(wm, a.y, lin[1]);
-            lin[2] = fmaf(wm, a.z, lin[2]);
-            lin[3] = fmaf(wm, a.w, lin[3]);
-            lin[4] = fmaf(wm, c.x, lin[4]);
-            lin[5] = fmaf(wm, c.y, lin[5]);
-            lin[6] = fmaf(wm, c.z, lin[6]);
-            lin[7] = fmaf(wm, c.w, lin[7]);
-        }
-        static_assert(kIstftFrames == 8, "the tile product is written for 8 frames");
-        const float* ph = phb + (long long)k * p.T + f0;
-        float xr[kIstftFrames], xi[kIstftFrames];
+            const float mv[kIstftFrames] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
-        for (int f = 0; f < kIstftFrames; ++f) {
-            const float mag = lin[f] < 0.f ? 0.f : lin[f];  // torch.relu: NaN stays NaN
+            for (int f = 0; f < kIstftFrames; ++f) {
+                l0[f] = fmaf(w0, mv[f], l0[f]);
+                l1[f] = fmaf(w1, mv[f], l1[f]);
+            }
+        }
+        static_assert(kIstftFrames == 8 && kBins == 2 * kIstftThreads + 1, "bin ownership of the tile product");
+        istft_emit(spec, tid, l0, ph0);
+        istft_emit(spec, tid + kIstftThreads, l1, ph1);
+    }
+    if (tid < 32) {
+        const int f = tid & 7, part = tid >> 3;
+        float lin = 0.f;
+#pragma unroll 4
+        for (int m = 16 * part; m < 16 * part + 16; ++m)
+            lin = fmaf(__ldg(p.winv_t + m * kBins + (kBins - 1)), mel_s[m * kIstftFrames + f], lin);
+        lin += __shfl_xor_sync(0xffffffffu, lin, 8);
+        lin += __shfl_xor_sync(0xffffffffu, lin, 16);
+        if (part == 0) {
+            const float mag = lin < 0.f ? 0.f : lin;
             float sn = 0.f, cs = 0.f;
-            if (f < nfr) sincosf(__ldg(ph + f), &sn, &cs);
-            xr[f] = mag * cs;
-            xi[f] = mag * sn;
+            if (f < nfr) sincosf(__ldg(phb + (long long)(kBins - 1) * p.T + f0 + f), &sn, &cs);
+            float* cell = reinterpret_cast<float*>(spec + (f >> 1) * kSpecLd + (kBins - 1)) + 2 * (f & 1);
+            cell[0] = mag * cs;
+            cell[1] = mag * sn;
         }
-#pragma unroll
-        for (int q = 0; q < kIstftFrames / 2; ++q)
-            spec[q * kSpecLd + k] = c2{xr[2 * q], xi[2 * q], xr[2 * q + 1], xi[2 * q + 1]};
     }
     __syncthreads();
 
@@ -131,21 +168,36 @@ __global__ void __launch_bounds__(kIstftThreads, 2) istft_pair_kernel(const Istf
     for (int i = tid; i < span; i += kIstftThreads) atomicAdd(ob + i, acc[i]);
 }
 
-// out[b, j] = ola[b, j + 512] / 1024 / (frames covering padded sample j + 512) for j < hop (T - 1), zero padding after
+// out[b, j] = ola[b, j + 512] / 1024 / (frames covering padded sample j + 512) for j < hop (T - 1), zero padding after.
+// Four consecutive samples per thread (128-bit loads / stores when the rows allow it), 32-bit index arithmetic.
+// ola * (1/1024) is exact; the division by the frame count is the one rounding, as in torch's y / window_envelop.
+__device__ __forceinline__ float istft_sample(float v, unsigned i, unsigned hop, unsigned t_last) {
+    const unsigned t_hi = min(t_last, i / hop);
+    const unsigned t_lo = i >= (unsigned)kNfft ? (i - kNfft) / hop + 1u : 0u;
+    return v * (1.0f / kNfft) / (float)(t_hi - t_lo + 1u);
+}
 __global__ void __launch_bounds__(256) istft_finish_kernel(const float* __restrict__ ola, long long ola_len, long long T,
                                                            int hop, float* __restrict__ out, long long out_len) {
     const int b = blockIdx.y;
-    const long long n_valid = (long long)hop * (T - 1);
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < out_len;
-         j += (long long)gridDim.x * blockDim.x) {
-        float v = 0.f;
-        if (j < n_valid) {
-            const long long i = j + kNfft / 2;
-            const long long t_hi = min(T - 1, i / hop);
-            const long long t_lo = i >= kNfft ? (i - kNfft) / hop + 1 : 0;
-            v = ola[(long long)b * ola_len + i] * (1.0f / kNfft) / (float)(t_hi - t_lo + 1);
+    const unsigned n_valid = (unsigned)((long long)hop * (T - 1)), t_last = (unsigned)(T - 1), h = (unsigned)hop;
+    const float* src = ola + (long long)b * ola_len + kNfft / 2;
+    float* dst = out + (long long)b * out_len;
+    const bool vec = ((ola_len | out_len) & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(ola) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    for (long long j0 = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); j0 < out_len;
+         j0 += 4LL * gridDim.x * blockDim.x) {
+        const unsigned j = (unsigned)j0;
+        if (vec && j + 4 <= n_valid && j0 + 4 <= out_len) {
+            float4 v = *reinterpret_cast<const float4*>(src + j);
+            v.x = istft_sample(v.x, j + 512u, h, t_last);
+            v.y = istft_sample(v.y, j + 513u, h, t_last);
+            v.z = istft_sample(v.z, j + 514u, h, t_last);
+            v.w = istft_sample(v.w, j + 515u, h, t_last);
+            *reinterpret_cast<float4*>(dst + j) = v;
+        } else {
+            for (unsigned q = 0; q < 4 && j0 + q < out_len; ++q)
+                dst[j + q] = (j + q < n_valid) ? istft_sample(src[j + q], j + q + 512u, h, t_last) : 0.f;
         }
-        out[(long long)b * out_len + j] = v;
     }
 }
 
@@ -192,7 +244,8 @@ extern "C" int dm_istft_mel_phase(const dm_stft_tables* tab, const float* winv_t
     const dim3 grid((unsigned)((T + kIstftFrames - 1) / kIstftFrames), B);
     istft_pair_kernel<<<grid, kIstftThreads, smem, as_stream(stream)>>>(p);
     DM_LAUNCHED();
-    const unsigned fx = (unsigned)min((out_len + 255) / 256, 1184LL);
+    DM_REQUIRE(p.ola_len < (1LL << 31) && out_len < (1LL << 31));
+    const unsigned fx = (unsigned)min((out_len + 1023) / 1024, 1184LL);
     istft_finish_kernel<<<dim3(fx, B), 256, 0, as_stream(stream)>>>(ola, p.ola_len, T, hop, out, out_len);
     DM_LAUNCHED();
     return DM_OK;
