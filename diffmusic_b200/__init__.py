@@ -13,5 +13,6 @@ from .schedulers import (DDIMScheduler, DiffMusicScheduler, DPSScheduler, DSGSch
 
 from .graph import GraphedGuidedStep, HostPipelinedStep  # noqa: F401,E402
 from .istft import mel_spectrogram_to_waveform_with_phase  # noqa: F401,E402
+from .driver import BatchedGuidedSampler, BatchedSamplerOutput  # noqa: F401,E402
 
 __version__ = "0.1.0"

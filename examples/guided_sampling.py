@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--seconds", type=int, default=10)
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--driver", action="store_true", help="run the loop through BatchedGuidedSampler (per-clip NaN restarts)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     sr, L = 16000, a.seconds * 16000
@@ -60,6 +61,21 @@ def main():
     eta, rate = RATES[a.scheduler]
     kw = dict(eta=eta, measurement=measurement, vae=vae, vocoder=vocoder, original_waveform_length=L,
               ip_guidance_rate=rate, supervised_space="mel_spectrogram")
+    if a.driver:  # the same loop, owned by the batched-clip driver (diffmusic_b200/driver.py)
+        from diffmusic_b200 import BatchedGuidedSampler
+        drv = BatchedGuidedSampler(sched, lambda x, t: unet(x), vae, vocoder, num_inference_steps=a.steps,
+                                   original_waveform_length=L, latent_shape=(8, a.seconds * 25, 16), eta=eta,
+                                   ip_guidance_rate=rate, graph=a.graph)
+        drv(measurement, generators)  # first call: lazy initialisation, cuDNN heuristics, graph capture
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = drv(measurement, generators, decode=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print(f"{a.task} / {a.scheduler} through BatchedGuidedSampler: {a.batch} clips x {a.steps} steps in {dt:.3f} s "
+              f"({a.batch * a.steps / dt:.0f} clip-steps/s, {'graph' if a.graph else 'eager'}, second call), final per-clip loss "
+              f"{[round(float(v), 3) for v in res.loss]}, restarts {res.restarts}, audio {tuple(res.audios.shape)}")
+        return
     step = GraphedGuidedStep(sched, tuple(latents.shape), **kw) if a.graph else None
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -992,3 +992,75 @@ def test_batched_clip_noise_is_torch_randn_bit_for_bit(shape, dt):
     # single generators and CPU generators keep going through torch
     assert ddim_base.randn_clips_f32(shape, gb[0], torch.device(DEV), dt) is None
     assert ddim_base.randn_clips_f32(shape, [torch.Generator().manual_seed(1) for _ in range(B)], torch.device(DEV), dt) is None
+
+
+# ------------------------------------------------------------------------------------------------ batched-clip driver
+@pytest.mark.parametrize("name,task,eta,rate,graph", [("dsg", "inpainting", 1.0, 0.08, False),
+                                                      ("dps", "super_resolution", 0.0, 5e-4, False),
+                                                      ("diffmusic", "inpainting", 1.0, 0.08, True)])
+def test_batched_driver_matches_the_per_clip_pipeline_loop(name, task, eta, rate, graph):
+    """BatchedGuidedSampler (4 clips in one batch, NaN guard evaluated once per trajectory, CUDA generators rewound to the
+    offset right after the first NaN step) against the reference's structure: one clip per call, `torch.isnan(out.loss)`
+    checked after every step, latents re-drawn from the clip's generator on a NaN (pipeline_musicldm.py:677-763).
+    Clip 1 is poisoned at the third step of its first attempt."""
+    from diffmusic_b200.ddim_base import randn_tensor
+    from diffmusic_b200.driver import BatchedGuidedSampler
+    torch.manual_seed(0)
+    B, H, L, steps = 4, 25, 16000, 6
+    nz = dm.get_noiser("gaussian", 0.0)
+    op = (dm.MusicInpaintingOperator(1, 16000, "box", 0.2, 0.3, 0.3, 0.1, 1, noiser=nz) if task == "inpainting"
+          else dm.SuperResolutionOperator(16000, scale=2, noiser=nz))
+    sched = dm.get_scheduler(name)(operator=op, **stubs.MUSICLDM_SCHED)
+    vae, voc = stubs.StubVAE().to(DEV), stubs.StubVocoder().to(DEV)
+    net = torch.nn.Conv2d(8, 8, 3, padding=1).to(DEV)
+    meas = torch.cat([op.forward(stubs.synth_clips(1, L, first=60 + j)) for j in range(B)]).to(DEV)  # run.py:286 per clip
+
+    class Predict:
+        def __init__(self):
+            self.attempt = {}
+
+        def __call__(self, x, t, clips):
+            eps = net(x)
+            for row, j in enumerate(clips):
+                if int(t) == int(sched.timesteps[0]):
+                    self.attempt[j] = self.attempt.get(j, 0) + 1
+                if j == 1 and int(t) == int(sched.timesteps[2]) and self.attempt[j] == 1:
+                    eps[row] = float("nan")
+            return eps
+
+    kw = dict(eta=eta, ip_guidance_rate=rate, supervised_space="mel_spectrogram")
+    gens = [torch.Generator(device=DEV).manual_seed(500 + j) for j in range(B)]
+    drv = BatchedGuidedSampler(sched, Predict(), vae, voc, num_inference_steps=steps, original_waveform_length=L,
+                               latent_shape=(8, H, 16), graph=graph, **kw)
+    out = drv(meas, gens, decode=True)
+    assert out.restarts == [0, 1, 0, 0]
+    assert torch.isfinite(out.latents).all() and torch.isfinite(out.loss_history).all()
+    assert tuple(out.audios.shape) == (B, L) and out.audios.dtype == torch.float32
+
+    # the reference's loop, one clip at a time
+    for j in range(B):
+        g = torch.Generator(device=DEV).manual_seed(500 + j)
+        predict = Predict()
+        sched.set_timesteps(steps, device=DEV)
+        retry, restarts = 10, 0
+        lat = randn_tensor((1, 8, H, 16), generator=g, device=DEV, dtype=torch.float32) * sched.init_noise_sigma
+        while True:
+            done = True
+            for t in sched.timesteps:
+                with torch.no_grad():
+                    eps = predict(sched.scale_model_input(lat, t), t, [j])
+                o = sched.step(eps, t, lat, generator=g, measurement=meas[j:j + 1], vae=vae, vocoder=voc,
+                               original_waveform_length=L, **kw)
+                if torch.isnan(o.loss) and retry >= 0:
+                    retry -= 1
+                    restarts += 1
+                    lat = randn_tensor((1, 8, H, 16), generator=g, device=DEV, dtype=torch.float32) * sched.init_noise_sigma
+                    done = False
+                    break
+                lat = o.prev_sample.detach()
+            if done:
+                break
+        assert restarts == out.restarts[j]
+        assert rel_l2(out.latents[j], lat[0]) < 1e-4, (j, rel_l2(out.latents[j], lat[0]))
+        assert abs(float(out.loss[j]) - float(o.loss)) <= 1e-4 * abs(float(o.loss))
+        assert gens[j].get_offset() == g.get_offset()  # same position in the clip's Philox stream, restarts included
