@@ -146,10 +146,12 @@ class BatchedGuidedSampler:
         return latents, hist, start, per_step
 
     # ---- the driver ----------------------------------------------------------------------------------------------------
-    def __call__(self, measurement, generators=None, *, batch=None, device=None, latents=None, decode=False):
+    def __call__(self, measurement, generators=None, *, batch=None, device=None, latents=None, decode=False,
+                 clip_ids=None):
         """measurement: (1, ...) shared by the batch or (B, ...) one row per clip (what `operator.forward(clip)` returned,
         run.py:286,312); generators: list of B generators (or one generator / None, then restarts cannot isolate clips);
-        latents: optional (B, ...) initial latents (first attempt only, like `pipe(latents=...)`)."""
+        latents: optional (B, ...) initial latents (first attempt only, like `pipe(latents=...)`); clip_ids: the labels the
+        noise predictor receives as `clips` (default 0..B-1; a sharded run passes the global clip indices)."""
         sched = self.scheduler
         if isinstance(generators, (list, tuple)):
             B = len(generators)
@@ -166,6 +168,9 @@ class BatchedGuidedSampler:
         sched.set_timesteps(self.num_inference_steps, device=dev)
         steps = len(sched.timesteps)
         per_clip_gens = isinstance(generators, (list, tuple))
+        labels = list(range(B)) if clip_ids is None else list(clip_ids)
+        if len(labels) != B:
+            raise ValueError(f"clip_ids names {len(labels)} clips for a batch of {B}")
 
         final = [None] * B
         final_hist = [None] * B
@@ -181,7 +186,7 @@ class BatchedGuidedSampler:
             else:
                 x = self.prepare_latents(gens, len(ids), dev)
             first = False
-            x, hist, start, per_step = self._trajectory(ids, meas, gens, x)
+            x, hist, start, per_step = self._trajectory([labels[j] for j in ids], meas, gens, x)
             bad = torch.isnan(hist)
             first_bad = torch.where(bad.any(0), bad.float().argmax(0), torch.full_like(bad[0], -1, dtype=torch.long))
             first_bad = first_bad.tolist()  # the one host synchronisation of the trajectory

@@ -30,3 +30,32 @@ def init_distributed(backend=None):
         else:
             dist.init_process_group(backend)
     return rank, world, local
+
+
+def run_sharded(sampler, measurement, generators, rank=None, world=None, gather=False, **call_kwargs):
+    """Run a `BatchedGuidedSampler` on this rank's clips (clip i -> rank i mod W; the guided path has no collective).
+
+    measurement: (B, ...) one row per clip, or (1, ...) shared; generators: list of B per-clip generators (every rank
+    builds the same list and uses its own entries, so a clip's stream does not depend on the world size); the noise
+    predictor's `clips` argument carries the GLOBAL clip indices.
+    Returns (clip indices of this rank, BatchedSamplerOutput of those clips).  gather=True additionally all-gathers the
+    per-clip losses and restart counts (logging only; a few bytes) and returns them as a third item
+    {clip index: (loss, restarts)}."""
+    import torch.distributed as dist
+    if rank is None or world is None:
+        on = dist.is_available() and dist.is_initialized()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+    B = len(generators)
+    ids = shard_indices(B, rank, world)
+    out = None
+    if ids:
+        meas = measurement if measurement.shape[0] == 1 else measurement[ids].contiguous()
+        out = sampler(meas, [generators[i] for i in ids], clip_ids=ids, **call_kwargs)
+    if not gather:
+        return ids, out
+    mine = {i: (float(out.loss[k]), int(out.restarts[k])) for k, i in enumerate(ids)} if ids else {}
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        mine = {k: v for part in parts for k, v in part.items()}
+    return ids, out, mine

@@ -55,3 +55,38 @@ def test_fad_allreduce_equals_chan_merge_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _driver_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.test_driver import Predictor, gens, sampler
+    meas = torch.arange(5, dtype=torch.float32).reshape(5, 1) * 0.1
+    ids, out, table = parallel.run_sharded(sampler(Predictor(poison=[3]), eta=1.0), meas, gens(range(5)), gather=True)
+    q.put((rank, ids, out.latents, table))
+    dist.destroy_process_group()
+
+
+def test_batched_driver_shards_clips_world2():
+    """5 clips over 2 ranks (clip i -> rank i mod 2), no collective on the path: every clip equals the single-process batch,
+    including the clip that restarts; the gathered loss table covers all clips on every rank."""
+    from tests.test_driver import Predictor, gens, sampler
+    meas = torch.arange(5, dtype=torch.float32).reshape(5, 1) * 0.1
+    whole = sampler(Predictor(poison=[3]), eta=1.0)(meas, gens(range(5)))
+    assert whole.restarts == [0, 0, 0, 1, 0]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_driver_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [[0, 2, 4], [1, 3]]
+    for _, ids, lat, table in res:
+        for k, i in enumerate(ids):
+            assert torch.equal(lat[k], whole.latents[i])
+        assert sorted(table) == [0, 1, 2, 3, 4]
+        assert [table[i][1] for i in range(5)] == whole.restarts
+        assert all(abs(table[i][0] - float(whole.loss[i])) < 1e-6 for i in range(5))
