@@ -12,7 +12,7 @@ from .schedulers import (DDIMScheduler, DiffMusicScheduler, DPSScheduler, DSGSch
                          InverseProblemSchedulerOutput, MPGDScheduler, get_scheduler)
 
 from .graph import GraphedGuidedStep, HostPipelinedStep  # noqa: F401,E402
-from .istft import mel_spectrogram_to_waveform_with_phase  # noqa: F401,E402
+from .istft import mel_spectrogram_to_waveform_with_phase, waveform_to_spectrogram  # noqa: F401,E402
 from .driver import BatchedGuidedSampler, BatchedSamplerOutput  # noqa: F401,E402
 
 __version__ = "0.1.0"

@@ -79,6 +79,7 @@ _SIGNATURES = {
     "dm_lsd_frames": (c_i, [C.POINTER(StftTables), c_p, c_ll, c_p, c_ll, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_p]),
     "dm_mse_num_chunks": (c_ll, [c_ll]),
     "dm_mse": (c_i, [c_p, c_ll, c_p, c_ll, c_ll, c_i, c_p, c_p, c_p]),
+    "dm_stft_spectrogram": (c_i, [C.POINTER(StftTables), c_p, c_ll, c_ll, c_i, c_i, c_p, c_p, c_p]),
     "dm_istft_workspace_floats": (c_ll, [c_i, c_ll, c_i]),
     "dm_istft_mel_phase": (c_i, [C.POINTER(StftTables), c_p, c_p, c_ll, c_ll, c_ll, c_p, c_ll, c_i, c_ll, c_i, c_p, c_p,
                                  c_ll, c_p]),

@@ -201,6 +201,87 @@ __global__ void __launch_bounds__(256) istft_finish_kernel(const float* __restri
     }
 }
 
+// ---- companion forward: waveform_to_spectrogram (diffmusic/utils.py:11-20; run.py:305 takes the phase of the degraded
+// clip from it): torch.stft(1024, hop, 1024, window = tab.window (the reference passes none: rectangular), centred with
+// reflection) -> |X| and angle(X), both (B, 513, T).  Frames t and t + 1 of a clip ride through one pair FFT; every
+// thread emits the magnitude and atan2 of the bins it owns straight from its registers.
+constexpr int kSpecThreads = 256;
+constexpr int kSpecGroups = kSpecThreads / kGroupThreads;
+
+struct SpectrogramParams {
+    StftTables tab;
+    const float* wav;
+    long long wav_bstride, L, T;
+    int hop, nf;
+    float* mag;    // (B, 513, T) or null
+    float* phase;  // (B, 513, T) or null
+};
+
+__device__ __forceinline__ void spec_emit(const SpectrogramParams& p, long long row, long long ta, bool has_b, cf xa,
+                                          cf xb) {
+    if (p.mag) {
+        p.mag[row + ta] = pair_bin_energy<kModePhaseWav>(xa);
+        if (has_b) p.mag[row + ta + 1] = pair_bin_energy<kModePhaseWav>(xb);
+    }
+    if (p.phase) {
+        p.phase[row + ta] = atan2f(xa.y, xa.x);
+        if (has_b) p.phase[row + ta + 1] = atan2f(xb.y, xb.x);
+    }
+}
+
+__global__ void __launch_bounds__(kSpecThreads, 2) spectrogram_pair_kernel(const SpectrogramParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, g = tid / kGroupThreads, gt = tid % kGroupThreads;
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const long long f0 = (long long)tile * p.nf;
+    const int nfr = (int)min((long long)p.nf, p.T - f0);
+    const int span = (nfr - 1) * p.hop + kNfft;
+    const int span_alloc = ((p.nf - 1) * p.hop + kNfft + 3) & ~3;
+    const long long base = f0 * p.hop;
+
+    float* sig = smem;
+    float* win = sig + span_alloc;
+    float* grp = win + kNfft;
+    PairSmem s;
+    s.a = reinterpret_cast<c2*>(grp + g * kPairSmemFloats);
+    s.b = reinterpret_cast<c2*>(grp + g * kPairSmemFloats + 4 * kH);
+    PairConsts pc;
+    load_pair_consts(gt, p.tab, pc);
+
+    const float* wb = p.wav + (long long)b * p.wav_bstride;
+    for (int i = tid; i < span; i += kSpecThreads) sig[i] = __ldg(wb + reflect_src(base + i, p.L));
+    reinterpret_cast<float4*>(win)[tid] = __ldg(reinterpret_cast<const float4*>(p.tab.window) + tid);
+    __syncthreads();
+
+    for (int fa = 2 * g; fa < nfr; fa += 2 * kSpecGroups) {
+        const bool has_b = fa + 1 < nfr;
+        const int fb = has_b ? fa + 1 : fa;
+        PairX x;
+        pair_fwd_pass1(gt, sig + fa * p.hop, sig + fb * p.hop, win, s);
+        istft_group_sync(g);
+        pair_fwd_pass2(gt, pc, s);
+        istft_group_sync(g);
+        pair_fwd_pass3(gt, pc, s);
+        istft_group_sync(g);
+        pair_unpack<kModePhaseWav>(gt, pc, s, x);
+        const long long ta = f0 + fa;
+        const long long rows = (long long)b * kBins;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = gt + 64 * i;  // k = 0: lo = bin 0, hi = bin 512
+            spec_emit(p, (rows + k) * p.T, ta, has_b, x.lo[i][0], x.lo[i][1]);
+            spec_emit(p, (rows + kH - k) * p.T, ta, has_b, x.hi[i][0], x.hi[i][1]);
+        }
+        if (gt == 0) spec_emit(p, (rows + kH / 2) * p.T, ta, has_b, x.q[0], x.q[1]);
+        istft_group_sync(g);  // the unpack's reads of `a` (and writes of P in `b`) are over before the next pass 1
+    }
+}
+
+static size_t spectrogram_smem_bytes(int nf, int hop) {
+    size_t span = ((size_t)(nf - 1) * hop + kNfft + 3) & ~(size_t)3;
+    return (span + kNfft + (size_t)kSpecGroups * kPairSmemFloats) * sizeof(float);
+}
+
 static size_t istft_smem_bytes(int hop) {
     size_t span = ((size_t)(kIstftFrames - 1) * hop + kNfft + 3) & ~(size_t)3;
     return ((size_t)(kIstftFrames / 2) * kSpecLd * 4 + (size_t)kIstftGroups * kPairSmemFloats + span +
@@ -247,6 +328,31 @@ extern "C" int dm_istft_mel_phase(const dm_stft_tables* tab, const float* winv_t
     DM_REQUIRE(p.ola_len < (1LL << 31) && out_len < (1LL << 31));
     const unsigned fx = (unsigned)min((out_len + 1023) / 1024, 1184LL);
     istft_finish_kernel<<<dim3(fx, B), 256, 0, as_stream(stream)>>>(ola, p.ola_len, T, hop, out, out_len);
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_stft_spectrogram(const dm_stft_tables* tab, const float* wav, long long wav_bstride, long long L, int B,
+                                   int hop, float* mag, float* phase, dm_stream_t stream) {
+    DM_REQUIRE(tab && wav && (mag || phase) && B > 0);
+    DM_REQUIRE(L > kNfft / 2);  // reflect padding needs pad < length (torch.stft raises otherwise)
+    DM_REQUIRE(hop > 0 && hop <= kNfft && (hop & 1) == 0);
+    SpectrogramParams p;
+    p.tab = StftTables{tab->window, reinterpret_cast<const cf*>(tab->tw512), reinterpret_cast<const cf*>(tab->w1024),
+                       tab->mel_kstart, tab->mel_klen, tab->mel_w, tab->mel_wstride, tab->bin_m0, tab->bin_w0,
+                       tab->bin_w1};
+    p.wav = wav;
+    p.wav_bstride = wav_bstride;
+    p.L = L;
+    p.T = 1 + L / hop;
+    p.hop = hop;
+    p.nf = hop <= 256 ? 16 : 8;
+    p.mag = mag;
+    p.phase = phase;
+    const size_t smem = spectrogram_smem_bytes(p.nf, hop);
+    DM_SMEM_ONCE(spectrogram_pair_kernel, smem);
+    const dim3 grid((unsigned)((p.T + p.nf - 1) / p.nf), B);
+    spectrogram_pair_kernel<<<grid, kSpecThreads, smem, as_stream(stream)>>>(p);
     DM_LAUNCHED();
     return DM_OK;
 }

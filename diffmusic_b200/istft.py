@@ -67,3 +67,32 @@ def mel_spectrogram_to_waveform_with_phase(mel_spectrogram, original_phase, n_ff
               mel.stride(1), phase.data_ptr(), phase_bstride, B, T, hop_length, ola.data_ptr(), out.data_ptr(), out_len,
               _lib.stream())
     return out
+
+
+def waveform_to_spectrogram(waveform, n_fft=1024, hop_length=160, win_length=1024):
+    """diffmusic/utils.py:11-20 (run.py:305 takes the degraded clip's phase from it): `torch.stft(waveform, n_fft,
+    hop_length, win_length, return_complex=True)` -- no window given, i.e. rectangular; centred, reflect padding -- and
+    its `(abs, angle)`, each (B, 513, 1 + L // hop) fp32.  One launch, the complex spectrogram is never materialised."""
+    if (n_fft, win_length) != (1024, 1024):
+        raise NotImplementedError("the STFT kernels are built for n_fft = win_length = 1024")
+    if hop_length <= 0 or hop_length > 1024 or hop_length % 2:
+        raise NotImplementedError("hop_length must be even and <= n_fft")
+    _lib.require_cuda(waveform)
+    squeeze = waveform.dim() == 1
+    wav = (waveform[None] if squeeze else waveform).to(torch.float32)
+    if wav.dim() != 2:
+        raise RuntimeError(f"stft: expected a 1D or 2D tensor, got {waveform.dim()}D")
+    if wav.stride(1) != 1:
+        wav = wav.contiguous()
+    B, L = wav.shape
+    if L <= 512:
+        raise RuntimeError(f"Argument #4: Padding size should be less than the corresponding input dimension, but got: "
+                           f"padding (512, 512) at dimension 2 of input {[1, B, L]}")
+    dev = wav.device
+    T = 1 + L // hop_length
+    tab, _ = _tables(dev)
+    mag = torch.empty((B, tables.N_BINS, T), device=dev, dtype=torch.float32)
+    phase = torch.empty_like(mag)
+    _lib.call("dm_stft_spectrogram", tab.ref, wav.data_ptr(), wav.stride(0), L, B, hop_length, mag.data_ptr(),
+              phase.data_ptr(), _lib.stream())
+    return (mag[0], phase[0]) if squeeze else (mag, phase)

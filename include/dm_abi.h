@@ -315,6 +315,11 @@ int dm_mse(const float* ref, long long ref_bstride, const float* est, long long 
  * is read in place: mstride 1, tstride 64); phase: (513, T) shared by the batch (phase_bstride 0) or (B, 513, T);
  * winv_t: (64, 513) = W^T; ola: dm_istft_workspace_floats(B, T, hop) floats of device scratch (zeroed by the call);
  * out: (B, out_len), out[b, j] = 0 for j >= hop (T - 1).  hop even. */
+/* waveform_to_spectrogram (diffmusic/utils.py:11-20; run.py:305): torch.stft(n_fft 1024, hop, win 1024, window =
+ * tab->window -- the reference passes none, i.e. rectangular --, center=True, reflect) -> mag = |X| and phase = angle(X),
+ * each (B, 513, T = 1 + L/hop); either output may be null.  wav: (B, L) fp32 rows wav_bstride apart.  hop even. */
+int dm_stft_spectrogram(const dm_stft_tables* tab, const float* wav, long long wav_bstride, long long L, int B, int hop,
+                        float* mag, float* phase, dm_stream_t stream);
 long long dm_istft_workspace_floats(int B, long long T, int hop);
 int dm_istft_mel_phase(const dm_stft_tables* tab, const float* winv_t, const float* mel, long long mel_bstride,
                        long long mel_mstride, long long mel_tstride, const float* phase, long long phase_bstride, int B,

@@ -67,3 +67,15 @@ def mel_spectrogram_to_waveform_with_phase(mel_spectrogram, original_phase, n_ff
         elif wav.shape[-1] < original_waveform_length:
             wav = np.pad(wav, ((0, 0), (0, original_waveform_length - wav.shape[-1])))
     return wav
+
+
+def waveform_to_spectrogram(waveform, n_fft=1024, hop_length=160, win_length=1024):
+    """diffmusic/utils.py:11-20 restated in float64: rectangular window (none is passed), centred frames over the
+    reflect-padded signal, one-sided DFT; returns (abs, angle), each (B, n_fft/2 + 1, 1 + L // hop)."""
+    assert win_length == n_fft
+    x = np.asarray(waveform, np.float64)
+    xp = np.pad(x, ((0, 0), (n_fft // 2, n_fft // 2)), mode="reflect")
+    T = 1 + x.shape[1] // hop_length
+    frames = np.stack([xp[:, t * hop_length:t * hop_length + n_fft] for t in range(T)], axis=2)  # (B, n_fft, T)
+    spec = np.fft.rfft(frames, axis=1)
+    return np.abs(spec), np.angle(spec)

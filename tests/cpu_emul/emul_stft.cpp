@@ -310,6 +310,50 @@ void emul_istft_mel_phase(const EmulTables* e, const float* winv_t, const float*
     }
 }
 
+// waveform_to_spectrogram (csrc/istft.cu spectrogram_pair_kernel): frames t, t + 1 through one pair FFT, magnitude and
+// atan2 of the owned bins from the registers.  mag / phase: (513, T).
+void emul_stft_spectrogram(const EmulTables* e, const float* wav, long long L, int hop, float* mag, float* phase) {
+    StftTables t{e->window, reinterpret_cast<const cf*>(e->tw512), reinterpret_cast<const cf*>(e->w1024),
+                 e->mel_kstart, e->mel_klen, e->mel_w, e->mel_wstride, e->bin_m0, e->bin_w0, e->bin_w1};
+    const long long T = 1 + L / hop;
+    std::vector<float> buf(kPairSmemFloats + 8, 0.f), fa(kNfft), fb(kNfft);
+    float* base = buf.data();
+    while (reinterpret_cast<uintptr_t>(base) & 15) ++base;
+    PairSmem s;
+    s.a = reinterpret_cast<c2*>(base);
+    s.b = reinterpret_cast<c2*>(base + 4 * kH);
+    std::vector<PairConsts> pc(64);
+    std::vector<PairX> px(64);
+    for (int tid = 0; tid < 64; ++tid) load_pair_consts(tid, t, pc[tid]);
+    auto emit = [&](int k, long long ta, bool has_b, cf xa, cf xb) {
+        mag[k * T + ta] = pair_bin_energy<kModePhaseWav>(xa);
+        phase[k * T + ta] = atan2f(xa.y, xa.x);
+        if (has_b) {
+            mag[k * T + ta + 1] = pair_bin_energy<kModePhaseWav>(xb);
+            phase[k * T + ta + 1] = atan2f(xb.y, xb.x);
+        }
+    };
+    for (long long f = 0; f < T; f += 2) {
+        const bool has_b = f + 1 < T;
+        for (int n = 0; n < kNfft; ++n) {
+            fa[n] = wav[reflect_src(f * hop + n, L)];
+            fb[n] = wav[reflect_src((has_b ? f + 1 : f) * hop + n, L)];
+        }
+        for (int tid = 0; tid < 64; ++tid) pair_fwd_pass1(tid, fa.data(), fb.data(), t.window, s);
+        for (int tid = 0; tid < 64; ++tid) pair_fwd_pass2(tid, pc[tid], s);
+        for (int tid = 0; tid < 64; ++tid) pair_fwd_pass3(tid, pc[tid], s);
+        for (int tid = 0; tid < 64; ++tid) pair_unpack<kModePhaseWav>(tid, pc[tid], s, px[tid]);
+        for (int tid = 0; tid < 64; ++tid) {
+            for (int i = 0; i < 4; ++i) {
+                const int k = tid + 64 * i;
+                emit(k, f, has_b, px[tid].lo[i][0], px[tid].lo[i][1]);
+                emit(kH - k, f, has_b, px[tid].hi[i][0], px[tid].hi[i][1]);
+            }
+            if (tid == 0) emit(kH / 2, f, has_b, px[0].q[0], px[0].q[1]);
+        }
+    }
+}
+
 // Bank-conflict audit of the cell swizzle: a 128-bit shared access is served per quarter-warp (8 consecutive lanes),
 // conflict-free iff the 8 cells fall into 8 distinct 16-byte bank groups (cell index mod 8).  Returns the number of
 // (pattern, quarter-warp) instances with a conflict, and checks st_c2_addr / the load form against sw4 of the logical index.

@@ -24,18 +24,18 @@ SRC = "/root/reference/diffmusic/pipelines/pipeline_musicldm.py"
 NAME = "mel_spectrogram_to_waveform_with_phase"
 
 
-def reference_function():
-    tree = ast.parse(open(SRC).read())
+def reference_function(src=SRC, name=NAME):
+    tree = ast.parse(open(src).read())
     for node in ast.walk(tree):
-        if isinstance(node, ast.FunctionDef) and node.name == NAME:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
             mod = ast.Module(body=[node], type_ignores=[])
             ns = {"torch": torch, "torchaudio": torchaudio}
-            exec(compile(mod, SRC, "exec"), ns)
-            return ns[NAME]
-    raise RuntimeError(f"{NAME} not found in {SRC}")
+            exec(compile(mod, src, "exec"), ns)
+            return ns[name]
+    raise RuntimeError(f"{name} not found in {src}")
 
 
-from tests.stubs import ISTFT_CASES, istft_inputs  # noqa: E402  (seeded inputs, rebuilt by the tests)
+from tests.stubs import ISTFT_CASES, SPECTROGRAM_CASES, istft_inputs  # noqa: E402  (seeded inputs, rebuilt by the tests)
 
 if __name__ == "__main__":
     fn = reference_function()
@@ -47,4 +47,12 @@ if __name__ == "__main__":
         wav = fn(None, mel, phase, original_waveform_length=case[4])
         out[name] = wav.numpy().astype(np.float32)
         print(name, tuple(wav.shape), float(wav.abs().max()))
+    # the companion forward, diffmusic/utils.py:11-20 (that module imports soundfile etc., hence the same extraction):
+    # magnitude and phase of two seeded 0.25 s clips (the second one ends in a ragged last hop)
+    w2s = reference_function("/root/reference/diffmusic/utils.py", "waveform_to_spectrogram")
+    from tests import stubs
+    for name, length in SPECTROGRAM_CASES.items():
+        mag, phase = w2s(stubs.synth_clips(2, length, first=70))
+        out[name + "_mag"], out[name + "_phase"] = mag.numpy(), phase.numpy()
+        print(name, tuple(mag.shape))
     np.savez_compressed(os.path.join(HERE, "istft.npz"), **out)

@@ -97,3 +97,7 @@ def istft_inputs(name):
     mel = torch.rand(B, 1, T, 64, generator=g) * 6.0 - 1.0
     phase = (torch.rand(1 if shared else B, 513, T, generator=g) * 2.0 - 1.0) * math.pi
     return mel, phase
+
+
+#: waveform_to_spectrogram fixtures of istft.npz: name -> clip length (clips synth_clips(2, L, first=70))
+SPECTROGRAM_CASES = {"w2s_4000": 4000, "w2s_4133": 4133}

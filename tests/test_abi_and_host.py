@@ -184,3 +184,7 @@ def test_mel_to_waveform_with_phase_has_no_cpu_path():
         dm.mel_spectrogram_to_waveform_with_phase(mel, phase)
     with pytest.raises(NotImplementedError):
         dm.mel_spectrogram_to_waveform_with_phase(mel, phase, hop_length=161)
+    with pytest.raises(DiffMusicB200Error):
+        dm.waveform_to_spectrogram(torch.zeros(1, 4000))
+    with pytest.raises(NotImplementedError):
+        dm.waveform_to_spectrogram(torch.zeros(1, 4000), n_fft=512, win_length=512)

@@ -311,6 +311,26 @@ def test_istft_through_the_pair_pipeline(emul, name):
         assert not got[160 * (T - 1):].any()
 
 
+@pytest.mark.parametrize("name", sorted(stubs.SPECTROGRAM_CASES))
+def test_spectrogram_through_the_pair_pipeline(emul, name):
+    """waveform_to_spectrogram through the device code of spectrogram_pair_kernel (rectangular window, frames t / t + 1 as
+    one pair, magnitude and atan2 from the owned-bin registers) against the reference function's output."""
+    from tests.test_oracle_vs_golden import _spectrogram_error
+    z = np.load(os.path.join(ROOT, "tests", "golden", "istft.npz"))
+    L = stubs.SPECTROGRAM_CASES[name]
+    wav = stubs.synth_clips(2, L, first=70).numpy()
+    t, keep = _tables(tables.rect_window())
+    T = 1 + L // 160
+    for b in range(2):
+        mag = np.zeros((513, T), np.float32)
+        ph = np.zeros((513, T), np.float32)
+        emul.emul_stft_spectrogram(C.byref(t), _ptr(wav[b].copy()), C.c_longlong(L), 160, _ptr(mag), _ptr(ph))
+        rel, dphi = _spectrogram_error(mag, ph, z[name + "_mag"][b], z[name + "_phase"][b])
+        assert rel < 3e-6 and dphi < 2e-3
+        # DC and Nyquist are real: their angle is exactly 0 or pi, as torch.angle returns it
+        assert np.isin(ph[[0, 512]], np.float32([0.0, np.pi])).all()
+
+
 def test_pair_swizzle_is_conflict_free(emul):
     """cell swizzle of the frame-pair pipeline: closed-form addresses equal sw4(logical index) and every 128-bit access
     pattern of the FFT passes / unpack hits 8 distinct 16-byte bank groups per quarter-warp."""

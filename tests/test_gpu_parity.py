@@ -520,6 +520,42 @@ def test_mel_to_waveform_with_phase_full_size():
         mel_spectrogram_to_waveform_with_phase(mel.to(DEV), phase[..., :1000].to(DEV))
 
 
+def test_waveform_to_spectrogram_vs_reference():
+    """waveform_to_spectrogram (diffmusic/utils.py:11-20) through dm_stft_spectrogram: the reference function's own output
+    (tests/golden/istft.npz), the float64 oracle at full size, and the magnitude bit-equal to PhaseRetrievalOperator.forward
+    (same frame-pair arithmetic, different tiling)."""
+    import os
+    from oracle import istft as oi
+    from tests.conftest import GOLDEN
+    from tests.test_oracle_vs_golden import _spectrogram_error
+    z = np.load(os.path.join(GOLDEN, "istft.npz"))
+    for name, L in stubs.SPECTROGRAM_CASES.items():
+        wav = stubs.synth_clips(2, L, first=70)
+        mag, phase = dm.waveform_to_spectrogram(wav.to(DEV))
+        assert tuple(mag.shape) == tuple(phase.shape) == z[name + "_mag"].shape
+        rel, dphi = _spectrogram_error(mag.cpu().numpy(), phase.cpu().numpy(), z[name + "_mag"], z[name + "_phase"])
+        assert rel < 3e-6 and dphi < 2e-3
+        m1, p1 = dm.waveform_to_spectrogram(wav[1].to(DEV))          # 1-D input, like torch.stft
+        assert torch.equal(m1, mag[1]) and torch.equal(p1, phase[1])
+    L = 160000
+    wav = stubs.synth_clips(3, L, first=80)
+    mag, phase = dm.waveform_to_spectrogram(wav.to(DEV))
+    assert tuple(mag.shape) == (3, 513, 1001)
+    wm, wp = oi.waveform_to_spectrogram(wav[2:3].numpy())
+    rel, dphi = _spectrogram_error(mag[2:3].cpu().numpy(), phase[2:3].cpu().numpy(), wm, wp)
+    assert rel < 3e-6 and dphi < 2e-3
+    op = dm.PhaseRetrievalOperator(1024, 160, 1024, noiser=dm.get_noiser("gaussian", 0.0))
+    assert torch.equal(op.forward(wav.to(DEV)), mag)
+    ph = phase.cpu().numpy()
+    assert np.isin(ph[:, [0, 512]], np.float32([0.0, np.pi])).all()   # real DC / Nyquist bins: angle 0 or pi exactly
+    m512, p512 = dm.waveform_to_spectrogram(wav[:1, :20000].to(DEV), hop_length=512)
+    wm, wp = oi.waveform_to_spectrogram(wav[:1, :20000].numpy(), hop_length=512)
+    rel, dphi = _spectrogram_error(m512.cpu().numpy(), p512.cpu().numpy(), wm, wp)
+    assert tuple(m512.shape) == (1, 513, 40) and rel < 3e-6 and dphi < 2e-3
+    with pytest.raises(RuntimeError):
+        dm.waveform_to_spectrogram(wav[:, :500].to(DEV))
+
+
 def test_mean_squared_error_vs_reference_formula():
     from diffmusic_b200 import metrics
     from oracle import metrics as om

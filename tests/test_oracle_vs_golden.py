@@ -204,3 +204,30 @@ def test_inverse_mel_scale_is_the_minimum_norm_matrix():
     assert w_t.shape == (64, 513) and w_t.dtype == torch.float32
     assert rel_l2(torch.relu(torch.einsum("mk,bmt->bkt", w_t, mel)), live) < 2e-6
     assert not w_t[:, 0].any() and not w_t[:, 512].any()  # the filterbank has no weight on DC / Nyquist
+
+
+def _spectrogram_error(mag, phase, want_mag, want_phase):
+    """relative L2 error of mag * exp(i phase) (the phase alone is ill-conditioned where the magnitude vanishes and jumps
+    by 2 pi at the branch cut), and the largest wrapped phase error over the bins that carry energy"""
+    mag, phase, want_mag, want_phase = (np.asarray(a, np.float64) for a in (mag, phase, want_mag, want_phase))
+    z, w = mag * np.exp(1j * phase), want_mag * np.exp(1j * want_phase)
+    rel = np.linalg.norm(z - w) / np.linalg.norm(w)
+    loud = want_mag > 1e-3 * want_mag.max()
+    d = np.angle(np.exp(1j * (phase - want_phase)))
+    return rel, np.abs(d[loud]).max()
+
+
+@pytest.mark.parametrize("name", sorted(stubs.SPECTROGRAM_CASES))
+def test_waveform_to_spectrogram_oracle_matches_reference(name):
+    """oracle/istft.py waveform_to_spectrogram against the reference function's own output (diffmusic/utils.py:11-20 run
+    by tests/golden/make_istft_golden.py)."""
+    import os
+    from oracle import istft as oi
+    from tests.conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "istft.npz"))
+    wav = stubs.synth_clips(2, stubs.SPECTROGRAM_CASES[name], first=70).numpy()
+    mag, phase = oi.waveform_to_spectrogram(wav)
+    assert mag.shape == z[name + "_mag"].shape
+    rel, dphi = _spectrogram_error(mag, phase, z[name + "_mag"], z[name + "_phase"])
+    assert rel < 2e-6 and dphi < 2e-3
+    assert rel_l2(mag, z[name + "_mag"]) < 2e-6
