@@ -18,6 +18,8 @@
 // (three rotating slots in device memory: written / read / cleared), so nothing synchronises with the host.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "dm_common.cuh"
 
 namespace dm {
@@ -36,11 +38,12 @@ __device__ __forceinline__ void round_robin_pair(int n, int r, int k, int& i, in
 
 // state[0..2]: largest |<wi,wj>| / (|wi||wj|) over the significant pairs of sweep s in slot s % 3 (bits of a
 // non-negative double, so integer max orders them); state[3]: sweeps actually executed; state[4]: bits of |W|_F^2;
-// state[5]: converged flag.
+// state[5]: converged flag; state[6]: sweep counter of the graph-replayed path.
 __global__ void __launch_bounds__(kJacThreads) jacobi_round_kernel(double* __restrict__ W, int d, int n_even, int round,
                                                                    int sweep, double tol,
                                                                    unsigned long long* __restrict__ state) {
     if (state[5] != 0ull) return;  // converged in an earlier sweep (sticky)
+    if (sweep < 0) sweep = (int)state[6];  // graph replay: the sweep index lives on the device (jacobi_sweep_end_kernel)
     if (sweep > 0 && __longlong_as_double((long long)state[(sweep + 2) % 3]) <= tol) {
         if (threadIdx.x == 0) state[5] = 1ull;  // every CTA of this launch takes the same decision from the same slot
         return;
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(256) frob2_kernel(const double* __restrict__ W
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += red[w];
-        state[0] = state[1] = state[2] = state[3] = state[5] = 0ull;
+        state[0] = state[1] = state[2] = state[3] = state[5] = state[6] = 0ull;
         state[4] = (unsigned long long)__double_as_longlong(t);
     }
 }
@@ -257,11 +260,63 @@ __global__ void __launch_bounds__(128) gather_rows_kernel_h(const __half* __rest
     }
 }
 
+__global__ void jacobi_sweep_end_kernel(unsigned long long* __restrict__ state) { state[6] += 1ull; }
+
+// DM_JACOBI_GRAPH=0 keeps the plain launch loop
+static bool jacobi_use_graph() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DM_JACOBI_GRAPH");
+        v = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+    }
+    return v != 0;
+}
+// capture happens on a private stream (the caller's may be the legacy default stream, which cannot be captured)
+static cudaStream_t jacobi_capture_stream() {
+    static thread_local cudaStream_t cap[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (cap[dev] == nullptr && cudaStreamCreateWithFlags(&cap[dev], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        cap[dev] = nullptr;
+    }
+    return cap[dev];
+}
+
+// One sweep = n_even - 1 dependent rounds of ~2 us kernels: launched one by one the host (and the launch path) bound the
+// solve.  The rounds of ONE sweep are captured into a CUDA graph once per solve (the sweep index is read from
+// state[6] on the device, so every sweep replays the same graph) and the graph is launched max_sweeps times.
 static int jacobi_rows(double* W, int d, int max_sweeps, double tol, unsigned long long* state, cudaStream_t st) {
     frob2_kernel<<<1, 256, 0, st>>>(W, (long long)d * d, state);
     DM_LAUNCHED();
     const int n_even = d + (d & 1);
     const size_t smem = 2 * (size_t)d * sizeof(double);
+    cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+    DM_CUDA(cudaStreamIsCapturing(st, &capturing));
+    cudaStream_t cap = nullptr;
+    if (jacobi_use_graph() && capturing == cudaStreamCaptureStatusNone && n_even - 1 >= 16)
+        cap = jacobi_capture_stream();
+    if (cap != nullptr) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        DM_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+        for (int r = 0; r < n_even - 1; ++r)
+            jacobi_round_kernel<<<n_even / 2, kJacThreads, smem, cap>>>(W, d, n_even, r, -1, tol, state);
+        jacobi_sweep_end_kernel<<<1, 1, 0, cap>>>(state);
+        cudaError_t e = cudaStreamEndCapture(cap, &graph);
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph != nullptr) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(DM_ERR_CUDA, "%s: capturing a Jacobi sweep failed: %s", __func__, cudaGetErrorString(e));
+        }
+        for (int s = 0; s < max_sweeps && e == cudaSuccess; ++s) e = cudaGraphLaunch(exec, st);
+        cudaGraphExecDestroy(exec);  // released once the launches in flight have completed
+        if (e != cudaSuccess)
+            return fail(DM_ERR_CUDA, "%s: launching a Jacobi sweep failed: %s", __func__, cudaGetErrorString(e));
+        g_launches.fetch_add((unsigned long long)max_sweeps * (unsigned long long)n_even, std::memory_order_relaxed);
+        return DM_OK;
+    }
     for (int s = 0; s < max_sweeps; ++s)
         for (int r = 0; r < n_even - 1; ++r) {
             jacobi_round_kernel<<<n_even / 2, kJacThreads, smem, st>>>(W, d, n_even, r, s, tol, state);
