@@ -88,7 +88,7 @@ def calculate_embd_statistics_online(arrays, group=None):
 # ---------------------------------------------------------------------------------------------------------------------
 # Frechet distance and FAD-inf (fadtk/fad.py:50-119, 303-350)
 JACOBI_MAX_SWEEPS = 40        # cap of the retry
-JACOBI_FIRST_SWEEPS = 16      # launches enqueued up front: sweeps * (d - 1) per solve, no-ops once converged
+JACOBI_FIRST_SWEEPS = 16      # sweeps enqueued up front (one graph replay of d - 1 rounds each), no-ops once converged
 JACOBI_TOL = 1e-14
 
 
@@ -157,6 +157,17 @@ class FADInfResults(tuple):
     points = property(lambda s: s[3])
 
 
+SCORE_INF_STREAMS = 4
+_STREAMS = {}
+
+
+def _side_streams(dev, k):
+    pool = _STREAMS.setdefault(str(dev), [])
+    while len(pool) < k:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:k]
+
+
 def score_inf(mu_base, cov_base, embeds, steps=25, min_n=500):
     """fadtk/fad.py:303-350 with the statistics on the GPU: for `steps` sample sizes n between min_n and len(embeds),
     draw n rows with replacement (np.random.choice -- the reference's generator and draw order, so a seeded run picks
@@ -171,14 +182,25 @@ def score_inf(mu_base, cov_base, embeds, steps=25, min_n=500):
     mu_b, cov_b = _as_dev_f64(np.atleast_1d(mu_base), dev), _as_dev_f64(np.atleast_2d(cov_base), dev)
     ns = [int(n) for n in np.linspace(min_n, N, steps)]
     outs, args = [], []
-    for n in ns:
+    # The points are independent and a Jacobi solve is a chain of ~2-4 us rounds that leaves most of the GPU idle: they
+    # are spread round-robin over a few side streams (rows are still drawn in the reference's order on the host).
+    cur = torch.cuda.current_stream(dev)
+    pool = _side_streams(dev, min(SCORE_INF_STREAMS, len(ns))) if SCORE_INF_STREAMS > 1 else [cur]
+    for s in pool:
+        if s is not cur:
+            s.wait_stream(cur)  # x and the baseline statistics are ready
+    for i, n in enumerate(ns):
         indices = np.random.choice(N, size=n, replace=True)
-        idx = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int64)).to(dev)
-        sub = torch.empty((n, d), device=dev, dtype=torch.float16)
-        _lib.call("dm_fad_gather_rows", x.data_ptr(), N, d, idx.data_ptr(), n, sub.data_ptr(), _lib.stream())
-        mu, cov = EmbeddingMoments(d, device=dev).update(sub).finalize()
-        args.append((mu_b, cov_b, mu, cov))
-        outs.append(frechet_distance_device(*args[-1]))
+        with torch.cuda.stream(pool[i % len(pool)]):
+            idx = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int64)).to(dev)
+            sub = torch.empty((n, d), device=dev, dtype=torch.float16)
+            _lib.call("dm_fad_gather_rows", x.data_ptr(), N, d, idx.data_ptr(), n, sub.data_ptr(), _lib.stream())
+            mu, cov = EmbeddingMoments(d, device=dev).update(sub).finalize()
+            args.append((mu_b, cov_b, mu, cov))
+            outs.append(frechet_distance_device(*args[-1]))
+    for s in pool:
+        if s is not cur:
+            cur.wait_stream(s)
     fad = _frechet_checked(outs, args)[:, 0].numpy()  # one synchronisation for the whole sweep (+ rare retries)
     results = [[n, float(s)] for n, s in zip(ns, fad)]
     ys = np.array(results)

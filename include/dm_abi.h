@@ -279,8 +279,9 @@ int dm_fad_gather_rows(const void* x_f16, long long N, int d, const long long* i
                        dm_stream_t stream);
 /* Singular values (= eigenvalues for a symmetric PSD input) of the d x d row-major float64 matrix W by one-sided
  * Jacobi row rotations, in place (W ends with mutually orthogonal rows); eig[k] = |row k|.  state: 8 x uint64 of device
- * scratch; state[3] = sweeps executed.  All launches of max_sweeps sweeps are enqueued; they become no-ops once the
- * largest normalised inner product of a sweep is <= tol. */
+ * scratch; state[3] = sweeps executed.  All max_sweeps sweeps are enqueued (each one replay of a CUDA graph holding its d - 1
+ * rounds; DM_JACOBI_GRAPH=0: one launch per round); they become no-ops once the largest normalised inner product of a
+ * sweep is <= tol. */
 int dm_sym_eig_jacobi(double* W, int d, int max_sweeps, double tol, double* eig, unsigned long long* state,
                       dm_stream_t stream);
 /* doubles of device scratch for dm_frechet_distance */

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--dims", type=int, nargs="+", default=[128, 512, 768])
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--cpu", type=int, default=1)
+    ap.add_argument("--inf", type=int, default=0, help="also time score_inf at this embedding width")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     rows = []
@@ -54,7 +55,25 @@ def main():
             row["cpu_threads"] = torch.get_num_threads()
             row["rel_diff_vs_cpu"] = abs(row["value"] - want) / abs(want)
         rows.append(row)
-    print(json.dumps({"what": "dm_frechet_distance device time per solve pair",
+    inf = None
+    if a.inf:  # FAD-inf (fadtk/fad.py:303-350): 25 bootstrap points = 25 x (gather + moments + Frechet distance)
+        d, n = a.inf, 8000
+        rng = np.random.default_rng(3)
+        base = rng.standard_normal((4096, d)) * 0.6 + 0.2
+        emb = (rng.standard_normal((n, d)) * 0.5 + 0.25).astype(np.float16)
+        mu_b, cov_b = base.mean(0), np.cov(base, rowvar=False)
+        inf = {"d": d, "embeddings": n, "points": 25}
+        for streams in (1, fad.SCORE_INF_STREAMS):
+            fad.SCORE_INF_STREAMS = streams
+            np.random.seed(0)
+            fad.score_inf(mu_b, cov_b, emb, steps=3, min_n=500)  # warm-up
+            np.random.seed(0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = fad.score_inf(mu_b, cov_b, emb, steps=25, min_n=500)
+            inf[f"wall_ms_{streams}_stream"] = (time.perf_counter() - t0) * 1e3
+            inf[f"score_{streams}_stream"] = float(res.score)
+    print(json.dumps({"what": "dm_frechet_distance device time per solve pair", "fad_inf": inf,
                       "jacobi_graph": os.environ.get("DM_JACOBI_GRAPH", "1") != "0", "rows": rows}, indent=1))
 
 
