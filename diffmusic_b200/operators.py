@@ -21,7 +21,6 @@ import os
 import torch
 
 from . import _lib, tables
-from .noise import GaussianNoise
 
 _MODE_MEL_DB, _MODE_PHASE_MEL, _MODE_PHASE_WAV = 0, 1, 2
 _RESID_CHUNK = 4096

@@ -12,7 +12,6 @@ streams stay aligned with the reference.
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import Optional
 

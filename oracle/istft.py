@@ -18,7 +18,6 @@ Published algorithms restated in float64:
 from __future__ import annotations
 
 import numpy as np
-import torch
 import torchaudio
 
 

@@ -231,3 +231,31 @@ def test_waveform_to_spectrogram_oracle_matches_reference(name):
     rel, dphi = _spectrogram_error(mag, phase, z[name + "_mag"], z[name + "_phase"])
     assert rel < 2e-6 and dphi < 2e-3
     assert rel_l2(mag, z[name + "_mag"]) < 2e-6
+
+
+@pytest.mark.parametrize("hop,T", [(160, 12), (512, 37), (1024, 5), (160, 2)])
+def test_istft_oracle_vs_live_libraries(hop, T):
+    """The GPU parity tests use oracle/istft.py at hops the reference fixture does not cover: hold it to the live
+    torchaudio InverseMelScale + torch.istft (the calls the reference makes) there as well."""
+    import torchaudio
+    from oracle import istft as oi
+    g = torch.Generator().manual_seed(100 + hop + T)
+    mel = torch.rand(2, 1, T, 64, generator=g) * 5.0 - 0.5
+    phase = (torch.rand(2, 513, T, generator=g) * 2.0 - 1.0) * np.pi
+    lin = torchaudio.transforms.InverseMelScale(n_stft=513, n_mels=64, sample_rate=16000)(mel.squeeze(1).permute(0, 2, 1))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = torch.istft(lin * torch.exp(1j * phase), n_fft=1024, hop_length=hop, win_length=1024)
+    got = oi.mel_spectrogram_to_waveform_with_phase(mel.numpy(), phase.numpy(), hop_length=hop)
+    assert got.shape == tuple(want.shape) == (2, hop * (T - 1))
+    assert rel_l2(got, want) < 3e-6
+
+
+def test_waveform_to_spectrogram_oracle_vs_live_torch():
+    from oracle import istft as oi
+    wav = stubs.synth_clips(2, 20000, first=90)
+    spec = torch.stft(wav, 1024, hop_length=512, win_length=1024, return_complex=True)
+    mag, phase = oi.waveform_to_spectrogram(wav.numpy(), hop_length=512)
+    rel, dphi = _spectrogram_error(mag, phase, spec.abs().numpy(), spec.angle().numpy())
+    assert mag.shape == tuple(spec.shape) and rel < 2e-6 and dphi < 2e-3
