@@ -26,6 +26,7 @@ prompt conditioning and classifier-free guidance, `vae`, `vocoder`).  Multi-GPU:
 from __future__ import annotations
 
 import inspect
+from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -56,13 +57,14 @@ class BatchedGuidedSampler:
     noise_predictor  callable `(latent_model_input, t) -> eps`; if it has a `clips` parameter it also receives the indices
                      (into the call's batch) of the clips in this sub-batch, for per-clip conditioning across restarts
     vae, vocoder     the differentiable decoders `scheduler.step` backpropagates through
+    max_graphs       captured steps kept alive in graph mode (one per batch size and measurement tensor)
     step keywords    eta, ip_guidance_rate, supervised_space, original_waveform_length (+ eps for dsg / diffmusic through
                      `step_kwargs`): the keyword arguments of `scheduler.step` (pipeline_musicldm.py:726-739)
     """
 
     def __init__(self, scheduler, noise_predictor, vae, vocoder, *, num_inference_steps, original_waveform_length,
                  latent_shape=(8, 250, 16), eta=None, ip_guidance_rate=None, supervised_space="mel_spectrogram",
-                 graph=False, dtype=torch.float32, max_restarts=MAX_RESTARTS, step_kwargs=None):
+                 graph=False, dtype=torch.float32, max_restarts=MAX_RESTARTS, step_kwargs=None, max_graphs=2):
         self.scheduler = scheduler
         self.noise_predictor = noise_predictor
         self.vae, self.vocoder = vae, vocoder
@@ -83,7 +85,8 @@ class BatchedGuidedSampler:
             self._wants_clips = "clips" in inspect.signature(noise_predictor).parameters
         except (TypeError, ValueError):
             self._wants_clips = False
-        self._graphs = {}
+        self._graphs = OrderedDict()
+        self.max_graphs = max(1, int(max_graphs))
 
     # ---- pieces of the reference pipeline -------------------------------------------------------------------------------
     def prepare_latents(self, generators, batch, device):
@@ -117,8 +120,15 @@ class BatchedGuidedSampler:
         key = (batch, measurement.data_ptr(), tuple(measurement.shape))
         g = self._graphs.get(key)
         if g is None:
+            # a captured step holds its measurement, static buffers and the networks' activations: keep only the most
+            # recent ones (normally the full batch and a restart sub-batch).  Every trajectory ends with a host read of
+            # its distances, so no replay of an evicted graph is still in flight here.
+            while len(self._graphs) >= self.max_graphs:
+                self._graphs.popitem(last=False)
             g = self._graphs[key] = GraphedGuidedStep(self.scheduler, (batch,) + self.latent_shape, dtype=self.dtype,
                                                       device=device, measurement=measurement, **self.step_kwargs)
+        else:
+            self._graphs.move_to_end(key)
         return lambda eps, t, x, gens: g(eps, t, x, generator=gens)
 
     # ---- one trajectory of a (sub-)batch ---------------------------------------------------------------------------------

@@ -107,3 +107,33 @@ def test_arguments():
     g = torch.Generator().manual_seed(5)
     shared = sampler(lambda x, t: torch.tanh(x))(torch.zeros(1, 1), g, batch=3)
     assert shared.latents.shape == (3,) + SHAPE
+
+
+def test_graph_mode_keeps_a_bounded_number_of_captured_steps(monkeypatch):
+    """graph=True builds one captured step per (batch size, measurement tensor); the cache is an LRU of `max_graphs`."""
+    import diffmusic_b200.graph as graph_mod
+    built = []
+
+    class FakeGraphedStep:
+        def __init__(self, scheduler, shape, *, dtype, device, measurement, **kw):
+            self.sched, self.kw = scheduler, dict(kw, measurement=measurement)
+            built.append((shape[0], measurement.data_ptr()))
+
+        def __call__(self, eps, t, x, generator=None):
+            kw = {k: v for k, v in self.kw.items() if k not in ("vae", "vocoder")}
+            return self.sched.step(eps, t, x, generator=generator, **kw)
+
+    monkeypatch.setattr(graph_mod, "GraphedGuidedStep", FakeGraphedStep)
+    s = sampler(Predictor(poison=[1]), eta=1.0, graph=True, max_graphs=2)
+    meas = [torch.full((3, 1), float(i)) for i in range(3)]
+    eager = sampler(Predictor(poison=[1]), eta=1.0)(meas[0], gens(range(3)))
+    out = s(meas[0], gens(range(3)))
+    assert out.restarts == [0, 1, 0] and torch.equal(out.latents, eager.latents)
+    assert [b for b, _ in built] == [3, 1] and len(s._graphs) == 2  # full batch + the restart sub-batch
+    s.noise_predictor = Predictor()
+    s(meas[0], gens(range(3)))
+    assert len(built) == 2  # same measurement tensor, same batch: the captured step is reused
+    s(meas[1], gens(range(3)))
+    s(meas[2], gens(range(3)))
+    assert len(built) == 4 and len(s._graphs) == 2
+    assert [k[1] for k in s._graphs] == [meas[1].data_ptr(), meas[2].data_ptr()]
