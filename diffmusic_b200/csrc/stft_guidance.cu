@@ -12,6 +12,7 @@
 #include "dm_common.cuh"
 #include "stft_frame.cuh"
 #include "stft_pair.cuh"
+#include "stft_params.cuh"
 
 namespace dm {
 
@@ -19,47 +20,6 @@ constexpr int kCtaThreads = 256;
 constexpr int kGroups = kCtaThreads / kGroupThreads;
 constexpr int kTileLd = kMels + 1;  // padded row of the ref/out tile
 __host__ __device__ constexpr int tile_floats(int nf) { return (nf * kTileLd + 3) & ~3; }
-
-struct StftParams {
-    StftTables tab;
-    int clamp, hop, B, nf, ntiles;
-    long long Ly, T, y_bstride, ref_bstride;
-    const void* y;  // waveform-typed (y_io)
-    int y_io;
-    const float* mask;
-    const float* ref;
-    const float* noise;
-    float sigma;
-    float* out;
-    float* ypbar;
-    float* partial;
-};
-
-// ---- TMA bulk copy (cp.async.bulk) of an interior tile's contiguous signal span into shared memory ----
-__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bulk_load_span(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_addr_u32(bar))
-                 : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_addr_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_addr_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_addr_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
-}
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kGroupThreads)); }
 
@@ -509,7 +469,7 @@ using namespace dm;
 static int g_stft_engine = DM_STFT_ENGINE_AUTO;
 
 extern "C" int dm_stft_set_engine(int engine) {
-    DM_REQUIRE(engine == DM_STFT_ENGINE_AUTO || engine == DM_STFT_ENGINE_FRAME);
+    DM_REQUIRE(engine == DM_STFT_ENGINE_AUTO || engine == DM_STFT_ENGINE_FRAME || engine == DM_STFT_ENGINE_PAIR);
     g_stft_engine = engine;
     return DM_OK;
 }
@@ -567,6 +527,8 @@ extern "C" int dm_stft_guidance_io(const dm_stft_tables* tab, int mode, int clam
     DM_REQUIRE(tab->mel_wstride >= 1 && tab->mel_wstride <= 64);
     dim3 grid(p.ntiles, B), block(kCtaThreads);
     cudaStream_t st = as_stream(stream);
+    // warp-per-frame-pair engine (stft_warp.cu): hops that keep the gathered overlap-add 16-byte aligned, one round per tile
+    if ((hop & 3) == 0 && p.nf <= 16 && g_stft_engine == DM_STFT_ENGINE_AUTO) return launch_stft_warp(p, mode, st);
     if ((hop & 1) == 0 && (g_stft_engine != DM_STFT_ENGINE_FRAME || y_dtype != DM_IO_F32)) {  // frame-pair kernel
         size_t smem2 = stft_pair_smem_bytes(p.nf, hop, tab->mel_wstride);
         if (smem2 > 227 * 1024)

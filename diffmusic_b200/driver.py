@@ -140,11 +140,15 @@ class BatchedGuidedSampler:
         hist = torch.zeros((len(timesteps), len(ids)), device=dev, dtype=torch.float32)
         rewind = _rewindable(gens)
         start = per_step = None
-        for i, t in enumerate(timesteps):
+        # one host read of the schedule per trajectory: the step needs Python ints (coefficient lookup), and reading
+        # them one by one from the device tensor would synchronise the host with the stream at every step
+        t_ints = timesteps.tolist()
+        for i, t_int in enumerate(t_ints):
+            t = timesteps[i]  # the noise predictor still gets the tensor element the reference pipelines pass
             eps = self._predict(sched.scale_model_input(latents, t), t, ids)
             if i == 0 and rewind:
                 start = [g.get_offset() for g in gens]
-            out = step(eps, t, latents, gens)
+            out = step(eps, t_int, latents, gens)
             if i == 0 and rewind:  # every step consumes the same amount of every clip's stream
                 per_step = [g.get_offset() - s for g, s in zip(gens, start)]
             per_clip = getattr(out, "loss_per_clip", None)

@@ -54,7 +54,12 @@ class GraphedGuidedStep:
             self._ir_dev = torch.zeros(self.op.ir_length, device=dev, dtype=torch.float32)
             self.op.static_ir = self._ir_dev
         t0 = int(scheduler.timesteps[0]) if warmup_timestep is None else int(warmup_timestep)
-        self._prepare(t0, None, None)
+        # the warm-up inputs must not shift anybody's random streams: the step noise of a generator-less warm-up comes
+        # from the device's default generator and a dereverberation impulse response from the global CPU generator;
+        # both states are restored, so a seeded run that builds a graph (including the driver's restart sub-batch
+        # graphs) stays aligned with the eager and the reference streams
+        with torch.random.fork_rng(devices=[dev]):
+            self._prepare(t0, None, None)
         scheduler._coef_dev = self.coef
         # warm-up on a side stream (allocator pools, lazy module init, cached measurement transform), then capture
         side = torch.cuda.Stream(device=dev)
@@ -89,10 +94,11 @@ class GraphedGuidedStep:
                 self.z.copy_(z, non_blocking=True)
         elif self.eta > 0:
             self.sched.draw_step_noise(self.eta, generator, variance_noise, self.e)  # DDIM: discarded draw
-        row = self._coef_rows.get(timestep)
+        key = (timestep, self.sched.num_inference_steps)  # t_prev, hence sqrt_p / dir_coef / std, depends on the step count
+        row = self._coef_rows.get(key)
         if row is None:  # one pinned 32-byte row per timestep, built once (host-side scalar math is slow)
             row = self.sched.coef_vector(timestep, self.eta, self.n_clip).clone().pin_memory()
-            self._coef_rows[timestep] = row
+            self._coef_rows[key] = row
         self.coef.copy_(row, non_blocking=True)
         if self._ir_host is not None:
             ir = self.op.generate_impulse_response(ir_length=self.op.ir_length, decay_factor=self.op.decay_factor)

@@ -86,24 +86,25 @@ def _grad_buffer(dwav, B, L, device, dtype=torch.float32):
 
 
 def _frames_per_tile(B, T, device):
-    """frames per CTA tile of the frame-pair STFT kernel (stft_guidance.cu: 4 groups x 2 frames = 8 frames per round).
+    """frames per CTA tile of the STFT guidance kernel.
 
-    Shared memory per CTA = 85 KB (FFT cells of 4 groups, window, filterbank by band and by bin) + 8 B per staged
-    signal sample and accumulator, so tiles of up to 15 frames keep 2 CTAs resident per SM.  Cost model: a CTA costs `ceil(nf / 8)` rounds plus a fixed
-    staging overhead, CTAs run in waves of 2 x SMs; pick the cheapest size, larger tiles on ties (fewer re-staged
-    samples).  6 frames is the minimum for the bit-reproducible two-tile overlap of the cotangent.
-    `DM_STFT_FRAMES_PER_TILE` overrides the choice (tuning / tests)."""
+    The warp-per-frame-pair engine (csrc/stft_warp.cu) gives each of its 8 warps one frame pair, so a tile holds at most
+    16 frames; its persistent grid is 2 CTAs per SM.  Cost model: a CTA walks `ceil(ctas / slots)` tiles, a tile costs
+    its frames plus a fixed staging / barrier overhead; pick the cheapest even size, larger tiles on ties (fewer
+    re-staged samples and overlapping cotangent adds).  6 frames is the minimum for the bit-reproducible two-tile overlap
+    of the cotangent.  `DM_STFT_FRAMES_PER_TILE` overrides the choice (tuning / tests; > 16 selects the 64-thread
+    frame-pair kernel of stft_guidance.cu)."""
     forced = os.environ.get("DM_STFT_FRAMES_PER_TILE")
     if forced:
-        return max(6, min(22, int(forced)))  # > 15: one CTA per SM
+        return max(6, min(22, int(forced)))
     key = (B, T, str(device))
     if key in _NF_CACHE:
         return _NF_CACHE[key]
     slots = 2 * torch.cuda.get_device_properties(device).multi_processor_count
-    best, best_cost = 6, float("inf")
-    for nf in range(6, 16):
+    best, best_cost = 16, float("inf")
+    for nf in range(8, 17, 2):
         ctas = B * math.ceil(T / nf)
-        cost = math.ceil(ctas / slots) * (math.ceil(nf / 8) + 0.35)
+        cost = math.ceil(ctas / slots) * (nf + 3)
         if cost <= best_cost + 1e-9:
             best, best_cost = nf, min(cost, best_cost)
     _NF_CACHE[key] = best

@@ -131,6 +131,24 @@ class _GuidedBase(DDIMBase):
                   float(self.config.clip_sample_range), self._coef_ptr(), io, _lib.stream())
         return x0, (x0 if pub is None else pub), leaf
 
+    def _clip_grad_mask(self, g0, x, eps, c):
+        """clip_sample=True (the constructor default; every shipped config sets False): DPS / DSG / DiffMusic
+        differentiate w.r.t. `sample` THROUGH the base step's `pred_original_sample.clamp(+-clip_sample_range)`
+        (scheduling_dps.py:165-175), so autograd zeroes the gradient where the unclipped x0 lies outside the range
+        (clamp passes it at equality).  The fused update kernels start from dLoss/dx0 of the clipped x0, so the mask is
+        applied to that gradient here; the unclipped x0 is recomputed with the arithmetic of dm_sched_x0.  Plain torch
+        elementwise work on a configuration outside the shipped ones (MPGD leafs the clipped x0: no mask)."""
+        if not self.config.clip_sample:
+            return g0
+        if self._coef_dev is not None:  # graph mode: per-timestep scalars live on the device
+            sa, sb = self._coef_dev[0], self._coef_dev[1]
+        else:
+            sa, sb = c["sqrt_a"], c["sqrt_b"]
+        t = (x.float() - sb * eps.float()) / sa
+        r = float(self.config.clip_sample_range)
+        keep = (t >= -r) & (t <= r)
+        return (g0 * keep.to(g0.dtype)).contiguous()
+
     @staticmethod
     def _leaf_scale(vae):
         """1 / vae.config.scaling_factor as the fp32 value torch multiplies by (scheduling_dps.py:195-197)."""
@@ -296,6 +314,7 @@ class DPSScheduler(_GuidedBase):
         x0, x0_pub, leaf = self._x0(x, eps, c, io, leaf_scale=ls)
         losses, g0 = self._guidance(leaf, measurement, vae, vocoder, original_waveform_length, supervised_space,
                                     sample.dtype)
+        g0 = self._clip_grad_mask(g0, x, eps, c)
         prev = torch.empty_like(x)
         losses, total = self._loss_slot(losses)
         _lib.call("dm_sched_dps_update_io", x.data_ptr(), x0.data_ptr(), g0.data_ptr(), ls, _lib.ptr(z),
@@ -347,6 +366,7 @@ class _SphericalBase(_GuidedBase):
         # base step called without eta (scheduling_dsg.py:178-186): no RNG draw
         x0, x0_pub, leaf = self._x0(x, e, c, io, leaf_scale=ls)
         losses, g0 = self._guidance(leaf, measurement, vae, vocoder, L, supervised_space, sample.dtype)
+        g0 = self._clip_grad_mask(g0, x, e, c)
         B = x.shape[0]
         n_clip = x.numel() // B
         prev = torch.empty_like(x)
@@ -403,6 +423,36 @@ class DiffMusicScheduler(_SphericalBase):
                                     supervised_space, _noise)
 
 
+def _reference_ditto():
+    """The reference's own DITTOScheduler.  With the drop-in ahead of the reference on sys.path the package
+    `diffmusic.schedulers` is ours (its search path is extended with the reference's directory, dropin/diffmusic/
+    schedulers/__init__.py); should the import still not resolve, the file is located on sys.path and loaded directly."""
+    import importlib
+    import importlib.util
+    import os
+    import sys
+    try:
+        return importlib.import_module("diffmusic.schedulers.scheduling_ditto").DITTOScheduler
+    except ModuleNotFoundError as exc:
+        if exc.name not in ("diffmusic", "diffmusic.schedulers", "diffmusic.schedulers.scheduling_ditto"):
+            raise  # the reference file was found, one of ITS dependencies (e.g. diffusers) is missing
+        first = exc
+    for entry in sys.path:
+        path = os.path.join(entry or ".", "diffmusic", "schedulers", "scheduling_ditto.py")
+        if os.path.isfile(path):
+            spec = importlib.util.spec_from_file_location("diffmusic.schedulers.scheduling_ditto", path)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[spec.name] = mod
+            try:
+                spec.loader.exec_module(mod)
+            except BaseException:
+                sys.modules.pop(spec.name, None)
+                raise
+            return mod.DITTOScheduler
+    raise ImportError("DITTOScheduler is not part of diffmusic_b200; put the reference's "
+                      "diffmusic/schedulers/scheduling_ditto.py on sys.path to use it") from first
+
+
 def get_scheduler(scheduler_name):
     """diffmusic/schedulers/__init__.py:9-24."""
     table = {"ddim": DDIMScheduler, "dps": DPSScheduler, "mpgd": MPGDScheduler, "dsg": DSGScheduler,
@@ -411,11 +461,6 @@ def get_scheduler(scheduler_name):
         return table[scheduler_name]
     if scheduler_name == "ditto":
         # DITTO back-propagates through the whole sampling chain including the UNet (scheduling_ditto.py:187-208):
-        # out of the hot-path scope, so the reference class is re-exported when the reference is importable.
-        try:
-            import importlib
-            return importlib.import_module("diffmusic.schedulers.scheduling_ditto").DITTOScheduler
-        except Exception as exc:  # pragma: no cover - depends on the deployment
-            raise ImportError("DITTOScheduler is not part of diffmusic_b200; put the reference's "
-                              "diffmusic/schedulers/scheduling_ditto.py on sys.path to use it") from exc
+        # out of the hot-path scope, so the reference class is re-exported (diffmusic/schedulers/__init__.py:19-20).
+        return _reference_ditto()
     raise ValueError(f"Unknown scheduler: {scheduler_name}")

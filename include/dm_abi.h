@@ -134,11 +134,15 @@ typedef struct dm_stft_tables {
 #define DM_STFT_PHASE_MEL 1 /* |X|   -> mel [-> clamp +-80]                                                    */
 #define DM_STFT_PHASE_WAV 2 /* |X|                                                                             */
 
-/* Kernel selection for dm_stft_guidance (process-wide; for A/B measurements and tests).  AUTO: the frame-pair kernel
- * (two frames per 64-thread group, 128-bit shared-memory FFT traffic) whenever hop is even, else the frame-at-a-time
- * kernel.  FRAME: always the frame-at-a-time kernel.  Both compute the same quantities (<= 1e-6 apart). */
+/* Kernel selection for dm_stft_guidance (process-wide; for A/B measurements and tests).
+ *   AUTO : the warp-per-frame-pair kernel (one warp = two frames as one 32 x 32 complex FFT, csrc/stft_warp.cu) when
+ *          hop % 4 == 0 and frames_per_tile <= 16; else the 64-thread frame-pair kernel when hop is even; else the
+ *          frame-at-a-time kernel.
+ *   PAIR : the 64-thread frame-pair kernel (even hops).      FRAME: always the frame-at-a-time kernel (fp32 waveforms).
+ * All three compute the same quantities (<= 1e-6 apart). */
 #define DM_STFT_ENGINE_AUTO 0
 #define DM_STFT_ENGINE_FRAME 1
+#define DM_STFT_ENGINE_PAIR 2
 int dm_stft_set_engine(int engine);
 
 /* number of frame tiles per clip for a signal of Ly samples: ceil((1 + Ly/hop) / frames_per_tile) */

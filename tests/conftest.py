@@ -35,6 +35,12 @@ def golden_steps():
     return np.load(os.path.join(GOLDEN, "steps.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_steps_clip():
+    """clip_sample=True cases (tests/golden/make_golden.py::make_steps_clip, from the reference's scheduler files)"""
+    return np.load(os.path.join(GOLDEN, "steps_clip.npz"))
+
+
 def rel_l2(a, b):
     """relative L2 error of a against reference b (numpy or torch)."""
     import torch

@@ -203,6 +203,143 @@ void emul_stft_guidance_pair(const EmulTables* e, int mode, int clamp, const flo
     else run_pair<kModePhaseWav>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-per-frame-pair pipeline (diffmusic_b200/csrc/stft_warp.cuh): 32 "lanes" carry two frames as one 32 x 32 complex
+// FFT; a shuffle is a phase boundary (all lanes publish, then all lanes read), the gathered overlap-add as in
+// stft_warp_kernel.
+#include "../../diffmusic_b200/csrc/stft_warp.cuh"
+
+template <int MODE>
+static void run_warp(const EmulTables& e, int clamp, const float* y, long long Ly, int hop, const float* mask,
+                     const float* ref, float* out, float* ypbar, double* sumsq) {
+    StftTables t{e.window, reinterpret_cast<const cf*>(e.tw512), reinterpret_cast<const cf*>(e.w1024),
+                 e.mel_kstart, e.mel_klen, e.mel_w, e.mel_wstride, e.bin_m0, e.bin_w0, e.bin_w1};
+    const long long T = 1 + Ly / hop;
+    std::vector<float> raw(kWarpBufFloats + 8, 0.f), fa(kNfft), fb(kNfft);
+    float* wbuf = raw.data();
+    while (reinterpret_cast<uintptr_t>(wbuf) & 15) ++wbuf;
+    cf* xbuf = reinterpret_cast<cf*>(wbuf);
+    f2* P = reinterpret_cast<f2*>(wbuf + kWarpPOff);
+    f2* melbar = reinterpret_cast<f2*>(wbuf + kWarpMelbarOff);
+    std::vector<f2> win2(kH);
+    for (int i = 0; i < kH; ++i) win2[i] = f2{0.5f * t.window[i], 0.5f * t.window[i + kH]};
+    std::vector<f4> tw4raw(16 * 32 + 1);
+    f4* tw4 = tw4raw.data();
+    while (reinterpret_cast<uintptr_t>(tw4) & 15) tw4 = reinterpret_cast<f4*>(reinterpret_cast<char*>(tw4) + 4);
+    std::vector<f4> tw4v(16 * 32);
+    for (int i = 0; i < 16 * 32; ++i) {
+        const int m = i >> 5, l = i & 31;
+        const cf a = w1024_any(t.w1024, l * (2 * m)), b = w1024_any(t.w1024, l * (2 * m + 1));
+        tw4v[i] = f4{a.x, a.y, b.x, b.y};
+    }
+    std::vector<f2> binw(kBins);
+    std::vector<unsigned char> binm(kBins);
+    for (int k = 0; k < kBins; ++k) { binw[k] = f2{e.bin_w0[k], e.bin_w1[k]}; binm[k] = (unsigned char)e.bin_m0[k]; }
+    const PairBinTab bins{binw.data(), binm.data()};
+    std::vector<WarpMelConsts> mc(32);
+    for (int l = 0; l < 32; ++l) load_warp_mel_consts(l, t, mc[l]);
+    struct Lane { cf v[32]; WarpX x; f2 g[17]; f2 en[17]; cf snd[16]; cf rcv[16]; };
+    std::vector<Lane> L(32);
+    if (ypbar) std::memset(ypbar, 0, sizeof(float) * (Ly + 1024));
+    double acc = 0.0;
+    for (long long f = 0; f < T; f += 2) {
+        const bool has_b = f + 1 < T;
+        const long long f2i = has_b ? f + 1 : f;
+        for (int n = 0; n < kNfft; ++n) {
+            long long ja = reflect_src(f * hop + n, Ly), jb = reflect_src(f2i * hop + n, Ly);
+            fa[n] = y[ja] * (mask ? mask[ja] : 1.f);
+            fb[n] = y[jb] * (mask ? mask[jb] : 1.f);
+        }
+        for (int l = 0; l < 32; ++l) {
+            warp_load_frames(l, fa.data(), fb.data(), win2.data(), L[l].v);
+            dft32<-1>(L[l].v);
+            warp_twiddle_store<-1>(l, L[l].v, tw4v.data(), xbuf);
+        }
+        for (int l = 0; l < 32; ++l) {
+            warp_xchg_load(l, xbuf, L[l].v);
+            dft32<-1>(L[l].v);
+            warp_split_send(l, L[l].v, L[l].snd);
+        }
+        for (int l = 0; l < 32; ++l)
+            for (int i = 0; i < 16; ++i) L[l].rcv[i] = L[(32 - l) & 31].snd[i];
+        for (int l = 0; l < 32; ++l) {
+            warp_split_recv(l, L[l].v, L[l].rcv, L[l].x);
+            warp_energies<MODE>(L[l].x, L[l].en);
+        }
+        if (MODE == kModePhaseWav) {
+            for (int l = 0; l < 32; ++l)
+                for (int i = 0; i < 17; ++i) {
+                    const int k = (i < 16) ? l + 32 * i : kH;
+                    L[l].g[i] = f2{0.f, 0.f};
+                    if (!(i < 16 || l == 0)) continue;
+                    const f2 mag = L[l].en[i];
+                    if (out) { out[k * T + f] = mag.x; if (has_b) out[k * T + f2i] = mag.y; }
+                    if (ref) {
+                        float da = ref[k * T + f] - mag.x, db = ref[k * T + f2i] - mag.y;
+                        acc += (double)da * da;
+                        if (has_b) acc += (double)db * db;
+                        L[l].g[i] = f2{-da, -db};
+                    }
+                }
+        } else {
+            for (int l = 0; l < 32; ++l) {
+                warp_store_energies(l, L[l].en, P);
+                if (l < 8) melbar[64 + l] = f2{0.f, 0.f};
+            }
+            std::vector<f2> lo(32), hi(32);
+            for (int l = 0; l < 32; ++l) warp_mel_project(l, mc[l], e.mel_w, P, lo[l], hi[l]);
+            for (int l = 0; l < 32; ++l) {
+                const int ms[2] = {l, 63 - l};
+                const f2 mel[2] = {lo[l], hi[l]};
+                for (int q = 0; q < 2; ++q) {
+                    const int m = ms[q];
+                    float va, da, vb, db;
+                    mel_value<MODE>(mel[q].x, clamp != 0, va, da);
+                    mel_value<MODE>(mel[q].y, clamp != 0, vb, db);
+                    if (ref) {
+                        float ra = ref[m * T + f] - va, rb = ref[m * T + f2i] - vb;
+                        melbar[m] = f2{-ra * da, -rb * db};
+                        acc += (double)ra * ra;
+                        if (has_b) acc += (double)rb * rb;
+                    }
+                    if (out) { out[m * T + f] = va; if (has_b) out[m * T + f2i] = vb; }
+                }
+            }
+            if (ypbar)
+                for (int l = 0; l < 32; ++l) warp_bin_cotangents(l, bins, melbar, L[l].g);
+        }
+        if (!ypbar) continue;
+        for (int l = 0; l < 32; ++l) warp_pack_send<MODE>(l, L[l].x, L[l].g, L[l].v, L[l].snd);
+        for (int l = 0; l < 32; ++l)
+            for (int i = 0; i < 16; ++i) L[l].rcv[i] = L[(32 - l) & 31].snd[i];
+        for (int l = 0; l < 32; ++l) {
+            warp_pack_recv<MODE>(l, L[l].x, L[l].g, L[l].rcv, L[l].v);
+            dft32<+1>(L[l].v);
+        }
+        for (int l = 0; l < 32; ++l) warp_twiddle_store<+1>(l, L[l].v, tw4v.data(), xbuf);
+        for (int l = 0; l < 32; ++l) {
+            warp_xchg_load(l, xbuf, L[l].v);
+            dft32<+1>(L[l].v);
+        }
+        for (int l = 0; l < 32; ++l) warp_store_gradients(l, L[l].v, win2.data(), wbuf + kWarpGOff);
+        for (int n = 0; n < kNfft; ++n) {
+            ypbar[f * hop + n] += wbuf[kWarpGOff + n];
+            if (has_b) ypbar[f2i * hop + n] += wbuf[kWarpGOff + kNfft + n];
+        }
+    }
+    *sumsq = acc;
+}
+
+extern "C" {
+void emul_stft_guidance_warp(const EmulTables* e, int mode, int clamp, const float* y, long long Ly, int hop,
+                             const float* mask, const float* ref, float* out, float* ypbar, double* sumsq) {
+    if (mode == 0) run_warp<kModeMelDb>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
+    else if (mode == 1) run_warp<kModePhaseMel>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
+    else run_warp<kModePhaseWav>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
+}
+
 // LogSpectralDistance frames (csrc/metrics.cu lsd_pair_kernel): frame t of the reference clip rides as frame A, frame t of
 // the estimate as frame B of ONE pair FFT; per-frame distance from the magnitudes side by side in P.
 void emul_lsd_frames(const EmulTables* e, const float* ref, const float* est, long long L, int hop, int pad_reflect,

@@ -203,6 +203,42 @@ def make_steps():
     print("steps.npz:", len(out), "arrays")
 
 
+def make_steps_clip():
+    """clip_sample=True (the constructor default, scheduling_dps.py:29): the reference differentiates through the base
+    step's `pred_original_sample.clamp(+-clip_sample_range)`, so autograd zeroes the guidance gradient wherever the
+    unclipped x0 lies outside the range (DPS / DSG / DiffMusic re-leaf `sample`; MPGD leafs the clipped x0).
+    Seeded latents give |x0| > 1 for almost every element at t = 999, about half at t = 501, a third at t = 1."""
+    out = {}
+    noiser = get_noiser("gaussian", 0.0)
+    vae, voc = stubs.StubVAE(), stubs.StubVocoder()
+    ref_wav = stubs.synth_clips(1, L1, first=50)
+    op = refop.MusicInpaintingOperator(audio_length_in_s=1, sample_rate=16000, mask_percentage=0.3, interval_s=1,
+                                       mask_duration_s=0.1, noiser=noiser, mask_type="box", start_inpainting_s=0.25,
+                                       end_inpainting_s=0.5)
+    cfg = dict(stubs.MUSICLDM_SCHED, clip_sample=True)
+    x, e = stubs.synth_latents(1, 25)
+    meas = op.forward(ref_wav)
+    for sched_name, eta, rate in (("dps", 0.0, 5e-4), ("mpgd", 0.0, 0.005), ("dsg", 1.0, 0.08),
+                                  ("diffmusic", 1.0, 0.08)):
+        sched = get_scheduler(sched_name)(operator=op, **cfg)
+        sched.set_timesteps(500)
+        for t in (999, 501, 1):
+            gen = torch.Generator().manual_seed(3000)
+            o = sched.step(e, t, x, eta=eta, generator=gen, measurement=meas, vae=vae, vocoder=voc,
+                           original_waveform_length=L1, supervised_space="mel_spectrogram", ip_guidance_rate=rate)
+            key = f"{sched_name}|inpainting|mel_spectrogram|eta{eta}|t{t}"
+            out[key + "|prev"] = npf(o.prev_sample)
+            out[key + "|x0"] = npf(o.pred_original_sample)
+            out[key + "|loss"] = npf(o.loss.float())
+            out[key + "|clipped_frac"] = np.float32((npf(o.pred_original_sample).__abs__() >= 1.0).mean())
+    np.savez_compressed(os.path.join(HERE, "steps_clip.npz"), **out)
+    print("steps_clip.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    if "--clip-only" in sys.argv:
+        make_steps_clip()
+        sys.exit(0)
     make_operators()
     make_steps()
+    make_steps_clip()

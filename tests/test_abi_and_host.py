@@ -129,6 +129,36 @@ def test_dropin_namespace_imports():
     assert out.strip().endswith("ok")
 
 
+def test_ditto_stays_importable_under_the_dropin(tmp_path):
+    """diffmusic/schedulers/__init__.py:19-20: get_scheduler("ditto") must keep returning the REFERENCE's class when the
+    drop-in shadows `diffmusic.schedulers` (DITTO is out of scope here).  A stand-in reference tree
+    (regular sub-package + scheduling_ditto.py) sits behind the drop-in on sys.path, as /root/reference would."""
+    import subprocess
+    ref = tmp_path / "ref" / "diffmusic" / "schedulers"
+    ref.mkdir(parents=True)
+    (ref / "__init__.py").write_text("raise RuntimeError('the reference package must stay shadowed')\n")
+    (ref / "scheduling_ditto.py").write_text(
+        "from diffmusic.schedulers.utils import InverseProblemSchedulerOutput\n"
+        "class DITTOScheduler:\n    origin = 'reference'\n    out = InverseProblemSchedulerOutput\n")
+    dropin = os.path.join(ROOT, "diffmusic_b200", "dropin")
+    code = ("import sys; sys.path[:0] = [%r, %r, %r];"
+            "from diffmusic.schedulers import get_scheduler; import diffmusic_b200;"
+            "c = get_scheduler('ditto'); assert c.origin == 'reference', c;"
+            "assert c.out is diffmusic_b200.InverseProblemSchedulerOutput;"
+            "assert c.__module__ == 'diffmusic.schedulers.scheduling_ditto';"
+            "assert get_scheduler('dps') is diffmusic_b200.DPSScheduler; print('ok')"
+            % (dropin, ROOT, str(tmp_path / "ref")))
+    out = subprocess.check_output([sys.executable, "-c", code], text=True)
+    assert out.strip().endswith("ok")
+    if os.path.isdir("/root/reference/diffmusic/schedulers"):  # build container: the real file, with the diffusers shim
+        code3 = ("import sys; sys.path[:0] = [%r, %r, %r, '/root/reference'];"
+                 "from diffmusic.schedulers import get_scheduler; c = get_scheduler('ditto');"
+                 "import inspect; assert inspect.getsourcefile(c).startswith('/root/reference'), c; print('ok')"
+                 % (dropin, ROOT, os.path.join(ROOT, "tests", "golden", "_shim")))
+        out = subprocess.check_output([sys.executable, "-c", code3], text=True)
+        assert out.strip().endswith("ok")
+
+
 def test_bench_hooks_the_entry_point_the_operators_call():
     """bench.py times the dominant kernel by wrapping _lib.call for the STFT guidance entry point: the name it matches
     must be the one diffmusic_b200/operators.py actually calls (a silent mismatch leaves roofline.achieved null)."""

@@ -94,7 +94,7 @@ def test_stockham_fft(emul, n, inverse):
     assert rel_l2(np.stack([got.real, got.imag]), np.stack([want.real, want.imag])) < 5e-7
 
 
-ENGINES = ["frame", "pair"]
+ENGINES = ["frame", "pair", "warp"]
 
 
 def _run(emul, mode, clamp, y, hop, window, ref=None, mask=None, grad=True, engine="frame"):
@@ -109,7 +109,8 @@ def _run(emul, mode, clamp, y, hop, window, ref=None, mask=None, grad=True, engi
     refp = _ptr(np.ascontiguousarray(ref, np.float32)) if ref is not None else None
     refk = np.ascontiguousarray(ref, np.float32) if ref is not None else None
     maskk = np.ascontiguousarray(mask, np.float32) if mask is not None else None
-    fn = emul.emul_stft_guidance if engine == "frame" else emul.emul_stft_guidance_pair
+    fn = {"frame": emul.emul_stft_guidance, "pair": emul.emul_stft_guidance_pair,
+          "warp": emul.emul_stft_guidance_warp}[engine]
     fn(C.byref(t), mode, clamp, _ptr(y), C.c_longlong(Ly), hop,
        _ptr(maskk) if maskk is not None else None, _ptr(refk) if refk is not None else None, _ptr(out),
        _ptr(ypbar) if grad else None, C.byref(ss))

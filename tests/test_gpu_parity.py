@@ -179,6 +179,43 @@ def test_steps_vs_reference_golden(golden_steps):
     print("worst rel-L2 over 33 reference step cases:", worst)
 
 
+def test_clip_sample_steps_vs_reference_golden(golden_steps_clip):
+    """clip_sample=True (constructor default): the guidance gradient is masked where the unclipped x0 leaves
+    +-clip_sample_range, as autograd does through the reference's clamp (scheduling_dps.py:165-175); 12 cases produced
+    by the reference's scheduler files, eager and CUDA-graph replay."""
+    from diffmusic_b200.graph import GraphedGuidedStep
+    vae, voc = stubs.StubVAE().to(DEV), stubs.StubVocoder().to(DEV)
+    ref_wav = stubs.synth_clips(1, L1, first=50).to(DEV)
+    x, e = stubs.synth_latents(1, 25)
+    x, e = x.to(DEV), e.to(DEV)
+    op = _inpaint()
+    meas = op.forward(ref_wav)
+    cases = [k[:-5] for k in golden_steps_clip.files if k.endswith("|prev")]
+    assert len(cases) == 12
+    for key in cases:
+        sched_name, _, space, eta, t = key.split("|")
+        eta, t = float(eta[3:]), int(t[1:])
+        sched = dm.get_scheduler(sched_name)(operator=op, **dict(stubs.MUSICLDM_SCHED, clip_sample=True))
+        sched.set_timesteps(500)
+        kwargs = dict(eta=eta, measurement=meas, vae=vae, vocoder=voc, original_waveform_length=L1,
+                      ip_guidance_rate=RATES[sched_name], supervised_space=space)
+        out = sched.step(e, t, x, generator=torch.Generator().manual_seed(3000), **kwargs)
+        ep = rel_l2(out.prev_sample, golden_steps_clip[key + "|prev"])
+        e0 = rel_l2(out.pred_original_sample, golden_steps_clip[key + "|x0"])
+        assert ep < TOL and e0 < TOL, (key, ep, e0)
+        gl = float(golden_steps_clip[key + "|loss"].ravel()[0])
+        assert abs(float(out.loss.float().ravel()[0]) - gl) <= TOL * max(1.0, abs(gl)), key
+    # graph replay keeps the mask per timestep (the scalars come from the device-side coefficient row)
+    sched = dm.DPSScheduler(operator=op, **dict(stubs.MUSICLDM_SCHED, clip_sample=True))
+    sched.set_timesteps(500)
+    graphed = GraphedGuidedStep(sched, x.shape, measurement=meas, vae=vae, vocoder=voc, original_waveform_length=L1,
+                                ip_guidance_rate=RATES["dps"], eta=0.0, supervised_space="mel_spectrogram")
+    for t in (999, 501, 1):
+        out = graphed(e, t, x)
+        key = f"dps|inpainting|mel_spectrogram|eta0.0|t{t}"
+        assert rel_l2(out.prev_sample, golden_steps_clip[key + "|prev"]) < TOL, key
+
+
 @pytest.mark.parametrize("sched_name,op_name,eta", [("dps", "super_resolution", 0.0), ("mpgd", "inpainting", 1.0),
                                                     ("dsg", "phase_retrieval", 1.0), ("diffmusic", "inpainting", 1.0),
                                                     ("diffmusic", "dereverberation", 1.0)])
@@ -653,31 +690,36 @@ def test_host_pipelined_steps_equal_direct_replays(two_graphs):
 @pytest.mark.parametrize("nf", [6, 7, 8, 13, 16, 22])
 @pytest.mark.parametrize("op_name", ["inpainting", "phase_retrieval"])
 def test_stft_kernels_agree_for_every_tile_size(op_name, nf, monkeypatch):
-    """frame-pair kernel (default) vs frame-at-a-time kernel, over tile sizes with full, partial and odd rounds:
-    loss and gradient agree to fp32 rounding, in both supervised spaces."""
+    """warp-per-frame-pair kernel (default for <= 16 frames per tile) vs 64-thread frame-pair kernel vs frame-at-a-time
+    kernel, over tile sizes with full, partial and odd frame counts: loss and gradient agree to fp32 rounding, in both
+    supervised spaces."""
     from diffmusic_b200 import _lib
     monkeypatch.setenv("DM_STFT_FRAMES_PER_TILE", str(nf))
     B, L = 3, L1  # T = 101 frames: every tile size leaves a partial last tile, some with an odd frame count
     wav = stubs.synth_clips(B, L).to(DEV)
     op = _inpaint() if op_name == "inpainting" else dm.PhaseRetrievalOperator(noiser=_noiser())
     meas = op.forward(stubs.synth_clips(1, L, first=50).to(DEV))
+    engines = (("auto", 0), ("pair", 2), ("frame", 1))
     for space in ("mel_spectrogram", "wav_form"):
         res = {}
-        for name, eng in (("pair", 0), ("frame", 1)):
+        for name, eng in engines:
             _lib.call("dm_stft_set_engine", eng)
             try:
                 res[name] = _loss_grad(op, wav, meas, space)
             finally:
                 _lib.call("dm_stft_set_engine", 0)
-        assert rel_l2(res["pair"][0], res["frame"][0]) < 1e-6, space
-        assert rel_l2(res["pair"][1], res["frame"][1]) < 2e-6, space
-    t_pair = op.transform(op.forward(wav))
-    _lib.call("dm_stft_set_engine", 1)
-    try:
-        t_frame = op.transform(op.forward(wav))
-    finally:
-        _lib.call("dm_stft_set_engine", 0)
-    assert rel_l2(t_pair, t_frame) < 1e-6
+        for name in ("auto", "pair"):
+            assert rel_l2(res[name][0], res["frame"][0]) < 1e-6, (space, name)
+            assert rel_l2(res[name][1], res["frame"][1]) < 2e-6, (space, name)
+    t = {}
+    for name, eng in engines:
+        _lib.call("dm_stft_set_engine", eng)
+        try:
+            t[name] = op.transform(op.forward(wav))
+        finally:
+            _lib.call("dm_stft_set_engine", 0)
+    assert rel_l2(t["auto"], t["frame"]) < 1e-6
+    assert rel_l2(t["pair"], t["frame"]) < 1e-6
 
 
 # ------------------------------------------------------------------------------------------------ update kernels, all paths

@@ -130,6 +130,31 @@ def test_steps_match_reference(golden_steps):
         assert abs(float(o.loss.float().ravel()[0]) - gl) <= 1e-5 * max(1.0, abs(gl)), key
 
 
+def test_clip_sample_steps_match_reference(golden_steps_clip):
+    """clip_sample=True: the oracle differentiates through the clamp of the base step like the reference
+    (scheduling_dps.py:165-175); 4 schedulers x t in {999, 501, 1}, 18-99 % of the latent clipped."""
+    vae, voc = stubs.StubVAE(), stubs.StubVocoder()
+    ref_wav = stubs.synth_clips(1, L1, first=50)
+    x, e = stubs.synth_latents(1, 25)
+    op = oo.OracleOperator("inpainting", mask=oo.inpaint_mask(1, 16000, "box", 0.25, 0.5))
+    base = osteps.make_base(**dict(stubs.MUSICLDM_SCHED, clip_sample=True))
+    base.set_timesteps(500)
+    cases = _step_cases(golden_steps_clip)
+    assert len(cases) == 12
+    meas = op.forward(ref_wav)
+    for key in cases:
+        sched, _, space, eta, t = key.split("|")
+        eta, t = float(eta[3:]), int(t[1:])
+        rate = {"dps": 5e-4, "mpgd": 0.005, "dsg": 0.08, "diffmusic": 0.08}[sched]
+        o = osteps.reference_step(sched, base, op, e, t, x, eta=eta, ip_guidance_rate=rate,
+                                  generator=torch.Generator().manual_seed(3000), measurement=meas, vae=vae, vocoder=voc,
+                                  original_waveform_length=L1, supervised_space=space)
+        assert rel_l2(o.prev_sample, golden_steps_clip[key + "|prev"]) < 5e-6, key
+        assert rel_l2(o.pred_original_sample, golden_steps_clip[key + "|x0"]) < 5e-6, key
+        gl = float(golden_steps_clip[key + "|loss"].ravel()[0])
+        assert abs(float(o.loss.float().ravel()[0]) - gl) <= 1e-5 * max(1.0, abs(gl)), key
+
+
 # ------------------------------------------------------------------------------------------------ section 8(f) oracles
 def test_frechet_oracle_closed_forms():
     """oracle.fad.calc_frechet_distance (restated fadtk/fad.py:50-119) against closed forms: identical Gaussians -> 0;
