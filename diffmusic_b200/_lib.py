@@ -18,7 +18,8 @@ c_f, c_i, c_ll, c_p = C.c_float, C.c_int, C.c_longlong, C.c_void_p
 class StftTables(C.Structure):
     """struct dm_stft_tables (include/dm_abi.h)."""
     _fields_ = [("window", c_p), ("tw512", c_p), ("w1024", c_p), ("mel_kstart", c_p), ("mel_klen", c_p),
-                ("mel_w", c_p), ("mel_wstride", c_i), ("bin_m0", c_p), ("bin_w0", c_p), ("bin_w1", c_p)]
+                ("mel_w", c_p), ("mel_wstride", c_i), ("bin_m0", c_p), ("bin_w0", c_p), ("bin_w1", c_p),
+                ("warp_image", c_p), ("warp_image_floats", c_i), ("warp_na", c_i), ("warp_nb", c_i)]
 
 
 _SIGNATURES = {

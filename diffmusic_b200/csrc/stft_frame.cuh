@@ -39,6 +39,10 @@ struct StftTables {
     const int* bin_m0;       // [513]  first mel band touching bin k
     const float* bin_w0;     // [513]  fb[k, m0]
     const float* bin_w1;     // [513]  fb[k, m0+1] (0 if none)
+    // optional (warp-per-frame-pair kernel): host-built shared-memory image of its tables, diffmusic_b200/tables.py
+    // warp_image(); na / nb = bin-pair rows of the two mel bands a lane sums
+    const float* warp_image = nullptr;
+    int warp_image_floats = 0, warp_na = 0, warp_nb = 0;
 };
 
 // Shared-memory working set of one frame group (all float): two swizzled complex buffers and the mel cotangent.

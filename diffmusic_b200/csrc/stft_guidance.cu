@@ -505,7 +505,7 @@ extern "C" int dm_stft_guidance_io(const dm_stft_tables* tab, int mode, int clam
     StftParams p;
     p.tab = StftTables{tab->window, reinterpret_cast<const cf*>(tab->tw512), reinterpret_cast<const cf*>(tab->w1024),
                        tab->mel_kstart, tab->mel_klen, tab->mel_w, tab->mel_wstride, tab->bin_m0, tab->bin_w0,
-                       tab->bin_w1};
+                       tab->bin_w1, tab->warp_image, tab->warp_image_floats, tab->warp_na, tab->warp_nb};
     p.clamp = clamp;
     p.hop = hop;
     p.B = B;
@@ -528,7 +528,8 @@ extern "C" int dm_stft_guidance_io(const dm_stft_tables* tab, int mode, int clam
     dim3 grid(p.ntiles, B), block(kCtaThreads);
     cudaStream_t st = as_stream(stream);
     // warp-per-frame-pair engine (stft_warp.cu): hops that keep the gathered overlap-add 16-byte aligned, one round per tile
-    if ((hop & 3) == 0 && p.nf <= 16 && g_stft_engine == DM_STFT_ENGINE_AUTO) return launch_stft_warp(p, mode, st);
+    if ((hop & 3) == 0 && p.nf <= 16 && g_stft_engine == DM_STFT_ENGINE_AUTO && tab->warp_image != nullptr)
+        return launch_stft_warp(p, mode, st);
     if ((hop & 1) == 0 && (g_stft_engine != DM_STFT_ENGINE_FRAME || y_dtype != DM_IO_F32)) {  // frame-pair kernel
         size_t smem2 = stft_pair_smem_bytes(p.nf, hop, tab->mel_wstride);
         if (smem2 > 227 * 1024)

@@ -48,6 +48,6 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity)
 
 // defined in stft_warp.cu: the warp-per-frame-pair kernel (even hops, <= 16 frames per tile)
 int launch_stft_warp(const StftParams& p, int mode, cudaStream_t st);
-size_t stft_warp_smem_bytes(int nf, int hop, int mel_wstride);
+size_t stft_warp_smem_bytes(int nf, int hop, int image_floats);
 
 }  // namespace dm

@@ -1,12 +1,14 @@
 // Fused STFT / mel guidance kernel for sm_100a, warp-per-frame-pair engine (stft_warp.cuh).
 //
-// A CTA of 8 warps walks over tiles of <= 16 consecutive frames of one clip (persistent: grid = 2 CTAs per SM, tile
-// list strided over the grid; the tables are staged once per CTA).  Per tile:
-//   * the tile's signal span is staged in shared memory (one cp.async.bulk for interior fp32 tiles; reflect padding,
-//     16-bit waveforms and the inpainting mask sample by sample);
+// A CTA of 8 warps walks over tiles of <= 16 consecutive frames of one clip (persistent: grid = 2 CTAs per SM, the tile
+// list strided over the grid).  Its constant tables arrive as ONE cp.async.bulk of a host-built shared-memory image
+// (tables.py warp_image), overlapped with the first tile's signal.  Per tile:
+//   * the tile's signal span is staged in shared memory by one cp.async.bulk (interior fp32 tiles; edge tiles, 16-bit
+//     waveforms and the inpainting mask go sample by sample).  The span is dead as soon as every warp has loaded its two
+//     frames into registers, so the NEXT tile's span is fetched behind the current tile's transforms;
 //   * warp w owns frames 2w, 2w+1 and runs the whole chain window -> FFT -> energies -> sparse mel -> dB / clamp ->
-//     residual -> VJP -> inverse FFT out of registers and its private 8.5 KB buffer; warps only meet at the CTA
-//     barrier that ends the tile's transform phase (no named-barrier ring, no ordered chain);
+//     residual -> VJP -> inverse FFT out of registers and its private 8.5 KB buffer; warps only meet at CTA barriers
+//     around the gather (no named-barrier ring, no ordered chain);
 //   * gathered overlap-add: every warp leaves its two windowed frame gradients in its buffer, then all 256 threads sum,
 //     per 4 output samples, the <= 7 frames that cover them in ascending frame order (bit-reproducible) and add the
 //     result to the padded cotangent in HBM (tiles overlap by < 1 frame -> <= 2 commutative adds per address).
@@ -17,190 +19,221 @@
 
 namespace dm {
 
-constexpr int kWarpCtaThreads = 256;
-constexpr int kWarpsPerCta = kWarpCtaThreads / 32;
-constexpr int kWarpMaxFrames = 2 * kWarpsPerCta;
+constexpr int kWarpsPerCta = 8;  // warps (= frame pairs) per CTA.  (7 warps with 144 registers for 14-frame tiles was
+                                 // measured: registers are allocated per four warps, so only ONE such CTA fits an SM: 44 vs 37 us)
 
 struct WarpSmemLayout {
-    int sig, win2, tw4, melw, binw, binm, red, wbuf, total;  // float offsets
+    int sig, img, red, wbuf, total;  // float offsets
 };
-__host__ __device__ inline WarpSmemLayout warp_smem_layout(int nf, int hop, int mel_wstride) {
+__host__ __device__ inline WarpSmemLayout warp_smem_layout(int nf, int hop, int img_floats, int warps) {
     WarpSmemLayout l;
     const int span = ((nf - 1) * hop + kNfft + 3) & ~3;
     l.sig = 0;
-    l.win2 = l.sig + span;
-    l.tw4 = l.win2 + kNfft;
-    l.melw = l.tw4 + 16 * 32 * 4;
-    l.binw = l.melw + mel_wstride * kMels;
-    l.binm = l.binw + 2 * 514;
-    l.red = l.binm + 132;
+    l.img = l.sig + span;
+    l.red = l.img + img_floats;
     l.wbuf = l.red + 8;
-    l.total = l.wbuf + kWarpsPerCta * kWarpBufFloats;
+    l.total = l.wbuf + warps * kWarpBufFloats;
     return l;
 }
-size_t stft_warp_smem_bytes(int nf, int hop, int mel_wstride) {
-    return (size_t)warp_smem_layout(nf, hop, mel_wstride).total * sizeof(float);
+size_t stft_warp_smem_bytes(int nf, int hop, int img_floats) {
+    return (size_t)warp_smem_layout(nf, hop, img_floats, kWarpsPerCta).total * sizeof(float);
 }
 
 __device__ __forceinline__ cf shfl_cf(cf v, int src) {
     return cf{__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)};
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kWarpCtaThreads, 2) stft_warp_kernel(const StftParams p, int total_tiles) {
+struct TileGeom {
+    int b, tile, nfr, span;
+    long long f0, base;
+    const void* yb;
+    const float* span_src;
+    bool interior;
+};
+__device__ __forceinline__ TileGeom tile_geom(const StftParams& p, int item, int hop) {
+    TileGeom g;
+    g.b = item / p.ntiles;
+    g.tile = item - g.b * p.ntiles;
+    g.f0 = (long long)g.tile * p.nf;
+    g.nfr = (int)min((long long)p.nf, p.T - g.f0);
+    g.span = (g.nfr - 1) * hop + kNfft;
+    g.base = g.f0 * hop;  // first padded-signal index of the tile
+    g.yb = wave_row(p.y, p.y_io, (long long)g.b * p.y_bstride);
+    g.span_src = static_cast<const float*>(g.yb) + (g.base - kNfft / 2);
+    // fp32 interior tiles without a mask: one TMA bulk copy; everything else is converted / mirrored / masked per sample
+    g.interior = p.y_io == DM_IO_F32 && p.mask == nullptr && g.base >= kNfft / 2 &&
+                 g.base - kNfft / 2 + g.span <= p.Ly && (reinterpret_cast<uintptr_t>(g.span_src) & 15) == 0;
+    return g;
+}
+// stage the tile's signal span: asynchronously (thread 0 issues the bulk copy) or by all threads
+__device__ __forceinline__ void stage_async(const TileGeom& g, float* sig, uint64_t* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    bulk_load_span(sig, g.span_src, (uint32_t)g.span * 4u, bar);
+}
+template <int THREADS>
+__device__ __forceinline__ void stage_generic(const StftParams& p, const TileGeom& g, float* sig, int tid) {
+    // four samples per thread and round, all loads issued before the first store (edge tiles are few, but a CTA that
+    // walks through them sample by sample becomes the straggler of the grid)
+    for (int i0 = tid; i0 < g.span; i0 += 4 * THREADS) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * THREADS;
+            v[u] = 0.f;
+            if (i < g.span) {
+                const long long j = reflect_src(g.base + i, p.Ly);
+                v[u] = ld_wave(g.yb, p.y_io, j);
+                if (p.mask) v[u] *= __ldg(p.mask + j);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * THREADS;
+            if (i < g.span) sig[i] = v[u];
+        }
+    }
+}
+
+// HOP: compile-time hop (160 in every shipped configuration) or 0 = read it from the parameters
+// WARPS: warps per CTA (every warp owns one frame pair of the tile, so tiles hold <= 2 * WARPS frames)
+template <int MODE, int HOP, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 2) stft_warp_kernel(const StftParams p, int total_tiles) {
+    constexpr int kWarpCtaThreads = 32 * WARPS;
     extern __shared__ __align__(16) float smem[];
-    __shared__ __align__(8) uint64_t stage_bar;
+    __shared__ __align__(8) uint64_t bar_sig, bar_img;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int hop = HOP ? HOP : p.hop;
     const bool has_ref = p.ref != nullptr, want_grad = p.ypbar != nullptr;
-    const WarpSmemLayout lay = warp_smem_layout(p.nf, p.hop, p.tab.mel_wstride);
+    const int na = p.tab.warp_na, nb = p.tab.warp_nb;
+    const WarpSmemLayout lay = warp_smem_layout(p.nf, hop, p.tab.warp_image_floats, WARPS);
+    const WarpImage il = warp_image_layout(na, nb);
     float* sig = smem + lay.sig;
-    f2* win2 = reinterpret_cast<f2*>(smem + lay.win2);
-    f4* tw4 = reinterpret_cast<f4*>(smem + lay.tw4);
-    float* melw_t = smem + lay.melw;
-    f2* binw = reinterpret_cast<f2*>(smem + lay.binw);
-    unsigned char* binm = reinterpret_cast<unsigned char*>(smem + lay.binm);
+    float* img = smem + lay.img;
+    const f2* win2 = reinterpret_cast<const f2*>(img + il.win2);
+    const f4* tw4 = reinterpret_cast<const f4*>(img + il.tw4);
+    const f2* melp = reinterpret_cast<const f2*>(img + il.melp);
+    const int* lanek = reinterpret_cast<const int*>(img + il.lanek);
+    const PairBinTab bins{reinterpret_cast<const f2*>(img + il.binw),
+                          reinterpret_cast<const unsigned char*>(img + il.binm)};
     float* red = smem + lay.red;
     float* wbuf_all = smem + lay.wbuf;
     float* wbuf = wbuf_all + w * kWarpBufFloats;
     cf* xbuf = reinterpret_cast<cf*>(wbuf);
     f2* P = reinterpret_cast<f2*>(wbuf + kWarpPOff);
     f2* melbar = reinterpret_cast<f2*>(wbuf + kWarpMelbarOff);
-    const PairBinTab bins{binw, binm};
 
-    // ---- once per CTA: window (halved, paired), exchange twiddles, filterbank by band and by bin ----
+    // ---- prologue: the table image and the first tile's signal are fetched concurrently ----
+    TileGeom g = tile_geom(p, blockIdx.x, hop);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&stage_bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&bar_sig)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&bar_img)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bulk_load_span(img, p.tab.warp_image, (uint32_t)p.tab.warp_image_floats * 4u, &bar_img);
+        if (g.interior) stage_async(g, sig, &bar_sig);
     }
-    for (int i = tid; i < kH; i += kWarpCtaThreads)
-        win2[i] = f2{0.5f * __ldg(p.tab.window + i), 0.5f * __ldg(p.tab.window + i + kH)};
-    for (int i = tid; i < 16 * 32; i += kWarpCtaThreads) {
-        const int m = i >> 5, l = i & 31;
-        const cf a = w1024_any(p.tab.w1024, l * (2 * m)), b = w1024_any(p.tab.w1024, l * (2 * m + 1));
-        tw4[i] = f4{a.x, a.y, b.x, b.y};
-    }
-    {
-        const float4* src = reinterpret_cast<const float4*>(p.tab.mel_w);
-        float4* dst = reinterpret_cast<float4*>(melw_t);
-        for (int i = tid; i < p.tab.mel_wstride * kMels / 4; i += kWarpCtaThreads) dst[i] = __ldg(src + i);
-    }
-    for (int k = tid; k < kBins; k += kWarpCtaThreads) {
-        binw[k] = f2{__ldg(p.tab.bin_w0 + k), __ldg(p.tab.bin_w1 + k)};
-        binm[k] = (unsigned char)__ldg(p.tab.bin_m0 + k);
-    }
-    WarpMelConsts mc;
-    load_warp_mel_consts(lane, p.tab, mc);
-    __syncthreads();
+    if (!g.interior) stage_generic<kWarpCtaThreads>(p, g, sig, tid);
+    __syncthreads();  // barrier initialisation and a generically staged span are visible
+    mbar_wait_parity(&bar_img, 0);
+    const int pa0 = lanek[lane], pb0 = lanek[32 + lane], ma = lanek[64 + lane], mb = lanek[96 + lane];
 
-    uint32_t bar_parity = 0;
+    uint32_t sig_parity = 0;
     for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
-        const int b = item / p.ntiles, tile = item - b * p.ntiles;
-        const long long f0 = (long long)tile * p.nf;
-        const int nfr = (int)min((long long)p.nf, p.T - f0);
-        const int span = (nfr - 1) * p.hop + kNfft;
-        const long long base = f0 * p.hop;  // first padded-signal index of the tile
-
-        // ---- stage the signal span ----
-        const void* yb = wave_row(p.y, p.y_io, (long long)b * p.y_bstride);
-        const float* span_src = static_cast<const float*>(yb) + (base - kNfft / 2);
-        const bool interior = p.y_io == DM_IO_F32 && base >= kNfft / 2 && base - kNfft / 2 + span <= p.Ly &&
-                              (reinterpret_cast<uintptr_t>(span_src) & 15) == 0;
-        if (interior) {
-            if (tid == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                bulk_load_span(sig, span_src, (uint32_t)span * 4u, &stage_bar);
-            }
-        } else {
-            for (int i = tid; i < span; i += kWarpCtaThreads) {
-                const long long j = reflect_src(base + i, p.Ly);
-                float v = ld_wave(yb, p.y_io, j);
-                if (p.mask) v *= __ldg(p.mask + j);
-                sig[i] = v;
-            }
+        if (g.interior) {
+            mbar_wait_parity(&bar_sig, sig_parity);
+            sig_parity ^= 1u;
         }
-        __syncthreads();
-        if (interior) {
-            mbar_wait_parity(&stage_bar, bar_parity);
-            bar_parity ^= 1u;
-            if (p.mask) {
-                const float* mk = p.mask + (base - kNfft / 2);
-                for (int i = tid; i < span; i += kWarpCtaThreads) sig[i] *= __ldg(mk + i);
-                __syncthreads();
-            }
-        }
+        const int b = g.b, nfr = g.nfr, f0 = (int)g.f0;
 
         // ---- transform phase: warp w owns frames 2w, 2w + 1 of the tile ----
         float lsum = 0.f;
         const int fa = 2 * w;
-        if (fa < nfr) {
-            const bool active_b = fa + 1 < nfr;  // otherwise frame B recomputes frame A and its results are dropped
-            const int fb = active_b ? fa + 1 : fa;
-            const long long ta = f0 + fa, tb = f0 + fb;
-            cf v[32];
-            WarpX x;
-            f2 g[17];
-            // forward: pass 1 -> exchange -> pass 2 -> split
-            warp_load_frames(lane, sig + fa * p.hop, sig + fb * p.hop, win2, v);
+        const bool active = fa < nfr;
+        const bool active_b = fa + 1 < nfr;  // otherwise frame B recomputes frame A and its results are dropped
+        const int fb = active_b ? fa + 1 : fa;
+        const int ta = f0 + fa, tb = f0 + fb;
+        cf v[32];
+        float ssa = 0.f, ssb = 0.f;
+        if (active) warp_load_frames(lane, sig + fa * hop, sig + fb * hop, win2, v, ssa, ssb);
+        __syncthreads();  // every warp holds its frames in registers: the span is dead
+        const int next = item + gridDim.x;
+        if (next < total_tiles && tid == 0) {
+            const TileGeom gn = tile_geom(p, next, hop);
+            if (gn.interior) stage_async(gn, sig, &bar_sig);  // lands behind this tile's transforms
+        }
+        if (active) {
+            WarpX x;  // forward spectrum of the owned bins; in PhaseWav mode overwritten by its cotangent right away
+            const int partner = (32 - lane) & 31;
+            // balance the two frames' magnitudes for the joint transform (warp_balance)
+            float bal_s, bal_inv;
+            bool zero_a, zero_b;
+            warp_balance(warp_sum(ssa), warp_sum(ssb), bal_s, bal_inv, zero_a, zero_b);
+            warp_scale_b(v, bal_s);
+            // forward: pass 1 -> exchange -> pass 2
             dft32<-1>(v);
             warp_twiddle_store<-1>(lane, v, tw4, xbuf);
             __syncwarp();
             warp_xchg_load(lane, xbuf, v);
             dft32<-1>(v);
-            {
-                cf snd[16], rcv[16];
-                warp_split_send(lane, v, snd);
-                const int partner = (32 - lane) & 31;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) rcv[i] = shfl_cf(snd[i], partner);
-                warp_split_recv(lane, v, rcv, x);
+            if (MODE != kModePhaseWav) {
+                __syncwarp();  // every lane has read its exchange row before P overwrites the buffer
+                if (lane < 8) melbar[64 + lane] = f2{0.f, 0.f};
+                if (lane == 1) P[kH + 1] = f2{0.f, 0.f};  // touched by the bin-pair loads with a zero weight
             }
-            f2 e[17];
-            warp_energies<MODE>(x, e);
-            if (MODE != kModeMelDb && p.noise != nullptr) {  // GaussianNoise on the magnitude (operator.py:171)
+            // split into the two frames' spectra, one owned bin per step; energies leave for P (mel modes) or meet the
+            // reference magnitude right here (PhaseWav)
 #pragma unroll
-                for (int i = 0; i < 17; ++i) {
-                    const int k = (i < 16) ? lane + 32 * i : kH;
-                    if (i < 16 || lane == 0) {
-                        const float* nz = p.noise + ((long long)b * kBins + k) * p.T;
-                        e[i].x += p.sigma * __ldg(nz + ta);
-                        e[i].y += p.sigma * __ldg(nz + tb);
-                    }
+            for (int i = 0; i < 17; ++i) {
+                if (i < 16) {
+                    const cf rcv = shfl_cf(warp_split_send_i(lane, v, i), partner);
+                    warp_split_recv_i(v, i, rcv, x.a[i], x.b[i]);
+                } else {
+                    warp_split_nyquist(v, x.a[16], x.b[16]);
                 }
-            }
-            if (MODE == kModePhaseWav) {
-#pragma unroll
-                for (int i = 0; i < 17; ++i) {
-                    const int k = (i < 16) ? lane + 32 * i : kH;
-                    g[i] = f2{0.f, 0.f};
-                    if (i < 16 || lane == 0) {
+                x.b[i] = cf{x.b[i].x * bal_inv, x.b[i].y * bal_inv};
+                if (zero_a) x.a[i] = cf{0.f, 0.f};
+                if (zero_b) x.b[i] = cf{0.f, 0.f};
+                const bool mine = i < 16 || lane == 0;
+                const int k = warp_bin_of(lane, i);
+                f2 e = warp_bin_energies<MODE>(x.a[i], x.b[i]);
+                if (MODE != kModeMelDb && p.noise != nullptr && mine) {  // GaussianNoise on |STFT| (operator.py:171)
+                    const float* nz = p.noise + ((long long)b * kBins + k) * p.T;
+                    e.x += p.sigma * __ldg(nz + ta);
+                    e.y += p.sigma * __ldg(nz + tb);
+                }
+                if (MODE == kModePhaseWav) {
+                    f2 gk = f2{0.f, 0.f};
+                    if (mine) {
                         const long long row = ((long long)b * kBins + k) * p.T;
                         if (p.out) {
-                            p.out[row + ta] = e[i].x;
-                            if (active_b) p.out[row + tb] = e[i].y;
+                            p.out[row + ta] = e.x;
+                            if (active_b) p.out[row + tb] = e.y;
                         }
                         if (has_ref) {
                             const float* rr = p.ref + (long long)b * p.ref_bstride + (long long)k * p.T;
-                            const float da = __ldg(rr + ta) - e[i].x, db = __ldg(rr + tb) - e[i].y;
+                            const float da = __ldg(rr + ta) - e.x, db = __ldg(rr + tb) - e.y;
                             lsum = fmaf(da, da, lsum);
                             if (active_b) lsum = fmaf(db, db, lsum);
-                            g[i] = f2{-da, -db};
+                            gk = f2{-da, -db};
                         }
                     }
+                    x.a[i] = warp_xbar<MODE>(x.a[i], gk.x);
+                    x.b[i] = warp_xbar<MODE>(x.b[i], gk.y);
+                } else if (mine) {
+                    P[k] = e;
                 }
-            } else {
-                __syncwarp();  // every lane has read its exchange row before P overwrites the buffer
-                warp_store_energies(lane, e, P);
-                if (lane < 8) melbar[64 + lane] = f2{0.f, 0.f};
+            }
+            if (MODE != kModePhaseWav) {
                 float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
                 if (has_ref) {  // issued before the mel loop, consumed after it
                     const float* rb = p.ref + (long long)b * p.ref_bstride;
-                    const float* rlo = rb + (long long)lane * p.T;
-                    const float* rhi = rb + (long long)(63 - lane) * p.T;
+                    const float* rlo = rb + (long long)ma * p.T;
+                    const float* rhi = rb + (long long)mb * p.T;
                     r0 = __ldg(rlo + ta), r1 = __ldg(rlo + tb), r2 = __ldg(rhi + ta), r3 = __ldg(rhi + tb);
                 }
                 __syncwarp();
                 f2 lo, hi;
-                warp_mel_project(lane, mc, melw_t, P, lo, hi);
+                warp_mel_project(lane, na, nb, pa0, pb0, melp, P, lo, hi);
                 float v0, d0, v1, d1, v2, d2, v3, d3;
                 mel_value<MODE>(lo.x, p.clamp != 0, v0, d0);
                 mel_value<MODE>(lo.y, p.clamp != 0, v1, d1);
@@ -208,8 +241,8 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 2) stft_warp_kernel(const Stf
                 mel_value<MODE>(hi.y, p.clamp != 0, v3, d3);
                 if (has_ref) {
                     r0 -= v0, r1 -= v1, r2 -= v2, r3 -= v3;
-                    melbar[lane] = f2{-r0 * d0, -r1 * d1};
-                    melbar[63 - lane] = f2{-r2 * d2, -r3 * d3};
+                    melbar[ma] = f2{-r0 * d0, -r1 * d1};
+                    melbar[mb] = f2{-r2 * d2, -r3 * d3};
                     lsum = fmaf(r0, r0, lsum);
                     lsum = fmaf(r2, r2, lsum);
                     if (active_b) {
@@ -219,27 +252,43 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 2) stft_warp_kernel(const Stf
                 }
                 if (p.out) {
                     float* ob = p.out + (long long)b * kMels * p.T;
-                    ob[(long long)lane * p.T + ta] = v0;
-                    ob[(long long)(63 - lane) * p.T + ta] = v2;
+                    ob[(long long)ma * p.T + ta] = v0;
+                    ob[(long long)mb * p.T + ta] = v2;
                     if (active_b) {
-                        ob[(long long)lane * p.T + tb] = v1;
-                        ob[(long long)(63 - lane) * p.T + tb] = v3;
+                        ob[(long long)ma * p.T + tb] = v1;
+                        ob[(long long)mb * p.T + tb] = v3;
                     }
                 }
-                if (want_grad) {
-                    __syncwarp();
-                    warp_bin_cotangents(lane, bins, melbar, g);
-                }
+                if (want_grad) __syncwarp();  // melbar complete
             }
             if (want_grad) {
-                // backward: Q -> pass 1 -> exchange -> pass 2 -> windowed frame gradients in the warp buffer
-                {
-                    cf snd[16], rcv[16];
-                    warp_pack_send<MODE>(lane, x, g, v, snd);
-                    const int partner = (32 - lane) & 31;
+                // backward, one owned bin per step: Xbar -> Q[k] (register i) and Q[1024 - k] (partner's register 31 - i;
+                // lane 0, its own partner, needs it in register 32 - i: one step later)
+                cf prev = cf{0.f, 0.f};
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) rcv[i] = shfl_cf(snd[i], partner);
-                    warp_pack_recv<MODE>(lane, x, g, rcv, v);
+                for (int i = 0; i < 16; ++i) {
+                    cf ya = x.a[i], yb = x.b[i];
+                    if (MODE != kModePhaseWav) {
+                        const f2 gk = warp_bin_cotangent(lane + 32 * i, bins, melbar);
+                        ya = warp_xbar<MODE>(ya, gk.x);
+                        yb = warp_xbar<MODE>(yb, gk.y);
+                    }
+                    cf q, qm;
+                    warp_q_pair(ya, yb, q, qm);
+                    if (i == 0 && lane == 0) q = warp_q_real(ya, yb);
+                    v[i] = q;
+                    const cf rcv = shfl_cf(qm, partner);
+                    if (i > 0) v[32 - i] = lane == 0 ? rcv : prev;
+                    prev = rcv;
+                }
+                {
+                    cf ya = x.a[16], yb = x.b[16];
+                    if (MODE != kModePhaseWav) {
+                        const f2 gk = warp_bin_cotangent(kH, bins, melbar);
+                        ya = warp_xbar<MODE>(ya, gk.x);
+                        yb = warp_xbar<MODE>(yb, gk.y);
+                    }
+                    v[16] = lane == 0 ? warp_q_real(ya, yb) : prev;
                 }
                 dft32<+1>(v);
                 __syncwarp();  // P / melbar are dead in every lane
@@ -248,7 +297,7 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 2) stft_warp_kernel(const Stf
                 warp_xchg_load(lane, xbuf, v);
                 dft32<+1>(v);
                 __syncwarp();  // exchange rows consumed before G overwrites them
-                warp_store_gradients(lane, v, win2, wbuf + kWarpGOff);
+                warp_store_gradients(lane, v, win2, wbuf);
             }
         }
         if (p.partial) {
@@ -259,54 +308,81 @@ __global__ void __launch_bounds__(kWarpCtaThreads, 2) stft_warp_kernel(const Stf
 
         // ---- gathered overlap-add of the tile's frame gradients, straight to HBM ----
         if (want_grad) {
-            float* gb = p.ypbar + (long long)b * (p.Ly + kNfft) + base;
-            const bool vec = (reinterpret_cast<uintptr_t>(gb) & 15) == 0;
-            for (int q = tid; q < span / 4; q += kWarpCtaThreads) {
+            float* gout = p.ypbar + (long long)b * (p.Ly + kNfft) + g.base;
+            const bool vec = (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
+            // frame f of the tile sits at wbuf_all + f * kWarpGStride; sample x of the span is its sample x - f * hop
+            const int fstep = kWarpGStride - hop;
+            for (int q = tid; q < g.span / 4; q += kWarpCtaThreads) {
                 const int xq = 4 * q;
-                const int f_hi = min(nfr - 1, xq / p.hop);
-                const int f_lo = xq > kNfft - 4 ? (xq - (kNfft - 4) + p.hop - 1) / p.hop : 0;
+                const int f_hi = min(nfr - 1, xq / hop);
+                const int f_lo = xq > kNfft - 4 ? (xq - (kNfft - 4) + hop - 1) / hop : 0;
+                const float* src = wbuf_all + xq + f_lo * fstep;
                 float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int f = f_lo; f <= f_hi; ++f) {
-                    const float4 t = *reinterpret_cast<const float4*>(wbuf_all + (f >> 1) * kWarpBufFloats + kWarpGOff +
-                                                                      (f & 1) * kNfft + (xq - f * p.hop));
-                    s.x += t.x, s.y += t.y, s.z += t.z, s.w += t.w;
+                const int n = f_hi - f_lo;
+                if (HOP >= 160) {  // at most 7 frames cover a sample: predicated, fully unrolled
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) {
+                        if (j <= n) {
+                            const float4 t = *reinterpret_cast<const float4*>(src + j * fstep);
+                            s.x += t.x, s.y += t.y, s.z += t.z, s.w += t.w;
+                        }
+                    }
+                } else {
+                    for (int j = 0; j <= n; ++j) {
+                        const float4 t = *reinterpret_cast<const float4*>(src + j * fstep);
+                        s.x += t.x, s.y += t.y, s.z += t.z, s.w += t.w;
+                    }
                 }
                 if (vec) {
-                    atomicAdd(reinterpret_cast<float4*>(gb + xq), s);
+                    atomicAdd(reinterpret_cast<float4*>(gout + xq), s);
                 } else {
-                    atomicAdd(gb + xq, s.x);
-                    atomicAdd(gb + xq + 1, s.y);
-                    atomicAdd(gb + xq + 2, s.z);
-                    atomicAdd(gb + xq + 3, s.w);
+                    atomicAdd(gout + xq, s.x);
+                    atomicAdd(gout + xq + 1, s.y);
+                    atomicAdd(gout + xq + 2, s.z);
+                    atomicAdd(gout + xq + 3, s.w);
                 }
             }
         }
         if (p.partial && tid == 0) {
             float t = 0.f;
-            for (int i = 0; i < kWarpsPerCta; ++i) t += red[i];  // idle warps left 0
-            p.partial[(long long)b * p.ntiles + tile] = t;
+            for (int i = 0; i < WARPS; ++i) t += red[i];  // idle warps left 0
+            p.partial[(long long)b * p.ntiles + g.tile] = t;
         }
-        __syncthreads();  // warp buffers, the signal span and `red` are free for the next tile
+        if (next < total_tiles) {
+            g = tile_geom(p, next, hop);
+            if (!g.interior) stage_generic<kWarpCtaThreads>(p, g, sig, tid);  // the span has been dead since the barrier above
+        }
+        __syncthreads();  // warp buffers and `red` are free, a generically staged span is visible
     }
 }
 
 int launch_stft_warp(const StftParams& p, int mode, cudaStream_t st) {
-    const size_t smem = stft_warp_smem_bytes(p.nf, p.hop, p.tab.mel_wstride);
+    if (p.tab.warp_image == nullptr || p.tab.warp_image_floats <= 0 || (p.tab.warp_image_floats & 3) != 0 ||
+        (reinterpret_cast<uintptr_t>(p.tab.warp_image) & 15) != 0 || p.tab.warp_na < 1 || p.tab.warp_nb < 1 ||
+        warp_image_layout(p.tab.warp_na, p.tab.warp_nb).total != p.tab.warp_image_floats)
+        return fail(DM_ERR_INVALID, "%s: dm_stft_tables.warp_image is missing or malformed", __func__);
+    const size_t smem = stft_warp_smem_bytes(p.nf, p.hop, p.tab.warp_image_floats);
     if (smem > 113 * 1024)
         return fail(DM_ERR_UNSUPPORTED, "%s: tile needs %zu B of shared memory (2 CTAs per SM need <= 113 KB)", __func__,
                     smem);
     const long long total = (long long)p.B * p.ntiles;
     if (total > 0x7fffffffLL) return fail(DM_ERR_INVALID, "%s: too many tiles", __func__);
     const int grid = (int)min(total, (long long)2 * num_sms());
-#define DM_LAUNCH_WARP(M)                                                                         \
+#define DM_LAUNCH_WARP(M, H, W)                                                                   \
     do {                                                                                          \
-        DM_SMEM_ONCE(stft_warp_kernel<M>, smem);                                                  \
-        DM_CARVEOUT_ONCE(stft_warp_kernel<M>);                                                    \
-        stft_warp_kernel<M><<<grid, kWarpCtaThreads, smem, st>>>(p, (int)total);                  \
+        DM_SMEM_ONCE((stft_warp_kernel<M, H, W>), smem);                                          \
+        DM_CARVEOUT_ONCE((stft_warp_kernel<M, H, W>));                                            \
+        stft_warp_kernel<M, H, W><<<grid, 32 * W, smem, st>>>(p, (int)total);                     \
     } while (0)
-    if (mode == DM_STFT_MEL_DB) DM_LAUNCH_WARP(kModeMelDb);
-    else if (mode == DM_STFT_PHASE_MEL) DM_LAUNCH_WARP(kModePhaseMel);
-    else DM_LAUNCH_WARP(kModePhaseWav);
+#define DM_LAUNCH_WARP_HOP(M)                                        \
+    do {                                                             \
+        if (p.hop == 160) DM_LAUNCH_WARP(M, 160, kWarpsPerCta);      \
+        else DM_LAUNCH_WARP(M, 0, kWarpsPerCta);                     \
+    } while (0)
+    if (mode == DM_STFT_MEL_DB) DM_LAUNCH_WARP_HOP(kModeMelDb);
+    else if (mode == DM_STFT_PHASE_MEL) DM_LAUNCH_WARP_HOP(kModePhaseMel);
+    else DM_LAUNCH_WARP_HOP(kModePhaseWav);
+#undef DM_LAUNCH_WARP_HOP
 #undef DM_LAUNCH_WARP
     DM_LAUNCHED();
     return DM_OK;

@@ -31,9 +31,26 @@ struct alignas(16) f4 {
 constexpr int kWarpRow = 34;                        // cf per exchange row: 32 + 2 pad -> 272 B, LDS.128 conflict-free
 constexpr int kWarpBufFloats = 32 * kWarpRow * 2;   // 2176 floats = 8704 B per warp
 // While it is not an exchange buffer the warp buffer holds (float offsets):
-constexpr int kWarpPOff = 0;        // f2 P[513]       per-bin energies (frame A, frame B)
+constexpr int kWarpPOff = 0;          // f2 P[514]       per-bin energies (frame A, frame B); P[513] = 0 (pair padding)
 constexpr int kWarpMelbarOff = 1040;  // f2 melbar[72]   mel cotangent (entries 64.. stay zero)
-constexpr int kWarpGOff = 0;        // float G[2][1024] windowed frame gradients of frame A / B
+constexpr int kWarpGStride = kWarpBufFloats / 2;  // float G[2][1088]: windowed frame gradients, frame f of the TILE at
+                                                  // wbuf_all + f * kWarpGStride (uniform stride across warps)
+
+// Host-built table image (diffmusic_b200/tables.py warp_image): float offsets of its sections
+struct WarpImage {
+    int win2, tw4, melp, lanek, binw, binm, total;
+};
+DM_HD WarpImage warp_image_layout(int na, int nb) {
+    WarpImage l;
+    l.win2 = 0;
+    l.tw4 = l.win2 + kNfft;
+    l.melp = l.tw4 + 16 * 32 * 4;
+    l.lanek = l.melp + (na + nb) * 64;
+    l.binw = l.lanek + 128;  // int32 [4][32]: pa0, pb0, ma, mb
+    l.binm = l.binw + 2 * 514;
+    l.total = l.binm + 132;
+    return l;
+}
 
 // register position of output k of dft32 and its inverse map
 DM_HDC int perm32(int p) { return (p >> 3) + 4 * (p & 7); }
@@ -123,8 +140,9 @@ DM_HD void warp_twiddle_store(int lane, cf (&v)[32], const f4* __restrict__ tw4,
         if (m > 0) v[p0] = cmul(v[p0], w0);
         v[p1] = cmul(v[p1], w1);
     }
+    f2* x2 = reinterpret_cast<f2*>(xbuf);  // 64-bit stores (cf itself is only 4-byte aligned)
 #pragma unroll
-    for (int p = 0; p < 32; ++p) xbuf[perm32(p) * kWarpRow + lane] = v[p];
+    for (int p = 0; p < 32; ++p) x2[perm32(p) * kWarpRow + lane] = f2{v[p].x, v[p].y};
 }
 DM_HD void warp_xchg_load(int lane, const cf* __restrict__ xbuf, cf (&v)[32]) {
     const f4* row = reinterpret_cast<const f4*>(xbuf + lane * kWarpRow);
@@ -137,15 +155,56 @@ DM_HD void warp_xchg_load(int lane, const cf* __restrict__ xbuf, cf (&v)[32]) {
 }
 
 // ---- forward pass 1: z[n] = win[n]/2 * (a[n] + i b[n]), n = lane + 32 r.  win2[n] = (win[n], win[n + 512]) / 2.
+// ssa / ssb: this lane's share of the two frames' windowed energies (see warp_balance)
 DM_HD void warp_load_frames(int lane, const float* __restrict__ fa, const float* __restrict__ fb,
-                            const f2* __restrict__ win2, cf (&v)[32]) {
+                            const f2* __restrict__ win2, cf (&v)[32], float& ssa, float& ssb) {
+    ssa = ssb = 0.f;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         const int n = lane + 32 * r;
         const f2 w = win2[n];
         v[r] = cf{fa[n] * w.x, fb[n] * w.x};
         v[r + 16] = cf{fa[n + 512] * w.y, fb[n + 512] * w.y};
+        ssa = fmaf(v[r].x, v[r].x, fmaf(v[r + 16].x, v[r + 16].x, ssa));
+        ssb = fmaf(v[r].y, v[r].y, fmaf(v[r + 16].y, v[r + 16].y, ssb));
     }
+}
+// The joint transform of z = a + i b carries rounding noise of ~1e-7 max(|A|, |B|) into BOTH spectra, so a quiet frame
+// next to a loud one (an inpainting mask edge, an onset) would come out far less accurate than from a transform of its
+// own -- and the dB floor's 1 / mel derivative amplifies exactly those frames.  Frame B is therefore scaled by the power
+// of two s that brings its energy next to frame A's (exact), and its spectrum is scaled back by 1 / s after the split;
+// an all-zero frame (masked stretch, digital silence) gets an exactly zero spectrum, as torch.stft returns.
+// ssa / ssb: the frames' windowed energies summed over the warp.
+DM_HD int f32_exponent(float x) {
+#if defined(__CUDA_ARCH__)
+    return (__float_as_int(x) >> 23) & 0xff;
+#else
+    union { float f; int i; } u;
+    u.f = x;
+    return (u.i >> 23) & 0xff;
+#endif
+}
+DM_HD float f32_pow2(int k) {  // 2^k, -126 <= k <= 127
+#if defined(__CUDA_ARCH__)
+    return __int_as_float((127 + k) << 23);
+#else
+    union { float f; int i; } u;
+    u.i = (127 + k) << 23;
+    return u.f;
+#endif
+}
+DM_HD void warp_balance(float ssa, float ssb, float& s, float& inv_s, bool& zero_a, bool& zero_b) {
+    zero_a = ssa == 0.f;
+    zero_b = ssb == 0.f;
+    int k = 0;
+    if (!zero_a && !zero_b) k = (f32_exponent(ssa) - f32_exponent(ssb)) >> 1;  // ~ log2 sqrt(ssa / ssb)
+    k = k < -40 ? -40 : (k > 40 ? 40 : k);
+    s = f32_pow2(k);
+    inv_s = f32_pow2(-k);
+}
+DM_HD void warp_scale_b(cf (&v)[32], float s) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) v[r].y *= s;
 }
 
 // Spectrum of the owned bins: slot i = bin lane + 32 i (i < 16); slot 16 = bin 512 (lane 0 only).
@@ -153,101 +212,97 @@ struct WarpX {
     cf a[17], b[17];
 };
 
-// ---- split, part 1: what this lane hands to its partner lane (32 - lane) & 31 at step i: Z[lane + 32 (31 - i)];
-// lane 0 is its own partner and needs Z[32 ((32 - i) & 31)] back instead.
-DM_HD void warp_split_send(int lane, const cf (&v)[32], cf (&snd)[16]) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const cf g = v[pinv32(31 - i)], z = v[pinv32((32 - i) & 31)];
-        snd[i] = lane == 0 ? z : g;
-    }
+// ---- split, one owned bin at a time (keeps the register footprint at the 64 values of the transform): at step i this
+// lane hands Z[lane + 32 (31 - i)] to its partner lane (32 - lane) & 31 -- lane 0 is its own partner and needs
+// Z[32 ((32 - i) & 31)] back instead -- and receives p = Z[1024 - k] for its bin k = lane + 32 i:
+//   A[k] = Z[k] + conj p,  B[k] = -i (Z[k] - conj p)        (already halved through the window)
+DM_HD cf warp_split_send_i(int lane, const cf (&v)[32], int i) {
+    const cf g = v[pinv32(31 - i)], z = v[pinv32((32 - i) & 31)];
+    return lane == 0 ? z : g;
 }
-// part 2: rcv[i] = Z[1024 - k], k = lane + 32 i  ->  A[k], B[k]  (already halved through the window)
-DM_HD void warp_split_recv(int lane, const cf (&v)[32], const cf (&rcv)[16], WarpX& x) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const cf z = v[pinv32(i)], p = rcv[i];
-        x.a[i] = cf{z.x + p.x, z.y - p.y};
-        x.b[i] = cf{z.y + p.y, p.x - z.x};
-    }
-    const cf z = v[pinv32(16)];  // bin 512 is its own mirror (lane 0)
-    x.a[16] = cf{z.x + z.x, 0.f};
-    x.b[16] = cf{z.y + z.y, 0.f};
+DM_HD void warp_split_recv_i(const cf (&v)[32], int i, cf p, cf& a, cf& b) {
+    const cf z = v[pinv32(i)];
+    a = cf{z.x + p.x, z.y - p.y};
+    b = cf{z.y + p.y, p.x - z.x};
+}
+// bin 512 is its own mirror (lane 0)
+DM_HD void warp_split_nyquist(const cf (&v)[32], cf& a, cf& b) {
+    const cf z = v[pinv32(16)];
+    a = cf{z.x + z.x, 0.f};
+    b = cf{z.y + z.y, 0.f};
 }
 
-// ---- per-bin energies -> P (shared); optional Gaussian noise on the magnitude is added by the caller in between
+// ---- per-bin energies (-> P in shared memory, natural bin order, (frame A, frame B) per entry)
 template <int MODE>
-DM_HD void warp_energies(const WarpX& x, f2 (&e)[17]) {
-#pragma unroll
-    for (int i = 0; i < 17; ++i) e[i] = f2{pair_bin_energy<MODE>(x.a[i]), pair_bin_energy<MODE>(x.b[i])};
+DM_HD f2 warp_bin_energies(cf a, cf b) {
+    return f2{pair_bin_energy<MODE>(a), pair_bin_energy<MODE>(b)};
 }
-DM_HD void warp_store_energies(int lane, const f2 (&e)[17], f2* __restrict__ P) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) P[lane + 32 * i] = e[i];
-    if (lane == 0) P[kH] = e[16];
-}
+DM_HD int warp_bin_of(int lane, int i) { return i < 16 ? lane + 32 * i : kH; }
 
-// ---- mel projection: lane j sums band j, then band 63 - j (3 + 41 ... 12 + 12 bins: <= 44 per lane)
-struct WarpMelConsts {
-    int k0a, na, k0b, nb;
-};
-DM_HD void load_warp_mel_consts(int lane, const StftTables& t, WarpMelConsts& c) {
-    c.k0a = t.mel_kstart[lane];
-    c.na = t.mel_klen[lane];
-    c.k0b = t.mel_kstart[63 - lane];
-    c.nb = t.mel_klen[63 - lane];
-}
-DM_HD void warp_mel_project(int lane, const WarpMelConsts& c, const float* __restrict__ melw_t,
+// ---- mel projection: lane l sums its short band ma[l] (na bin-pair rows from pair pa0[l]), then its long band mb[l]
+// (nb rows from pb0[l]); every lane runs the same na + nb iterations (weights are zero outside the band) with one 128-bit
+// load of (P_A, P_B) of two bins and one 64-bit load of the two weights per iteration.  The host picks the band -> lane
+// assignment and the window starts so that the 128-bit loads are bank-conflict free (tables.py warp_image).
+// melp[row * 32 + lane] = weights of bins 2 (p0 + i), 2 (p0 + i) + 1.
+DM_HD void warp_mel_project(int lane, int na, int nb, int pa0, int pb0, const f2* __restrict__ melp,
                             const f2* __restrict__ P, f2& lo, f2& hi) {
-    lo = pair_mel_segment(melw_t, P, lane, c.k0a, 0, c.na);
-    hi = pair_mel_segment(melw_t, P, 63 - lane, c.k0b, 0, c.nb);
+    const f4* Pa = reinterpret_cast<const f4*>(P) + pa0;
+    const f4* Pb = reinterpret_cast<const f4*>(P) + pb0;
+    const f2* wa = melp + lane;
+    const f2* wb = melp + na * 32 + lane;
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < na; ++i) {
+        const f2 w = wa[i * 32];
+        const f4 v = Pa[i];
+        a0 = fmaf(w.x, v.x, a0);
+        a1 = fmaf(w.x, v.y, a1);
+        a0 = fmaf(w.y, v.z, a0);
+        a1 = fmaf(w.y, v.w, a1);
+    }
+#pragma unroll 4
+    for (int i = 0; i < nb; ++i) {
+        const f2 w = wb[i * 32];
+        const f4 v = Pb[i];
+        b0 = fmaf(w.x, v.x, b0);
+        b1 = fmaf(w.x, v.y, b1);
+        b0 = fmaf(w.y, v.z, b0);
+        b1 = fmaf(w.y, v.w, b1);
+    }
+    lo = f2{a0, a1};
+    hi = f2{b0, b1};
 }
 
-// ---- backward: cotangent of the owned bins -> Q (natural order in v) and what the partner lane needs
-// g[i] = d loss / d energy (or magnitude) of bin lane + 32 i for (frame A, frame B)
+// ---- backward, one owned bin at a time: spectrum cotangent Xbar = scale * X of both frames ->
+//   Q[k]        = Xbar_A[k] + i Xbar_B[k]              (stays in this lane, register k2 = i of the inverse pass 1)
+//   Q[1024 - k] = conj Xbar_A[k] + i conj Xbar_B[k]    (for the partner lane's register k2 = 31 - i)
+// (the 1/2 of Re(.) = (. + conj .)/2 rides on the halved synthesis window)
 template <int MODE>
 DM_HD float warp_bin_scale(cf x, float g) {
     if (MODE == kModeMelDb) return 2.f * g;  // d|X|^2 = 2 X
     const float e = x.x * x.x + x.y * x.y;
     return e > 0.f ? g * fast_rsqrt(e) : 0.f;  // d|X| = X / |X|, 0 at X = 0
 }
-DM_HD void warp_bin_cotangents(int lane, const PairBinTab& t, const f2* __restrict__ melbar, f2 (&g)[17]) {
-#pragma unroll
-    for (int i = 0; i < 17; ++i) {
-        const int k = (i < 16) ? lane + 32 * i : kH;
-        const int m0 = t.binm[k];
-        const f2 w = t.binw[k];
-        const f2 g0 = melbar[m0], g1 = melbar[m0 + 1];
-        g[i] = f2{w.x * g0.x + w.y * g1.x, w.x * g0.y + w.y * g1.y};
-    }
-}
-// Q[k] = Xbar_A[k] + i Xbar_B[k] -> v[i];  Q[1024 - k] = conj Xbar_A[k] + i conj Xbar_B[k] -> snd[i] (for the partner).
-// (The 1/2 of Re(.) = (. + conj .)/2 rides on the halved synthesis window.)
 template <int MODE>
-DM_HD void warp_pack_send(int lane, const WarpX& x, const f2 (&g)[17], cf (&v)[32], cf (&snd)[16]) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float sa = warp_bin_scale<MODE>(x.a[i], g[i].x), sb = warp_bin_scale<MODE>(x.b[i], g[i].y);
-        const float ar = sa * x.a[i].x, ai = sa * x.a[i].y, br = sb * x.b[i].x, bi = sb * x.b[i].y;
-        v[i] = cf{ar - bi, ai + br};
-        snd[i] = cf{ar + bi, br - ai};
-    }
-    if (lane == 0) {  // DC: both halves land on Q[0]; only the real parts of the cotangent act
-        const float sa = warp_bin_scale<MODE>(x.a[0], g[0].x), sb = warp_bin_scale<MODE>(x.b[0], g[0].y);
-        v[0] = cf{2.f * sa * x.a[0].x, 2.f * sb * x.b[0].x};
-    }
+DM_HD cf warp_xbar(cf x, float g) {
+    const float s = warp_bin_scale<MODE>(x, g);
+    return cf{s * x.x, s * x.y};
 }
-// rcv[i] = partner's snd[i] = Q[lane + 32 (31 - i)]; lane 0 received its own: Q[32 (32 - i)], and owns Q[512]
-template <int MODE>
-DM_HD void warp_pack_recv(int lane, const WarpX& x, const f2 (&g)[17], const cf (&rcv)[16], cf (&v)[32]) {
-    const float sa = warp_bin_scale<MODE>(x.a[16], g[16].x), sb = warp_bin_scale<MODE>(x.b[16], g[16].y);
-    const cf q512 = cf{2.f * sa * x.a[16].x, 2.f * sb * x.b[16].x};
-    v[16] = lane == 0 ? q512 : rcv[15];
-#pragma unroll
-    for (int k2 = 17; k2 < 32; ++k2) v[k2] = lane == 0 ? rcv[32 - k2] : rcv[31 - k2];
+// energy cotangent of bin k for (frame A, frame B) from the mel cotangent (<= 2 bands touch a bin)
+DM_HD f2 warp_bin_cotangent(int k, const PairBinTab& t, const f2* __restrict__ melbar) {
+    const int m0 = t.binm[k];
+    const f2 w = t.binw[k];
+    const f2 g0 = melbar[m0], g1 = melbar[m0 + 1];
+    return f2{w.x * g0.x + w.y * g1.x, w.x * g0.y + w.y * g1.y};
 }
+DM_HD void warp_q_pair(cf ya, cf yb, cf& q, cf& qm) {
+    q = cf{ya.x - yb.y, ya.y + yb.x};
+    qm = cf{ya.x + yb.y, yb.x - ya.y};
+}
+// DC and Nyquist: both halves land on the same Q entry and only the real parts of the cotangent act
+DM_HD cf warp_q_real(cf ya, cf yb) { return cf{2.f * ya.x, 2.f * yb.x}; }
 
-// ---- last inverse pass output -> windowed frame gradients in the warp buffer: G[0][n] (frame A), G[1][n] (frame B)
+// ---- last inverse pass output -> windowed frame gradients in the warp buffer: G[n] (frame A), G[kWarpGStride + n] (B)
 DM_HD void warp_store_gradients(int lane, const cf (&v)[32], const f2* __restrict__ win2, float* __restrict__ G) {
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
@@ -255,9 +310,9 @@ DM_HD void warp_store_gradients(int lane, const cf (&v)[32], const f2* __restric
         const f2 w = win2[n];
         const cf lo = v[pinv32(r)], hi = v[pinv32(r + 16)];
         G[n] = lo.x * w.x;
-        G[kNfft + n] = lo.y * w.x;
+        G[kWarpGStride + n] = lo.y * w.x;
         G[n + 512] = hi.x * w.y;
-        G[kNfft + n + 512] = hi.y * w.y;
+        G[kWarpGStride + n + 512] = hi.y * w.y;
     }
 }
 

@@ -69,9 +69,12 @@ class _DeviceTables:
                   "w1024": tables.half_twiddles(1024).to(device)}
         for k, v in mt.items():
             self.t[k] = v.to(device).contiguous()
+        img, na, nb = tables.warp_image(window, fb)
+        self.t["warp_image"] = img.to(device).contiguous()
         p = {k: v.data_ptr() for k, v in self.t.items()}
         self.struct = _lib.StftTables(p["window"], p["tw512"], p["w1024"], p["mel_kstart"], p["mel_klen"], p["mel_w"],
-                                      tables.MEL_WSTRIDE, p["bin_m0"], p["bin_w0"], p["bin_w1"])
+                                      tables.MEL_WSTRIDE, p["bin_m0"], p["bin_w0"], p["bin_w1"], p["warp_image"],
+                                      img.numel(), na, nb)
         self.ref = C.byref(self.struct)
 
 

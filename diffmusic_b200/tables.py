@@ -104,6 +104,110 @@ def mel_tables(fb: torch.Tensor):
                 bin_m0=torch.from_numpy(m0), bin_w0=torch.from_numpy(w0), bin_w1=torch.from_numpy(w1))
 
 
+def warp_image(window: torch.Tensor, fb: torch.Tensor):
+    """Shared-memory image of the constant tables of the warp-per-frame-pair STFT kernel (csrc/stft_warp.cu), built once
+    on the host so that a CTA fetches it with ONE bulk copy instead of recomputing it.  Returns (image fp32 (n,), na, nb).
+
+    Sections (float offsets, each a multiple of 4 floats; the kernel derives them from na / nb):
+      win2  [512][2]        (window[n], window[n + 512]) / 2   -- the 1/2 of the two-real-frames split rides on the window
+      tw4   [16][32][4]     (w^(2m), w^(2m+1)) for w = exp(-2 pi i lane / 1024): the twiddles between the two DFT-32 passes
+      melp  [na + nb][32][2] filterbank weights of lane l for bin PAIRS: rows < na belong to its short band ma[l] (pairs
+                            pa0[l] + i), rows >= na to its long band mb[l] (pairs pb0[l] + i - na); zero outside the band,
+                            so every lane runs the same na + nb iterations with 128-bit loads of (P_A, P_B) of two bins
+      lanek [4][32] int32   pa0, pb0 (first bin pair of lane l's two row blocks), ma, mb (its two mel bands)
+      binw  [514][2]        (fb[k, m0], fb[k, m0 + 1]) per bin;   binm [528] uint8  m0 per bin
+    """
+    mt = mel_tables(fb)
+    fbn = fb.detach().cpu().to(torch.float32).numpy()
+    k0, kl = mt["mel_kstart"].numpy(), mt["mel_klen"].numpy()
+    win = window.detach().cpu().to(torch.float32).numpy()
+    win2 = np.stack([0.5 * win[:512], 0.5 * win[512:]], axis=1).astype(np.float32)
+    lane = np.arange(32, dtype=np.float64)
+    tw4 = np.zeros((16, 32, 4), np.float32)
+    for m in range(16):
+        for j, e in enumerate((2 * m, 2 * m + 1)):
+            ang = -2.0 * math.pi * lane * e / 1024.0
+            tw4[m, :, 2 * j] = np.cos(ang)
+            tw4[m, :, 2 * j + 1] = np.sin(ang)
+
+    def pairs(m):
+        a, b = int(k0[m]), int(k0[m] + kl[m] - 1)
+        return a >> 1, (b >> 1) - (a >> 1) + 1
+
+    # Band -> lane assignment.  Lane l sums one SHORT band (0..31) in `na` rows and one LONG band (32..63) in `nb` rows;
+    # every lane runs all rows (zero weights outside its band), so which bands a lane takes is free.  The 128-bit loads
+    # of row i hit bin pair p0[l] + i: a quarter-warp (8 consecutive lanes) is conflict-free iff its eight p0 are
+    # distinct mod 8.  A band shorter than the row count may start its window up to (rows - count) pairs early, which
+    # gives every band a set of reachable residues; bands are matched to residues (capacity 4 = one per quarter-warp)
+    # by augmenting paths, and the band with residue r of quarter-warp o sits in lane 8 o + r.
+    def assign(bands, rows):
+        reach = {}
+        for m in bands:
+            p0, cnt = pairs(m)
+            lo = max(0, p0 - (rows - cnt))
+            hi = min(p0, 257 - rows)
+            assert lo <= hi, (m, p0, cnt, rows)
+            reach[m] = {}
+            for start in range(hi, lo - 1, -1):      # prefer the latest start (fewest padded rows in front)
+                reach[m].setdefault(start % 8, start)
+        owner = {r: [] for r in range(8)}
+
+        def place(m, seen):
+            for r in reach[m]:
+                if r in seen:
+                    continue
+                seen.add(r)
+                if len(owner[r]) < 4:
+                    owner[r].append(m)
+                    return True
+                for j, other in enumerate(owner[r]):
+                    if place(other, seen):
+                        owner[r][j] = m
+                        return True
+            return False
+
+        for m in sorted(bands, key=lambda m: len(reach[m])):
+            if not place(m, set()):
+                return None
+        lanes = [None] * 32
+        for r in range(8):
+            for o, m in enumerate(owner[r]):
+                lanes[8 * o + r] = (m, reach[m][r])
+        return lanes
+
+    na = max(pairs(m)[1] for m in range(32))
+    nb = max(pairs(m)[1] for m in range(32, 64))
+    la, lb = assign(range(32), na), assign(range(32, 64), nb)
+    if la is None or lb is None:  # no conflict-free assignment (other filterbanks): natural order, still correct
+        la = [(l, min(pairs(l)[0], 257 - na)) for l in range(32)]
+        lb = [(63 - l, min(pairs(63 - l)[0], 257 - nb)) for l in range(32)]
+    melp = np.zeros((na + nb, 32, 2), np.float32)
+    chk = np.zeros_like(fbn)
+    for l in range(32):
+        for (m, p0), base, n in ((la[l], 0, na), (lb[l], na, nb)):
+            assert 0 <= p0 and 2 * (p0 + n - 1) + 1 <= 513, (l, m, p0, n)  # padded reads stay inside P[0 .. 513]
+            for i in range(n):
+                for h in range(2):
+                    k = 2 * (p0 + i) + h
+                    if k < N_BINS:
+                        melp[base + i, l, h] = fbn[k, m]
+                        chk[k, m] = fbn[k, m]
+            assert int(k0[m]) >= 2 * p0 and int(k0[m] + kl[m] - 1) <= 2 * (p0 + n - 1) + 1, (l, m)
+    assert np.array_equal(chk, fbn)  # the pair tables reproduce the filterbank exactly
+    assert sorted(m for m, _ in la) == list(range(32)) and sorted(m for m, _ in lb) == list(range(32, 64))
+    lanek = np.array([[p for _, p in la], [p for _, p in lb], [m for m, _ in la], [m for m, _ in lb]], np.int32)
+    binw = np.zeros((514, 2), np.float32)
+    binw[:N_BINS, 0] = mt["bin_w0"].numpy()
+    binw[:N_BINS, 1] = mt["bin_w1"].numpy()
+    binm = np.zeros(528, np.uint8)
+    binm[:N_BINS] = mt["bin_m0"].numpy().astype(np.uint8)
+    parts = [win2.ravel(), tw4.ravel(), melp.ravel(), lanek.ravel().view(np.float32), binw.ravel(),
+             binm.view(np.float32)]
+    for q in parts:
+        assert q.size % 4 == 0
+    return torch.from_numpy(np.concatenate(parts).copy()), int(na), int(nb)
+
+
 def sinc_resample_kernel(orig_freq, new_freq):
     """(kernel (new, taps) fp32, width, orig, new) exactly as torchaudio.transforms.Resample builds them."""
     rs = torchaudio.transforms.Resample(orig_freq=orig_freq, new_freq=new_freq)

@@ -128,6 +128,12 @@ typedef struct dm_stft_tables {
     const int* bin_m0;     /* [513] */
     const float* bin_w0;   /* [513] */
     const float* bin_w1;   /* [513] */
+    /* optional: shared-memory image of the warp-per-frame-pair kernel's tables (halved paired window, exchange
+     * twiddles, per-lane bin-pair filterbank rows, per-bin filterbank), built on the host by
+     * diffmusic_b200/tables.py warp_image() from the tables above; NULL selects the 64-thread frame-pair kernel. */
+    const float* warp_image;
+    int warp_image_floats; /* multiple of 4 */
+    int warp_na, warp_nb;  /* bin-pair rows per lane for band l and band 63 - l */
 } dm_stft_tables;
 
 #define DM_STFT_MEL_DB 0    /* |X|^2 -> mel -> 10 log10(max(.,1e-10)) [-> clamp +-80]   (n_fft = win = 1024) */

@@ -213,9 +213,8 @@ void emul_stft_guidance_pair(const EmulTables* e, int mode, int clamp, const flo
 
 template <int MODE>
 static void run_warp(const EmulTables& e, int clamp, const float* y, long long Ly, int hop, const float* mask,
-                     const float* ref, float* out, float* ypbar, double* sumsq) {
-    StftTables t{e.window, reinterpret_cast<const cf*>(e.tw512), reinterpret_cast<const cf*>(e.w1024),
-                 e.mel_kstart, e.mel_klen, e.mel_w, e.mel_wstride, e.bin_m0, e.bin_w0, e.bin_w1};
+                     const float* ref, float* out, float* ypbar, double* sumsq, const float* image, int na, int nb,
+                     int pair_shift) {
     const long long T = 1 + Ly / hop;
     std::vector<float> raw(kWarpBufFloats + 8, 0.f), fa(kNfft), fb(kNfft);
     float* wbuf = raw.data();
@@ -223,75 +222,92 @@ static void run_warp(const EmulTables& e, int clamp, const float* y, long long L
     cf* xbuf = reinterpret_cast<cf*>(wbuf);
     f2* P = reinterpret_cast<f2*>(wbuf + kWarpPOff);
     f2* melbar = reinterpret_cast<f2*>(wbuf + kWarpMelbarOff);
-    std::vector<f2> win2(kH);
-    for (int i = 0; i < kH; ++i) win2[i] = f2{0.5f * t.window[i], 0.5f * t.window[i + kH]};
-    std::vector<f4> tw4raw(16 * 32 + 1);
-    f4* tw4 = tw4raw.data();
-    while (reinterpret_cast<uintptr_t>(tw4) & 15) tw4 = reinterpret_cast<f4*>(reinterpret_cast<char*>(tw4) + 4);
-    std::vector<f4> tw4v(16 * 32);
-    for (int i = 0; i < 16 * 32; ++i) {
-        const int m = i >> 5, l = i & 31;
-        const cf a = w1024_any(t.w1024, l * (2 * m)), b = w1024_any(t.w1024, l * (2 * m + 1));
-        tw4v[i] = f4{a.x, a.y, b.x, b.y};
-    }
-    std::vector<f2> binw(kBins);
-    std::vector<unsigned char> binm(kBins);
-    for (int k = 0; k < kBins; ++k) { binw[k] = f2{e.bin_w0[k], e.bin_w1[k]}; binm[k] = (unsigned char)e.bin_m0[k]; }
-    const PairBinTab bins{binw.data(), binm.data()};
-    std::vector<WarpMelConsts> mc(32);
-    for (int l = 0; l < 32; ++l) load_warp_mel_consts(l, t, mc[l]);
-    struct Lane { cf v[32]; WarpX x; f2 g[17]; f2 en[17]; cf snd[16]; cf rcv[16]; };
+    // the host-built table image (diffmusic_b200/tables.py warp_image), 16-byte aligned like its shared-memory copy
+    const WarpImage il = warp_image_layout(na, nb);
+    std::vector<float> imgraw(il.total + 8);
+    float* img = imgraw.data();
+    while (reinterpret_cast<uintptr_t>(img) & 15) ++img;
+    std::memcpy(img, image, sizeof(float) * il.total);
+    const f2* win2 = reinterpret_cast<const f2*>(img + il.win2);
+    const f4* tw4 = reinterpret_cast<const f4*>(img + il.tw4);
+    const f2* melp = reinterpret_cast<const f2*>(img + il.melp);
+    const int* lanek = reinterpret_cast<const int*>(img + il.lanek);
+    const PairBinTab bins{reinterpret_cast<const f2*>(img + il.binw), reinterpret_cast<const unsigned char*>(img + il.binm)};
+    struct Lane { cf v[32]; WarpX x; cf snd, rcv, prev; };
     std::vector<Lane> L(32);
     if (ypbar) std::memset(ypbar, 0, sizeof(float) * (Ly + 1024));
     double acc = 0.0;
-    for (long long f = 0; f < T; f += 2) {
-        const bool has_b = f + 1 < T;
+    // pair_shift = 1: frame 0 rides alone (as the last frame of an odd tile does), the pairs are (1, 2), (3, 4), ...
+    for (long long f = 0; f < T; f += (pair_shift && f == 0) ? 1 : 2) {
+        const bool has_b = f + 1 < T && !(pair_shift && f == 0);
         const long long f2i = has_b ? f + 1 : f;
         for (int n = 0; n < kNfft; ++n) {
             long long ja = reflect_src(f * hop + n, Ly), jb = reflect_src(f2i * hop + n, Ly);
             fa[n] = y[ja] * (mask ? mask[ja] : 1.f);
             fb[n] = y[jb] * (mask ? mask[jb] : 1.f);
         }
+        float ssa = 0.f, ssb = 0.f;
         for (int l = 0; l < 32; ++l) {
-            warp_load_frames(l, fa.data(), fb.data(), win2.data(), L[l].v);
+            float sa, sb;
+            warp_load_frames(l, fa.data(), fb.data(), win2, L[l].v, sa, sb);
+            ssa += sa;
+            ssb += sb;
+        }
+        float bal_s, bal_inv;
+        bool zero_a, zero_b;
+        warp_balance(ssa, ssb, bal_s, bal_inv, zero_a, zero_b);
+        for (int l = 0; l < 32; ++l) {
+            warp_scale_b(L[l].v, bal_s);
             dft32<-1>(L[l].v);
-            warp_twiddle_store<-1>(l, L[l].v, tw4v.data(), xbuf);
+            warp_twiddle_store<-1>(l, L[l].v, tw4, xbuf);
         }
         for (int l = 0; l < 32; ++l) {
             warp_xchg_load(l, xbuf, L[l].v);
             dft32<-1>(L[l].v);
-            warp_split_send(l, L[l].v, L[l].snd);
         }
-        for (int l = 0; l < 32; ++l)
-            for (int i = 0; i < 16; ++i) L[l].rcv[i] = L[(32 - l) & 31].snd[i];
-        for (int l = 0; l < 32; ++l) {
-            warp_split_recv(l, L[l].v, L[l].rcv, L[l].x);
-            warp_energies<MODE>(L[l].x, L[l].en);
+        if (MODE != kModePhaseWav) {
+            for (int l = 0; l < 8; ++l) melbar[64 + l] = f2{0.f, 0.f};
+            P[kH + 1] = f2{0.f, 0.f};
         }
-        if (MODE == kModePhaseWav) {
-            for (int l = 0; l < 32; ++l)
-                for (int i = 0; i < 17; ++i) {
-                    const int k = (i < 16) ? l + 32 * i : kH;
-                    L[l].g[i] = f2{0.f, 0.f};
-                    if (!(i < 16 || l == 0)) continue;
-                    const f2 mag = L[l].en[i];
-                    if (out) { out[k * T + f] = mag.x; if (has_b) out[k * T + f2i] = mag.y; }
-                    if (ref) {
-                        float da = ref[k * T + f] - mag.x, db = ref[k * T + f2i] - mag.y;
-                        acc += (double)da * da;
-                        if (has_b) acc += (double)db * db;
-                        L[l].g[i] = f2{-da, -db};
-                    }
-                }
-        } else {
-            for (int l = 0; l < 32; ++l) {
-                warp_store_energies(l, L[l].en, P);
-                if (l < 8) melbar[64 + l] = f2{0.f, 0.f};
+        // split, one owned bin per step (a shuffle = all lanes publish, then all lanes read)
+        for (int i = 0; i < 17; ++i) {
+            if (i < 16) {
+                for (int l = 0; l < 32; ++l) L[l].snd = warp_split_send_i(l, L[l].v, i);
+                for (int l = 0; l < 32; ++l) L[l].rcv = L[(32 - l) & 31].snd;
             }
-            std::vector<f2> lo(32), hi(32);
-            for (int l = 0; l < 32; ++l) warp_mel_project(l, mc[l], e.mel_w, P, lo[l], hi[l]);
             for (int l = 0; l < 32; ++l) {
-                const int ms[2] = {l, 63 - l};
+                WarpX& x = L[l].x;
+                if (i < 16) warp_split_recv_i(L[l].v, i, L[l].rcv, x.a[i], x.b[i]);
+                else warp_split_nyquist(L[l].v, x.a[16], x.b[16]);
+                x.b[i] = cf{x.b[i].x * bal_inv, x.b[i].y * bal_inv};
+                if (zero_a) x.a[i] = cf{0.f, 0.f};
+                if (zero_b) x.b[i] = cf{0.f, 0.f};
+                const bool mine = i < 16 || l == 0;
+                const int k = warp_bin_of(l, i);
+                const f2 en = warp_bin_energies<MODE>(x.a[i], x.b[i]);
+                if (MODE == kModePhaseWav) {
+                    f2 gk = f2{0.f, 0.f};
+                    if (mine) {
+                        if (out) { out[k * T + f] = en.x; if (has_b) out[k * T + f2i] = en.y; }
+                        if (ref) {
+                            float da = ref[k * T + f] - en.x, db = ref[k * T + f2i] - en.y;
+                            acc += (double)da * da;
+                            if (has_b) acc += (double)db * db;
+                            gk = f2{-da, -db};
+                        }
+                    }
+                    x.a[i] = warp_xbar<MODE>(x.a[i], gk.x);
+                    x.b[i] = warp_xbar<MODE>(x.b[i], gk.y);
+                } else if (mine) {
+                    P[k] = en;
+                }
+            }
+        }
+        if (MODE != kModePhaseWav) {
+            std::vector<f2> lo(32), hi(32);
+            for (int l = 0; l < 32; ++l) warp_mel_project(l, na, nb, lanek[l], lanek[32 + l], melp, P, lo[l], hi[l]);
+            for (int l = 0; l < 32; ++l) {
+                const int ms[2] = {lanek[64 + l], lanek[96 + l]};
                 const f2 mel[2] = {lo[l], hi[l]};
                 for (int q = 0; q < 2; ++q) {
                     const int m = ms[q];
@@ -307,26 +323,48 @@ static void run_warp(const EmulTables& e, int clamp, const float* y, long long L
                     if (out) { out[m * T + f] = va; if (has_b) out[m * T + f2i] = vb; }
                 }
             }
-            if (ypbar)
-                for (int l = 0; l < 32; ++l) warp_bin_cotangents(l, bins, melbar, L[l].g);
         }
         if (!ypbar) continue;
-        for (int l = 0; l < 32; ++l) warp_pack_send<MODE>(l, L[l].x, L[l].g, L[l].v, L[l].snd);
-        for (int l = 0; l < 32; ++l)
-            for (int i = 0; i < 16; ++i) L[l].rcv[i] = L[(32 - l) & 31].snd[i];
+        // backward, one owned bin per step
+        auto xbar = [&](int l, int i, cf& ya, cf& yb) {
+            ya = L[l].x.a[i];
+            yb = L[l].x.b[i];
+            if (MODE != kModePhaseWav) {
+                const f2 gk = warp_bin_cotangent(warp_bin_of(l, i), bins, melbar);
+                ya = warp_xbar<MODE>(ya, gk.x);
+                yb = warp_xbar<MODE>(yb, gk.y);
+            }
+        };
+        for (int i = 0; i < 16; ++i) {
+            for (int l = 0; l < 32; ++l) {
+                cf ya, yb, q, qm;
+                xbar(l, i, ya, yb);
+                warp_q_pair(ya, yb, q, qm);
+                if (i == 0 && l == 0) q = warp_q_real(ya, yb);
+                L[l].v[i] = q;
+                L[l].snd = qm;
+            }
+            for (int l = 0; l < 32; ++l) L[l].rcv = L[(32 - l) & 31].snd;
+            for (int l = 0; l < 32; ++l) {
+                if (i > 0) L[l].v[32 - i] = l == 0 ? L[l].rcv : L[l].prev;
+                L[l].prev = L[l].rcv;
+            }
+        }
         for (int l = 0; l < 32; ++l) {
-            warp_pack_recv<MODE>(l, L[l].x, L[l].g, L[l].rcv, L[l].v);
+            cf ya, yb;
+            xbar(l, 16, ya, yb);
+            L[l].v[16] = l == 0 ? warp_q_real(ya, yb) : L[l].prev;
             dft32<+1>(L[l].v);
         }
-        for (int l = 0; l < 32; ++l) warp_twiddle_store<+1>(l, L[l].v, tw4v.data(), xbuf);
+        for (int l = 0; l < 32; ++l) warp_twiddle_store<+1>(l, L[l].v, tw4, xbuf);
         for (int l = 0; l < 32; ++l) {
             warp_xchg_load(l, xbuf, L[l].v);
             dft32<+1>(L[l].v);
         }
-        for (int l = 0; l < 32; ++l) warp_store_gradients(l, L[l].v, win2.data(), wbuf + kWarpGOff);
+        for (int l = 0; l < 32; ++l) warp_store_gradients(l, L[l].v, win2, wbuf);
         for (int n = 0; n < kNfft; ++n) {
-            ypbar[f * hop + n] += wbuf[kWarpGOff + n];
-            if (has_b) ypbar[f2i * hop + n] += wbuf[kWarpGOff + kNfft + n];
+            ypbar[f * hop + n] += wbuf[n];
+            if (has_b) ypbar[f2i * hop + n] += wbuf[kWarpGStride + n];
         }
     }
     *sumsq = acc;
@@ -334,10 +372,11 @@ static void run_warp(const EmulTables& e, int clamp, const float* y, long long L
 
 extern "C" {
 void emul_stft_guidance_warp(const EmulTables* e, int mode, int clamp, const float* y, long long Ly, int hop,
-                             const float* mask, const float* ref, float* out, float* ypbar, double* sumsq) {
-    if (mode == 0) run_warp<kModeMelDb>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
-    else if (mode == 1) run_warp<kModePhaseMel>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
-    else run_warp<kModePhaseWav>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq);
+                             const float* mask, const float* ref, float* out, float* ypbar, double* sumsq,
+                             const float* image, int na, int nb, int pair_shift) {
+    if (mode == 0) run_warp<kModeMelDb>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq, image, na, nb, pair_shift);
+    else if (mode == 1) run_warp<kModePhaseMel>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq, image, na, nb, pair_shift);
+    else run_warp<kModePhaseWav>(*e, clamp, y, Ly, hop, mask, ref, out, ypbar, sumsq, image, na, nb, pair_shift);
 }
 
 // LogSpectralDistance frames (csrc/metrics.cu lsd_pair_kernel): frame t of the reference clip rides as frame A, frame t of

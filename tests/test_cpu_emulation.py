@@ -97,7 +97,7 @@ def test_stockham_fft(emul, n, inverse):
 ENGINES = ["frame", "pair", "warp"]
 
 
-def _run(emul, mode, clamp, y, hop, window, ref=None, mask=None, grad=True, engine="frame"):
+def _run(emul, mode, clamp, y, hop, window, ref=None, mask=None, grad=True, engine="frame", pair_shift=0):
     t, keep = _tables(window)
     Ly = y.shape[0]
     T = 1 + Ly // hop
@@ -111,9 +111,14 @@ def _run(emul, mode, clamp, y, hop, window, ref=None, mask=None, grad=True, engi
     maskk = np.ascontiguousarray(mask, np.float32) if mask is not None else None
     fn = {"frame": emul.emul_stft_guidance, "pair": emul.emul_stft_guidance_pair,
           "warp": emul.emul_stft_guidance_warp}[engine]
+    extra = ()
+    if engine == "warp":  # the kernel's host-built table image (tables.py warp_image)
+        img, na, nb = tables.warp_image(window, tables.mel_filterbank(16000))
+        keep["img"] = img.numpy().copy()
+        extra = (_ptr(keep["img"]), na, nb, pair_shift)
     fn(C.byref(t), mode, clamp, _ptr(y), C.c_longlong(Ly), hop,
        _ptr(maskk) if maskk is not None else None, _ptr(refk) if refk is not None else None, _ptr(out),
-       _ptr(ypbar) if grad else None, C.byref(ss))
+       _ptr(ypbar) if grad else None, C.byref(ss), *extra)
     del refp
     return out, ypbar, ss.value
 
@@ -153,6 +158,54 @@ def test_mel_db_guidance(emul, L, engine):
         if mask is not None:
             got = got * mask[0].numpy()
         assert rel_l2(got, g) < 1e-4
+
+
+@pytest.mark.parametrize("pair_shift", [0, 1])
+def test_warp_engine_pairs_quiet_with_loud_frames(emul, pair_shift):
+    """The warp engine transforms two frames jointly; without balancing their magnitudes a quiet frame picks up ~1e-7 of
+    its loud partner, which the 1 / mel derivative near the dB floor amplifies (measured: 3.4e-5 on this case when the
+    pairs start at an odd frame, against 1.5e-6 for per-frame transforms).  With the power-of-two balancing both
+    pairings stay at fp32 rounding distance from the frame-at-a-time pipeline and inside 1e-4 of torch."""
+    L = 16000
+    mask = oo.inpaint_mask(1, 16000, "box", 0.25, 0.5)
+    op = oo.OracleOperator("inpainting", mask=mask)
+    ref_wav = stubs.synth_clips(1, L, first=50)
+    wav = stubs.synth_clips(1, L)
+    ref_mel = op.transform(op.forward(ref_wav))[0].numpy()
+    grads = {}
+    for eng in ("frame", "warp"):
+        _, ypbar, ss = _run(emul, 0, 0, wav[0].numpy(), 160, tables.hann_window(), engine=eng, ref=ref_mel,
+                            mask=mask[0].numpy(), pair_shift=pair_shift)
+        grads[eng] = _fold(ypbar, L) / np.sqrt(ss) * mask[0].numpy()
+    loss, g = _torch_loss_grad(op, wav, op.forward(ref_wav), "mel_spectrogram")
+    assert rel_l2(grads["warp"], grads["frame"]) < 4e-6
+    assert rel_l2(grads["warp"], g) < 1e-5
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("shift", [0, 160])
+def test_silent_frames_next_to_loud_ones(emul, engine, shift):
+    """A masked stretch longer than a frame leaves all-zero frames right next to loud ones (every inpainting step does).
+    torch.stft returns an exactly zero spectrum for them (-100 dB after the 1e-10 floor, zero gradient); the warp engine
+    transforms two frames jointly and has to restore that exactly (the joint transform alone leaves ~1e-7 of the loud
+    frame's magnitude in the silent one, enough to cross the floor).  `shift` moves the frame pairing by one frame."""
+    L = 8000
+    wav = stubs.synth_clips(1, L) * 3.0
+    ref_wav = stubs.synth_clips(1, L, first=50) * 3.0
+    mask = torch.ones(1, L)
+    mask[:, 2000 + shift:6000 + shift] = 0.0
+    op = oo.OracleOperator("inpainting", mask=mask)
+    ref_mel = op.transform(op.forward(ref_wav))
+    out, ypbar, ss = _run(emul, 0, 0, wav[0].numpy(), 160, tables.hann_window(), engine=engine,
+                          ref=ref_mel[0].numpy(), mask=mask[0].numpy())
+    want = op.transform(op.forward(wav))[0].numpy()
+    silent = (want == -100.0).all(axis=0)
+    assert silent.sum() >= 15
+    assert (out[:, silent] == -100.0).all()
+    assert rel_l2(out, want) < 2e-5
+    loss, g = _torch_loss_grad(op, wav, op.forward(ref_wav), "mel_spectrogram")
+    assert abs(np.sqrt(ss) - loss) < 1e-4 * loss
+    assert rel_l2(_fold(ypbar, L) / np.sqrt(ss) * mask[0].numpy(), g) < 1e-4
 
 
 @pytest.mark.parametrize("engine", ENGINES)

@@ -258,6 +258,57 @@ def test_batched_step_is_per_clip(sched_name, op_name, eta):
         assert rel_l2(got.prev_sample[i], want.prev_sample[i]) < TOL
 
 
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3", "cfg4"])
+def test_step_parity_at_baseline_shapes(cfg):
+    """`.step` at the exact BASELINE.json shapes -- 10 s clips (L = 160000), latents (B, 8, 250, 16), the bench's batch
+    sizes -- against `oracle.steps.per_clip_step` (scheduling_dps.py:137-219 and its clones), t in {999, 501, 1}:
+      cfg1 inpainting box[2 s, 3 s) + DDIM, B = 1;      cfg2 super-resolution x2 + DPS, B = 16;
+      cfg3 phase retrieval + DSG (eta 1), B = 8;        cfg4 dereverberation K = 5000 + DiffMusic (eta 1), B = 16.
+    The product runs the whole batch in one call; the oracle runs the first, a middle and the last clip as batch-1
+    steps (per-clip semantics; the CPU convolution with 5000 taps costs seconds per clip)."""
+    sched_name, op_name, B, eta = {"cfg1": ("ddim", "inpainting", 1, 0.0), "cfg2": ("dps", "super_resolution", 16, 0.0),
+                                   "cfg3": ("dsg", "phase_retrieval", 8, 1.0),
+                                   "cfg4": ("diffmusic", "dereverberation", 16, 1.0)}[cfg]
+    L, H = 160000, 250
+    vae, voc = stubs.StubVAE(), stubs.StubVocoder()
+    x, e = stubs.synth_latents(B, H)
+    ref = stubs.synth_clips(1, L, first=50)
+    ir = None
+    if op_name == "inpainting":
+        oop, op = oo.OracleOperator("inpainting", mask=oo.inpaint_mask(10, 16000, "box", 2, 3)), _inpaint(10, 2, 3)
+    elif op_name == "super_resolution":
+        oop, op = oo.OracleOperator("super_resolution", scale=2), dm.SuperResolutionOperator(16000, 2, _noiser())
+    elif op_name == "phase_retrieval":
+        oop, op = oo.OracleOperator("phase_retrieval"), dm.PhaseRetrievalOperator(noiser=_noiser())
+    else:
+        torch.manual_seed(5)
+        ir = oo.draw_impulse_response(5000, 0.99)
+        oop, op = oo.OracleOperator("dereverberation", fixed_ir=ir), dm.MusicDereverberationOperator(5000, 0.99, _noiser())
+        op.generate_impulse_response = lambda ir_length, decay_factor: ir  # the step's draw, same as the oracle's
+    meas = oop.forward(ref)
+    base = osteps.make_base(**stubs.MUSICLDM_SCHED)
+    base.set_timesteps(500)
+    sched = dm.get_scheduler(sched_name)(operator=op, **stubs.MUSICLDM_SCHED)
+    sched.set_timesteps(500)
+    vae_d, voc_d = stubs.StubVAE().to(DEV), stubs.StubVocoder().to(DEV)
+    pick = sorted({0, B // 2, B - 1})
+    kw = dict(eta=eta, vae=None, vocoder=None, original_waveform_length=L)
+    if RATES[sched_name] is not None:
+        kw.update(ip_guidance_rate=RATES[sched_name], supervised_space="mel_spectrogram")
+    for t in (999, 501, 1):
+        got = sched.step(e.to(DEV), t, x.to(DEV), generator=stubs.step_generators(B), measurement=meas.to(DEV),
+                         **dict(kw, vae=vae_d, vocoder=voc_d))
+        gens = stubs.step_generators(B)
+        for i in pick:
+            want = osteps.reference_step(sched_name, base, oop, e[i:i + 1], t, x[i:i + 1], generator=gens[i],
+                                         measurement=meas, **dict(kw, vae=vae, vocoder=voc))
+            assert rel_l2(got.prev_sample[i:i + 1], want.prev_sample) < TOL, (cfg, t, i)
+            assert rel_l2(got.pred_original_sample[i:i + 1], want.pred_original_sample) < TOL, (cfg, t, i)
+            if sched_name != "ddim":
+                wl = float(want.loss)
+                assert abs(float(got.loss_per_clip[i]) - wl) < TOL * wl, (cfg, t, i)
+
+
 def test_step_argument_errors():
     op = _inpaint()
     sched = dm.DPSScheduler(operator=op, **stubs.MUSICLDM_SCHED)
@@ -559,8 +610,8 @@ def test_mel_to_waveform_with_phase_full_size():
 
 def test_waveform_to_spectrogram_vs_reference():
     """waveform_to_spectrogram (diffmusic/utils.py:11-20) through dm_stft_spectrogram: the reference function's own output
-    (tests/golden/istft.npz), the float64 oracle at full size, and the magnitude bit-equal to PhaseRetrievalOperator.forward
-    (same frame-pair arithmetic, different tiling)."""
+    (tests/golden/istft.npz), the float64 oracle at full size, and the magnitude against PhaseRetrievalOperator.forward
+    (bit-equal on the same 64-thread frame-pair engine, fp32 rounding apart from the warp-per-pair engine)."""
     import os
     from oracle import istft as oi
     from tests.conftest import GOLDEN
@@ -582,7 +633,13 @@ def test_waveform_to_spectrogram_vs_reference():
     rel, dphi = _spectrogram_error(mag[2:3].cpu().numpy(), phase[2:3].cpu().numpy(), wm, wp)
     assert rel < 3e-6 and dphi < 2e-3
     op = dm.PhaseRetrievalOperator(1024, 160, 1024, noiser=dm.get_noiser("gaussian", 0.0))
-    assert torch.equal(op.forward(wav.to(DEV)), mag)
+    from diffmusic_b200 import _lib
+    assert rel_l2(op.forward(wav.to(DEV)), mag) < 1e-6
+    _lib.call("dm_stft_set_engine", 2)
+    try:
+        assert torch.equal(op.forward(wav.to(DEV)), mag)
+    finally:
+        _lib.call("dm_stft_set_engine", 0)
     ph = phase.cpu().numpy()
     assert np.isin(ph[:, [0, 512]], np.float32([0.0, np.pi])).all()   # real DC / Nyquist bins: angle 0 or pi exactly
     m512, p512 = dm.waveform_to_spectrogram(wav[:1, :20000].to(DEV), hop_length=512)
@@ -708,9 +765,9 @@ def test_stft_kernels_agree_for_every_tile_size(op_name, nf, monkeypatch):
                 res[name] = _loss_grad(op, wav, meas, space)
             finally:
                 _lib.call("dm_stft_set_engine", 0)
-        for name in ("auto", "pair"):
+        for name, tol in (("auto", 5e-6), ("pair", 2e-6)):  # 32 x 32 transform vs radix-8 passes: fp32 rounding apart
             assert rel_l2(res[name][0], res["frame"][0]) < 1e-6, (space, name)
-            assert rel_l2(res[name][1], res["frame"][1]) < 2e-6, (space, name)
+            assert rel_l2(res[name][1], res["frame"][1]) < tol, (space, name)
     t = {}
     for name, eng in engines:
         _lib.call("dm_stft_set_engine", eng)

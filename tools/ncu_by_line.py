@@ -14,6 +14,7 @@ import sys
 
 sass_path, kernel, csv_path = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+by_samples = len(sys.argv) > 5 and sys.argv[5] == "samples"  # order the per-line table by stall samples
 
 lines = open(sass_path).read().split("\n")
 start = next(i for i, l in enumerate(lines) if l.startswith(".text." + kernel + ":"))
@@ -61,5 +62,5 @@ for (f, ln), v in agg.items():
     byfile[f][1] += v[1]
 for f, v in sorted(byfile.items(), key=lambda kv: -kv[1][0]):
     print(f"{f:24s} inst {100 * v[0] / ti:5.1f}%  samples {100 * v[1] / max(ts, 1):5.1f}%")
-for (f, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, ln), v in sorted(agg.items(), key=lambda kv: -kv[1][1 if by_samples else 0])[:top]:
     print(f"{f}:{ln:<5d} inst {v[0]:9d} {100 * v[0] / ti:5.1f}%  samples {v[1]:6d} {100 * v[1] / max(ts, 1):5.1f}%")
