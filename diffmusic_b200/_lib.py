@@ -74,6 +74,21 @@ _SIGNATURES = {
     "dm_fad_moments": (c_i, [c_p, c_ll, c_i, c_p, c_p]),
     "dm_fad_moments_ex": (c_i, [c_p, c_ll, c_i, c_p, c_i, c_p]),
     "dm_fad_finalize": (c_i, [c_p, c_i, c_p, c_p, c_p]),
+    "dm_fad_finalize_sym": (c_i, [c_p, c_i, c_p, c_p, c_p]),
+    "dm_enable_peer_access": (c_i, [c_i, c_i]),
+    "dm_peer_alloc": (c_i, [c_i, c_ll, c_p]),
+    "dm_peer_free": (c_i, [c_i, c_p]),
+    "dm_ipc_export": (c_i, [c_i, c_p, c_p]),
+    "dm_ipc_open": (c_i, [c_i, c_p, c_p]),
+    "dm_ipc_close": (c_i, [c_i, c_p]),
+    "dm_fad_packed_doubles": (c_ll, [c_i]),
+    "dm_fad_flag_words": (c_i, []),
+    "dm_fad_reset_shared": (c_i, [c_p, c_i, c_p, c_i, C.c_uint, c_p]),
+    "dm_fad_allreduce_peers": (c_i, [c_p, c_p, c_i, c_i, c_i, C.c_uint, c_p, c_p]),
+    "dm_fad_allreduce": (c_i, [c_p, c_p, c_i, c_p, c_p]),
+    "dm_fad_pack_tri": (c_i, [c_p, c_i, c_p, c_p]),
+    "dm_fad_unpack_tri": (c_i, [c_p, c_i, c_p, c_p]),
+    "dm_workspace_bytes": (c_ll, [c_i, c_ll, c_ll, c_i]),
     "dm_fad_gather_rows": (c_i, [c_p, c_ll, c_i, c_p, c_ll, c_p, c_p]),
     "dm_sym_eig_jacobi": (c_i, [c_p, c_i, c_i, C.c_double, c_p, c_p, c_p]),
     "dm_frechet_workspace_doubles": (c_ll, [c_i]),

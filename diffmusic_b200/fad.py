@@ -14,16 +14,52 @@ from . import _lib
 
 
 class EmbeddingMoments:
-    """Accumulator of raw moments for one embedding model of width d."""
+    """Accumulator of raw moments for one embedding model of width d.
+
+    exchange: how `all_reduce` sums the moments over ranks (only the upper triangle of sum x x^T travels either way):
+      "peer"  -- one kernel per rank reads every peer's accumulator over NVLink (CUDA-IPC mapped memory, no collective
+                 library, no host synchronisation; csrc/fad_exchange.cu).  The accumulator then lives in peer-visible
+                 memory and is reused round after round: call `reset()` to start the next one.
+      "nccl"  -- torch.distributed all_reduce of the packed triangle (any backend; what the gloo tests exercise).
+      None    -- "nccl" when torch.distributed is initialised with more than one rank, else nothing to do."""
 
     ENGINES = {"auto": 0, "simt": 1, "tcgen05": 2, "tcgen05_pair": 3}
 
-    def __init__(self, d, device=None, engine="auto"):
+    def __init__(self, d, device=None, engine="auto", exchange=None, group=None):
         self.d = int(d)
         self.engine = self.ENGINES[engine]
+        self.exchange = exchange
+        self.group = group
         # the accumulator may live on the CPU (gloo tests of the exchange step); update()/finalize() need CUDA
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.acc = torch.zeros(1 + self.d + self.d * self.d, device=self.device, dtype=torch.float64)
+        n = 1 + self.d + self.d * self.d
+        self.peers = None
+        self._reduced = None
+        self._round = 0
+        if exchange == "peer":
+            from . import parallel
+            self.peers = parallel.PeerGroup(n, int(_lib.load().dm_fad_flag_words()), device=self.device, group=group)
+            self.acc = self.peers.buf
+            self._sum = torch.empty(n, device=self.device, dtype=torch.float64)
+            import ctypes as C
+            W = self.peers.world
+            self._acc_ptrs = (C.c_void_p * W)(*self.peers.ptrs)
+            self._flag_ptrs = (C.c_void_p * W)(*self.peers.flag_ptrs)
+            self.reset()
+        else:
+            self.acc = torch.zeros(n, device=self.device, dtype=torch.float64)
+
+    def reset(self):
+        """start a new round: clear the accumulator (peer mode: once every peer has finished reading the last round)"""
+        self._reduced = None
+        if self.peers is not None:
+            # wait for the peers' DONE of the last exchange this accumulator took part in (round numbers count
+            # exchanges, so any number of resets between two exchanges is fine)
+            _lib.call("dm_fad_reset_shared", self.acc.data_ptr(), self.d, self.peers.flags.data_ptr(), self.peers.world,
+                      self._round, _lib.stream())
+        else:
+            self.acc.zero_()
+        return self
 
     def update(self, embd):
         """embd: (n_frames, d) fp16 (what fadtk caches, model_loader.py:46-48) or any float dtype (cast to fp16 only
@@ -40,14 +76,49 @@ class EmbeddingMoments:
         return self
 
     def all_reduce(self, group=None):
-        """Sum the moments over ranks: one collective of 1 + d + d^2 float64 (the only exchange on this path)."""
+        """Sum the moments over ranks: the only exchange on this path, 1 + d + d (d + 1) / 2 float64 per rank."""
         import torch.distributed as dist
+        group = group if group is not None else self.group
+        if self.peers is not None:
+            self._round += 1
+            _lib.call("dm_fad_allreduce_peers", self._acc_ptrs, self._flag_ptrs, self.peers.world, self.peers.rank,
+                      self.d, self._round, self._sum.data_ptr(), _lib.stream())
+            self._reduced = self._sum
+            return self
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.acc, op=dist.ReduceOp.SUM, group=group)
+            packed = self.packed()
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+            self._reduced = self.unpacked(packed)
         return self
 
+    # packed = [n | sum x | rows i of sum x x^T from column i on]: what travels between ranks
+    def packed(self):
+        d = self.d
+        if self.acc.is_cuda:
+            out = torch.empty(int(_lib.load().dm_fad_packed_doubles(d)), device=self.device, dtype=torch.float64)
+            _lib.call("dm_fad_pack_tri", self.acc.data_ptr(), d, out.data_ptr(), _lib.stream())
+            return out
+        iu = torch.triu_indices(d, d)
+        return torch.cat([self.acc[:1 + d], self.acc[1 + d:].reshape(d, d)[iu[0], iu[1]]])
+
+    def unpacked(self, packed):
+        """accumulator with (at least) the upper triangle of sum x x^T filled from `packed`"""
+        d = self.d
+        out = torch.zeros_like(self.acc)
+        if self.acc.is_cuda:
+            _lib.call("dm_fad_unpack_tri", packed.data_ptr(), d, out.data_ptr(), _lib.stream())
+            return out
+        iu = torch.triu_indices(d, d)
+        out[:1 + d] = packed[:1 + d]
+        out[1 + d:].reshape(d, d)[iu[0], iu[1]] = packed[1 + d:]
+        return out
+
+    def moments(self):
+        """the (all-reduced, if all_reduce ran) accumulator; sum x x^T is guaranteed on the upper triangle only"""
+        return self._reduced if self._reduced is not None else self.acc
+
     def count(self):
-        return int(round(float(self.acc[0].item())))
+        return int(round(float(self.moments()[0].item())))
 
     def finalize(self):
         """(mu (d,), cov (d, d)) float64 on the device; cov is zeros when fewer than 2 frames (fadtk/utils.py:42-46)."""
@@ -55,8 +126,12 @@ class EmbeddingMoments:
             raise _lib.DiffMusicB200Error("dm_fad_finalize needs a CUDA accumulator (no CPU fallback)")
         mu = torch.empty(self.d, device=self.device, dtype=torch.float64)
         cov = torch.empty((self.d, self.d), device=self.device, dtype=torch.float64)
-        _lib.call("dm_fad_finalize", self.acc.data_ptr(), self.d, mu.data_ptr(), cov.data_ptr(), _lib.stream())
+        _lib.call("dm_fad_finalize_sym", self.moments().data_ptr(), self.d, mu.data_ptr(), cov.data_ptr(), _lib.stream())
         return mu, cov
+
+    def close(self):
+        if self.peers is not None:
+            self.peers.close()
 
 
 def calc_embd_statistics(embd_lst):
@@ -65,7 +140,16 @@ def calc_embd_statistics(embd_lst):
         raise AssertionError(f"FAD requires at least two embedding window frames, you have {tuple(embd_lst.shape)}.")
     t = torch.as_tensor(embd_lst)
     mu, cov = EmbeddingMoments(t.shape[1]).update(t).finalize()
-    return mu.cpu().numpy(), cov.cpu().numpy()
+    return _mean_like_numpy(mu, t.dtype).cpu().numpy(), cov.cpu().numpy()
+
+
+def _mean_like_numpy(mu, in_dtype):
+    """np.mean keeps a floating input's dtype: for the fp16 arrays fadtk caches (model_loader.py:46-48) the reference's
+    mean is an fp16 array while np.cov is float64.  The exact float64 mean is rounded to that dtype
+    once (numpy rounds a float32-accumulated mean: the two can differ by one fp16 ulp in rare elements)."""
+    if in_dtype in (torch.float16, torch.float32):
+        return mu.to(in_dtype)
+    return mu
 
 
 def calculate_embd_statistics_online(arrays, group=None):
@@ -140,7 +224,13 @@ def calc_frechet_distance(mu1, cov1, mu2, cov2, eps=1e-6):
         raise _lib.DiffMusicB200Error("dm_frechet_distance needs CUDA (no CPU fallback)")
     dev = torch.device("cuda", torch.cuda.current_device())
     args = (_as_dev_f64(mu1, dev), _as_dev_f64(cov1, dev), _as_dev_f64(mu2, dev), _as_dev_f64(cov2, dev))
-    return float(_frechet_checked([frechet_distance_device(*args)], [args])[0, 0])
+    d2 = float(_frechet_checked([frechet_distance_device(*args)], [args])[0, 0])
+    # The mean term in the reference's own arithmetic: `diff = mu1 - mu2; diff.dot(diff)` runs in the dtype NumPy
+    # promotes the two means to (fadtk/fad.py:83, 112) -- fp16 when both come from fp16 embedding caches,
+    # which rounds |mu1 - mu2|^2 to 11 bits.  d of these on the host; the trace terms stay on the device.
+    diff = mu1 - mu2
+    exact = (mu1.astype(np.float64) - mu2.astype(np.float64))
+    return d2 - float(exact.dot(exact)) + float(diff.dot(diff))
 
 
 class FADInfResults(tuple):
@@ -177,11 +267,13 @@ def score_inf(mu_base, cov_base, embeds, steps=25, min_n=500):
     if not torch.cuda.is_available():
         raise _lib.DiffMusicB200Error("score_inf needs CUDA (no CPU fallback)")
     dev = torch.device("cuda", torch.cuda.current_device())
+    emb_dtype = torch.as_tensor(embeds).dtype
     x = torch.as_tensor(embeds).to(device=dev, dtype=torch.float16).contiguous()
     N, d = x.shape
     mu_b, cov_b = _as_dev_f64(np.atleast_1d(mu_base), dev), _as_dev_f64(np.atleast_2d(cov_base), dev)
     ns = [int(n) for n in np.linspace(min_n, N, steps)]
-    outs, args = [], []
+    base_dtype = np.atleast_1d(mu_base).dtype
+    outs, args, fixes = [], [], []
     # The points are independent and a Jacobi solve is a chain of ~2-4 us rounds that leaves most of the GPU idle: they
     # are spread round-robin over a few side streams (rows are still drawn in the reference's order on the host).
     cur = torch.cuda.current_stream(dev)
@@ -196,12 +288,23 @@ def score_inf(mu_base, cov_base, embeds, steps=25, min_n=500):
             sub = torch.empty((n, d), device=dev, dtype=torch.float16)
             _lib.call("dm_fad_gather_rows", x.data_ptr(), N, d, idx.data_ptr(), n, sub.data_ptr(), _lib.stream())
             mu, cov = EmbeddingMoments(d, device=dev).update(sub).finalize()
+            # the reference takes np.mean of the fp16 rows (fad.py:334): an fp16-rounded mean enters the distance
+            mu = _mean_like_numpy(mu, emb_dtype).to(torch.float64)
             args.append((mu_b, cov_b, mu, cov))
             outs.append(frechet_distance_device(*args[-1]))
+            if base_dtype == np.float16 and emb_dtype == torch.float16:
+                # both means are fp16 arrays in the reference: `diff.dot(diff)` is fp16 arithmetic (see
+                # calc_frechet_distance); the same rounding here, on the device, without a host read
+                diff16 = mu_b.to(torch.float16) - mu.to(torch.float16)
+                quirk = (diff16.double() ** 2).sum().to(torch.float16).double()
+                fixes.append(quirk - ((mu_b - mu) ** 2).sum())
+            else:
+                fixes.append(torch.zeros((), device=dev, dtype=torch.float64))
     for s in pool:
         if s is not cur:
             cur.wait_stream(s)
-    fad = _frechet_checked(outs, args)[:, 0].numpy()  # one synchronisation for the whole sweep (+ rare retries)
+    fix = torch.stack(fixes)
+    fad = _frechet_checked(outs, args)[:, 0].numpy() + fix.cpu().numpy()  # one synchronisation for the whole sweep
     results = [[n, float(s)] for n, s in zip(ns, fad)]
     ys = np.array(results)
     xs = 1 / np.array(ns)

@@ -242,6 +242,50 @@ int dm_fad_moments(const void* x_f16, long long N, int d, double* acc, dm_stream
 int dm_fad_moments_ex(const void* x_f16, long long N, int d, double* acc, int engine, dm_stream_t stream);
 /* mu (d) and cov (d, d) in float64 from acc */
 int dm_fad_finalize(const double* acc, int d, double* mu, double* cov, dm_stream_t stream);
+/* the same from an accumulator whose sum x x^T holds (at least) the upper triangle -- what the exchanges below leave */
+int dm_fad_finalize_sym(const double* acc, int d, double* mu, double* cov, dm_stream_t stream);
+
+/* The one exchange of the path (fadtk/utils.py:36-40 across GPUs): sum acc over the ranks of a node.
+ * Only [n | sum x | UPPER TRIANGLE of sum x x^T] crosses the links: dm_fad_packed_doubles(d) = 1 + d + d (d + 1) / 2.
+ *
+ * (a) over NVLink peer memory, no collective library: every rank's acc and a flag pad of dm_fad_flag_words() zeroed
+ *     32-bit words live in memory the peers have mapped (e.g. CUDA IPC).  Per round (round = 1, 2, ... per call, the same
+ *     on all ranks):  dm_fad_reset_shared (waits until every peer has read exchange round `done_round` -- the last
+ *     one this accumulator took part in, 0 if none -- then clears acc) -> dm_fad_moments ... -> dm_fad_allreduce_peers (one kernel: flags READY to the peers, waits for theirs, sums
+ *     every peer's acc in rank order -- bit-identical on all ranks -- into out_acc, flags DONE).  peer_acc /
+ *     peer_flags: HOST arrays of `world` device pointers, entry r = rank r's buffers (entry `rank` = this rank's own).
+ *     Nothing synchronises with the host.
+ * (b) dm_fad_allreduce: through ncclAllReduce on a caller-owned communicator (ncclComm_t passed as void*; the symbol is
+ *     resolved from the process at run time, the library does not link NCCL), in place on acc;
+ *     packed_work: dm_fad_packed_doubles(d) doubles of scratch. */
+int dm_enable_peer_access(int device, int peer_device); /* kernels on `device` may read / write `peer_device` memory */
+/* Peer-visible buffers for the exchange above: zeroed device memory of this process (dm_peer_alloc), its 64-byte CUDA
+ * IPC handle (dm_ipc_export; hand it to the other ranks of the node by any host channel), and the mapping of a peer's
+ * handle into this process WITH `device` CURRENT (dm_ipc_open), so kernels on `device` can dereference the result. */
+int dm_peer_alloc(int device, long long bytes, void** ptr);
+int dm_peer_free(int device, void* ptr);
+int dm_ipc_export(int device, const void* ptr, unsigned char* handle64);
+int dm_ipc_open(int device, const unsigned char* handle64, void** ptr);
+int dm_ipc_close(int device, void* ptr);
+long long dm_fad_packed_doubles(int d);
+int dm_fad_flag_words(void);
+int dm_fad_reset_shared(double* acc, int d, const unsigned* my_flags, int world, unsigned done_round,
+                        dm_stream_t stream);
+int dm_fad_allreduce_peers(const double* const* peer_acc, unsigned* const* peer_flags, int world, int rank, int d,
+                           unsigned round, double* out_acc, dm_stream_t stream);
+int dm_fad_allreduce(void* nccl_comm, double* acc, int d, double* packed_work, dm_stream_t stream);
+int dm_fad_pack_tri(const double* acc, int d, double* packed, dm_stream_t stream);
+int dm_fad_unpack_tri(const double* packed, int d, double* acc, dm_stream_t stream);
+
+/* Workspace sizes in bytes (the library never allocates; callers size their buffers with this):
+ *   DM_WS_STFT_COTANGENT (a = Ly, b = B), DM_WS_STFT_PARTIAL (a = Ly, b = B, c = frames per tile; hop 160),
+ *   DM_WS_FAD_ACC / DM_WS_FAD_PACKED (c = d), DM_WS_FAD_FLAGS.  Returns -1 for invalid arguments. */
+#define DM_WS_STFT_COTANGENT 0
+#define DM_WS_STFT_PARTIAL 1
+#define DM_WS_FAD_ACC 2
+#define DM_WS_FAD_PACKED 3
+#define DM_WS_FAD_FLAGS 4
+long long dm_workspace_bytes(int kind, long long a, long long b, int c);
 
 
 /* ------------------------------------------------------------------------------------------------------------------

@@ -18,8 +18,10 @@ What is restated here (each function cites the reference file:line it follows, p
 * ``oracle.steps``      -- diffmusic/schedulers/scheduling_{ddim,dps,mpgd,dsg,diffmusic}.py ``.step``.  **Pinned**
   against fixtures produced by running the reference's unmodified scheduler files (through a diffusers shim whose
   base class is ``oracle.ddim_base``; so the guidance algebra is pinned, the diffusers base is not).
-* ``oracle.fad``        -- fadtk/fad.py:41-47 and fadtk/utils.py:13-46 in NumPy float64.  fadtk/utils.py cannot be
-  imported (needs hypy_utils), and the reference's only fadtk test needs network models and a missing blob
-  (fadtk/stats/fma_pop.npz), so mean/cov are **unpinned** by reference vectors; they are pinned to NumPy itself
-  (np.mean / np.cov ARE the reference's implementation).
+* ``oracle.fad``        -- fadtk/fad.py:41-47, 50-119, 303-350 and fadtk/utils.py:13-46 in NumPy / SciPy float64.
+  fadtk cannot be imported (hypy_utils, embedding-model loaders) and its only test needs network models and a
+  missing blob (fadtk/stats/fma_pop.npz).  **Pinned**: tests/golden/make_fad_golden.py cuts the reference's own
+  functions out of fadtk/fad.py and fadtk/utils.py with ``ast`` and runs them unmodified on seeded fp16 embeddings
+  (statistics incl. the fp16 mean of SURVEY.md D.11, Frechet distance, FAD-inf, the online merge over .npy files)
+  -> tests/golden/fad.npz; tests/test_oracle_vs_golden.py holds the restatement to those outputs.
 """

@@ -4,11 +4,11 @@ fadtk/fad.py:41-47 (`calc_embd_statistics`) and fadtk/utils.py:13-46 (`_process_
 `calculate_embd_statistics_online`).  fadtk/utils.py cannot be imported here (hypy_utils is absent); its arithmetic
 is np.mean / np.cov (float64) and a pairwise (Chan) merge, restated below on in-memory arrays instead of .npy files.
 
-`calc_frechet_distance` / `score_inf` restate fadtk/fad.py:50-119, 303-350 with the same SciPy / NumPy calls.  PARITY
-UNPINNED for these two: fadtk/fad.py itself cannot be imported (hypy_utils, embedding-model loaders), and the reference's
-only FAD test (fadtk/test, samples_FAD_scores.csv) needs network models and a missing statistics blob.  What pins them
-here instead: closed forms (identical Gaussians -> 0, commuting covariances -> sum (sqrt(a) - sqrt(b))^2), checked in
-tests/test_oracle_vs_golden.py.
+`calc_frechet_distance` / `score_inf` restate fadtk/fad.py:50-119, 303-350 with the same SciPy / NumPy calls.  PINNED:
+tests/golden/make_fad_golden.py cuts the reference's own functions (calc_embd_statistics, calc_frechet_distance,
+FrechetAudioDistanceTK.score_inf, _process_file, calculate_embd_statistics_online) out of fadtk/fad.py and fadtk/utils.py
+with `ast` and runs them unmodified on seeded fp16 embeddings; tests/test_oracle_vs_golden.py holds every function of this
+file to those outputs (tests/golden/fad.npz), next to the closed forms (identical Gaussians -> 0, commuting covariances).
 """
 from __future__ import annotations
 

@@ -101,3 +101,21 @@ def istft_inputs(name):
 
 #: waveform_to_spectrogram fixtures of istft.npz: name -> clip length (clips synth_clips(2, L, first=70))
 SPECTROGRAM_CASES = {"w2s_4000": 4000, "w2s_4133": 4133}
+
+
+# ---- FAD statistics / Frechet distance cases (tests/golden/make_fad_golden.py, fad.npz) ----
+#: name -> (frames of set 1, frames of set 2, embedding width d, files the first set is split into for the online merge)
+FAD_CASES = {"d128": (900, 700, 128, 5), "d64_few": (90, 400, 64, 3), "d96": (1500, 1200, 96, 7)}
+
+
+def fad_embeddings(name):
+    """two seeded (n, d) fp16 embedding sets, as fadtk caches them (model_loader.py:46-48): correlated features with
+    different means and scales, so that the covariances are neither diagonal nor equal"""
+    import numpy as np
+    n1, n2, d, _ = FAD_CASES[name]
+    rng = np.random.default_rng(100 + d + n1)
+    mix1 = rng.standard_normal((d, d)) / np.sqrt(d)
+    mix2 = mix1 + 0.3 * rng.standard_normal((d, d)) / np.sqrt(d)
+    a = rng.standard_normal((n1, d)) @ mix1 * 1.5 + rng.standard_normal(d) * 0.4
+    b = rng.standard_normal((n2, d)) @ mix2 * 1.2 + rng.standard_normal(d) * 0.4 + 0.1
+    return a.astype(np.float16), b.astype(np.float16)

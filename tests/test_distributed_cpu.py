@@ -1,5 +1,5 @@
 """world_size-2 gloo tests (CPU) of the N>1 host logic: clip sharding (no collective on the guided path) and the single
-all-reduce of the packed FAD moments [n | sum x | sum x x^T] (fadtk/utils.py:19-46 equivalence)."""
+all-reduce of the packed FAD moments [n | sum x | upper triangle of sum x x^T] (fadtk/utils.py:19-46 equivalence)."""
 import os
 
 import numpy as np
@@ -32,10 +32,13 @@ def _worker(rank, world, port, d, q):
         mom.acc[0] += a64.shape[0]
         mom.acc[1:1 + d] += torch.from_numpy(a64.sum(0))
         mom.acc[1 + d:] += torch.from_numpy((a64.T @ a64).ravel())
+    assert mom.packed().numel() == 1 + d + d * (d + 1) // 2   # only the upper triangle of sum x x^T travels
     mom.all_reduce()
     n = mom.count()
-    sx = mom.acc[1:1 + d].numpy()
-    sxx = mom.acc[1 + d:].numpy().reshape(d, d)
+    acc = mom.moments()
+    sx = acc[1:1 + d].numpy()
+    up = np.triu(acc[1 + d:].numpy().reshape(d, d))
+    sxx = up + np.triu(up, 1).T
     mu, cov = ofad.moments_to_stats(n, sx, sxx)
     want_mu, want_cov = ofad.embd_statistics_online([f.astype(np.float64) for f in files])
     ok = (n == sum(f.shape[0] for f in files) and np.allclose(mu, want_mu, rtol=1e-10, atol=1e-12)

@@ -434,19 +434,70 @@ def test_fad_moments_engines(n, d, engine):
 
 @pytest.mark.parametrize("n,d", [(40, 128), (1000, 512), (4990, 768), (333, 1024)])
 def test_fad_statistics_vs_numpy(n, d):
+    """calc_embd_statistics / the online merge on the SAME fp16 array the reference sees (fadtk caches embeddings as
+    fp16, model_loader.py:46-48).  np.mean of an fp16 array is an fp16 array: the product returns its
+    exact float64 mean rounded to fp16 once, which may differ from numpy's float32-accumulated rounding by one fp16 ulp
+    in rare elements; np.cov is float64.  The online merge of the reference feeds the fp16-rounded per-file means into
+    the Chan update (fadtk/utils.py:13-16, 36-40); the product sums exact raw moments instead (superseded quirk):
+    bounded by the fp16 rounding of the means, 2^-11 relative per element."""
     from diffmusic_b200 import fad
     from oracle import fad as ofad
     rng = np.random.default_rng(d)
     X = (rng.standard_normal((n, d)) * 0.7 + rng.standard_normal(d) * 0.3).astype(np.float16)
     mu, cov = fad.calc_embd_statistics(X)
-    wmu, wcov = ofad.calc_embd_statistics(X.astype(np.float64))
-    assert rel_l2(mu, wmu) < 1e-6 and rel_l2(cov, wcov) < 1e-5
-    # file-wise online merge (fadtk/utils.py:19-46) == one pass over all frames
+    wmu, wcov = ofad.calc_embd_statistics(X)          # same fp16 input: fp16 mean, float64 covariance
+    assert mu.dtype == wmu.dtype == np.float16
+    ulp = np.abs(mu.view(np.int16).astype(np.int32) - wmu.view(np.int16).astype(np.int32))
+    assert ulp.max() <= 1 and (ulp == 0).mean() >= 0.95, (ulp.max(), (ulp == 0).mean())
+    assert rel_l2(cov, wcov) < 1e-5
+    mu64, _ = fad.calc_embd_statistics(X.astype(np.float64))   # float64 in -> float64 mean, like np.mean
+    assert mu64.dtype == np.float64 and rel_l2(mu64, X.astype(np.float64).mean(0)) < 1e-6
+    # file-wise online merge (fadtk/utils.py:19-46) against one pass over all frames
     parts = np.array_split(X, 7)
     mu2, cov2 = fad.calculate_embd_statistics_online(parts)
-    omu, ocov = ofad.embd_statistics_online([p.astype(np.float64) for p in parts])
-    assert rel_l2(mu2, omu) < 1e-6 and rel_l2(cov2, ocov) < 1e-5
+    omu, ocov = ofad.embd_statistics_online(parts)    # the reference's arithmetic on the same fp16 files
+    exact_mu, exact_cov = ofad.embd_statistics_online([p.astype(np.float64) for p in parts])
+    assert rel_l2(mu2, exact_mu) < 1e-6 and rel_l2(cov2, exact_cov) < 1e-5
+    # the reference's quirk, bounded: fp16 rounding of the per-file means (2^-11 relative per element) and what it does
+    # to the cross terms of the Chan update (largest for few frames per file: 3e-4 at 6 frames, 1e-4 at 48)
+    assert rel_l2(mu2, omu) < 2.0 ** -11 and rel_l2(cov2, ocov) < 5e-4, (rel_l2(mu2, omu), rel_l2(cov2, ocov))
     assert np.allclose(cov2, cov2.T)
+
+
+def test_fad_vs_reference_functions():
+    """the product against tests/golden/fad.npz: outputs of the reference's own calc_embd_statistics,
+    calc_frechet_distance, calculate_embd_statistics_online and score_inf (fadtk/fad.py:41-47, 50-119, 303-350,
+    fadtk/utils.py:13-46) run unmodified on seeded fp16 embeddings (tests/golden/make_fad_golden.py)."""
+    import os
+    from diffmusic_b200 import fad
+    from tests.conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "fad.npz"))
+    for name, (n1, n2, d, parts) in stubs.FAD_CASES.items():
+        a, b = stubs.fad_embeddings(name)
+        mu1, c1 = fad.calc_embd_statistics(a)
+        mu2, c2 = fad.calc_embd_statistics(b)
+        for got, want in ((mu1, z[name + "_mu1"]), (mu2, z[name + "_mu2"])):
+            assert got.dtype == np.float16
+            ulp = np.abs(got.view(np.int16).astype(np.int32) - want.view(np.int16).astype(np.int32))
+            assert ulp.max() <= 1 and (ulp == 0).mean() >= 0.95
+        assert rel_l2(c1, z[name + "_cov1"]) < 1e-5 and rel_l2(c2, z[name + "_cov2"]) < 1e-5
+        # distance from the reference's own statistics (isolates the solver) and from the product's (end to end)
+        want = float(z[name + "_fd"])
+        got = fad.calc_frechet_distance(z[name + "_mu1"], z[name + "_cov1"], z[name + "_mu2"], z[name + "_cov2"])
+        assert abs(got - want) <= 1e-8 * want, (name, got, want)
+        got2 = fad.calc_frechet_distance(mu1, c1, mu2, c2)
+        assert abs(got2 - want) <= 1e-4 * want, (name, got2, want)
+        omu, ocov = fad.calculate_embd_statistics_online(np.array_split(a, parts))
+        assert rel_l2(omu, z[name + "_online_mu"]) < 2.0 ** -11 and rel_l2(ocov, z[name + "_online_cov"]) < 5e-4
+    a, b = stubs.fad_embeddings("d128")
+    mu_b, cov_b = fad.calc_embd_statistics(b)
+    np.random.seed(1234)
+    r = fad.score_inf(mu_b, cov_b, a, steps=6, min_n=200)
+    want = z["inf_points"]
+    pts = np.array(r.points)
+    assert np.array_equal(pts[:, 0], want[:, 0])                 # same sample sizes, same rows (numpy's global generator)
+    assert np.allclose(pts[:, 1], want[:, 1], rtol=1e-4, atol=0)
+    assert abs(r.score - float(z["inf_score"])) <= 1e-3 * abs(float(z["inf_score"]))   # intercept of a 6-point fit
 
 
 # ------------------------------------------------------------------------------------------------ Frechet distance
@@ -503,7 +554,7 @@ def test_fad_inf_matches_reference_loop():
     emb = (rng.standard_normal((N, d)) * rng.uniform(0.5, 1.5, d) + 0.1).astype(np.float16)
     mu_b, cov_b = _gauss_stats(rng, 5000, d, 1.0, 0.0)
     np.random.seed(123)
-    want = ofad.score_inf(mu_b, cov_b, emb.astype(np.float64), steps=7, min_n=500)
+    want = ofad.score_inf(mu_b, cov_b, emb, steps=7, min_n=500)  # the same fp16 rows: fp16 means
     np.random.seed(123)
     got = fad.score_inf(mu_b, cov_b, emb, steps=7, min_n=500)
     assert [p[0] for p in got.points] == [p[0] for p in want[3]]
@@ -1051,6 +1102,54 @@ def test_guided_steps_in_16_bit_pipelines(sched_name, op_name, eta, dt, tol):
     assert rel_l2(low.prev_sample.float(), full.prev_sample) < tol
     assert rel_l2(low.pred_original_sample.float(), full.pred_original_sample) < tol
     assert rel_l2(low.loss_per_clip, full.loss_per_clip) < 4 * tol
+
+
+@pytest.mark.parametrize("sched_name,op_name,eta", [("dps", "super_resolution", 0.0), ("mpgd", "inpainting", 1.0),
+                                                    ("dsg", "inpainting", 1.0), ("diffmusic", "inpainting", 1.0)])
+def test_fp16_step_against_the_reference_arithmetic_run_in_fp16(sched_name, op_name, eta):
+    """run.py:218 loads the pipelines with torch_dtype=float16, so the REFERENCE does the scheduler algebra in fp16 (the
+    0-d fp32 scalars promote to the tensors' dtype).  The oracle is run exactly like that -- half latents,
+    half stand-in networks, half step noise from the same seeded generator, CPU -- and the product gets the same half
+    inputs on the GPU: its fp16 step (fp32 algebra, rounded once) stays within a few fp16 ulps of the reference-in-fp16.
+    DPS / MPGD take a given `variance_noise`, so their fp32 oracle run sees the same noise and the product must also be
+    at least as close to it as the reference-in-fp16 is; DSG / DiffMusic always draw their noise in the tensors' dtype
+    (scheduling_dsg.py:215-220), and a half draw is a different sample than a float draw, so only the fp16 runs compare."""
+    vae, voc = stubs.StubVAE(), stubs.StubVocoder()
+    x, e = stubs.synth_latents(1, 25)
+    oop = {"super_resolution": oo.OracleOperator("super_resolution", scale=2),
+           "inpainting": oo.OracleOperator("inpainting", mask=oo.inpaint_mask(1, 16000, "box", 0.25, 0.5))}[op_name]
+    op = _ops()[op_name]
+    meas = oop.forward(stubs.synth_clips(1, L1, first=50))
+    base = osteps.make_base(**stubs.MUSICLDM_SCHED)
+    base.set_timesteps(500)
+    z = torch.randn(1, 8, 25, 16, generator=torch.Generator().manual_seed(7))
+    noise_kw = (lambda dt: dict(variance_noise=z.to(dt))) if sched_name in ("dps", "mpgd") else \
+        (lambda dt: dict(generator=torch.Generator().manual_seed(3)))
+    kw = dict(eta=eta, ip_guidance_rate=RATES[sched_name], measurement=meas, original_waveform_length=L1,
+              supervised_space="mel_spectrogram")
+    want32 = osteps.reference_step(sched_name, base, oop, e, 501, x, vae=vae, vocoder=voc, **noise_kw(torch.float32), **kw)
+    want16 = osteps.reference_step(sched_name, base, oop, e.half(), 501, x.half(), vae=stubs.StubVAE().half(),
+                                   vocoder=stubs.StubVocoder().half(), **noise_kw(torch.float16), **kw)
+    assert want16.prev_sample.dtype == torch.float16
+    sched = dm.get_scheduler(sched_name)(operator=op, **stubs.MUSICLDM_SCHED)
+    sched.set_timesteps(500)
+    gkw = dict(kw, measurement=meas.to(DEV))
+    if sched_name in ("dps", "mpgd"):
+        gkw["variance_noise"] = z.to(DEV).half()
+    else:
+        gkw["generator"] = torch.Generator().manual_seed(3)
+    got = sched.step(e.to(DEV).half(), 501, x.to(DEV).half(), vae=stubs.StubVAE().to(DEV).half(),
+                     vocoder=stubs.StubVocoder().to(DEV).half(), **gkw)
+    assert got.prev_sample.dtype == torch.float16
+    err16 = rel_l2(got.prev_sample.float(), want16.prev_sample.float())
+    err16_x0 = rel_l2(got.pred_original_sample.float(), want16.pred_original_sample.float())
+    print(sched_name, "product-fp16 vs reference-in-fp16: prev", err16, "x0", err16_x0)
+    assert err16 < 3e-3 and err16_x0 < 3e-3, (err16, err16_x0)
+    assert abs(float(got.loss) - float(want16.loss)) < 3e-3 * float(want16.loss)
+    if sched_name in ("dps", "mpgd"):
+        err_prod = rel_l2(got.prev_sample.float(), want32.prev_sample)
+        err_ref16 = rel_l2(want16.prev_sample.float(), want32.prev_sample)
+        assert err_prod <= max(1.5 * err_ref16, 2e-3), (err_prod, err_ref16)
 
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])

@@ -177,6 +177,36 @@ def test_frechet_oracle_closed_forms():
     assert slope > 0  # the finite-sample bias of FAD shrinks like 1/n
 
 
+def test_fad_oracle_matches_reference_functions():
+    """oracle.fad against tests/golden/fad.npz = the outputs of the reference's own calc_embd_statistics,
+    calc_frechet_distance, score_inf (fadtk/fad.py:41-47, 50-119, 303-350) and calculate_embd_statistics_online
+    (fadtk/utils.py:13-46), cut out of the reference with `ast` and run unmodified (tests/golden/make_fad_golden.py)."""
+    import os
+    from oracle import fad as ofad
+    from tests.conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "fad.npz"))
+    for name, (n1, n2, d, parts) in stubs.FAD_CASES.items():
+        a, b = stubs.fad_embeddings(name)
+        mu1, c1 = ofad.calc_embd_statistics(a)
+        mu2, c2 = ofad.calc_embd_statistics(b)
+        assert mu1.dtype == np.float16 and np.array_equal(mu1, z[name + "_mu1"])   # the fp16 mean of SURVEY.md D.11
+        assert np.array_equal(mu2, z[name + "_mu2"])
+        assert np.array_equal(c1, z[name + "_cov1"]) and np.array_equal(c2, z[name + "_cov2"])
+        fd = float(np.real(ofad.calc_frechet_distance(mu1, c1, mu2, c2)))
+        assert abs(fd - float(z[name + "_fd"])) <= 1e-9 * float(z[name + "_fd"])
+        omu, ocov = ofad.embd_statistics_online(np.array_split(a, parts))
+        assert np.array_equal(omu, z[name + "_online_mu"]) and np.array_equal(ocov, z[name + "_online_cov"])
+    a, b = stubs.fad_embeddings("d128")
+    mu_b, cov_b = ofad.calc_embd_statistics(b)
+    np.random.seed(1234)
+    score, slope, r2, points = ofad.score_inf(mu_b, cov_b, a, steps=6, min_n=200)
+    want = z["inf_points"]
+    assert np.array_equal(np.array(points)[:, 0], want[:, 0])
+    assert np.allclose(np.real(np.array(points)[:, 1]), want[:, 1], rtol=1e-9, atol=0)
+    assert abs(score - float(z["inf_score"])) <= 1e-8 * abs(float(z["inf_score"]))
+    assert abs(r2 - float(z["inf_r2"])) <= 1e-8
+
+
 def test_metric_oracles_closed_forms():
     """oracle.metrics: LSD of a clip with itself is 0, scaling a clip by c shifts every log-magnitude by log10(c);
     MSE of constant offsets; nan_to_num sanitising as in lsd.py:23 / mse.py:14-15."""
