@@ -396,21 +396,66 @@ __global__ void __launch_bounds__(kEwThreads) resample2_adjoint_reg_kernel(
     }
 }
 
+// ---- pure streaming kernels: 128-bit accesses (two float4 in flight per thread and iteration) with a scalar tail;
+// the scalar path also takes rows / pointers that are not 16-byte aligned
+__device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 __global__ void __launch_bounds__(kEwThreads) mask_apply_kernel(const float* __restrict__ x, long long x_bstride,
                                                                 long long L, const float* __restrict__ mask,
                                                                 float* __restrict__ y) {
     const int b = blockIdx.y;
+    const float* xb = x + (long long)b * x_bstride;
+    float* yb = y + (long long)b * L;
     const long long stride = (long long)gridDim.x * kEwThreads;
-    for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < L; i += stride)
-        y[(long long)b * L + i] = x[(long long)b * x_bstride + i] * __ldg(mask + i);
+    const long long t0 = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+    long long done = 0;
+    if (aligned16_dev(xb) && aligned16_dev(yb) && aligned16_dev(mask)) {
+        const long long nv = L / 4;
+        const float4* x4 = reinterpret_cast<const float4*>(xb);
+        const float4* m4 = reinterpret_cast<const float4*>(mask);
+        float4* y4 = reinterpret_cast<float4*>(yb);
+        for (long long i = t0; i < nv; i += 2 * stride) {
+            const long long i2 = i + stride;
+            const float4 a = x4[i], m = __ldg(m4 + i);
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f), n = c;
+            if (i2 < nv) c = x4[i2], n = __ldg(m4 + i2);
+            y4[i] = make_float4(a.x * m.x, a.y * m.y, a.z * m.z, a.w * m.w);
+            if (i2 < nv) y4[i2] = make_float4(c.x * n.x, c.y * n.y, c.z * n.z, c.w * n.w);
+        }
+        done = nv * 4;
+    }
+    for (long long i = done + t0; i < L; i += stride) yb[i] = xb[i] * __ldg(mask + i);
 }
 
 __global__ void __launch_bounds__(kEwThreads) add_scaled_kernel(float* __restrict__ y,
                                                                 const float* __restrict__ noise, float sigma,
                                                                 long long n) {
     const long long stride = (long long)gridDim.x * kEwThreads;
-    for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += stride)
-        y[i] = y[i] + noise[i] * sigma;
+    const long long t0 = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+    long long done = 0;
+    if (aligned16_dev(y) && aligned16_dev(noise)) {
+        const long long nv = n / 4;
+        float4* y4 = reinterpret_cast<float4*>(y);
+        const float4* z4 = reinterpret_cast<const float4*>(noise);
+        for (long long i = t0; i < nv; i += 2 * stride) {
+            const long long i2 = i + stride;
+            float4 a = y4[i];
+            const float4 z = z4[i];
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f), w = c;
+            if (i2 < nv) c = y4[i2], w = z4[i2];
+            // y + noise * sigma with the product rounded first, like the reference's two torch ops (noise.py:17-18)
+            a.x = __fadd_rn(a.x, __fmul_rn(z.x, sigma)), a.y = __fadd_rn(a.y, __fmul_rn(z.y, sigma));
+            a.z = __fadd_rn(a.z, __fmul_rn(z.z, sigma)), a.w = __fadd_rn(a.w, __fmul_rn(z.w, sigma));
+            y4[i] = a;
+            if (i2 < nv) {
+                c.x = __fadd_rn(c.x, __fmul_rn(w.x, sigma)), c.y = __fadd_rn(c.y, __fmul_rn(w.y, sigma));
+                c.z = __fadd_rn(c.z, __fmul_rn(w.z, sigma)), c.w = __fadd_rn(c.w, __fmul_rn(w.w, sigma));
+                y4[i2] = c;
+            }
+        }
+        done = nv * 4;
+    }
+    for (long long i = done + t0; i < n; i += stride) y[i] = __fadd_rn(y[i], __fmul_rn(noise[i], sigma));
 }
 
 }  // namespace dm
@@ -606,7 +651,7 @@ extern "C" int dm_resample_adjoint(const float* ybar, int pad, long long Ly, int
 extern "C" int dm_mask_apply(const float* x, long long x_bstride, long long L, int B, const float* mask, float* y,
                              dm_stream_t stream) {
     DM_REQUIRE(x && mask && y && L > 0 && B > 0);
-    const int nblk = (int)min((long long)num_sms() * 4, (L + kEwThreads - 1) / kEwThreads);
+    const int nblk = (int)min((long long)num_sms() * 4, (L / 8 + kEwThreads) / kEwThreads);  // two float4 per thread
     mask_apply_kernel<<<dim3(nblk, B), kEwThreads, 0, as_stream(stream)>>>(x, x_bstride, L, mask, y);
     DM_LAUNCHED();
     return DM_OK;
@@ -615,12 +660,21 @@ extern "C" int dm_mask_apply(const float* x, long long x_bstride, long long L, i
 __global__ void __launch_bounds__(kEwThreads) copy_f32_kernel(float* __restrict__ dst, const float* __restrict__ src,
                                                               long long n) {
     const long long stride = (long long)gridDim.x * kEwThreads;
-    for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+    const long long t0 = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+    long long done = 0;
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+        const long long nv = n / 4;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (long long i = t0; i < nv; i += stride) d4[i] = s4[i];
+        done = nv * 4;
+    }
+    for (long long i = done + t0; i < n; i += stride) dst[i] = src[i];
 }
 
 extern "C" int dm_copy_f32(float* dst, const float* src, long long n, dm_stream_t stream) {
     DM_REQUIRE(dst && src && n > 0);
-    const int nblk = (int)min((long long)num_sms() * 2, (n + kEwThreads - 1) / kEwThreads);
+    const int nblk = (int)min((long long)num_sms() * 2, (n / 4 + kEwThreads) / kEwThreads);
     copy_f32_kernel<<<nblk, kEwThreads, 0, as_stream(stream)>>>(dst, src, n);
     DM_LAUNCHED();
     return DM_OK;
@@ -628,7 +682,7 @@ extern "C" int dm_copy_f32(float* dst, const float* src, long long n, dm_stream_
 
 extern "C" int dm_add_scaled(float* y, const float* noise, float sigma, long long n, dm_stream_t stream) {
     DM_REQUIRE(y && noise && n > 0);
-    const int nblk = (int)min((long long)num_sms() * 8, (n + kEwThreads - 1) / kEwThreads);
+    const int nblk = (int)min((long long)num_sms() * 8, (n / 8 + kEwThreads) / kEwThreads);
     add_scaled_kernel<<<nblk, kEwThreads, 0, as_stream(stream)>>>(y, noise, sigma, n);
     DM_LAUNCHED();
     return DM_OK;

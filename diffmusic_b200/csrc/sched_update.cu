@@ -132,17 +132,27 @@ __device__ __forceinline__ void load_coef(const float* __restrict__ c, float& sq
 
 enum EwKind { kX0 = 0, kDdim = 1, kDps = 2, kMpgd = 3 };
 
+// one vector of the elementwise step, split into its load and its compute / store half so that the kernel can keep the
+// loads of TWO grid-stride iterations in flight per thread (these kernels are pure HBM streams: bytes in flight per SM
+// decide the achieved bandwidth)
 template <int KIND, int W, int IO>
-__global__ void __launch_bounds__(kThreads) ew_update_kernel(EwParams p, long long nvec) {
-    load_coef(p.coef, p.sqrt_a, p.sqrt_b, p.sqrt_p, p.dir_coef, p.std);
-    if (KIND != kX0 && p.loss_total != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
-        write_loss_total(p.losses, p.n_losses, p.loss_total);
-    const long long stride = (long long)gridDim.x * kThreads;
-    for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += stride) {
-        float x[W], a[W], g[W], z[W], o[W], o2[W];
+struct EwVec {
+    float x[W], a[W], g[W], z[W];
+    bool has_z;
+    __device__ __forceinline__ void load(const EwParams& p, long long v) {
         ldio<IO, W>(p.x, v, x);
         if (KIND == kX0) {
             ldio<IO, W>(p.eps, v, a);
+            return;
+        }
+        ldv<W>(p.x0, v, a);
+        if (KIND != kDdim) ldio<IO, W>(p.g0, v, g);
+        has_z = (KIND != kDdim) && p.z != nullptr;
+        if (has_z) ldv<W>(p.z, v, z);
+    }
+    __device__ __forceinline__ void finish(const EwParams& p, long long v) {
+        float o[W], o2[W];
+        if (KIND == kX0) {
 #pragma unroll
             for (int i = 0; i < W; ++i) {
                 float t = dvd(sub(x[i], mul(p.sqrt_b, a[i])), p.sqrt_a);
@@ -156,32 +166,44 @@ __global__ void __launch_bounds__(kThreads) ew_update_kernel(EwParams p, long lo
                 for (int i = 0; i < W; ++i) o2[i] = mul(p.leaf_scale, o[i]);
                 stio<IO, W>(p.x0_leaf, v, o2);
             }
-        } else {
-            ldv<W>(p.x0, v, a);
-            if (KIND != kDdim) {
-                ldio<IO, W>(p.g0, v, g);
-#pragma unroll
-                for (int i = 0; i < W; ++i) g[i] = mul(g[i], p.leaf_scale);  // dLoss/dx0 (autograd of leaf_scale * x0)
-            }
-            const bool has_z = (KIND != kDdim) && p.z != nullptr;
-            if (has_z) ldv<W>(p.z, v, z);
-#pragma unroll
-            for (int i = 0; i < W; ++i) {
-                float x0 = a[i];
-                if (KIND == kMpgd) x0 = sub(x0, mul(p.rate, g[i]));                 // scheduling_mpgd.py:199-200
-                float e = dvd(sub(x[i], mul(p.sqrt_a, x0)), p.sqrt_b);              // noise_pred
-                float prev = add(mul(p.sqrt_p, x0), mul(p.dir_coef, e));
-                if (has_z) prev = add(prev, mul(p.std, z[i]));
-                if (KIND == kDps) prev = sub(prev, mul(p.rate, dvd(g[i], p.sqrt_a)));  // scheduling_dps.py:212-213
-                o[i] = prev;
-                o2[i] = x0;
-            }
-            stio<IO, W>(p.prev, v, o);
-            if (KIND == kMpgd) {
-                if (IO == DM_IO_F32 || p.x0_pub == nullptr) stv<W>(p.x0_out, v, o2);
-                else stio<IO, W>(p.x0_pub, v, o2);
-            }
+            return;
         }
+        if (KIND != kDdim) {
+#pragma unroll
+            for (int i = 0; i < W; ++i) g[i] = mul(g[i], p.leaf_scale);  // dLoss/dx0 (autograd of leaf_scale * x0)
+        }
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            float x0 = a[i];
+            if (KIND == kMpgd) x0 = sub(x0, mul(p.rate, g[i]));                 // scheduling_mpgd.py:199-200
+            float e = dvd(sub(x[i], mul(p.sqrt_a, x0)), p.sqrt_b);              // noise_pred
+            float prev = add(mul(p.sqrt_p, x0), mul(p.dir_coef, e));
+            if (has_z) prev = add(prev, mul(p.std, z[i]));
+            if (KIND == kDps) prev = sub(prev, mul(p.rate, dvd(g[i], p.sqrt_a)));  // scheduling_dps.py:212-213
+            o[i] = prev;
+            o2[i] = x0;
+        }
+        stio<IO, W>(p.prev, v, o);
+        if (KIND == kMpgd) {
+            if (IO == DM_IO_F32 || p.x0_pub == nullptr) stv<W>(p.x0_out, v, o2);
+            else stio<IO, W>(p.x0_pub, v, o2);
+        }
+    }
+};
+
+template <int KIND, int W, int IO>
+__global__ void __launch_bounds__(kThreads) ew_update_kernel(EwParams p, long long nvec) {
+    load_coef(p.coef, p.sqrt_a, p.sqrt_b, p.sqrt_p, p.dir_coef, p.std);
+    if (KIND != kX0 && p.loss_total != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+        write_loss_total(p.losses, p.n_losses, p.loss_total);
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long v = (long long)blockIdx.x * kThreads + threadIdx.x; v < nvec; v += 2 * stride) {
+        const long long v2 = v + stride;
+        EwVec<KIND, W, IO> e0, e1;
+        e0.load(p, v);
+        if (v2 < nvec) e1.load(p, v2);
+        e0.finish(p, v);
+        if (v2 < nvec) e1.finish(p, v2);
     }
 }
 
