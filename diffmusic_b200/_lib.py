@@ -86,6 +86,8 @@ _SIGNATURES = {
     "dm_fad_reset_shared": (c_i, [c_p, c_i, c_p, c_i, C.c_uint, c_p]),
     "dm_fad_allreduce_peers": (c_i, [c_p, c_p, c_i, c_i, c_i, C.c_uint, c_p, c_p]),
     "dm_fad_allreduce": (c_i, [c_p, c_p, c_i, c_p, c_p]),
+    "dm_fad_allreduce_push": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, C.c_uint, c_p]),
+    "dm_fad_finalize_shared": (c_i, [c_p, c_i, c_p, c_i, C.c_uint, c_p, c_p, c_p]),
     "dm_fad_pack_tri": (c_i, [c_p, c_i, c_p, c_p]),
     "dm_fad_unpack_tri": (c_i, [c_p, c_i, c_p, c_p]),
     "dm_workspace_bytes": (c_ll, [c_i, c_ll, c_ll, c_i]),

@@ -1,14 +1,18 @@
 // The one exchange step of the path: summing the per-rank FAD moments  acc = [n | sum x | sum x x^T]
 // (fadtk/utils.py:36-40, the Chan merge, as a sum of raw moments) over the GPUs of one node.
 //
-// One-shot all-reduce over NVLink peer memory, written here instead of calling a collective library:
-//   * every rank keeps its accumulator in memory its peers have mapped (CUDA IPC; the host side only exchanges the
-//     handles once, diffmusic_b200/parallel.py PeerGroup);
-//   * dm_fad_allreduce_peers launches ONE kernel per rank: block 0 raises this rank's READY flag in every peer's flag pad
-//     (system-scope release), every block waits until all peers are READY (acquire), then each block sums its rows of
-//     every peer's accumulator in rank order -- the same order on every rank, so all ranks hold bit-identical sums --
-//     and only the UPPER TRIANGLE of sum x x^T crosses the links (the matrix is symmetric: 1 + d + d (d + 1) / 2 doubles
-//     instead of 1 + d + d^2); the last block raises DONE in every peer's pad;
+// All-reduce over NVLink peer memory, written here instead of calling a collective library:
+//   * every rank keeps its accumulator (and the buffer the sum lands in) in memory its peers have mapped (CUDA IPC; the
+//     host side only exchanges the handles once, diffmusic_b200/parallel.py PeerGroup);
+//   * dm_fad_allreduce_push (the default, "two-shot"): ONE kernel per rank.  Block 0 raises this rank's READY flag in
+//     every peer's flag pad (system-scope release) and every block waits until all peers are READY (acquire).  Rank r then
+//     REDUCES the rows i = r, r + W, r + 2W, ... of the upper triangle of sum x x^T -- reading that row from every peer in
+//     rank order, so all ranks end up with bit-identical sums -- and PUSHES the reduced row into every peer's sum buffer.
+//     Per GPU 2 (W - 1) / W of the 1 + d + d (d + 1) / 2 doubles cross the links (4.1 MB at d = 768, W = 8) instead of
+//     W - 1 times the triangle (16.6 MB) for the one-shot variant below.  The last block raises DONE in every peer's pad
+//     (after a system fence: the pushed rows are visible); dm_fad_finalize_shared waits for every rank's DONE before it
+//     reads the sum;
+//   * dm_fad_allreduce_peers (one-shot, kept for A/B and tiny worlds): every rank reads the whole triangle of every peer;
 //   * dm_fad_reset_shared (before the next accumulation) waits for every peer's DONE of the last exchange round before it
 //     clears the accumulator, so no rank overwrites moments a slower peer is still reading.
 // Flags are monotonically increasing round numbers: no flag is ever reset, nothing synchronises with the host.
@@ -100,10 +104,62 @@ __global__ void __launch_bounds__(kXchgThreads) fad_allreduce_peers_kernel(PeerP
     }
 }
 
+// two-shot: reduce my rows of the triangle from all peers, push them into every peer's sum buffer
+struct PushPtrs {
+    double* sum[kXchgMaxWorld];
+};
+__global__ void __launch_bounds__(kXchgThreads) fad_allreduce_push_kernel(PeerPtrs p, PushPtrs q, int world, int rank,
+                                                                          int d, unsigned round) {
+    unsigned* mine = p.flags[rank];
+    if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+        __threadfence_system();  // this rank's moments (written by the kernels before this one) are visible system-wide
+        st_release_sys(p.flags[threadIdx.x] + kFlagReady + rank, round);
+    }
+    wait_flags(mine + kFlagReady, world, round);
+    if (blockIdx.x == 0) {  // n and sum x: d + 1 values, every rank sums them for itself
+        double* out = q.sum[rank];
+        for (int i = threadIdx.x; i < 1 + d; i += kXchgThreads) {
+            double s = 0.0;
+            for (int r = 0; r < world; ++r) s += ld_peer(p.acc[r] + i);
+            out[i] = s;
+        }
+    } else {
+        const int i = rank + world * (blockIdx.x - 1);  // rows are interleaved over the ranks: equal triangle shares
+        if (i < d) {
+            const long long row = 1 + d + (long long)i * d;
+            for (int j = i + threadIdx.x; j < d; j += kXchgThreads) {
+                double s = 0.0;
+                for (int r = 0; r < world; ++r) s += ld_peer(p.acc[r] + row + j);
+                for (int r = 0; r < world; ++r) q.sum[r][row + j] = s;
+            }
+        }
+    }
+    // last block: every pushed row is visible system-wide, then DONE (= "my rows have landed in your sum buffer" and
+    // "I have finished reading your accumulator")
+    __threadfence_system();  // every thread: its pushed values before the block counts itself done
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(mine + kFlagCounter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) mine[kFlagCounter] = 0u;
+        if ((int)threadIdx.x < world) {
+            __threadfence_system();
+            st_release_sys(p.flags[threadIdx.x] + kFlagDone + rank, round);
+        }
+    }
+}
+
 // mu, cov from an accumulator whose sxx holds (at least) the upper triangle
 __global__ void __launch_bounds__(kXchgThreads) fad_finalize_sym_kernel(const double* __restrict__ acc, int d,
                                                                         double* __restrict__ mu,
-                                                                        double* __restrict__ cov) {
+                                                                        double* __restrict__ cov,
+                                                                        const unsigned* __restrict__ my_flags,
+                                                                        int world, unsigned round) {
+    if (my_flags != nullptr) wait_flags(my_flags + kFlagDone, world, round);  // every rank's rows have landed in acc
     const double n = acc[0];
     const long long idx = (long long)blockIdx.x * kXchgThreads + threadIdx.x;
     if (idx >= (long long)d * d) return;
@@ -171,7 +227,37 @@ extern "C" int dm_fad_finalize_sym(const double* acc, int d, double* mu, double*
     DM_REQUIRE(acc && mu && cov && d > 0);
     const long long n = (long long)d * d;
     fad_finalize_sym_kernel<<<(unsigned)((n + kXchgThreads - 1) / kXchgThreads), kXchgThreads, 0, as_stream(stream)>>>(
-        acc, d, mu, cov);
+        acc, d, mu, cov, nullptr, 0, 0u);
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_fad_finalize_shared(const double* sum, int d, const unsigned* my_flags, int world, unsigned round,
+                                      double* mu, double* cov, dm_stream_t stream) {
+    DM_REQUIRE(sum && mu && cov && my_flags && d > 0 && world >= 1 && world <= kXchgMaxWorld && round >= 1);
+    const long long n = (long long)d * d;
+    fad_finalize_sym_kernel<<<(unsigned)((n + kXchgThreads - 1) / kXchgThreads), kXchgThreads, 0, as_stream(stream)>>>(
+        sum, d, mu, cov, my_flags, world, round);
+    DM_LAUNCHED();
+    return DM_OK;
+}
+
+extern "C" int dm_fad_allreduce_push(const double* const* peer_acc, double* const* peer_sum,
+                                     unsigned* const* peer_flags, int world, int rank, int d, unsigned round,
+                                     dm_stream_t stream) {
+    DM_REQUIRE(peer_acc && peer_sum && peer_flags && d > 0 && world >= 1 && world <= kXchgMaxWorld);
+    DM_REQUIRE(rank >= 0 && rank < world && round >= 1);
+    PeerPtrs p;
+    PushPtrs q;
+    for (int r = 0; r < kXchgMaxWorld; ++r) {
+        p.acc[r] = r < world ? peer_acc[r] : nullptr;
+        p.flags[r] = r < world ? peer_flags[r] : nullptr;
+        q.sum[r] = r < world ? peer_sum[r] : nullptr;
+        DM_REQUIRE(r >= world || (p.acc[r] != nullptr && p.flags[r] != nullptr && q.sum[r] != nullptr));
+    }
+    const int rows = (d - rank + world - 1) / world;  // rows rank, rank + W, ...
+    fad_allreduce_push_kernel<<<1 + (rows > 0 ? rows : 0), kXchgThreads, 0, as_stream(stream)>>>(p, q, world, rank, d,
+                                                                                                 round);
     DM_LAUNCHED();
     return DM_OK;
 }

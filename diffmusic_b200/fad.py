@@ -17,9 +17,11 @@ class EmbeddingMoments:
     """Accumulator of raw moments for one embedding model of width d.
 
     exchange: how `all_reduce` sums the moments over ranks (only the upper triangle of sum x x^T travels either way):
-      "peer"  -- one kernel per rank reads every peer's accumulator over NVLink (CUDA-IPC mapped memory, no collective
-                 library, no host synchronisation; csrc/fad_exchange.cu).  The accumulator then lives in peer-visible
-                 memory and is reused round after round: call `reset()` to start the next one.
+      "peer"  -- one kernel per rank over NVLink (CUDA-IPC mapped memory, no collective library, no host
+                 synchronisation; csrc/fad_exchange.cu): rank r reduces the triangle rows r, r + W, ... from every peer
+                 and pushes them into every rank's sum buffer.  The accumulator lives in peer-visible memory and is
+                 reused round after round: call `reset()` to start the next one.  "peer_oneshot": every rank reads the
+                 whole triangle of every peer instead (A/B).
       "nccl"  -- torch.distributed all_reduce of the packed triangle (any backend; what the gloo tests exercise).
       None    -- "nccl" when torch.distributed is initialised with more than one rank, else nothing to do."""
 
@@ -35,16 +37,21 @@ class EmbeddingMoments:
         n = 1 + self.d + self.d * self.d
         self.peers = None
         self._reduced = None
+        self._wait_done = False
         self._round = 0
-        if exchange == "peer":
+        if exchange in ("peer", "peer_oneshot", "peer_push"):
             from . import parallel
-            self.peers = parallel.PeerGroup(n, int(_lib.load().dm_fad_flag_words()), device=self.device, group=group)
-            self.acc = self.peers.buf
-            self._sum = torch.empty(n, device=self.device, dtype=torch.float64)
+            # one peer-visible allocation per rank: [accumulator | sum buffer | flag pad]
+            self.peers = parallel.PeerGroup(2 * n, int(_lib.load().dm_fad_flag_words()), device=self.device,
+                                            group=group)
+            self.acc = self.peers.buf[:n]
+            self._sum = self.peers.buf[n:]
             import ctypes as C
             W = self.peers.world
             self._acc_ptrs = (C.c_void_p * W)(*self.peers.ptrs)
+            self._sum_ptrs = (C.c_void_p * W)(*[q + 8 * n for q in self.peers.ptrs])
             self._flag_ptrs = (C.c_void_p * W)(*self.peers.flag_ptrs)
+            self._wait_done = False
             self.reset()
         else:
             self.acc = torch.zeros(n, device=self.device, dtype=torch.float64)
@@ -52,6 +59,7 @@ class EmbeddingMoments:
     def reset(self):
         """start a new round: clear the accumulator (peer mode: once every peer has finished reading the last round)"""
         self._reduced = None
+        self._wait_done = False
         if self.peers is not None:
             # wait for the peers' DONE of the last exchange this accumulator took part in (round numbers count
             # exchanges, so any number of resets between two exchanges is fine)
@@ -81,8 +89,14 @@ class EmbeddingMoments:
         group = group if group is not None else self.group
         if self.peers is not None:
             self._round += 1
-            _lib.call("dm_fad_allreduce_peers", self._acc_ptrs, self._flag_ptrs, self.peers.world, self.peers.rank,
-                      self.d, self._round, self._sum.data_ptr(), _lib.stream())
+            if self.exchange == "peer_oneshot" or (self.exchange == "peer" and self.peers.world <= 2):
+                # two ranks: reading the peer's triangle once moves the same bytes as reduce-and-push, in one phase
+                _lib.call("dm_fad_allreduce_peers", self._acc_ptrs, self._flag_ptrs, self.peers.world, self.peers.rank,
+                          self.d, self._round, self._sum.data_ptr(), _lib.stream())
+            else:  # reduce my rows, push them to everybody; complete once every rank has raised DONE (see finalize)
+                _lib.call("dm_fad_allreduce_push", self._acc_ptrs, self._sum_ptrs, self._flag_ptrs, self.peers.world,
+                          self.peers.rank, self.d, self._round, _lib.stream())
+                self._wait_done = True
             self._reduced = self._sum
             return self
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -114,7 +128,9 @@ class EmbeddingMoments:
         return out
 
     def moments(self):
-        """the (all-reduced, if all_reduce ran) accumulator; sum x x^T is guaranteed on the upper triangle only"""
+        """the (all-reduced, if all_reduce ran) accumulator; sum x x^T is guaranteed on the upper triangle only.  In
+        "peer" mode the sum is complete on the stream only after `finalize()` (whose kernel waits for every rank's
+        pushed rows); n and sum x are this rank's own work and valid right after `all_reduce()`."""
         return self._reduced if self._reduced is not None else self.acc
 
     def count(self):
@@ -126,7 +142,12 @@ class EmbeddingMoments:
             raise _lib.DiffMusicB200Error("dm_fad_finalize needs a CUDA accumulator (no CPU fallback)")
         mu = torch.empty(self.d, device=self.device, dtype=torch.float64)
         cov = torch.empty((self.d, self.d), device=self.device, dtype=torch.float64)
-        _lib.call("dm_fad_finalize_sym", self.moments().data_ptr(), self.d, mu.data_ptr(), cov.data_ptr(), _lib.stream())
+        if self.peers is not None and self._reduced is not None and self._wait_done:
+            _lib.call("dm_fad_finalize_shared", self._sum.data_ptr(), self.d, self.peers.flags.data_ptr(),
+                      self.peers.world, self._round, mu.data_ptr(), cov.data_ptr(), _lib.stream())
+        else:
+            _lib.call("dm_fad_finalize_sym", self.moments().data_ptr(), self.d, mu.data_ptr(), cov.data_ptr(),
+                      _lib.stream())
         return mu, cov
 
     def close(self):

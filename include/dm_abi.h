@@ -273,6 +273,14 @@ int dm_fad_reset_shared(double* acc, int d, const unsigned* my_flags, int world,
                         dm_stream_t stream);
 int dm_fad_allreduce_peers(const double* const* peer_acc, unsigned* const* peer_flags, int world, int rank, int d,
                            unsigned round, double* out_acc, dm_stream_t stream);
+/* (a') the default for W > 2: reduce-and-push ("two-shot").  Rank r reduces the triangle rows r, r + W, ... from every
+ *     peer's acc and writes them into EVERY rank's sum buffer (peer_sum[r]: peer-visible, same layout as acc), so
+ *     2 (W - 1) / W of the packed size crosses the links per GPU instead of (W - 1) times.  The sum is complete on a
+ *     rank once every rank has raised DONE for the round: dm_fad_finalize_shared waits for that inside its kernel. */
+int dm_fad_allreduce_push(const double* const* peer_acc, double* const* peer_sum, unsigned* const* peer_flags,
+                          int world, int rank, int d, unsigned round, dm_stream_t stream);
+int dm_fad_finalize_shared(const double* sum, int d, const unsigned* my_flags, int world, unsigned round, double* mu,
+                           double* cov, dm_stream_t stream);
 int dm_fad_allreduce(void* nccl_comm, double* acc, int d, double* packed_work, dm_stream_t stream);
 int dm_fad_pack_tri(const double* acc, int d, double* packed, dm_stream_t stream);
 int dm_fad_unpack_tri(const double* packed, int d, double* acc, dm_stream_t stream);

@@ -30,8 +30,14 @@ def _peer_worker(rank, world, port, d, q):
         dist.init_process_group("gloo", rank=rank, world_size=world)
         from diffmusic_b200 import _lib, fad
         rounds = _data(None, world, d, 3)
-        mom = fad.EmbeddingMoments(d, device=f"cuda:{rank}", exchange="peer")
         ok = True
+        one = fad.EmbeddingMoments(d, device=f"cuda:{rank}", exchange="peer_oneshot")  # A/B variant: same sums, bit for bit
+        mom = fad.EmbeddingMoments(d, device=f"cuda:{rank}", exchange="peer")
+        for i, b in enumerate(rounds[0]):
+            if i % world == rank:
+                one.update(torch.from_numpy(b))
+        one.all_reduce()
+        mu1, cov1 = one.finalize()
         for r, blocks in enumerate(rounds):
             if r > 0:
                 mom.reset()
@@ -41,8 +47,8 @@ def _peer_worker(rank, world, port, d, q):
                     mom.update(torch.from_numpy(b))
             local = mom.acc.clone()
             mom.all_reduce()
+            mu, cov = mom.finalize()       # its kernel waits until every rank's rows have landed
             got = mom.moments().clone()
-            mu, cov = mom.finalize()
             torch.cuda.synchronize()
             # (1) the sum over ranks, in rank order, of the ranks' own accumulators: bit-exact on the exchanged part
             parts = [torch.zeros_like(local).cpu() for _ in range(world)]
@@ -58,6 +64,8 @@ def _peer_worker(rank, world, port, d, q):
             emu = np.linalg.norm(mu.cpu().numpy() - A.mean(0)) / np.linalg.norm(A.mean(0))
             ecov = np.linalg.norm(cov.cpu().numpy() - np.cov(A, rowvar=False)) / np.linalg.norm(np.cov(A, rowvar=False))
             ok &= bool(mom.count() == A.shape[0] and emu < 1e-6 and ecov < 1e-5)
+            if r == 0:
+                ok &= bool(torch.equal(mu, mu1) and torch.equal(cov, cov1))
         # NCCL variant on a communicator of our own (ncclComm_t handed over as a raw pointer)
         import glob
         import torch as _t
@@ -94,6 +102,7 @@ def _peer_worker(rank, world, port, d, q):
         nccl.ncclCommDestroy.argtypes = [C.c_void_p]
         nccl.ncclCommDestroy(comm)
         mom.close()
+        one.close()
         q.put((rank, bool(ok), ""))
         dist.destroy_process_group()
     except Exception as exc:  # surface the failure in the parent

@@ -4,6 +4,11 @@ the fused kernels that replace them.  Uses the library calls of diffmusic/invers
 oracle and none of the reference's files.
 
     python tools/torch_gpu_yardstick.py [--batch 16] > gpurun_out/torch_gpu_yardstick.json
+
+Two timings per chain: `*_eager_us` (CUDA events around the Python call: includes host dispatch, which dominates the
+torch column) and `*_graph_us` (the same call captured once in a CUDA graph and replayed: DEVICE time of the kernels
+only -- the kernel-vs-kernel comparison SURVEY.md section 0.1 asks for).  Also records the TF32 matmul peak of this GPU
+(8192^3, allow_tf32) next to the bf16 figure of MEASURED_PEAKS.json: the yardstick of any tensor-core DFT experiment.
 """
 import argparse
 import json
@@ -36,6 +41,54 @@ def timed(fn, iters=20):
     return statistics.median(ms) * 1e3  # us
 
 
+def graph_timed(fn, iters=20):
+    """device time of `fn` (us): captured once in a CUDA graph, replayed under CUDA events"""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        keep = fn()  # noqa: F841  (outputs stay alive with the graph)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(iters):
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        g.replay()
+        t.record()
+        torch.cuda.synchronize()
+        ms.append(s.elapsed_time(t))
+    return statistics.median(ms) * 1e3
+
+
+def tf32_peak():
+    n = 8192
+    a, b = torch.randn(n, n, device="cuda"), torch.randn(n, n, device="cuda")
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            a @ b
+            t.record()
+            torch.cuda.synchronize()
+            best = min(best, s.elapsed_time(t))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
@@ -54,7 +107,15 @@ def main():
     rows = []
 
     def add(name, torch_fn, ours_fn):
-        rows.append({"chain": name, "torch_eager_us": timed(torch_fn), "fused_kernels_us": timed(ours_fn)})
+        row = {"chain": name, "torch_eager_us": timed(torch_fn), "fused_kernels_us": timed(ours_fn)}
+        for key, fn in (("torch_graph_us", torch_fn), ("fused_kernels_graph_us", ours_fn)):
+            try:
+                row[key] = graph_timed(fn)
+            except Exception as exc:  # a library call that cannot be captured: keep the eager number
+                import traceback
+                row[key + "_error"] = traceback.format_exc()[-600:]
+                torch.cuda.synchronize()
+        rows.append(row)
 
     nz = dm.get_noiser("gaussian", 0.0)
     # identity operator: loss + gradient in mel space
@@ -96,7 +157,10 @@ def main():
         lambda: dv.fused_loss_and_grad(wav.detach(), meas_dv, "mel_spectrogram"))
     for r in rows:
         r["speedup"] = r["torch_eager_us"] / r["fused_kernels_us"]
+        if "torch_graph_us" in r and "fused_kernels_graph_us" in r:
+            r["device_time_speedup"] = r["torch_graph_us"] / r["fused_kernels_graph_us"]
     print(json.dumps({"what": "reference's torch/torchaudio calls (eager, same GPU) vs the fused kernels", "batch": B,
+                      "tf32_matmul_8192_tflops": tf32_peak(),
                       "clip_samples": L, "note": "whole-batch norm in the torch column (as the reference writes it), "
                       "per-clip norms in ours; both include Python dispatch, no L2 flush", "rows": rows}, indent=1))
 
