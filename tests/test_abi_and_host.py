@@ -159,6 +159,59 @@ def test_ditto_stays_importable_under_the_dropin(tmp_path):
         assert out.strip().endswith("ok")
 
 
+def test_workspace_sizes_and_exchange_payload():
+    """dm_workspace_bytes / dm_fad_packed_doubles are host arithmetic (no device work): the caller-provided buffers of
+    SURVEY.md 8(b) and the payload of the one exchange on the path -- the upper triangle only, 1 + d + d (d + 1) / 2."""
+    from diffmusic_b200 import _lib
+    lib = _lib.load()
+    for d in (1, 128, 768, 1024):
+        assert lib.dm_fad_packed_doubles(d) == 1 + d + d * (d + 1) // 2
+        assert lib.dm_workspace_bytes(3, 0, 0, d) == 8 * (1 + d + d * (d + 1) // 2)      # DM_WS_FAD_PACKED
+        assert lib.dm_workspace_bytes(2, 0, 0, d) == 8 * (1 + d + d * d)                  # DM_WS_FAD_ACC
+    assert lib.dm_workspace_bytes(0, 80000, 16, 0) == 4 * 16 * (80000 + 1024)             # DM_WS_STFT_COTANGENT
+    assert lib.dm_workspace_bytes(1, 80000, 16, 14) == 4 * 16 * 36                        # 501 frames in 14-frame tiles
+    assert lib.dm_workspace_bytes(1, 80000, 16, 14) == 4 * 16 * lib.dm_stft_num_tiles(80000, 160, 14)
+    assert lib.dm_workspace_bytes(4, 0, 0, 0) == 4 * lib.dm_fad_flag_words()
+    assert lib.dm_workspace_bytes(99, 1, 1, 1) == -1 and lib.dm_workspace_bytes(0, 0, 16, 0) == -1
+
+
+def test_warp_kernel_table_image():
+    """tables.warp_image: the host-built shared-memory image of the warp-per-frame-pair STFT kernel -- the pair-row
+    filterbank reproduces the reference's filterbank exactly, every band sits in exactly one lane, and the window starts
+    are bank-conflict free (eight distinct residues mod 8 in every quarter-warp), for both windows."""
+    from diffmusic_b200 import tables
+    fb = tables.mel_filterbank(16000)
+    for win in (tables.hann_window(), tables.rect_window()):
+        img, na, nb = tables.warp_image(win, fb)
+        a = img.numpy()
+        assert a.size % 4 == 0 and a.size == 1024 + 2048 + (na + nb) * 64 + 128 + 1028 + 132
+        assert np.array_equal(a[:1024].reshape(512, 2), np.stack([0.5 * win.numpy()[:512], 0.5 * win.numpy()[512:]], 1))
+        off = 1024 + 2048
+        melp = a[off:off + (na + nb) * 64].reshape(na + nb, 32, 2)
+        lanek = a[off + (na + nb) * 64:off + (na + nb) * 64 + 128].view(np.int32).reshape(4, 32)
+        dense = np.zeros((513, 64), np.float32)
+        for l in range(32):
+            for base, n, p0, m in ((0, na, lanek[0, l], lanek[2, l]), (na, nb, lanek[1, l], lanek[3, l])):
+                for i in range(n):
+                    for h in range(2):
+                        k = 2 * (p0 + i) + h
+                        if k < 513:
+                            assert dense[k, m] == 0 or melp[base + i, l, h] == 0
+                            dense[k, m] += melp[base + i, l, h]
+                        else:
+                            assert melp[base + i, l, h] == 0
+        assert np.array_equal(dense, fb.numpy())
+        assert sorted(lanek[2]) == list(range(32)) and sorted(lanek[3]) == list(range(32, 64))
+        for row in (0, 1):
+            for q in range(4):
+                assert sorted(lanek[row, 8 * q:8 * q + 8] % 8) == list(range(8))
+        tw = a[1024:3072].reshape(16, 32, 4)
+        lane = np.arange(32)
+        for m in (0, 5, 15):
+            ang = -2 * np.pi * lane * (2 * m + 1) / 1024
+            assert np.allclose(tw[m, :, 2], np.cos(ang), atol=1e-7) and np.allclose(tw[m, :, 3], np.sin(ang), atol=1e-7)
+
+
 def test_bench_hooks_the_entry_point_the_operators_call():
     """bench.py times the dominant kernel by wrapping _lib.call for the STFT guidance entry point: the name it matches
     must be the one diffmusic_b200/operators.py actually calls (a silent mismatch leaves roofline.achieved null)."""
