@@ -27,6 +27,8 @@ _SIGNATURES = {
     "dm_last_error": (C.c_char_p, []),
     "dm_launch_count": (C.c_ulonglong, []),
     "dm_reset_launch_count": (None, []),
+    "dm_set_tuning": (c_i, [c_i, c_i]),
+    "dm_get_tuning": (c_i, [c_i]),
     "dm_sched_x0": (c_i, [c_p, c_p, c_p, c_ll, c_f, c_f, c_i, c_f, c_p, c_p]),
     "dm_sched_ddim_update": (c_i, [c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_p, c_p]),
     "dm_sched_dps_update": (c_i, [c_p, c_p, c_p, c_p, c_p, c_ll, c_f, c_f, c_f, c_f, c_f, c_f, c_p, c_p]),
@@ -47,9 +49,12 @@ _SIGNATURES = {
                                            c_f, c_f, c_p, c_i, c_p, c_p, c_p]),
     "dm_stft_guidance_io": (c_i, [C.POINTER(StftTables), c_i, c_i, c_i, c_p, c_i, c_ll, c_ll, c_p, c_i, c_p, c_ll, c_p,
                                   c_f, c_p, c_p, c_p, c_i, c_p]),
+    "dm_stft_guidance_fir2": (c_i, [C.POINTER(StftTables), c_i, c_i, c_p, c_ll, c_ll, c_p, c_i, c_p, c_ll, c_p, c_p,
+                                    c_i, c_p]),
     "dm_residual_wav_io": (c_i, [c_p, c_i, c_ll, c_ll, c_i, c_p, c_p, c_ll, c_p, c_p, c_p]),
     "dm_fold_adjoint_io": (c_i, [c_p, c_i, c_ll, c_i, c_p, c_p, c_i, c_p, c_i, c_ll, c_p, c_p]),
     "dm_resample_fwd_io": (c_i, [c_p, c_i, c_ll, c_ll, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_ll, c_p]),
+    "dm_resample_fwd_fill_io": (c_i, [c_p, c_i, c_ll, c_ll, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_ll, c_p, c_ll, c_p]),
     "dm_resample_adjoint_io": (c_i, [c_p, c_i, c_ll, c_i, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_ll, c_ll,
                                      c_p, c_p]),
     "dm_rir_correlate_io": (c_i, [c_p, c_i, c_ll, c_ll, c_i, c_p, c_i, c_p, c_p, c_p, c_ll, c_p]),

@@ -12,6 +12,7 @@ namespace dm {
 
 extern thread_local char g_err[512];
 extern std::atomic<unsigned long long> g_launches;
+extern int g_tuning[DM_TUNE_COUNT];  // dm_set_tuning
 
 template <typename... A>
 inline int fail(int code, const char* fmt, A... a) {

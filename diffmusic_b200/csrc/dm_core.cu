@@ -6,7 +6,15 @@
 namespace dm {
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+int g_tuning[DM_TUNE_COUNT] = {1};
 }  // namespace dm
+
+extern "C" int dm_set_tuning(int knob, int value) {
+    DM_REQUIRE(knob >= 0 && knob < DM_TUNE_COUNT);
+    dm::g_tuning[knob] = value;
+    return DM_OK;
+}
+extern "C" int dm_get_tuning(int knob) { return (knob >= 0 && knob < DM_TUNE_COUNT) ? dm::g_tuning[knob] : DM_ERR_INVALID; }
 
 extern "C" int dm_version(void) { return 100; }
 extern "C" const char* dm_last_error(void) { return dm::g_err; }

@@ -1,5 +1,7 @@
 // Bandwidth-bound pieces of the guidance path: wav-space residual, reflect-fold + mask adjoint, sinc resampling
 // forward / adjoint, noise add.  All coalesced, per-clip reductions through per-chunk partial slots (deterministic).
+#include <algorithm>
+
 #include "dm_common.cuh"
 #include "fir_poly.cuh"
 
@@ -33,12 +35,59 @@ __global__ void __launch_bounds__(kEwThreads) residual_wav_kernel(const void* __
     const float* mb = meas + (long long)b * meas_bstride;
     float* ob = ybar + (long long)b * n;
     float s = 0.f;
-    for (long long i = lo + threadIdx.x; i < hi; i += kEwThreads) {
-        float v = ld_wave(yb, y_io, i);
-        if (mask) v *= __ldg(mask + i);
-        float d = mb[i] - v;
-        ob[i] = -d;
-        s = fmaf(d, d, s);
+    // full chunks of aligned rows: four vectors of 4 samples per thread (128-bit fp32 / 64-bit fp16, bf16 loads), all
+    // loads issued before the first use; the same summation order for every waveform dtype
+    const bool fast = hi - lo == DM_RESID_CHUNK && ((n | y_bstride | meas_bstride) & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y) & (y_io == DM_IO_F32 ? 15 : 7)) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(meas) | reinterpret_cast<uintptr_t>(ybar) |
+                        reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
+    if (fast) {
+        constexpr int kV = DM_RESID_CHUNK / 4 / kEwThreads;  // 4
+        const float4* m4 = reinterpret_cast<const float4*>(mb + lo);
+        const float4* k4 = mask ? reinterpret_cast<const float4*>(mask + lo) : nullptr;
+        float4* o4 = reinterpret_cast<float4*>(ob + lo);
+        float4 v[kV], m[kV], k[kV];
+        if (y_io == DM_IO_F32) {
+            const float4* y4 = reinterpret_cast<const float4*>(static_cast<const float*>(yb) + lo);
+#pragma unroll
+            for (int u = 0; u < kV; ++u) v[u] = y4[threadIdx.x + u * kEwThreads];
+        } else {
+            const uint2* y2 = reinterpret_cast<const uint2*>(static_cast<const unsigned short*>(yb) + lo);
+#pragma unroll
+            for (int u = 0; u < kV; ++u) {
+                const uint2 raw = y2[threadIdx.x + u * kEwThreads];
+                float2 a, c;
+                if (y_io == DM_IO_F16) {
+                    a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+                    c = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+                } else {
+                    a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+                    c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+                }
+                v[u] = make_float4(a.x, a.y, c.x, c.y);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kV; ++u) {
+            m[u] = m4[threadIdx.x + u * kEwThreads];
+            k[u] = k4 ? __ldg(k4 + threadIdx.x + u * kEwThreads) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kV; ++u) {
+            float4 d;
+            if (k4) v[u].x *= k[u].x, v[u].y *= k[u].y, v[u].z *= k[u].z, v[u].w *= k[u].w;
+            d.x = m[u].x - v[u].x, d.y = m[u].y - v[u].y, d.z = m[u].z - v[u].z, d.w = m[u].w - v[u].w;
+            o4[threadIdx.x + u * kEwThreads] = make_float4(-d.x, -d.y, -d.z, -d.w);
+            s = fmaf(d.x, d.x, s), s = fmaf(d.y, d.y, s), s = fmaf(d.z, d.z, s), s = fmaf(d.w, d.w, s);
+        }
+    } else {
+        for (long long i = lo + threadIdx.x; i < hi; i += kEwThreads) {
+            float v = ld_wave(yb, y_io, i);
+            if (mask) v *= __ldg(mask + i);
+            float d = mb[i] - v;
+            ob[i] = -d;
+            s = fmaf(d, d, s);
+        }
     }
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -396,6 +445,205 @@ __global__ void __launch_bounds__(kEwThreads) resample2_adjoint_reg_kernel(
     }
 }
 
+// ---- persistent ("stream") variants for the shipped shapes.  The kernels above spend one CTA on 2048 samples: at 16
+// clips that is a thousand CTAs living one or two dependent memory latencies each (the adjoints first reduce the clip's
+// loss), and the forward window loads (lane stride 64 B) cost 16 L1 wavefronts per 128-bit load.  Here a fixed grid
+// walks the work: every CTA owns a contiguous range of windows, reduces the scales of the (one or two) clips it touches
+// once, keeps two windows in flight per thread and stores a full 32-byte sector per lane (st.global.v8); the forward
+// stages its input span with cp.async into a swizzled shared-memory buffer (double buffered) from which the same
+// window reads are bank-conflict free.  Arithmetic is unchanged (bit-identical).  [Measured and dropped: the same
+// treatment of fold_adjoint_kernel (slower: it is already a plain two-vector stream).]
+constexpr int kStreamMaxClips = 1024;
+
+// s_scale[b - b_lo] = 1 / loss_b (0 at 0) for the clips b_lo..b_hi a CTA works on, one warp per clip, loss_b exactly as
+// clip_loss() computes it; the CTA that owns a clip's first item publishes its loss
+__device__ __forceinline__ void clip_scales_smem(const float* __restrict__ partial, int ntiles, int b_lo, int b_hi,
+                                                 int b_pub_lo, float* __restrict__ loss, float* __restrict__ s_scale) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b = b_lo + warp; b <= b_hi; b += kEwThreads / 32) {
+        const float* pb = partial + (long long)b * ntiles;
+        double acc = 0.0;
+        for (int i = lane; i < ntiles; i += 32) acc += (double)pb[i];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float l = sqrtf((float)acc);
+            s_scale[b - b_lo] = inv_loss(l);
+            if (b >= b_pub_lo && loss) loss[b] = l;
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void st_global_256(float* p, const float (&o)[8]) {  // one full 32-byte sector per lane
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+                 "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                 : "memory");
+}
+
+struct Rs2AdjWin {
+    float win[kFir2AdjWin];
+    int b, i0;
+};
+template <int IO>
+__device__ __forceinline__ void rs2_adj_load(Rs2AdjWin& w, int item, int nwin_clip, const float* __restrict__ ybar,
+                                             int pad, long long Ly) {
+    w.b = item / nwin_clip;
+    w.i0 = (item - w.b * nwin_clip) * kFir2Out;
+    const float* yb = ybar + (long long)w.b * (Ly + 2 * pad);
+    const long long m0 = w.i0 / 2 - 8;
+    const bool plain = pad ? (m0 >= 513 && m0 + kFir2AdjWin <= Ly - 513) : (m0 >= 0 && m0 + kFir2AdjWin <= Ly);
+    if (plain) {
+        const float4* src = reinterpret_cast<const float4*>(yb + pad + m0);
+#pragma unroll
+        for (int q = 0; q < kFir2AdjWin / 4; ++q) {
+            const float4 t = src[q];
+            w.win[4 * q] = t.x, w.win[4 * q + 1] = t.y, w.win[4 * q + 2] = t.z, w.win[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int n = 0; n < kFir2AdjWin; ++n) {
+            const long long j = m0 + n;
+            w.win[n] = (j >= 0 && j < Ly) ? ybar_at(yb, pad, j, Ly) : 0.f;
+        }
+    }
+}
+template <int IO>
+__device__ __forceinline__ void rs2_adj_finish(const Rs2AdjWin& w, const float (&h)[kFir2Taps],
+                                               const float* __restrict__ s_scale, int b_lo, void* __restrict__ dwav,
+                                               long long dwav_bstride, long long L) {
+    float out[kFir2Out];
+    fir2_adj8(w.win, h, out);
+    const float sc = s_scale[w.b - b_lo];
+    void* ob = wave_row(dwav, IO, (long long)w.b * dwav_bstride + w.i0);
+#pragma unroll
+    for (int c = 0; c < kFir2Out; ++c) out[c] *= sc;
+    if (w.i0 + kFir2Out <= L) {
+        if (IO == DM_IO_F32) {
+            if ((reinterpret_cast<uintptr_t>(ob) & 31) == 0) {
+                st_global_256(static_cast<float*>(ob), out);
+            } else {
+                reinterpret_cast<float4*>(ob)[0] = make_float4(out[0], out[1], out[2], out[3]);
+                reinterpret_cast<float4*>(ob)[1] = make_float4(out[4], out[5], out[6], out[7]);
+            }
+        } else {
+            *reinterpret_cast<uint4*>(ob) = pack8<IO>(out);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < kFir2Out; ++c)
+            if (w.i0 + c < L) st_wave(ob, IO, c, out[c]);
+    }
+}
+template <int IO>
+__global__ void __launch_bounds__(kEwThreads) resample2_adjoint_stream_kernel(
+    const float* __restrict__ ybar, int pad, long long Ly, int B, const float* __restrict__ partial, int ntiles,
+    const float* __restrict__ kernel, void* __restrict__ dwav, long long dwav_bstride, long long L,
+    float* __restrict__ loss) {
+    __shared__ float s_scale[kStreamMaxClips];
+    const int nwin_clip = (int)((L + kFir2Out - 1) / kFir2Out), total = nwin_clip * B;  // host: total < 2^30
+    const int per_cta = ((total + gridDim.x - 1) / gridDim.x + kEwThreads - 1) / kEwThreads * kEwThreads;  // as the host
+    const int start = blockIdx.x * per_cta, end = min(total, start + per_cta);
+    if (start >= end) return;
+    const int b_lo = start / nwin_clip, b_hi = (end - 1) / nwin_clip;
+    int item = start + threadIdx.x;
+    Rs2AdjWin w0, w1;
+    if (item < end) rs2_adj_load<IO>(w0, item, nwin_clip, ybar, pad, Ly);  // in flight behind the scale reduction
+    float h[kFir2Taps];
+    load_taps28(kernel, h);
+    clip_scales_smem(partial, ntiles, b_lo, b_hi, (start + nwin_clip - 1) / nwin_clip, loss, s_scale);
+    for (; item < end; item += 2 * kEwThreads) {
+        const int item1 = item + kEwThreads;
+        if (item1 < end) rs2_adj_load<IO>(w1, item1, nwin_clip, ybar, pad, Ly);
+        rs2_adj_finish<IO>(w0, h, s_scale, b_lo, dwav, dwav_bstride, L);
+        const int item2 = item1 + kEwThreads;
+        if (item2 < end) rs2_adj_load<IO>(w0, item2, nwin_clip, ybar, pad, Ly);
+        if (item1 < end) rs2_adj_finish<IO>(w1, h, s_scale, b_lo, dwav, dwav_bstride, L);
+    }
+}
+
+// forward: cp.async staging of the chunk's input span, swizzled so that the window reads (lane stride 64 B) are
+// conflict-free: 16-byte cell c sits at (c & ~7) | ((c & 7) ^ ((c >> 3) & 3)).  [Per quarter-warp the cells 4 i + q of 8
+// consecutive lanes fall into two columns a, a ^ 4 of four consecutive 128-byte rows each; xor-ing the column with
+// row & 3 spreads each set over a ^ {0..3} resp. a ^ 4 ^ {0..3}: eight different bank groups.]
+constexpr int kRs2ChunkOut = 1024;                     // outputs per chunk = 8 per thread of a 128-thread CTA
+constexpr int kRs2Threads = kRs2ChunkOut / kFir2Out;   // 128
+constexpr int kRs2Cells = (2 * kRs2ChunkOut + 32) / 4 + 0;  // 520 cells of 4 floats: x[2 j0 - 16 .. 2 j0 + 2048 + 16)
+constexpr int kRs2BufFloats = ((kRs2Cells + 7) / 8) * 8 * 4;
+__device__ __forceinline__ int rs2_cell(int c) { return (c & ~7) | ((c & 7) ^ ((c >> 3) & 3)); }
+__device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__global__ void __launch_bounds__(kRs2Threads) resample2_fwd_stream_kernel(const float* __restrict__ x,
+                                                                           long long x_bstride, long long L, int B,
+                                                                           const float* __restrict__ kernel,
+                                                                           float* __restrict__ y, long long Ly,
+                                                                           float4* __restrict__ fill,
+                                                                           long long fill_n4) {
+    __shared__ __align__(16) float buf[2][kRs2BufFloats];
+    const int t = threadIdx.x;
+    // optional: zero a side buffer on the way (the cotangent buffer the STFT kernel accumulates into next: saves the
+    // fill launch of the chain).  Stores only, issued before anything else.
+    for (long long i = (long long)blockIdx.x * kRs2Threads + t; i < fill_n4; i += (long long)gridDim.x * kRs2Threads)
+        fill[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int chunks_clip = (int)((Ly + kRs2ChunkOut - 1) / kRs2ChunkOut);
+    const long long total = (long long)chunks_clip * B;
+    auto stage = [&](long long item, float* dst) {
+        const int b = (int)(item / chunks_clip);
+        const long long j0c = (item - (long long)b * chunks_clip) * kRs2ChunkOut;
+        const float* xb = x + (long long)b * x_bstride;
+        const long long x0 = 2 * j0c - 16;  // a multiple of 4 floats
+        for (int c = t; c < kRs2Cells; c += kRs2Threads) {
+            const long long g = x0 + 4 * c;
+            int nbytes = 0;
+            if (g >= 0 && g < L) nbytes = (int)min((long long)16, (L - g) * 4);
+            cp_async16_zfill(dst + 4 * rs2_cell(c), nbytes ? xb + g : xb, nbytes);  // zero-fills what lies outside [0, L)
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float h[kFir2Taps];
+    load_taps28(kernel, h);
+    long long item = blockIdx.x;
+    if (item < total) stage(item, buf[0]);
+    int cur = 0;
+    for (; item < total; item += gridDim.x, cur ^= 1) {
+        const long long next = item + gridDim.x;
+        if (next < total) {
+            stage(next, buf[cur ^ 1]);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int b = (int)(item / chunks_clip);
+        const long long j0 = (item - (long long)b * chunks_clip) * kRs2ChunkOut + (long long)t * kFir2Out;
+        if (j0 < Ly) {
+            float win[kFir2FwdWin], out[kFir2Out];
+            const float4* cells = reinterpret_cast<const float4*>(buf[cur]);
+#pragma unroll
+            for (int q = 0; q < kFir2FwdWin / 4; ++q) {
+                const float4 v = cells[rs2_cell(4 * t + q)];
+                win[4 * q] = v.x, win[4 * q + 1] = v.y, win[4 * q + 2] = v.z, win[4 * q + 3] = v.w;
+            }
+            fir2_fwd8(win, h, out);
+            float* yb = y + (long long)b * Ly + j0;
+            if (j0 + kFir2Out <= Ly) {
+                if ((reinterpret_cast<uintptr_t>(yb) & 31) == 0) {
+                    st_global_256(yb, out);
+                } else {
+                    reinterpret_cast<float4*>(yb)[0] = make_float4(out[0], out[1], out[2], out[3]);
+                    reinterpret_cast<float4*>(yb)[1] = make_float4(out[4], out[5], out[6], out[7]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < kFir2Out; ++c)
+                    if (j0 + c < Ly) yb[c] = out[c];
+            }
+        }
+        __syncthreads();  // the buffer is free for the chunk after next
+    }
+}
+
 // ---- pure streaming kernels: 128-bit accesses (two float4 in flight per thread and iteration) with a scalar tail;
 // the scalar path also takes rows / pointers that are not 16-byte aligned
 __device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -498,7 +746,18 @@ extern "C" int dm_fold_adjoint_io(const float* ybar, int pad, long long Ly, int 
 
 template <int IO>
 static void launch_rs2_fwd(const void* x, long long x_bstride, long long L, int B, const float* kernel, float* y,
-                           long long Ly, cudaStream_t st) {
+                           long long Ly, cudaStream_t st, float* fill = nullptr, long long fill_n = 0) {
+    const long long chunks = ((Ly + kRs2ChunkOut - 1) / kRs2ChunkOut) * B;
+    if (IO == DM_IO_F32 && g_tuning[DM_TUNE_STREAM_KERNELS] && chunks < 0x7fffffffLL) {
+        const int grid = (int)std::min<long long>(chunks, (long long)num_sms() * 12);
+        const bool fuse_fill = fill != nullptr && (fill_n & 3) == 0 && (reinterpret_cast<uintptr_t>(fill) & 15) == 0;
+        if (fill != nullptr && !fuse_fill) cudaMemsetAsync(fill, 0, (size_t)fill_n * sizeof(float), st);
+        resample2_fwd_stream_kernel<<<grid, kRs2Threads, 0, st>>>(static_cast<const float*>(x), x_bstride, L, B, kernel,
+                                                                  y, Ly, reinterpret_cast<float4*>(fill),
+                                                                  fuse_fill ? fill_n / 4 : 0);
+        return;
+    }
+    if (fill != nullptr) cudaMemsetAsync(fill, 0, (size_t)fill_n * sizeof(float), st);
     const long long nthr = (Ly + kFir2Out - 1) / kFir2Out;
     resample2_fwd_reg_kernel<IO><<<dim3((unsigned)((nthr + kEwThreads - 1) / kEwThreads), B), kEwThreads, 0, st>>>(
         x, x_bstride, L, kernel, y, Ly);
@@ -507,6 +766,16 @@ template <int IO>
 static void launch_rs2_adj(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
                            const float* kernel, void* dwav, long long dwav_bstride, long long L, float* loss,
                            cudaStream_t st) {
+    const long long nwin = ((L + kFir2Out - 1) / kFir2Out) * B;
+    if (g_tuning[DM_TUNE_STREAM_KERNELS] && B <= kStreamMaxClips && nwin < (1LL << 30)) {
+        // one resident wave (4 CTAs of 64 registers per SM), every CTA a whole number of 256-window rounds
+        long long per_cta = (nwin + (long long)num_sms() * 4 - 1) / ((long long)num_sms() * 4);
+        per_cta = std::max<long long>(2, (per_cta + kEwThreads - 1) / kEwThreads) * kEwThreads;
+        const int grid = (int)((nwin + per_cta - 1) / per_cta);
+        resample2_adjoint_stream_kernel<IO><<<grid, kEwThreads, 0, st>>>(ybar, pad, Ly, B, partial, ntiles, kernel, dwav,
+                                                                         dwav_bstride, L, loss);
+        return;
+    }
     const long long nthr = (L + kFir2Out - 1) / kFir2Out;
     resample2_adjoint_reg_kernel<IO><<<dim3((unsigned)((nthr + kEwThreads - 1) / kEwThreads), B), kEwThreads, 0, st>>>(
         ybar, pad, Ly, partial, ntiles, kernel, dwav, dwav_bstride, L, loss);
@@ -524,15 +793,20 @@ static bool rs2_fwd_ok(const void* x, long long x_bstride, const float* y, long 
            (reinterpret_cast<uintptr_t>(y) & 15) == 0;
 }
 static int resample_fwd_core(const void* x, int x_io, long long x_bstride, long long L, int B, const float* kernel,
-                             int n_new, int taps, int orig, int width, float* y, long long Ly, cudaStream_t st) {
+                             int n_new, int taps, int orig, int width, float* y, long long Ly, cudaStream_t st,
+                             float* fill = nullptr, long long fill_n = 0) {
     DM_REQUIRE(x && kernel && y && L > 0 && B > 0 && Ly > 0 && io_dtype_ok(x_io));
     DM_REQUIRE(n_new >= 1 && taps >= 1 && orig >= 1 && width >= 0);
+    DM_REQUIRE(fill == nullptr || fill_n > 0);
     if (rs2_filter(n_new, orig, taps, width, kernel)) {  // scale 2: register-window kernel
         if (x_io == DM_IO_F32 && rs2_fwd_ok<DM_IO_F32>(x, x_bstride, y, Ly)) {
-            launch_rs2_fwd<DM_IO_F32>(x, x_bstride, L, B, kernel, y, Ly, st);
+            launch_rs2_fwd<DM_IO_F32>(x, x_bstride, L, B, kernel, y, Ly, st, fill, fill_n);
             DM_LAUNCHED();
             return DM_OK;
         }
+    }
+    if (fill != nullptr) DM_CUDA(cudaMemsetAsync(fill, 0, (size_t)fill_n * sizeof(float), st));  // every other path
+    if (rs2_filter(n_new, orig, taps, width, kernel)) {
         if (x_io != DM_IO_F32 && rs2_fwd_ok<DM_IO_F16>(x, x_bstride, y, Ly)) {
             if (x_io == DM_IO_F16) launch_rs2_fwd<DM_IO_F16>(x, x_bstride, L, B, kernel, y, Ly, st);
             else launch_rs2_fwd<DM_IO_BF16>(x, x_bstride, L, B, kernel, y, Ly, st);
@@ -627,6 +901,12 @@ extern "C" int dm_resample_fwd_io(const void* x, int x_dtype, long long x_bstrid
                                   const float* kernel, int n_new, int taps, int orig, int width, float* y, long long Ly,
                                   dm_stream_t stream) {
     return resample_fwd_core(x, x_dtype, x_bstride, L, B, kernel, n_new, taps, orig, width, y, Ly, as_stream(stream));
+}
+extern "C" int dm_resample_fwd_fill_io(const void* x, int x_dtype, long long x_bstride, long long L, int B,
+                                       const float* kernel, int n_new, int taps, int orig, int width, float* y,
+                                       long long Ly, float* fill, long long fill_count, dm_stream_t stream) {
+    return resample_fwd_core(x, x_dtype, x_bstride, L, B, kernel, n_new, taps, orig, width, y, Ly, as_stream(stream),
+                             fill, fill_count);
 }
 extern "C" int dm_resample_fwd(const float* x, long long x_bstride, long long L, int B, const float* kernel,
                                int n_new, int taps, int orig, int width, float* y, long long Ly,

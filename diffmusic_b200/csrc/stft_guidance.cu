@@ -563,6 +563,44 @@ extern "C" int dm_stft_guidance_io(const dm_stft_tables* tab, int mode, int clam
     return DM_OK;
 }
 
+extern "C" int dm_stft_guidance_fir2(const dm_stft_tables* tab, int clamp, int hop, const float* x,
+                                     long long x_bstride, long long L, const float* taps, int B, const float* ref,
+                                     long long ref_bstride, float* ypbar, float* partial, int frames_per_tile,
+                                     dm_stream_t stream) {
+    DM_REQUIRE(tab != nullptr && x != nullptr && taps != nullptr && ref != nullptr && partial != nullptr);
+    DM_REQUIRE(tab->warp_image != nullptr && hop == 160);
+    DM_REQUIRE(B > 0 && L > kNfft);  // Ly = ceil(L / 2) > 512: reflect padding needs pad < length
+    DM_REQUIRE(frames_per_tile >= 1 && frames_per_tile <= 14);
+    DM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bstride & 3) == 0);
+    StftParams p;
+    p.tab = StftTables{tab->window, reinterpret_cast<const cf*>(tab->tw512), reinterpret_cast<const cf*>(tab->w1024),
+                       tab->mel_kstart, tab->mel_klen, tab->mel_w, tab->mel_wstride, tab->bin_m0, tab->bin_w0,
+                       tab->bin_w1, tab->warp_image, tab->warp_image_floats, tab->warp_na, tab->warp_nb};
+    p.clamp = clamp;
+    p.hop = hop;
+    p.B = B;
+    p.nf = frames_per_tile;
+    p.Ly = (L + 1) / 2;
+    p.T = 1 + p.Ly / hop;
+    p.ntiles = (int)((p.T + p.nf - 1) / p.nf);
+    p.y_bstride = 0;
+    p.ref_bstride = ref_bstride;
+    p.y = nullptr;
+    p.y_io = DM_IO_F32;
+    p.mask = nullptr;
+    p.ref = ref;
+    p.noise = nullptr;
+    p.sigma = 0.f;
+    p.out = nullptr;
+    p.ypbar = ypbar;
+    p.partial = partial;
+    p.fir_x = x;
+    p.fir_x_bstride = x_bstride;
+    p.fir_L = L;
+    for (int k = 0; k < 28; ++k) p.fir_h[k] = taps[k];  // HOST array
+    return launch_stft_warp(p, DM_STFT_MEL_DB, as_stream(stream));
+}
+
 extern "C" int dm_mel_project(const dm_stft_tables* tab, const float* mag, int B, long long T, int clamp, float* out,
                               dm_stream_t stream) {
     DM_REQUIRE(tab && mag && out && B > 0 && T > 0);

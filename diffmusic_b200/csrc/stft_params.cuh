@@ -18,6 +18,11 @@ struct StftParams {
     float* out;
     float* ypbar;
     float* partial;
+    // fused scale-2 super-resolution chain (dm_stft_guidance_fir2, warp engine only): the signal of the tiles is
+    // y = sinc-resample(x) computed inside the kernel from fir_x (B, fir_L) fp32 rows; `y` is NULL then
+    const float* fir_x = nullptr;
+    long long fir_x_bstride = 0, fir_L = 0;
+    float fir_h[28] = {};  // the filter taps BY VALUE: FFMA reads them straight from the constant bank, no registers
 };
 
 // ---- TMA bulk copy (cp.async.bulk) of an interior tile's contiguous signal span into shared memory ----

@@ -14,6 +14,7 @@
 //     result to the padded cotangent in HBM (tiles overlap by < 1 frame -> <= 2 commutative adds per address).
 // Same inputs / outputs / arithmetic as stft_pair_kernel (stft_guidance.cu), which stays as the engine for hops that
 // are not a multiple of 4 and tiles of more than 16 frames, and as the A/B reference of the tests.
+#include "fir_poly.cuh"
 #include "stft_params.cuh"
 #include "stft_warp.cuh"
 
@@ -58,10 +59,10 @@ __device__ __forceinline__ TileGeom tile_geom(const StftParams& p, int item, int
     g.nfr = (int)min((long long)p.nf, p.T - g.f0);
     g.span = (g.nfr - 1) * hop + kNfft;
     g.base = g.f0 * hop;  // first padded-signal index of the tile
-    g.yb = wave_row(p.y, p.y_io, (long long)g.b * p.y_bstride);
+    g.yb = p.y ? wave_row(p.y, p.y_io, (long long)g.b * p.y_bstride) : nullptr;
     g.span_src = static_cast<const float*>(g.yb) + (g.base - kNfft / 2);
     // fp32 interior tiles without a mask: one TMA bulk copy; everything else is converted / mirrored / masked per sample
-    g.interior = p.y_io == DM_IO_F32 && p.mask == nullptr && g.base >= kNfft / 2 &&
+    g.interior = p.fir_x == nullptr && p.y_io == DM_IO_F32 && p.mask == nullptr && g.base >= kNfft / 2 &&
                  g.base - kNfft / 2 + g.span <= p.Ly && (reinterpret_cast<uintptr_t>(g.span_src) & 15) == 0;
     return g;
 }
@@ -94,9 +95,92 @@ __device__ __forceinline__ void stage_generic(const StftParams& p, const TileGeo
     }
 }
 
+
+// ---- fused scale-2 super-resolution chain (dm_stft_guidance_fir2): the tile's signal span is the sinc-resampled
+// waveform y[j] = sum_k xz[2 j + k - 13] h[k] (torchaudio Resample 2 -> 1, 28 taps: operator.py:180,203-205), computed
+// from x straight into the span buffer with the register-window body of resample2_fwd_reg_kernel (same arithmetic, so
+// the span is bit-identical to the resampled signal the unfused chain reads back from HBM).  The span is covered in
+// windows of 8 outputs: the first tile of a CTA by all threads; every following tile while the current one is being
+// transformed -- the warp that owns no frame pair takes all windows but 32 per transforming warp, which those add as ONE
+// round after their inverse transform (a single warp would need 13 dependent load round trips per tile and become the
+// critical path: measured 44 us against 33.5 us).  Positions in the reflect padding are mirrored inside the span afterwards.
+__device__ __forceinline__ float fir2_at(const float* __restrict__ xb, long long L, const float (&h)[kFir2Taps],
+                                         long long j) {  // h: the by-value taps of the kernel parameters
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < kFir2Taps; ++k) {
+        const long long n = 2 * j + k - kFir2Width;
+        a = fmaf((n >= 0 && n < L) ? __ldg(xb + n) : 0.f, h[k], a);
+    }
+    return a;
+}
+struct Fir2Span {
+    const float* xb;
+    long long jb, jlo, jhi;  // signal index of span position 0 (a multiple of 32); the in-range part [jlo, jhi) of the span
+    int nwin;                // windows of 8 outputs covering [jlo, jhi)
+    bool mirrored;           // the span reaches into the reflect padding
+};
+__device__ __forceinline__ Fir2Span fir2_span(const StftParams& p, const TileGeom& g) {
+    Fir2Span f;
+    f.xb = p.fir_x + (long long)g.b * p.fir_x_bstride;
+    f.jb = g.base - kNfft / 2;
+    f.jlo = f.jb < 0 ? 0 : f.jb;  // a multiple of 8
+    f.jhi = min(p.Ly, f.jb + g.span);
+    f.nwin = (int)((f.jhi - f.jlo + kFir2Out - 1) / kFir2Out);
+    f.mirrored = f.jb < 0 || f.jb + g.span > p.Ly;
+    return f;
+}
+// windows wi = first, first + stride, ... < last of the span (8 outputs each, all loads of a window issued up front)
+__device__ __forceinline__ void fir2_windows(const StftParams& p, const Fir2Span& f, float* __restrict__ sig, int first,
+                                             int last, int stride) {
+    const long long L = p.fir_L;
+    const float(&h)[kFir2Taps] = p.fir_h;  // uniform / constant-bank operands of the FFMAs
+    for (int wi = first; wi < last; wi += stride) {
+        const long long j0 = f.jlo + (long long)wi * kFir2Out;
+        const long long x0 = 2 * j0 - 16;
+        float win[kFir2FwdWin], out[kFir2Out];
+        if (x0 >= 0 && x0 + kFir2FwdWin <= L) {
+            const float4* src = reinterpret_cast<const float4*>(f.xb + x0);
+#pragma unroll
+            for (int q = 0; q < kFir2FwdWin / 4; ++q) {
+                const float4 v = __ldg(src + q);
+                win[4 * q] = v.x, win[4 * q + 1] = v.y, win[4 * q + 2] = v.z, win[4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < kFir2FwdWin; ++n) {
+                const long long i = x0 + n;
+                win[n] = (i >= 0 && i < L) ? __ldg(f.xb + i) : 0.f;
+            }
+        }
+        fir2_fwd8(win, h, out);
+        float* dst = sig + (j0 - f.jb);
+        if (j0 + kFir2Out <= f.jhi) {
+            reinterpret_cast<float4*>(dst)[0] = make_float4(out[0], out[1], out[2], out[3]);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(out[4], out[5], out[6], out[7]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < kFir2Out; ++c)
+                if (j0 + c < f.jhi) dst[c] = out[c];
+        }
+    }
+}
+// positions of the span inside the reflect padding, after every in-range sample is in place (a barrier in between)
+__device__ __forceinline__ void fir2_mirror(const StftParams& p, const TileGeom& g, const Fir2Span& f,
+                                            float* __restrict__ sig, int t, int nt) {
+    for (int i = t; i < g.span; i += nt) {
+        const long long j = f.jb + i;
+        if (j >= 0 && j < p.Ly) continue;
+        const long long jr = reflect_src(g.base + i, p.Ly);  // mirrored source, inside the signal
+        sig[i] = (jr >= f.jlo && jr < f.jhi) ? sig[jr - f.jb] : fir2_at(f.xb, p.fir_L, p.fir_h, jr);
+    }
+}
+
 // HOP: compile-time hop (160 in every shipped configuration) or 0 = read it from the parameters
 // WARPS: warps per CTA (every warp owns one frame pair of the tile, so tiles hold <= 2 * WARPS frames)
-template <int MODE, int HOP, int WARPS>
+// FIR: fused scale-2 resampling (see fir2_stage_tile): tiles hold <= 2 * (WARPS - 1) frames and the last warp, which owns
+//      no frame pair, computes the NEXT tile's span behind the transforms of the current one
+template <int MODE, int HOP, int WARPS, bool FIR>
 __global__ void __launch_bounds__(32 * WARPS, 2) stft_warp_kernel(const StftParams p, int total_tiles) {
     constexpr int kWarpCtaThreads = 32 * WARPS;
     extern __shared__ __align__(16) float smem[];
@@ -132,7 +216,16 @@ __global__ void __launch_bounds__(32 * WARPS, 2) stft_warp_kernel(const StftPara
         bulk_load_span(img, p.tab.warp_image, (uint32_t)p.tab.warp_image_floats * 4u, &bar_img);
         if (g.interior) stage_async(g, sig, &bar_sig);
     }
-    if (!g.interior) stage_generic<kWarpCtaThreads>(p, g, sig, tid);
+    if (FIR) {
+        const Fir2Span f = fir2_span(p, g);
+        fir2_windows(p, f, sig, tid, f.nwin, kWarpCtaThreads);
+        if (f.mirrored) {  // uniform per tile
+            __syncthreads();
+            fir2_mirror(p, g, f, sig, tid, kWarpCtaThreads);
+        }
+    } else if (!g.interior) {
+        stage_generic<kWarpCtaThreads>(p, g, sig, tid);
+    }
     __syncthreads();  // barrier initialisation and a generically staged span are visible
     mbar_wait_parity(&bar_img, 0);
     const int pa0 = lanek[lane], pb0 = lanek[32 + lane], ma = lanek[64 + lane], mb = lanek[96 + lane];
@@ -148,7 +241,8 @@ __global__ void __launch_bounds__(32 * WARPS, 2) stft_warp_kernel(const StftPara
         // ---- transform phase: warp w owns frames 2w, 2w + 1 of the tile ----
         float lsum = 0.f;
         const int fa = 2 * w;
-        const bool active = fa < nfr;
+        const bool producer = FIR && w == WARPS - 1;  // owns no frames (the host keeps tiles <= 2 (WARPS - 1) frames)
+        const bool active = fa < nfr && !producer;
         const bool active_b = fa + 1 < nfr;  // otherwise frame B recomputes frame A and its results are dropped
         const int fb = active_b ? fa + 1 : fa;
         const int ta = f0 + fa, tb = f0 + fb;
@@ -157,7 +251,7 @@ __global__ void __launch_bounds__(32 * WARPS, 2) stft_warp_kernel(const StftPara
         if (active) warp_load_frames(lane, sig + fa * hop, sig + fb * hop, win2, v, ssa, ssb);
         __syncthreads();  // every warp holds its frames in registers: the span is dead
         const int next = item + gridDim.x;
-        if (next < total_tiles && tid == 0) {
+        if (!FIR && next < total_tiles && tid == 0) {
             const TileGeom gn = tile_geom(p, next, hop);
             if (gn.interior) stage_async(gn, sig, &bar_sig);  // lands behind this tile's transforms
         }
@@ -300,11 +394,21 @@ __global__ void __launch_bounds__(32 * WARPS, 2) stft_warp_kernel(const StftPara
                 warp_store_gradients(lane, v, win2, wbuf);
             }
         }
+        if (FIR && next < total_tiles) {  // this warp's share of the NEXT tile's span (the current one is dead)
+            const Fir2Span f = fir2_span(p, tile_geom(p, next, hop));
+            if (producer) fir2_windows(p, f, sig, 32 * (WARPS - 1) + lane, f.nwin, 32);
+            else fir2_windows(p, f, sig, 32 * w + lane, min(f.nwin, 32 * w + 32), 32);
+        }
         if (p.partial) {
             lsum = warp_sum(lsum);
             if (lane == 0) red[w] = lsum;
         }
         __syncthreads();
+        if (FIR && next < total_tiles) {
+            const TileGeom gn = tile_geom(p, next, hop);
+            const Fir2Span f = fir2_span(p, gn);
+            if (f.mirrored) fir2_mirror(p, gn, f, sig, tid, kWarpCtaThreads);  // visible after the barrier below
+        }
 
         // ---- gathered overlap-add of the tile's frame gradients, straight to HBM ----
         if (want_grad) {
@@ -350,7 +454,7 @@ __global__ void __launch_bounds__(32 * WARPS, 2) stft_warp_kernel(const StftPara
         }
         if (next < total_tiles) {
             g = tile_geom(p, next, hop);
-            if (!g.interior) stage_generic<kWarpCtaThreads>(p, g, sig, tid);  // the span has been dead since the barrier above
+            if (!FIR && !g.interior) stage_generic<kWarpCtaThreads>(p, g, sig, tid);  // the span has been dead since the barrier above
         }
         __syncthreads();  // warp buffers and `red` are free, a generically staged span is visible
     }
@@ -370,16 +474,24 @@ int launch_stft_warp(const StftParams& p, int mode, cudaStream_t st) {
     const int grid = (int)min(total, (long long)2 * num_sms());
 #define DM_LAUNCH_WARP(M, H, W)                                                                   \
     do {                                                                                          \
-        DM_SMEM_ONCE((stft_warp_kernel<M, H, W>), smem);                                          \
-        DM_CARVEOUT_ONCE((stft_warp_kernel<M, H, W>));                                            \
-        stft_warp_kernel<M, H, W><<<grid, 32 * W, smem, st>>>(p, (int)total);                     \
+        DM_SMEM_ONCE((stft_warp_kernel<M, H, W, false>), smem);                                   \
+        DM_CARVEOUT_ONCE((stft_warp_kernel<M, H, W, false>));                                     \
+        stft_warp_kernel<M, H, W, false><<<grid, 32 * W, smem, st>>>(p, (int)total);              \
     } while (0)
 #define DM_LAUNCH_WARP_HOP(M)                                        \
     do {                                                             \
         if (p.hop == 160) DM_LAUNCH_WARP(M, 160, kWarpsPerCta);      \
         else DM_LAUNCH_WARP(M, 0, kWarpsPerCta);                     \
     } while (0)
-    if (mode == DM_STFT_MEL_DB) DM_LAUNCH_WARP_HOP(kModeMelDb);
+    if (p.fir_x != nullptr) {  // fused scale-2 resampling: mel-dB guidance with hop 160 only (the shipped chain)
+        if (mode != DM_STFT_MEL_DB || p.hop != 160 || p.nf > 2 * (kWarpsPerCta - 1) || p.ref == nullptr ||
+            p.mask != nullptr || p.out != nullptr)
+            return fail(DM_ERR_UNSUPPORTED, "%s: the fused resampling chain needs mel-dB guidance, hop 160, <= %d frames "
+                        "per tile", __func__, 2 * (kWarpsPerCta - 1));
+        DM_SMEM_ONCE((stft_warp_kernel<kModeMelDb, 160, kWarpsPerCta, true>), smem);
+        DM_CARVEOUT_ONCE((stft_warp_kernel<kModeMelDb, 160, kWarpsPerCta, true>));
+        stft_warp_kernel<kModeMelDb, 160, kWarpsPerCta, true><<<grid, 32 * kWarpsPerCta, smem, st>>>(p, (int)total);
+    } else if (mode == DM_STFT_MEL_DB) DM_LAUNCH_WARP_HOP(kModeMelDb);
     else if (mode == DM_STFT_PHASE_MEL) DM_LAUNCH_WARP_HOP(kModePhaseMel);
     else DM_LAUNCH_WARP_HOP(kModePhaseWav);
 #undef DM_LAUNCH_WARP_HOP

@@ -88,8 +88,9 @@ def _grad_buffer(dwav, B, L, device, dtype=torch.float32):
     return dwav
 
 
-def _frames_per_tile(B, T, device):
-    """frames per CTA tile of the STFT guidance kernel.
+def _frames_per_tile(B, T, device, max_nf=16):
+    """frames per CTA tile of the STFT guidance kernel (`max_nf` = 14 for the fused resampling chain, whose last warp
+    owns no frame pair).
 
     The warp-per-frame-pair engine (csrc/stft_warp.cu) gives each of its 8 warps one frame pair, so a tile holds at most
     16 frames; its persistent grid is 2 CTAs per SM.  Cost model: a CTA walks `ceil(ctas / slots)` tiles, a tile costs
@@ -99,13 +100,13 @@ def _frames_per_tile(B, T, device):
     frame-pair kernel of stft_guidance.cu)."""
     forced = os.environ.get("DM_STFT_FRAMES_PER_TILE")
     if forced:
-        return max(6, min(22, int(forced)))
-    key = (B, T, str(device))
+        return max(6, min(22 if max_nf == 16 else max_nf, int(forced)))
+    key = (B, T, str(device), max_nf)
     if key in _NF_CACHE:
         return _NF_CACHE[key]
     slots = 2 * torch.cuda.get_device_properties(device).multi_processor_count
-    best, best_cost = 16, float("inf")
-    for nf in range(8, 17, 2):
+    best, best_cost = max_nf, float("inf")
+    for nf in range(8, max_nf + 1, 2):
         ctas = B * math.ceil(T / nf)
         cost = math.ceil(ctas / slots) * (nf + 3)
         if cost <= best_cost + 1e-9:
@@ -154,7 +155,7 @@ class BaseOperator:
         return float(getattr(n, "sigma", 0.0) or 0.0) if n is not None else 0.0
 
     def _stft(self, mode, y, *, mask=None, ref=None, out_rows=None, want_grad=False, clamp=None, noise=None,
-              sigma=0.0):
+              sigma=0.0, ypbar=None):
         """Launch dm_stft_guidance.  y: (B, Ly) fp32 rows on the GPU.
         transform mode (ref None) -> returns out (B, R, T); guidance mode -> returns (ypbar or None, partial, ntiles)."""
         B, Ly = y.shape
@@ -176,7 +177,10 @@ class BaseOperator:
             raise ValueError(f"measurement transform has shape {tuple(ref.shape)}, prediction needs (1|{B}, {rows}, {T})")
         ref_b = 0 if ref.shape[0] == 1 else ref.stride(0)
         partial = torch.empty((B, ntiles), device=dev, dtype=torch.float32)
-        ypbar = torch.zeros((B, Ly + 1024), device=dev, dtype=torch.float32) if want_grad else None
+        if not want_grad:
+            ypbar = None
+        elif ypbar is None:  # the kernel accumulates into it; a caller-provided buffer has been zeroed on the way
+            ypbar = torch.zeros((B, Ly + 1024), device=dev, dtype=torch.float32)
         _lib.call("dm_stft_guidance_io", tab.ref, mode, int(clamp), _HOP, y.data_ptr(), y_io, y.stride(0), Ly,
                   _lib.ptr(mask), B, ref.data_ptr(), ref_b, _lib.ptr(noise), float(sigma), None, _lib.ptr(ypbar),
                   partial.data_ptr(), nf, _lib.stream())
@@ -270,11 +274,12 @@ class BaseOperator:
                   dwav.data_ptr(), _lib.IO_DTYPES[dtype], dwav.stride(0), loss.data_ptr(), _lib.stream())
         return loss, dwav
 
-    def _space_stage(self, y, measurement, space, want_grad, mask=None):
-        """stage B: residual in `space` on y = A(x).  Returns (ybar, pad, partial, ntiles)."""
+    def _space_stage(self, y, measurement, space, want_grad, mask=None, ypbar=None):
+        """stage B: residual in `space` on y = A(x).  Returns (ybar, pad, partial, ntiles).  `ypbar`: an already
+        zeroed (B, Ly + 1024) cotangent buffer for the mel space (else allocated and zeroed here)."""
         if space == "mel_spectrogram":
             ref = self._ref_mel(measurement).to(y.device)
-            ypbar, partial, nt = self._stft(_MODE_MEL_DB, y, mask=mask, ref=ref, want_grad=want_grad)
+            ypbar, partial, nt = self._stft(_MODE_MEL_DB, y, mask=mask, ref=ref, want_grad=want_grad, ypbar=ypbar)
             return ypbar, 512, partial, nt
         ybar, partial, nt = self._residual_wav(y, measurement.to(y.device), mask=mask)
         return ybar, 0, partial, nt
@@ -469,15 +474,23 @@ class SuperResolutionOperator(BaseOperator):
             cache[str(device)] = self.kernel.to(device).contiguous()
         return cache[str(device)]
 
-    def _resample(self, x):
+    def _resample(self, x, fill=None):
+        """A(x); `fill`: a tensor the same launch zeroes on the way (the cotangent buffer of the chain)."""
         B, L = x.shape
         if self.kernel is None:  # orig == new: torchaudio returns the input unchanged
+            if fill is not None:
+                fill.zero_()
             return x.contiguous().clone()
         Ly = int(math.ceil(self.new * L / self.orig))
         k = self._kernel_on(x.device)
         y = torch.empty((B, Ly), device=x.device, dtype=torch.float32)
-        _lib.call("dm_resample_fwd_io", x.data_ptr(), _lib.IO_DTYPES[x.dtype], x.stride(0), L, B, k.data_ptr(),
-                  k.shape[0], k.shape[1], self.orig, self.width, y.data_ptr(), Ly, _lib.stream())
+        if fill is None:
+            _lib.call("dm_resample_fwd_io", x.data_ptr(), _lib.IO_DTYPES[x.dtype], x.stride(0), L, B, k.data_ptr(),
+                      k.shape[0], k.shape[1], self.orig, self.width, y.data_ptr(), Ly, _lib.stream())
+        else:
+            _lib.call("dm_resample_fwd_fill_io", x.data_ptr(), _lib.IO_DTYPES[x.dtype], x.stride(0), L, B,
+                      k.data_ptr(), k.shape[0], k.shape[1], self.orig, self.width, y.data_ptr(), Ly, fill.data_ptr(),
+                      fill.numel(), _lib.stream())
         return y
 
     def forward(self, data, **kwargs):
@@ -487,13 +500,47 @@ class SuperResolutionOperator(BaseOperator):
         y = self._resample(x)
         return self._finish_forward(y.reshape(*lead, y.shape[-1]), data)
 
+    def _fir2_fusable(self, wav, space):
+        """the shipped chain (scale 2, mel space, no measurement noise inside the step, fp32 rows the kernel can read
+        with 128-bit loads) with the resampled signal computed inside the STFT kernel and never written to HBM.
+        Opt-in (DM_STFT_FUSE_FIR=1): bit-identical, but measured SLOWER on B200 than the separate resampling launch
+        (45.5 us against 33.5 + 9.2 us for 16 x 10 s clips: the window loads of the in-kernel FIR compete with the FFT
+        exchanges for the same L1 / shared-memory pipe)."""
+        return (space == "mel_spectrogram" and self.kernel is not None and (self.orig, self.new) == (2, 1)
+                and tuple(self.kernel.shape) == (1, 28) and self.width == 13 and self._sigma() == 0.0
+                and wav.dtype == torch.float32 and wav.shape[1] > 1024 and wav.data_ptr() % 16 == 0
+                and wav.stride(0) % 4 == 0 and os.environ.get("DM_STFT_FUSE_FIR", "0") == "1")
+
     def _fused(self, wav, measurement, space, want_grad, dwav=None):
         B, L = wav.shape
-        y = self._resample(wav)
-        if self._sigma() != 0.0:
-            y = self._finish_forward(y, y)
-        Ly = y.shape[1]
-        ybar, pad, partial, nt = self._space_stage(y, measurement, space, want_grad)
+        if self._fir2_fusable(wav, space):
+            dev = wav.device
+            Ly = (L + 1) // 2
+            T = 1 + Ly // _HOP
+            nf = _frames_per_tile(B, T, dev, max_nf=14)
+            nt = math.ceil(T / nf)
+            ref = self._ref_mel(measurement).to(dev)
+            if tuple(ref.shape[1:]) != (64, T) or ref.shape[0] not in (1, B):
+                raise ValueError(f"measurement transform has shape {tuple(ref.shape)}, prediction needs (1|{B}, 64, {T})")
+            partial = torch.empty((B, nt), device=dev, dtype=torch.float32)
+            ybar = torch.zeros((B, Ly + 1024), device=dev, dtype=torch.float32) if want_grad else None
+            taps = self.__dict__.get("_taps_host")
+            if taps is None:
+                taps = self.__dict__["_taps_host"] = (C.c_float * 28)(*self.kernel[0].tolist())
+            _lib.call("dm_stft_guidance_fir2", self._tables(dev).ref, int(self.clamp_transform), _HOP, wav.data_ptr(),
+                      wav.stride(0), L, C.addressof(taps), B, ref.data_ptr(),
+                      0 if ref.shape[0] == 1 else ref.stride(0), _lib.ptr(ybar), partial.data_ptr(), nf, _lib.stream())
+            pad = 512
+        else:
+            ypbar = None
+            if space == "mel_spectrogram" and want_grad:  # zeroed by the resampling launch: no fill kernel in the chain
+                Ly = L if self.kernel is None else int(math.ceil(self.new * L / self.orig))
+                ypbar = torch.empty((B, Ly + 1024), device=wav.device, dtype=torch.float32)
+            y = self._resample(wav, fill=ypbar)
+            if self._sigma() != 0.0:
+                y = self._finish_forward(y, y)
+            Ly = y.shape[1]
+            ybar, pad, partial, nt = self._space_stage(y, measurement, space, want_grad, ypbar=ypbar)
         if not want_grad:
             return self._fold_adjoint(None, pad, Ly, B, partial, nt, None, False)
         if self.kernel is None:

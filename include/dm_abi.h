@@ -30,6 +30,13 @@ const char* dm_last_error(void);
 /* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 unsigned long long dm_launch_count(void);
 void dm_reset_launch_count(void);
+/* Process-wide kernel-selection knobs for A/B measurements and tests (results do not depend on them):
+ *   DM_TUNE_STREAM_KERNELS  1 (default): persistent-grid variants of the scale-2 resampling forward / adjoint
+ *                           (16-byte aligned rows, <= 1024 clips); 0: one CTA per 2048 samples. */
+#define DM_TUNE_STREAM_KERNELS 0
+#define DM_TUNE_COUNT 1
+int dm_set_tuning(int knob, int value);
+int dm_get_tuning(int knob);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Scheduler algebra on the latent  (SURVEY.md Appendix B).  n = total elements, n_clip = C*H*W of one clip.
@@ -171,6 +178,19 @@ int dm_stft_guidance(const dm_stft_tables* tab, int mode, int clamp, int hop, co
                      const float* noise, float sigma, float* out, float* ypbar, float* partial, int frames_per_tile,
                      dm_stream_t stream);
 
+/* The mel-space guidance chain of SuperResolutionOperator at scale 2 with the resampling FUSED into the STFT kernel:
+ * the same as dm_resample_fwd (orig 2, new 1, 28 taps, width 13: torchaudio Resample 16 kHz -> 8 kHz, operator.py:180,
+ * 203-205 with run.py:188) followed by dm_stft_guidance(DM_STFT_MEL_DB, guidance mode) on y (B, Ly = ceil(L / 2)), but y
+ * never exists in HBM: every CTA computes its tile's span of y from x (B, L) fp32 (row stride x_bstride, rows 16-byte
+ * aligned) -- the first tile by all warps, the following ones by the warp that owns no frame pair, behind the
+ * transforms of the current tile.  taps: [28] floats in HOST memory (row 0 of the resampling kernel; they travel as
+ * kernel parameters and are read by the FMAs from the constant bank).
+ * frames_per_tile <= 14, hop = 160.  ypbar (B, Ly + 1024) / partial (B, ntiles) as in dm_stft_guidance; the VJP
+ * continues with dm_resample_adjoint.  Bit-identical to the unfused chain. */
+int dm_stft_guidance_fir2(const dm_stft_tables* tab, int clamp, int hop, const float* x, long long x_bstride,
+                          long long L, const float* taps, int B, const float* ref, long long ref_bstride, float* ypbar,
+                          float* partial, int frames_per_tile, dm_stream_t stream);
+
 /* out (B, 64, T) = clamp(mel filterbank applied to a materialised magnitude (B, 513, T), +-80)
  * (PhaseRetrievalOperator.transform, operator.py:153-154: MelScale matmul + clamp, no log). */
 int dm_mel_project(const dm_stft_tables* tab, const float* mag, int B, long long T, int clamp, float* out,
@@ -311,6 +331,12 @@ int dm_fold_adjoint_io(const float* ybar, int pad, long long Ly, int B, const fl
                        int ntiles, void* dwav, int dwav_dtype, long long dwav_bstride, float* loss, dm_stream_t stream);
 int dm_resample_fwd_io(const void* x, int x_dtype, long long x_bstride, long long L, int B, const float* kernel,
                        int n_new, int taps, int orig, int width, float* y, long long Ly, dm_stream_t stream);
+/* dm_resample_fwd_io that also sets fill[0 .. fill_count) = 0 (fill may be NULL): the padded cotangent buffer that the
+ * dm_stft_guidance call of the same chain accumulates into -- folded into the resampling kernel where it is the
+ * persistent scale-2 one (a memset node on the same stream otherwise), so the chain has no fill launch of its own. */
+int dm_resample_fwd_fill_io(const void* x, int x_dtype, long long x_bstride, long long L, int B, const float* kernel,
+                            int n_new, int taps, int orig, int width, float* y, long long Ly, float* fill,
+                            long long fill_count, dm_stream_t stream);
 int dm_resample_adjoint_io(const float* ybar, int pad, long long Ly, int B, const float* partial, int ntiles,
                            const float* kernel, int n_new, int taps, int orig, int width, void* dwav, int dwav_dtype,
                            long long dwav_bstride, long long L, float* loss, dm_stream_t stream);

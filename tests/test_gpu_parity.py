@@ -830,6 +830,65 @@ def test_stft_kernels_agree_for_every_tile_size(op_name, nf, monkeypatch):
     assert rel_l2(t["pair"], t["frame"]) < 1e-6
 
 
+@pytest.mark.parametrize("B,L", [(1, 16000), (3, 16000), (5, 32008), (2, 20016), (16, 160000), (3, 4104)])
+def test_stream_resampling_kernels_are_bit_identical(B, L):
+    """the persistent-grid scale-2 resampling kernels (cp.async-staged swizzled windows forward, contiguous ranges with
+    the scales of the touched clips adjoint, 256-bit stores; dm_set_tuning DM_TUNE_STREAM_KERNELS = 1, the default)
+    against the one-CTA-per-2048-samples kernels: A(x), loss and gradient bit-identical in both supervised spaces, for
+    one clip, clips that straddle CTA ranges, short rows and the BASELINE batch."""
+    from diffmusic_b200 import _lib
+    op = dm.SuperResolutionOperator(16000, scale=2, noiser=_noiser())
+    wav = stubs.synth_clips(B, L).to(DEV)
+    meas = op.forward(stubs.synth_clips(1, L, first=50).to(DEV))
+    res = {}
+    for knob in (1, 0):
+        _lib.call("dm_set_tuning", 0, knob)
+        try:
+            res[knob] = (op.forward(wav),) + tuple(op.fused_loss_and_grad(wav, meas, "mel_spectrogram")) + tuple(
+                op.fused_loss_and_grad(wav, meas, "wav_form"))
+        finally:
+            _lib.call("dm_set_tuning", 0, 1)
+    for a, b in zip(res[1], res[0]):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("nf", [6, 10, 14])
+@pytest.mark.parametrize("B,L", [(3, 16000), (2, 20011), (1, 4099), (2, 160000)])
+def test_fused_resampling_chain_is_bit_identical(B, L, nf, monkeypatch):
+    """dm_stft_guidance_fir2 (the scale-2 sinc resampling computed inside the STFT kernel, its spans never written to
+    HBM; opt-in, DM_STFT_FUSE_FIR=1) against dm_resample_fwd -> dm_stft_guidance with the same tile size: same arithmetic
+    per sample, so loss and gradient are bit-identical; odd lengths, lengths whose last tile is a single frame (L = 16000, nf = 10: its mirrored
+    right edge starts one sample outside the tile's span), and the 10 s clip; and against the oracle."""
+    from diffmusic_b200 import _lib
+    monkeypatch.setenv("DM_STFT_FRAMES_PER_TILE", str(nf))
+    op = dm.SuperResolutionOperator(16000, scale=2, noiser=_noiser())
+    buf = torch.zeros((B, (L + 3) // 4 * 4), device=DEV)  # rows the kernel can read with 128-bit loads (the vocoder
+    wav = buf[:, :L]                                      # output of the pipelines: a [:, :L] slice of aligned rows)
+    wav.copy_(stubs.synth_clips(B, L))
+    meas = op.forward(stubs.synth_clips(1, L, first=50).to(DEV))
+    op._ref_mel(meas)  # cached from here on: the counted launches below are the chain's own
+    res = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("DM_STFT_FUSE_FIR", fuse)
+        n0 = _lib.launch_count()
+        res[fuse] = op.fused_loss_and_grad(wav, meas, "mel_spectrogram")
+        res[fuse + "n"] = _lib.launch_count() - n0
+    assert res["1n"] == 2 and res["0n"] == 3  # the resampling launch is gone
+    if ((L + 1) // 2) % 4 == 0:  # otherwise the unfused chain resamples with the staged polyphase kernel (other rounding)
+        assert torch.equal(res["1"][0], res["0"][0])
+        assert torch.equal(res["1"][1], res["0"][1])
+    else:
+        assert rel_l2(res["1"][0], res["0"][0]) < 1e-6 and rel_l2(res["1"][1], res["0"][1]) < TOL
+    if L <= 20011:
+        oop = oo.OracleOperator("super_resolution", scale=2)
+        for i in range(B):
+            w = wav[i:i + 1].cpu().clone().requires_grad_(True)
+            want = torch.linalg.norm(oop.transform(meas.cpu()) - oop.transform(oop.forward(w)))
+            (gw,) = torch.autograd.grad(want, w)
+            assert abs(float(res["1"][0][i]) - float(want)) < TOL * float(want)
+            assert rel_l2(res["1"][1][i:i + 1], gw) < TOL
+
+
 # ------------------------------------------------------------------------------------------------ update kernels, all paths
 @pytest.mark.parametrize("n_clip", [3200, 32000, 38400, 3203])
 @pytest.mark.parametrize("kind", ["dsg", "diffmusic"])
