@@ -110,6 +110,7 @@ _SIGNATURES = {
 }
 
 EXPORTS = tuple(_SIGNATURES)
+TUNING_ENV = ("DM_TUNE_STREAM_KERNELS", "DM_TUNE_PDL")  # index = knob number
 _lib = None
 
 
@@ -130,6 +131,9 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        for knob, env in enumerate(TUNING_ENV):  # process-wide kernel-selection knobs (include/dm_abi.h DM_TUNE_*)
+            if os.environ.get(env) is not None:
+                lib.dm_set_tuning(knob, int(os.environ[env]))
         _lib = lib
     return _lib
 

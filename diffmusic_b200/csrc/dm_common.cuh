@@ -63,6 +63,27 @@ inline int fail(int code, const char* fmt, A... a) {
         }                                                                                                  \
     } while (0)
 
+// Launch with the programmatic-stream-serialization attribute (when `pdl`): the kernel may be scheduled while the
+// previous kernel of the stream is still running (after all its CTAs have executed griddepcontrol.launch_dependents, or
+// have exited); everything it reads from / writes in common with that kernel comes after its own griddepcontrol.wait
+// (pdl_wait()), which returns once the previous kernel has completed and flushed.  Both instructions are no-ops in a
+// kernel launched without the attribute / without a dependent.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline bool io_dtype_ok(int io) { return io == DM_IO_F32 || io == DM_IO_F16 || io == DM_IO_BF16; }
 inline cudaStream_t as_stream(dm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -101,6 +122,8 @@ __device__ __forceinline__ const void* wave_row(const void* p, int io, long long
 __device__ __forceinline__ void* wave_row(void* p, int io, long long elems) {
     return static_cast<char*>(p) + elems * (io == DM_IO_F32 ? 4 : 2);
 }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

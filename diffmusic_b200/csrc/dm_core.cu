@@ -6,7 +6,7 @@
 namespace dm {
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-int g_tuning[DM_TUNE_COUNT] = {1};
+int g_tuning[DM_TUNE_COUNT] = {1, 1};
 }  // namespace dm
 
 extern "C" int dm_set_tuning(int knob, int value) {

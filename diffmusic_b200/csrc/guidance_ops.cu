@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kEwThreads) fold_adjoint_kernel(const float* _
                                                                   float* __restrict__ loss) {
     __shared__ float scratch[2];
     const int b = blockIdx.y;
+    pdl_wait();  // cotangent and partial sums of the previous kernel of the chain
     const float* yb = ybar + (long long)b * (Ly + 2 * pad);
     void* ob = wave_row(dwav, dwav_io, (long long)b * dwav_bstride);
     const long long lo = (long long)blockIdx.x * (kEwThreads * 8);
@@ -546,9 +547,10 @@ __global__ void __launch_bounds__(kEwThreads) resample2_adjoint_stream_kernel(
     const int b_lo = start / nwin_clip, b_hi = (end - 1) / nwin_clip;
     int item = start + threadIdx.x;
     Rs2AdjWin w0, w1;
-    if (item < end) rs2_adj_load<IO>(w0, item, nwin_clip, ybar, pad, Ly);  // in flight behind the scale reduction
     float h[kFir2Taps];
     load_taps28(kernel, h);
+    pdl_wait();  // cotangent and partial sums of the STFT kernel from here on
+    if (item < end) rs2_adj_load<IO>(w0, item, nwin_clip, ybar, pad, Ly);  // in flight behind the scale reduction
     clip_scales_smem(partial, ntiles, b_lo, b_hi, (start + nwin_clip - 1) / nwin_clip, loss, s_scale);
     for (; item < end; item += 2 * kEwThreads) {
         const int item1 = item + kEwThreads;
@@ -574,6 +576,10 @@ __device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, i
                  "r"(src_bytes)
                  : "memory");
 }
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
 __global__ void __launch_bounds__(kRs2Threads) resample2_fwd_stream_kernel(const float* __restrict__ x,
                                                                            long long x_bstride, long long L, int B,
                                                                            const float* __restrict__ kernel,
@@ -582,32 +588,55 @@ __global__ void __launch_bounds__(kRs2Threads) resample2_fwd_stream_kernel(const
                                                                            long long fill_n4) {
     __shared__ __align__(16) float buf[2][kRs2BufFloats];
     const int t = threadIdx.x;
+    pdl_trigger();  // the STFT kernel of the chain may stage its tables while this one runs
     // optional: zero a side buffer on the way (the cotangent buffer the STFT kernel accumulates into next: saves the
     // fill launch of the chain).  Stores only, issued before anything else.
     for (long long i = (long long)blockIdx.x * kRs2Threads + t; i < fill_n4; i += (long long)gridDim.x * kRs2Threads)
         fill[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int chunks_clip = (int)((Ly + kRs2ChunkOut - 1) / kRs2ChunkOut);
-    const long long total = (long long)chunks_clip * B;
-    auto stage = [&](long long item, float* dst) {
-        const int b = (int)(item / chunks_clip);
-        const long long j0c = (item - (long long)b * chunks_clip) * kRs2ChunkOut;
+    const int total = chunks_clip * B;  // the host keeps it below 2^31
+    // chunk-independent addressing, computed once: where this thread's staged cells go, where its window cells are
+    constexpr int kStageIt = (kRs2Cells + kRs2Threads - 1) / kRs2Threads;  // 5, the last one for 8 threads only
+    int stage_off[kStageIt];
+#pragma unroll
+    for (int k = 0; k < kStageIt; ++k) stage_off[k] = 4 * rs2_cell(t + k * kRs2Threads);
+    // window cells 4 t + q, q = 0..11 = cells 4 u .. 4 u + 3 of u = t, t + 1, t + 2: rs2_cell(4 u + j) = 4 u + (j ^ ((u >> 1) & 3))
+    int win_base[3], win_x[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        win_base[g] = 4 * (t + g);
+        win_x[g] = ((t + g) >> 1) & 3;
+    }
+    auto stage = [&](int item, float* dst) {
+        const int b = item / chunks_clip;
+        const long long j0c = (long long)(item - b * chunks_clip) * kRs2ChunkOut;
         const float* xb = x + (long long)b * x_bstride;
         const long long x0 = 2 * j0c - 16;  // a multiple of 4 floats
-        for (int c = t; c < kRs2Cells; c += kRs2Threads) {
-            const long long g = x0 + 4 * c;
-            int nbytes = 0;
-            if (g >= 0 && g < L) nbytes = (int)min((long long)16, (L - g) * 4);
-            cp_async16_zfill(dst + 4 * rs2_cell(c), nbytes ? xb + g : xb, nbytes);  // zero-fills what lies outside [0, L)
+        if (x0 >= 0 && x0 + 4 * kRs2Cells <= L) {  // interior chunk (uniform): plain 16-byte copies
+            const float* src = xb + x0 + 4 * t;
+#pragma unroll
+            for (int k = 0; k < kStageIt; ++k)
+                if (k + 1 < kStageIt || t + k * kRs2Threads < kRs2Cells) cp_async16(dst + stage_off[k], src + 4 * k * kRs2Threads);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kStageIt; ++k) {
+                const int c = t + k * kRs2Threads;
+                if (c >= kRs2Cells) break;
+                const long long g = x0 + 4 * c;
+                int nbytes = 0;
+                if (g >= 0 && g < L) nbytes = (int)min((long long)16, (L - g) * 4);
+                cp_async16_zfill(dst + stage_off[k], nbytes ? xb + g : xb, nbytes);  // zero-fills outside [0, L)
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     float h[kFir2Taps];
     load_taps28(kernel, h);
-    long long item = blockIdx.x;
+    int item = blockIdx.x;
     if (item < total) stage(item, buf[0]);
     int cur = 0;
     for (; item < total; item += gridDim.x, cur ^= 1) {
-        const long long next = item + gridDim.x;
+        const int next = item + gridDim.x;
         if (next < total) {
             stage(next, buf[cur ^ 1]);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -615,14 +644,14 @@ __global__ void __launch_bounds__(kRs2Threads) resample2_fwd_stream_kernel(const
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const int b = (int)(item / chunks_clip);
-        const long long j0 = (item - (long long)b * chunks_clip) * kRs2ChunkOut + (long long)t * kFir2Out;
+        const int b = item / chunks_clip;
+        const long long j0 = (long long)(item - b * chunks_clip) * kRs2ChunkOut + t * kFir2Out;
         if (j0 < Ly) {
             float win[kFir2FwdWin], out[kFir2Out];
             const float4* cells = reinterpret_cast<const float4*>(buf[cur]);
 #pragma unroll
             for (int q = 0; q < kFir2FwdWin / 4; ++q) {
-                const float4 v = cells[rs2_cell(4 * t + q)];
+                const float4 v = cells[win_base[q >> 2] + ((q & 3) ^ win_x[q >> 2])];
                 win[4 * q] = v.x, win[4 * q + 1] = v.y, win[4 * q + 2] = v.z, win[4 * q + 3] = v.w;
             }
             fir2_fwd8(win, h, out);
@@ -738,8 +767,8 @@ extern "C" int dm_fold_adjoint_io(const float* ybar, int pad, long long Ly, int 
     DM_REQUIRE((dwav == nullptr && loss != nullptr) || ybar != nullptr);
     DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 512));
     const int nblk = dwav ? (int)((Ly + kEwThreads * 8 - 1) / (kEwThreads * 8)) : 1;
-    fold_adjoint_kernel<<<dim3(nblk, B), kEwThreads, 0, as_stream(stream)>>>(ybar, pad, Ly, mask, partial, ntiles,
-                                                                             dwav, dwav_dtype, dwav_bstride, loss);
+    launch_pdl(fold_adjoint_kernel, dim3(nblk, B), dim3(kEwThreads), 0, as_stream(stream), g_tuning[DM_TUNE_PDL] != 0,
+               ybar, pad, Ly, mask, partial, ntiles, dwav, dwav_dtype, dwav_bstride, loss);
     DM_LAUNCHED();
     return DM_OK;
 }
@@ -772,8 +801,8 @@ static void launch_rs2_adj(const float* ybar, int pad, long long Ly, int B, cons
         long long per_cta = (nwin + (long long)num_sms() * 4 - 1) / ((long long)num_sms() * 4);
         per_cta = std::max<long long>(2, (per_cta + kEwThreads - 1) / kEwThreads) * kEwThreads;
         const int grid = (int)((nwin + per_cta - 1) / per_cta);
-        resample2_adjoint_stream_kernel<IO><<<grid, kEwThreads, 0, st>>>(ybar, pad, Ly, B, partial, ntiles, kernel, dwav,
-                                                                         dwav_bstride, L, loss);
+        launch_pdl(resample2_adjoint_stream_kernel<IO>, dim3(grid), dim3(kEwThreads), 0, st, g_tuning[DM_TUNE_PDL] != 0,
+                   ybar, pad, Ly, B, partial, ntiles, kernel, dwav, dwav_bstride, L, loss);
         return;
     }
     const long long nthr = (L + kFir2Out - 1) / kFir2Out;

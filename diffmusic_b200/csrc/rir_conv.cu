@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(kRirThreads, 2) rir_correlate_kernel(const voi
     extern __shared__ __align__(16) float smem[];
     RirSmem s = carve(smem);
     const int b = blockIdx.y;
+    pdl_trigger();  // the STFT kernel of the chain may stage its tables while this one runs
     const long long i0 = (long long)blockIdx.x * g.valid;
     SrcPlain src{wave_row(x, x_io, (long long)b * x_bstride), x_io, i0 - g.pad, g.L};
     RirStore st{y + (long long)b * g.nout + i0, 0, (int)min((long long)g.valid, g.nout - i0), 1.0f / kRirN};
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kRirThreads, 2) rir_adjoint_kernel(const float
     __shared__ float scratch[2];
     RirSmem s = carve(smem);
     const int b = blockIdx.y;
+    pdl_wait();  // cotangent and partial sums of the STFT kernel
     const float l = clip_loss(partial + (long long)b * ntiles, ntiles, scratch);
     if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[b] = l;
     const long long j0 = (long long)blockIdx.x * g.valid;
@@ -158,9 +160,10 @@ extern "C" int dm_rir_adjoint_io(const float* ybar, int pad, long long Ly, int B
     DM_REQUIRE(pad == 0 || (pad == 512 && Ly > 512));
     const int nblk = (int)((L + g.valid - 1) / g.valid);
     DM_SMEM_ONCE(rir_adjoint_kernel, kRirSmemBytes);
-    rir_adjoint_kernel<<<dim3(nblk, B), kRirThreads, kRirSmemBytes, as_stream(stream)>>>(
-        ybar, pad, g, partial, ntiles, reinterpret_cast<const cf*>(spec), reinterpret_cast<const cf*>(tw4096),
-        reinterpret_cast<const cf*>(w8192), dwav, dwav_dtype, dwav_bstride, loss);
+    launch_pdl(rir_adjoint_kernel, dim3(nblk, B), dim3(kRirThreads), kRirSmemBytes, as_stream(stream),
+               g_tuning[DM_TUNE_PDL] != 0, ybar, pad, g, partial, ntiles, reinterpret_cast<const cf*>(spec),
+               reinterpret_cast<const cf*>(tw4096), reinterpret_cast<const cf*>(w8192), dwav, dwav_dtype, dwav_bstride,
+               loss);
     DM_LAUNCHED();
     return DM_OK;
 }

@@ -208,14 +208,16 @@ __global__ void __launch_bounds__(32 * WARPS, 2) stft_warp_kernel(const StftPara
 
     // ---- prologue: the table image and the first tile's signal are fetched concurrently ----
     TileGeom g = tile_geom(p, blockIdx.x, hop);
+    pdl_trigger();  // the adjoint kernel of the chain may be scheduled as soon as CTAs of this one retire
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&bar_sig)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&bar_img)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        bulk_load_span(img, p.tab.warp_image, (uint32_t)p.tab.warp_image_floats * 4u, &bar_img);
-        if (g.interior) stage_async(g, sig, &bar_sig);
+        bulk_load_span(img, p.tab.warp_image, (uint32_t)p.tab.warp_image_floats * 4u, &bar_img);  // constant tables
     }
+    pdl_wait();  // the signal (and the zeroed cotangent buffer) of the previous kernel from here on
+    if (tid == 0 && g.interior) stage_async(g, sig, &bar_sig);
     if (FIR) {
         const Fir2Span f = fir2_span(p, g);
         fir2_windows(p, f, sig, tid, f.nwin, kWarpCtaThreads);
@@ -476,7 +478,8 @@ int launch_stft_warp(const StftParams& p, int mode, cudaStream_t st) {
     do {                                                                                          \
         DM_SMEM_ONCE((stft_warp_kernel<M, H, W, false>), smem);                                   \
         DM_CARVEOUT_ONCE((stft_warp_kernel<M, H, W, false>));                                     \
-        stft_warp_kernel<M, H, W, false><<<grid, 32 * W, smem, st>>>(p, (int)total);              \
+        launch_pdl(stft_warp_kernel<M, H, W, false>, dim3(grid), dim3(32 * W), smem, st,          \
+                   g_tuning[DM_TUNE_PDL] != 0, p, (int)total);                                    \
     } while (0)
 #define DM_LAUNCH_WARP_HOP(M)                                        \
     do {                                                             \
@@ -490,7 +493,8 @@ int launch_stft_warp(const StftParams& p, int mode, cudaStream_t st) {
                         "per tile", __func__, 2 * (kWarpsPerCta - 1));
         DM_SMEM_ONCE((stft_warp_kernel<kModeMelDb, 160, kWarpsPerCta, true>), smem);
         DM_CARVEOUT_ONCE((stft_warp_kernel<kModeMelDb, 160, kWarpsPerCta, true>));
-        stft_warp_kernel<kModeMelDb, 160, kWarpsPerCta, true><<<grid, 32 * kWarpsPerCta, smem, st>>>(p, (int)total);
+        launch_pdl(stft_warp_kernel<kModeMelDb, 160, kWarpsPerCta, true>, dim3(grid), dim3(32 * kWarpsPerCta), smem, st,
+                   g_tuning[DM_TUNE_PDL] != 0, p, (int)total);
     } else if (mode == DM_STFT_MEL_DB) DM_LAUNCH_WARP_HOP(kModeMelDb);
     else if (mode == DM_STFT_PHASE_MEL) DM_LAUNCH_WARP_HOP(kModePhaseMel);
     else DM_LAUNCH_WARP_HOP(kModePhaseWav);

@@ -34,7 +34,12 @@ void dm_reset_launch_count(void);
  *   DM_TUNE_STREAM_KERNELS  1 (default): persistent-grid variants of the scale-2 resampling forward / adjoint
  *                           (16-byte aligned rows, <= 1024 clips); 0: one CTA per 2048 samples. */
 #define DM_TUNE_STREAM_KERNELS 0
-#define DM_TUNE_COUNT 1
+/*   DM_TUNE_PDL             1: the kernels of a fused guidance chain (A(x) -> STFT guidance -> adjoint) are launched with
+ *                           programmatic stream serialization: the next kernel's launch and prologue (table staging,
+ *                           filter taps) overlap the tail of the previous one, its first dependent access waits
+ *                           (griddepcontrol.wait); 0: plain stream order. */
+#define DM_TUNE_PDL 1
+#define DM_TUNE_COUNT 2
 int dm_set_tuning(int knob, int value);
 int dm_get_tuning(int knob);
 

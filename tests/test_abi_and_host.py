@@ -212,6 +212,29 @@ def test_warp_kernel_table_image():
             assert np.allclose(tw[m, :, 2], np.cos(ang), atol=1e-7) and np.allclose(tw[m, :, 3], np.sin(ang), atol=1e-7)
 
 
+def test_tuning_knobs_and_fused_resampling_switch(lib, monkeypatch):
+    """dm_set_tuning / dm_get_tuning (host state, no GPU): defaults, round trip, range check; the environment names
+    _lib.load() applies; and the opt-in rule of the in-kernel resampling chain (SuperResolutionOperator._fir2_fusable)."""
+    import torch
+    from diffmusic_b200 import _lib
+    import diffmusic_b200 as dm
+    assert len(_lib.TUNING_ENV) == 2  # one environment name per DM_TUNE_* knob of include/dm_abi.h
+    assert lib.dm_get_tuning(0) == 1 and lib.dm_get_tuning(1) == 1  # persistent kernels and dependent launches on
+    assert lib.dm_set_tuning(0, 0) == 0 and lib.dm_get_tuning(0) == 0
+    assert lib.dm_set_tuning(0, 1) == 0 and lib.dm_get_tuning(0) == 1
+    assert lib.dm_set_tuning(7, 1) != 0 and lib.dm_get_tuning(7) < 0
+    op = dm.SuperResolutionOperator(16000, scale=2, noiser=dm.get_noiser("gaussian", 0.0))
+    wav = torch.zeros(2, 16000)
+    monkeypatch.delenv("DM_STFT_FUSE_FIR", raising=False)
+    assert not op._fir2_fusable(wav, "mel_spectrogram")  # measured slower than the separate launch: opt-in only
+    monkeypatch.setenv("DM_STFT_FUSE_FIR", "1")
+    assert op._fir2_fusable(wav, "mel_spectrogram")
+    assert not op._fir2_fusable(wav, "wav_form")
+    assert not op._fir2_fusable(wav.half(), "mel_spectrogram")
+    assert not op._fir2_fusable(torch.zeros(2, 16001)[:, :16000], "mel_spectrogram")  # rows not 16-byte aligned
+    assert not dm.SuperResolutionOperator(16000, scale=10, noiser=None)._fir2_fusable(wav, "mel_spectrogram")
+
+
 def test_bench_hooks_the_entry_point_the_operators_call():
     """bench.py times the dominant kernel by wrapping _lib.call for the STFT guidance entry point: the name it matches
     must be the one diffmusic_b200/operators.py actually calls (a silent mismatch leaves roofline.achieved null)."""

@@ -21,7 +21,7 @@ from diffmusic_b200 import _lib  # noqa: E402
 from tests import stubs  # noqa: E402
 
 L = 160000
-TUNE_STREAM = 0
+TUNE_STREAM, TUNE_PDL = 0, 1
 
 
 def main():
@@ -94,6 +94,23 @@ def main():
         res["bit_identical"] = all(torch.equal(p, q) for p, q in zip(v0, v1))
         out["stream_kernels"][name] = res
 
+    # programmatic dependent launch along the chains (knob 1)
+    der = dm.MusicDereverberationOperator(ir_length=5000, decay_factor=0.99, noiser=nz)
+    torch.manual_seed(0)
+    chains["dereverberation.loss+vjp[mel]"] = lambda m=der.forward(ref_wav): der.fused_loss_and_grad(wav, m, "mel_spectrogram")
+    out["pdl"] = {}
+    for name in ("super_resolution.loss+vjp[mel]", "inpainting.loss+vjp[mel]", "dereverberation.loss+vjp[mel]"):
+        res = {}
+        for knob in (0, 1):
+            _lib.call("dm_set_tuning", TUNE_PDL, knob)
+            torch.manual_seed(1)
+            row, val = run(chains[name])
+            res[str(knob)] = row
+            res[f"val{knob}"] = val
+        _lib.call("dm_set_tuning", TUNE_PDL, 0)
+        v0, v1 = res.pop("val0"), res.pop("val1")
+        res["bit_identical"] = all(torch.equal(p, q) for p, q in zip(v0, v1))
+        out["pdl"][name] = res
     print(json.dumps(out, indent=1))
 
 
