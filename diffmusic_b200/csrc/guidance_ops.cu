@@ -796,7 +796,10 @@ static void launch_rs2_adj(const float* ybar, int pad, long long Ly, int B, cons
                            const float* kernel, void* dwav, long long dwav_bstride, long long L, float* loss,
                            cudaStream_t st) {
     const long long nwin = ((L + kFir2Out - 1) / kFir2Out) * B;
-    if (g_tuning[DM_TUNE_STREAM_KERNELS] && B <= kStreamMaxClips && nwin < (1LL << 30)) {
+    // The persistent kernel wins once the work exceeds about two resident waves of the plain one (measured under ncu,
+    // 10 s clips: 128 clips 33 us against 46 us; 16 clips 11.9 us against 10.5 us) -- below that the plain kernel stays.
+    if (g_tuning[DM_TUNE_STREAM_KERNELS] && B <= kStreamMaxClips && nwin < (1LL << 30) &&
+        (nwin > (long long)num_sms() * 4096 || g_tuning[DM_TUNE_STREAM_KERNELS] == 2)) {
         // one resident wave (4 CTAs of 64 registers per SM), every CTA a whole number of 256-window rounds
         long long per_cta = (nwin + (long long)num_sms() * 4 - 1) / ((long long)num_sms() * 4);
         per_cta = std::max<long long>(2, (per_cta + kEwThreads - 1) / kEwThreads) * kEwThreads;

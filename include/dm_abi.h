@@ -31,8 +31,9 @@ const char* dm_last_error(void);
 unsigned long long dm_launch_count(void);
 void dm_reset_launch_count(void);
 /* Process-wide kernel-selection knobs for A/B measurements and tests (results do not depend on them):
- *   DM_TUNE_STREAM_KERNELS  1 (default): persistent-grid variants of the scale-2 resampling forward / adjoint
- *                           (16-byte aligned rows, <= 1024 clips); 0: one CTA per 2048 samples. */
+ *   DM_TUNE_STREAM_KERNELS  1 (default): persistent-grid variants of the scale-2 resampling forward (always) and adjoint
+ *                           (from about 32 ten-second clips per launch; below that the plain kernel is faster);
+ *                           16-byte aligned rows, <= 1024 clips.  2: both always.  0: one CTA per 2048 samples. */
 #define DM_TUNE_STREAM_KERNELS 0
 /*   DM_TUNE_PDL             1: the kernels of a fused guidance chain (A(x) -> STFT guidance -> adjoint) are launched with
  *                           programmatic stream serialization: the next kernel's launch and prologue (table staging,

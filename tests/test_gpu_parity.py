@@ -841,15 +841,16 @@ def test_stream_resampling_kernels_are_bit_identical(B, L):
     wav = stubs.synth_clips(B, L).to(DEV)
     meas = op.forward(stubs.synth_clips(1, L, first=50).to(DEV))
     res = {}
-    for knob in (1, 0):
+    for knob in (2, 1, 0):  # 2: persistent kernels whatever the batch; 1: the default choice; 0: plain kernels
         _lib.call("dm_set_tuning", 0, knob)
         try:
             res[knob] = (op.forward(wav),) + tuple(op.fused_loss_and_grad(wav, meas, "mel_spectrogram")) + tuple(
                 op.fused_loss_and_grad(wav, meas, "wav_form"))
         finally:
             _lib.call("dm_set_tuning", 0, 1)
-    for a, b in zip(res[1], res[0]):
-        assert torch.equal(a, b)
+    for knob in (2, 1):
+        for a, b in zip(res[knob], res[0]):
+            assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("nf", [6, 10, 14])
