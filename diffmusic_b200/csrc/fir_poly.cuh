@@ -144,6 +144,20 @@ DM_HD void fir2_adj8(const float (&win)[kFir2AdjWin], const float (&h)[kFir2Taps
     }
 }
 
+// ---- persistent forward kernel (resample2_fwd_stream_kernel): chunk geometry and shared-memory cell maps.
+// A chunk = 1024 outputs = 8 per thread of a 128-thread CTA; its input span x[2 j0 - 16 .. 2 j0 + 2064) is staged as 520
+// cells of 4 floats; logical cell c sits at rs2_cell(c) (its position inside the 128-byte row of 8 cells xor-ed with
+// row & 3), which makes both the coalesced staging writes (8 consecutive cells per quarter-warp) and the window reads
+// (thread t reads cells 4 t .. 4 t + 11: lane stride 64 B) bank-conflict free (audited on the host).
+constexpr int kRs2ChunkOut = 1024;
+constexpr int kRs2Threads = kRs2ChunkOut / kFir2Out;      // 128
+constexpr int kRs2Cells = (2 * kRs2ChunkOut + 32) / 4;    // 520
+constexpr int kRs2BufFloats = ((kRs2Cells + 7) / 8) * 8 * 4;
+DM_HDC int rs2_cell(int c) { return (c & ~7) | ((c & 7) ^ ((c >> 3) & 3)); }
+// physical cell of window cell q (0..11) of thread t = rs2_cell(4 t + q), in the cheap form the kernel evaluates:
+// cells 4 u .. 4 u + 3 of u = t + q / 4 share a half row, so only the low two bits are permuted
+DM_HDC int rs2_win_cell(int t, int q) { return 4 * (t + (q >> 2)) + ((q & 3) ^ (((t + (q >> 2)) >> 1) & 3)); }
+
 // signed ceil-division (orig > 0)
 DM_HD long long ceil_div_ll(long long a, long long b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
 

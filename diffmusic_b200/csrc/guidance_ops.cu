@@ -566,11 +566,7 @@ __global__ void __launch_bounds__(kEwThreads) resample2_adjoint_stream_kernel(
 // conflict-free: 16-byte cell c sits at (c & ~7) | ((c & 7) ^ ((c >> 3) & 3)).  [Per quarter-warp the cells 4 i + q of 8
 // consecutive lanes fall into two columns a, a ^ 4 of four consecutive 128-byte rows each; xor-ing the column with
 // row & 3 spreads each set over a ^ {0..3} resp. a ^ 4 ^ {0..3}: eight different bank groups.]
-constexpr int kRs2ChunkOut = 1024;                     // outputs per chunk = 8 per thread of a 128-thread CTA
-constexpr int kRs2Threads = kRs2ChunkOut / kFir2Out;   // 128
-constexpr int kRs2Cells = (2 * kRs2ChunkOut + 32) / 4 + 0;  // 520 cells of 4 floats: x[2 j0 - 16 .. 2 j0 + 2048 + 16)
-constexpr int kRs2BufFloats = ((kRs2Cells + 7) / 8) * 8 * 4;
-__device__ __forceinline__ int rs2_cell(int c) { return (c & ~7) | ((c & 7) ^ ((c >> 3) & 3)); }
+// (chunk geometry and the cell maps rs2_cell / rs2_win_cell: fir_poly.cuh, shared with the host emulation)
 __device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
                  "r"(src_bytes)
@@ -600,13 +596,7 @@ __global__ void __launch_bounds__(kRs2Threads) resample2_fwd_stream_kernel(const
     int stage_off[kStageIt];
 #pragma unroll
     for (int k = 0; k < kStageIt; ++k) stage_off[k] = 4 * rs2_cell(t + k * kRs2Threads);
-    // window cells 4 t + q, q = 0..11 = cells 4 u .. 4 u + 3 of u = t, t + 1, t + 2: rs2_cell(4 u + j) = 4 u + (j ^ ((u >> 1) & 3))
-    int win_base[3], win_x[3];
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-        win_base[g] = 4 * (t + g);
-        win_x[g] = ((t + g) >> 1) & 3;
-    }
+
     auto stage = [&](int item, float* dst) {
         const int b = item / chunks_clip;
         const long long j0c = (long long)(item - b * chunks_clip) * kRs2ChunkOut;
@@ -651,7 +641,7 @@ __global__ void __launch_bounds__(kRs2Threads) resample2_fwd_stream_kernel(const
             const float4* cells = reinterpret_cast<const float4*>(buf[cur]);
 #pragma unroll
             for (int q = 0; q < kFir2FwdWin / 4; ++q) {
-                const float4 v = cells[win_base[q >> 2] + ((q & 3) ^ win_x[q >> 2])];
+                const float4 v = cells[rs2_win_cell(t, q)];
                 win[4 * q] = v.x, win[4 * q + 1] = v.y, win[4 * q + 2] = v.z, win[4 * q + 3] = v.w;
             }
             fir2_fwd8(win, h, out);

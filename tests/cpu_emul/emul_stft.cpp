@@ -711,6 +711,56 @@ void emul_resample2_adjoint(const float* ybar, long long Ly, const float* kernel
 }
 }
 
+// persistent forward kernel: stage a chunk's input span cell by cell into the swizzled buffer, then every thread reads
+// its window through rs2_win_cell -- the data path of resample2_fwd_stream_kernel (guidance_ops.cu)
+extern "C" {
+void emul_resample2_fwd_stream(const float* x, long long L, const float* kernel, float* y, long long Ly) {
+    float h[kFir2Taps];
+    for (int k = 0; k < kFir2Taps; ++k) h[k] = kernel[k];
+    std::vector<float> buf(kRs2BufFloats);
+    const long long chunks = (Ly + kRs2ChunkOut - 1) / kRs2ChunkOut;
+    for (long long ch = 0; ch < chunks; ++ch) {
+        const long long j0c = ch * kRs2ChunkOut, x0 = 2 * j0c - 16;
+        std::fill(buf.begin(), buf.end(), -1e30f);  // poison: every cell a window reads must have been staged
+        for (int c = 0; c < kRs2Cells; ++c)
+            for (int e = 0; e < 4; ++e) {
+                const long long g = x0 + 4 * c + e;
+                buf[4 * rs2_cell(c) + e] = (g >= 0 && g < L) ? x[g] : 0.f;
+            }
+        for (int t = 0; t < kRs2Threads; ++t) {
+            const long long j0 = j0c + (long long)t * kFir2Out;
+            if (j0 >= Ly) continue;
+            float win[kFir2FwdWin], out[kFir2Out];
+            for (int q = 0; q < kFir2FwdWin / 4; ++q)
+                for (int e = 0; e < 4; ++e) win[4 * q + e] = buf[4 * rs2_win_cell(t, q) + e];
+            fir2_fwd8(win, h, out);
+            for (int c = 0; c < kFir2Out; ++c)
+                if (j0 + c < Ly) y[j0 + c] = out[c];
+        }
+    }
+}
+// bank-conflict audit: per quarter-warp (8 lanes) the 16-byte cells of one 128-bit access must fall into 8 different
+// bank groups (cell index mod 8).  Returns the number of conflicting accesses.
+int emul_rs2_audit() {
+    int bad = 0;
+    for (int c = 0; c < kRs2Cells; ++c) bad += rs2_cell(c) < 0 || rs2_cell(c) >= kRs2BufFloats / 4;
+    for (int t = 0; t < kRs2Threads; ++t)
+        for (int q = 0; q < 12; ++q) bad += rs2_win_cell(t, q) != rs2_cell(4 * t + q);
+    for (int c0 = 0; c0 + 8 <= kRs2Cells + 7; c0 += 8) {  // staging: 8 consecutive cells per quarter-warp
+        int seen = 0;
+        for (int i = 0; i < 8; ++i) seen |= 1 << (rs2_cell(c0 + i) & 7);
+        bad += seen != 0xff;
+    }
+    for (int t0 = 0; t0 < kRs2Threads; t0 += 8)  // window reads: lanes t0 .. t0 + 7, cell q each
+        for (int q = 0; q < 12; ++q) {
+            int seen = 0;
+            for (int i = 0; i < 8; ++i) seen |= 1 << (rs2_win_cell(t0 + i, q) & 7);
+            bad += seen != 0xff;
+        }
+    return bad;
+}
+}
+
 // exhaustive check of the closed-form swizzled addresses (fft_core.cuh) against swz() of the logical index
 extern "C" int emul_check_swizzle_forms() {
     int bad = 0;

@@ -325,6 +325,27 @@ def test_register_window_scale2_resample(emul, L):
     assert rel_l2(gotb, 0.25 * gx[0]) < 2e-6
 
 
+@pytest.mark.parametrize("L", [16000, 4099, 2049, 57])
+def test_persistent_scale2_forward_data_path(emul, L):
+    """resample2_fwd_stream_kernel's data path on the host: the chunk's span staged cell by cell into the swizzled buffer
+    (poisoned first), windows read back through rs2_win_cell, fir2_fwd8 -- bit-identical to the direct register-window
+    path and equal to torchaudio; and the bank-conflict audit of both access patterns."""
+    import torchaudio
+    kern, width, orig, new = tables.sinc_resample_kernel(16000, 8000)
+    g = torch.Generator().manual_seed(L + 1)
+    x = torch.randn(1, L, generator=g)
+    y = torchaudio.transforms.Resample(16000, 8000)(x)
+    Ly = y.shape[1]
+    k = kern[0].numpy().copy()
+    xn = x[0].numpy().copy()
+    got, direct = np.zeros(Ly, np.float32), np.zeros(Ly, np.float32)
+    emul.emul_resample2_fwd_stream(_ptr(xn), C.c_longlong(L), _ptr(k), _ptr(got), C.c_longlong(Ly))
+    emul.emul_resample2_fwd(_ptr(xn), C.c_longlong(L), _ptr(k), _ptr(direct), C.c_longlong(Ly))
+    assert np.array_equal(got, direct)
+    assert rel_l2(got, y[0]) < 2e-6
+    assert emul.emul_rs2_audit() == 0
+
+
 @pytest.mark.parametrize("hop,pad", [(160, "constant"), (512, "constant"), (512, "reflect")])
 def test_lsd_frames_through_the_pair_pipeline(emul, hop, pad):
     """LogSpectralDistance per-frame distances through the frame-pair device code (reference clip = frame A, estimate =
